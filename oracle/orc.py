@@ -1,0 +1,345 @@
+"""TEST INFRASTRUCTURE — ctypes view of the CPU oracle (oracle/build/liborc.so).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+Poses are numpy float64[7]: t.x t.y t.z q.w q.x q.y q.z.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+
+
+class SolveSummary(C.Structure):
+    _fields_ = [("initial_cost", C.c_double), ("final_cost", C.c_double), ("num_iterations", C.c_int),
+                ("num_successful_steps", C.c_int), ("num_unsuccessful_steps", C.c_int), ("termination", C.c_int),
+                ("num_residual_evaluations", C.c_int), ("num_jacobian_evaluations", C.c_int)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class FrontEndOptions(C.Structure):
+    """Field-for-field the parameters LocalTrajectoryBuilder3D reads on the hot path; defaults =
+    configuration_files/trajectory_builder_3d.lua."""
+    _fields_ = [("min_range", C.c_float), ("max_range", C.c_float), ("voxel_filter_size", C.c_float),
+                ("hi_max_length", C.c_float), ("hi_min_num_points", C.c_float), ("hi_max_range", C.c_float),
+                ("lo_max_length", C.c_float), ("lo_min_num_points", C.c_float), ("lo_max_range", C.c_float),
+                ("use_rtcsm", C.c_int), ("scan_period", C.c_double),
+                ("rtcsm_linear_window", C.c_double), ("rtcsm_angular_window", C.c_double),
+                ("rtcsm_w_t", C.c_double), ("rtcsm_w_r", C.c_double),
+                ("occ_w0", C.c_double), ("occ_w1", C.c_double), ("trans_w", C.c_double), ("rot_w", C.c_double),
+                ("only_yaw", C.c_int), ("nonmono", C.c_int), ("max_iter", C.c_int)]
+
+    @staticmethod
+    def defaults(**kw):
+        o = FrontEndOptions(min_range=1.0, max_range=60.0, voxel_filter_size=0.15,
+                            hi_max_length=2.0, hi_min_num_points=150, hi_max_range=15.0,
+                            lo_max_length=4.0, lo_min_num_points=200, lo_max_range=60.0,
+                            use_rtcsm=0, scan_period=0.1,
+                            rtcsm_linear_window=0.15, rtcsm_angular_window=np.deg2rad(1.0),
+                            rtcsm_w_t=1e-1, rtcsm_w_r=1e-1,
+                            occ_w0=1.0, occ_w1=6.0, trans_w=5.0, rot_w=4e2, only_yaw=0, nonmono=0, max_iter=12)
+        for k, v in kw.items():
+            setattr(o, k, v)
+        return o
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = os.path.join(_HERE, "build", "liborc.so")
+    if not os.path.exists(path):
+        build()
+    L = C.CDLL(path)
+    L.orc_value_to_probability.restype = C.c_float
+    L.orc_value_to_probability.argtypes = [C.c_uint16]
+    L.orc_probability_to_value.restype = C.c_uint16
+    L.orc_probability_to_value.argtypes = [C.c_float]
+    L.orc_odds.restype = C.c_float
+    L.orc_odds.argtypes = [C.c_float]
+    L.orc_lookup_table_to_apply_odds.argtypes = [C.c_float, u16p]
+    L.orc_value_to_probability_table.argtypes = [f32p]
+    L.orc_grid_create.restype = C.c_void_p
+    L.orc_grid_create.argtypes = [C.c_float]
+    L.orc_grid_destroy.argtypes = [C.c_void_p]
+    L.orc_grid_resolution.restype = C.c_float
+    L.orc_grid_resolution.argtypes = [C.c_void_p]
+    L.orc_grid_bits.argtypes = [C.c_void_p]
+    L.orc_grid_set_probability.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float]
+    L.orc_grid_set_value.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint16]
+    L.orc_grid_value.restype = C.c_uint16
+    L.orc_grid_value.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.orc_grid_probability.restype = C.c_float
+    L.orc_grid_probability.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.orc_grid_cell_index.argtypes = [C.c_void_p, f32p, i32p]
+    L.orc_grid_center_of_cell.argtypes = [C.c_void_p, i32p, f32p]
+    L.orc_grid_apply_lookup_table.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, u16p]
+    L.orc_grid_finish_update.argtypes = [C.c_void_p]
+    L.orc_grid_num_cells.restype = C.c_int64
+    L.orc_grid_num_cells.argtypes = [C.c_void_p]
+    L.orc_grid_export.argtypes = [C.c_void_p, i32p, i32p, i32p, u16p]
+    L.orc_grid_insert_range_data.argtypes = [C.c_void_p, f32p, f32p, C.c_int64, C.c_double, C.c_double, C.c_int]
+    L.orc_interpolate.restype = C.c_double
+    L.orc_interpolate.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+    L.orc_interpolate_grad.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, f64p]
+    L.orc_voxel_filter.restype = C.c_int64
+    L.orc_voxel_filter.argtypes = [f32p, C.c_int64, C.c_int, C.c_float, i64p]
+    L.orc_voxel_indices.argtypes = [f32p, C.c_int64, C.c_int, C.c_float, i32p]
+    L.orc_adaptive_voxel_filter.restype = C.c_int64
+    L.orc_adaptive_voxel_filter.argtypes = [f32p, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float, i64p, f32p,
+                                            C.POINTER(C.c_int)]
+    L.orc_rtcsm_match.restype = C.c_float
+    L.orc_rtcsm_match.argtypes = [C.c_void_p, f32p, C.c_int64, f64p, C.c_double, C.c_double, C.c_double, C.c_double,
+                                  f64p, C.POINTER(C.c_int64), i32p, f32p, C.c_void_p]
+    L.orc_ceres_match.argtypes = [C.c_int, C.POINTER(C.c_void_p), i64p, C.POINTER(C.c_void_p), f64p, C.c_double,
+                                  C.c_double, C.c_int, C.c_int, C.c_int, f64p, f64p, f64p, C.POINTER(SolveSummary),
+                                  C.c_void_p]
+    L.orc_ceres_normal_equations.argtypes = [C.c_int, C.POINTER(C.c_void_p), i64p, C.POINTER(C.c_void_p), f64p,
+                                             C.c_double, C.c_double, f64p, f64p, f64p, f64p, f64p, f64p]
+    L.orc_ingest_scan.argtypes = [C.POINTER(FrontEndOptions), C.c_void_p, C.c_int64, f32p, f64p, f64p, i64p, f32p,
+                                  f32p, f32p, f32p, i64p]
+    L.orc_match_scan.argtypes = [C.POINTER(FrontEndOptions), f32p, C.c_int64, f64p, f64p, C.c_void_p, C.c_void_p,
+                                 f64p, f64p, C.POINTER(SolveSummary), i64p, i64p, i64p, C.POINTER(C.c_float)]
+    L.orc_frontend_batch.restype = C.c_double
+    L.orc_frontend_batch.argtypes = [C.POINTER(FrontEndOptions), C.c_int, C.POINTER(C.c_void_p), i64p, f32p, f64p,
+                                     f64p, f64p, C.c_void_p, C.c_void_p, C.c_int, f64p, i32p]
+    _LIB = L
+    return L
+
+
+IDENTITY_POSE = np.array([0, 0, 0, 1, 0, 0, 0], np.float64)
+
+
+def pose(t=(0, 0, 0), q=(1, 0, 0, 0)):
+    return np.array(list(t) + list(q), np.float64)
+
+
+def angle_axis_pose(t, angle, axis):
+    """Rigid3d(t, AngleAxisd(angle, axis)) — Eigen: w = cos(a/2), xyz = sin(a/2) * axis (axis used as given)."""
+    axis = np.asarray(axis, np.float64)
+    return pose(t, [np.cos(angle / 2)] + list(np.sin(angle / 2) * axis))
+
+
+class Grid:
+    """The oracle's HybridGrid (uint16 probability values in a sparse 3-level voxel tree)."""
+
+    def __init__(self, resolution):
+        self.L = lib()
+        self.h = C.c_void_p(self.L.orc_grid_create(np.float32(resolution)))
+        self.resolution = np.float32(resolution)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_grid_destroy(self.h)
+            self.h = None
+
+    def cell_index(self, p):
+        out = np.zeros(3, np.int32)
+        self.L.orc_grid_cell_index(self.h, np.ascontiguousarray(p, np.float32), out)
+        return out
+
+    def center_of_cell(self, idx):
+        out = np.zeros(3, np.float32)
+        self.L.orc_grid_center_of_cell(self.h, np.ascontiguousarray(idx, np.int32), out)
+        return out
+
+    def set_probability(self, idx, p):
+        if self.L.orc_grid_set_probability(self.h, int(idx[0]), int(idx[1]), int(idx[2]), np.float32(p)):
+            raise RuntimeError("grid growth limit (CHECK_LE(new_bits, 8))")
+
+    def set_value(self, idx, v):
+        if self.L.orc_grid_set_value(self.h, int(idx[0]), int(idx[1]), int(idx[2]), int(v)):
+            raise RuntimeError("grid growth limit")
+
+    def value(self, idx):
+        return self.L.orc_grid_value(self.h, int(idx[0]), int(idx[1]), int(idx[2]))
+
+    def probability(self, idx):
+        return self.L.orc_grid_probability(self.h, int(idx[0]), int(idx[1]), int(idx[2]))
+
+    def apply_lookup_table(self, idx, table):
+        return bool(self.L.orc_grid_apply_lookup_table(self.h, int(idx[0]), int(idx[1]), int(idx[2]), table))
+
+    def finish_update(self):
+        self.L.orc_grid_finish_update(self.h)
+
+    def bits(self):
+        return self.L.orc_grid_bits(self.h)
+
+    def export(self):
+        """(x, y, z, value) parallel arrays in the reference's iteration order (HybridGrid proto layout)."""
+        n = self.L.orc_grid_num_cells(self.h)
+        xs, ys, zs = (np.zeros(n, np.int32) for _ in range(3))
+        vs = np.zeros(n, np.uint16)
+        if n:
+            self.L.orc_grid_export(self.h, xs, ys, zs, vs)
+        return xs, ys, zs, vs
+
+    def insert_range_data(self, origin, returns, hit=0.55, miss=0.49, num_free=2):
+        returns = np.ascontiguousarray(returns, np.float32).reshape(-1, 3)
+        self.L.orc_grid_insert_range_data(self.h, np.ascontiguousarray(origin, np.float32), returns, len(returns),
+                                          hit, miss, num_free)
+
+    def interpolate(self, x, y, z):
+        return self.L.orc_interpolate(self.h, x, y, z)
+
+    def interpolate_grad(self, x, y, z):
+        out = np.zeros(4)
+        self.L.orc_interpolate_grad(self.h, x, y, z, out)
+        return out
+
+
+def voxel_filter(points, resolution):
+    """Indices (input order) of the first point in each voxel. points: (n, stride) float32, stride >= 3."""
+    points = np.ascontiguousarray(points, np.float32)
+    n, stride = points.shape
+    keep = np.zeros(max(n, 1), np.int64)
+    m = lib().orc_voxel_filter(points, n, stride, np.float32(resolution), keep)
+    return keep[:m].copy()
+
+
+def voxel_indices(points, resolution):
+    points = np.ascontiguousarray(points, np.float32)
+    n, stride = points.shape
+    out = np.zeros((n, 3), np.int32)
+    lib().orc_voxel_indices(points, n, stride, np.float32(resolution), out)
+    return out
+
+
+def adaptive_voxel_filter(points, max_length, min_num_points, max_range):
+    points = np.ascontiguousarray(points, np.float32)
+    n, stride = points.shape
+    keep = np.zeros(max(n, 1), np.int64)
+    passes = np.zeros(32, np.float32)
+    npass = C.c_int(0)
+    m = lib().orc_adaptive_voxel_filter(points, n, stride, max_length, min_num_points, max_range, keep, passes,
+                                        C.byref(npass))
+    return keep[:m].copy(), passes[:npass.value].copy()
+
+
+def rtcsm_match(grid, points, initial_pose, linear_window, angular_window, w_t, w_r, want_scores=False):
+    points = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    out_pose = np.zeros(7)
+    best = C.c_int64(-1)
+    window = np.zeros(2, np.int32)
+    step = np.zeros(2, np.float32)
+    scores = None
+    sp = None
+    if want_scores:
+        # upper bound on the candidate count is not known before the call: run once for the window
+        lib().orc_rtcsm_match(grid.h, points, len(points), np.ascontiguousarray(initial_pose, np.float64),
+                              linear_window, angular_window, w_t, w_r, out_pose, C.byref(best), window, step, None)
+        k = (2 * window[0] + 1) ** 3 * (2 * window[1] + 1) ** 3
+        scores = np.zeros(int(k), np.float32)
+        sp = scores.ctypes.data_as(C.c_void_p)
+    score = lib().orc_rtcsm_match(grid.h, points, len(points), np.ascontiguousarray(initial_pose, np.float64),
+                                  linear_window, angular_window, w_t, w_r, out_pose, C.byref(best), window, step, sp)
+    return {"score": np.float32(score), "pose": out_pose, "best_index": best.value, "linear": int(window[0]),
+            "angular": int(window[1]), "angular_step": step[0], "max_scan_range": step[1], "scores": scores}
+
+
+def _pairs(clouds, grids):
+    clouds = [np.ascontiguousarray(c, np.float32).reshape(-1, 3) for c in clouds]
+    n = len(clouds)
+    cp = (C.c_void_p * n)(*[c.ctypes.data for c in clouds])
+    gp = (C.c_void_p * n)(*[g.h.value for g in grids])
+    sizes = np.array([len(c) for c in clouds], np.int64)
+    return clouds, cp, gp, sizes
+
+
+def ceres_match(clouds, grids, occ_weights, trans_w, rot_w, target_translation, initial_pose, only_yaw=False,
+                nonmono=False, max_iter=12):
+    clouds, cp, gp, sizes = _pairs(clouds, grids)
+    out_pose = np.zeros(7)
+    s = SolveSummary()
+    costs = np.full(max_iter + 2, np.nan)
+    lib().orc_ceres_match(len(clouds), cp, sizes, gp, np.asarray(occ_weights, np.float64), trans_w, rot_w,
+                          int(only_yaw), int(nonmono), max_iter, np.ascontiguousarray(target_translation, np.float64),
+                          np.ascontiguousarray(initial_pose, np.float64), out_pose, C.byref(s),
+                          costs.ctypes.data_as(C.c_void_p))
+    d = s.as_dict()
+    d["iteration_costs"] = costs[:s.num_iterations].copy()
+    return out_pose, d
+
+
+def ceres_normal_equations(clouds, grids, occ_weights, trans_w, rot_w, target_translation, reference_pose, at_pose):
+    clouds, cp, gp, sizes = _pairs(clouds, grids)
+    cost = np.zeros(1)
+    g = np.zeros(6)
+    h = np.zeros(36)
+    lib().orc_ceres_normal_equations(len(clouds), cp, sizes, gp, np.asarray(occ_weights, np.float64), trans_w, rot_w,
+                                     np.ascontiguousarray(target_translation, np.float64),
+                                     np.ascontiguousarray(reference_pose, np.float64),
+                                     np.ascontiguousarray(at_pose, np.float64), cost, g, h)
+    return cost[0], g, h.reshape(6, 6)
+
+
+RANGE_DTYPE = np.dtype([("x", np.float32), ("y", np.float32), ("z", np.float32), ("t", np.float32),
+                        ("origin_index", np.uint64), ("_pad", np.uint64)])
+assert RANGE_DTYPE.itemsize == 32
+
+
+def make_ranges(xyzt, origin_index=0):
+    r = np.zeros(len(xyzt), RANGE_DTYPE)
+    r["x"], r["y"], r["z"], r["t"] = xyzt[:, 0], xyzt[:, 1], xyzt[:, 2], xyzt[:, 3]
+    r["origin_index"] = origin_index
+    return r
+
+
+def ingest_scan(opts, ranges, origins, prev_pose, cur_pose):
+    n = len(ranges)
+    origins = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+    first_keep = np.zeros(n, np.int64)
+    rl, rt, mt = (np.zeros((n, 3), np.float32) for _ in range(3))
+    cp = np.zeros(7, np.float32)
+    counts = np.zeros(4, np.int64)
+    lib().orc_ingest_scan(C.byref(opts), ranges.ctypes.data_as(C.c_void_p), n, origins,
+                          np.ascontiguousarray(prev_pose, np.float64), np.ascontiguousarray(cur_pose, np.float64),
+                          first_keep, rl, rt, mt, cp, counts)
+    return {"first_keep": first_keep[:counts[0]].copy(), "returns_local": rl[:counts[1]].copy(),
+            "returns_tracking": rt[:counts[2]].copy(), "misses_tracking": mt[:counts[3]].copy(), "current_pose": cp}
+
+
+def match_scan(opts, returns_tracking, pose_prediction, submap_local_pose, hi_grid, lo_grid):
+    pts = np.ascontiguousarray(returns_tracking, np.float32).reshape(-1, 3)
+    n = len(pts)
+    obs, est = np.zeros(7), np.zeros(7)
+    s = SolveSummary()
+    hi_keep, lo_keep = np.zeros(max(n, 1), np.int64), np.zeros(max(n, 1), np.int64)
+    counts = np.zeros(2, np.int64)
+    score = C.c_float(0)
+    ok = lib().orc_match_scan(C.byref(opts), pts, n, np.ascontiguousarray(pose_prediction, np.float64),
+                              np.ascontiguousarray(submap_local_pose, np.float64), hi_grid.h, lo_grid.h, obs, est,
+                              C.byref(s), hi_keep, lo_keep, counts, C.byref(score))
+    return {"ok": bool(ok), "pose_observation_in_submap": obs, "pose_estimate_local": est, "summary": s.as_dict(),
+            "hi_keep": hi_keep[:counts[0]].copy(), "lo_keep": lo_keep[:counts[1]].copy(), "rtcsm_score": score.value}
+
+
+def frontend_batch(opts, ranges_list, origin, prev_poses, cur_poses, submap_local_pose, hi_grid, lo_grid, threads):
+    """CPU baseline: the whole per-scan hot path for independent scans over `threads` host threads."""
+    n = len(ranges_list)
+    rp = (C.c_void_p * n)(*[r.ctypes.data for r in ranges_list])
+    sizes = np.array([len(r) for r in ranges_list], np.int64)
+    poses = np.zeros((n, 7))
+    ok = np.zeros(n, np.int32)
+    secs = lib().orc_frontend_batch(C.byref(opts), n, rp, sizes, np.ascontiguousarray(origin, np.float32),
+                                    np.ascontiguousarray(prev_poses, np.float64),
+                                    np.ascontiguousarray(cur_poses, np.float64),
+                                    np.ascontiguousarray(submap_local_pose, np.float64), hi_grid.h, lo_grid.h,
+                                    threads, poses, ok)
+    return secs, poses, ok

@@ -1,0 +1,290 @@
+// TEST INFRASTRUCTURE — CPU oracle (see orc_math.h header). Flat C interface for ctypes
+// (tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl reference only).
+// Poses cross this interface as 7 doubles: t.x t.y t.z q.w q.x q.y q.z.
+#include <chrono>
+#include <cstring>
+#include <thread>
+
+#include "orc_filters.h"
+#include "orc_frontend.h"
+#include "orc_grid.h"
+#include "orc_nls.h"
+#include "orc_rtcsm.h"
+
+using namespace orc;
+
+namespace {
+Rigid3d pose_in(const double* p) { return {{p[0], p[1], p[2]}, {p[3], p[4], p[5], p[6]}}; }
+void pose_out(const Rigid3d& r, double* p) {
+  p[0] = r.t.x; p[1] = r.t.y; p[2] = r.t.z; p[3] = r.q.w; p[4] = r.q.x; p[5] = r.q.y; p[6] = r.q.z;
+}
+}  // namespace
+
+extern "C" {
+
+// ---- probability tables
+float orc_value_to_probability(uint16_t v) { return value_to_probability(v); }
+uint16_t orc_probability_to_value(float p) { return probability_to_value(p); }
+float orc_odds(float p) { return odds(p); }
+void orc_lookup_table_to_apply_odds(float o, uint16_t* out) {
+  const auto t = lookup_table_to_apply_odds(o);
+  std::memcpy(out, t.data(), 32768 * sizeof(uint16_t));
+}
+void orc_value_to_probability_table(float* out65536) {
+  std::memcpy(out65536, value_to_probability_table().data(), 65536 * sizeof(float));
+}
+
+// ---- grid
+void* orc_grid_create(float resolution) { return new HybridGrid(resolution); }
+void orc_grid_destroy(void* g) { delete (HybridGrid*)g; }
+float orc_grid_resolution(void* g) { return ((HybridGrid*)g)->resolution(); }
+int orc_grid_bits(void* g) { return ((HybridGrid*)g)->bits(); }
+int orc_grid_set_probability(void* g, int x, int y, int z, float p) {
+  try { ((HybridGrid*)g)->SetProbability({x, y, z}, p); } catch (...) { return 1; }
+  return 0;
+}
+int orc_grid_set_value(void* g, int x, int y, int z, uint16_t v) {
+  try { *((HybridGrid*)g)->mutable_value({x, y, z}) = v; } catch (...) { return 1; }
+  return 0;
+}
+uint16_t orc_grid_value(void* g, int x, int y, int z) { return ((HybridGrid*)g)->value({x, y, z}); }
+float orc_grid_probability(void* g, int x, int y, int z) { return ((HybridGrid*)g)->GetProbability({x, y, z}); }
+void orc_grid_cell_index(void* g, const float* p, int* out) {
+  const I3 i = ((HybridGrid*)g)->GetCellIndex({p[0], p[1], p[2]});
+  out[0] = i.x; out[1] = i.y; out[2] = i.z;
+}
+void orc_grid_center_of_cell(void* g, const int* i, float* out) {
+  const V3f c = ((HybridGrid*)g)->GetCenterOfCell({i[0], i[1], i[2]});
+  out[0] = c.x; out[1] = c.y; out[2] = c.z;
+}
+int orc_grid_apply_lookup_table(void* g, int x, int y, int z, const uint16_t* table) {
+  std::vector<uint16_t> t(table, table + 32768);
+  return ((HybridGrid*)g)->ApplyLookupTable({x, y, z}, t) ? 1 : 0;
+}
+void orc_grid_finish_update(void* g) { ((HybridGrid*)g)->FinishUpdate(); }
+int64_t orc_grid_num_cells(void* g) {
+  int64_t n = 0;
+  ((HybridGrid*)g)->ForEachCell([&](const I3&, uint16_t) { ++n; });
+  return n;
+}
+// Parallel arrays in the reference's iteration order (the HybridGrid proto layout, hybrid_grid.h:530-542).
+void orc_grid_export(void* g, int* xs, int* ys, int* zs, uint16_t* vs) {
+  int64_t n = 0;
+  ((HybridGrid*)g)->ForEachCell([&](const I3& i, uint16_t v) { xs[n] = i.x; ys[n] = i.y; zs[n] = i.z; vs[n] = v; ++n; });
+}
+void orc_grid_insert_range_data(void* g, const float* origin, const float* returns, int64_t n, double hit_p,
+                                double miss_p, int num_free) {
+  RangeDataInserter ins(RangeDataInserterOptions{hit_p, miss_p, num_free});
+  ins.Insert({origin[0], origin[1], origin[2]}, returns, n, (HybridGrid*)g);
+}
+
+// ---- interpolation
+double orc_interpolate(void* g, double x, double y, double z) {
+  return InterpolatedGrid(*(HybridGrid*)g).GetProbability(x, y, z);
+}
+// out[0] = value, out[1..3] = d/dx, d/dy, d/dz (forward-mode Jets)
+void orc_interpolate_grad(void* g, double x, double y, double z, double* out) {
+  const Jet r = InterpolatedGrid(*(HybridGrid*)g).GetProbability(Jet(x, 0), Jet(y, 1), Jet(z, 2));
+  out[0] = r.a; out[1] = r.v[0]; out[2] = r.v[1]; out[3] = r.v[2];
+}
+
+// ---- filters
+int64_t orc_voxel_filter(const float* pts, int64_t n, int stride, float resolution, int64_t* keep) {
+  std::vector<int64_t> k;
+  VoxelFilter(resolution).Filter(pts, n, stride, &k);
+  std::memcpy(keep, k.data(), k.size() * sizeof(int64_t));
+  return (int64_t)k.size();
+}
+void orc_voxel_indices(const float* pts, int64_t n, int stride, float resolution, int* out) {
+  for (int64_t i = 0; i < n; ++i) {
+    const I3 c = cell_index({pts[i * stride], pts[i * stride + 1], pts[i * stride + 2]}, resolution);
+    out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z;
+  }
+}
+int64_t orc_adaptive_voxel_filter(const float* pts, int64_t n, int stride, float max_length, float min_num_points,
+                                  float max_range, int64_t* keep, float* passes, int* num_passes) {
+  std::vector<float> p;
+  const auto k = AdaptiveVoxelFilter({max_length, min_num_points, max_range}, pts, n, stride, &p);
+  std::memcpy(keep, k.data(), k.size() * sizeof(int64_t));
+  if (passes) std::memcpy(passes, p.data(), std::min<size_t>(p.size(), 32) * sizeof(float));
+  if (num_passes) *num_passes = (int)p.size();
+  return (int64_t)k.size();
+}
+
+// ---- correlative matcher
+// window_out: [linear, angular]; step_out: [angular_step, max_scan_range]
+float orc_rtcsm_match(void* grid, const float* pts, int64_t n, const double* initial_pose, double linear_window,
+                      double angular_window, double w_t, double w_r, double* pose, int64_t* best_index,
+                      int* window_out, float* step_out, float* all_scores) {
+  std::vector<float> scores;
+  const RtcsmResult r = rtcsm_match({linear_window, angular_window, w_t, w_r}, pose_in(initial_pose), pts, n,
+                                    *(HybridGrid*)grid, all_scores ? &scores : nullptr);
+  pose_out(r.pose, pose);
+  if (best_index) *best_index = r.best_index;
+  if (window_out) { window_out[0] = r.window.linear; window_out[1] = r.window.angular; }
+  if (step_out) { step_out[0] = r.window.angular_step; step_out[1] = r.window.max_scan_range; }
+  if (all_scores) std::memcpy(all_scores, scores.data(), scores.size() * sizeof(float));
+  return r.score;
+}
+
+// ---- Ceres-equivalent matcher
+struct OrcSolveSummary {
+  double initial_cost, final_cost;
+  int num_iterations;  // recorded iterations, including iteration 0
+  int num_successful_steps, num_unsuccessful_steps, termination;
+  int num_residual_evaluations, num_jacobian_evaluations;
+};
+
+static CeresMatcherOptions make_ceres_options(int n_pairs, const double* occ_w, double trans_w, double rot_w,
+                                              int only_yaw, int nonmono, int max_iter) {
+  CeresMatcherOptions o;
+  o.occupied_space_weight.assign(occ_w, occ_w + n_pairs);
+  o.translation_weight = trans_w;
+  o.rotation_weight = rot_w;
+  o.only_optimize_yaw = only_yaw != 0;
+  o.use_nonmonotonic_steps = nonmono != 0;
+  o.max_num_iterations = max_iter;
+  return o;
+}
+
+void orc_ceres_match(int n_pairs, const float* const* clouds, const int64_t* sizes, void* const* grids,
+                     const double* occ_w, double trans_w, double rot_w, int only_yaw, int nonmono, int max_iter,
+                     const double* target_translation, const double* initial_pose, double* pose,
+                     OrcSolveSummary* summary, double* iteration_costs /* >= max_iter + 1, optional */) {
+  std::vector<CloudAndGrid> pairs;
+  for (int i = 0; i < n_pairs; ++i) pairs.push_back({clouds[i], sizes[i], (const HybridGrid*)grids[i]});
+  SolveSummary s;
+  Rigid3d out;
+  ceres_scan_match(make_ceres_options(n_pairs, occ_w, trans_w, rot_w, only_yaw, nonmono, max_iter),
+                   {target_translation[0], target_translation[1], target_translation[2]}, pose_in(initial_pose), pairs,
+                   &out, &s);
+  pose_out(out, pose);
+  if (summary) {
+    *summary = {s.initial_cost, s.final_cost, (int)s.iterations.size(), s.num_successful_steps,
+                s.num_unsuccessful_steps, s.termination, s.num_residual_evaluations, s.num_jacobian_evaluations};
+  }
+  if (iteration_costs)
+    for (size_t i = 0; i < s.iterations.size(); ++i) iteration_costs[i] = s.iterations[i].cost;
+}
+
+// Cost, local gradient (6) and local Gauss-Newton matrix J^T J (6x6 row-major) at a pose: the quantities
+// the device reduction produces, for a direct kernel-level comparison.
+void orc_ceres_normal_equations(int n_pairs, const float* const* clouds, const int64_t* sizes, void* const* grids,
+                                const double* occ_w, double trans_w, double rot_w, const double* target_translation,
+                                const double* reference_pose, const double* at_pose, double* cost, double* g6,
+                                double* h36) {
+  std::vector<CloudAndGrid> pairs;
+  for (int i = 0; i < n_pairs; ++i) pairs.push_back({clouds[i], sizes[i], (const HybridGrid*)grids[i]});
+  ScanMatchProblem problem(make_ceres_options(n_pairs, occ_w, trans_w, rot_w, 0, 0, 1),
+                           {target_translation[0], target_translation[1], target_translation[2]},
+                           pose_in(reference_pose), pairs);
+  const int m = problem.num_residuals();
+  std::vector<double> r(m), J((size_t)m * 6);
+  problem.Evaluate(at_pose, r.data(), J.data());
+  double c = 0;
+  for (int i = 0; i < 6; ++i) g6[i] = 0;
+  for (int i = 0; i < 36; ++i) h36[i] = 0;
+  for (int i = 0; i < m; ++i) {
+    c += r[i] * r[i];
+    for (int a = 0; a < 6; ++a) {
+      g6[a] += J[(size_t)i * 6 + a] * r[i];
+      for (int b = 0; b < 6; ++b) h36[a * 6 + b] += J[(size_t)i * 6 + a] * J[(size_t)i * 6 + b];
+    }
+  }
+  *cost = 0.5 * c;
+}
+
+// ---- per-scan front end
+struct OrcFrontEndOptions {
+  float min_range, max_range, voxel_filter_size;
+  float hi_max_length, hi_min_num_points, hi_max_range;
+  float lo_max_length, lo_min_num_points, lo_max_range;
+  int use_rtcsm;
+  double scan_period;
+  double rtcsm_linear_window, rtcsm_angular_window, rtcsm_w_t, rtcsm_w_r;
+  double occ_w0, occ_w1, trans_w, rot_w;
+  int only_yaw, nonmono, max_iter;
+};
+
+static FrontEndOptions make_frontend(const OrcFrontEndOptions& o) {
+  FrontEndOptions f;
+  f.min_range = o.min_range; f.max_range = o.max_range; f.voxel_filter_size = o.voxel_filter_size;
+  f.scan_period = o.scan_period;
+  f.hi_filter = {o.hi_max_length, o.hi_min_num_points, o.hi_max_range};
+  f.lo_filter = {o.lo_max_length, o.lo_min_num_points, o.lo_max_range};
+  f.use_online_correlative_scan_matching = o.use_rtcsm != 0;
+  f.rtcsm = {o.rtcsm_linear_window, o.rtcsm_angular_window, o.rtcsm_w_t, o.rtcsm_w_r};
+  const double w[2] = {o.occ_w0, o.occ_w1};
+  f.ceres = make_ceres_options(2, w, o.trans_w, o.rot_w, o.only_yaw, o.nonmono, o.max_iter);
+  return f;
+}
+
+// Scan ingest. ranges: n rows of 8 floats (x y z t + 8 bytes origin index). Outputs sized by the caller
+// (n rows each); counts returned through n_out[4] = {first_keep, returns_local, returns_tracking, misses_tracking}.
+void orc_ingest_scan(const OrcFrontEndOptions* o, const void* ranges, int64_t n, const float* origins,
+                     const double* prev_pose, const double* cur_pose, int64_t* first_keep, float* returns_local,
+                     float* returns_tracking, float* misses_tracking, float* current_pose7f, int64_t* n_out) {
+  const ScanIngest s = ingest_scan(make_frontend(*o), (const RangeMeasurement*)ranges, n, (const V3f*)origins,
+                                   pose_in(prev_pose), pose_in(cur_pose));
+  std::memcpy(first_keep, s.first_filter_keep.data(), s.first_filter_keep.size() * sizeof(int64_t));
+  std::memcpy(returns_local, s.returns_local.data(), s.returns_local.size() * sizeof(float));
+  std::memcpy(returns_tracking, s.returns_tracking.data(), s.returns_tracking.size() * sizeof(float));
+  std::memcpy(misses_tracking, s.misses_tracking.data(), s.misses_tracking.size() * sizeof(float));
+  const Rigid3f& c = s.current_pose;
+  const float cp[7] = {c.t.x, c.t.y, c.t.z, c.q.w, c.q.x, c.q.y, c.q.z};
+  std::memcpy(current_pose7f, cp, sizeof(cp));
+  n_out[0] = (int64_t)s.first_filter_keep.size();
+  n_out[1] = (int64_t)s.returns_local.size() / 3;
+  n_out[2] = (int64_t)s.returns_tracking.size() / 3;
+  n_out[3] = (int64_t)s.misses_tracking.size() / 3;
+}
+
+// Adaptive filters + (RT-CSM) + Ceres match for one scan already in the tracking frame.
+// Returns 1 on success. counts[2] = {n_hi, n_lo}.
+int orc_match_scan(const OrcFrontEndOptions* o, const float* returns_tracking, int64_t n, const double* pose_prediction,
+                   const double* submap_local_pose, void* hi_grid, void* lo_grid, double* pose_observation_in_submap,
+                   double* pose_estimate_local, OrcSolveSummary* summary, int64_t* hi_keep, int64_t* lo_keep,
+                   int64_t* counts, float* rtcsm_score) {
+  const ScanMatchOutput r = match_scan(make_frontend(*o), returns_tracking, n, pose_in(pose_prediction),
+                                       pose_in(submap_local_pose), *(HybridGrid*)hi_grid, *(HybridGrid*)lo_grid);
+  if (!r.ok) return 0;
+  pose_out(r.pose_observation_in_submap, pose_observation_in_submap);
+  pose_out(r.pose_estimate_local, pose_estimate_local);
+  if (summary)
+    *summary = {r.summary.initial_cost, r.summary.final_cost, (int)r.summary.iterations.size(),
+                r.summary.num_successful_steps, r.summary.num_unsuccessful_steps, r.summary.termination,
+                r.summary.num_residual_evaluations, r.summary.num_jacobian_evaluations};
+  if (hi_keep) std::memcpy(hi_keep, r.hi_keep.data(), r.hi_keep.size() * sizeof(int64_t));
+  if (lo_keep) std::memcpy(lo_keep, r.lo_keep.data(), r.lo_keep.size() * sizeof(int64_t));
+  if (counts) { counts[0] = (int64_t)r.hi_keep.size(); counts[1] = (int64_t)r.lo_keep.size(); }
+  if (rtcsm_score) *rtcsm_score = r.rtcsm_score;
+  return 1;
+}
+
+// Whole per-scan hot path (ingest + match) for a batch of independent scans on `threads` host threads:
+// the CPU baseline. scans share the option block and the submap. Returns wall seconds.
+double orc_frontend_batch(const OrcFrontEndOptions* o, int num_scans, const void* const* ranges, const int64_t* sizes,
+                          const float* origin, const double* prev_poses, const double* cur_poses,
+                          const double* submap_local_pose, void* hi_grid, void* lo_grid, int threads,
+                          double* poses_out /* 7 per scan */, int* ok_out) {
+  const FrontEndOptions fe = make_frontend(*o);
+  const auto t0 = std::chrono::steady_clock::now();
+  auto work = [&](int tid) {
+    for (int s = tid; s < num_scans; s += threads) {
+      const ScanIngest ing = ingest_scan(fe, (const RangeMeasurement*)ranges[s], sizes[s], (const V3f*)origin,
+                                         pose_in(prev_poses + 7 * s), pose_in(cur_poses + 7 * s));
+      const ScanMatchOutput r =
+          match_scan(fe, ing.returns_tracking.data(), (int64_t)ing.returns_tracking.size() / 3,
+                     cast_d(ing.current_pose), pose_in(submap_local_pose), *(HybridGrid*)hi_grid, *(HybridGrid*)lo_grid);
+      ok_out[s] = r.ok ? 1 : 0;
+      if (r.ok) pose_out(r.pose_estimate_local, poses_out + 7 * s);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
+  work(0);
+  for (auto& t : pool) t.join();
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+}  // extern "C"
