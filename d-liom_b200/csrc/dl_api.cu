@@ -1,0 +1,925 @@
+// C-ABI of libdliom_b200.so (declared in include/dliom_b200.h): contexts, the device grid mirror, and the host
+// orchestration of the kernels in dl_voxel.cu / dl_rtcsm.cu / dl_nls.cu / dl_ingest.cu.
+// There is deliberately no CPU implementation of anything here: without a CUDA device every call fails.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "dl_internal.cuh"
+#include "dl_pipeline.cuh"
+
+using namespace dl;
+
+// ------------------------------------------------------------------------------------------------ context
+int dl_context::reserve_device(size_t bytes) {
+  if (bytes <= d_scratch_bytes) return DL_OK;
+  if (d_scratch) {
+    DL_CUDA(this, cudaStreamSynchronize(stream));
+    DL_CUDA(this, cudaFree(d_scratch));
+    d_scratch = nullptr;
+    d_scratch_bytes = 0;
+  }
+  const size_t want = bytes + bytes / 4;
+  DL_CUDA(this, cudaMalloc(&d_scratch, want));
+  d_scratch_bytes = want;
+  return DL_OK;
+}
+int dl_context::reserve_pinned(size_t bytes) {
+  if (bytes <= h_pinned_bytes) return DL_OK;
+  if (h_pinned) {
+    DL_CUDA(this, cudaStreamSynchronize(stream));
+    DL_CUDA(this, cudaFreeHost(h_pinned));
+    h_pinned = nullptr;
+    h_pinned_bytes = 0;
+  }
+  DL_CUDA(this, cudaMallocHost(&h_pinned, bytes + bytes / 4));
+  h_pinned_bytes = bytes + bytes / 4;
+  return DL_OK;
+}
+
+namespace {
+thread_local std::string g_create_error;
+
+int64_t next_pow2(int64_t v) {
+  int64_t p = 64;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+#define DL_TRY(expr)            \
+  do {                          \
+    const int st__ = (expr);    \
+    if (st__ != DL_OK) return st__; \
+  } while (0)
+
+template <typename T>
+int h2d(dl_context* ctx, T* dst, const T* src, size_t count) {
+  if (count == 0) return DL_OK;
+  DL_CUDA(ctx, cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return DL_OK;
+}
+template <typename T>
+int ensure_capacity(dl_context* ctx, T** ptr, size_t* cap, size_t need) {
+  if (need <= *cap) return DL_OK;
+  DL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (*ptr) DL_CUDA(ctx, cudaFree(*ptr));
+  *ptr = nullptr;
+  const size_t want = need + need / 2 + 512;
+  DL_CUDA(ctx, cudaMalloc((void**)ptr, want * sizeof(T)));
+  *cap = want;
+  return DL_OK;
+}
+
+template <typename T>
+int d2h(dl_context* ctx, T* dst, const T* src, size_t count) {
+  if (count == 0) return DL_OK;
+  DL_CUDA(ctx, cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+  return DL_OK;
+}
+int sync(dl_context* ctx) {
+  DL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return DL_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int dl_context_create(int device_ordinal, dl_context** out) {
+  if (!out) return DL_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || device_ordinal < 0 || device_ordinal >= count) {
+    g_create_error = e != cudaSuccess ? cudaGetErrorString(e) : "no such CUDA device";
+    return DL_ERR_CUDA;
+  }
+  dl_context* ctx = new (std::nothrow) dl_context();
+  if (!ctx) return DL_ERR_ARG;
+  ctx->device = device_ordinal;
+  if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    delete ctx;
+    return DL_ERR_CUDA;
+  }
+  *out = ctx;
+  return DL_OK;
+}
+
+void dl_context_destroy(dl_context* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* dl_last_error(const dl_context* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+const char* dl_status_string(int status) {
+  switch (status) {
+    case DL_OK: return "ok";
+    case DL_ERR_CUDA: return "CUDA error";
+    case DL_ERR_ARG: return "invalid argument";
+    case DL_ERR_GRID_RANGE: return "cell index outside the growable grid range";
+    case DL_ERR_EMPTY: return "empty point cloud";
+    case DL_ERR_SCORE: return "non-positive correlative score";
+    default: return "unknown status";
+  }
+}
+int64_t dl_context_kernel_launches(const dl_context* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t dl_context_stream(const dl_context* ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
+int dl_context_synchronize(dl_context* ctx) {
+  if (!ctx) return DL_ERR_ARG;
+  return sync(ctx);
+}
+
+int dl_device_alloc(dl_context* ctx, int64_t bytes, void** out_dev) {
+  if (!ctx || !out_dev || bytes < 0) return DL_ERR_ARG;
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  DL_CUDA(ctx, cudaMalloc(out_dev, (size_t)std::max<int64_t>(bytes, 1)));
+  return DL_OK;
+}
+int dl_device_free(dl_context* ctx, void* dev) {
+  if (!ctx) return DL_ERR_ARG;
+  DL_CUDA(ctx, cudaFree(dev));
+  return DL_OK;
+}
+int dl_copy_to_device(dl_context* ctx, void* dst_dev, const void* src_host, int64_t bytes) {
+  if (!ctx || bytes < 0) return DL_ERR_ARG;
+  DL_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return sync(ctx);
+}
+int dl_copy_to_host(dl_context* ctx, void* dst_host, const void* src_dev, int64_t bytes) {
+  if (!ctx || bytes < 0) return DL_ERR_ARG;
+  DL_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return sync(ctx);
+}
+
+// ------------------------------------------------------------------------------------------------ grid
+int dl_grid_create(dl_context* ctx, float resolution, dl_grid** out) {
+  if (!ctx || !out || !(resolution > 0.f)) return DL_ERR_ARG;
+  dl_grid* g = new (std::nothrow) dl_grid();
+  if (!g) return ctx->fail(DL_ERR_ARG, "out of memory");
+  g->ctx = ctx;
+  g->resolution = resolution;
+  g->bits = 1;  // DynamicGrid starts with 2^3 top cells (hybrid_grid.h:255)
+  g->top.assign(8, -1);
+  *out = g;
+  return DL_OK;
+}
+
+void dl_grid_destroy(dl_grid* g) {
+  if (!g) return;
+  cudaSetDevice(g->ctx->device);
+  cudaStreamSynchronize(g->ctx->stream);
+  cudaFree(g->d_top);
+  cudaFree(g->d_nodes);
+  cudaFree(g->d_bricks);
+  delete g;
+}
+
+float dl_grid_resolution(const dl_grid* g) { return g ? g->resolution : 0.f; }
+int64_t dl_grid_num_bricks(const dl_grid* g) { return g ? (int64_t)(g->bricks.size() / 512) : 0; }
+
+static inline size_t top_flat(int x, int y, int z, int bits) { return ((((size_t)z << bits) + y) << bits) + x; }
+
+// Grow(): double every axis, old content moves to the centre (hybrid_grid.h:389-407).
+static int grid_grow(dl_grid* g) {
+  const int nb = g->bits + 1;
+  if (nb > 8) return DL_ERR_GRID_RANGE;
+  std::vector<int32_t> grown((size_t)8 * g->top.size(), -1);
+  const int n = 1 << g->bits, o = 1 << (g->bits - 1);
+  for (int z = 0; z < n; ++z)
+    for (int y = 0; y < n; ++y)
+      for (int x = 0; x < n; ++x) grown[top_flat(x + o, y + o, z + o, nb)] = g->top[top_flat(x, y, z, g->bits)];
+  g->top.swap(grown);
+  g->bits = nb;
+  g->structure_dirty = true;
+  return DL_OK;
+}
+
+int dl_grid_set_cells(dl_grid* g, int64_t n, const int32_t* xs, const int32_t* ys, const int32_t* zs,
+                      const uint16_t* values) {
+  if (!g || n < 0 || (n > 0 && (!xs || !ys || !zs || !values))) return DL_ERR_ARG;
+  for (int64_t i = 0; i < n; ++i) {
+    for (;;) {
+      const int gs = 64 << g->bits, half = gs >> 1;
+      const unsigned sx = (unsigned)(xs[i] + half), sy = (unsigned)(ys[i] + half), sz = (unsigned)(zs[i] + half);
+      if (sx >= (unsigned)gs || sy >= (unsigned)gs || sz >= (unsigned)gs) {
+        if (grid_grow(g) != DL_OK) return g->ctx->fail(DL_ERR_GRID_RANGE, "cell index outside +-8192 cells");
+        continue;
+      }
+      int32_t& node = g->top[top_flat(sx >> 6, sy >> 6, sz >> 6, g->bits)];
+      if (node < 0) {
+        node = (int32_t)(g->nodes.size() / 512);
+        g->nodes.insert(g->nodes.end(), 512, -1);
+        g->structure_dirty = true;
+      }
+      int32_t& brick = g->nodes[(size_t)node * 512 + ((((sz >> 3) & 7) << 6) | (((sy >> 3) & 7) << 3) | ((sx >> 3) & 7))];
+      if (brick < 0) {
+        brick = (int32_t)(g->bricks.size() / 512);
+        g->bricks.insert(g->bricks.end(), 512, 0);
+        g->brick_dirty.push_back(1);
+        g->structure_dirty = true;
+      }
+      g->bricks[(size_t)brick * 512 + (((sz & 7) << 6) | ((sy & 7) << 3) | (sx & 7))] = values[i];
+      g->brick_dirty[brick] = 1;
+      break;
+    }
+  }
+  return DL_OK;
+}
+
+int dl_grid_sync(dl_grid* g) {
+  if (!g) return DL_ERR_ARG;
+  dl_context* ctx = g->ctx;
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t nbricks = g->bricks.size() / 512;
+  if (g->structure_dirty) {
+    DL_TRY(ensure_capacity(ctx, &g->d_top, &g->d_top_cap, g->top.size()));
+    DL_TRY(ensure_capacity(ctx, &g->d_nodes, &g->d_nodes_cap, std::max<size_t>(g->nodes.size(), 1)));
+    const size_t old_cap = g->d_bricks_cap;
+    DL_TRY(ensure_capacity(ctx, &g->d_bricks, &g->d_bricks_cap, std::max<size_t>(g->bricks.size(), 512)));
+    if (g->d_bricks_cap != old_cap) std::fill(g->brick_dirty.begin(), g->brick_dirty.end(), 1);  // reallocated
+    DL_TRY(h2d(ctx, g->d_top, g->top.data(), g->top.size()));
+    DL_TRY(h2d(ctx, g->d_nodes, g->nodes.data(), g->nodes.size()));
+    g->structure_dirty = false;
+  }
+  // upload dirty bricks, coalescing runs of consecutive dirty bricks into one copy
+  size_t b = 0;
+  while (b < nbricks) {
+    if (!g->brick_dirty[b]) { ++b; continue; }
+    size_t e = b;
+    while (e < nbricks && g->brick_dirty[e]) g->brick_dirty[e++] = 0;
+    DL_TRY(h2d(ctx, g->d_bricks + b * 512, g->bricks.data() + b * 512, (e - b) * 512));
+    b = e;
+  }
+  return sync(ctx);
+}
+
+int dl_grid_lookup(dl_context* ctx, const dl_grid* g, int64_t n, const int32_t* xyz, uint16_t* value_out) {
+  if (!ctx || !g || n < 0 || (n > 0 && (!xyz || !value_out))) return DL_ERR_ARG;
+  if (g->structure_dirty) return ctx->fail(DL_ERR_ARG, "dl_grid_sync not called after dl_grid_set_cells");
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  DL_TRY(ctx->reserve_device(arena_bytes({(size_t)n * 12, (size_t)n * 2})));
+  Arena a(ctx->d_scratch);
+  int32_t* d_xyz = a.take<int32_t>(3 * n);
+  uint16_t* d_out = a.take<uint16_t>(n);
+  DL_TRY(h2d(ctx, d_xyz, xyz, 3 * n));
+  DL_TRY(launch_grid_lookup(ctx, g->view(), n, d_xyz, d_out));
+  DL_TRY(d2h(ctx, value_out, d_out, n));
+  return sync(ctx);
+}
+
+int dl_grid_interpolate(dl_context* ctx, const dl_grid* g, int64_t n, const double* xyz, double* out) {
+  if (!ctx || !g || n < 0 || (n > 0 && (!xyz || !out))) return DL_ERR_ARG;
+  if (g->structure_dirty) return ctx->fail(DL_ERR_ARG, "dl_grid_sync not called after dl_grid_set_cells");
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  DL_TRY(ctx->reserve_device(arena_bytes({(size_t)n * 24, (size_t)n * 32})));
+  Arena a(ctx->d_scratch);
+  double* d_xyz = a.take<double>(3 * n);
+  double* d_out = a.take<double>(4 * n);
+  DL_TRY(h2d(ctx, d_xyz, xyz, 3 * n));
+  DL_TRY(launch_interpolate(ctx, g->view(), n, d_xyz, d_out));
+  DL_TRY(d2h(ctx, out, d_out, 4 * n));
+  return sync(ctx);
+}
+
+// ------------------------------------------------------------------------------------------------ voxel filters
+int dl_voxel_indices(dl_context* ctx, const float* points, int64_t n, int stride, float resolution, int32_t* out) {
+  if (!ctx || n < 0 || stride < 3 || !(resolution > 0.f) || (n > 0 && (!points || !out))) return DL_ERR_ARG;
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  DL_TRY(ctx->reserve_device(arena_bytes({(size_t)n * stride * 4, (size_t)n * 12})));
+  Arena a(ctx->d_scratch);
+  float* d_pts = a.take<float>(n * stride);
+  int32_t* d_out = a.take<int32_t>(3 * n);
+  DL_TRY(h2d(ctx, d_pts, points, n * stride));
+  DL_TRY(launch_voxel_indices(ctx, d_pts, stride, n, resolution, d_out));
+  DL_TRY(d2h(ctx, out, d_out, 3 * n));
+  return sync(ctx);
+}
+
+int dl_voxel_filter(dl_context* ctx, const float* points, int64_t n, int stride, float resolution, int64_t* keep_out,
+                    int64_t* n_keep) {
+  if (!ctx || n < 0 || stride < 3 || !(resolution > 0.f) || !n_keep || (n > 0 && (!points || !keep_out)))
+    return DL_ERR_ARG;
+  *n_keep = 0;
+  if (n == 0) return DL_OK;
+  if (n > 0x7fffffff) return ctx->fail(DL_ERR_ARG, "more than 2^31-1 points");
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t tcap = next_pow2(2 * n);
+  const int tiles = (int)((n + 255) / 256);
+  DL_TRY(ctx->reserve_device(arena_bytes({(size_t)n * stride * 4, (size_t)tcap * 4, (size_t)n * 4, (size_t)n * 4,
+                                          (size_t)tiles * 4, 64})));
+  Arena a(ctx->d_scratch);
+  float* d_pts = a.take<float>(n * stride);
+  uint32_t* d_table = a.take<uint32_t>(tcap);
+  uint32_t* d_slot = a.take<uint32_t>(n);
+  int32_t* d_keep = a.take<int32_t>(n);
+  int32_t* d_blocks = a.take<int32_t>(tiles);
+  int32_t* d_counts = a.take<int32_t>(2);  // [0] = n, [1] = survivors
+  const int32_t n32 = (int32_t)n;
+  DL_TRY(h2d(ctx, d_pts, points, n * stride));
+  DL_TRY(h2d(ctx, d_counts, &n32, 1));
+  DL_TRY(launch_voxel_filter(ctx, d_pts, stride, n, d_counts, 1, resolution, d_table, tcap, d_slot, d_keep, d_counts + 1,
+                             d_blocks));
+  int32_t kept = 0;
+  DL_TRY(d2h(ctx, &kept, d_counts + 1, 1));
+  DL_TRY(sync(ctx));
+  std::vector<int32_t> keep32(kept);
+  DL_TRY(d2h(ctx, keep32.data(), d_keep, kept));
+  DL_TRY(sync(ctx));
+  for (int32_t i = 0; i < kept; ++i) keep_out[i] = keep32[i];
+  *n_keep = kept;
+  return DL_OK;
+}
+
+int dl_adaptive_voxel_filter(dl_context* ctx, const dl_adaptive_voxel_filter_options* options, const float* points,
+                             int64_t n, int stride, int64_t* keep_out, int64_t* n_keep, float* passes_out,
+                             int* n_passes) {
+  if (!ctx || !options || n < 0 || stride < 3 || !n_keep || (n > 0 && (!points || !keep_out))) return DL_ERR_ARG;
+  *n_keep = 0;
+  if (n_passes) *n_passes = 0;
+  if (n == 0) return DL_OK;
+  if (n > 0x7fffffff) return ctx->fail(DL_ERR_ARG, "more than 2^31-1 points");
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t tcap = next_pow2(2 * n);
+  DL_TRY(ctx->reserve_device(arena_bytes({(size_t)n * stride * 4, (size_t)tcap * 4, (size_t)n * 8, (size_t)n * 4, 64,
+                                          sizeof(AdaptiveParams), 32 * 4, 64})));
+  Arena a(ctx->d_scratch);
+  float* d_pts = a.take<float>(n * stride);
+  uint32_t* d_table = a.take<uint32_t>(tcap);
+  uint32_t* d_scratch = a.take<uint32_t>(2 * n);
+  int32_t* d_keep = a.take<int32_t>(n);
+  int32_t* d_counts = a.take<int32_t>(3);  // n, survivors, passes
+  AdaptiveParams* d_params = a.take<AdaptiveParams>(1);
+  float* d_passes = a.take<float>(32);
+  const int32_t n32 = (int32_t)n;
+  const AdaptiveParams params{options->max_length, options->min_num_points, options->max_range};
+  DL_TRY(h2d(ctx, d_pts, points, n * stride));
+  DL_TRY(h2d(ctx, d_counts, &n32, 1));
+  DL_TRY(h2d(ctx, d_params, &params, 1));
+  DL_TRY(launch_adaptive_voxel_filter(ctx, d_pts, stride, n, d_counts, 1, d_params, 1, d_table, tcap, d_scratch, d_keep,
+                                      d_counts + 1, d_passes, d_counts + 2));
+  int32_t res[2] = {0, 0};
+  float passes[32];
+  DL_TRY(d2h(ctx, res, d_counts + 1, 2));
+  DL_TRY(d2h(ctx, passes, d_passes, 32));
+  DL_TRY(sync(ctx));
+  std::vector<int32_t> keep32(res[0]);
+  DL_TRY(d2h(ctx, keep32.data(), d_keep, res[0]));
+  DL_TRY(sync(ctx));
+  for (int32_t i = 0; i < res[0]; ++i) keep_out[i] = keep32[i];
+  *n_keep = res[0];
+  if (n_passes) *n_passes = res[1];
+  if (passes_out) std::memcpy(passes_out, passes, sizeof(float) * std::min(res[1], 32));
+  return DL_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ RT-CSM (host part)
+namespace {
+
+// AngleAxisVectorToRotationQuaternion<float> (C/transform/transform.h:85-99): the cutoff compare and sin/cos run
+// in double, results narrow to float.
+Quatf angle_axis_to_quat(const Vec3f& aa) {
+  float s = 0.5f, w = 1.f;
+  if ((double)dot3(aa, aa) > 1e-8) {
+    const float n = norm3(aa);
+    s = (float)(std::sin((double)n / 2.) / (double)n);
+    w = (float)std::cos((double)n / 2.);
+  }
+  return {w, s * aa.x, s * aa.y, s * aa.z};
+}
+float rotation_angle(const Quatf& q) {  // transform.h:33-37
+  return 2.f * std::atan2(norm3(Vec3f{q.x, q.y, q.z}), std::fabs(q.w));
+}
+
+struct RtcsmTables {
+  int linear = 0, angular = 0;
+  float step = 0.f;
+  std::vector<Quatf> cand_q;
+  std::vector<Vec3f> cand_t;
+  std::vector<double> pen_r, pen_t;
+};
+
+// GenerateExhaustiveSearchTransforms (SM/real_time_correlative_scan_matcher_3d.cc:55-95), factored into the
+// R rotations and L translations it is the outer product of, each composed with the initial pose.
+void build_rtcsm_tables(const dl_rtcsm_options& opt, float resolution, float max_scan_range, const Rigidf& initial,
+                        RtcsmTables* t) {
+  t->linear = (int)std::lround(opt.linear_search_window / resolution);  // double / float -> double
+  const float kSafetyMargin = 1.f - 1e-3f;
+  t->step = kSafetyMargin * std::acos(1.f - (resolution * resolution) / (2.f * (max_scan_range * max_scan_range)));
+  t->angular = (int)std::lround(opt.angular_search_window / t->step);
+  const int L = t->linear, A = t->angular;
+  for (int rz = -A; rz <= A; ++rz)
+    for (int ry = -A; ry <= A; ++ry)
+      for (int rx = -A; rx <= A; ++rx) {
+        const Quatf q = angle_axis_to_quat(Vec3f{rx * t->step, ry * t->step, rz * t->step});
+        t->cand_q.push_back(qnormalized(qmul(initial.q, q)));
+        t->pen_r.push_back(rotation_angle(q) * opt.rotation_delta_cost_weight);
+      }
+  for (int z = -L; z <= L; ++z)
+    for (int y = -L; y <= L; ++y)
+      for (int x = -L; x <= L; ++x) {
+        const Vec3f off{x * resolution, y * resolution, z * resolution};
+        t->cand_t.push_back(add(rotate(initial.q, off), initial.t));
+        t->pen_t.push_back(norm3(off) * opt.translation_delta_cost_weight);
+      }
+}
+
+// Runs the search for a cloud already on the device. Leaves the best pose in pose_out.
+int rtcsm_device(dl_context* ctx, const dl_rtcsm_options& opt, const Rigidd& initial, const float* d_points, int64_t n,
+                 const dl_grid* grid, Arena& a, Rigidd* pose_out, float* score_out, dl_rtcsm_info* info,
+                 float* all_scores_host) {
+  float* d_max = a.take<float>(1);
+  DL_TRY(launch_max_range(ctx, d_points, n, 3.f * grid->resolution, d_max));
+  float max_scan_range = 0.f;
+  DL_TRY(d2h(ctx, &max_scan_range, d_max, 1));
+  DL_TRY(sync(ctx));
+  RtcsmTables t;
+  const Rigidf initial_f = to_float(initial);
+  build_rtcsm_tables(opt, grid->resolution, max_scan_range, initial_f, &t);
+  const int64_t R = (int64_t)t.cand_q.size(), L = (int64_t)t.cand_t.size(), K = R * L;
+  if (K >= 0xFFFFFFFFll) return ctx->fail(DL_ERR_ARG, "more than 2^32-1 correlative candidates");
+  Quatf* d_q = a.take<Quatf>(R);
+  Vec3f* d_t = a.take<Vec3f>(L);
+  double* d_pr = a.take<double>(R);
+  double* d_pt = a.take<double>(L);
+  unsigned long long* d_best = a.take<unsigned long long>(1);
+  float* d_scores = all_scores_host ? a.take<float>(K) : nullptr;
+  if (a.off > ctx->d_scratch_bytes) return ctx->fail(DL_ERR_ARG, "internal: RT-CSM scratch underestimated");
+  DL_TRY(h2d(ctx, d_q, t.cand_q.data(), R));
+  DL_TRY(h2d(ctx, d_t, t.cand_t.data(), L));
+  DL_TRY(h2d(ctx, d_pr, t.pen_r.data(), R));
+  DL_TRY(h2d(ctx, d_pt, t.pen_t.data(), L));
+  DL_CUDA(ctx, cudaMemsetAsync(d_best, 0, sizeof(unsigned long long), ctx->stream));
+  RtcsmLaunch p{d_points, n, d_q, d_t, d_pr, d_pt, R, L, d_scores, d_best};
+  DL_TRY(launch_rtcsm(ctx, grid->view(), p));
+  unsigned long long best = 0;
+  DL_TRY(d2h(ctx, &best, d_best, 1));
+  if (all_scores_host) DL_TRY(d2h(ctx, all_scores_host, d_scores, K));
+  DL_TRY(sync(ctx));
+  if (best == 0) return ctx->fail(DL_ERR_SCORE, "no candidate with a positive score (CHECK_GT(score, 0))");
+  const uint32_t score_bits = (uint32_t)(best >> 32);
+  const int64_t index = (int64_t)(0xFFFFFFFFull - (best & 0xFFFFFFFFull));
+  float score;
+  std::memcpy(&score, &score_bits, 4);
+  const int64_t l = index / R, r = index - l * R;
+  *pose_out = to_double(Rigidf{t.cand_t[l], t.cand_q[r]});
+  if (score_out) *score_out = score;
+  if (info) {
+    info->best_index = index;
+    info->num_candidates = K;
+    info->linear_window = t.linear;
+    info->angular_window = t.angular;
+    info->angular_step = t.step;
+    info->max_scan_range = max_scan_range;
+  }
+  return DL_OK;
+}
+
+// Upper bound of the scratch rtcsm_device needs, from the options alone (max range <= farthest possible point is
+// unknown before the reduction, so bound the angular window by the window / smallest possible step).
+size_t rtcsm_scratch_bound(const dl_rtcsm_options& opt, float resolution, bool scores) {
+  const int L1 = 2 * (int)std::lround(opt.linear_search_window / resolution) + 1;
+  // step >= 0.999 * acos(1 - res^2 / (2 r^2)) with r <= 200 m (beyond any LiDAR the front end accepts)
+  const float r = 200.f;
+  const float step = 0.999f * std::acos(1.f - (resolution * resolution) / (2.f * r * r));
+  const int A1 = 2 * (int)std::lround(opt.angular_search_window / step) + 1;
+  const size_t R = (size_t)A1 * A1 * A1, L = (size_t)L1 * L1 * L1;
+  return arena_bytes({64, R * 16, L * 12, R * 8, L * 8, 64, scores ? R * L * 4 : 0}) + 4096;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dl_rtcsm_match(dl_context* ctx, const dl_rtcsm_options* options, const double* initial_pose, const float* points,
+                   int64_t n, const dl_grid* grid, double* pose_out, float* score_out, dl_rtcsm_info* info,
+                   float* all_scores) {
+  if (!ctx || !options || !initial_pose || !grid || !pose_out || n < 0 || (n > 0 && !points)) return DL_ERR_ARG;  // CHECK_NOTNULL(pose_estimate)
+  if (n == 0) return ctx->fail(DL_ERR_EMPTY, "empty point cloud");
+  if (grid->structure_dirty) return ctx->fail(DL_ERR_ARG, "dl_grid_sync not called after dl_grid_set_cells");
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  DL_TRY(ctx->reserve_device(arena_bytes({(size_t)n * 12}) + rtcsm_scratch_bound(*options, grid->resolution, all_scores != nullptr)));
+  Arena a(ctx->d_scratch);
+  float* d_pts = a.take<float>(3 * n);
+  DL_TRY(h2d(ctx, d_pts, points, 3 * n));
+  Rigidd best;
+  DL_TRY(rtcsm_device(ctx, *options, pose_from7(initial_pose), d_pts, n, grid, a, &best, score_out, info, all_scores));
+  pose_to7(best, pose_out);
+  return DL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ Ceres-equivalent matcher
+static int check_ceres_options(dl_context* ctx, const dl_ceres_options* o, int num_pairs) {
+  if (!o) return DL_ERR_ARG;
+  if (num_pairs < 1 || num_pairs > DL_MAX_PAIRS) return ctx->fail(DL_ERR_ARG, "num_pairs out of range");
+  if (o->num_occupied_space_weights != num_pairs)
+    return ctx->fail(DL_ERR_ARG, "occupied_space_weight count != number of (cloud, grid) pairs (CHECK_EQ)");
+  for (int i = 0; i < num_pairs; ++i)
+    if (!(o->occupied_space_weight[i] > 0.)) return ctx->fail(DL_ERR_ARG, "occupied_space_weight must be > 0 (CHECK_GT)");
+  if (o->max_num_iterations <= 0) return ctx->fail(DL_ERR_ARG, "max_num_iterations must be > 0 (CHECK_GT)");
+  return DL_OK;
+}
+static NlsOptions to_nls_options(const dl_ceres_options& o, int num_pairs) {
+  NlsOptions n{};
+  n.num_pairs = num_pairs;
+  for (int i = 0; i < num_pairs; ++i) n.occ_weight[i] = o.occupied_space_weight[i];
+  n.trans_weight = o.translation_weight;
+  n.rot_weight = o.rotation_weight;
+  n.only_yaw = o.only_optimize_yaw;
+  n.nonmono = o.use_nonmonotonic_steps;
+  n.max_iter = o.max_num_iterations;
+  return n;
+}
+
+int dl_ceres_match_batch(dl_context* ctx, const dl_ceres_options* options, int32_t count, int32_t num_pairs,
+                         const double* target_translations, const double* initial_poses, const float* const* clouds,
+                         const int64_t* sizes, const dl_grid* const* grids, double* poses_out,
+                         dl_solve_summary* summaries) {
+  if (!ctx) return DL_ERR_ARG;
+  DL_TRY(check_ceres_options(ctx, options, num_pairs));
+  if (count < 0 || (count > 0 && (!target_translations || !initial_poses || !clouds || !sizes || !grids || !poses_out)))
+    return DL_ERR_ARG;
+  if (count == 0) return DL_OK;
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t total_points = 0;
+  for (int i = 0; i < count * num_pairs; ++i) {
+    if (sizes[i] < 0 || !grids[i] || (sizes[i] > 0 && !clouds[i])) return DL_ERR_ARG;
+    if (sizes[i] == 0) return ctx->fail(DL_ERR_EMPTY, "empty point cloud");
+    if (grids[i]->structure_dirty) return ctx->fail(DL_ERR_ARG, "dl_grid_sync not called after dl_grid_set_cells");
+    total_points += (size_t)sizes[i];
+  }
+  DL_TRY(ctx->reserve_device(arena_bytes({total_points * 12 + (size_t)count * num_pairs * 256,
+                                          (size_t)count * sizeof(NlsProblem), (size_t)count * sizeof(NlsOutput)})));
+  Arena a(ctx->d_scratch);
+  std::vector<NlsProblem> problems(count);
+  for (int c = 0; c < count; ++c) {
+    NlsProblem& p = problems[c];
+    std::memset(&p, 0, sizeof(p));
+    for (int k = 0; k < num_pairs; ++k) {
+      const int i = c * num_pairs + k;
+      float* d = a.take<float>(3 * sizes[i]);
+      DL_TRY(h2d(ctx, d, clouds[i], 3 * sizes[i]));
+      p.cloud[k] = d;
+      p.count[k] = (int32_t)sizes[i];
+      p.grid[k] = grids[i]->view();
+    }
+    for (int j = 0; j < 3; ++j) p.target_t[j] = target_translations[3 * c + j];
+    for (int j = 0; j < 7; ++j) p.initial[j] = initial_poses[7 * c + j];
+  }
+  NlsProblem* d_problems = a.take<NlsProblem>(count);
+  NlsOutput* d_out = a.take<NlsOutput>(count);
+  DL_TRY(h2d(ctx, d_problems, problems.data(), count));
+  DL_TRY(launch_nls(ctx, to_nls_options(*options, num_pairs), d_problems, count, d_out));
+  std::vector<NlsOutput> out(count);
+  DL_TRY(d2h(ctx, out.data(), d_out, count));
+  DL_TRY(sync(ctx));
+  for (int c = 0; c < count; ++c) {
+    std::memcpy(poses_out + 7 * c, out[c].pose, 7 * sizeof(double));
+    if (summaries) summaries[c] = out[c].summary;
+  }
+  return DL_OK;
+}
+
+int dl_ceres_match(dl_context* ctx, const dl_ceres_options* options, const double* target_translation,
+                   const double* initial_pose, int32_t num_pairs, const float* const* clouds, const int64_t* sizes,
+                   const dl_grid* const* grids, double* pose_out, dl_solve_summary* summary) {
+  return dl_ceres_match_batch(ctx, options, 1, num_pairs, target_translation, initial_pose, clouds, sizes, grids,
+                              pose_out, summary);
+}
+
+int dl_ceres_normal_equations(dl_context* ctx, const dl_ceres_options* options, const double* target_translation,
+                              const double* reference_pose, const double* at_pose, int32_t num_pairs,
+                              const float* const* clouds, const int64_t* sizes, const dl_grid* const* grids,
+                              double* cost, double* gradient6, double* hessian36) {
+  if (!ctx) return DL_ERR_ARG;
+  DL_TRY(check_ceres_options(ctx, options, num_pairs));
+  if (!target_translation || !reference_pose || !at_pose || !clouds || !sizes || !grids || !cost || !gradient6 || !hessian36)
+    return DL_ERR_ARG;
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t total_points = 0;
+  for (int i = 0; i < num_pairs; ++i) total_points += (size_t)sizes[i];
+  DL_TRY(ctx->reserve_device(arena_bytes({total_points * 12 + (size_t)num_pairs * 256, sizeof(NlsProblem), 64, 28 * 8})));
+  Arena a(ctx->d_scratch);
+  NlsProblem p;
+  std::memset(&p, 0, sizeof(p));
+  for (int k = 0; k < num_pairs; ++k) {
+    float* d = a.take<float>(3 * sizes[k]);
+    DL_TRY(h2d(ctx, d, clouds[k], 3 * sizes[k]));
+    p.cloud[k] = d;
+    p.count[k] = (int32_t)sizes[k];
+    p.grid[k] = grids[k]->view();
+  }
+  for (int j = 0; j < 3; ++j) p.target_t[j] = target_translation[j];
+  for (int j = 0; j < 7; ++j) p.initial[j] = reference_pose[j];
+  NlsProblem* d_p = a.take<NlsProblem>(1);
+  double* d_at = a.take<double>(7);
+  double* d_out = a.take<double>(28);
+  DL_TRY(h2d(ctx, d_p, &p, 1));
+  DL_TRY(h2d(ctx, d_at, at_pose, 7));
+  DL_TRY(launch_nls_normal_equations(ctx, to_nls_options(*options, num_pairs), d_p, d_at, d_out));
+  double out[28];
+  DL_TRY(d2h(ctx, out, d_out, 28));
+  DL_TRY(sync(ctx));
+  *cost = out[0];
+  for (int i = 0; i < 6; ++i) gradient6[i] = out[1 + i];
+  int t = 7;
+  for (int r = 0; r < 6; ++r)
+    for (int c = r; c < 6; ++c) hessian36[r * 6 + c] = hessian36[c * 6 + r] = out[t++];
+  return DL_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ batched front end
+namespace {
+
+struct FrontendBuffers {
+  int batch = 0;
+  int64_t cap = 0, tcap = 0;
+  int tiles = 0;
+  int32_t *counts0, *n1, *n_ret, *n_miss, *n2, *n3, *countsA, *npassesA, *block_counts, *tile_counts;
+  uint32_t *table, *slot, *tableA, *scratchA;
+  int32_t *keep1, *keep2, *keep3, *keepA;
+  float *tmp_points, *returns_local, *misses_local, *returns_tracking, *misses_tracking, *clouds, *current_pose, *origins,
+      *passesA, *rtcsm_scores;
+  uint8_t* cls;
+  ScanConstants* scans;
+  AdaptiveParams* filters;
+  double *initial_pose, *target;
+  NlsProblem* problems;
+  NlsOutput* nls_out;
+};
+
+size_t frontend_bytes(int batch, int64_t cap, int num_origins, size_t extra) {
+  const size_t B = (size_t)batch, C = (size_t)cap;
+  const size_t tcap = (size_t)next_pow2(2 * cap);
+  const size_t tiles = (C + 255) / 256;
+  return arena_bytes({B * 4, B * 4, B * 4, B * 4, B * 4, B * 4, B * 8, B * 8, B * tiles * 4, B * tiles * 8,
+                      B * tcap * 4, B * C * 4, B * 2 * tcap * 4, B * 4 * C * 4,
+                      B * C * 4, B * C * 4, B * C * 4, B * 2 * C * 4,
+                      B * C * 12, B * C * 12, B * C * 12, B * C * 12, B * C * 12, B * 2 * C * 12, B * 28, (size_t)num_origins * 12,
+                      B * 2 * 32 * 4, B * 4, B * C, B * sizeof(ScanConstants), 2 * sizeof(AdaptiveParams), B * 56, B * 24,
+                      B * sizeof(NlsProblem), B * sizeof(NlsOutput)}) + extra + 8192;
+}
+
+void carve(Arena& a, int batch, int64_t cap, int num_origins, FrontendBuffers* f) {
+  const size_t B = (size_t)batch, C = (size_t)cap;
+  f->batch = batch;
+  f->cap = cap;
+  f->tcap = next_pow2(2 * cap);
+  f->tiles = (int)((cap + 255) / 256);
+  f->counts0 = a.take<int32_t>(B); f->n1 = a.take<int32_t>(B); f->n_ret = a.take<int32_t>(B); f->n_miss = a.take<int32_t>(B);
+  f->n2 = a.take<int32_t>(B); f->n3 = a.take<int32_t>(B); f->countsA = a.take<int32_t>(2 * B); f->npassesA = a.take<int32_t>(2 * B);
+  f->block_counts = a.take<int32_t>(B * f->tiles); f->tile_counts = a.take<int32_t>(B * f->tiles * 2);
+  f->table = a.take<uint32_t>(B * f->tcap); f->slot = a.take<uint32_t>(B * C);
+  f->tableA = a.take<uint32_t>(B * 2 * f->tcap); f->scratchA = a.take<uint32_t>(B * 4 * C);
+  f->keep1 = a.take<int32_t>(B * C); f->keep2 = a.take<int32_t>(B * C); f->keep3 = a.take<int32_t>(B * C);
+  f->keepA = a.take<int32_t>(B * 2 * C);
+  f->tmp_points = a.take<float>(B * C * 3); f->returns_local = a.take<float>(B * C * 3); f->misses_local = a.take<float>(B * C * 3);
+  f->returns_tracking = a.take<float>(B * C * 3); f->misses_tracking = a.take<float>(B * C * 3);
+  f->clouds = a.take<float>(B * 2 * C * 3); f->current_pose = a.take<float>(B * 7); f->origins = a.take<float>((size_t)num_origins * 3);
+  f->passesA = a.take<float>(B * 2 * 32); f->rtcsm_scores = a.take<float>(B);
+  f->cls = a.take<uint8_t>(B * C);
+  f->scans = a.take<ScanConstants>(B); f->filters = a.take<AdaptiveParams>(2);
+  f->initial_pose = a.take<double>(B * 7); f->target = a.take<double>(B * 3);
+  f->problems = a.take<NlsProblem>(B); f->nls_out = a.take<NlsOutput>(B);
+}
+
+// Per-scan constants of the deskew (LTB:426-428 and the scan-constant half of Eigen's slerp), host double math.
+ScanConstants make_scan_constants(const double* prev7, const double* cur7) {
+  ScanConstants c;
+  c.prev = pose_from7(prev7);
+  c.cur = pose_from7(cur7);
+  c.rel = compose(inverse(c.prev), c.cur);
+  const double d = (0.0 * c.rel.q.x + 0.0 * c.rel.q.y) + (0.0 * c.rel.q.z + 1.0 * c.rel.q.w);  // Identity.dot(rel.q)
+  const double abs_d = std::fabs(d);
+  const double one = 1.0 - 2.220446049250313e-16;
+  c.linear_slerp = abs_d >= one;
+  c.negative_dot = d < 0;
+  c.theta = c.linear_slerp ? 0.0 : std::acos(abs_d);
+  c.sin_theta = c.linear_slerp ? 1.0 : std::sin(c.theta);
+  return c;
+}
+
+// Stages 1-3: first voxel filter, deskew/transform/gate, second voxel filters, back to the tracking frame.
+int frontend_ingest(dl_context* ctx, const dl_frontend_options& o, const FrontendBuffers& f, const float* d_ranges,
+                    int64_t in_cap) {
+  DL_TRY(launch_voxel_filter(ctx, d_ranges, 8, in_cap, f.counts0, f.batch, 0.5f * o.voxel_filter_size, f.table, f.tcap,
+                             f.slot, f.keep1, f.n1, f.block_counts));
+  IngestArgs ia{};
+  ia.ranges = d_ranges; ia.in_cap = in_cap; ia.scans = f.scans; ia.origins = f.origins; ia.keep = f.keep1;
+  ia.keep_counts = f.n1; ia.cap = f.cap; ia.tiles = f.tiles; ia.min_range = o.min_range; ia.max_range = o.max_range;
+  ia.scan_period = o.scan_period; ia.tmp_points = f.tmp_points; ia.cls = f.cls; ia.tile_counts = f.tile_counts;
+  ia.returns_local = f.returns_local; ia.misses_local = f.misses_local; ia.num_returns = f.n_ret; ia.num_misses = f.n_miss;
+  ia.current_pose = f.current_pose;
+  DL_TRY(launch_ingest(ctx, ia, f.batch));
+  DL_TRY(launch_voxel_filter(ctx, f.returns_local, 3, f.cap, f.n_ret, f.batch, o.voxel_filter_size, f.table, f.tcap, f.slot,
+                             f.keep2, f.n2, f.block_counts));
+  DL_TRY(launch_gather_to_tracking(ctx, f.returns_local, f.cap, f.keep2, f.n2, f.current_pose, f.returns_tracking, f.batch));
+  DL_TRY(launch_voxel_filter(ctx, f.misses_local, 3, f.cap, f.n_miss, f.batch, o.voxel_filter_size, f.table, f.tcap, f.slot,
+                             f.keep3, f.n3, f.block_counts));
+  DL_TRY(launch_gather_to_tracking(ctx, f.misses_local, f.cap, f.keep3, f.n3, f.current_pose, f.misses_tracking, f.batch));
+  return DL_OK;
+}
+
+// Uploads the small per-call tables (counts, deskew constants, origins, filter options).
+int frontend_upload_small(dl_context* ctx, const dl_frontend_options& o, const FrontendBuffers& f, const int64_t* sizes,
+                          const float* origins, int num_origins, const double* prev_poses, const double* cur_poses) {
+  std::vector<int32_t> counts(f.batch);
+  std::vector<ScanConstants> sc(f.batch);
+  for (int b = 0; b < f.batch; ++b) {
+    counts[b] = (int32_t)sizes[b];
+    sc[b] = make_scan_constants(prev_poses + 7 * b, cur_poses + 7 * b);
+  }
+  const AdaptiveParams filt[2] = {
+      {o.high_resolution_adaptive_voxel_filter.max_length, o.high_resolution_adaptive_voxel_filter.min_num_points,
+       o.high_resolution_adaptive_voxel_filter.max_range},
+      {o.low_resolution_adaptive_voxel_filter.max_length, o.low_resolution_adaptive_voxel_filter.min_num_points,
+       o.low_resolution_adaptive_voxel_filter.max_range}};
+  DL_TRY(h2d(ctx, f.counts0, counts.data(), f.batch));
+  DL_TRY(h2d(ctx, f.scans, sc.data(), f.batch));
+  DL_TRY(h2d(ctx, f.origins, origins, (size_t)num_origins * 3));
+  DL_TRY(h2d(ctx, f.filters, filt, 2));
+  return sync(ctx);  // the staging vectors go out of scope
+}
+
+int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, const float* d_ranges, int64_t in_cap,
+                 const int64_t* sizes, const float* origins, int num_origins, const double* prev_poses,
+                 const double* cur_poses, const double* submap_local_pose, const dl_grid* hi, const dl_grid* lo,
+                 Arena& a, dl_scan_result* d_results) {
+  FrontendBuffers f;
+  carve(a, num_scans, in_cap, num_origins, &f);
+  DL_TRY(frontend_upload_small(ctx, o, f, sizes, origins, num_origins, prev_poses, cur_poses));
+  DL_TRY(frontend_ingest(ctx, o, f, d_ranges, in_cap));
+  // adaptive voxel filters (high, low resolution) on the tracking-frame returns: one CTA per (scan, filter)
+  DL_TRY(launch_adaptive_voxel_filter(ctx, f.returns_tracking, 3, f.cap, f.n2, f.batch, f.filters, 2, f.tableA, f.tcap,
+                                      f.scratchA, f.keepA, f.countsA, f.passesA, f.npassesA));
+  DL_TRY(launch_gather_rows(ctx, f.returns_tracking, f.cap, 2, f.keepA, f.countsA, f.cap, f.clouds, 2 * f.batch));
+  const Rigidd submap = pose_from7(submap_local_pose);
+  DL_TRY(launch_initial_pose(ctx, f.batch, f.current_pose, inverse(submap), f.initial_pose, f.target));
+  bool have_scores = false;
+  if (o.use_online_correlative_scan_matching) {
+    // The angular window depends on the farthest point of each cloud through acosf, which must be the host's to
+    // stay bit-exact, so this optional stage synchronises once per scan.
+    std::vector<int32_t> countsA(2 * f.batch);
+    std::vector<double> init(7 * f.batch);
+    DL_TRY(d2h(ctx, countsA.data(), f.countsA, 2 * f.batch));
+    DL_TRY(d2h(ctx, init.data(), f.initial_pose, 7 * f.batch));
+    DL_TRY(sync(ctx));
+    std::vector<float> scores(f.batch, 0.f);
+    const size_t mark = a.off;
+    for (int b = 0; b < f.batch; ++b) {
+      if (countsA[2 * b] <= 0) continue;
+      a.off = mark;
+      Rigidd best;
+      DL_TRY(rtcsm_device(ctx, o.real_time_correlative_scan_matcher, pose_from7(init.data() + 7 * b),
+                          f.clouds + (size_t)(2 * b) * f.cap * 3, countsA[2 * b], hi, a, &best, &scores[b], nullptr, nullptr));
+      pose_to7(best, init.data() + 7 * b);
+    }
+    DL_TRY(h2d(ctx, f.initial_pose, init.data(), 7 * f.batch));
+    DL_TRY(h2d(ctx, f.rtcsm_scores, scores.data(), f.batch));
+    DL_TRY(sync(ctx));
+    have_scores = true;
+  }
+  std::vector<NlsProblem> problems(f.batch);
+  for (int b = 0; b < f.batch; ++b) {
+    NlsProblem& p = problems[b];
+    std::memset(&p, 0, sizeof(p));
+    for (int k = 0; k < 2; ++k) {
+      p.cloud[k] = f.clouds + (size_t)(2 * b + k) * f.cap * 3;
+      p.count_dev[k] = f.countsA + 2 * b + k;
+      p.grid[k] = k == 0 ? hi->view() : lo->view();
+    }
+    p.initial_dev = f.initial_pose + 7 * b;
+    p.target_dev = f.target + 3 * b;
+  }
+  DL_TRY(h2d(ctx, f.problems, problems.data(), f.batch));
+  DL_TRY(sync(ctx));
+  DL_TRY(launch_nls(ctx, to_nls_options(o.ceres_scan_matcher, 2), f.problems, f.batch, f.nls_out));
+  ResultArgs ra{};
+  ra.batch = f.batch; ra.first_counts = f.n1; ra.return_counts = f.n2; ra.miss_counts = f.n3; ra.adaptive_counts = f.countsA;
+  ra.rtcsm_scores = have_scores ? f.rtcsm_scores : nullptr; ra.nls = f.nls_out; ra.submap = submap; ra.results = d_results;
+  DL_TRY(launch_finalize_results(ctx, ra));
+  return DL_OK;
+}
+
+int check_frontend(dl_context* ctx, const dl_frontend_options* o, int num_scans, const int64_t* sizes,
+                   const dl_grid* hi, const dl_grid* lo, int64_t* max_size) {
+  if (!o || num_scans < 0 || !hi || !lo || (num_scans > 0 && !sizes)) return DL_ERR_ARG;
+  DL_TRY(check_ceres_options(ctx, &o->ceres_scan_matcher, 2));
+  if (hi->structure_dirty || lo->structure_dirty) return ctx->fail(DL_ERR_ARG, "dl_grid_sync not called after dl_grid_set_cells");
+  int64_t m = 0;
+  for (int b = 0; b < num_scans; ++b) {
+    if (sizes[b] < 0 || sizes[b] > 0x3fffffff) return ctx->fail(DL_ERR_ARG, "scan size out of range");
+    m = std::max(m, sizes[b]);
+  }
+  *max_size = m;
+  return DL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dl_frontend_match_batch_dev(dl_context* ctx, const dl_frontend_options* options, int32_t num_scans,
+                                const void* ranges_dev, int64_t cap_rows, const int64_t* sizes, const float* origins,
+                                int32_t num_origins, const double* prev_poses, const double* predicted_poses,
+                                const double* submap_local_pose, const dl_grid* hi, const dl_grid* lo,
+                                dl_scan_result* results_dev) {
+  if (!ctx) return DL_ERR_ARG;
+  int64_t max_size = 0;
+  DL_TRY(check_frontend(ctx, options, num_scans, sizes, hi, lo, &max_size));
+  if (num_scans == 0) return DL_OK;
+  if (!ranges_dev || !origins || num_origins < 1 || !prev_poses || !predicted_poses || !submap_local_pose || !results_dev ||
+      cap_rows < max_size || cap_rows < 1)
+    return DL_ERR_ARG;
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t extra = options->use_online_correlative_scan_matching
+                           ? rtcsm_scratch_bound(options->real_time_correlative_scan_matcher, hi->resolution, false) : 0;
+  DL_TRY(ctx->reserve_device(frontend_bytes(num_scans, cap_rows, num_origins, extra)));
+  Arena a(ctx->d_scratch);
+  return frontend_run(ctx, *options, num_scans, (const float*)ranges_dev, cap_rows, sizes, origins, num_origins, prev_poses,
+                      predicted_poses, submap_local_pose, hi, lo, a, results_dev);
+}
+
+int dl_frontend_fetch_results(dl_context* ctx, const dl_scan_result* results_dev, int32_t num_scans,
+                              dl_scan_result* results) {
+  if (!ctx || num_scans < 0 || (num_scans > 0 && (!results_dev || !results))) return DL_ERR_ARG;
+  DL_TRY(d2h(ctx, results, results_dev, num_scans));
+  return sync(ctx);
+}
+
+int dl_frontend_match_batch(dl_context* ctx, const dl_frontend_options* options, int32_t num_scans,
+                            const void* const* ranges, const int64_t* sizes, const float* origins, int32_t num_origins,
+                            const double* prev_poses, const double* predicted_poses, const double* submap_local_pose,
+                            const dl_grid* hi, const dl_grid* lo, dl_scan_result* results) {
+  if (!ctx) return DL_ERR_ARG;
+  int64_t max_size = 0;
+  DL_TRY(check_frontend(ctx, options, num_scans, sizes, hi, lo, &max_size));
+  if (num_scans == 0) return DL_OK;
+  if (!ranges || !origins || num_origins < 1 || !prev_poses || !predicted_poses || !submap_local_pose || !results)
+    return DL_ERR_ARG;
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t cap = std::max<int64_t>(max_size, 1);
+  const size_t extra = options->use_online_correlative_scan_matching
+                           ? rtcsm_scratch_bound(options->real_time_correlative_scan_matcher, hi->resolution, false) : 0;
+  DL_TRY(ctx->reserve_device(frontend_bytes(num_scans, cap, num_origins, extra) + (size_t)num_scans * cap * 32 + 256 +
+                             (size_t)num_scans * sizeof(dl_scan_result) + 256));
+  Arena a(ctx->d_scratch);
+  float* d_ranges = a.take<float>((size_t)num_scans * cap * 8);
+  dl_scan_result* d_results = a.take<dl_scan_result>(num_scans);
+  for (int b = 0; b < num_scans; ++b) {
+    if (sizes[b] > 0 && !ranges[b]) return DL_ERR_ARG;
+    DL_TRY(h2d(ctx, d_ranges + (size_t)b * cap * 8, (const float*)ranges[b], (size_t)sizes[b] * 8));
+  }
+  DL_TRY(frontend_run(ctx, *options, num_scans, d_ranges, cap, sizes, origins, num_origins, prev_poses, predicted_poses,
+                      submap_local_pose, hi, lo, a, d_results));
+  DL_TRY(d2h(ctx, results, d_results, num_scans));
+  return sync(ctx);
+}
+
+int dl_ingest_scan(dl_context* ctx, const dl_frontend_options* options, const void* ranges, int64_t n,
+                   const float* origins, int32_t num_origins, const double* prev_pose, const double* predicted_pose,
+                   int64_t* first_keep_out, float* returns_local_out, float* returns_tracking_out,
+                   float* misses_tracking_out, float* current_pose7f_out, int64_t* counts_out) {
+  if (!ctx || !options || !ranges || n < 1 || n > 0x3fffffff || !origins || num_origins < 1 || !prev_pose || !predicted_pose ||
+      !counts_out)
+    return DL_ERR_ARG;
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  DL_TRY(ctx->reserve_device(frontend_bytes(1, n, num_origins, 0) + (size_t)n * 32 + 256));
+  Arena a(ctx->d_scratch);
+  float* d_ranges = a.take<float>((size_t)n * 8);
+  DL_TRY(h2d(ctx, d_ranges, (const float*)ranges, (size_t)n * 8));
+  FrontendBuffers f;
+  carve(a, 1, n, num_origins, &f);
+  DL_TRY(frontend_upload_small(ctx, *options, f, &n, origins, num_origins, prev_pose, predicted_pose));
+  DL_TRY(frontend_ingest(ctx, *options, f, d_ranges, n));
+  int32_t c[4];
+  DL_TRY(d2h(ctx, &c[0], f.n1, 1));
+  DL_TRY(d2h(ctx, &c[1], f.n_ret, 1));
+  DL_TRY(d2h(ctx, &c[2], f.n2, 1));
+  DL_TRY(d2h(ctx, &c[3], f.n3, 1));
+  DL_TRY(sync(ctx));
+  for (int i = 0; i < 4; ++i) counts_out[i] = c[i];
+  std::vector<int32_t> keep32(c[0]);
+  DL_TRY(d2h(ctx, keep32.data(), f.keep1, c[0]));
+  if (returns_local_out) DL_TRY(d2h(ctx, returns_local_out, f.returns_local, (size_t)c[1] * 3));
+  if (returns_tracking_out) DL_TRY(d2h(ctx, returns_tracking_out, f.returns_tracking, (size_t)c[2] * 3));
+  if (misses_tracking_out) DL_TRY(d2h(ctx, misses_tracking_out, f.misses_tracking, (size_t)c[3] * 3));
+  if (current_pose7f_out) DL_TRY(d2h(ctx, current_pose7f_out, f.current_pose, 7));
+  DL_TRY(sync(ctx));
+  if (first_keep_out)
+    for (int i = 0; i < c[0]; ++i) first_keep_out[i] = keep32[i];
+  return DL_OK;
+}
+
+}  // extern "C"

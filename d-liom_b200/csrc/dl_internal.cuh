@@ -1,0 +1,182 @@
+// Internal declarations shared by the translation units of libdliom_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/dliom_b200.h"
+#include "dl_math.cuh"
+
+namespace dl {
+
+constexpr int kNumSMs = 148;  // B200
+
+// ------------------------------------------------------------------------------------------------ device grid
+// Index-array form of HybridGrid's three levels (hybrid_grid.h:411-412): top cell = 64^3 voxels
+// (DynamicGrid meta cell), node = 8^3 bricks (NestedGrid), brick = 8^3 uint16 voxels, z-major (FlatGrid).
+// A brick is 1 KiB and 1 KiB-aligned in HBM, so a whole brick is one bulk-copy unit.
+struct GridView {
+  const int32_t* __restrict__ top;    // (1 << bits)^3 entries -> node index, -1 = absent
+  const int32_t* __restrict__ nodes;  // num_nodes * 512 entries -> brick index, -1 = absent
+  const uint16_t* __restrict__ bricks;  // num_bricks * 512 voxels
+  float resolution;
+  int bits;
+};
+
+// HybridGrid::value(): origin shift by grid_size/2, unsigned bounds test, three dependent reads.
+__device__ __forceinline__ uint16_t grid_value(const GridView& g, int x, int y, int z) {
+  const int gs = 64 << g.bits;
+  const int half = gs >> 1;
+  const unsigned sx = (unsigned)(x + half), sy = (unsigned)(y + half), sz = (unsigned)(z + half);
+  if (sx >= (unsigned)gs || sy >= (unsigned)gs || sz >= (unsigned)gs) return 0;
+  const int node = __ldg(g.top + ((((sz >> 6) << g.bits) + (sy >> 6)) << g.bits) + (sx >> 6));
+  if (node < 0) return 0;
+  const int brick = __ldg(g.nodes + (size_t)node * 512 + ((((sz >> 3) & 7) << 6) | (((sy >> 3) & 7) << 3) | ((sx >> 3) & 7)));
+  if (brick < 0) return 0;
+  return __ldg(g.bricks + (size_t)brick * 512 + (((sz & 7) << 6) | ((sy & 7) << 3) | (sx & 7)));
+}
+
+}  // namespace dl
+
+// ------------------------------------------------------------------------------------------------ handles
+struct dl_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string error;
+  int64_t launches = 0;
+  // growable scratch arenas (device + pinned host), reused across calls
+  void* d_scratch = nullptr;
+  size_t d_scratch_bytes = 0;
+  void* h_pinned = nullptr;
+  size_t h_pinned_bytes = 0;
+
+  int fail(int status, const std::string& msg) {
+    error = msg;
+    return status;
+  }
+  int cuda_fail(cudaError_t e, const char* what) {
+    error = std::string(what) + ": " + cudaGetErrorString(e);
+    return DL_ERR_CUDA;
+  }
+  int reserve_device(size_t bytes);
+  int reserve_pinned(size_t bytes);
+};
+
+struct dl_grid {
+  dl_context* ctx = nullptr;
+  float resolution = 0.f;
+  int bits = 1;
+  // host mirror of the three levels
+  std::vector<int32_t> top;                 // (1<<bits)^3
+  std::vector<int32_t> nodes;               // num_nodes * 512
+  std::vector<uint16_t> bricks;             // num_bricks * 512
+  std::vector<uint8_t> brick_dirty;         // per brick
+  bool structure_dirty = true;
+  // device copies
+  int32_t* d_top = nullptr;
+  int32_t* d_nodes = nullptr;
+  uint16_t* d_bricks = nullptr;
+  size_t d_top_cap = 0, d_nodes_cap = 0, d_bricks_cap = 0;  // element capacities
+  dl::GridView view() const { return {d_top, d_nodes, d_bricks, resolution, bits}; }
+};
+
+#define DL_CUDA(ctx, call)                                  \
+  do {                                                      \
+    cudaError_t e__ = (call);                               \
+    if (e__ != cudaSuccess) return (ctx)->cuda_fail(e__, #call); \
+  } while (0)
+
+#define DL_LAUNCH_CHECK(ctx, name)                          \
+  do {                                                      \
+    (ctx)->launches++;                                      \
+    cudaError_t e__ = cudaGetLastError();                   \
+    if (e__ != cudaSuccess) return (ctx)->cuda_fail(e__, name); \
+  } while (0)
+
+namespace dl {
+
+struct Arena {  // bump allocator over the context's device scratch
+  char* base;
+  size_t off = 0;
+  explicit Arena(void* p) : base((char*)p) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = (off + 255) & ~size_t(255);
+    T* p = (T*)(base + off);
+    off += count * sizeof(T);
+    return p;
+  }
+};
+inline size_t arena_bytes(std::initializer_list<size_t> sizes) {
+  size_t t = 0;
+  for (size_t s : sizes) t = ((t + 255) & ~size_t(255)) + s;
+  return t + 256;
+}
+
+// ---- kernel launchers (each defined in its own .cu), all asynchronous on `stream`, device pointers only.
+
+// Voxel filter over `batch` clouds. Cloud b = rows [b * cap, b * cap + counts[b]) of `points` (stride floats per row).
+// keep[b * cap ...] receives the surviving row indices (relative to the cloud) in input order, keep_counts[b] their number.
+// table: batch * table_cap uint32 (table_cap a power of two >= 2 * max count); slot: batch * cap uint32.
+int launch_voxel_filter(dl_context* ctx, const float* points, int stride, int64_t cap, const int32_t* counts, int batch,
+                        float resolution, uint32_t* table, int64_t table_cap, uint32_t* slot, int32_t* keep,
+                        int32_t* keep_counts, int32_t* block_counts);
+int launch_voxel_indices(dl_context* ctx, const float* points, int stride, int64_t n, float resolution, int32_t* out);
+
+struct AdaptiveParams {
+  float max_length, min_num_points, max_range;
+};
+// One CTA per (cloud, filter) pair: adaptive bisection entirely on the device.
+// filters: num_filters parameter blocks; outputs indexed [(b * num_filters + f) * cap ...].
+int launch_adaptive_voxel_filter(dl_context* ctx, const float* points, int stride, int64_t cap, const int32_t* counts,
+                                 int batch, const AdaptiveParams* filters_dev, int num_filters, uint32_t* table,
+                                 int64_t table_cap, uint32_t* scratch /* pairs * 2 * cap */, int32_t* keep, int32_t* keep_counts,
+                                 float* passes /* (batch*num_filters) * 32 */, int32_t* num_passes);
+
+struct RtcsmLaunch {
+  const float* points;  // n x 3
+  int64_t n;
+  const Quatf* cand_q;  // R rotations (composed with the initial pose, normalised)
+  const Vec3f* cand_t;  // L translations (composed with the initial pose)
+  const double* pen_r;  // R: angle * rotation_delta_cost_weight
+  const double* pen_t;  // L: |t| * translation_delta_cost_weight
+  int64_t R, L;
+  float* scores;                     // optional, R * L
+  unsigned long long* best_packed;   // (score bits << 32) | ~index
+};
+int launch_rtcsm(dl_context* ctx, const GridView& grid, const RtcsmLaunch& p);
+int launch_max_range(dl_context* ctx, const float* points, int64_t n, float init, float* out);
+
+// ---- NLS
+struct NlsProblem {  // one scan-to-submap registration problem, device pointers
+  const float* cloud[DL_MAX_PAIRS];
+  int32_t count[DL_MAX_PAIRS];
+  const int32_t* count_dev[DL_MAX_PAIRS];  // optional: read the count from device memory instead
+  GridView grid[DL_MAX_PAIRS];
+  double target_t[3];
+  double initial[7];
+  const double* initial_dev;  // optional: 7 doubles on the device override `initial` (and target_t = its translation
+                              // unless target_dev is set)
+  const double* target_dev;
+};
+struct NlsOptions {
+  int num_pairs;
+  double occ_weight[DL_MAX_PAIRS];
+  double trans_weight, rot_weight;
+  int only_yaw, nonmono, max_iter;
+};
+struct NlsOutput {
+  double pose[7];
+  dl_solve_summary summary;
+};
+int launch_nls(dl_context* ctx, const NlsOptions& opt, const NlsProblem* problems_dev, int count, NlsOutput* out_dev);
+int launch_nls_normal_equations(dl_context* ctx, const NlsOptions& opt, const NlsProblem* problems_dev,
+                                const double* at_pose_dev, double* out28_dev);
+int launch_interpolate(dl_context* ctx, const GridView& grid, int64_t n, const double* xyz, double* out);
+int launch_grid_lookup(dl_context* ctx, const GridView& grid, int64_t n, const int32_t* xyz, uint16_t* out);
+
+}  // namespace dl

@@ -1,0 +1,602 @@
+// Point-to-probability-grid nonlinear least squares with the whole Levenberg-Marquardt loop on the device.
+//
+// Replaces CeresScanMatcher3D::Match -> ceres::Solve (SM/ceres_scan_matcher_3d.cc:71-123) for the problem the
+// reference assembles: one OccupiedSpaceCostFunction3D block per (cloud, grid) pair
+// (SM/occupied_space_cost_function_3d.h:46-80, interpolation SM/interpolated_grid.h:50-146), a
+// TranslationDeltaCostFunctor3D and a RotationDeltaCostFunctor3D (SM/*_delta_cost_functor_3d.h), pose parameter
+// blocks t[3], q[4] with ceres::QuaternionParameterization or YawOnlyQuaternionPlus
+// (C/mapping/internal/3d/rotation_parameterization.h:27-39), LM trust region + DENSE_QR, Ceres 1.13 defaults.
+//
+// Design: ONE CTA per registration problem, many problems per launch (the reference solves them one at a time on
+// one thread, or 8 at a time in the loop-closure thread pool). Each evaluation is a single fused pass
+//   transform (fp64) -> float cell selection -> 8 voxel reads -> smoothstep interpolation -> analytic gradient ->
+//   chain rule to the 6 local parameters -> J^T J (21) / J^T r (6) / cost (1) accumulation
+// reduced with warp shuffles in a fixed order (bit-reproducible run to run). The N x 6 Jacobian the reference
+// materialises (N x 7 doubles, then QR) never exists: the normal equations carry everything the LM loop needs —
+// Jacobi scaling, the LM diagonal, the step (6x6 Cholesky of S J^T J S + D^2, algebraically the stacked QR
+// solution), the model cost change and the projected gradient. Candidate points are evaluated speculatively
+// WITH their normal equations, so an accepted step costs one pass instead of Ceres's two (cost-only, then
+// re-evaluation with Jacobians). All accumulation is fp64; cell selection mirrors the reference's float/double
+// mix exactly, so the piecewise-polynomial pieces are the same ones the CPU path picks.
+//
+// Algorithmic bytes: 12 B point + 8 corners * 2 B = 28 B per point per evaluation.
+#include "dl_internal.cuh"
+
+namespace dl {
+namespace {
+
+constexpr int kBlock = 256;
+constexpr int kWarps = kBlock / 32;
+constexpr int kRed = 28;  // cost, g[6], H upper triangle [21]
+
+struct Lm {  // Ceres 1.13 Solver::Options defaults (trust_region_minimizer.cc, levenberg_marquardt_strategy.cc)
+  static constexpr double initial_radius = 1e4, max_radius = 1e16, min_radius = 1e-32;
+  static constexpr double min_relative_decrease = 1e-3, min_lm_diagonal = 1e-6, max_lm_diagonal = 1e32;
+  static constexpr double function_tolerance = 1e-6, gradient_tolerance = 1e-10, parameter_tolerance = 1e-8;
+  static constexpr int max_consecutive_invalid = 5, max_consecutive_nonmonotonic = 5;
+};
+
+__device__ __forceinline__ int tri(int a, int b) {  // a <= b, row-major upper triangle of 6x6
+  return a * 6 - a * (a - 1) / 2 + (b - a);
+}
+
+// brick index of the brick containing the (shifted, in-bounds) cell, or -1
+__device__ __forceinline__ int find_brick(const GridView& g, unsigned sx, unsigned sy, unsigned sz) {
+  const int node = __ldg(g.top + ((((sz >> 6) << g.bits) + (sy >> 6)) << g.bits) + (sx >> 6));
+  if (node < 0) return -1;
+  return __ldg(g.nodes + (size_t)node * 512 + ((((sz >> 3) & 7) << 6) | (((sy >> 3) & 7) << 3) | ((sx >> 3) & 7)));
+}
+
+// InterpolatedGrid::GetProbability at (x, y, z) plus its spatial gradient.
+__device__ __forceinline__ void interpolate(const GridView& g, double x, double y, double z, double* value,
+                                            double* gx, double* gy, double* gz) {
+  const float res = g.resolution;
+  // CenterOfLowerVoxel (interpolated_grid.h:120-139): float cell of the narrowed point, float centre compared
+  // with the double coordinate.
+  const Int3 ci = cell_index(Vec3f{(float)x, (float)y, (float)z}, res);
+  float cx = (float)ci.x * res, cy = (float)ci.y * res, cz = (float)ci.z * res;
+  if ((double)cx > x) cx -= res;
+  if ((double)cy > y) cy -= res;
+  if ((double)cz > z) cz -= res;
+  const double x1 = cx, y1 = cy, z1 = cz;
+  const double x2 = (double)(cx + res), y2 = (double)(cy + res), z2 = (double)(cz + res);
+  const Int3 i1 = cell_index(Vec3f{cx, cy, cz}, res);
+
+  // 8 corners: one tree walk when the 2x2x2 block sits inside one brick (probability (7/8)^3), else 8 walks.
+  float q[8];  // index = dx*4 + dy*2 + dz
+  const int gs = 64 << g.bits, half = gs >> 1;
+  const unsigned sx = (unsigned)(i1.x + half), sy = (unsigned)(i1.y + half), sz = (unsigned)(i1.z + half);
+  if (sx < (unsigned)gs - 1 && sy < (unsigned)gs - 1 && sz < (unsigned)gs - 1 && (sx & 7) != 7 && (sy & 7) != 7 &&
+      (sz & 7) != 7) {
+    const int brick = find_brick(g, sx, sy, sz);
+    if (brick < 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) q[k] = 0.1f;
+    } else {
+      const uint16_t* b = g.bricks + (size_t)brick * 512 + (((sz & 7) << 6) | ((sy & 7) << 3) | (sx & 7));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) q[k] = value_to_probability(__ldg(b + ((k & 1) << 6) + (((k >> 1) & 1) << 3) + (k >> 2)));
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) q[k] = value_to_probability(grid_value(g, i1.x + (k >> 2), i1.y + ((k >> 1) & 1), i1.z + (k & 1)));
+  }
+  const double q111 = q[0], q112 = q[1], q121 = q[2], q122 = q[3], q211 = q[4], q212 = q[5], q221 = q[6], q222 = q[7];
+
+  const double ix = 1.0 / (x2 - x1), iy = 1.0 / (y2 - y1), iz = 1.0 / (z2 - z1);
+  const double nx = (x - x1) / (x2 - x1), ny = (y - y1) / (y2 - y1), nz = (z - z1) / (z2 - z1);
+  const double nxx = nx * nx, nxxx = nx * nxx, nyy = ny * ny, nyyy = ny * nyy, nzz = nz * nz, nzzz = nz * nzz;
+  // value: the reference's expression order (interpolated_grid.h:84-102)
+  const double q11 = (q111 - q112) * nzzz * 2. + (q112 - q111) * nzz * 3. + q111;
+  const double q12 = (q121 - q122) * nzzz * 2. + (q122 - q121) * nzz * 3. + q121;
+  const double q21 = (q211 - q212) * nzzz * 2. + (q212 - q211) * nzz * 3. + q211;
+  const double q22 = (q221 - q222) * nzzz * 2. + (q222 - q221) * nzz * 3. + q221;
+  const double q1 = (q11 - q12) * nyyy * 2. + (q12 - q11) * nyy * 3. + q11;
+  const double q2 = (q21 - q22) * nyyy * 2. + (q22 - q21) * nyy * 3. + q21;
+  *value = (q1 - q2) * nxxx * 2. + (q2 - q1) * nxx * 3. + q1;
+  // gradient of the same polynomial: S(t) = 3t^2 - 2t^3, S'(t) = 6t(1 - t)
+  const double sx_ = 3. * nxx - 2. * nxxx, sy_ = 3. * nyy - 2. * nyyy;
+  const double dsx = 6. * nx * (1. - nx), dsy = 6. * ny * (1. - ny), dsz = 6. * nz * (1. - nz);
+  *gx = (q2 - q1) * dsx * ix;
+  *gy = ((q12 - q11) * (1. - sx_) + (q22 - q21) * sx_) * dsy * iy;
+  const double dz1 = (q112 - q111) * (1. - sy_) + (q122 - q121) * sy_;
+  const double dz2 = (q212 - q211) * (1. - sy_) + (q222 - q221) * sy_;
+  *gz = (dz1 * (1. - sx_) + dz2 * sx_) * dsz * iz;
+}
+
+// d(q_delta (x) x)/d(delta) at delta = 0: 4 x 3 for ceres::QuaternionParameterization, 4 x 1 for yaw-only.
+__device__ __forceinline__ void plus_jacobian(const double* x, bool only_yaw, double P[4][3]) {
+  const double q0 = x[3], q1 = x[4], q2 = x[5], q3 = x[6];
+  if (!only_yaw) {
+    P[0][0] = -q1; P[0][1] = -q2; P[0][2] = -q3;
+    P[1][0] = q0;  P[1][1] = q3;  P[1][2] = -q2;
+    P[2][0] = -q3; P[2][1] = q0;  P[2][2] = q1;
+    P[3][0] = q2;  P[3][1] = -q1; P[3][2] = q0;
+  } else {
+    P[0][0] = -q3; P[1][0] = -q2; P[2][0] = q1; P[3][0] = q0;
+    for (int i = 0; i < 4; ++i) P[i][1] = P[i][2] = 0.0;
+  }
+}
+
+__device__ __forceinline__ void plus(const double* x, const double* delta, bool only_yaw, double* out) {
+  out[0] = x[0] + delta[0]; out[1] = x[1] + delta[1]; out[2] = x[2] + delta[2];
+  const Quatd q{x[3], x[4], x[5], x[6]};
+  Quatd r = q;
+  if (!only_yaw) {
+    const double n = sqrt(delta[3] * delta[3] + delta[4] * delta[4] + delta[5] * delta[5]);
+    if (n > 0.0) {
+      const double sbd = sin(n) / n;
+      r = qmul(Quatd{cos(n), sbd * delta[3], sbd * delta[4], sbd * delta[5]}, q);
+    }
+  } else {
+    double d = delta[3];
+    d = d > 0.5 ? 0.5 : (d < -0.5 ? -0.5 : d);
+    r = qmul(Quatd{sqrt(1. - d * d), 0., 0., d}, q);
+  }
+  out[3] = r.w; out[4] = r.x; out[5] = r.y; out[6] = r.z;
+}
+
+struct Shared {
+  double red[kWarps][kRed];
+  double acc[kRed];      // block total of the last evaluation
+  double x[7];           // evaluation point broadcast
+  int n[DL_MAX_PAIRS];
+  double scaling[DL_MAX_PAIRS];
+  int stop;
+};
+
+// Fused evaluation pass at sh.x: leaves cost*2, J^T r and J^T J (local parameterisation) in sh.acc.
+__device__ void evaluate(const NlsOptions& opt, const NlsProblem& prob, Shared& sh, const double* target_q_inv,
+                         const double* target_t) {
+  double x[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) x[i] = sh.x[i];
+  double P[4][3];
+  plus_jacobian(x, opt.only_yaw != 0, P);
+  const Quatd q{x[3], x[4], x[5], x[6]};
+  const Vec3d a{x[4], x[5], x[6]};
+  double acc[kRed];
+#pragma unroll
+  for (int i = 0; i < kRed; ++i) acc[i] = 0.0;
+
+  for (int k = 0; k < opt.num_pairs; ++k) {
+    const int n = sh.n[k];
+    const double s = sh.scaling[k];
+    const float* __restrict__ cloud = prob.cloud[k];
+    const GridView g = prob.grid[k];
+    for (int i = threadIdx.x; i < n; i += kBlock) {
+      const Vec3d v{(double)cloud[3 * i], (double)cloud[3 * i + 1], (double)cloud[3 * i + 2]};
+      const Vec3d w = add(rotate(q, v), Vec3d{x[0], x[1], x[2]});
+      double m, gx, gy, gz;
+      interpolate(g, w.x, w.y, w.z, &m, &gx, &gy, &gz);
+      const double r = s * (1. - m);
+      // ambient Jacobian row: -s * grad(M) . [ I | d world / d(qw, qx, qy, qz) ]
+      const double jx = -s * gx, jy = -s * gy, jz = -s * gz;
+      const Vec3d dw = mul(2.0, cross3(a, v));                       // d/d qw
+      const double av = dot3(a, v);
+      // d/d a_j = 2 qw (e_j x v) + 2 (e_j (a.v) + a v_j - 2 v a_j)
+      const Vec3d dxv{2. * (av + a.x * v.x - 2. * v.x * a.x), 2. * (q.w * v.z + a.y * v.x - 2. * v.y * a.x),
+                      2. * (-q.w * v.y + a.z * v.x - 2. * v.z * a.x)};
+      const Vec3d dyv{2. * (-q.w * v.z + a.x * v.y - 2. * v.x * a.y), 2. * (av + a.y * v.y - 2. * v.y * a.y),
+                      2. * (q.w * v.x + a.z * v.y - 2. * v.z * a.y)};
+      const Vec3d dzv{2. * (q.w * v.y + a.x * v.z - 2. * v.x * a.z), 2. * (-q.w * v.x + a.y * v.z - 2. * v.y * a.z),
+                      2. * (av + a.z * v.z - 2. * v.z * a.z)};
+      const double gq0 = jx * dw.x + jy * dw.y + jz * dw.z;
+      const double gq1 = jx * dxv.x + jy * dxv.y + jz * dxv.z;
+      const double gq2 = jx * dyv.x + jy * dyv.y + jz * dyv.z;
+      const double gq3 = jx * dzv.x + jy * dzv.y + jz * dzv.z;
+      double J[6];
+      J[0] = jx; J[1] = jy; J[2] = jz;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) J[3 + j] = gq0 * P[0][j] + gq1 * P[1][j] + gq2 * P[2][j] + gq3 * P[3][j];
+      acc[0] += r * r;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) acc[1 + c] += J[c] * r;
+      int t = 7;
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+#pragma unroll
+        for (int d = c; d < 6; ++d) acc[t++] += J[c] * J[d];
+    }
+  }
+  // fixed-order reduction: lanes (xor tree), then warps in index order
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < kRed; ++i) {
+    double v = acc[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0) sh.red[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kRed) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) v += sh.red[w][threadIdx.x];
+    sh.acc[threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // the two 3-residual blocks (translation_delta_cost_functor_3d.h:38-44, rotation_delta_cost_functor_3d.h:42-53)
+    if (opt.trans_weight > 0.) {
+      const double s = opt.trans_weight;
+      for (int c = 0; c < 3; ++c) {
+        const double r = s * (x[c] - target_t[c]);
+        sh.acc[0] += r * r;
+        sh.acc[1 + c] += s * r;
+        sh.acc[7 + tri(c, c)] += s * s;
+      }
+    }
+    if (opt.rot_weight > 0.) {
+      const double s = opt.rot_weight;
+      const double zw = target_q_inv[0], zx = target_q_inv[1], zy = target_q_inv[2], zz = target_q_inv[3];
+      const double* w = x + 3;
+      const double d[3] = {zw * w[1] + zx * w[0] + zy * w[3] - zz * w[2], zw * w[2] - zx * w[3] + zy * w[0] + zz * w[1],
+                           zw * w[3] + zx * w[2] - zy * w[1] + zz * w[0]};
+      const double dd[3][4] = {{zx, zw, -zz, zy}, {zy, zz, zw, -zx}, {zz, -zy, zx, zw}};
+      for (int c = 0; c < 3; ++c) {
+        const double r = s * d[c];
+        double J[6] = {0, 0, 0, 0, 0, 0};
+        for (int j = 0; j < 3; ++j)
+          J[3 + j] = s * (dd[c][0] * P[0][j] + dd[c][1] * P[1][j] + dd[c][2] * P[2][j] + dd[c][3] * P[3][j]);
+        sh.acc[0] += r * r;
+        for (int e = 3; e < 6; ++e) sh.acc[1 + e] += J[e] * r;
+        for (int e = 3; e < 6; ++e)
+          for (int f = e; f < 6; ++f) sh.acc[7 + tri(e, f)] += J[e] * J[f];
+      }
+    }
+  }
+  __syncthreads();
+}
+
+struct Eval {
+  double cost;
+  double g[6];
+  double H[6][6];
+};
+__device__ __forceinline__ void load_eval(const Shared& sh, Eval* e) {
+  e->cost = 0.5 * sh.acc[0];
+  for (int c = 0; c < 6; ++c) e->g[c] = sh.acc[1 + c];
+  for (int c = 0; c < 6; ++c)
+    for (int d = c; d < 6; ++d) e->H[c][d] = e->H[d][c] = sh.acc[7 + tri(c, d)];
+}
+
+// Solves (A) y = b for symmetric positive definite A (n <= 6) by Cholesky; false if not PD / not finite.
+__device__ bool cholesky_solve(int n, double A[6][6], const double* b, double* y) {
+  double Lm[6][6];
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j <= i; ++j) {
+      double s = A[i][j];
+      for (int k = 0; k < j; ++k) s -= Lm[i][k] * Lm[j][k];
+      if (i == j) {
+        if (!(s > 0.0)) return false;
+        Lm[i][i] = sqrt(s);
+      } else {
+        Lm[i][j] = s / Lm[j][j];
+      }
+    }
+  }
+  double z[6];
+  for (int i = 0; i < n; ++i) {
+    double s = b[i];
+    for (int k = 0; k < i; ++k) s -= Lm[i][k] * z[k];
+    z[i] = s / Lm[i][i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = z[i];
+    for (int k = i + 1; k < n; ++k) s -= Lm[k][i] * y[k];
+    y[i] = s / Lm[i][i];
+  }
+  for (int i = 0; i < n; ++i)
+    if (!isfinite(y[i])) return false;
+  return true;
+}
+
+__device__ __forceinline__ void setup_problem(const NlsOptions& opt, const NlsProblem& prob, Shared& sh, double* x0,
+                                              double* target_t, double* target_q_inv) {
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < opt.num_pairs; ++k) {
+      const int n = prob.count_dev[k] ? *prob.count_dev[k] : prob.count[k];
+      sh.n[k] = n;
+      sh.scaling[k] = opt.occ_weight[k] / sqrt((double)n);  // ceres_scan_matcher_3d.cc:98-99
+    }
+    const double* init = prob.initial_dev ? prob.initial_dev : prob.initial;
+    for (int i = 0; i < 7; ++i) sh.x[i] = init[i];
+  }
+  __syncthreads();
+  for (int i = 0; i < 7; ++i) x0[i] = sh.x[i];
+  if (prob.target_dev) {
+    for (int i = 0; i < 3; ++i) target_t[i] = prob.target_dev[i];
+  } else if (prob.initial_dev) {
+    for (int i = 0; i < 3; ++i) target_t[i] = x0[i];
+  } else {
+    for (int i = 0; i < 3; ++i) target_t[i] = prob.target_t[i];
+  }
+  target_q_inv[0] = x0[3]; target_q_inv[1] = -x0[4]; target_q_inv[2] = -x0[5]; target_q_inv[3] = -x0[6];
+}
+
+// Trust-region state of one problem (names follow Ceres 1.13 TrustRegionMinimizer / LevenbergMarquardtStrategy /
+// TrustRegionStepEvaluator members). Lives in shared memory and is touched by thread 0 only, so the evaluation
+// pass keeps the registers.
+struct LmState {
+  Eval cur;
+  double x[7], cand[7], best_x[7], target_t[3], target_q_inv[4];
+  double scale[6], diag[6];
+  double x_norm, minimum_cost, radius, decrease_factor, gradient_max_norm, initial_cost, final_cost, last_cost;
+  double model_cost_change;
+  double ev_minimum, ev_current, ev_reference, ev_candidate, ev_acc_ref, ev_acc_cand;
+  int ev_num_nonmono, max_nonmono;
+  int reuse_diagonal, last_successful, num_invalid, iteration, recorded, successful, unsuccessful, termination, evals;
+  int nl, only_yaw, max_iter;
+};
+
+__device__ __forceinline__ double norm7(const double* v) {
+  double s = 0;
+  for (int i = 0; i < 7; ++i) s += v[i] * v[i];
+  return sqrt(s);
+}
+// max-norm of x - Plus(x, -g): the projected gradient Ceres tests against gradient_tolerance
+__device__ double projected_gradient_max_norm(const double* at, const double* g, bool only_yaw) {
+  double ng[6], px[7];
+  for (int j = 0; j < 6; ++j) ng[j] = -g[j];
+  plus(at, ng, only_yaw, px);
+  double mx = 0;
+  for (int i = 0; i < 7; ++i) mx = fmax(mx, fabs(at[i] - px[i]));
+  return mx;
+}
+
+__device__ __noinline__ void lm_iteration_zero(LmState& st, const Shared& sh) {
+  load_eval(sh, &st.cur);
+  st.evals = 1;
+  for (int j = 0; j < st.nl; ++j) st.scale[j] = 1.0 / (1.0 + sqrt(st.cur.H[j][j]));
+  for (int j = st.nl; j < 6; ++j) st.scale[j] = 0.0;
+  st.x_norm = norm7(st.x);
+  st.gradient_max_norm = projected_gradient_max_norm(st.x, st.cur.g, st.only_yaw);
+  st.initial_cost = st.final_cost = st.last_cost = st.cur.cost;
+  st.ev_minimum = st.ev_current = st.ev_reference = st.ev_candidate = st.cur.cost;
+  st.ev_acc_ref = st.ev_acc_cand = 0;
+  st.ev_num_nonmono = 0;
+  st.minimum_cost = 1.7976931348623157e308;
+  st.radius = Lm::initial_radius;
+  st.decrease_factor = 2.0;
+  st.reuse_diagonal = 0;
+  st.last_successful = 1;
+  st.num_invalid = st.iteration = st.recorded = st.successful = st.unsuccessful = 0;
+  st.termination = 1;
+}
+
+// FinalizeIterationAndCheckIfMinimizerCanContinue + ComputeTrustRegionStep (+ HandleInvalidStep retries).
+// Returns 1 to stop; otherwise st.cand holds the candidate point.
+__device__ __noinline__ int lm_prepare_step(LmState& st) {
+  if (st.last_successful) {
+    ++st.successful;
+    if (st.cur.cost < st.minimum_cost) {
+      st.minimum_cost = st.cur.cost;
+      for (int i = 0; i < 7; ++i) st.best_x[i] = st.x[i];
+    }
+  } else {
+    ++st.unsuccessful;
+  }
+  ++st.recorded;
+  st.final_cost = fmin(st.final_cost, st.last_cost);
+  if (st.iteration >= st.max_iter) { st.termination = 1; return 1; }
+  if (st.last_successful && st.gradient_max_norm <= Lm::gradient_tolerance) { st.termination = 0; return 1; }
+  if (st.radius <= Lm::min_radius) { st.termination = 0; return 1; }
+  const int nl = st.nl;
+  for (;;) {
+    ++st.iteration;
+    // LevenbergMarquardtStrategy::ComputeStep on the Jacobi-scaled system
+    double A[6][6], Hs[6][6], gs[6], y[6], step[6];
+    for (int c = 0; c < nl; ++c) {
+      gs[c] = st.scale[c] * st.cur.g[c];
+      for (int d = 0; d < nl; ++d) Hs[c][d] = A[c][d] = st.scale[c] * st.cur.H[c][d] * st.scale[d];
+    }
+    if (!st.reuse_diagonal)
+      for (int c = 0; c < nl; ++c) st.diag[c] = fmin(fmax(A[c][c], Lm::min_lm_diagonal), Lm::max_lm_diagonal);
+    for (int c = 0; c < nl; ++c) A[c][c] += st.diag[c] / st.radius;
+    bool valid = cholesky_solve(nl, A, gs, y);
+    st.reuse_diagonal = 1;
+    if (valid) {
+      double lin = 0, quad = 0;
+      for (int c = 0; c < nl; ++c) {
+        step[c] = -y[c];
+        lin += step[c] * gs[c];
+      }
+      for (int c = 0; c < nl; ++c) {
+        double row = 0;
+        for (int d = 0; d < nl; ++d) row += Hs[c][d] * step[d];
+        quad += step[c] * row;
+      }
+      st.model_cost_change = -(lin + 0.5 * quad);
+      valid = st.model_cost_change > 0.0;
+    }
+    if (valid) {
+      st.num_invalid = 0;
+      double delta[6] = {0, 0, 0, 0, 0, 0};
+      for (int c = 0; c < nl; ++c) delta[c] = step[c] * st.scale[c];
+      plus(st.x, delta, st.only_yaw, st.cand);
+      return 0;
+    }
+    // HandleInvalidStep, then finalize that iteration and retry with the smaller radius
+    if (++st.num_invalid >= Lm::max_consecutive_invalid) { st.termination = 2; return 1; }
+    st.radius *= 0.5;
+    st.last_successful = 0;
+    st.last_cost = st.cur.cost;
+    ++st.unsuccessful;
+    ++st.recorded;
+    if (st.iteration >= st.max_iter) { st.termination = 1; return 1; }
+    if (st.radius <= Lm::min_radius) { st.termination = 0; return 1; }
+  }
+}
+
+// Tolerance tests, step acceptance and trust-region update for the evaluated candidate. Returns 1 to stop.
+__device__ __noinline__ int lm_process_candidate(LmState& st, const Shared& sh) {
+  Eval ce;
+  load_eval(sh, &ce);
+  ++st.evals;
+  double candidate_cost = ce.cost;
+  if (!isfinite(candidate_cost)) candidate_cost = 1.7976931348623157e308;
+  // ParameterToleranceReached
+  double sn = 0;
+  for (int i = 0; i < 7; ++i) sn += (st.x[i] - st.cand[i]) * (st.x[i] - st.cand[i]);
+  if (sqrt(sn) <= Lm::parameter_tolerance * (st.x_norm + Lm::parameter_tolerance)) { st.termination = 0; return 1; }
+  // FunctionToleranceReached
+  if (fabs(st.cur.cost - candidate_cost) <= Lm::function_tolerance * st.cur.cost) { st.termination = 0; return 1; }
+  const double relative = (st.ev_current - candidate_cost) / st.model_cost_change;
+  const double historical = (st.ev_reference - candidate_cost) / (st.ev_acc_ref + st.model_cost_change);
+  const double relative_decrease = fmax(relative, historical);
+  if (relative_decrease > Lm::min_relative_decrease) {
+    // HandleSuccessfulStep (the candidate's normal equations were computed speculatively in the same pass)
+    for (int i = 0; i < 7; ++i) st.x[i] = st.cand[i];
+    st.x_norm = norm7(st.x);
+    st.cur = ce;
+    st.cur.cost = candidate_cost;
+    st.gradient_max_norm = projected_gradient_max_norm(st.x, st.cur.g, st.only_yaw);
+    st.last_successful = 1;
+    st.last_cost = candidate_cost;
+    st.radius = st.radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * relative_decrease - 1.0, 3.0));
+    st.radius = fmin(Lm::max_radius, st.radius);
+    st.decrease_factor = 2.0;
+    st.reuse_diagonal = 0;
+    st.ev_current = candidate_cost;
+    st.ev_acc_cand += st.model_cost_change;
+    st.ev_acc_ref += st.model_cost_change;
+    if (st.ev_current < st.ev_minimum) {
+      st.ev_minimum = st.ev_current;
+      st.ev_num_nonmono = 0;
+      st.ev_candidate = st.ev_current;
+      st.ev_acc_cand = 0;
+    } else {
+      ++st.ev_num_nonmono;
+      if (st.ev_current > st.ev_candidate) {
+        st.ev_candidate = st.ev_current;
+        st.ev_acc_cand = 0;
+      }
+    }
+    if (st.ev_num_nonmono == st.max_nonmono) {
+      st.ev_reference = st.ev_candidate;
+      st.ev_acc_ref = st.ev_acc_cand;
+    }
+  } else {
+    // HandleUnsuccessfulStep
+    st.last_successful = 0;
+    st.last_cost = candidate_cost;
+    st.radius = st.radius / st.decrease_factor;
+    st.decrease_factor *= 2.0;
+    st.reuse_diagonal = 1;
+  }
+  return 0;
+}
+
+// The trust-region loop of Ceres 1.13 (TrustRegionMinimizer::Minimize): thread 0 drives the state machine between
+// evaluation passes in which every thread takes part.
+__global__ void __launch_bounds__(kBlock) nls_solve_kernel(NlsOptions opt, const NlsProblem* __restrict__ problems,
+                                                           NlsOutput* __restrict__ outputs) {
+  __shared__ Shared sh;
+  __shared__ LmState st;
+  const NlsProblem& prob = problems[blockIdx.x];
+  {
+    double x[7], target_t[3], target_q_inv[4];
+    setup_problem(opt, prob, sh, x, target_t, target_q_inv);
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < 7; ++i) st.x[i] = x[i];
+      for (int i = 0; i < 3; ++i) st.target_t[i] = target_t[i];
+      for (int i = 0; i < 4; ++i) st.target_q_inv[i] = target_q_inv[i];
+      st.only_yaw = opt.only_yaw != 0;
+      st.nl = st.only_yaw ? 4 : 6;
+      st.max_iter = opt.max_iter;
+      st.max_nonmono = opt.nonmono ? Lm::max_consecutive_nonmonotonic : 0;
+    }
+  }
+  __syncthreads();
+  evaluate(opt, prob, sh, st.target_q_inv, st.target_t);
+  if (threadIdx.x == 0) lm_iteration_zero(st, sh);
+  for (;;) {
+    __syncthreads();  // every thread has consumed sh.stop / sh.acc of the previous round
+    if (threadIdx.x == 0) {
+      const int stop = lm_prepare_step(st);
+      sh.stop = stop;
+      if (!stop)
+        for (int i = 0; i < 7; ++i) sh.x[i] = st.cand[i];
+    }
+    __syncthreads();
+    if (sh.stop) break;
+    evaluate(opt, prob, sh, st.target_q_inv, st.target_t);  // candidate cost + speculative normal equations
+    if (threadIdx.x == 0) sh.stop = lm_process_candidate(st, sh);
+    __syncthreads();
+    if (sh.stop) break;
+  }
+  if (threadIdx.x == 0) {
+    NlsOutput& o = outputs[blockIdx.x];
+    for (int i = 0; i < 7; ++i) o.pose[i] = st.best_x[i];
+    o.summary.initial_cost = st.initial_cost;
+    o.summary.final_cost = st.final_cost;
+    o.summary.num_iterations = st.recorded;
+    o.summary.num_successful_steps = st.successful;
+    o.summary.num_unsuccessful_steps = st.unsuccessful;
+    o.summary.termination = st.termination;
+    o.summary.num_evaluations = st.evals;
+    o.summary.reserved = 0;
+  }
+}
+
+// One evaluation pass at a given pose; writes the 28 reduced doubles (cost, g, H upper triangle).
+__global__ void __launch_bounds__(kBlock) nls_normal_equations_kernel(NlsOptions opt, const NlsProblem* problems,
+                                                                      const double* at_pose, double* out28) {
+  __shared__ Shared sh;
+  const NlsProblem& prob = problems[blockIdx.x];
+  double x[7], target_t[3], target_q_inv[4];
+  setup_problem(opt, prob, sh, x, target_t, target_q_inv);
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int i = 0; i < 7; ++i) sh.x[i] = at_pose[i];
+  __syncthreads();
+  evaluate(opt, prob, sh, target_q_inv, target_t);
+  if (threadIdx.x < kRed) out28[blockIdx.x * kRed + threadIdx.x] = threadIdx.x == 0 ? 0.5 * sh.acc[0] : sh.acc[threadIdx.x];
+}
+
+__global__ void interpolate_kernel(GridView g, int64_t n, const double* __restrict__ xyz, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v, gx, gy, gz;
+  interpolate(g, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], &v, &gx, &gy, &gz);
+  out[4 * i] = v; out[4 * i + 1] = gx; out[4 * i + 2] = gy; out[4 * i + 3] = gz;
+}
+
+__global__ void grid_lookup_kernel(GridView g, int64_t n, const int32_t* __restrict__ xyz, uint16_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = grid_value(g, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+}
+
+}  // namespace
+
+int launch_nls(dl_context* ctx, const NlsOptions& opt, const NlsProblem* problems_dev, int count, NlsOutput* out_dev) {
+  if (count <= 0) return DL_OK;
+  nls_solve_kernel<<<count, kBlock, 0, ctx->stream>>>(opt, problems_dev, out_dev);
+  DL_LAUNCH_CHECK(ctx, "nls_solve_kernel");
+  return DL_OK;
+}
+
+int launch_nls_normal_equations(dl_context* ctx, const NlsOptions& opt, const NlsProblem* problems_dev,
+                                const double* at_pose_dev, double* out28_dev) {
+  nls_normal_equations_kernel<<<1, kBlock, 0, ctx->stream>>>(opt, problems_dev, at_pose_dev, out28_dev);
+  DL_LAUNCH_CHECK(ctx, "nls_normal_equations_kernel");
+  return DL_OK;
+}
+
+int launch_interpolate(dl_context* ctx, const GridView& grid, int64_t n, const double* xyz, double* out) {
+  if (n <= 0) return DL_OK;
+  interpolate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(grid, n, xyz, out);
+  DL_LAUNCH_CHECK(ctx, "interpolate_kernel");
+  return DL_OK;
+}
+
+int launch_grid_lookup(dl_context* ctx, const GridView& grid, int64_t n, const int32_t* xyz, uint16_t* out) {
+  if (n <= 0) return DL_OK;
+  grid_lookup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(grid, n, xyz, out);
+  DL_LAUNCH_CHECK(ctx, "grid_lookup_kernel");
+  return DL_OK;
+}
+
+}  // namespace dl

@@ -1,0 +1,58 @@
+// Argument blocks of the batched front-end kernels (dl_ingest.cu) and their launchers.
+#pragma once
+#include "dl_internal.cuh"
+
+namespace dl {
+
+// Per-scan constants of the deskew, prepared on the host with the reference's double arithmetic (LTB:426-428,
+// LTB:871-879): prev = previous optimised pose, cur = IMU-predicted pose at scan end, rel = prev^-1 * cur, and the
+// scan-constant part of Eigen's slerp (theta = acos|d|, sin(theta), the |d| >= 1 - eps and d < 0 switches).
+struct ScanConstants {
+  Rigidd prev, cur, rel;
+  double theta, sin_theta;
+  int linear_slerp, negative_dot;
+};
+
+struct IngestArgs {
+  const float* ranges;        // all scans, RangeMeasurement rows (8 floats); scan b starts at row b * in_cap
+  int64_t in_cap;
+  const ScanConstants* scans;
+  const float* origins;       // 3 floats per sensor
+  const int32_t* keep;        // first voxel filter survivors, b * cap + k -> row within the scan
+  const int32_t* keep_counts;
+  int64_t cap;
+  int tiles;
+  float min_range, max_range;
+  double scan_period;
+  float* tmp_points;          // b * cap * 3
+  uint8_t* cls;               // b * cap
+  int32_t* tile_counts;       // b * tiles * 2
+  float* returns_local;       // b * cap * 3
+  float* misses_local;
+  int32_t* num_returns;
+  int32_t* num_misses;
+  float* current_pose;        // b * 7 floats (t, q wxyz)
+};
+
+struct ResultArgs {
+  int batch;
+  const int32_t* first_counts;
+  const int32_t* return_counts;
+  const int32_t* miss_counts;
+  const int32_t* adaptive_counts;  // 2 per scan: high, low resolution
+  const float* rtcsm_scores;       // optional
+  const NlsOutput* nls;
+  Rigidd submap;
+  dl_scan_result* results;
+};
+
+int launch_ingest(dl_context* ctx, const IngestArgs& a, int batch);
+int launch_gather_to_tracking(dl_context* ctx, const float* in, int64_t cap, const int32_t* keep,
+                              const int32_t* keep_counts, const float* current_pose, float* out, int batch);
+int launch_gather_rows(dl_context* ctx, const float* in, int64_t cap_in, int pairs_per_cloud, const int32_t* keep,
+                       const int32_t* keep_counts, int64_t cap_out, float* out, int pairs);
+int launch_initial_pose(dl_context* ctx, int batch, const float* current_pose, const Rigidd& submap_inverse,
+                        double* initial_pose, double* target_translation);
+int launch_finalize_results(dl_context* ctx, const ResultArgs& a);
+
+}  // namespace dl

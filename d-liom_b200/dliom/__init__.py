@@ -1,0 +1,404 @@
+"""ctypes binding of libdliom_b200.so (the C-ABI in include/dliom_b200.h) for tests and bench.py.
+
+The product is the shared library; this module only marshals numpy arrays into its plain-pointer signatures.
+There is no fallback: if the library is missing, or no CUDA device is present, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "libdliom_b200.so")
+_LIB = None
+
+f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+
+DL_MAX_PAIRS = 4
+EXPORTS = [
+    "dl_context_create", "dl_context_destroy", "dl_last_error", "dl_status_string", "dl_context_kernel_launches",
+    "dl_context_stream", "dl_context_synchronize", "dl_grid_create", "dl_grid_destroy", "dl_grid_set_cells",
+    "dl_grid_sync", "dl_grid_resolution", "dl_grid_num_bricks", "dl_grid_lookup", "dl_grid_interpolate",
+    "dl_voxel_filter", "dl_voxel_indices", "dl_adaptive_voxel_filter", "dl_rtcsm_match", "dl_ceres_match",
+    "dl_ceres_match_batch", "dl_ceres_normal_equations", "dl_ingest_scan", "dl_frontend_match_batch",
+    "dl_frontend_match_batch_dev", "dl_frontend_fetch_results", "dl_device_alloc", "dl_device_free",
+    "dl_copy_to_device", "dl_copy_to_host",
+]
+
+
+class DlError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"dliom_b200 status {status}: {message}")
+        self.status = status
+
+
+class AdaptiveVoxelFilterOptions(C.Structure):
+    _fields_ = [("max_length", C.c_float), ("min_num_points", C.c_float), ("max_range", C.c_float)]
+
+
+class RtcsmOptions(C.Structure):
+    _fields_ = [("linear_search_window", C.c_double), ("angular_search_window", C.c_double),
+                ("translation_delta_cost_weight", C.c_double), ("rotation_delta_cost_weight", C.c_double)]
+
+
+class RtcsmInfo(C.Structure):
+    _fields_ = [("best_index", C.c_int64), ("num_candidates", C.c_int64), ("linear_window", C.c_int32),
+                ("angular_window", C.c_int32), ("angular_step", C.c_float), ("max_scan_range", C.c_float)]
+
+
+class CeresOptions(C.Structure):
+    _fields_ = [("num_occupied_space_weights", C.c_int32), ("occupied_space_weight", C.c_double * DL_MAX_PAIRS),
+                ("translation_weight", C.c_double), ("rotation_weight", C.c_double), ("only_optimize_yaw", C.c_int32),
+                ("use_nonmonotonic_steps", C.c_int32), ("max_num_iterations", C.c_int32), ("num_threads", C.c_int32)]
+
+    @staticmethod
+    def make(occ, trans_w, rot_w, only_yaw=False, nonmono=False, max_iter=12):
+        o = CeresOptions()
+        o.num_occupied_space_weights = len(occ)
+        for i, w in enumerate(occ):
+            o.occupied_space_weight[i] = w
+        o.translation_weight, o.rotation_weight = trans_w, rot_w
+        o.only_optimize_yaw, o.use_nonmonotonic_steps = int(only_yaw), int(nonmono)
+        o.max_num_iterations, o.num_threads = max_iter, 1
+        return o
+
+
+class SolveSummary(C.Structure):
+    _fields_ = [("initial_cost", C.c_double), ("final_cost", C.c_double), ("num_iterations", C.c_int32),
+                ("num_successful_steps", C.c_int32), ("num_unsuccessful_steps", C.c_int32),
+                ("termination", C.c_int32), ("num_evaluations", C.c_int32), ("reserved", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+class FrontendOptions(C.Structure):
+    _fields_ = [("min_range", C.c_float), ("max_range", C.c_float), ("voxel_filter_size", C.c_float),
+                ("high_resolution_adaptive_voxel_filter", AdaptiveVoxelFilterOptions),
+                ("low_resolution_adaptive_voxel_filter", AdaptiveVoxelFilterOptions),
+                ("use_online_correlative_scan_matching", C.c_int32), ("scan_period", C.c_double),
+                ("real_time_correlative_scan_matcher", RtcsmOptions), ("ceres_scan_matcher", CeresOptions)]
+
+    @staticmethod
+    def from_oracle(o):
+        """Same parameters as an oracle FrontEndOptions block (oracle/orc.py), field for field."""
+        f = FrontendOptions()
+        f.min_range, f.max_range, f.voxel_filter_size = o.min_range, o.max_range, o.voxel_filter_size
+        f.high_resolution_adaptive_voxel_filter = AdaptiveVoxelFilterOptions(o.hi_max_length, o.hi_min_num_points,
+                                                                             o.hi_max_range)
+        f.low_resolution_adaptive_voxel_filter = AdaptiveVoxelFilterOptions(o.lo_max_length, o.lo_min_num_points,
+                                                                            o.lo_max_range)
+        f.use_online_correlative_scan_matching = o.use_rtcsm
+        f.scan_period = o.scan_period
+        f.real_time_correlative_scan_matcher = RtcsmOptions(o.rtcsm_linear_window, o.rtcsm_angular_window, o.rtcsm_w_t,
+                                                            o.rtcsm_w_r)
+        f.ceres_scan_matcher = CeresOptions.make([o.occ_w0, o.occ_w1], o.trans_w, o.rot_w, o.only_yaw, o.nonmono,
+                                                 o.max_iter)
+        return f
+
+
+class ScanResult(C.Structure):
+    _fields_ = [("pose_estimate_local", C.c_double * 7), ("pose_observation_in_submap", C.c_double * 7),
+                ("summary", SolveSummary), ("rtcsm_score", C.c_float), ("ok", C.c_int32),
+                ("num_first_filter", C.c_int32), ("num_returns", C.c_int32), ("num_misses", C.c_int32),
+                ("num_high_resolution", C.c_int32), ("num_low_resolution", C.c_int32), ("reserved", C.c_int32)]
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` first")
+    L = C.CDLL(LIB_PATH)
+    vp, ip = C.c_void_p, C.POINTER
+    L.dl_context_create.argtypes = [C.c_int, ip(vp)]
+    L.dl_context_destroy.argtypes = [vp]
+    L.dl_context_destroy.restype = None
+    L.dl_last_error.argtypes = [vp]
+    L.dl_last_error.restype = C.c_char_p
+    L.dl_status_string.argtypes = [C.c_int]
+    L.dl_status_string.restype = C.c_char_p
+    L.dl_context_kernel_launches.argtypes = [vp]
+    L.dl_context_kernel_launches.restype = C.c_int64
+    L.dl_context_stream.argtypes = [vp]
+    L.dl_context_stream.restype = C.c_uint64
+    L.dl_context_synchronize.argtypes = [vp]
+    L.dl_grid_create.argtypes = [vp, C.c_float, ip(vp)]
+    L.dl_grid_destroy.argtypes = [vp]
+    L.dl_grid_destroy.restype = None
+    L.dl_grid_set_cells.argtypes = [vp, C.c_int64, i32p, i32p, i32p, u16p]
+    L.dl_grid_sync.argtypes = [vp]
+    L.dl_grid_resolution.argtypes = [vp]
+    L.dl_grid_resolution.restype = C.c_float
+    L.dl_grid_num_bricks.argtypes = [vp]
+    L.dl_grid_num_bricks.restype = C.c_int64
+    L.dl_grid_lookup.argtypes = [vp, vp, C.c_int64, i32p, u16p]
+    L.dl_grid_interpolate.argtypes = [vp, vp, C.c_int64, f64p, f64p]
+    L.dl_voxel_filter.argtypes = [vp, f32p, C.c_int64, C.c_int, C.c_float, i64p, ip(C.c_int64)]
+    L.dl_voxel_indices.argtypes = [vp, f32p, C.c_int64, C.c_int, C.c_float, i32p]
+    L.dl_adaptive_voxel_filter.argtypes = [vp, ip(AdaptiveVoxelFilterOptions), f32p, C.c_int64, C.c_int, i64p,
+                                           ip(C.c_int64), f32p, ip(C.c_int)]
+    L.dl_rtcsm_match.argtypes = [vp, ip(RtcsmOptions), f64p, f32p, C.c_int64, vp, f64p, ip(C.c_float), ip(RtcsmInfo), vp]
+    L.dl_ceres_match.argtypes = [vp, ip(CeresOptions), f64p, f64p, C.c_int32, ip(vp), i64p, ip(vp), f64p,
+                                 ip(SolveSummary)]
+    L.dl_ceres_match_batch.argtypes = [vp, ip(CeresOptions), C.c_int32, C.c_int32, f64p, f64p, ip(vp), i64p, ip(vp),
+                                       f64p, ip(SolveSummary)]
+    L.dl_ceres_normal_equations.argtypes = [vp, ip(CeresOptions), f64p, f64p, f64p, C.c_int32, ip(vp), i64p, ip(vp),
+                                            f64p, f64p, f64p]
+    L.dl_ingest_scan.argtypes = [vp, ip(FrontendOptions), vp, C.c_int64, f32p, C.c_int32, f64p, f64p, i64p, f32p, f32p,
+                                 f32p, f32p, i64p]
+    L.dl_frontend_match_batch.argtypes = [vp, ip(FrontendOptions), C.c_int32, ip(vp), i64p, f32p, C.c_int32, f64p,
+                                          f64p, f64p, vp, vp, ip(ScanResult)]
+    L.dl_frontend_match_batch_dev.argtypes = [vp, ip(FrontendOptions), C.c_int32, vp, C.c_int64, i64p, f32p, C.c_int32,
+                                              f64p, f64p, f64p, vp, vp, vp]
+    L.dl_frontend_fetch_results.argtypes = [vp, vp, C.c_int32, ip(ScanResult)]
+    L.dl_device_alloc.argtypes = [vp, C.c_int64, ip(vp)]
+    L.dl_device_free.argtypes = [vp, vp]
+    L.dl_copy_to_device.argtypes = [vp, vp, vp, C.c_int64]
+    L.dl_copy_to_host.argtypes = [vp, vp, vp, C.c_int64]
+    _LIB = L
+    return L
+
+
+class Context:
+    def __init__(self, device=0):
+        self.L = lib()
+        h = C.c_void_p()
+        st = self.L.dl_context_create(device, C.byref(h))
+        if st != 0:
+            raise DlError(st, self.L.dl_last_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.dl_context_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def check(self, st):
+        if st != 0:
+            raise DlError(st, self.L.dl_last_error(self.h).decode() or self.L.dl_status_string(st).decode())
+
+    @property
+    def launches(self):
+        return self.L.dl_context_kernel_launches(self.h)
+
+    @property
+    def stream(self):
+        return self.L.dl_context_stream(self.h)
+
+    def synchronize(self):
+        self.check(self.L.dl_context_synchronize(self.h))
+
+    # ---- grid
+    def grid(self, resolution):
+        return Grid(self, resolution)
+
+    # ---- filters
+    def voxel_filter(self, points, resolution):
+        points = np.ascontiguousarray(points, np.float32)
+        n, stride = points.shape
+        keep = np.zeros(max(n, 1), np.int64)
+        m = C.c_int64(0)
+        self.check(self.L.dl_voxel_filter(self.h, points, n, stride, resolution, keep, C.byref(m)))
+        return keep[:m.value].copy()
+
+    def voxel_indices(self, points, resolution):
+        points = np.ascontiguousarray(points, np.float32)
+        n, stride = points.shape
+        out = np.zeros((max(n, 1), 3), np.int32)
+        self.check(self.L.dl_voxel_indices(self.h, points, n, stride, resolution, out))
+        return out[:n]
+
+    def adaptive_voxel_filter(self, points, max_length, min_num_points, max_range):
+        points = np.ascontiguousarray(points, np.float32)
+        n, stride = points.shape
+        keep = np.zeros(max(n, 1), np.int64)
+        passes = np.zeros(32, np.float32)
+        m, npass = C.c_int64(0), C.c_int(0)
+        opt = AdaptiveVoxelFilterOptions(max_length, min_num_points, max_range)
+        self.check(self.L.dl_adaptive_voxel_filter(self.h, C.byref(opt), points, n, stride, keep, C.byref(m), passes,
+                                                   C.byref(npass)))
+        return keep[:m.value].copy(), passes[:npass.value].copy()
+
+    # ---- matchers
+    def rtcsm_match(self, grid, points, initial_pose, linear_window, angular_window, w_t, w_r, want_scores=False):
+        points = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        opt = RtcsmOptions(linear_window, angular_window, w_t, w_r)
+        pose = np.zeros(7)
+        score = C.c_float(0)
+        info = RtcsmInfo()
+        init = np.ascontiguousarray(initial_pose, np.float64)
+        scores = None
+        sp = None
+        if want_scores:
+            self.check(self.L.dl_rtcsm_match(self.h, C.byref(opt), init, points, len(points), grid.h, pose,
+                                             C.byref(score), C.byref(info), None))
+            scores = np.zeros(info.num_candidates, np.float32)
+            sp = scores.ctypes.data_as(C.c_void_p)
+        self.check(self.L.dl_rtcsm_match(self.h, C.byref(opt), init, points, len(points), grid.h, pose, C.byref(score),
+                                         C.byref(info), sp))
+        return {"score": np.float32(score.value), "pose": pose, "best_index": info.best_index,
+                "linear": info.linear_window, "angular": info.angular_window, "angular_step": np.float32(info.angular_step),
+                "max_scan_range": np.float32(info.max_scan_range), "num_candidates": info.num_candidates,
+                "scores": scores}
+
+    @staticmethod
+    def _pairs(clouds, grids):
+        clouds = [np.ascontiguousarray(c, np.float32).reshape(-1, 3) for c in clouds]
+        n = len(clouds)
+        cp = (C.c_void_p * n)(*[c.ctypes.data for c in clouds])
+        gp = (C.c_void_p * n)(*[g.h.value for g in grids])
+        sizes = np.array([len(c) for c in clouds], np.int64)
+        return clouds, cp, gp, sizes
+
+    def ceres_match(self, clouds, grids, occ_weights, trans_w, rot_w, target_translation, initial_pose, only_yaw=False,
+                    nonmono=False, max_iter=12):
+        clouds, cp, gp, sizes = self._pairs(clouds, grids)
+        opt = CeresOptions.make(occ_weights, trans_w, rot_w, only_yaw, nonmono, max_iter)
+        pose = np.zeros(7)
+        s = SolveSummary()
+        self.check(self.L.dl_ceres_match(self.h, C.byref(opt), np.ascontiguousarray(target_translation, np.float64),
+                                         np.ascontiguousarray(initial_pose, np.float64), len(clouds), cp, sizes, gp,
+                                         pose, C.byref(s)))
+        return pose, s.as_dict()
+
+    def ceres_match_batch(self, problems, grids_per_problem, occ_weights, trans_w, rot_w, targets, initial_poses,
+                          nonmono=False, max_iter=12):
+        """problems: list (per problem) of list (per pair) of clouds."""
+        count, num_pairs = len(problems), len(problems[0])
+        flat_c = [c for p in problems for c in p]
+        flat_g = [g for p in grids_per_problem for g in p]
+        clouds, cp, gp, sizes = self._pairs(flat_c, flat_g)
+        opt = CeresOptions.make(occ_weights, trans_w, rot_w, False, nonmono, max_iter)
+        poses = np.zeros((count, 7))
+        sums = (SolveSummary * count)()
+        self.check(self.L.dl_ceres_match_batch(self.h, C.byref(opt), count, num_pairs,
+                                               np.ascontiguousarray(targets, np.float64),
+                                               np.ascontiguousarray(initial_poses, np.float64), cp, sizes, gp, poses,
+                                               sums))
+        return poses, [s.as_dict() for s in sums]
+
+    def ceres_normal_equations(self, clouds, grids, occ_weights, trans_w, rot_w, target_translation, reference_pose,
+                               at_pose):
+        clouds, cp, gp, sizes = self._pairs(clouds, grids)
+        opt = CeresOptions.make(occ_weights, trans_w, rot_w)
+        cost, g, h = np.zeros(1), np.zeros(6), np.zeros(36)
+        self.check(self.L.dl_ceres_normal_equations(self.h, C.byref(opt),
+                                                    np.ascontiguousarray(target_translation, np.float64),
+                                                    np.ascontiguousarray(reference_pose, np.float64),
+                                                    np.ascontiguousarray(at_pose, np.float64), len(clouds), cp, sizes,
+                                                    gp, cost, g, h))
+        return cost[0], g, h.reshape(6, 6)
+
+    # ---- front end
+    def ingest_scan(self, options, ranges, origins, prev_pose, cur_pose):
+        n = len(ranges)
+        origins = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        first_keep = np.zeros(n, np.int64)
+        rl, rt, mt = (np.zeros((n, 3), np.float32) for _ in range(3))
+        cp = np.zeros(7, np.float32)
+        counts = np.zeros(4, np.int64)
+        self.check(self.L.dl_ingest_scan(self.h, C.byref(options), ranges.ctypes.data_as(C.c_void_p), n, origins,
+                                         len(origins), np.ascontiguousarray(prev_pose, np.float64),
+                                         np.ascontiguousarray(cur_pose, np.float64), first_keep, rl, rt, mt, cp, counts))
+        return {"first_keep": first_keep[:counts[0]].copy(), "returns_local": rl[:counts[1]].copy(),
+                "returns_tracking": rt[:counts[2]].copy(), "misses_tracking": mt[:counts[3]].copy(), "current_pose": cp}
+
+    def frontend_match_batch(self, options, ranges_list, origins, prev_poses, cur_poses, submap_local_pose, hi, lo):
+        n = len(ranges_list)
+        rp = (C.c_void_p * n)(*[r.ctypes.data for r in ranges_list])
+        sizes = np.array([len(r) for r in ranges_list], np.int64)
+        origins = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        results = (ScanResult * n)()
+        self.check(self.L.dl_frontend_match_batch(self.h, C.byref(options), n, rp, sizes, origins, len(origins),
+                                                  np.ascontiguousarray(prev_poses, np.float64),
+                                                  np.ascontiguousarray(cur_poses, np.float64),
+                                                  np.ascontiguousarray(submap_local_pose, np.float64), hi.h, lo.h,
+                                                  results))
+        return results
+
+    def frontend_match_batch_dev(self, options, ranges_dev_ptr, cap_rows, sizes, origins, prev_poses, cur_poses,
+                                 submap_local_pose, hi, lo, results_dev_ptr):
+        sizes = np.ascontiguousarray(sizes, np.int64)
+        origins = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        self.check(self.L.dl_frontend_match_batch_dev(self.h, C.byref(options), len(sizes), ranges_dev_ptr, cap_rows,
+                                                      sizes, origins, len(origins),
+                                                      np.ascontiguousarray(prev_poses, np.float64),
+                                                      np.ascontiguousarray(cur_poses, np.float64),
+                                                      np.ascontiguousarray(submap_local_pose, np.float64), hi.h, lo.h,
+                                                      results_dev_ptr))
+
+    def fetch_results(self, results_dev_ptr, n):
+        results = (ScanResult * n)()
+        self.check(self.L.dl_frontend_fetch_results(self.h, results_dev_ptr, n, results))
+        return results
+
+    def device_alloc(self, nbytes):
+        p = C.c_void_p()
+        self.check(self.L.dl_device_alloc(self.h, nbytes, C.byref(p)))
+        return p
+
+    def device_free(self, p):
+        self.check(self.L.dl_device_free(self.h, p))
+
+    def copy_to_device(self, dst, src_array):
+        src_array = np.ascontiguousarray(src_array)
+        self.check(self.L.dl_copy_to_device(self.h, dst, src_array.ctypes.data_as(C.c_void_p), src_array.nbytes))
+
+
+class Grid:
+    """Device mirror of a HybridGrid. Fill with the proto layout (x, y, z, value arrays), then sync()."""
+
+    def __init__(self, ctx, resolution):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx.check(ctx.L.dl_grid_create(ctx.h, np.float32(resolution), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.L.dl_grid_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def set_cells(self, xs, ys, zs, values, sync=True):
+        xs, ys, zs = (np.ascontiguousarray(a, np.int32) for a in (xs, ys, zs))
+        values = np.ascontiguousarray(values, np.uint16)
+        self.ctx.check(self.ctx.L.dl_grid_set_cells(self.h, len(xs), xs, ys, zs, values))
+        if sync:
+            self.sync()
+
+    def sync(self):
+        self.ctx.check(self.ctx.L.dl_grid_sync(self.h))
+
+    @property
+    def num_bricks(self):
+        return self.ctx.L.dl_grid_num_bricks(self.h)
+
+    def lookup(self, xyz):
+        xyz = np.ascontiguousarray(xyz, np.int32).reshape(-1, 3)
+        out = np.zeros(max(len(xyz), 1), np.uint16)
+        self.ctx.check(self.ctx.L.dl_grid_lookup(self.ctx.h, self.h, len(xyz), xyz, out))
+        return out[:len(xyz)]
+
+    def interpolate(self, xyz):
+        xyz = np.ascontiguousarray(xyz, np.float64).reshape(-1, 3)
+        out = np.zeros((max(len(xyz), 1), 4))
+        self.ctx.check(self.ctx.L.dl_grid_interpolate(self.ctx.h, self.h, len(xyz), xyz, out))
+        return out[:len(xyz)]
+
+    @staticmethod
+    def from_oracle(ctx, oracle_grid):
+        g = Grid(ctx, oracle_grid.resolution)
+        g.set_cells(*oracle_grid.export())
+        return g

@@ -1,0 +1,211 @@
+/* dliom_b200 — C-ABI of the B200-native scan-registration hot path.
+ *
+ * Every entry point replaces one CPU interface of the reference (peterWon/D-LIOM, a Cartographer fork).
+ * Citations: C/ = src/cartographer/cartographer/, SM/ = C/mapping/internal/3d/scan_matching/,
+ * LTB = C/mapping/internal/3d/local_trajectory_builder_3d.cc.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all buffers are caller-owned HOST memory unless the name ends in _dev;
+ *   - a pose is 7 doubles: t.x t.y t.z q.w q.x q.y q.z (the reference's CeresPose order, ceres_pose.cc:23-28);
+ *   - a point cloud is n rows of `stride` floats, the first three being x y z
+ *     (stride 3 = sensor::PointCloud, 4 = TimedPointCloud, 8 = RangeMeasurement{Vector4f,size_t});
+ *   - every function returns DL_OK (0) or a negative dl_status; nothing aborts (the reference CHECK-fails,
+ *     SM/ceres_scan_matcher_3d.cc:89-92); dl_last_error() gives the message for the calling context;
+ *   - a dl_context owns one CUDA stream plus scratch and must be used by one host thread at a time;
+ *     create one per thread for the re-entrant use ConstraintBuilder3D makes of CeresScanMatcher3D::Match
+ *     (C/mapping/internal/constraints/constraint_builder_3d.cc:318-326). dl_grid objects are shared, read-only
+ *     during matching.
+ *   - there is no CPU fallback: without a CUDA device every call fails with DL_ERR_CUDA.
+ */
+#ifndef DLIOM_B200_H_
+#define DLIOM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum dl_status {
+  DL_OK = 0,
+  DL_ERR_CUDA = -1,        /* CUDA runtime error (incl. no device)                                  */
+  DL_ERR_ARG = -2,         /* null pointer, negative size, weight count mismatch, ...               */
+  DL_ERR_GRID_RANGE = -3,  /* cell index outside +-8192 cells (hybrid_grid.h:391 CHECK_LE(bits,8)) */
+  DL_ERR_EMPTY = -4,       /* empty cloud where the reference would drop the scan (LTB:497-534)     */
+  DL_ERR_SCORE = -5        /* RT-CSM best score <= 0 (real_time_correlative_scan_matcher_3d.cc:111) */
+} dl_status;
+
+typedef struct dl_context dl_context;
+typedef struct dl_grid dl_grid;
+
+int dl_context_create(int device_ordinal, dl_context** out);
+void dl_context_destroy(dl_context* ctx);
+const char* dl_last_error(const dl_context* ctx);
+const char* dl_status_string(int status);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+int64_t dl_context_kernel_launches(const dl_context* ctx);
+/* The context's cudaStream_t as an integer, and a blocking wait on it. */
+uint64_t dl_context_stream(const dl_context* ctx);
+int dl_context_synchronize(dl_context* ctx);
+
+/* ---- probability grid: device mirror of mapping::HybridGrid (C/mapping/3d/hybrid_grid.h:411-547) ---------
+ * Cells are given as the HybridGrid proto layout (parallel x/y/z/value arrays, hybrid_grid.h:530-542) and must
+ * hold post-FinishUpdate values (< 32768). dl_grid_set_cells may be called again after every host
+ * InsertRangeData with just the touched cells; only dirty 8^3 bricks are re-uploaded by dl_grid_sync. */
+int dl_grid_create(dl_context* ctx, float resolution, dl_grid** out);
+void dl_grid_destroy(dl_grid* grid);
+int dl_grid_set_cells(dl_grid* grid, int64_t n, const int32_t* x, const int32_t* y, const int32_t* z,
+                      const uint16_t* value);
+int dl_grid_sync(dl_grid* grid);
+float dl_grid_resolution(const dl_grid* grid);
+int64_t dl_grid_num_bricks(const dl_grid* grid);
+/* HybridGrid::value() for n cell indices (xyz interleaved), evaluated ON THE DEVICE (hybrid_grid.h:263-281). */
+int dl_grid_lookup(dl_context* ctx, const dl_grid* grid, int64_t n, const int32_t* xyz, uint16_t* value_out);
+/* InterpolatedGrid::GetProbability (SM/interpolated_grid.h:50-103) and its spatial gradient for n points
+ * (xyz interleaved doubles), on the device. out: n rows of 4 doubles (value, d/dx, d/dy, d/dz). */
+int dl_grid_interpolate(dl_context* ctx, const dl_grid* grid, int64_t n, const double* xyz, double* out);
+
+/* ---- sensor::VoxelFilter::Filter (C/sensor/internal/voxel_filter.h:34-62, voxel_filter.cc:81-131) ------------
+ * keep_out receives the input-order indices of the first point in each voxel (capacity n). */
+int dl_voxel_filter(dl_context* ctx, const float* points, int64_t n, int stride, float resolution,
+                    int64_t* keep_out, int64_t* n_keep);
+/* Voxel indices only (GetCellIndex, voxel_filter.cc:126-131): out = n rows of 3 int32. */
+int dl_voxel_indices(dl_context* ctx, const float* points, int64_t n, int stride, float resolution, int32_t* out);
+
+/* ---- sensor::AdaptiveVoxelFilter::Filter (voxel_filter.cc:28-77,147-150; options proto
+ *      C/sensor/proto/adaptive_voxel_filter_options.proto) ------------------------------------------------------ */
+typedef struct dl_adaptive_voxel_filter_options {
+  float max_length;
+  float min_num_points;
+  float max_range;
+} dl_adaptive_voxel_filter_options;
+/* passes_out (optional, capacity 32) receives every voxel edge tried, in order. */
+int dl_adaptive_voxel_filter(dl_context* ctx, const dl_adaptive_voxel_filter_options* options, const float* points,
+                             int64_t n, int stride, int64_t* keep_out, int64_t* n_keep, float* passes_out,
+                             int* n_passes);
+
+/* ---- scan_matching::RealTimeCorrelativeScanMatcher3D::Match
+ *      (SM/real_time_correlative_scan_matcher_3d.h:33-60, .cc:34-113; options
+ *      C/mapping/proto/scan_matching/real_time_correlative_scan_matcher_options.proto) ------------------------- */
+typedef struct dl_rtcsm_options {
+  double linear_search_window;
+  double angular_search_window;
+  double translation_delta_cost_weight;
+  double rotation_delta_cost_weight;
+} dl_rtcsm_options;
+typedef struct dl_rtcsm_info {
+  int64_t best_index;    /* linear candidate index in the reference's loop order (z,y,x,rz,ry,rx) */
+  int64_t num_candidates;
+  int32_t linear_window; /* cells */
+  int32_t angular_window;
+  float angular_step;
+  float max_scan_range;
+} dl_rtcsm_info;
+/* Returns the best score through score_out (the reference's return value). all_scores (optional) has room for
+ * every candidate. */
+int dl_rtcsm_match(dl_context* ctx, const dl_rtcsm_options* options, const double* initial_pose,
+                   const float* points, int64_t n, const dl_grid* grid, double* pose_out, float* score_out,
+                   dl_rtcsm_info* info, float* all_scores);
+
+/* ---- scan_matching::CeresScanMatcher3D::Match (SM/ceres_scan_matcher_3d.h:41-61, .cc:63-123; options
+ *      C/mapping/proto/scan_matching/ceres_scan_matcher_options_3d.proto + C/common/proto/ceres_solver_options.proto)
+ * The Levenberg-Marquardt loop (Ceres 1.13 TrustRegionMinimizer semantics) runs entirely on the device. ------ */
+#define DL_MAX_PAIRS 4
+typedef struct dl_ceres_options {
+  int32_t num_occupied_space_weights;
+  double occupied_space_weight[DL_MAX_PAIRS];
+  double translation_weight;
+  double rotation_weight;
+  int32_t only_optimize_yaw;
+  int32_t use_nonmonotonic_steps;
+  int32_t max_num_iterations;
+  int32_t num_threads; /* accepted and ignored (ceres_solver_options.proto) */
+} dl_ceres_options;
+typedef struct dl_solve_summary { /* the subset of ceres::Solver::Summary the reference reads (LTB:543) + counters */
+  double initial_cost;
+  double final_cost;
+  int32_t num_iterations; /* recorded iterations incl. iteration 0 */
+  int32_t num_successful_steps;
+  int32_t num_unsuccessful_steps;
+  int32_t termination; /* 0 CONVERGENCE, 1 NO_CONVERGENCE, 2 FAILURE */
+  int32_t num_evaluations;
+  int32_t reserved;
+} dl_solve_summary;
+int dl_ceres_match(dl_context* ctx, const dl_ceres_options* options, const double* target_translation,
+                   const double* initial_pose, int32_t num_pairs, const float* const* clouds, const int64_t* sizes,
+                   const dl_grid* const* grids, double* pose_out, dl_solve_summary* summary);
+/* `count` independent problems in one launch (the ConstraintBuilder3D fan-out, and multi-trajectory front ends).
+ * Arrays are indexed [problem * num_pairs + pair]; poses / targets are count rows. */
+int dl_ceres_match_batch(dl_context* ctx, const dl_ceres_options* options, int32_t count, int32_t num_pairs,
+                         const double* target_translations, const double* initial_poses,
+                         const float* const* clouds, const int64_t* sizes, const dl_grid* const* grids,
+                         double* poses_out, dl_solve_summary* summaries);
+/* Cost, local gradient (6) and J^T J (6x6 row-major) at `at_pose` — the quantities the device reduction feeds
+ * to the LM loop — for kernel-level checks. */
+int dl_ceres_normal_equations(dl_context* ctx, const dl_ceres_options* options, const double* target_translation,
+                              const double* reference_pose, const double* at_pose, int32_t num_pairs,
+                              const float* const* clouds, const int64_t* sizes, const dl_grid* const* grids,
+                              double* cost, double* gradient6, double* hessian36);
+
+/* ---- the per-scan front end of LocalTrajectoryBuilder3D::AddRangeData / AddAccumulatedRangeData
+ *      (LTB:393-554): voxel filter -> deskew/transform/range gate -> voxel filter -> adaptive filters ->
+ *      [RT-CSM] -> Ceres match, for a batch of independent scans against one submap. ---------------------------- */
+typedef struct dl_frontend_options { /* C/mapping/proto/3d/local_trajectory_builder_options_3d.proto */
+  float min_range;
+  float max_range;
+  float voxel_filter_size;
+  dl_adaptive_voxel_filter_options high_resolution_adaptive_voxel_filter;
+  dl_adaptive_voxel_filter_options low_resolution_adaptive_voxel_filter;
+  int32_t use_online_correlative_scan_matching;
+  double scan_period;
+  dl_rtcsm_options real_time_correlative_scan_matcher;
+  dl_ceres_options ceres_scan_matcher;
+} dl_frontend_options;
+
+typedef struct dl_scan_result {
+  double pose_estimate_local[7];          /* matching_submap->local_pose() * pose_observation_in_submap (LTB:553) */
+  double pose_observation_in_submap[7];
+  dl_solve_summary summary;
+  float rtcsm_score;
+  int32_t ok;                             /* 0 = dropped (empty cloud), like the reference's nullptr */
+  int32_t num_first_filter, num_returns, num_misses, num_high_resolution, num_low_resolution;
+  int32_t reserved;
+} dl_scan_result;
+
+/* Scan ingest only (LTB:393-487). ranges: n RangeMeasurement rows (32 bytes: x y z t + uint64 origin index);
+ * origins: 3 floats per sensor. Outputs have capacity n rows. counts_out[4] = {first filter survivors,
+ * returns (local frame, before 2nd filter), returns in tracking frame, misses in tracking frame}. */
+int dl_ingest_scan(dl_context* ctx, const dl_frontend_options* options, const void* ranges, int64_t n,
+                   const float* origins, int32_t num_origins, const double* prev_pose, const double* predicted_pose,
+                   int64_t* first_keep_out, float* returns_local_out, float* returns_tracking_out,
+                   float* misses_tracking_out, float* current_pose7f_out, int64_t* counts_out);
+
+/* Whole hot path for `num_scans` scans; host buffers, copies included (this is the "e2e" call). */
+int dl_frontend_match_batch(dl_context* ctx, const dl_frontend_options* options, int32_t num_scans,
+                            const void* const* ranges, const int64_t* sizes, const float* origins,
+                            int32_t num_origins, const double* prev_poses, const double* predicted_poses,
+                            const double* submap_local_pose, const dl_grid* high_resolution_grid,
+                            const dl_grid* low_resolution_grid, dl_scan_result* results);
+
+/* Device-resident variant: ranges_dev is ONE device buffer of num_scans * cap_rows RangeMeasurement rows; scan s
+ * occupies rows [s * cap_rows, s * cap_rows + sizes[s]). Results stay in results_dev (device) until
+ * dl_frontend_fetch_results copies them out. No scan data is copied from or to the host inside this call. */
+int dl_frontend_match_batch_dev(dl_context* ctx, const dl_frontend_options* options, int32_t num_scans,
+                                const void* ranges_dev, int64_t cap_rows, const int64_t* sizes,
+                                const float* origins, int32_t num_origins, const double* prev_poses,
+                                const double* predicted_poses, const double* submap_local_pose,
+                                const dl_grid* high_resolution_grid, const dl_grid* low_resolution_grid,
+                                dl_scan_result* results_dev);
+int dl_frontend_fetch_results(dl_context* ctx, const dl_scan_result* results_dev, int32_t num_scans,
+                              dl_scan_result* results);
+
+/* Device memory helpers so a host language without CUDA bindings can stage buffers. */
+int dl_device_alloc(dl_context* ctx, int64_t bytes, void** out_dev);
+int dl_device_free(dl_context* ctx, void* dev);
+int dl_copy_to_device(dl_context* ctx, void* dst_dev, const void* src_host, int64_t bytes);
+int dl_copy_to_host(dl_context* ctx, void* dst_host, const void* src_dev, int64_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DLIOM_B200_H_ */
