@@ -174,12 +174,12 @@ __device__ void evaluate(const NlsOptions& opt, const NlsProblem& prob, Shared& 
       const double jx = -s * gx, jy = -s * gy, jz = -s * gz;
       const Vec3d dw = mul(2.0, cross3(a, v));                       // d/d qw
       const double av = dot3(a, v);
-      // d/d a_j = 2 qw (e_j x v) + 2 (e_j (a.v) + a v_j - 2 v a_j)
-      const Vec3d dxv{2. * (av + a.x * v.x - 2. * v.x * a.x), 2. * (q.w * v.z + a.y * v.x - 2. * v.y * a.x),
-                      2. * (-q.w * v.y + a.z * v.x - 2. * v.z * a.x)};
-      const Vec3d dyv{2. * (-q.w * v.z + a.x * v.y - 2. * v.x * a.y), 2. * (av + a.y * v.y - 2. * v.y * a.y),
-                      2. * (q.w * v.x + a.z * v.y - 2. * v.z * a.y)};
-      const Vec3d dzv{2. * (q.w * v.y + a.x * v.z - 2. * v.x * a.z), 2. * (-q.w * v.x + a.y * v.z - 2. * v.y * a.z),
+      // d/d a_j = 2 qw (e_j x v) + 2 (e_j (a.v) + a v_j - 2 v a_j), e_x x v = (0, -v_z, v_y) etc.
+      const Vec3d dxv{2. * (av + a.x * v.x - 2. * v.x * a.x), 2. * (-q.w * v.z + a.y * v.x - 2. * v.y * a.x),
+                      2. * (q.w * v.y + a.z * v.x - 2. * v.z * a.x)};
+      const Vec3d dyv{2. * (q.w * v.z + a.x * v.y - 2. * v.x * a.y), 2. * (av + a.y * v.y - 2. * v.y * a.y),
+                      2. * (-q.w * v.x + a.z * v.y - 2. * v.z * a.y)};
+      const Vec3d dzv{2. * (-q.w * v.y + a.x * v.z - 2. * v.x * a.z), 2. * (q.w * v.x + a.y * v.z - 2. * v.y * a.z),
                       2. * (av + a.z * v.z - 2. * v.z * a.z)};
       const double gq0 = jx * dw.x + jy * dw.y + jz * dw.z;
       const double gq1 = jx * dxv.x + jy * dxv.y + jz * dxv.z;
