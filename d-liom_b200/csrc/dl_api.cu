@@ -38,6 +38,25 @@ int dl_context::reserve_pinned(size_t bytes) {
   return DL_OK;
 }
 
+int dl_context::stage_id(const char* name) {
+  for (size_t i = 0; i < stage_names.size(); ++i)
+    if (stage_names[i] == name) return (int)i;
+  stage_names.push_back(name);
+  stage_ms.push_back(0.0);
+  stage_calls.push_back(0);
+  return (int)stage_names.size() - 1;
+}
+cudaEvent_t dl_context::take_event() {
+  if (!event_pool.empty()) {
+    cudaEvent_t e = event_pool.back();
+    event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
 namespace {
 thread_local std::string g_create_error;
 
@@ -111,6 +130,8 @@ void dl_context_destroy(dl_context* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (const dl_context::Mark& m : ctx->marks) { cudaEventDestroy(m.begin); cudaEventDestroy(m.end); }
+  for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -135,6 +156,36 @@ uint64_t dl_context_stream(const dl_context* ctx) { return ctx ? (uint64_t)(uint
 int dl_context_synchronize(dl_context* ctx) {
   if (!ctx) return DL_ERR_ARG;
   return sync(ctx);
+}
+int dl_context_set_profiling(dl_context* ctx, int enabled) {
+  if (!ctx) return DL_ERR_ARG;
+  ctx->profiling = enabled != 0;
+  return DL_OK;
+}
+int dl_context_read_profile(dl_context* ctx, dl_stage_time* out, int32_t capacity, int32_t* num_stages) {
+  if (!ctx || !num_stages || capacity < 0 || (capacity > 0 && !out)) return DL_ERR_ARG;
+  DL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (const dl_context::Mark& m : ctx->marks) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, m.begin, m.end) == cudaSuccess) {
+      ctx->stage_ms[m.stage] += ms;
+      ctx->stage_calls[m.stage] += 1;
+    }
+    ctx->event_pool.push_back(m.begin);
+    ctx->event_pool.push_back(m.end);
+  }
+  ctx->marks.clear();
+  const int n = (int)std::min<size_t>(ctx->stage_names.size(), (size_t)capacity);
+  for (int i = 0; i < n; ++i) {
+    std::memset(out[i].name, 0, sizeof(out[i].name));
+    std::strncpy(out[i].name, ctx->stage_names[i].c_str(), sizeof(out[i].name) - 1);
+    out[i].ms = ctx->stage_ms[i];
+    out[i].calls = ctx->stage_calls[i];
+    ctx->stage_ms[i] = 0.0;
+    ctx->stage_calls[i] = 0;
+  }
+  *num_stages = n;
+  return DL_OK;
 }
 
 int dl_device_alloc(dl_context* ctx, int64_t bytes, void** out_dev) {
@@ -364,7 +415,7 @@ int dl_adaptive_voxel_filter(dl_context* ctx, const dl_adaptive_voxel_filter_opt
   DL_TRY(h2d(ctx, d_counts, &n32, 1));
   DL_TRY(h2d(ctx, d_params, &params, 1));
   DL_TRY(launch_adaptive_voxel_filter(ctx, d_pts, stride, n, d_counts, 1, d_params, 1, d_table, tcap, d_scratch, d_keep,
-                                      d_counts + 1, d_passes, d_counts + 2));
+                                      d_counts + 1, d_passes, d_counts + 2, nullptr));
   int32_t res[2] = {0, 0};
   float passes[32];
   DL_TRY(d2h(ctx, res, d_counts + 1, 2));
@@ -646,7 +697,7 @@ struct FrontendBuffers {
   int batch = 0;
   int64_t cap = 0, tcap = 0;
   int tiles = 0;
-  int32_t *counts0, *n1, *n_ret, *n_miss, *n2, *n3, *countsA, *npassesA, *block_counts, *tile_counts;
+  int32_t *counts0, *n1, *n_ret, *n_miss, *n2, *n3, *countsA, *npassesA, *croppedA, *block_counts, *tile_counts;
   uint32_t *table, *slot, *tableA, *scratchA;
   int32_t *keep1, *keep2, *keep3, *keepA;
   float *tmp_points, *returns_local, *misses_local, *returns_tracking, *misses_tracking, *clouds, *current_pose, *origins,
@@ -663,7 +714,7 @@ size_t frontend_bytes(int batch, int64_t cap, int num_origins, size_t extra) {
   const size_t B = (size_t)batch, C = (size_t)cap;
   const size_t tcap = (size_t)next_pow2(2 * cap);
   const size_t tiles = (C + 255) / 256;
-  return arena_bytes({B * 4, B * 4, B * 4, B * 4, B * 4, B * 4, B * 8, B * 8, B * tiles * 4, B * tiles * 8,
+  return arena_bytes({B * 4, B * 4, B * 4, B * 4, B * 4, B * 4, B * 8, B * 8, B * 8, B * tiles * 4, B * tiles * 8,
                       B * tcap * 4, B * C * 4, B * 2 * tcap * 4, B * 4 * C * 4,
                       B * C * 4, B * C * 4, B * C * 4, B * 2 * C * 4,
                       B * C * 12, B * C * 12, B * C * 12, B * C * 12, B * C * 12, B * 2 * C * 12, B * 28, (size_t)num_origins * 12,
@@ -679,6 +730,7 @@ void carve(Arena& a, int batch, int64_t cap, int num_origins, FrontendBuffers* f
   f->tiles = (int)((cap + 255) / 256);
   f->counts0 = a.take<int32_t>(B); f->n1 = a.take<int32_t>(B); f->n_ret = a.take<int32_t>(B); f->n_miss = a.take<int32_t>(B);
   f->n2 = a.take<int32_t>(B); f->n3 = a.take<int32_t>(B); f->countsA = a.take<int32_t>(2 * B); f->npassesA = a.take<int32_t>(2 * B);
+  f->croppedA = a.take<int32_t>(2 * B);
   f->block_counts = a.take<int32_t>(B * f->tiles); f->tile_counts = a.take<int32_t>(B * f->tiles * 2);
   f->table = a.take<uint32_t>(B * f->tcap); f->slot = a.take<uint32_t>(B * C);
   f->tableA = a.take<uint32_t>(B * 2 * f->tcap); f->scratchA = a.take<uint32_t>(B * 4 * C);
@@ -713,15 +765,22 @@ ScanConstants make_scan_constants(const double* prev7, const double* cur7) {
 // Stages 1-3: first voxel filter, deskew/transform/gate, second voxel filters, back to the tracking frame.
 int frontend_ingest(dl_context* ctx, const dl_frontend_options& o, const FrontendBuffers& f, const float* d_ranges,
                     int64_t in_cap) {
-  DL_TRY(launch_voxel_filter(ctx, d_ranges, 8, in_cap, f.counts0, f.batch, 0.5f * o.voxel_filter_size, f.table, f.tcap,
-                             f.slot, f.keep1, f.n1, f.block_counts));
+  {
+    StageScope st(ctx, "voxel_filter_first");
+    DL_TRY(launch_voxel_filter(ctx, d_ranges, 8, in_cap, f.counts0, f.batch, 0.5f * o.voxel_filter_size, f.table, f.tcap,
+                               f.slot, f.keep1, f.n1, f.block_counts));
+  }
   IngestArgs ia{};
   ia.ranges = d_ranges; ia.in_cap = in_cap; ia.scans = f.scans; ia.origins = f.origins; ia.keep = f.keep1;
   ia.keep_counts = f.n1; ia.cap = f.cap; ia.tiles = f.tiles; ia.min_range = o.min_range; ia.max_range = o.max_range;
   ia.scan_period = o.scan_period; ia.tmp_points = f.tmp_points; ia.cls = f.cls; ia.tile_counts = f.tile_counts;
   ia.returns_local = f.returns_local; ia.misses_local = f.misses_local; ia.num_returns = f.n_ret; ia.num_misses = f.n_miss;
   ia.current_pose = f.current_pose;
-  DL_TRY(launch_ingest(ctx, ia, f.batch));
+  {
+    StageScope st(ctx, "deskew_transform_gate");
+    DL_TRY(launch_ingest(ctx, ia, f.batch));
+  }
+  StageScope st2(ctx, "voxel_filter_second");
   DL_TRY(launch_voxel_filter(ctx, f.returns_local, 3, f.cap, f.n_ret, f.batch, o.voxel_filter_size, f.table, f.tcap, f.slot,
                              f.keep2, f.n2, f.block_counts));
   DL_TRY(launch_gather_to_tracking(ctx, f.returns_local, f.cap, f.keep2, f.n2, f.current_pose, f.returns_tracking, f.batch));
@@ -761,8 +820,11 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, c
   DL_TRY(frontend_upload_small(ctx, o, f, sizes, origins, num_origins, prev_poses, cur_poses));
   DL_TRY(frontend_ingest(ctx, o, f, d_ranges, in_cap));
   // adaptive voxel filters (high, low resolution) on the tracking-frame returns: one CTA per (scan, filter)
-  DL_TRY(launch_adaptive_voxel_filter(ctx, f.returns_tracking, 3, f.cap, f.n2, f.batch, f.filters, 2, f.tableA, f.tcap,
-                                      f.scratchA, f.keepA, f.countsA, f.passesA, f.npassesA));
+  {
+    StageScope st(ctx, "adaptive_voxel_filter");
+    DL_TRY(launch_adaptive_voxel_filter(ctx, f.returns_tracking, 3, f.cap, f.n2, f.batch, f.filters, 2, f.tableA, f.tcap,
+                                        f.scratchA, f.keepA, f.countsA, f.passesA, f.npassesA, f.croppedA));
+  }
   DL_TRY(launch_gather_rows(ctx, f.returns_tracking, f.cap, 2, f.keepA, f.countsA, f.cap, f.clouds, 2 * f.batch));
   const Rigidd submap = pose_from7(submap_local_pose);
   DL_TRY(launch_initial_pose(ctx, f.batch, f.current_pose, inverse(submap), f.initial_pose, f.target));
@@ -776,6 +838,7 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, c
     DL_TRY(d2h(ctx, init.data(), f.initial_pose, 7 * f.batch));
     DL_TRY(sync(ctx));
     std::vector<float> scores(f.batch, 0.f);
+    StageScope st(ctx, "rtcsm");
     const size_t mark = a.off;
     for (int b = 0; b < f.batch; ++b) {
       if (countsA[2 * b] <= 0) continue;
@@ -804,9 +867,13 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, c
   }
   DL_TRY(h2d(ctx, f.problems, problems.data(), f.batch));
   DL_TRY(sync(ctx));
-  DL_TRY(launch_nls(ctx, to_nls_options(o.ceres_scan_matcher, 2), f.problems, f.batch, f.nls_out));
+  {
+    StageScope st(ctx, "nls_solve");
+    DL_TRY(launch_nls(ctx, to_nls_options(o.ceres_scan_matcher, 2), f.problems, f.batch, f.nls_out));
+  }
   ResultArgs ra{};
   ra.batch = f.batch; ra.first_counts = f.n1; ra.return_counts = f.n2; ra.miss_counts = f.n3; ra.adaptive_counts = f.countsA;
+  ra.adaptive_cropped = f.croppedA; ra.adaptive_passes = f.npassesA;
   ra.rtcsm_scores = have_scores ? f.rtcsm_scores : nullptr; ra.nls = f.nls_out; ra.submap = submap; ra.results = d_results;
   DL_TRY(launch_finalize_results(ctx, ra));
   return DL_OK;

@@ -199,6 +199,10 @@ __global__ void finalize_results_kernel(ResultArgs a) {
   r.num_misses = a.miss_counts[b];
   r.num_high_resolution = n_hi;
   r.num_low_resolution = n_lo;
+  r.num_cropped_high = a.adaptive_cropped[2 * b];
+  r.num_cropped_low = a.adaptive_cropped[2 * b + 1];
+  r.num_passes_high = a.adaptive_passes[2 * b];
+  r.num_passes_low = a.adaptive_passes[2 * b + 1];
   r.rtcsm_score = a.rtcsm_scores ? a.rtcsm_scores[b] : 0.f;
   r.reserved = 0;
   // the reference drops the scan when any of the three clouds is empty (LTB:497-500, :510-513, :531-534)

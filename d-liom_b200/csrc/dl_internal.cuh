@@ -53,6 +53,19 @@ struct dl_context {
   size_t d_scratch_bytes = 0;
   void* h_pinned = nullptr;
   size_t h_pinned_bytes = 0;
+  // optional per-stage timing (events recorded on `stream`)
+  bool profiling = false;
+  struct Mark {
+    int stage;
+    cudaEvent_t begin, end;
+  };
+  std::vector<Mark> marks;
+  std::vector<cudaEvent_t> event_pool;
+  std::vector<std::string> stage_names;
+  std::vector<double> stage_ms;
+  std::vector<int64_t> stage_calls;
+  int stage_id(const char* name);
+  cudaEvent_t take_event();
 
   int fail(int status, const std::string& msg) {
     error = msg;
@@ -99,6 +112,22 @@ struct dl_grid {
 
 namespace dl {
 
+// RAII stage bracket: records begin/end events on the context stream when profiling is on.
+struct StageScope {
+  dl_context* ctx;
+  int mark = -1;
+  StageScope(dl_context* c, const char* name) : ctx(c) {
+    if (!c->profiling) return;
+    dl_context::Mark m{c->stage_id(name), c->take_event(), c->take_event()};
+    cudaEventRecord(m.begin, c->stream);
+    mark = (int)c->marks.size();
+    c->marks.push_back(m);
+  }
+  ~StageScope() {
+    if (mark >= 0) cudaEventRecord(ctx->marks[mark].end, ctx->stream);
+  }
+};
+
 struct Arena {  // bump allocator over the context's device scratch
   char* base;
   size_t off = 0;
@@ -135,7 +164,8 @@ struct AdaptiveParams {
 int launch_adaptive_voxel_filter(dl_context* ctx, const float* points, int stride, int64_t cap, const int32_t* counts,
                                  int batch, const AdaptiveParams* filters_dev, int num_filters, uint32_t* table,
                                  int64_t table_cap, uint32_t* scratch /* pairs * 2 * cap */, int32_t* keep, int32_t* keep_counts,
-                                 float* passes /* (batch*num_filters) * 32 */, int32_t* num_passes);
+                                 float* passes /* (batch*num_filters) * 32 */, int32_t* num_passes,
+                                 int32_t* cropped_counts /* optional, batch*num_filters */);
 
 struct RtcsmLaunch {
   const float* points;  // n x 3

@@ -40,6 +40,8 @@ struct ResultArgs {
   const int32_t* return_counts;
   const int32_t* miss_counts;
   const int32_t* adaptive_counts;  // 2 per scan: high, low resolution
+  const int32_t* adaptive_cropped;
+  const int32_t* adaptive_passes;
   const float* rtcsm_scores;       // optional
   const NlsOutput* nls;
   Rigidd submap;

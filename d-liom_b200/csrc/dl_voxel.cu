@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kAdaptiveBlock) adaptive_voxel_kernel(
     const float* __restrict__ points, int stride, int64_t cap, const int32_t* __restrict__ counts,
     const AdaptiveParams* __restrict__ filters, int num_filters, uint32_t* table, int64_t table_cap,
     uint32_t* scratch /* per pair: cap cropped rows + cap slots */, int32_t* keep, int32_t* keep_counts,
-    float* passes, int32_t* num_passes) {
+    float* passes, int32_t* num_passes, int32_t* cropped_counts) {
   const int pair = blockIdx.x;
   const int b = pair / num_filters;
   const AdaptiveParams opt = filters[pair % num_filters];
@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(kAdaptiveBlock) adaptive_voxel_kernel(
       },
       [&](int pos, int i) { rows[pos] = (uint32_t)i; });
 
+  if (threadIdx.x == 0 && cropped_counts) cropped_counts[pair] = m;
   auto finish_all = [&]() {  // 'point_cloud' is already sparse enough
     for (int j = threadIdx.x; j < m; j += kAdaptiveBlock) out[j] = (int32_t)rows[j];
     if (threadIdx.x == 0) {
@@ -318,11 +319,11 @@ int launch_voxel_indices(dl_context* ctx, const float* points, int stride, int64
 int launch_adaptive_voxel_filter(dl_context* ctx, const float* points, int stride, int64_t cap, const int32_t* counts,
                                  int batch, const AdaptiveParams* filters_dev, int num_filters, uint32_t* table,
                                  int64_t table_cap, uint32_t* scratch, int32_t* keep, int32_t* keep_counts,
-                                 float* passes, int32_t* num_passes) {
+                                 float* passes, int32_t* num_passes, int32_t* cropped_counts) {
   if (batch <= 0 || num_filters <= 0) return DL_OK;
   adaptive_voxel_kernel<<<batch * num_filters, kAdaptiveBlock, 0, ctx->stream>>>(
       points, stride, cap, counts, filters_dev, num_filters, table, table_cap, scratch, keep, keep_counts, passes,
-      num_passes);
+      num_passes, cropped_counts);
   DL_LAUNCH_CHECK(ctx, "adaptive_voxel_kernel");
   return DL_OK;
 }

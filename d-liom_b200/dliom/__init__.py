@@ -21,7 +21,7 @@ u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
 DL_MAX_PAIRS = 4
 EXPORTS = [
     "dl_context_create", "dl_context_destroy", "dl_last_error", "dl_status_string", "dl_context_kernel_launches",
-    "dl_context_stream", "dl_context_synchronize", "dl_grid_create", "dl_grid_destroy", "dl_grid_set_cells",
+    "dl_context_stream", "dl_context_synchronize", "dl_context_set_profiling", "dl_context_read_profile", "dl_grid_create", "dl_grid_destroy", "dl_grid_set_cells",
     "dl_grid_sync", "dl_grid_resolution", "dl_grid_num_bricks", "dl_grid_lookup", "dl_grid_interpolate",
     "dl_voxel_filter", "dl_voxel_indices", "dl_adaptive_voxel_filter", "dl_rtcsm_match", "dl_ceres_match",
     "dl_ceres_match_batch", "dl_ceres_normal_equations", "dl_ingest_scan", "dl_frontend_match_batch",
@@ -34,6 +34,10 @@ class DlError(RuntimeError):
     def __init__(self, status, message):
         super().__init__(f"dliom_b200 status {status}: {message}")
         self.status = status
+
+
+class StageTime(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("ms", C.c_double), ("calls", C.c_int64)]
 
 
 class AdaptiveVoxelFilterOptions(C.Structure):
@@ -105,7 +109,9 @@ class ScanResult(C.Structure):
     _fields_ = [("pose_estimate_local", C.c_double * 7), ("pose_observation_in_submap", C.c_double * 7),
                 ("summary", SolveSummary), ("rtcsm_score", C.c_float), ("ok", C.c_int32),
                 ("num_first_filter", C.c_int32), ("num_returns", C.c_int32), ("num_misses", C.c_int32),
-                ("num_high_resolution", C.c_int32), ("num_low_resolution", C.c_int32), ("reserved", C.c_int32)]
+                ("num_high_resolution", C.c_int32), ("num_low_resolution", C.c_int32),
+                ("num_cropped_high", C.c_int32), ("num_cropped_low", C.c_int32), ("num_passes_high", C.c_int32),
+                ("num_passes_low", C.c_int32), ("reserved", C.c_int32)]
 
 
 def lib():
@@ -128,6 +134,8 @@ def lib():
     L.dl_context_stream.argtypes = [vp]
     L.dl_context_stream.restype = C.c_uint64
     L.dl_context_synchronize.argtypes = [vp]
+    L.dl_context_set_profiling.argtypes = [vp, C.c_int]
+    L.dl_context_read_profile.argtypes = [vp, ip(StageTime), C.c_int32, ip(C.c_int32)]
     L.dl_grid_create.argtypes = [vp, C.c_float, ip(vp)]
     L.dl_grid_destroy.argtypes = [vp]
     L.dl_grid_destroy.restype = None
@@ -196,6 +204,16 @@ class Context:
 
     def synchronize(self):
         self.check(self.L.dl_context_synchronize(self.h))
+
+    def set_profiling(self, on):
+        self.check(self.L.dl_context_set_profiling(self.h, int(on)))
+
+    def read_profile(self):
+        """{stage: (total ms, calls)} since the last read (device time between CUDA events on the context stream)."""
+        buf = (StageTime * 16)()
+        n = C.c_int32(0)
+        self.check(self.L.dl_context_read_profile(self.h, buf, 16, C.byref(n)))
+        return {buf[i].name.decode(): (buf[i].ms, buf[i].calls) for i in range(n.value)}
 
     # ---- grid
     def grid(self, resolution):

@@ -44,6 +44,16 @@ const char* dl_last_error(const dl_context* ctx);
 const char* dl_status_string(int status);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t dl_context_kernel_launches(const dl_context* ctx);
+/* Per-stage device timing of the front end (CUDA events on the context's stream). When enabled, every
+ * dl_frontend_* call brackets its stages with events; dl_context_read_profile synchronises, returns the
+ * accumulated milliseconds and call counts per stage since the last read, and resets them. */
+typedef struct dl_stage_time {
+  char name[32];
+  double ms;
+  int64_t calls;
+} dl_stage_time;
+int dl_context_set_profiling(dl_context* ctx, int enabled);
+int dl_context_read_profile(dl_context* ctx, dl_stage_time* out, int32_t capacity, int32_t* num_stages);
 /* The context's cudaStream_t as an integer, and a blocking wait on it. */
 uint64_t dl_context_stream(const dl_context* ctx);
 int dl_context_synchronize(dl_context* ctx);
@@ -169,6 +179,8 @@ typedef struct dl_scan_result {
   float rtcsm_score;
   int32_t ok;                             /* 0 = dropped (empty cloud), like the reference's nullptr */
   int32_t num_first_filter, num_returns, num_misses, num_high_resolution, num_low_resolution;
+  /* adaptive filter bookkeeping: points inside max_range and voxel passes run, per filter (high, low) */
+  int32_t num_cropped_high, num_cropped_low, num_passes_high, num_passes_low;
   int32_t reserved;
 } dl_scan_result;
 

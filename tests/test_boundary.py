@@ -29,7 +29,7 @@ def test_struct_layouts_match_header():
     import dliom
     assert ctypes.sizeof(dliom.SolveSummary) == 40
     assert ctypes.sizeof(dliom.CeresOptions) == 8 + 8 * 4 + 16 + 16
-    assert ctypes.sizeof(dliom.ScanResult) == 56 * 2 + 40 + 8 * 4
+    assert ctypes.sizeof(dliom.ScanResult) == 56 * 2 + 40 + 12 * 4
     assert ctypes.sizeof(dliom.RtcsmInfo) == 32
 
 
