@@ -1,0 +1,201 @@
+// Header-only C++ mirror of the reference's matcher / filter classes over the dliom_b200 C-ABI.
+//
+// Same class names, argument meaning and call shapes as the reference interfaces they replace
+// (C/ = src/cartographer/cartographer/, SM/ = C/mapping/internal/3d/scan_matching/):
+//   sensor::VoxelFilter, sensor::AdaptiveVoxelFilter        C/sensor/internal/voxel_filter.h:34-79
+//   scan_matching::RealTimeCorrelativeScanMatcher3D          SM/real_time_correlative_scan_matcher_3d.h:33-60
+//   scan_matching::CeresScanMatcher3D                        SM/ceres_scan_matcher_3d.h:34-61
+// Eigen / protobuf types are replaced by the plain structs below (this image has neither); INTEGRATION.md shows
+// the three-line adapters for Eigen::Vector3f / transform::Rigid3d / proto options in a real Cartographer tree.
+// Errors: the reference CHECK-aborts; this shim throws dliom::Error carrying the C-ABI status and message.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/dliom_b200.h"
+
+namespace dliom {
+
+struct Error : std::runtime_error {
+  int status;
+  Error(int s, const std::string& m) : std::runtime_error(m), status(s) {}
+};
+
+struct Rigid3d {  // transform::Rigid3d: translation + rotation quaternion (w, x, y, z)
+  double t[3] = {0, 0, 0};
+  double q[4] = {1, 0, 0, 0};
+  void to7(double* p) const { for (int i = 0; i < 3; ++i) p[i] = t[i]; for (int i = 0; i < 4; ++i) p[3 + i] = q[i]; }
+  static Rigid3d from7(const double* p) { Rigid3d r; for (int i = 0; i < 3; ++i) r.t[i] = p[i]; for (int i = 0; i < 4; ++i) r.q[i] = p[3 + i]; return r; }
+};
+using PointCloud = std::vector<std::array<float, 3>>;       // sensor::PointCloud
+using TimedPointCloud = std::vector<std::array<float, 4>>;  // sensor::TimedPointCloud
+
+class Context {  // one per host thread (re-entrancy contract of CeresScanMatcher3D::Match)
+ public:
+  explicit Context(int device = 0) {
+    const int st = dl_context_create(device, &ctx_);
+    if (st != DL_OK) throw Error(st, dl_last_error(nullptr));
+  }
+  ~Context() { dl_context_destroy(ctx_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  dl_context* get() const { return ctx_; }
+  void check(int st) const { if (st != DL_OK) throw Error(st, dl_last_error(ctx_)); }
+ private:
+  dl_context* ctx_ = nullptr;
+};
+
+// Device mirror of a mapping::HybridGrid. Fill from `for (auto it : hybrid_grid)` (x, y, z, value), or from
+// HybridGrid::ToProto()'s parallel arrays; call Update() with the touched cells after each InsertRangeData.
+class DeviceHybridGrid {
+ public:
+  DeviceHybridGrid(Context* ctx, float resolution) : ctx_(ctx) { ctx->check(dl_grid_create(ctx->get(), resolution, &grid_)); }
+  ~DeviceHybridGrid() { dl_grid_destroy(grid_); }
+  DeviceHybridGrid(const DeviceHybridGrid&) = delete;
+  DeviceHybridGrid& operator=(const DeviceHybridGrid&) = delete;
+  void Update(const std::vector<int32_t>& x, const std::vector<int32_t>& y, const std::vector<int32_t>& z,
+              const std::vector<uint16_t>& value) {
+    ctx_->check(dl_grid_set_cells(grid_, (int64_t)x.size(), x.data(), y.data(), z.data(), value.data()));
+    ctx_->check(dl_grid_sync(grid_));
+  }
+  float resolution() const { return dl_grid_resolution(grid_); }
+  const dl_grid* get() const { return grid_; }
+ private:
+  Context* ctx_;
+  dl_grid* grid_ = nullptr;
+};
+
+namespace sensor {
+
+class VoxelFilter {  // voxel_filter.h:34-62 (hot-path use: a temporary per call, LTB:393-395, :479-484)
+ public:
+  VoxelFilter(Context* ctx, float size) : ctx_(ctx), resolution_(size) {}
+  PointCloud Filter(const PointCloud& point_cloud) { return FilterRows(point_cloud); }
+  TimedPointCloud Filter(const TimedPointCloud& timed_point_cloud) { return FilterRows(timed_point_cloud); }
+ private:
+  template <typename Cloud>
+  Cloud FilterRows(const Cloud& in) {
+    std::vector<int64_t> keep(in.size() ? in.size() : 1);
+    int64_t n_keep = 0;
+    ctx_->check(dl_voxel_filter(ctx_->get(), in.empty() ? nullptr : in[0].data(), (int64_t)in.size(),
+                                (int)(sizeof(in[0]) / sizeof(float)), resolution_, keep.data(), &n_keep));
+    Cloud out;
+    out.reserve(n_keep);
+    for (int64_t i = 0; i < n_keep; ++i) out.push_back(in[keep[i]]);
+    return out;
+  }
+  Context* ctx_;
+  float resolution_;
+};
+
+struct AdaptiveVoxelFilterOptions {  // proto::AdaptiveVoxelFilterOptions
+  float max_length, min_num_points, max_range;
+};
+class AdaptiveVoxelFilter {  // voxel_filter.h:66-79
+ public:
+  AdaptiveVoxelFilter(Context* ctx, const AdaptiveVoxelFilterOptions& options) : ctx_(ctx), options_(options) {}
+  PointCloud Filter(const PointCloud& point_cloud) const {
+    std::vector<int64_t> keep(point_cloud.size() ? point_cloud.size() : 1);
+    int64_t n_keep = 0;
+    const dl_adaptive_voxel_filter_options o{options_.max_length, options_.min_num_points, options_.max_range};
+    ctx_->check(dl_adaptive_voxel_filter(ctx_->get(), &o, point_cloud.empty() ? nullptr : point_cloud[0].data(),
+                                         (int64_t)point_cloud.size(), 3, keep.data(), &n_keep, nullptr, nullptr));
+    PointCloud out;
+    out.reserve(n_keep);
+    for (int64_t i = 0; i < n_keep; ++i) out.push_back(point_cloud[keep[i]]);
+    return out;
+  }
+ private:
+  Context* ctx_;
+  AdaptiveVoxelFilterOptions options_;
+};
+
+}  // namespace sensor
+
+namespace scan_matching {
+
+struct RealTimeCorrelativeScanMatcherOptions {  // proto::RealTimeCorrelativeScanMatcherOptions
+  double linear_search_window, angular_search_window, translation_delta_cost_weight, rotation_delta_cost_weight;
+};
+class RealTimeCorrelativeScanMatcher3D {  // real_time_correlative_scan_matcher_3d.h:33-60
+ public:
+  RealTimeCorrelativeScanMatcher3D(Context* ctx, const RealTimeCorrelativeScanMatcherOptions& options)
+      : ctx_(ctx), options_(options) {}
+  // Returns the best score; *pose_estimate receives the best candidate (CHECK_NOTNULL in the reference).
+  float Match(const Rigid3d& initial_pose_estimate, const PointCloud& point_cloud, const DeviceHybridGrid& hybrid_grid,
+              Rigid3d* pose_estimate) const {
+    if (!pose_estimate) throw Error(DL_ERR_ARG, "pose_estimate is null");
+    const dl_rtcsm_options o{options_.linear_search_window, options_.angular_search_window,
+                             options_.translation_delta_cost_weight, options_.rotation_delta_cost_weight};
+    double init[7], out[7];
+    initial_pose_estimate.to7(init);
+    float score = 0.f;
+    ctx_->check(dl_rtcsm_match(ctx_->get(), &o, init, point_cloud.empty() ? nullptr : point_cloud[0].data(),
+                               (int64_t)point_cloud.size(), hybrid_grid.get(), out, &score, nullptr, nullptr));
+    *pose_estimate = Rigid3d::from7(out);
+    return score;
+  }
+ private:
+  Context* ctx_;
+  RealTimeCorrelativeScanMatcherOptions options_;
+};
+
+struct CeresScanMatcherOptions3D {  // proto::CeresScanMatcherOptions3D + common::proto::CeresSolverOptions
+  std::vector<double> occupied_space_weight;
+  double translation_weight = 5., rotation_weight = 4e2;
+  bool only_optimize_yaw = false;
+  bool use_nonmonotonic_steps = false;
+  int max_num_iterations = 12;
+  int num_threads = 1;
+};
+struct SolverSummary {  // the fields of ceres::Solver::Summary the reference reads (LTB:543) + counters
+  double initial_cost = 0, final_cost = 0;
+  int num_iterations = 0, num_successful_steps = 0, num_unsuccessful_steps = 0, termination = 1;
+};
+using PointCloudAndHybridGridPointers = std::pair<const PointCloud*, const DeviceHybridGrid*>;
+
+class CeresScanMatcher3D {  // ceres_scan_matcher_3d.h:41-61
+ public:
+  CeresScanMatcher3D(Context* ctx, const CeresScanMatcherOptions3D& options) : ctx_(ctx), options_(options) {}
+  void Match(const std::array<double, 3>& target_translation, const Rigid3d& initial_pose_estimate,
+             const std::vector<PointCloudAndHybridGridPointers>& point_clouds_and_hybrid_grids,
+             Rigid3d* pose_estimate, SolverSummary* summary) const {
+    dl_ceres_options o{};
+    o.num_occupied_space_weights = (int32_t)options_.occupied_space_weight.size();
+    for (size_t i = 0; i < options_.occupied_space_weight.size() && i < DL_MAX_PAIRS; ++i)
+      o.occupied_space_weight[i] = options_.occupied_space_weight[i];
+    o.translation_weight = options_.translation_weight;
+    o.rotation_weight = options_.rotation_weight;
+    o.only_optimize_yaw = options_.only_optimize_yaw;
+    o.use_nonmonotonic_steps = options_.use_nonmonotonic_steps;
+    o.max_num_iterations = options_.max_num_iterations;
+    o.num_threads = options_.num_threads;
+    std::vector<const float*> clouds;
+    std::vector<int64_t> sizes;
+    std::vector<const dl_grid*> grids;
+    for (const auto& pg : point_clouds_and_hybrid_grids) {
+      clouds.push_back(pg.first->empty() ? nullptr : (*pg.first)[0].data());
+      sizes.push_back((int64_t)pg.first->size());
+      grids.push_back(pg.second->get());
+    }
+    double init[7], out[7];
+    initial_pose_estimate.to7(init);
+    dl_solve_summary s{};
+    ctx_->check(dl_ceres_match(ctx_->get(), &o, target_translation.data(), init, (int32_t)clouds.size(), clouds.data(),
+                               sizes.data(), grids.data(), out, &s));
+    *pose_estimate = Rigid3d::from7(out);
+    if (summary)
+      *summary = {s.initial_cost, s.final_cost, s.num_iterations, s.num_successful_steps, s.num_unsuccessful_steps,
+                  s.termination};
+  }
+ private:
+  Context* ctx_;
+  CeresScanMatcherOptions3D options_;
+};
+
+}  // namespace scan_matching
+}  // namespace dliom

@@ -48,3 +48,32 @@ def test_status_strings():
     L = dliom.lib()
     assert L.dl_status_string(0) == b"ok"
     assert b"CUDA" in L.dl_status_string(-1)
+
+
+def _build_example(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "example_match")
+    host = os.path.join(ROOT, "d-liom_b200", "host")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(host, "example_match.cc"), "-o", exe,
+                           "-L" + os.path.join(ROOT, "d-liom_b200"), "-ldliom_b200",
+                           "-Wl,-rpath," + os.path.join(ROOT, "d-liom_b200")])
+    return exe
+
+
+def test_cpp_shim_compiles_and_fails_loudly_without_gpu(tmp_path):
+    """The header-only C++ mirror of the reference classes (d-liom_b200/host) builds against the C-ABI."""
+    import subprocess
+    import torch
+    exe = _build_example(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "dliom error -1" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_shim_reference_matcher_case(tmp_path):
+    import subprocess
+    r = subprocess.run([_build_example(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "voxel filter kept" in r.stdout
