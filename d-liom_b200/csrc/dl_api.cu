@@ -117,7 +117,9 @@ int dl_context_create(int device_ordinal, dl_context** out) {
   if (!ctx) return DL_ERR_ARG;
   ctx->device = device_ordinal;
   if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess ||
-      (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+      (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->staging_done, cudaEventDisableTiming)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e);
     delete ctx;
     return DL_ERR_CUDA;
@@ -135,6 +137,8 @@ void dl_context_destroy(dl_context* ctx) {
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->staging_done) cudaEventDestroy(ctx->staging_done);
   delete ctx;
 }
 
@@ -703,6 +707,12 @@ struct FrontendBuffers {
   float *tmp_points, *returns_local, *misses_local, *returns_tracking, *misses_tracking, *clouds, *current_pose, *origins,
       *passesA, *rtcsm_scores;
   uint8_t* cls;
+  // fused front half
+  int64_t tcap2 = 0;
+  unsigned long long* keys2;
+  uint32_t *min2, *slot2;
+  int32_t *last_index, *error_flag;
+  float* back_pose;
   ScanConstants* scans;
   AdaptiveParams* filters;
   double *initial_pose, *target;
@@ -719,7 +729,8 @@ size_t frontend_bytes(int batch, int64_t cap, int num_origins, size_t extra) {
                       B * C * 4, B * C * 4, B * C * 4, B * 2 * C * 4,
                       B * C * 12, B * C * 12, B * C * 12, B * C * 12, B * C * 12, B * 2 * C * 12, B * 28, (size_t)num_origins * 12,
                       B * 2 * 32 * 4, B * 4, B * C, B * sizeof(ScanConstants), 2 * sizeof(AdaptiveParams), B * 56, B * 24,
-                      B * sizeof(NlsProblem), B * sizeof(NlsOutput)}) + extra + 8192;
+                      B * sizeof(NlsProblem), B * sizeof(NlsOutput),
+                      B * (size_t)next_pow2(cap) * 8, B * (size_t)next_pow2(cap) * 4, B * C * 4, B * 4, 64, B * 28}) + extra + 8192;
 }
 
 void carve(Arena& a, int batch, int64_t cap, int num_origins, FrontendBuffers* f) {
@@ -744,7 +755,29 @@ void carve(Arena& a, int batch, int64_t cap, int num_origins, FrontendBuffers* f
   f->scans = a.take<ScanConstants>(B); f->filters = a.take<AdaptiveParams>(2);
   f->initial_pose = a.take<double>(B * 7); f->target = a.take<double>(B * 3);
   f->problems = a.take<NlsProblem>(B); f->nls_out = a.take<NlsOutput>(B);
+  f->tcap2 = next_pow2(cap);
+  f->keys2 = a.take<unsigned long long>(B * f->tcap2); f->min2 = a.take<uint32_t>(B * f->tcap2);
+  f->slot2 = a.take<uint32_t>(B * C); f->last_index = a.take<int32_t>(B); f->error_flag = a.take<int32_t>(1);
+  f->back_pose = a.take<float>(B * 7);
 }
+
+FrontendArgs make_frontend_args(const dl_frontend_options& o, const FrontendBuffers& f, const float* d_ranges,
+                                int64_t in_cap, int row_floats) {
+  FrontendArgs fa{};
+  fa.ranges = d_ranges; fa.in_cap = in_cap; fa.row_floats = row_floats; fa.counts = f.counts0; fa.scans = f.scans;
+  fa.origins = f.origins; fa.cap = f.cap; fa.tiles = f.tiles; fa.tcap1 = f.tcap; fa.tcap2 = f.tcap2;
+  fa.first_resolution = 0.5f * o.voxel_filter_size;  // LTB:394
+  fa.second_resolution = o.voxel_filter_size;        // LTB:479-484
+  fa.min_range = o.min_range; fa.max_range = o.max_range; fa.scan_period = o.scan_period;
+  fa.table1 = f.table; fa.slot1 = f.slot; fa.keys2 = f.keys2; fa.min2 = f.min2; fa.slot2 = f.slot2;
+  fa.local = f.tmp_points; fa.cls = f.cls; fa.tile_counts = f.tile_counts;
+  fa.returns_tracking = f.returns_tracking; fa.misses_tracking = f.misses_tracking;
+  fa.n_first = f.n1; fa.n_returns_local = f.n_ret; fa.n_returns = f.n2; fa.n_misses = f.n3; fa.last_index = f.last_index;
+  fa.current_pose = f.current_pose; fa.back_pose = f.back_pose; fa.error_flag = f.error_flag;
+  return fa;
+}
+
+int row_floats_of(const dl_frontend_options& o) { return o.range_row_floats == 4 ? 4 : 8; }
 
 // Per-scan constants of the deskew (LTB:426-428 and the scan-constant half of Eigen's slerp), host double math.
 ScanConstants make_scan_constants(const double* prev7, const double* cur7) {
@@ -790,35 +823,93 @@ int frontend_ingest(dl_context* ctx, const dl_frontend_options& o, const Fronten
   return DL_OK;
 }
 
-// Uploads the small per-call tables (counts, deskew constants, origins, filter options).
+// Uploads the small per-call tables (counts, deskew constants, origins, filter options, NLS problem records)
+// through one pinned staging block. No host synchronisation: the block is reused only after `staging_done`.
 int frontend_upload_small(dl_context* ctx, const dl_frontend_options& o, const FrontendBuffers& f, const int64_t* sizes,
-                          const float* origins, int num_origins, const double* prev_poses, const double* cur_poses) {
-  std::vector<int32_t> counts(f.batch);
-  std::vector<ScanConstants> sc(f.batch);
+                          const float* origins, int num_origins, const double* prev_poses, const double* cur_poses,
+                          const dl_grid* hi, const dl_grid* lo) {
+  const size_t B = (size_t)f.batch;
+  const size_t bytes = arena_bytes({B * 4, B * sizeof(ScanConstants), (size_t)num_origins * 12, 2 * sizeof(AdaptiveParams),
+                                    B * sizeof(NlsProblem)});
+  DL_TRY(ctx->reserve_pinned(bytes));
+  DL_CUDA(ctx, cudaEventSynchronize(ctx->staging_done));
+  Arena h(ctx->h_pinned);
+  int32_t* counts = h.take<int32_t>(B);
+  ScanConstants* sc = h.take<ScanConstants>(B);
+  float* org = h.take<float>((size_t)num_origins * 3);
+  AdaptiveParams* filt = h.take<AdaptiveParams>(2);
+  NlsProblem* problems = h.take<NlsProblem>(B);
   for (int b = 0; b < f.batch; ++b) {
     counts[b] = (int32_t)sizes[b];
     sc[b] = make_scan_constants(prev_poses + 7 * b, cur_poses + 7 * b);
+    NlsProblem& p = problems[b];
+    std::memset(&p, 0, sizeof(p));
+    if (hi && lo) {
+      for (int k = 0; k < 2; ++k) {
+        p.cloud[k] = f.clouds + (size_t)(2 * b + k) * f.cap * 3;
+        p.count_dev[k] = f.countsA + 2 * b + k;
+        p.grid[k] = k == 0 ? hi->view() : lo->view();
+      }
+      p.initial_dev = f.initial_pose + 7 * b;
+      p.target_dev = f.target + 3 * b;
+    }
   }
-  const AdaptiveParams filt[2] = {
-      {o.high_resolution_adaptive_voxel_filter.max_length, o.high_resolution_adaptive_voxel_filter.min_num_points,
-       o.high_resolution_adaptive_voxel_filter.max_range},
-      {o.low_resolution_adaptive_voxel_filter.max_length, o.low_resolution_adaptive_voxel_filter.min_num_points,
-       o.low_resolution_adaptive_voxel_filter.max_range}};
-  DL_TRY(h2d(ctx, f.counts0, counts.data(), f.batch));
-  DL_TRY(h2d(ctx, f.scans, sc.data(), f.batch));
-  DL_TRY(h2d(ctx, f.origins, origins, (size_t)num_origins * 3));
+  std::memcpy(org, origins, (size_t)num_origins * 12);
+  filt[0] = {o.high_resolution_adaptive_voxel_filter.max_length, o.high_resolution_adaptive_voxel_filter.min_num_points,
+             o.high_resolution_adaptive_voxel_filter.max_range};
+  filt[1] = {o.low_resolution_adaptive_voxel_filter.max_length, o.low_resolution_adaptive_voxel_filter.min_num_points,
+             o.low_resolution_adaptive_voxel_filter.max_range};
+  DL_TRY(h2d(ctx, f.counts0, counts, B));
+  DL_TRY(h2d(ctx, f.scans, sc, B));
+  DL_TRY(h2d(ctx, f.origins, org, (size_t)num_origins * 3));
   DL_TRY(h2d(ctx, f.filters, filt, 2));
-  return sync(ctx);  // the staging vectors go out of scope
+  DL_TRY(h2d(ctx, f.problems, problems, B));
+  DL_CUDA(ctx, cudaEventRecord(ctx->staging_done, ctx->stream));
+  return DL_OK;
 }
 
-int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, const float* d_ranges, int64_t in_cap,
-                 const int64_t* sizes, const float* origins, int num_origins, const double* prev_poses,
-                 const double* cur_poses, const double* submap_local_pose, const dl_grid* hi, const dl_grid* lo,
-                 Arena& a, dl_scan_result* d_results) {
+// host_ranges != nullptr: the scans are still on the host; they are uploaded on the copy stream in chunks while the
+// first-filter kernel of the previous chunk runs (the raw scans are read exactly once, by that kernel and by the
+// survivors' row reads that follow).
+int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, float* d_ranges, int64_t in_cap,
+                 const void* const* host_ranges, const int64_t* sizes, const float* origins, int num_origins,
+                 const double* prev_poses, const double* cur_poses, const double* submap_local_pose, const dl_grid* hi,
+                 const dl_grid* lo, Arena& a, dl_scan_result* d_results) {
   FrontendBuffers f;
   carve(a, num_scans, in_cap, num_origins, &f);
-  DL_TRY(frontend_upload_small(ctx, o, f, sizes, origins, num_origins, prev_poses, cur_poses));
-  DL_TRY(frontend_ingest(ctx, o, f, d_ranges, in_cap));
+  const int rf = row_floats_of(o);
+  DL_TRY(frontend_upload_small(ctx, o, f, sizes, origins, num_origins, prev_poses, cur_poses, hi, lo));
+  const FrontendArgs fa = make_frontend_args(o, f, d_ranges, in_cap, rf);
+  DL_TRY(launch_fe_prepare(ctx, fa, f.batch));
+  {
+    StageScope st(ctx, "voxel_filter_first");
+    if (host_ranges) {
+      // the upload target may still be in use by kernels of an earlier (asynchronous) call on this context
+      cudaEvent_t idle = ctx->take_event();
+      DL_CUDA(ctx, cudaEventRecord(idle, ctx->stream));
+      DL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, idle, 0));
+      ctx->event_pool.push_back(idle);
+      const int chunk = 8;
+      for (int c0 = 0; c0 < f.batch; c0 += chunk) {
+        const int c1 = std::min(f.batch, c0 + chunk);
+        for (int b = c0; b < c1; ++b)
+          if (sizes[b] > 0)
+            DL_CUDA(ctx, cudaMemcpyAsync(d_ranges + (size_t)b * in_cap * rf, host_ranges[b], (size_t)sizes[b] * rf * 4,
+                                         cudaMemcpyHostToDevice, ctx->copy_stream));
+        cudaEvent_t ev = ctx->take_event();
+        DL_CUDA(ctx, cudaEventRecord(ev, ctx->copy_stream));
+        DL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev, 0));
+        ctx->event_pool.push_back(ev);  // safe to recycle: the wait has been enqueued
+        DL_TRY(launch_fe_first_filter(ctx, fa, c0, c1 - c0));
+      }
+    } else {
+      DL_TRY(launch_fe_first_filter(ctx, fa, 0, f.batch));
+    }
+  }
+  {
+    StageScope st(ctx, "ingest_second_filter");
+    DL_TRY(launch_fe_rest(ctx, fa, f.batch));
+  }
   // adaptive voxel filters (high, low resolution) on the tracking-frame returns: one CTA per (scan, filter)
   {
     StageScope st(ctx, "adaptive_voxel_filter");
@@ -853,20 +944,6 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, c
     DL_TRY(sync(ctx));
     have_scores = true;
   }
-  std::vector<NlsProblem> problems(f.batch);
-  for (int b = 0; b < f.batch; ++b) {
-    NlsProblem& p = problems[b];
-    std::memset(&p, 0, sizeof(p));
-    for (int k = 0; k < 2; ++k) {
-      p.cloud[k] = f.clouds + (size_t)(2 * b + k) * f.cap * 3;
-      p.count_dev[k] = f.countsA + 2 * b + k;
-      p.grid[k] = k == 0 ? hi->view() : lo->view();
-    }
-    p.initial_dev = f.initial_pose + 7 * b;
-    p.target_dev = f.target + 3 * b;
-  }
-  DL_TRY(h2d(ctx, f.problems, problems.data(), f.batch));
-  DL_TRY(sync(ctx));
   {
     StageScope st(ctx, "nls_solve");
     DL_TRY(launch_nls(ctx, to_nls_options(o.ceres_scan_matcher, 2), f.problems, f.batch, f.nls_out));
@@ -875,6 +952,7 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, c
   ra.batch = f.batch; ra.first_counts = f.n1; ra.return_counts = f.n2; ra.miss_counts = f.n3; ra.adaptive_counts = f.countsA;
   ra.adaptive_cropped = f.croppedA; ra.adaptive_passes = f.npassesA;
   ra.rtcsm_scores = have_scores ? f.rtcsm_scores : nullptr; ra.nls = f.nls_out; ra.submap = submap; ra.results = d_results;
+  ra.error_flag = f.error_flag;
   DL_TRY(launch_finalize_results(ctx, ra));
   return DL_OK;
 }
@@ -914,8 +992,8 @@ int dl_frontend_match_batch_dev(dl_context* ctx, const dl_frontend_options* opti
                            ? rtcsm_scratch_bound(options->real_time_correlative_scan_matcher, hi->resolution, false) : 0;
   DL_TRY(ctx->reserve_device(frontend_bytes(num_scans, cap_rows, num_origins, extra)));
   Arena a(ctx->d_scratch);
-  return frontend_run(ctx, *options, num_scans, (const float*)ranges_dev, cap_rows, sizes, origins, num_origins, prev_poses,
-                      predicted_poses, submap_local_pose, hi, lo, a, results_dev);
+  return frontend_run(ctx, *options, num_scans, (float*)ranges_dev, cap_rows, nullptr, sizes, origins, num_origins,
+                      prev_poses, predicted_poses, submap_local_pose, hi, lo, a, results_dev);
 }
 
 int dl_frontend_fetch_results(dl_context* ctx, const dl_scan_result* results_dev, int32_t num_scans,
@@ -944,12 +1022,10 @@ int dl_frontend_match_batch(dl_context* ctx, const dl_frontend_options* options,
   Arena a(ctx->d_scratch);
   float* d_ranges = a.take<float>((size_t)num_scans * cap * 8);
   dl_scan_result* d_results = a.take<dl_scan_result>(num_scans);
-  for (int b = 0; b < num_scans; ++b) {
+  for (int b = 0; b < num_scans; ++b)
     if (sizes[b] > 0 && !ranges[b]) return DL_ERR_ARG;
-    DL_TRY(h2d(ctx, d_ranges + (size_t)b * cap * 8, (const float*)ranges[b], (size_t)sizes[b] * 8));
-  }
-  DL_TRY(frontend_run(ctx, *options, num_scans, d_ranges, cap, sizes, origins, num_origins, prev_poses, predicted_poses,
-                      submap_local_pose, hi, lo, a, d_results));
+  DL_TRY(frontend_run(ctx, *options, num_scans, d_ranges, cap, ranges, sizes, origins, num_origins, prev_poses,
+                      predicted_poses, submap_local_pose, hi, lo, a, d_results));
   DL_TRY(d2h(ctx, results, d_results, num_scans));
   return sync(ctx);
 }
@@ -968,8 +1044,25 @@ int dl_ingest_scan(dl_context* ctx, const dl_frontend_options* options, const vo
   DL_TRY(h2d(ctx, d_ranges, (const float*)ranges, (size_t)n * 8));
   FrontendBuffers f;
   carve(a, 1, n, num_origins, &f);
-  DL_TRY(frontend_upload_small(ctx, *options, f, &n, origins, num_origins, prev_pose, predicted_pose));
+  if (row_floats_of(*options) != 8) return ctx->fail(DL_ERR_ARG, "dl_ingest_scan takes RangeMeasurement rows (range_row_floats = 8)");
+  DL_TRY(frontend_upload_small(ctx, *options, f, &n, origins, num_origins, prev_pose, predicted_pose, nullptr, nullptr));
+  // stage-wise kernels (first_keep, returns_local) ...
   DL_TRY(frontend_ingest(ctx, *options, f, d_ranges, n));
+  int32_t stagewise[4];
+  DL_TRY(d2h(ctx, &stagewise[0], f.n1, 1));
+  DL_TRY(d2h(ctx, &stagewise[1], f.n_ret, 1));
+  DL_TRY(d2h(ctx, &stagewise[2], f.n2, 1));
+  DL_TRY(d2h(ctx, &stagewise[3], f.n3, 1));
+  DL_TRY(sync(ctx));
+  std::vector<int32_t> keep32(stagewise[0]);
+  DL_TRY(d2h(ctx, keep32.data(), f.keep1, stagewise[0]));
+  if (returns_local_out) DL_TRY(d2h(ctx, returns_local_out, f.returns_local, (size_t)stagewise[1] * 3));
+  DL_TRY(sync(ctx));
+  // ... then the fused kernels the batched front end uses, for everything in the tracking frame
+  const FrontendArgs fa = make_frontend_args(*options, f, d_ranges, n, 8);
+  DL_TRY(launch_fe_prepare(ctx, fa, 1));
+  DL_TRY(launch_fe_first_filter(ctx, fa, 0, 1));
+  DL_TRY(launch_fe_rest(ctx, fa, 1));
   int32_t c[4];
   DL_TRY(d2h(ctx, &c[0], f.n1, 1));
   DL_TRY(d2h(ctx, &c[1], f.n_ret, 1));
@@ -977,9 +1070,8 @@ int dl_ingest_scan(dl_context* ctx, const dl_frontend_options* options, const vo
   DL_TRY(d2h(ctx, &c[3], f.n3, 1));
   DL_TRY(sync(ctx));
   for (int i = 0; i < 4; ++i) counts_out[i] = c[i];
-  std::vector<int32_t> keep32(c[0]);
-  DL_TRY(d2h(ctx, keep32.data(), f.keep1, c[0]));
-  if (returns_local_out) DL_TRY(d2h(ctx, returns_local_out, f.returns_local, (size_t)c[1] * 3));
+  if (c[0] != stagewise[0] || c[1] != stagewise[1] || c[2] != stagewise[2] || c[3] != stagewise[3])
+    return ctx->fail(DL_ERR_ARG, "internal: fused and stage-wise front ends disagree on survivor counts");
   if (returns_tracking_out) DL_TRY(d2h(ctx, returns_tracking_out, f.returns_tracking, (size_t)c[2] * 3));
   if (misses_tracking_out) DL_TRY(d2h(ctx, misses_tracking_out, f.misses_tracking, (size_t)c[3] * 3));
   if (current_pose7f_out) DL_TRY(d2h(ctx, current_pose7f_out, f.current_pose, 7));

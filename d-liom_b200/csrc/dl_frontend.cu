@@ -1,0 +1,371 @@
+// Fused scan front half for the batched front end: 4 kernels instead of the 11 of the stage-wise path
+// (dl_voxel.cu + dl_ingest.cu, which stay as the standalone filter API and as a cross-check in the tests).
+//
+//   A  fe_first_filter_insert   first voxel filter (LTB:393-395): every point proposes its index for its voxel
+//                               (atomicCAS claim + atomicMin), one 128-bit load per point.
+//   B  fe_ingest_second_insert  for each first-filter survivor: deskew + transform + range gate (LTB:426-472) and
+//                               immediately the SECOND voxel filter's insert (LTB:479-484) keyed on the local-frame
+//                               voxel — no compaction in between: ids stay the original input indices, which
+//                               preserves "first point in input order wins" for free.
+//   C1 fe_count_tiles / C2 fe_scatter_tracking   ordered compaction of the second filter's survivors, fused with
+//                               the frame change back to tracking (TransformRangeData with current_pose^-1, LTB:485-487).
+//
+// The second filter's table stores packed 63-bit voxel keys (3 x 21 bits) + a min-index array, so a collision
+// never has to read another thread's freshly written point (no fence, no race). Keys outside +-2^20 voxels (> 75 km
+// at 0.075 m) set an error flag and the call fails with DL_ERR_ARG; the generic dl_voxel_filter has no such limit.
+// Returns and misses share the table (bit 63 distinguishes them).
+//
+// Algorithmic traffic per raw point: A reads 16 B; B reads 4 B slot + 4 B owner (+16 B row, writes 13 B for
+// survivors); C reads 1 B class (+ survivors' 12 B, writes 12 B per output point).
+#include "dl_internal.cuh"
+#include "dl_pipeline.cuh"
+
+namespace dl {
+namespace {
+
+constexpr uint32_t kEmpty32 = 0xFFFFFFFFu;
+constexpr unsigned long long kEmpty64 = 0xFFFFFFFFFFFFFFFFull;
+constexpr int kBlock = 256;
+
+__device__ __forceinline__ uint32_t hash_cell(const Int3& c) {
+  uint32_t h = (uint32_t)c.x * 73856093u ^ (uint32_t)c.y * 19349663u ^ (uint32_t)c.z * 83492791u;
+  h ^= h >> 15;
+  h *= 0x2c1b3c6du;
+  h ^= h >> 12;
+  return h;
+}
+
+__device__ __forceinline__ Vec3f load_xyz(const float* __restrict__ rows, int row_floats, uint32_t i) {
+  if (row_floats == 3) {
+    const float* p = rows + (size_t)i * 3;
+    return {p[0], p[1], p[2]};
+  }
+  const float4 v = __ldg((const float4*)(rows + (size_t)i * row_floats));  // rows are 16- or 32-byte records
+  return {v.x, v.y, v.z};
+}
+
+// ---------------------------------------------------------------------------------------------------- A
+__global__ void __launch_bounds__(kBlock) fe_first_filter_insert(FrontendArgs a, int first_scan) {
+  const int b = first_scan + blockIdx.y;
+  const int n = a.counts[b];
+  const float* rows = a.ranges + (size_t)b * a.in_cap * a.row_floats;
+  uint32_t* tab = a.table1 + (size_t)b * a.tcap1;
+  uint32_t* slot = a.slot1 + (size_t)b * a.cap;
+  const uint32_t mask = (uint32_t)a.tcap1 - 1;
+  const float res = a.first_resolution;
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    const Int3 c = cell_index(load_xyz(rows, a.row_floats, i), res);
+    uint32_t h = hash_cell(c) & mask;
+    for (;;) {
+      const uint32_t prev = atomicCAS(tab + h, kEmpty32, (uint32_t)i);
+      if (prev == kEmpty32) break;
+      const Int3 o = cell_index(load_xyz(rows, a.row_floats, prev), res);
+      if (o.x == c.x && o.y == c.y && o.z == c.z) {
+        atomicMin(tab + h, (uint32_t)i);
+        break;
+      }
+      h = (h + 1) & mask;
+    }
+    slot[i] = h;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- B
+__device__ __forceinline__ Rigidd interpolate_pose(double s, const ScanConstants& c) {
+  double scale0, scale1;
+  if (c.linear_slerp) {
+    scale0 = 1.0 - s;
+    scale1 = s;
+  } else {
+    scale0 = sin((1.0 - s) * c.theta) / c.sin_theta;
+    scale1 = sin(s * c.theta) / c.sin_theta;
+  }
+  if (c.negative_dot) scale1 = -scale1;
+  Rigidd out;
+  out.q = {scale0 * 1.0 + scale1 * c.rel.q.w, scale0 * 0.0 + scale1 * c.rel.q.x, scale0 * 0.0 + scale1 * c.rel.q.y,
+           scale0 * 0.0 + scale1 * c.rel.q.z};
+  out.t = mul(s, c.rel.t);
+  return out;
+}
+
+// pose applied to the point with per-point time t (LTB:430-445)
+__device__ __forceinline__ Rigidf point_pose(const ScanConstants& sc, bool no_deskew, double scan_period, float t) {
+  if (no_deskew) return to_float(sc.cur);
+  const double s = (scan_period + (double)t) / scan_period;
+  return to_float(compose(sc.prev, interpolate_pose(s, sc)));
+}
+
+__device__ __forceinline__ bool pack_key(const Int3& c, bool miss, unsigned long long* key) {
+  const int lim = 1 << 20;
+  if (c.x < -lim || c.x >= lim - 1 || c.y < -lim || c.y >= lim - 1 || c.z < -lim || c.z >= lim - 1) return false;
+  *key = ((unsigned long long)(c.x + lim) << 42) | ((unsigned long long)(c.y + lim) << 21) | (unsigned long long)(c.z + lim) |
+         (miss ? (1ull << 63) : 0ull);
+  return true;
+}
+
+// Heavy per-survivor work of kernel B (double slerp, pose composition, transform, gate, second-filter insert).
+__device__ __forceinline__ int ingest_survivor(const FrontendArgs& a, int b, const float* rows, int rf, const ScanConstants& sc,
+                                               bool no_deskew, unsigned long long* keys, uint32_t* mins, uint32_t mask2, int i) {
+  const float4 h = __ldg((const float4*)(rows + (size_t)i * rf));
+  const unsigned long long origin_index = rf >= 8 ? *(const unsigned long long*)(rows + (size_t)i * rf + 4) : 0ull;
+  const float* o = a.origins + 3 * origin_index;
+  const Rigidf pose = point_pose(sc, no_deskew, a.scan_period, h.w);
+  const Vec3f hit = apply(pose, Vec3f{h.x, h.y, h.z});
+  const Vec3f org = apply(pose, Vec3f{o[0], o[1], o[2]});
+  const Vec3f delta = sub(hit, org);
+  const float range = norm3(delta);
+  Vec3f outp = hit;
+  int cls = 0;
+  if (range >= a.min_range) {
+    if (range <= a.max_range) {
+      cls = 1;
+    } else {
+      cls = 2;
+      outp = add(org, mul(a.max_range / range, delta));
+    }
+  }
+  if (cls) {
+    float* l = a.local + ((size_t)b * a.cap + i) * 3;
+    l[0] = outp.x; l[1] = outp.y; l[2] = outp.z;
+    const Int3 c = cell_index(outp, a.second_resolution);
+    unsigned long long key;
+    if (!pack_key(c, cls == 2, &key)) {
+      *a.error_flag = 1;
+      cls = 0;
+    } else {
+      uint32_t hh = (hash_cell(c) ^ (cls == 2 ? 0x9e3779b9u : 0u)) & mask2;
+      for (;;) {
+        const unsigned long long prev = atomicCAS(keys + hh, kEmpty64, key);
+        if (prev == kEmpty64 || prev == key) {
+          atomicMin(mins + hh, (uint32_t)i);
+          break;
+        }
+        hh = (hh + 1) & mask2;
+      }
+      a.slot2[(size_t)b * a.cap + i] = hh;
+    }
+  }
+  a.cls[(size_t)b * a.cap + i] = (uint8_t)cls;
+  return cls;
+}
+
+// Only ~30 % of the raw points survive the first filter, so running the heavy path under the survivor predicate
+// would leave most lanes idle. Each warp instead appends its survivors to a small shared-memory queue and drains
+// it 32 at a time with all lanes busy.
+__global__ void __launch_bounds__(kBlock) fe_ingest_second_insert(FrontendArgs a) {
+  __shared__ int queue[kBlock / 32][64];
+  const int b = blockIdx.y;
+  const int n = a.counts[b];
+  const int rf = a.row_floats;
+  const float* rows = a.ranges + (size_t)b * a.in_cap * rf;
+  const uint32_t* tab = a.table1 + (size_t)b * a.tcap1;
+  const uint32_t* slot = a.slot1 + (size_t)b * a.cap;
+  unsigned long long* keys = a.keys2 + (size_t)b * a.tcap2;
+  uint32_t* mins = a.min2 + (size_t)b * a.tcap2;
+  const uint32_t mask2 = (uint32_t)a.tcap2 - 1;
+  const ScanConstants& sc = a.scans[b];
+  const bool no_deskew = n > 0 && (double)fabsf(rows[3]) < 1e-3;  // first survivor is row 0 (LTB:430-433)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int* q = queue[warp];
+  int queued = 0, survivors = 0, returns = 0, last = -1;
+  const int n_round = (n + 31) & ~31;  // whole warps iterate together
+  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n_round; i += gridDim.x * kBlock) {
+    bool surv = false;
+    if (i < n) {
+      surv = __ldcg(tab + slot[i]) == (uint32_t)i;
+      if (!surv) a.cls[(size_t)b * a.cap + i] = 0;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, surv);
+    if (surv) {
+      q[queued + __popc(ballot & ((1u << lane) - 1))] = i;
+      last = i;
+    }
+    queued += __popc(ballot);
+    survivors += surv;
+    __syncwarp();
+    if (queued >= 32) {
+      returns += ingest_survivor(a, b, rows, rf, sc, no_deskew, keys, mins, mask2, q[lane]) == 1;
+      __syncwarp();
+      const int rest = queued - 32;
+      const int moved = lane < rest ? q[32 + lane] : 0;
+      __syncwarp();
+      if (lane < rest) q[lane] = moved;
+      queued = rest;
+      __syncwarp();
+    }
+  }
+  if (lane < queued) returns += ingest_survivor(a, b, rows, rf, sc, no_deskew, keys, mins, mask2, q[lane]) == 1;
+  // bookkeeping: survivor counts and the LAST first-filter survivor (hits_poses.back(), LTB:476)
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    survivors += __shfl_xor_sync(0xffffffffu, survivors, d);
+    returns += __shfl_xor_sync(0xffffffffu, returns, d);
+    last = max(last, __shfl_xor_sync(0xffffffffu, last, d));
+  }
+  if (lane == 0) {
+    if (survivors) atomicAdd(a.n_first + b, survivors);
+    if (returns) atomicAdd(a.n_returns_local + b, returns);
+    if (last >= 0) atomicMax(a.last_index + b, last);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- C
+__device__ __forceinline__ int block_exclusive_scan(int value, int* total) {
+  __shared__ int warp_sums[kBlock / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = value;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  __syncthreads();
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  int base = 0, sum = 0;
+#pragma unroll
+  for (int w = 0; w < kBlock / 32; ++w) {
+    const int s = warp_sums[w];
+    if (w < warp) base += s;
+    sum += s;
+  }
+  *total = sum;
+  return base + inc - value;
+}
+
+__device__ __forceinline__ int second_filter_class(const FrontendArgs& a, int b, int i, int n) {
+  if (i >= n) return 0;
+  const int cls = a.cls[(size_t)b * a.cap + i];
+  if (!cls) return 0;
+  return __ldcg(a.min2 + (size_t)b * a.tcap2 + a.slot2[(size_t)b * a.cap + i]) == (uint32_t)i ? cls : 0;
+}
+
+__global__ void __launch_bounds__(kBlock) fe_count_tiles(FrontendArgs a) {
+  const int b = blockIdx.y;
+  const int n = a.counts[b];
+  if ((int)blockIdx.x * kBlock >= n) {
+    if (threadIdx.x == 0) {
+      a.tile_counts[((size_t)b * a.tiles + blockIdx.x) * 2] = 0;
+      a.tile_counts[((size_t)b * a.tiles + blockIdx.x) * 2 + 1] = 0;
+    }
+    return;
+  }
+  const int cls = second_filter_class(a, b, blockIdx.x * kBlock + threadIdx.x, n);
+  const int r = __syncthreads_count(cls == 1);
+  const int m = __syncthreads_count(cls == 2);
+  if (threadIdx.x == 0) {
+    a.tile_counts[((size_t)b * a.tiles + blockIdx.x) * 2] = r;
+    a.tile_counts[((size_t)b * a.tiles + blockIdx.x) * 2 + 1] = m;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) fe_scatter_tracking(FrontendArgs a) {
+  const int b = blockIdx.y;
+  const int n = a.counts[b];
+  const int my_tiles = (n + kBlock - 1) / kBlock;
+  if ((int)blockIdx.x >= my_tiles) return;
+  __shared__ int base_r, base_m;
+  __shared__ Rigidf back;
+  int pr = 0, pm = 0;
+  for (int t = threadIdx.x; t < (int)blockIdx.x; t += kBlock) {
+    pr += a.tile_counts[((size_t)b * a.tiles + t) * 2];
+    pm += a.tile_counts[((size_t)b * a.tiles + t) * 2 + 1];
+  }
+  int tr, tm;
+  block_exclusive_scan(pr, &tr);
+  block_exclusive_scan(pm, &tm);
+  if (threadIdx.x == 0) {
+    base_r = tr;
+    base_m = tm;
+    const float* bp = a.back_pose + 7 * b;
+    back = Rigidf{{bp[0], bp[1], bp[2]}, {bp[3], bp[4], bp[5], bp[6]}};
+  }
+  __syncthreads();
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  const int cls = second_filter_class(a, b, i, n);
+  int total_r, total_m;
+  const int off_r = block_exclusive_scan(cls == 1, &total_r);
+  const int off_m = block_exclusive_scan(cls == 2, &total_m);
+  if (cls) {
+    const float* l = a.local + ((size_t)b * a.cap + i) * 3;
+    const Vec3f q = apply(back, Vec3f{l[0], l[1], l[2]});
+    float* dst = cls == 1 ? a.returns_tracking + ((size_t)b * a.cap + base_r + off_r) * 3
+                          : a.misses_tracking + ((size_t)b * a.cap + base_m + off_m) * 3;
+    dst[0] = q.x; dst[1] = q.y; dst[2] = q.z;
+  }
+  if ((int)blockIdx.x == my_tiles - 1 && threadIdx.x == 0) {
+    a.n_returns[b] = base_r + total_r;
+    a.n_misses[b] = base_m + total_m;
+  }
+}
+
+// current_pose = pose of the LAST first-filter survivor (hits_poses.back(), LTB:476) and its inverse, once per scan.
+__global__ void fe_current_pose(FrontendArgs a, int batch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const int rf = a.row_floats;
+  const float* rows = a.ranges + (size_t)b * a.in_cap * rf;
+  const int last = a.last_index[b];
+  Rigidf cur = to_float(a.scans[b].cur);
+  if (last >= 0) {
+    const bool no_deskew = (double)fabsf(rows[3]) < 1e-3;
+    cur = point_pose(a.scans[b], no_deskew, a.scan_period, rows[(size_t)last * rf + 3]);
+  }
+  const Rigidf back = inverse(cur);
+  float* cp = a.current_pose + 7 * b;
+  cp[0] = cur.t.x; cp[1] = cur.t.y; cp[2] = cur.t.z; cp[3] = cur.q.w; cp[4] = cur.q.x; cp[5] = cur.q.y; cp[6] = cur.q.z;
+  float* bp = a.back_pose + 7 * b;
+  bp[0] = back.t.x; bp[1] = back.t.y; bp[2] = back.t.z; bp[3] = back.q.w; bp[4] = back.q.x; bp[5] = back.q.y; bp[6] = back.q.z;
+}
+
+__global__ void fe_reset_counters(FrontendArgs a, int batch) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  a.n_first[b] = 0;
+  a.n_returns_local[b] = 0;
+  a.last_index[b] = -1;
+  if (a.counts[b] == 0) {  // nothing will write these for an empty scan
+    a.n_returns[b] = 0;
+    a.n_misses[b] = 0;
+    const Rigidf cur = to_float(a.scans[b].cur);
+    float* cp = a.current_pose + 7 * b;
+    cp[0] = cur.t.x; cp[1] = cur.t.y; cp[2] = cur.t.z; cp[3] = cur.q.w; cp[4] = cur.q.x; cp[5] = cur.q.y; cp[6] = cur.q.z;
+  }
+  if (b == 0) *a.error_flag = 0;
+}
+
+}  // namespace
+
+int launch_fe_prepare(dl_context* ctx, const FrontendArgs& a, int batch) {
+  DL_CUDA(ctx, cudaMemsetAsync(a.table1, 0xFF, (size_t)batch * a.tcap1 * sizeof(uint32_t), ctx->stream));
+  DL_CUDA(ctx, cudaMemsetAsync(a.keys2, 0xFF, (size_t)batch * a.tcap2 * sizeof(unsigned long long), ctx->stream));
+  DL_CUDA(ctx, cudaMemsetAsync(a.min2, 0xFF, (size_t)batch * a.tcap2 * sizeof(uint32_t), ctx->stream));
+  fe_reset_counters<<<(batch + 127) / 128, 128, 0, ctx->stream>>>(a, batch);
+  DL_LAUNCH_CHECK(ctx, "fe_reset_counters");
+  return DL_OK;
+}
+
+// Kernel A for scans [first_scan, first_scan + num_scans): lets the host overlap the upload of later scans.
+int launch_fe_first_filter(dl_context* ctx, const FrontendArgs& a, int first_scan, int num_scans) {
+  if (num_scans <= 0) return DL_OK;
+  const int tiles = (int)std::min<int64_t>((a.cap + kBlock - 1) / kBlock, 128);
+  fe_first_filter_insert<<<dim3(tiles, num_scans), kBlock, 0, ctx->stream>>>(a, first_scan);
+  DL_LAUNCH_CHECK(ctx, "fe_first_filter_insert");
+  return DL_OK;
+}
+
+int launch_fe_rest(dl_context* ctx, const FrontendArgs& a, int batch) {
+  if (batch <= 0) return DL_OK;
+  const int tiles = (int)std::min<int64_t>((a.cap + kBlock - 1) / kBlock, 128);
+  fe_ingest_second_insert<<<dim3(tiles, batch), kBlock, 0, ctx->stream>>>(a);
+  DL_LAUNCH_CHECK(ctx, "fe_ingest_second_insert");
+  fe_current_pose<<<(batch + 127) / 128, 128, 0, ctx->stream>>>(a, batch);
+  DL_LAUNCH_CHECK(ctx, "fe_current_pose");
+  fe_count_tiles<<<dim3(a.tiles, batch), kBlock, 0, ctx->stream>>>(a);
+  DL_LAUNCH_CHECK(ctx, "fe_count_tiles");
+  fe_scatter_tracking<<<dim3(a.tiles, batch), kBlock, 0, ctx->stream>>>(a);
+  DL_LAUNCH_CHECK(ctx, "fe_scatter_tracking");
+  return DL_OK;
+}
+
+}  // namespace dl

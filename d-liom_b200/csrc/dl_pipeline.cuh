@@ -34,6 +34,38 @@ struct IngestArgs {
   float* current_pose;        // b * 7 floats (t, q wxyz)
 };
 
+// Fused front half (dl_frontend.cu).
+struct FrontendArgs {
+  const float* ranges;   // scan b starts at row b * in_cap; rows of row_floats floats (4: x y z t, 8: + u64 origin index)
+  int64_t in_cap;
+  int row_floats;
+  const int32_t* counts;
+  const ScanConstants* scans;
+  const float* origins;
+  int64_t cap;           // per-scan capacity of every per-point array below
+  int tiles;             // ceil(cap / 256)
+  int64_t tcap1, tcap2;  // table capacities (powers of two)
+  float first_resolution, second_resolution, min_range, max_range;
+  double scan_period;
+  uint32_t* table1;              // first filter: slot -> min point index
+  uint32_t* slot1;
+  unsigned long long* keys2;     // second filter: slot -> packed voxel key (bit 63 = miss)
+  uint32_t* min2;
+  uint32_t* slot2;
+  float* local;                  // local-frame point of every first-filter survivor, indexed by input row
+  uint8_t* cls;                  // 0 dropped, 1 return, 2 miss
+  int32_t* tile_counts;
+  float* returns_tracking;
+  float* misses_tracking;
+  int32_t *n_first, *n_returns_local, *n_returns, *n_misses, *last_index;
+  float* current_pose;
+  float* back_pose;              // inverse of current_pose, 7 floats per scan
+  int32_t* error_flag;
+};
+int launch_fe_prepare(dl_context* ctx, const FrontendArgs& a, int batch);
+int launch_fe_first_filter(dl_context* ctx, const FrontendArgs& a, int first_scan, int num_scans);
+int launch_fe_rest(dl_context* ctx, const FrontendArgs& a, int batch);
+
 struct ResultArgs {
   int batch;
   const int32_t* first_counts;
@@ -45,6 +77,7 @@ struct ResultArgs {
   const float* rtcsm_scores;       // optional
   const NlsOutput* nls;
   Rigidd submap;
+  const int32_t* error_flag;       // set by the fused front half when a voxel key could not be packed
   dl_scan_result* results;
 };
 

@@ -139,7 +139,8 @@ __global__ void voxel_indices_kernel(const float* __restrict__ points, int strid
 // One CTA runs the whole data-dependent pass sequence of AdaptivelyVoxelFiltered for one (cloud, filter) pair,
 // so the bisection needs no host round trip: every pass clears the table, re-inserts the range-cropped cloud and
 // block-reduces the survivor count; the control flow below is the reference's, statement for statement.
-constexpr int kAdaptiveBlock = 1024;
+constexpr int kAdaptiveBlock = 512;   // 128 registers per thread available: 32 cached points + working set
+constexpr int kAdaptiveWarps = kAdaptiveBlock / 32;
 
 __device__ __forceinline__ int block_sum_1024(int v) {
   __shared__ int ws[32];
@@ -151,7 +152,7 @@ __device__ __forceinline__ int block_sum_1024(int v) {
   if (lane == 0) ws[warp] = v;
   __syncthreads();
   if (warp == 0) {
-    int s = ws[lane];
+    int s = lane < kAdaptiveWarps ? ws[lane] : 0;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
     if (lane == 0) result = s;
@@ -177,7 +178,7 @@ __device__ __forceinline__ int block_compact_1024(int n, Pred pred, Emit emit) {
     __syncthreads();
     int warp_base = 0, tile_total = 0;
 #pragma unroll
-    for (int w = 0; w < 32; ++w) {
+    for (int w = 0; w < kAdaptiveWarps; ++w) {
       const int s = ws[w];
       if (w < warp) warp_base += s;
       tile_total += s;
@@ -191,11 +192,138 @@ __device__ __forceinline__ int block_compact_1024(int n, Pred pred, Emit emit) {
   return running;
 }
 
+// The reference's search over voxel edge lengths (AdaptivelyVoxelFiltered, voxel_filter.cc:40-77), statement for
+// statement, parameterised by `run_pass(edge) -> number of voxels` (negative = the pass could not be run in the
+// current mode). Returns false if a pass failed; otherwise *result_edge is the edge whose survivors are the result.
+template <typename RunPass>
+__device__ __forceinline__ bool adaptive_search(const AdaptiveParams& opt, RunPass run_pass, float* result_edge) {
+  *result_edge = opt.max_length;
+  int result_count = run_pass(opt.max_length);
+  if (result_count < 0) return false;
+  if ((float)result_count >= opt.min_num_points) return true;
+  for (float high_length = opt.max_length; high_length > 1e-2f * opt.max_length; high_length /= 2.f) {
+    float low_length = high_length / 2.f;
+    result_count = run_pass(low_length);
+    if (result_count < 0) return false;
+    *result_edge = low_length;
+    if ((float)result_count >= opt.min_num_points) {
+      while ((high_length - low_length) / low_length > 1e-1f) {
+        const float mid_length = (low_length + high_length) / 2.f;
+        const int candidate = run_pass(mid_length);
+        if (candidate < 0) return false;
+        if ((float)candidate >= opt.min_num_points) {
+          low_length = mid_length;
+          *result_edge = mid_length;
+        } else {
+          high_length = mid_length;
+        }
+      }
+      return true;
+    }
+  }
+  return true;
+}
+
+// ---- fast mode: the cropped cloud lives in registers (<= 16 points per thread), the hash table in shared memory
+// (packed 63-bit voxel keys + min index), duplicates inside a warp are merged with match.any before touching the
+// table. A pass is then ~16 ALU iterations + shared-memory atomics: no global traffic at all.
+constexpr int kFastPoints = 32;                       // points per thread held in registers (x 512 threads = 16 384)
+constexpr int kFastSlots = 4096;                      // shared-memory table slots (12 B each = 48 KiB)
+constexpr int kFastExtra = 14336;                     // further points cached in shared memory (12 B each = 168 KiB)
+constexpr int kFastCapacity = kFastPoints * 512 + kFastExtra;
+constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+
+struct FastTable {
+  unsigned long long keys[kFastSlots];
+  uint32_t mins[kFastSlots];
+  float extra[kFastExtra * 3];  // points with id >= kFastPoints * kAdaptiveBlock
+};
+
+__device__ __forceinline__ bool pack_cell(const Int3& c, unsigned long long* key) {
+  const int lim = 1 << 20;
+  if (c.x < -lim || c.x >= lim - 1 || c.y < -lim || c.y >= lim - 1 || c.z < -lim || c.z >= lim - 1) return false;
+  *key = ((unsigned long long)(c.x + lim) << 42) | ((unsigned long long)(c.y + lim) << 21) | (unsigned long long)(c.z + lim);
+  return true;
+}
+__device__ __forceinline__ uint32_t hash_key(unsigned long long k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 29;
+  return (uint32_t)k;
+}
+
+// One point of a pass (all 32 lanes of the warp call this together): lanes that fall into the same voxel are
+// merged with match.any and only the lowest lane (= lowest id) touches the table. Returns 1 for a new voxel.
+__device__ __forceinline__ int fast_insert(FastTable& tab, bool have, float x, float y, float z, int j, float edge,
+                                           int* fail_flag) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long key = kEmptyKey - 1 - lane;  // distinct dummy for idle lanes
+  bool ok = true;
+  if (have) ok = pack_cell(cell_index(Vec3f{x, y, z}, edge), &key);
+  if (!ok) *fail_flag = 1;
+  const unsigned peers = __match_any_sync(0xffffffffu, key);
+  int claimed = 0;
+  if (have && ok && (__ffs(peers) - 1) == lane) {
+    uint32_t h = hash_key(key) & (kFastSlots - 1);
+    int probes = 0;
+    for (;;) {
+      const unsigned long long prev = atomicCAS(&tab.keys[h], kEmptyKey, key);
+      if (prev == kEmptyKey) claimed = 1;
+      if (prev == kEmptyKey || prev == key) {
+        atomicMin(&tab.mins[h], (uint32_t)j);
+        break;
+      }
+      h = (h + 1) & (kFastSlots - 1);
+      if (++probes >= kFastSlots) {  // table full
+        *fail_flag = 1;
+        break;
+      }
+    }
+  }
+  return claimed;
+}
+
+// Returns the number of distinct voxels, or -1 if the table overflowed / a key could not be packed.
+__device__ __forceinline__ int fast_pass(FastTable& tab, const float (&px)[kFastPoints], const float (&py)[kFastPoints],
+                                         const float (&pz)[kFastPoints], int m, float edge, int* fail_flag) {
+  for (int i = threadIdx.x; i < kFastSlots; i += kAdaptiveBlock) {
+    tab.keys[i] = kEmptyKey;
+    tab.mins[i] = 0xFFFFFFFFu;
+  }
+  __syncthreads();
+  int claims = 0;
+#pragma unroll
+  for (int k = 0; k < kFastPoints; ++k) {
+    if (k * kAdaptiveBlock >= m) break;  // uniform
+    const int j = k * kAdaptiveBlock + threadIdx.x;
+    claims += fast_insert(tab, j < m, px[k], py[k], pz[k], j, edge, fail_flag);
+  }
+  for (int base = kFastPoints * kAdaptiveBlock; base < m; base += kAdaptiveBlock) {
+    const int j = base + threadIdx.x;
+    const float* e = tab.extra + (size_t)(j - kFastPoints * kAdaptiveBlock) * 3;
+    const bool have = j < m;
+    claims += fast_insert(tab, have, have ? e[0] : 0.f, have ? e[1] : 0.f, have ? e[2] : 0.f, j, edge, fail_flag);
+  }
+  const int total = block_sum_1024(claims);  // contains the barriers that publish fail_flag
+  return *fail_flag ? -1 : total;
+}
+
+__device__ __forceinline__ bool fast_survives(const FastTable& tab, float x, float y, float z, float edge, int j) {
+  unsigned long long key;
+  pack_cell(cell_index(Vec3f{x, y, z}, edge), &key);
+  uint32_t h = hash_key(key) & (kFastSlots - 1);
+  while (tab.keys[h] != key) h = (h + 1) & (kFastSlots - 1);
+  return tab.mins[h] == (uint32_t)j;
+}
+
 __global__ void __launch_bounds__(kAdaptiveBlock) adaptive_voxel_kernel(
     const float* __restrict__ points, int stride, int64_t cap, const int32_t* __restrict__ counts,
     const AdaptiveParams* __restrict__ filters, int num_filters, uint32_t* table, int64_t table_cap,
     uint32_t* scratch /* per pair: cap cropped rows + cap slots */, int32_t* keep, int32_t* keep_counts,
     float* passes, int32_t* num_passes, int32_t* cropped_counts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FastTable& fast = *reinterpret_cast<FastTable*>(smem_raw);
+  __shared__ int fail_flag;
   const int pair = blockIdx.x;
   const int b = pair / num_filters;
   const AdaptiveParams opt = filters[pair % num_filters];
@@ -207,6 +335,7 @@ __global__ void __launch_bounds__(kAdaptiveBlock) adaptive_voxel_kernel(
   int32_t* out = keep + (size_t)pair * cap;
   float* pass_log = passes + (size_t)pair * 32;
   int npass = 0;
+  if (threadIdx.x == 0) fail_flag = 0;
 
   // FilterByMaxRange (voxel_filter.cc:28-38): norm = sqrt(x^2 + (y^2 + z^2)) <= max_range
   const int m = block_compact_1024(
@@ -216,32 +345,103 @@ __global__ void __launch_bounds__(kAdaptiveBlock) adaptive_voxel_kernel(
         return norm3(Vec3f{p[0], p[1], p[2]}) <= opt.max_range;
       },
       [&](int pos, int i) { rows[pos] = (uint32_t)i; });
-
   if (threadIdx.x == 0 && cropped_counts) cropped_counts[pair] = m;
-  auto finish_all = [&]() {  // 'point_cloud' is already sparse enough
+
+  if ((float)m <= opt.min_num_points) {  // 'point_cloud' is already sparse enough
     for (int j = threadIdx.x; j < m; j += kAdaptiveBlock) out[j] = (int32_t)rows[j];
     if (threadIdx.x == 0) {
       keep_counts[pair] = m;
-      num_passes[pair] = npass;
+      num_passes[pair] = 0;
     }
-  };
-  if ((float)m <= opt.min_num_points) {
-    finish_all();
     return;
   }
+  auto log_pass = [&](float edge) {
+    if (threadIdx.x == 0 && npass < 32) pass_log[npass] = edge;
+    ++npass;
+  };
 
-  // table sized to the cropped cloud
+  // ---------------- fast mode
+  if (m <= kFastCapacity) {
+    float px[kFastPoints], py[kFastPoints], pz[kFastPoints];
+#pragma unroll
+    for (int k = 0; k < kFastPoints; ++k) {
+      const int j = k * kAdaptiveBlock + threadIdx.x;
+      px[k] = py[k] = pz[k] = 0.f;
+      if (j < m) {
+        const float* p = pts + (size_t)rows[j] * stride;
+        px[k] = p[0]; py[k] = p[1]; pz[k] = p[2];
+      }
+    }
+    for (int j = kFastPoints * kAdaptiveBlock + threadIdx.x; j < m; j += kAdaptiveBlock) {
+      const float* p = pts + (size_t)rows[j] * stride;
+      float* e = fast.extra + (size_t)(j - kFastPoints * kAdaptiveBlock) * 3;
+      e[0] = p[0]; e[1] = p[1]; e[2] = p[2];
+    }
+    __syncthreads();
+    float last_edge = -1.f, result_edge = 0.f;
+    const bool ok = adaptive_search(
+        opt,
+        [&](float edge) {
+          log_pass(edge);
+          last_edge = edge;
+          return fast_pass(fast, px, py, pz, m, edge, &fail_flag);
+        },
+        &result_edge);
+    bool done = ok;
+    if (ok && last_edge != result_edge) done = fast_pass(fast, px, py, pz, m, result_edge, &fail_flag) >= 0;
+    if (done) {
+      // ordered compaction of the survivors, 1024 ids per round
+      __shared__ int ws2[32];
+      __shared__ int running2;
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      if (threadIdx.x == 0) running2 = 0;
+      __syncthreads();
+      auto emit_round = [&](int j, float x, float y, float z) {
+        const int flag = (j < m && fast_survives(fast, x, y, z, result_edge, j)) ? 1 : 0;
+        const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) ws2[warp] = __popc(ballot);
+        __syncthreads();
+        int warp_base = 0, tile_total = 0;
+#pragma unroll
+        for (int w = 0; w < kAdaptiveWarps; ++w) {
+          const int s = ws2[w];
+          if (w < warp) warp_base += s;
+          tile_total += s;
+        }
+        const int start = running2;
+        if (flag) out[start + warp_base + __popc(ballot & ((1u << lane) - 1))] = (int32_t)rows[j];
+        __syncthreads();
+        if (threadIdx.x == 0) running2 = start + tile_total;
+        __syncthreads();
+      };
+#pragma unroll
+      for (int k = 0; k < kFastPoints; ++k) {
+        if (k * kAdaptiveBlock >= m) break;
+        emit_round(k * kAdaptiveBlock + threadIdx.x, px[k], py[k], pz[k]);
+      }
+      for (int base = kFastPoints * kAdaptiveBlock; base < m; base += kAdaptiveBlock) {
+        const int j = base + threadIdx.x;
+        const float* e = fast.extra + (size_t)(min(j, m - 1) - kFastPoints * kAdaptiveBlock) * 3;
+        emit_round(j, e[0], e[1], e[2]);
+      }
+      if (threadIdx.x == 0) {
+        keep_counts[pair] = running2;
+        num_passes[pair] = npass;
+      }
+      return;
+    }
+    // a pass overflowed the shared table or met an unpackable key: redo everything in generic mode
+    npass = 0;
+    __syncthreads();
+  }
+
+  // ---------------- generic mode: index-only table in global memory, any number of points, any coordinates
   uint32_t eff_cap = 64;
   while (eff_cap < 2u * (uint32_t)m) eff_cap <<= 1;
   if (eff_cap > (uint32_t)table_cap) eff_cap = (uint32_t)table_cap;
   const uint32_t mask = eff_cap - 1;
-
   float last_edge = -1.f;
-  auto run_pass = [&](float edge, bool log) -> int {
-    if (log) {
-      if (threadIdx.x == 0 && npass < 32) pass_log[npass] = edge;
-      ++npass;
-    }
+  auto run_pass = [&](float edge) -> int {
     for (uint32_t i = threadIdx.x; i < eff_cap; i += kAdaptiveBlock) tab[i] = kEmpty;
     __syncthreads();
     for (int j = threadIdx.x; j < m; j += kAdaptiveBlock) {
@@ -254,34 +454,15 @@ __global__ void __launch_bounds__(kAdaptiveBlock) adaptive_voxel_kernel(
     last_edge = edge;
     return block_sum_1024(local);
   };
-
-  // AdaptivelyVoxelFiltered (voxel_filter.cc:40-77)
-  float result_edge = opt.max_length;
-  int result_count = run_pass(opt.max_length, true);
-  bool done = (float)result_count >= opt.min_num_points;
-  if (!done) {
-    for (float high_length = opt.max_length; high_length > 1e-2f * opt.max_length; high_length /= 2.f) {
-      float low_length = high_length / 2.f;
-      result_count = run_pass(low_length, true);
-      result_edge = low_length;
-      if ((float)result_count >= opt.min_num_points) {
-        while ((high_length - low_length) / low_length > 1e-1f) {
-          const float mid_length = (low_length + high_length) / 2.f;
-          const int candidate = run_pass(mid_length, true);
-          if ((float)candidate >= opt.min_num_points) {
-            low_length = mid_length;
-            result_edge = mid_length;
-            result_count = candidate;
-          } else {
-            high_length = mid_length;
-          }
-        }
-        break;
-      }
-    }
-  }
-  // materialise `result`: the table must hold the pass that produced it
-  if (last_edge != result_edge) run_pass(result_edge, false);
+  float result_edge = 0.f;
+  adaptive_search(
+      opt,
+      [&](float edge) {
+        log_pass(edge);
+        return run_pass(edge);
+      },
+      &result_edge);
+  if (last_edge != result_edge) run_pass(result_edge);  // the table must hold the pass that produced `result`
   const int kept = block_compact_1024(
       m, [&](int j) { return __ldcg(tab + slot[j]) == (uint32_t)j; }, [&](int pos, int j) { out[pos] = (int32_t)rows[j]; });
   if (threadIdx.x == 0) {
@@ -321,7 +502,8 @@ int launch_adaptive_voxel_filter(dl_context* ctx, const float* points, int strid
                                  int64_t table_cap, uint32_t* scratch, int32_t* keep, int32_t* keep_counts,
                                  float* passes, int32_t* num_passes, int32_t* cropped_counts) {
   if (batch <= 0 || num_filters <= 0) return DL_OK;
-  adaptive_voxel_kernel<<<batch * num_filters, kAdaptiveBlock, 0, ctx->stream>>>(
+  DL_CUDA(ctx, cudaFuncSetAttribute(adaptive_voxel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastTable)));
+  adaptive_voxel_kernel<<<batch * num_filters, kAdaptiveBlock, sizeof(FastTable), ctx->stream>>>(
       points, stride, cap, counts, filters_dev, num_filters, table, table_cap, scratch, keep, keep_counts, passes,
       num_passes, cropped_counts);
   DL_LAUNCH_CHECK(ctx, "adaptive_voxel_kernel");

@@ -84,7 +84,8 @@ class FrontendOptions(C.Structure):
     _fields_ = [("min_range", C.c_float), ("max_range", C.c_float), ("voxel_filter_size", C.c_float),
                 ("high_resolution_adaptive_voxel_filter", AdaptiveVoxelFilterOptions),
                 ("low_resolution_adaptive_voxel_filter", AdaptiveVoxelFilterOptions),
-                ("use_online_correlative_scan_matching", C.c_int32), ("scan_period", C.c_double),
+                ("use_online_correlative_scan_matching", C.c_int32), ("range_row_floats", C.c_int32),
+                ("scan_period", C.c_double),
                 ("real_time_correlative_scan_matcher", RtcsmOptions), ("ceres_scan_matcher", CeresOptions)]
 
     @staticmethod
@@ -97,6 +98,7 @@ class FrontendOptions(C.Structure):
         f.low_resolution_adaptive_voxel_filter = AdaptiveVoxelFilterOptions(o.lo_max_length, o.lo_min_num_points,
                                                                             o.lo_max_range)
         f.use_online_correlative_scan_matching = o.use_rtcsm
+        f.range_row_floats = 8
         f.scan_period = o.scan_period
         f.real_time_correlative_scan_matcher = RtcsmOptions(o.rtcsm_linear_window, o.rtcsm_angular_window, o.rtcsm_w_t,
                                                             o.rtcsm_w_r)

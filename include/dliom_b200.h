@@ -167,6 +167,10 @@ typedef struct dl_frontend_options { /* C/mapping/proto/3d/local_trajectory_buil
   dl_adaptive_voxel_filter_options high_resolution_adaptive_voxel_filter;
   dl_adaptive_voxel_filter_options low_resolution_adaptive_voxel_filter;
   int32_t use_online_correlative_scan_matching;
+  /* layout of the `ranges` rows: 8 (default when 0) = RangeMeasurement {x y z t, u64 origin index} as produced by
+   * RangeDataSynchronizer; 4 = sensor::TimedPointCloud rows {x y z t} of a single sensor (origin index 0), the
+   * layout AddRangeData itself receives (timed_point_cloud_data.h:27-31) — half the host-to-device bytes. */
+  int32_t range_row_floats;
   double scan_period;
   dl_rtcsm_options real_time_correlative_scan_matcher;
   dl_ceres_options ceres_scan_matcher;
@@ -177,7 +181,8 @@ typedef struct dl_scan_result {
   double pose_observation_in_submap[7];
   dl_solve_summary summary;
   float rtcsm_score;
-  int32_t ok;                             /* 0 = dropped (empty cloud), like the reference's nullptr */
+  int32_t ok;                             /* 0 = dropped (empty cloud), like the reference's nullptr; -1 = a point lay
+                                             outside +-2^20 voxels of the fused front half (results invalid) */
   int32_t num_first_filter, num_returns, num_misses, num_high_resolution, num_low_resolution;
   /* adaptive filter bookkeeping: points inside max_range and voxel passes run, per filter (high, low) */
   int32_t num_cropped_high, num_cropped_low, num_passes_high, num_passes_low;

@@ -242,6 +242,41 @@ def test_ingest_scan_without_point_times(ctx, orc):
     assert np.array_equal(got["returns_tracking"].view(np.uint32), want["returns_tracking"].view(np.uint32))
 
 
+def test_frontend_batch_timed_point_cloud_rows(ctx, orc):
+    """16-byte TimedPointCloud rows (x y z t, single sensor) give exactly the results of the 32-byte RangeMeasurement rows."""
+    import dliom
+    w = workload()
+    hi, lo = dev_grid(ctx, w["hi"]), dev_grid(ctx, w["lo"])
+    fo8 = dliom.FrontendOptions.from_oracle(w["opts"])
+    fo4 = dliom.FrontendOptions.from_oracle(w["opts"])
+    fo4.range_row_floats = 4
+    rows4 = [np.ascontiguousarray(s.view(np.float32).reshape(-1, 8)[:, :4]) for s in w["scans"]]
+    r8 = ctx.frontend_match_batch(fo8, w["scans"], w["origin"], w["prev"], w["cur"], w["submap_pose"], hi, lo)
+    r4 = ctx.frontend_match_batch(fo4, rows4, w["origin"], w["prev"], w["cur"], w["submap_pose"], hi, lo)
+    for a, b in zip(r8, r4):
+        assert list(a.pose_estimate_local) == list(b.pose_estimate_local)
+        assert (a.num_first_filter, a.num_returns, a.num_misses, a.num_high_resolution, a.num_low_resolution) == \
+               (b.num_first_filter, b.num_returns, b.num_misses, b.num_high_resolution, b.num_low_resolution)
+
+
+def test_frontend_batch_full_size_scans(ctx, orc):
+    """BASELINE configs[1] size (64-beam, ~130k points): every count and the pose against the oracle."""
+    import dliom
+    w = workload(beams=64, num_map_scans=6, num_scans=3)
+    fo = dliom.FrontendOptions.from_oracle(w["opts"])
+    hi, lo = dev_grid(ctx, w["hi"]), dev_grid(ctx, w["lo"])
+    res = ctx.frontend_match_batch(fo, w["scans"], w["origin"], w["prev"], w["cur"], w["submap_pose"], hi, lo)
+    for s, r in enumerate(res):
+        ing = orc.ingest_scan(w["opts"], w["scans"][s], w["origin"], w["prev"][s], w["cur"][s])
+        want = orc.match_scan(w["opts"], ing["returns_tracking"], ing["current_pose"].astype(np.float64), w["submap_pose"],
+                              w["hi"], w["lo"])
+        assert (r.num_first_filter, r.num_returns, r.num_misses) == (len(ing["first_keep"]), len(ing["returns_tracking"]),
+                                                                      len(ing["misses_tracking"]))
+        assert (r.num_high_resolution, r.num_low_resolution) == (len(want["hi_keep"]), len(want["lo_keep"]))
+        dt, dr = pose_error(np.array(r.pose_estimate_local), want["pose_estimate_local"])
+        assert r.ok == 1 and dt < 1e-7 and dr < 1e-8
+
+
 @pytest.mark.parametrize("use_rtcsm", [0, 1])
 def test_frontend_batch_matches_oracle(ctx, orc, use_rtcsm):
     import dliom
