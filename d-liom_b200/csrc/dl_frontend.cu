@@ -50,9 +50,8 @@ __global__ void __launch_bounds__(kBlock) fe_first_filter_insert(FrontendArgs a,
   const int n = a.counts[b];
   const float* rows = a.ranges + (size_t)b * a.in_cap * a.row_floats;
   uint32_t* tab = a.table1 + (size_t)b * a.tcap1;
-  uint32_t* slot = a.slot1 + (size_t)b * a.cap;
   const uint32_t mask = (uint32_t)a.tcap1 - 1;
-  const float res = a.first_resolution;
+  const CellDivider res = make_divider(a.first_resolution);
   for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
     const Int3 c = cell_index(load_xyz(rows, a.row_floats, i), res);
     uint32_t h = hash_cell(c) & mask;
@@ -66,7 +65,6 @@ __global__ void __launch_bounds__(kBlock) fe_first_filter_insert(FrontendArgs a,
       }
       h = (h + 1) & mask;
     }
-    slot[i] = h;
   }
 }
 
@@ -127,13 +125,14 @@ __device__ __forceinline__ int ingest_survivor(const FrontendArgs& a, int b, con
   if (cls) {
     float* l = a.local + ((size_t)b * a.cap + i) * 3;
     l[0] = outp.x; l[1] = outp.y; l[2] = outp.z;
-    const Int3 c = cell_index(outp, a.second_resolution);
+    const Int3 c = cell_index(outp, make_divider(a.second_resolution));
     unsigned long long key;
     if (!pack_key(c, cls == 2, &key)) {
       *a.error_flag = 1;
       cls = 0;
     } else {
       uint32_t hh = (hash_cell(c) ^ (cls == 2 ? 0x9e3779b9u : 0u)) & mask2;
+      (void)0;
       for (;;) {
         const unsigned long long prev = atomicCAS(keys + hh, kEmpty64, key);
         if (prev == kEmpty64 || prev == key) {
@@ -142,7 +141,6 @@ __device__ __forceinline__ int ingest_survivor(const FrontendArgs& a, int b, con
         }
         hh = (hh + 1) & mask2;
       }
-      a.slot2[(size_t)b * a.cap + i] = hh;
     }
   }
   a.cls[(size_t)b * a.cap + i] = (uint8_t)cls;
@@ -159,7 +157,6 @@ __global__ void __launch_bounds__(kBlock) fe_ingest_second_insert(FrontendArgs a
   const int rf = a.row_floats;
   const float* rows = a.ranges + (size_t)b * a.in_cap * rf;
   const uint32_t* tab = a.table1 + (size_t)b * a.tcap1;
-  const uint32_t* slot = a.slot1 + (size_t)b * a.cap;
   unsigned long long* keys = a.keys2 + (size_t)b * a.tcap2;
   uint32_t* mins = a.min2 + (size_t)b * a.tcap2;
   const uint32_t mask2 = (uint32_t)a.tcap2 - 1;
@@ -168,17 +165,17 @@ __global__ void __launch_bounds__(kBlock) fe_ingest_second_insert(FrontendArgs a
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int* q = queue[warp];
   int queued = 0, survivors = 0, returns = 0, last = -1;
-  const int n_round = (n + 31) & ~31;  // whole warps iterate together
-  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n_round; i += gridDim.x * kBlock) {
-    bool surv = false;
-    if (i < n) {
-      surv = __ldcg(tab + slot[i]) == (uint32_t)i;
-      if (!surv) a.cls[(size_t)b * a.cap + i] = 0;
-    }
+  // The first filter's survivors are exactly the non-empty table slots: stream the table (coalesced) instead of
+  // probing it once per raw point. Order does not matter here: the second filter keys on the original index.
+  if (n == 0) return;
+  for (int h = blockIdx.x * kBlock + threadIdx.x; h < (int)a.tcap1; h += gridDim.x * kBlock) {
+    const uint32_t owner = __ldcg(tab + h);
+    const bool surv = owner != kEmpty32;
+    const int i = (int)owner;
     const unsigned ballot = __ballot_sync(0xffffffffu, surv);
     if (surv) {
       q[queued + __popc(ballot & ((1u << lane) - 1))] = i;
-      last = i;
+      last = max(last, i);
     }
     queued += __popc(ballot);
     survivors += surv;
@@ -233,11 +230,23 @@ __device__ __forceinline__ int block_exclusive_scan(int value, int* total) {
   return base + inc - value;
 }
 
+// cls[i] is 1/2 for gated first-filter survivors; win[i] is set by fe_mark_winners for the points that own their
+// second-filter voxel. A point is output iff both hold.
 __device__ __forceinline__ int second_filter_class(const FrontendArgs& a, int b, int i, int n) {
   if (i >= n) return 0;
-  const int cls = a.cls[(size_t)b * a.cap + i];
-  if (!cls) return 0;
-  return __ldcg(a.min2 + (size_t)b * a.tcap2 + a.slot2[(size_t)b * a.cap + i]) == (uint32_t)i ? cls : 0;
+  return a.win[(size_t)b * a.cap + i] ? a.cls[(size_t)b * a.cap + i] : 0;
+}
+
+// The second filter's survivors are the min-index entries of its non-empty slots: stream the table once.
+__global__ void __launch_bounds__(kBlock) fe_mark_winners(FrontendArgs a) {
+  const int b = blockIdx.y;
+  if (a.counts[b] == 0) return;
+  const uint32_t* mins = a.min2 + (size_t)b * a.tcap2;
+  uint8_t* win = a.win + (size_t)b * a.cap;
+  for (int h = blockIdx.x * kBlock + threadIdx.x; h < (int)a.tcap2; h += gridDim.x * kBlock) {
+    const uint32_t i = __ldcg(mins + h);
+    if (i != kEmpty32) win[i] = 1;  // store only: no read-modify-write latency
+  }
 }
 
 __global__ void __launch_bounds__(kBlock) fe_count_tiles(FrontendArgs a) {
@@ -259,44 +268,63 @@ __global__ void __launch_bounds__(kBlock) fe_count_tiles(FrontendArgs a) {
   }
 }
 
+// Exclusive prefix of the tile counts of one scan (one CTA per scan), in place; totals go to n_returns / n_misses.
+__global__ void __launch_bounds__(kBlock) fe_tile_prefix(FrontendArgs a) {
+  const int b = blockIdx.x;
+  const int n = a.counts[b];
+  const int my_tiles = (n + kBlock - 1) / kBlock;
+  int32_t* tc = a.tile_counts + (size_t)b * a.tiles * 2;
+  __shared__ int carry_r, carry_m;
+  if (threadIdx.x == 0) carry_r = carry_m = 0;
+  __syncthreads();
+  for (int base = 0; base < my_tiles; base += kBlock) {
+    const int t = base + threadIdx.x;
+    const int r = t < my_tiles ? tc[2 * t] : 0, m = t < my_tiles ? tc[2 * t + 1] : 0;
+    int tr, tm;
+    const int er = block_exclusive_scan(r, &tr);
+    const int em = block_exclusive_scan(m, &tm);
+    if (t < my_tiles) {
+      tc[2 * t] = carry_r + er;
+      tc[2 * t + 1] = carry_m + em;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      carry_r += tr;
+      carry_m += tm;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    a.n_returns[b] = carry_r;
+    a.n_misses[b] = carry_m;
+  }
+}
+
 __global__ void __launch_bounds__(kBlock) fe_scatter_tracking(FrontendArgs a) {
   const int b = blockIdx.y;
   const int n = a.counts[b];
-  const int my_tiles = (n + kBlock - 1) / kBlock;
-  if ((int)blockIdx.x >= my_tiles) return;
-  __shared__ int base_r, base_m;
-  __shared__ Rigidf back;
-  int pr = 0, pm = 0;
-  for (int t = threadIdx.x; t < (int)blockIdx.x; t += kBlock) {
-    pr += a.tile_counts[((size_t)b * a.tiles + t) * 2];
-    pm += a.tile_counts[((size_t)b * a.tiles + t) * 2 + 1];
-  }
-  int tr, tm;
-  block_exclusive_scan(pr, &tr);
-  block_exclusive_scan(pm, &tm);
-  if (threadIdx.x == 0) {
-    base_r = tr;
-    base_m = tm;
-    const float* bp = a.back_pose + 7 * b;
-    back = Rigidf{{bp[0], bp[1], bp[2]}, {bp[3], bp[4], bp[5], bp[6]}};
-  }
-  __syncthreads();
+  if ((int)blockIdx.x * kBlock >= n) return;
   const int i = blockIdx.x * kBlock + threadIdx.x;
   const int cls = second_filter_class(a, b, i, n);
-  int total_r, total_m;
-  const int off_r = block_exclusive_scan(cls == 1, &total_r);
-  const int off_m = block_exclusive_scan(cls == 2, &total_m);
-  if (cls) {
-    const float* l = a.local + ((size_t)b * a.cap + i) * 3;
-    const Vec3f q = apply(back, Vec3f{l[0], l[1], l[2]});
-    float* dst = cls == 1 ? a.returns_tracking + ((size_t)b * a.cap + base_r + off_r) * 3
-                          : a.misses_tracking + ((size_t)b * a.cap + base_m + off_m) * 3;
-    dst[0] = q.x; dst[1] = q.y; dst[2] = q.z;
+  const unsigned lane_mask = (1u << (threadIdx.x & 31)) - 1;
+  const unsigned br = __ballot_sync(0xffffffffu, cls == 1), bm = __ballot_sync(0xffffffffu, cls == 2);
+  __shared__ int wr[kBlock / 32], wm[kBlock / 32];
+  const int warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    wr[warp] = __popc(br);
+    wm[warp] = __popc(bm);
   }
-  if ((int)blockIdx.x == my_tiles - 1 && threadIdx.x == 0) {
-    a.n_returns[b] = base_r + total_r;
-    a.n_misses[b] = base_m + total_m;
-  }
+  __syncthreads();
+  if (!cls) return;
+  int off = a.tile_counts[((size_t)b * a.tiles + blockIdx.x) * 2 + (cls == 2)];
+  for (int w = 0; w < warp; ++w) off += cls == 1 ? wr[w] : wm[w];
+  off += __popc((cls == 1 ? br : bm) & lane_mask);
+  const float* bp = a.back_pose + 7 * b;
+  const Rigidf back{{bp[0], bp[1], bp[2]}, {bp[3], bp[4], bp[5], bp[6]}};
+  const float* l = a.local + ((size_t)b * a.cap + i) * 3;
+  const Vec3f q = apply(back, Vec3f{l[0], l[1], l[2]});
+  float* dst = (cls == 1 ? a.returns_tracking : a.misses_tracking) + ((size_t)b * a.cap + off) * 3;
+  dst[0] = q.x; dst[1] = q.y; dst[2] = q.z;
 }
 
 // current_pose = pose of the LAST first-filter survivor (hits_poses.back(), LTB:476) and its inverse, once per scan.
@@ -340,6 +368,8 @@ int launch_fe_prepare(dl_context* ctx, const FrontendArgs& a, int batch) {
   DL_CUDA(ctx, cudaMemsetAsync(a.table1, 0xFF, (size_t)batch * a.tcap1 * sizeof(uint32_t), ctx->stream));
   DL_CUDA(ctx, cudaMemsetAsync(a.keys2, 0xFF, (size_t)batch * a.tcap2 * sizeof(unsigned long long), ctx->stream));
   DL_CUDA(ctx, cudaMemsetAsync(a.min2, 0xFF, (size_t)batch * a.tcap2 * sizeof(uint32_t), ctx->stream));
+  DL_CUDA(ctx, cudaMemsetAsync(a.cls, 0, (size_t)batch * a.cap, ctx->stream));
+  DL_CUDA(ctx, cudaMemsetAsync(a.win, 0, (size_t)batch * a.cap, ctx->stream));
   fe_reset_counters<<<(batch + 127) / 128, 128, 0, ctx->stream>>>(a, batch);
   DL_LAUNCH_CHECK(ctx, "fe_reset_counters");
   return DL_OK;
@@ -357,12 +387,16 @@ int launch_fe_first_filter(dl_context* ctx, const FrontendArgs& a, int first_sca
 int launch_fe_rest(dl_context* ctx, const FrontendArgs& a, int batch) {
   if (batch <= 0) return DL_OK;
   const int tiles = (int)std::min<int64_t>((a.cap + kBlock - 1) / kBlock, 128);
-  fe_ingest_second_insert<<<dim3(tiles, batch), kBlock, 0, ctx->stream>>>(a);
+  fe_ingest_second_insert<<<dim3(20, batch), kBlock, 0, ctx->stream>>>(a);  // ~400 survivors per warp: the queue drains full
   DL_LAUNCH_CHECK(ctx, "fe_ingest_second_insert");
+  fe_mark_winners<<<dim3(tiles, batch), kBlock, 0, ctx->stream>>>(a);
+  DL_LAUNCH_CHECK(ctx, "fe_mark_winners");
   fe_current_pose<<<(batch + 127) / 128, 128, 0, ctx->stream>>>(a, batch);
   DL_LAUNCH_CHECK(ctx, "fe_current_pose");
   fe_count_tiles<<<dim3(a.tiles, batch), kBlock, 0, ctx->stream>>>(a);
   DL_LAUNCH_CHECK(ctx, "fe_count_tiles");
+  fe_tile_prefix<<<batch, kBlock, 0, ctx->stream>>>(a);
+  DL_LAUNCH_CHECK(ctx, "fe_tile_prefix");
   fe_scatter_tracking<<<dim3(a.tiles, batch), kBlock, 0, ctx->stream>>>(a);
   DL_LAUNCH_CHECK(ctx, "fe_scatter_tracking");
   return DL_OK;

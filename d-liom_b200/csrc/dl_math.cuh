@@ -111,6 +111,25 @@ DL_HD Int3 cell_index(const Vec3f& p, float resolution) {
   return {round_to_int(p.x / resolution), round_to_int(p.y / resolution), round_to_int(p.z / resolution)};
 }
 
+// Same result as cell_index(p, resolution), cheaper: q~ = x * (1/resolution) is within 2^-22 |q| of the IEEE
+// quotient fl(x / resolution); unless q~ lies that close to a rounding boundary k + 0.5 (where the two could round
+// to different integers) lround(q~) IS lround(fl(x / resolution)). The rare near-boundary case takes the division.
+struct CellDivider {
+  float resolution, inverse;
+};
+DL_HD CellDivider make_divider(float resolution) { return {resolution, 1.0f / resolution}; }
+DL_HD int round_div(float x, const CellDivider& d) {
+  const float q = x * d.inverse;
+  const float aq = fabsf(q);
+  const float fr = aq - floorf(aq);                       // exact
+  if (fabsf(fr - 0.5f) > aq * 4.8e-7f + 1e-30f && aq < 4194304.f) {
+    const int k = (int)floorf(aq + 0.5f);                   // aq + 0.5 is exact below 2^22
+    return q < 0.f ? -k : k;
+  }
+  return round_to_int(x / d.resolution);
+}
+DL_HD Int3 cell_index(const Vec3f& p, const CellDivider& d) { return {round_div(p.x, d), round_div(p.y, d), round_div(p.z, d)}; }
+
 // uint16 grid value -> probability: the expression that fills the reference's lookup table
 // (probability_values.cc:27-68): value * kScale + (0.1f - kScale), unknown (0) -> 0.1f, marker bit ignored.
 // Evaluated inline (two rounded float ops) it is bit-identical to a table read.

@@ -54,6 +54,7 @@ struct FrontendArgs {
   uint32_t* slot2;
   float* local;                  // local-frame point of every first-filter survivor, indexed by input row
   uint8_t* cls;                  // 0 dropped, 1 return, 2 miss
+  uint8_t* win;                  // 1 = owns its second-filter voxel
   int32_t* tile_counts;
   float* returns_tracking;
   float* misses_tracking;

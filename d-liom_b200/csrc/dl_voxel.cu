@@ -129,7 +129,9 @@ __global__ void voxel_indices_kernel(const float* __restrict__ points, int strid
                                      int32_t* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const Int3 c = row_cell(points, stride, (uint32_t)i, res);
+  // the reciprocal-multiply fast path with its exact fallback (dl_math.cuh round_div): what the fused front end uses
+  const float* p = points + (size_t)i * stride;
+  const Int3 c = cell_index(Vec3f{p[0], p[1], p[2]}, make_divider(res));
   out[3 * i] = c.x;
   out[3 * i + 1] = c.y;
   out[3 * i + 2] = c.z;
@@ -139,7 +141,7 @@ __global__ void voxel_indices_kernel(const float* __restrict__ points, int strid
 // One CTA runs the whole data-dependent pass sequence of AdaptivelyVoxelFiltered for one (cloud, filter) pair,
 // so the bisection needs no host round trip: every pass clears the table, re-inserts the range-cropped cloud and
 // block-reduces the survivor count; the control flow below is the reference's, statement for statement.
-constexpr int kAdaptiveBlock = 512;   // 128 registers per thread available: 32 cached points + working set
+constexpr int kAdaptiveBlock = 1024;  // 64 registers per thread: 8 cached points each, the rest in shared memory
 constexpr int kAdaptiveWarps = kAdaptiveBlock / 32;
 
 __device__ __forceinline__ int block_sum_1024(int v) {
@@ -227,10 +229,10 @@ __device__ __forceinline__ bool adaptive_search(const AdaptiveParams& opt, RunPa
 // ---- fast mode: the cropped cloud lives in registers (<= 16 points per thread), the hash table in shared memory
 // (packed 63-bit voxel keys + min index), duplicates inside a warp are merged with match.any before touching the
 // table. A pass is then ~16 ALU iterations + shared-memory atomics: no global traffic at all.
-constexpr int kFastPoints = 32;                       // points per thread held in registers (x 512 threads = 16 384)
+constexpr int kFastPoints = 8;                        // points per thread held in registers (x 1024 threads = 8 192)
 constexpr int kFastSlots = 4096;                      // shared-memory table slots (12 B each = 48 KiB)
 constexpr int kFastExtra = 14336;                     // further points cached in shared memory (12 B each = 168 KiB)
-constexpr int kFastCapacity = kFastPoints * 512 + kFastExtra;
+constexpr int kFastCapacity = kFastPoints * 1024 + kFastExtra;  // 22 528 points
 constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
 
 struct FastTable {
@@ -254,8 +256,8 @@ __device__ __forceinline__ uint32_t hash_key(unsigned long long k) {
 
 // One point of a pass (all 32 lanes of the warp call this together): lanes that fall into the same voxel are
 // merged with match.any and only the lowest lane (= lowest id) touches the table. Returns 1 for a new voxel.
-__device__ __forceinline__ int fast_insert(FastTable& tab, bool have, float x, float y, float z, int j, float edge,
-                                           int* fail_flag) {
+__device__ __forceinline__ int fast_insert(FastTable& tab, bool have, float x, float y, float z, int j,
+                                           const CellDivider& edge, int* fail_flag) {
   const int lane = threadIdx.x & 31;
   unsigned long long key = kEmptyKey - 1 - lane;  // distinct dummy for idle lanes
   bool ok = true;
@@ -285,7 +287,8 @@ __device__ __forceinline__ int fast_insert(FastTable& tab, bool have, float x, f
 
 // Returns the number of distinct voxels, or -1 if the table overflowed / a key could not be packed.
 __device__ __forceinline__ int fast_pass(FastTable& tab, const float (&px)[kFastPoints], const float (&py)[kFastPoints],
-                                         const float (&pz)[kFastPoints], int m, float edge, int* fail_flag) {
+                                         const float (&pz)[kFastPoints], int m, float edge_length, int* fail_flag) {
+  const CellDivider edge = make_divider(edge_length);
   for (int i = threadIdx.x; i < kFastSlots; i += kAdaptiveBlock) {
     tab.keys[i] = kEmptyKey;
     tab.mins[i] = 0xFFFFFFFFu;
@@ -310,7 +313,7 @@ __device__ __forceinline__ int fast_pass(FastTable& tab, const float (&px)[kFast
 
 __device__ __forceinline__ bool fast_survives(const FastTable& tab, float x, float y, float z, float edge, int j) {
   unsigned long long key;
-  pack_cell(cell_index(Vec3f{x, y, z}, edge), &key);
+  pack_cell(cell_index(Vec3f{x, y, z}, make_divider(edge)), &key);
   uint32_t h = hash_key(key) & (kFastSlots - 1);
   while (tab.keys[h] != key) h = (h + 1) & (kFastSlots - 1);
   return tab.mins[h] == (uint32_t)j;

@@ -78,6 +78,24 @@ def test_voxel_filter_bit_exact(ctx, orc, stride):
         assert np.array_equal(ctx.voxel_filter(pts, res), orc.voxel_filter(pts, res))
 
 
+def test_voxel_indices_reciprocal_path_adversarial(ctx, orc):
+    """dl_voxel_indices runs the multiply-by-reciprocal fast path with its exact-division fallback (round_div); the
+    oracle divides. Hammer the rounding boundaries: points at k + 0.5 voxels +- a few ulps, huge and tiny values."""
+    rng = np.random.RandomState(99)
+    for res in (np.float32(0.075), np.float32(0.15), np.float32(0.1), np.float32(0.45), np.float32(2.0), np.float32(3.25)):
+        k = rng.randint(-200000, 200000, 200000).astype(np.float32)
+        base = ((k + np.float32(0.5)) * res).astype(np.float32)
+        ulps = rng.randint(-4, 5, len(base))
+        x = base.copy()
+        for _ in range(4):
+            x = np.where(ulps > 0, np.nextafter(x, np.float32(np.inf)), np.where(ulps < 0, np.nextafter(x, np.float32(-np.inf)), x))
+            ulps = ulps - np.sign(ulps)
+        pts = np.stack([x, rng.uniform(-1e5, 1e5, len(x)).astype(np.float32),
+                        (rng.standard_cauchy(len(x)) * 1e-3).astype(np.float32)], 1).astype(np.float32)
+        pts[:10, 2] = [0.0, -0.0, 1e-30, -1e-30, 1e-45, 3e6, -3e6, 1e7 * float(res), 0.5 * float(res), -0.5 * float(res)]
+        assert np.array_equal(ctx.voxel_indices(pts, res), orc.voxel_indices(pts, res)), float(res)
+
+
 def test_voxel_filter_reference_fixtures(ctx):
     pc = np.array([[0, 0, 0], [0.1, -0.1, 0.1], [0.3, -0.1, 0], [0, 0, 0.1]], np.float32)
     assert ctx.voxel_filter(pc, 0.3).tolist() == [0, 2]
