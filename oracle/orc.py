@@ -28,6 +28,13 @@ class SolveSummary(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class Preintegration(C.Structure):
+    """Pre-integrated IMU measurement (layout shared with dl_preintegration in include/dliom_b200.h)."""
+    _fields_ = [("sum_dt", C.c_double), ("delta_p", C.c_double * 3), ("delta_q", C.c_double * 4),
+                ("delta_v", C.c_double * 3), ("ba", C.c_double * 3), ("bg", C.c_double * 3),
+                ("jacobian", C.c_double * 225), ("covariance", C.c_double * 225)]
+
+
 class FrontEndOptions(C.Structure):
     """Field-for-field the parameters LocalTrajectoryBuilder3D reads on the hot path; defaults =
     configuration_files/trajectory_builder_3d.lua."""
@@ -118,6 +125,12 @@ def lib():
     L.orc_frontend_batch.restype = C.c_double
     L.orc_frontend_batch.argtypes = [C.POINTER(FrontEndOptions), C.c_int, C.POINTER(C.c_void_p), i64p, f32p, f64p,
                                      f64p, f64p, C.c_void_p, C.c_void_p, C.c_int, f64p, i32p]
+    L.orc_imu_preintegrate.argtypes = [f64p, f64p, f64p, C.c_int, f64p, f64p, f64p, C.POINTER(Preintegration)]
+    L.orc_imu_predict.argtypes = [f64p, C.POINTER(Preintegration), f64p, f64p]
+    L.orc_imu_residual.argtypes = [f64p, f64p, C.POINTER(Preintegration), f64p, f64p, C.c_void_p]
+    L.orc_fused_match.argtypes = [C.c_int, C.POINTER(C.c_void_p), i64p, C.POINTER(C.c_void_p), f64p, C.c_double,
+                                  C.c_double, C.c_int, C.c_int, f64p, f64p, f64p, C.POINTER(Preintegration), f64p,
+                                  C.c_double, f64p, C.POINTER(SolveSummary)]
     _LIB = L
     return L
 
@@ -343,3 +356,51 @@ def frontend_batch(opts, ranges_list, origin, prev_poses, cur_poses, submap_loca
                                     np.ascontiguousarray(submap_local_pose, np.float64), hi_grid.h, lo_grid.h,
                                     threads, poses, ok)
     return secs, poses, ok
+
+
+# ---------------------------------------------------------------- IMU (orc_imu.h)
+GRAVITY = np.array([0.0, 0.0, 9.8])
+
+
+def nav_state(p=(0, 0, 0), q=(1, 0, 0, 0), v=(0, 0, 0), ba=(0, 0, 0), bg=(0, 0, 0)):
+    """16 doubles: p(3) q(4 wxyz) v(3) ba(3) bg(3)."""
+    return np.array(list(p) + list(q) + list(v) + list(ba) + list(bg), np.float64)
+
+
+def imu_preintegrate(noise4, ba, bg, dt, acc, gyr):
+    m = Preintegration()
+    dt = np.ascontiguousarray(dt, np.float64)
+    lib().orc_imu_preintegrate(np.ascontiguousarray(noise4, np.float64), np.ascontiguousarray(ba, np.float64),
+                               np.ascontiguousarray(bg, np.float64), len(dt), dt,
+                               np.ascontiguousarray(acc, np.float64).reshape(-1, 3),
+                               np.ascontiguousarray(gyr, np.float64).reshape(-1, 3), C.byref(m))
+    return m
+
+
+def imu_predict(state_i, m, G=GRAVITY):
+    out = np.zeros(16)
+    lib().orc_imu_predict(np.ascontiguousarray(state_i, np.float64), C.byref(m), np.ascontiguousarray(G, np.float64), out)
+    return out
+
+
+def imu_residual(state_i, state_j, m, G=GRAVITY, jacobian=True):
+    r = np.zeros(15)
+    J = np.zeros((15, 15))
+    lib().orc_imu_residual(np.ascontiguousarray(state_i, np.float64), np.ascontiguousarray(state_j, np.float64),
+                           C.byref(m), np.ascontiguousarray(G, np.float64), r,
+                           J.ctypes.data_as(C.c_void_p) if jacobian else None)
+    return r, J
+
+
+def fused_match(clouds, grids, occ_weights, trans_w, rot_w, target_translation, state_i, initial_j, m, G=GRAVITY,
+                imu_weight=1.0, nonmono=False, max_iter=12):
+    clouds, cp, gp, sizes = _pairs(clouds, grids)
+    out = np.zeros(16)
+    s = SolveSummary()
+    ok = lib().orc_fused_match(len(clouds), cp, sizes, gp, np.asarray(occ_weights, np.float64), trans_w, rot_w,
+                               int(nonmono), max_iter, np.ascontiguousarray(target_translation, np.float64),
+                               np.ascontiguousarray(state_i, np.float64), np.ascontiguousarray(initial_j, np.float64),
+                               C.byref(m), np.ascontiguousarray(G, np.float64), imu_weight, out, C.byref(s))
+    if not ok:
+        raise RuntimeError("pre-integration covariance is not positive definite")
+    return out, s.as_dict()

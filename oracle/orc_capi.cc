@@ -8,6 +8,7 @@
 #include "orc_filters.h"
 #include "orc_frontend.h"
 #include "orc_grid.h"
+#include "orc_imu.h"
 #include "orc_nls.h"
 #include "orc_rtcsm.h"
 
@@ -192,6 +193,85 @@ void orc_ceres_normal_equations(int n_pairs, const float* const* clouds, const i
     }
   }
   *cost = 0.5 * c;
+}
+
+// ---- IMU pre-integration and the fused solve (orc_imu.h). States cross as 16 doubles: p(3) q(4 wxyz) v(3) ba(3) bg(3).
+struct OrcPreintegration {
+  double sum_dt;
+  double delta_p[3], delta_q[4], delta_v[3], ba[3], bg[3];
+  double jacobian[225], covariance[225];  // row-major 15x15, order p, theta, v, ba, bg
+};
+static void preint_out(const Preintegration& p, OrcPreintegration* o) {
+  o->sum_dt = p.sum_dt;
+  o->delta_p[0] = p.delta_p.x; o->delta_p[1] = p.delta_p.y; o->delta_p[2] = p.delta_p.z;
+  o->delta_q[0] = p.delta_q.w; o->delta_q[1] = p.delta_q.x; o->delta_q[2] = p.delta_q.y; o->delta_q[3] = p.delta_q.z;
+  o->delta_v[0] = p.delta_v.x; o->delta_v[1] = p.delta_v.y; o->delta_v[2] = p.delta_v.z;
+  o->ba[0] = p.ba.x; o->ba[1] = p.ba.y; o->ba[2] = p.ba.z;
+  o->bg[0] = p.bg.x; o->bg[1] = p.bg.y; o->bg[2] = p.bg.z;
+  for (int i = 0; i < 15; ++i)
+    for (int j = 0; j < 15; ++j) {
+      o->jacobian[i * 15 + j] = p.jacobian[i][j];
+      o->covariance[i * 15 + j] = p.covariance[i][j];
+    }
+}
+static Preintegration preint_in(const OrcPreintegration& o) {
+  Preintegration p;
+  p.sum_dt = o.sum_dt;
+  p.delta_p = {o.delta_p[0], o.delta_p[1], o.delta_p[2]};
+  p.delta_q = {o.delta_q[0], o.delta_q[1], o.delta_q[2], o.delta_q[3]};
+  p.delta_v = {o.delta_v[0], o.delta_v[1], o.delta_v[2]};
+  p.ba = {o.ba[0], o.ba[1], o.ba[2]};
+  p.bg = {o.bg[0], o.bg[1], o.bg[2]};
+  for (int i = 0; i < 15; ++i)
+    for (int j = 0; j < 15; ++j) {
+      p.jacobian[i][j] = o.jacobian[i * 15 + j];
+      p.covariance[i][j] = o.covariance[i * 15 + j];
+    }
+  return p;
+}
+
+// n samples (dt, acc xyz, gyr xyz); the first only latches acc_0 / gyr_0 (integration_base.h:111-118).
+void orc_imu_preintegrate(const double* noise4, const double* ba, const double* bg, int n, const double* dt,
+                          const double* acc, const double* gyr, OrcPreintegration* out) {
+  Preintegration p;
+  preint_reset(&p, {ba[0], ba[1], ba[2]}, {bg[0], bg[1], bg[2]});
+  const ImuNoise noise{noise4[0], noise4[1], noise4[2], noise4[3]};
+  for (int i = 0; i < n; ++i)
+    preint_push(&p, dt[i], {acc[3 * i], acc[3 * i + 1], acc[3 * i + 2]}, {gyr[3 * i], gyr[3 * i + 1], gyr[3 * i + 2]}, noise);
+  preint_out(p, out);
+}
+void orc_imu_predict(const double* state_i, const OrcPreintegration* m, const double* G, double* state_j) {
+  const NavState j = imu_predict(FusedProblem::unpack(state_i), preint_in(*m), {G[0], G[1], G[2]});
+  FusedProblem::pack(j, state_j);
+}
+void orc_imu_residual(const double* state_i, const double* state_j, const OrcPreintegration* m, const double* G,
+                      double* r15, double* J225) {
+  double J[15][15];
+  imu_residual(FusedProblem::unpack(state_i), FusedProblem::unpack(state_j), preint_in(*m), {G[0], G[1], G[2]}, r15,
+               J225 ? J : nullptr);
+  if (J225)
+    for (int i = 0; i < 15; ++i)
+      for (int j = 0; j < 15; ++j) J225[i * 15 + j] = J[i][j];
+}
+int orc_fused_match(int n_pairs, const float* const* clouds, const int64_t* sizes, void* const* grids,
+                    const double* occ_w, double trans_w, double rot_w, int nonmono, int max_iter,
+                    const double* target_translation, const double* state_i, const double* initial_j,
+                    const OrcPreintegration* m, const double* G, double imu_weight, double* state_j,
+                    OrcSolveSummary* summary) {
+  std::vector<CloudAndGrid> pairs;
+  for (int i = 0; i < n_pairs; ++i) pairs.push_back({clouds[i], sizes[i], (const HybridGrid*)grids[i]});
+  SolveSummary s;
+  NavState out;
+  const bool ok = fused_scan_match(make_ceres_options(n_pairs, occ_w, trans_w, rot_w, 0, nonmono, max_iter),
+                                   {target_translation[0], target_translation[1], target_translation[2]},
+                                   FusedProblem::unpack(state_i), FusedProblem::unpack(initial_j), preint_in(*m),
+                                   {G[0], G[1], G[2]}, imu_weight, pairs, &out, &s);
+  if (!ok) return 0;
+  FusedProblem::pack(out, state_j);
+  if (summary)
+    *summary = {s.initial_cost, s.final_cost, (int)s.iterations.size(), s.num_successful_steps,
+                s.num_unsuccessful_steps, s.termination, s.num_residual_evaluations, s.num_jacobian_evaluations};
+  return 1;
 }
 
 // ---- per-scan front end

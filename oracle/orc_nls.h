@@ -144,6 +144,7 @@ class ScanMatchProblem {
 
   int num_residuals() const { return num_residuals_; }
   int num_local() const { return opt_.only_optimize_yaw ? 4 : 6; }
+  int num_ambient() const { return 7; }
 
   // x = [t(3), q(4) wxyz]. Fills residuals; if J != nullptr also the row-major
   // num_residuals x num_local Jacobian in the local parameterisation.
@@ -315,12 +316,14 @@ struct LmConstants {
   int max_consecutive_nonmonotonic_steps = 5;
 };
 
-inline void solve_trust_region(const ScanMatchProblem& problem, bool use_nonmonotonic_steps, int max_num_iterations,
-                               double* parameters /*7, in-out*/, SolveSummary* summary) {
+template <typename Problem>
+inline void solve_trust_region(const Problem& problem, bool use_nonmonotonic_steps, int max_num_iterations,
+                               double* parameters /*ambient size, in-out*/, SolveSummary* summary) {
   const LmConstants c;
   const int m = problem.num_residuals();
   const int n = problem.num_local();
-  std::vector<double> x(parameters, parameters + 7), cand(7);
+  const int na = problem.num_ambient();
+  std::vector<double> x(parameters, parameters + na), cand(na);
   std::vector<double> res(m), J((size_t)m * n), Jaug((size_t)(m + n) * n), rhs(m + n);
   std::vector<double> scale(n), diag(n), lmdiag(n), g(n), step(n), delta(n), model(m);
   double x_cost = 0, x_norm = 0, minimum_cost = std::numeric_limits<double>::max();
@@ -329,7 +332,7 @@ inline void solve_trust_region(const ScanMatchProblem& problem, bool use_nonmono
   int num_consecutive_invalid = 0;
 
   IterationLog it{};
-  auto norm7 = [](const double* a) { double s = 0; for (int i = 0; i < 7; ++i) s += a[i] * a[i]; return std::sqrt(s); };
+  auto norm7 = [na](const double* a) { double s = 0; for (int i = 0; i < na; ++i) s += a[i] * a[i]; return std::sqrt(s); };
 
   auto evaluate_gradient_and_jacobian = [&]() {
     problem.Evaluate(x.data(), res.data(), J.data());
@@ -349,11 +352,11 @@ inline void solve_trust_region(const ScanMatchProblem& problem, bool use_nonmono
     }
     for (int i = 0; i < m; ++i) for (int j = 0; j < n; ++j) J[(size_t)i * n + j] *= scale[j];
     // projected gradient: x - Plus(x, -g), ambient max-norm
-    std::vector<double> ng(n), px(7);
+    std::vector<double> ng(n), px(na);
     for (int j = 0; j < n; ++j) ng[j] = -g[j];
     problem.Plus(x.data(), ng.data(), px.data());
     double mx = 0;
-    for (int i = 0; i < 7; ++i) mx = std::max(mx, std::fabs(x[i] - px[i]));
+    for (int i = 0; i < na; ++i) mx = std::max(mx, std::fabs(x[i] - px[i]));
     it.gradient_max_norm = mx;
   };
 
@@ -384,7 +387,7 @@ inline void solve_trust_region(const ScanMatchProblem& problem, bool use_nonmono
       summary->num_successful_steps++;
       if (x_cost < minimum_cost) {
         minimum_cost = x_cost;
-        for (int i = 0; i < 7; ++i) parameters[i] = x[i];
+        for (int i = 0; i < na; ++i) parameters[i] = x[i];
       }
     } else {
       summary->num_unsuccessful_steps++;
@@ -455,7 +458,7 @@ inline void solve_trust_region(const ScanMatchProblem& problem, bool use_nonmono
     // ---- ParameterToleranceReached
     {
       double s = 0;
-      for (int i = 0; i < 7; ++i) s += (x[i] - cand[i]) * (x[i] - cand[i]);
+      for (int i = 0; i < na; ++i) s += (x[i] - cand[i]) * (x[i] - cand[i]);
       it.step_norm = std::sqrt(s);
       if (it.step_norm <= c.parameter_tolerance * (x_norm + c.parameter_tolerance)) {
         finish(kConvergence, "parameter tolerance");  // the unfinished iteration is not recorded

@@ -51,12 +51,13 @@ def workload(beams=16, num_map_scans=8, num_scans=4, hi_res=0.1, lo_res=0.45, st
         lo.insert_range_data(o, local)
         t += 0.1
     rng = np.random.RandomState(45)
-    scans, prevs, curs, truths = [], [], [], []
+    scans, prevs, curs, truths, times = [], [], [], [], []
     for _ in range(num_scans):
+        times.append(t)
         scans.append(synth.make_scan(scene, beams, t))
         prevs.append(synth.pose7(t - 0.1))
         truths.append(synth.pose7(t))
         curs.append(synth.perturb_pose(synth.pose7(t), rng, 0.05, 0.5))
         t += 0.1
     return {"opts": opts, "hi": hi, "lo": lo, "origin": origin, "scans": scans, "prev": np.array(prevs),
-            "cur": np.array(curs), "truth": np.array(truths), "submap_pose": orc.IDENTITY_POSE.copy()}
+            "cur": np.array(curs), "truth": np.array(truths), "times": times, "submap_pose": orc.IDENTITY_POSE.copy()}
