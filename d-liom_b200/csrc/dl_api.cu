@@ -694,6 +694,190 @@ int dl_ceres_normal_equations(dl_context* ctx, const dl_ceres_options* options, 
 
 }  // extern "C"
 
+// ------------------------------------------------------------------------------------------------ IMU
+namespace {
+struct HostImuTerm {  // must match ImuTerm in dl_nls.cu
+  double pi[3], qi[4], vi[3], bai[3], bgi[3];
+  double dp[3], dq[4], dv[3];
+  double G[3];
+  double sum_dt;
+  double W[225];
+};
+static_assert(sizeof(HostImuTerm) == kImuTermDoubles * sizeof(double), "ImuTerm layout");
+
+// W = weight^2 * Sigma^-1 by Cholesky (Sigma = L L^T, W = L^-T L^-1). False if Sigma is not positive definite.
+bool information_matrix(const double* sigma, double weight, double* W) {
+  double L[15][15] = {};
+  for (int i = 0; i < 15; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double s = sigma[i * 15 + j];
+      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+      if (i == j) {
+        if (!(s > 0)) return false;
+        L[i][i] = std::sqrt(s);
+      } else {
+        L[i][j] = s / L[j][j];
+      }
+    }
+  double Li[15][15] = {};  // L^-1 (lower)
+  for (int c = 0; c < 15; ++c) {
+    for (int i = c; i < 15; ++i) {
+      double s = i == c ? 1.0 : 0.0;
+      for (int k = c; k < i; ++k) s -= L[i][k] * Li[k][c];
+      Li[i][c] = s / L[i][i];
+    }
+  }
+  for (int a = 0; a < 15; ++a)
+    for (int b = 0; b < 15; ++b) {
+      double s = 0;
+      for (int k = std::max(a, b); k < 15; ++k) s += Li[k][a] * Li[k][b];
+      W[a * 15 + b] = weight * weight * s;
+    }
+  return true;
+}
+}  // namespace
+
+extern "C" {
+
+int dl_imu_preintegrate(dl_context* ctx, const dl_imu_noise* noise, int32_t count, const int32_t* offsets,
+                        const double* dt, const double* acc, const double* gyr, const double* biases,
+                        dl_preintegration* out) {
+  if (!ctx || !noise || count < 0 || (count > 0 && (!offsets || !dt || !acc || !gyr || !biases || !out))) return DL_ERR_ARG;
+  if (count == 0) return DL_OK;
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)offsets[count];
+  for (int k = 0; k < count; ++k)
+    if (offsets[k + 1] < offsets[k]) return ctx->fail(DL_ERR_ARG, "offsets must be non-decreasing");
+  DL_TRY(ctx->reserve_device(arena_bytes({(size_t)(count + 1) * 4, n * 8, n * 24, n * 24, (size_t)count * 48,
+                                          (size_t)count * sizeof(dl_preintegration)})));
+  Arena a(ctx->d_scratch);
+  int32_t* d_off = a.take<int32_t>(count + 1);
+  double* d_dt = a.take<double>(n);
+  double* d_acc = a.take<double>(3 * n);
+  double* d_gyr = a.take<double>(3 * n);
+  double* d_bias = a.take<double>(6 * (size_t)count);
+  dl_preintegration* d_out = a.take<dl_preintegration>(count);
+  DL_TRY(h2d(ctx, d_off, offsets, count + 1));
+  DL_TRY(h2d(ctx, d_dt, dt, n));
+  DL_TRY(h2d(ctx, d_acc, acc, 3 * n));
+  DL_TRY(h2d(ctx, d_gyr, gyr, 3 * n));
+  DL_TRY(h2d(ctx, d_bias, biases, 6 * (size_t)count));
+  DL_TRY(launch_imu_preintegrate(ctx, count, d_off, d_dt, d_acc, d_gyr, d_bias, *noise, d_out));
+  DL_TRY(d2h(ctx, out, d_out, count));
+  return sync(ctx);
+}
+
+int dl_imu_predict(const dl_nav_state* si, const dl_preintegration* m, const double* gravity, dl_nav_state* sj) {
+  if (!si || !m || !gravity || !sj) return DL_ERR_ARG;
+  const double T = m->sum_dt;
+  const Quatd qi{si->q[0], si->q[1], si->q[2], si->q[3]};
+  const Vec3d G{gravity[0], gravity[1], gravity[2]};
+  const Vec3d p = add(sub(add(Vec3d{si->p[0], si->p[1], si->p[2]}, mul(T, Vec3d{si->v[0], si->v[1], si->v[2]})), mul(0.5 * T * T, G)),
+                      rotate(qi, Vec3d{m->delta_p[0], m->delta_p[1], m->delta_p[2]}));
+  const Vec3d v = add(sub(Vec3d{si->v[0], si->v[1], si->v[2]}, mul(T, G)), rotate(qi, Vec3d{m->delta_v[0], m->delta_v[1], m->delta_v[2]}));
+  const Quatd q = qnormalized(qmul(qi, Quatd{m->delta_q[0], m->delta_q[1], m->delta_q[2], m->delta_q[3]}));
+  *sj = *si;
+  sj->p[0] = p.x; sj->p[1] = p.y; sj->p[2] = p.z;
+  sj->v[0] = v.x; sj->v[1] = v.y; sj->v[2] = v.z;
+  sj->q[0] = q.w; sj->q[1] = q.x; sj->q[2] = q.y; sj->q[3] = q.z;
+  return DL_OK;
+}
+
+int dl_fused_match_batch(dl_context* ctx, const dl_ceres_options* options, double imu_weight, const double* gravity,
+                         int32_t count, int32_t num_pairs, const double* submap_local_poses,
+                         const dl_nav_state* states_i, const dl_nav_state* initial_states_j,
+                         const dl_preintegration* preints, const float* const* clouds, const int64_t* sizes,
+                         const dl_grid* const* grids, dl_nav_state* states_j_out, dl_solve_summary* summaries) {
+  if (!ctx) return DL_ERR_ARG;
+  DL_TRY(check_ceres_options(ctx, options, num_pairs));
+  if (options->only_optimize_yaw) return ctx->fail(DL_ERR_ARG, "only_optimize_yaw is not supported by the fused solve");
+  if (count < 0 || !gravity || !(imu_weight >= 0.) ||
+      (count > 0 && (!submap_local_poses || !states_i || !initial_states_j || !preints || !clouds || !sizes || !grids || !states_j_out)))
+    return DL_ERR_ARG;
+  if (count == 0) return DL_OK;
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t total_points = 0;
+  for (int i = 0; i < count * num_pairs; ++i) {
+    if (sizes[i] < 0 || !grids[i] || (sizes[i] > 0 && !clouds[i])) return DL_ERR_ARG;
+    if (sizes[i] == 0) return ctx->fail(DL_ERR_EMPTY, "empty point cloud");
+    if (grids[i]->structure_dirty) return ctx->fail(DL_ERR_ARG, "dl_grid_sync not called after dl_grid_set_cells");
+    total_points += (size_t)sizes[i];
+  }
+  DL_TRY(ctx->reserve_device(arena_bytes({total_points * 12 + (size_t)count * num_pairs * 256, (size_t)count * sizeof(NlsProblem),
+                                          (size_t)count * sizeof(HostImuTerm), (size_t)count * 128,
+                                          (size_t)count * sizeof(FusedOutput)})));
+  Arena a(ctx->d_scratch);
+  std::vector<NlsProblem> problems(count);
+  std::vector<HostImuTerm> terms(count);
+  std::vector<double> init16((size_t)count * 16);
+  for (int c = 0; c < count; ++c) {
+    // everything is moved into the submap frame: the grids live there and the solve is frame-invariant
+    const Rigidd to_submap = inverse(pose_from7(submap_local_poses + 7 * c));
+    const dl_nav_state& si = states_i[c];
+    const dl_nav_state& sj = initial_states_j[c];
+    const Rigidd pose_i = compose(to_submap, Rigidd{{si.p[0], si.p[1], si.p[2]}, {si.q[0], si.q[1], si.q[2], si.q[3]}});
+    const Rigidd pose_j = compose(to_submap, Rigidd{{sj.p[0], sj.p[1], sj.p[2]}, {sj.q[0], sj.q[1], sj.q[2], sj.q[3]}});
+    const Vec3d vi = rotate(to_submap.q, Vec3d{si.v[0], si.v[1], si.v[2]});
+    const Vec3d vj = rotate(to_submap.q, Vec3d{sj.v[0], sj.v[1], sj.v[2]});
+    const Vec3d G = rotate(to_submap.q, Vec3d{gravity[0], gravity[1], gravity[2]});
+    HostImuTerm& t = terms[c];
+    t.pi[0] = pose_i.t.x; t.pi[1] = pose_i.t.y; t.pi[2] = pose_i.t.z;
+    t.qi[0] = pose_i.q.w; t.qi[1] = pose_i.q.x; t.qi[2] = pose_i.q.y; t.qi[3] = pose_i.q.z;
+    t.vi[0] = vi.x; t.vi[1] = vi.y; t.vi[2] = vi.z;
+    for (int k = 0; k < 3; ++k) {
+      t.bai[k] = si.ba[k]; t.bgi[k] = si.bg[k];
+      t.dp[k] = preints[c].delta_p[k]; t.dv[k] = preints[c].delta_v[k];
+    }
+    for (int k = 0; k < 4; ++k) t.dq[k] = preints[c].delta_q[k];
+    t.G[0] = G.x; t.G[1] = G.y; t.G[2] = G.z;
+    t.sum_dt = preints[c].sum_dt;
+    if (!information_matrix(preints[c].covariance, imu_weight, t.W))
+      return ctx->fail(DL_ERR_ARG, "pre-integration covariance is not positive definite");
+    double* x = init16.data() + 16 * c;
+    pose_to7(pose_j, x);
+    x[7] = vj.x; x[8] = vj.y; x[9] = vj.z;
+    for (int k = 0; k < 3; ++k) { x[10 + k] = sj.ba[k]; x[13 + k] = sj.bg[k]; }
+    NlsProblem& p = problems[c];
+    std::memset(&p, 0, sizeof(p));
+    for (int k = 0; k < num_pairs; ++k) {
+      const int i = c * num_pairs + k;
+      float* d = a.take<float>(3 * sizes[i]);
+      DL_TRY(h2d(ctx, d, clouds[i], 3 * sizes[i]));
+      p.cloud[k] = d;
+      p.count[k] = (int32_t)sizes[i];
+      p.grid[k] = grids[i]->view();
+    }
+    for (int k = 0; k < 7; ++k) p.initial[k] = x[k];
+    for (int k = 0; k < 3; ++k) p.target_t[k] = x[k];  // the translation prior (if weighted) pulls to the IMU prediction
+  }
+  NlsProblem* d_problems = a.take<NlsProblem>(count);
+  HostImuTerm* d_terms = a.take<HostImuTerm>(count);
+  double* d_init = a.take<double>((size_t)count * 16);
+  FusedOutput* d_out = a.take<FusedOutput>(count);
+  DL_TRY(h2d(ctx, d_problems, problems.data(), count));
+  DL_TRY(h2d(ctx, d_terms, terms.data(), count));
+  DL_TRY(h2d(ctx, d_init, init16.data(), (size_t)count * 16));
+  DL_TRY(launch_nls_fused(ctx, to_nls_options(*options, num_pairs), d_problems, d_terms, d_init, count, d_out));
+  std::vector<FusedOutput> out(count);
+  DL_TRY(d2h(ctx, out.data(), d_out, count));
+  DL_TRY(sync(ctx));
+  for (int c = 0; c < count; ++c) {
+    const Rigidd submap = pose_from7(submap_local_poses + 7 * c);
+    const double* x = out[c].state;
+    const Rigidd pose = compose(submap, pose_from7(x));
+    const Vec3d v = rotate(submap.q, Vec3d{x[7], x[8], x[9]});
+    dl_nav_state& o = states_j_out[c];
+    o.p[0] = pose.t.x; o.p[1] = pose.t.y; o.p[2] = pose.t.z;
+    o.q[0] = pose.q.w; o.q[1] = pose.q.x; o.q[2] = pose.q.y; o.q[3] = pose.q.z;
+    o.v[0] = v.x; o.v[1] = v.y; o.v[2] = v.z;
+    for (int k = 0; k < 3; ++k) { o.ba[k] = x[10 + k]; o.bg[k] = x[13 + k]; }
+    if (summaries) summaries[c] = out[c].summary;
+  }
+  return DL_OK;
+}
+
+}  // extern "C"
+
 // ------------------------------------------------------------------------------------------------ batched front end
 namespace {
 

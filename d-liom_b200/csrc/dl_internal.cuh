@@ -206,8 +206,18 @@ struct NlsOutput {
   dl_solve_summary summary;
 };
 int launch_nls(dl_context* ctx, const NlsOptions& opt, const NlsProblem* problems_dev, int count, NlsOutput* out_dev);
+struct FusedOutput {
+  double state[16];  // p(3) q(4 wxyz) v(3) ba(3) bg(3)
+  dl_solve_summary summary;
+};
+// Host-side mirror of the device ImuTerm (dl_nls.cu): 3+4+3+3+3 + 3+4+3 + 3 + 1 + 225 doubles.
+constexpr int kImuTermDoubles = 16 + 10 + 3 + 1 + 225;
+int launch_nls_fused(dl_context* ctx, const NlsOptions& opt, const NlsProblem* problems_dev, const void* imu_terms_dev,
+                     const double* initial16_dev, int count, FusedOutput* out_dev);
 int launch_nls_normal_equations(dl_context* ctx, const NlsOptions& opt, const NlsProblem* problems_dev,
                                 const double* at_pose_dev, double* out28_dev);
+int launch_imu_preintegrate(dl_context* ctx, int count, const int32_t* offsets, const double* dts, const double* accs,
+                            const double* gyrs, const double* biases, const dl_imu_noise& noise, dl_preintegration* out);
 int launch_interpolate(dl_context* ctx, const GridView& grid, int64_t n, const double* xyz, double* out);
 int launch_grid_lookup(dl_context* ctx, const GridView& grid, int64_t n, const int32_t* xyz, uint16_t* out);
 

@@ -249,21 +249,127 @@ __device__ void evaluate(const NlsOptions& opt, const NlsProblem& prob, Shared& 
   __syncthreads();
 }
 
-struct Eval {
+// ---------------------------------------------------------------------------------------------------------------
+// Everything below is templated on N, the size of the local parameter vector held by the LM state:
+//   N = 6   the reference's scan matcher (pose only; 4 of the 6 used with only_optimize_yaw), ambient size 7
+//   N = 15  the fused solve: pose + velocity + accelerometer / gyroscope biases of state j (ambient size 16), with
+//           the IMU pre-integration residual of integration_base.h:267-301 added to the normal equations.
+template <int N>
+struct EvalT {
   double cost;
-  double g[6];
-  double H[6][6];
+  double g[N];
+  double H[N][N];
 };
-__device__ __forceinline__ void load_eval(const Shared& sh, Eval* e) {
-  e->cost = 0.5 * sh.acc[0];
-  for (int c = 0; c < 6; ++c) e->g[c] = sh.acc[1 + c];
-  for (int c = 0; c < 6; ++c)
-    for (int d = c; d < 6; ++d) e->H[c][d] = e->H[d][c] = sh.acc[7 + tri(c, d)];
+template <int N>
+struct Dims {
+  static constexpr int ambient = N == 15 ? 16 : 7;
+};
+
+// IMU term of the fused solve, prepared on the host in the SUBMAP frame (dl_api.cu): state i (fixed), the
+// pre-integrated deltas, gravity, and W = weight^2 * Sigma^-1 (row-major 15x15, order p, theta, v, ba, bg).
+struct ImuTerm {
+  double pi[3], qi[4], vi[3], bai[3], bgi[3];
+  double dp[3], dq[4], dv[3];
+  double G[3];
+  double sum_dt;
+  double W[225];
+};
+struct ImuShared {
+  double r[15], Wr[15];
+  double J[15][15], WJ[15][15];
+  double H[15][15], g[15], cost2;
+};
+
+// Residual (15) and Jacobian (15 x 15) w.r.t. the local parameters of state j, thread 0 only.
+__device__ void imu_residual_jacobian(const ImuTerm& m, const double* x /*16*/, ImuShared& is) {
+  const double T = m.sum_dt;
+  const Quatd qi_inv{m.qi[0], -m.qi[1], -m.qi[2], -m.qi[3]};
+  const Vec3d G{m.G[0], m.G[1], m.G[2]};
+  const Vec3d pj{x[0], x[1], x[2]}, vj{x[7], x[8], x[9]};
+  const Vec3d pi{m.pi[0], m.pi[1], m.pi[2]}, vi{m.vi[0], m.vi[1], m.vi[2]};
+  const Quatd qj{x[3], x[4], x[5], x[6]};
+  const Vec3d rp = sub(rotate(qi_inv, sub(sub(add(mul(0.5 * T * T, G), pj), pi), mul(T, vi))), Vec3d{m.dp[0], m.dp[1], m.dp[2]});
+  const Quatd A = qmul(Quatd{m.dq[0], -m.dq[1], -m.dq[2], -m.dq[3]}, qi_inv);
+  const Quatd e = qmul(A, qj);
+  const Vec3d rv = sub(rotate(qi_inv, sub(add(mul(T, G), vj), vi)), Vec3d{m.dv[0], m.dv[1], m.dv[2]});
+  is.r[0] = rp.x; is.r[1] = rp.y; is.r[2] = rp.z;
+  is.r[3] = 2 * e.x; is.r[4] = 2 * e.y; is.r[5] = 2 * e.z;
+  is.r[6] = rv.x; is.r[7] = rv.y; is.r[8] = rv.z;
+  for (int a = 0; a < 3; ++a) {
+    is.r[9 + a] = x[10 + a] - m.bai[a];
+    is.r[12 + a] = x[13 + a] - m.bgi[a];
+  }
+  for (int a = 0; a < 15; ++a)
+    for (int b = 0; b < 15; ++b) is.J[a][b] = 0.0;
+  // R_i^T = rotation matrix of qi_inv, column by column
+  for (int b = 0; b < 3; ++b) {
+    const Vec3d col = rotate(qi_inv, Vec3d{b == 0 ? 1.0 : 0.0, b == 1 ? 1.0 : 0.0, b == 2 ? 1.0 : 0.0});
+    is.J[0][b] = col.x; is.J[1][b] = col.y; is.J[2][b] = col.z;
+    is.J[6][6 + b] = col.x; is.J[7][6 + b] = col.y; is.J[8][6 + b] = col.z;
+    const Quatd c = qmul(qmul(A, Quatd{0.0, b == 0 ? 1.0 : 0.0, b == 1 ? 1.0 : 0.0, b == 2 ? 1.0 : 0.0}), qj);
+    is.J[3][3 + b] = 2 * c.x; is.J[4][3 + b] = 2 * c.y; is.J[5][3 + b] = 2 * c.z;
+  }
+  for (int a = 0; a < 6; ++a) is.J[9 + a][9 + a] = 1.0;
 }
 
-// Solves (A) y = b for symmetric positive definite A (n <= 6) by Cholesky; false if not PD / not finite.
-__device__ bool cholesky_solve(int n, double A[6][6], const double* b, double* y) {
-  double Lm[6][6];
+// All threads: is.H = J^T W J, is.g = J^T W r, is.cost2 = r^T W r.
+__device__ void imu_normal_equations(const ImuTerm& m, const double* x, ImuShared& is) {
+  if (threadIdx.x == 0) imu_residual_jacobian(m, x, is);
+  __syncthreads();
+  for (int e = threadIdx.x; e < 225; e += kBlock) {
+    const int c = e / 15, b = e % 15;
+    double s = 0;
+    for (int d = 0; d < 15; ++d) s += m.W[c * 15 + d] * is.J[d][b];
+    is.WJ[c][b] = s;
+  }
+  if (threadIdx.x < 15) {
+    double s = 0;
+    for (int d = 0; d < 15; ++d) s += m.W[threadIdx.x * 15 + d] * is.r[d];
+    is.Wr[threadIdx.x] = s;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 225; e += kBlock) {
+    const int a = e / 15, b = e % 15;
+    double s = 0;
+    for (int c = 0; c < 15; ++c) s += is.J[c][a] * is.WJ[c][b];
+    is.H[a][b] = s;
+  }
+  if (threadIdx.x < 15) {
+    double s = 0;
+    for (int c = 0; c < 15; ++c) s += is.J[c][threadIdx.x] * is.Wr[c];
+    is.g[threadIdx.x] = s;
+  }
+  if (threadIdx.x == 32) {
+    double s = 0;
+    for (int c = 0; c < 15; ++c) s += is.r[c] * is.Wr[c];
+    is.cost2 = s;
+  }
+  __syncthreads();
+}
+
+template <int N>
+__device__ __forceinline__ void load_eval(const Shared& sh, const ImuShared* is, EvalT<N>* e) {
+  double c2 = sh.acc[0];
+  for (int c = 0; c < N; ++c) {
+    e->g[c] = c < 6 ? sh.acc[1 + c] : 0.0;
+    for (int d = 0; d < N; ++d) e->H[c][d] = 0.0;
+  }
+  for (int c = 0; c < 6; ++c)
+    for (int d = c; d < 6; ++d) e->H[c][d] = e->H[d][c] = sh.acc[7 + tri(c, d)];
+  if (N == 15 && is) {
+    c2 += is->cost2;
+    for (int c = 0; c < N; ++c) {
+      e->g[c] += is->g[c];
+      for (int d = 0; d < N; ++d) e->H[c][d] += is->H[c][d];
+    }
+  }
+  e->cost = 0.5 * c2;
+}
+
+// Solves A y = b for symmetric positive definite A (n <= N) by Cholesky; false if not PD / not finite.
+template <int N>
+__device__ bool cholesky_solve(int n, double A[N][N], const double* b, double* y) {
+  double Lm[N][N];
   for (int i = 0; i < n; ++i) {
     for (int j = 0; j <= i; ++j) {
       double s = A[i][j];
@@ -276,7 +382,7 @@ __device__ bool cholesky_solve(int n, double A[6][6], const double* b, double* y
       }
     }
   }
-  double z[6];
+  double z[N];
   for (int i = 0; i < n; ++i) {
     double s = b[i];
     for (int k = 0; k < i; ++k) s -= Lm[i][k] * z[k];
@@ -318,10 +424,12 @@ __device__ __forceinline__ void setup_problem(const NlsOptions& opt, const NlsPr
 // Trust-region state of one problem (names follow Ceres 1.13 TrustRegionMinimizer / LevenbergMarquardtStrategy /
 // TrustRegionStepEvaluator members). Lives in shared memory and is touched by thread 0 only, so the evaluation
 // pass keeps the registers.
-struct LmState {
-  Eval cur;
-  double x[7], cand[7], best_x[7], target_t[3], target_q_inv[4];
-  double scale[6], diag[6];
+template <int N>
+struct LmStateT {
+  static constexpr int NA = Dims<N>::ambient;
+  EvalT<N> cur;
+  double x[NA], cand[NA], best_x[NA], target_t[3], target_q_inv[4];
+  double scale[N], diag[N];
   double x_norm, minimum_cost, radius, decrease_factor, gradient_max_norm, initial_cost, final_cost, last_cost;
   double model_cost_change;
   double ev_minimum, ev_current, ev_reference, ev_candidate, ev_acc_ref, ev_acc_cand;
@@ -330,28 +438,39 @@ struct LmState {
   int nl, only_yaw, max_iter;
 };
 
-__device__ __forceinline__ double norm7(const double* v) {
+template <int NA>
+__device__ __forceinline__ double norm_ambient(const double* v) {
   double s = 0;
-  for (int i = 0; i < 7; ++i) s += v[i] * v[i];
+  for (int i = 0; i < NA; ++i) s += v[i] * v[i];
   return sqrt(s);
 }
+// x (+) delta for the N-dim local vector: pose like the scan matcher, the remaining 9 parameters additively.
+template <int N>
+__device__ __forceinline__ void plus_n(const double* x, const double* delta, bool only_yaw, double* out) {
+  plus(x, delta, only_yaw, out);
+  if (N == 15)
+    for (int i = 0; i < 9; ++i) out[7 + i] = x[7 + i] + delta[6 + i];
+}
 // max-norm of x - Plus(x, -g): the projected gradient Ceres tests against gradient_tolerance
+template <int N>
 __device__ double projected_gradient_max_norm(const double* at, const double* g, bool only_yaw) {
-  double ng[6], px[7];
-  for (int j = 0; j < 6; ++j) ng[j] = -g[j];
-  plus(at, ng, only_yaw, px);
+  constexpr int NA = Dims<N>::ambient;
+  double ng[N], px[NA];
+  for (int j = 0; j < N; ++j) ng[j] = -g[j];
+  plus_n<N>(at, ng, only_yaw, px);
   double mx = 0;
-  for (int i = 0; i < 7; ++i) mx = fmax(mx, fabs(at[i] - px[i]));
+  for (int i = 0; i < NA; ++i) mx = fmax(mx, fabs(at[i] - px[i]));
   return mx;
 }
 
-__device__ __noinline__ void lm_iteration_zero(LmState& st, const Shared& sh) {
-  load_eval(sh, &st.cur);
+template <int N>
+__device__ __noinline__ void lm_iteration_zero(LmStateT<N>& st, const Shared& sh, const ImuShared* is) {
+  load_eval<N>(sh, is, &st.cur);
   st.evals = 1;
   for (int j = 0; j < st.nl; ++j) st.scale[j] = 1.0 / (1.0 + sqrt(st.cur.H[j][j]));
-  for (int j = st.nl; j < 6; ++j) st.scale[j] = 0.0;
-  st.x_norm = norm7(st.x);
-  st.gradient_max_norm = projected_gradient_max_norm(st.x, st.cur.g, st.only_yaw);
+  for (int j = st.nl; j < N; ++j) st.scale[j] = 0.0;
+  st.x_norm = norm_ambient<Dims<N>::ambient>(st.x);
+  st.gradient_max_norm = projected_gradient_max_norm<N>(st.x, st.cur.g, st.only_yaw);
   st.initial_cost = st.final_cost = st.last_cost = st.cur.cost;
   st.ev_minimum = st.ev_current = st.ev_reference = st.ev_candidate = st.cur.cost;
   st.ev_acc_ref = st.ev_acc_cand = 0;
@@ -367,12 +486,14 @@ __device__ __noinline__ void lm_iteration_zero(LmState& st, const Shared& sh) {
 
 // FinalizeIterationAndCheckIfMinimizerCanContinue + ComputeTrustRegionStep (+ HandleInvalidStep retries).
 // Returns 1 to stop; otherwise st.cand holds the candidate point.
-__device__ __noinline__ int lm_prepare_step(LmState& st) {
+template <int N>
+__device__ __noinline__ int lm_prepare_step(LmStateT<N>& st) {
+  constexpr int NA = Dims<N>::ambient;
   if (st.last_successful) {
     ++st.successful;
     if (st.cur.cost < st.minimum_cost) {
       st.minimum_cost = st.cur.cost;
-      for (int i = 0; i < 7; ++i) st.best_x[i] = st.x[i];
+      for (int i = 0; i < NA; ++i) st.best_x[i] = st.x[i];
     }
   } else {
     ++st.unsuccessful;
@@ -386,7 +507,7 @@ __device__ __noinline__ int lm_prepare_step(LmState& st) {
   for (;;) {
     ++st.iteration;
     // LevenbergMarquardtStrategy::ComputeStep on the Jacobi-scaled system
-    double A[6][6], Hs[6][6], gs[6], y[6], step[6];
+    double A[N][N], Hs[N][N], gs[N], y[N], step[N];
     for (int c = 0; c < nl; ++c) {
       gs[c] = st.scale[c] * st.cur.g[c];
       for (int d = 0; d < nl; ++d) Hs[c][d] = A[c][d] = st.scale[c] * st.cur.H[c][d] * st.scale[d];
@@ -394,7 +515,7 @@ __device__ __noinline__ int lm_prepare_step(LmState& st) {
     if (!st.reuse_diagonal)
       for (int c = 0; c < nl; ++c) st.diag[c] = fmin(fmax(A[c][c], Lm::min_lm_diagonal), Lm::max_lm_diagonal);
     for (int c = 0; c < nl; ++c) A[c][c] += st.diag[c] / st.radius;
-    bool valid = cholesky_solve(nl, A, gs, y);
+    bool valid = cholesky_solve<N>(nl, A, gs, y);
     st.reuse_diagonal = 1;
     if (valid) {
       double lin = 0, quad = 0;
@@ -412,9 +533,9 @@ __device__ __noinline__ int lm_prepare_step(LmState& st) {
     }
     if (valid) {
       st.num_invalid = 0;
-      double delta[6] = {0, 0, 0, 0, 0, 0};
-      for (int c = 0; c < nl; ++c) delta[c] = step[c] * st.scale[c];
-      plus(st.x, delta, st.only_yaw, st.cand);
+      double delta[N];
+      for (int c = 0; c < N; ++c) delta[c] = c < nl ? step[c] * st.scale[c] : 0.0;
+      plus_n<N>(st.x, delta, st.only_yaw, st.cand);
       return 0;
     }
     // HandleInvalidStep, then finalize that iteration and retry with the smaller radius
@@ -430,15 +551,17 @@ __device__ __noinline__ int lm_prepare_step(LmState& st) {
 }
 
 // Tolerance tests, step acceptance and trust-region update for the evaluated candidate. Returns 1 to stop.
-__device__ __noinline__ int lm_process_candidate(LmState& st, const Shared& sh) {
-  Eval ce;
-  load_eval(sh, &ce);
+template <int N>
+__device__ __noinline__ int lm_process_candidate(LmStateT<N>& st, const Shared& sh, const ImuShared* is) {
+  constexpr int NA = Dims<N>::ambient;
+  EvalT<N> ce;
+  load_eval<N>(sh, is, &ce);
   ++st.evals;
   double candidate_cost = ce.cost;
   if (!isfinite(candidate_cost)) candidate_cost = 1.7976931348623157e308;
   // ParameterToleranceReached
   double sn = 0;
-  for (int i = 0; i < 7; ++i) sn += (st.x[i] - st.cand[i]) * (st.x[i] - st.cand[i]);
+  for (int i = 0; i < NA; ++i) sn += (st.x[i] - st.cand[i]) * (st.x[i] - st.cand[i]);
   if (sqrt(sn) <= Lm::parameter_tolerance * (st.x_norm + Lm::parameter_tolerance)) { st.termination = 0; return 1; }
   // FunctionToleranceReached
   if (fabs(st.cur.cost - candidate_cost) <= Lm::function_tolerance * st.cur.cost) { st.termination = 0; return 1; }
@@ -447,14 +570,15 @@ __device__ __noinline__ int lm_process_candidate(LmState& st, const Shared& sh) 
   const double relative_decrease = fmax(relative, historical);
   if (relative_decrease > Lm::min_relative_decrease) {
     // HandleSuccessfulStep (the candidate's normal equations were computed speculatively in the same pass)
-    for (int i = 0; i < 7; ++i) st.x[i] = st.cand[i];
-    st.x_norm = norm7(st.x);
+    for (int i = 0; i < NA; ++i) st.x[i] = st.cand[i];
+    st.x_norm = norm_ambient<NA>(st.x);
     st.cur = ce;
     st.cur.cost = candidate_cost;
-    st.gradient_max_norm = projected_gradient_max_norm(st.x, st.cur.g, st.only_yaw);
+    st.gradient_max_norm = projected_gradient_max_norm<N>(st.x, st.cur.g, st.only_yaw);
     st.last_successful = 1;
     st.last_cost = candidate_cost;
-    st.radius = st.radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * relative_decrease - 1.0, 3.0));
+    const double t = 2.0 * relative_decrease - 1.0;
+    st.radius = st.radius / fmax(1.0 / 3.0, 1.0 - t * t * t);
     st.radius = fmin(Lm::max_radius, st.radius);
     st.decrease_factor = 2.0;
     st.reuse_diagonal = 0;
@@ -489,55 +613,83 @@ __device__ __noinline__ int lm_process_candidate(LmState& st, const Shared& sh) 
 }
 
 // The trust-region loop of Ceres 1.13 (TrustRegionMinimizer::Minimize): thread 0 drives the state machine between
-// evaluation passes in which every thread takes part.
-__global__ void __launch_bounds__(kBlock) nls_solve_kernel(NlsOptions opt, const NlsProblem* __restrict__ problems,
-                                                           NlsOutput* __restrict__ outputs) {
+// evaluation passes in which every thread takes part. FUSED adds the IMU term (15 local parameters).
+template <bool FUSED>
+__device__ __forceinline__ void solve_body(const NlsOptions& opt, const NlsProblem& prob, const ImuTerm* imu,
+                                           const double* initial16, double* pose_out /*7 or 16*/,
+                                           dl_solve_summary* summary) {
+  constexpr int N = FUSED ? 15 : 6;
+  constexpr int NA = Dims<N>::ambient;
   __shared__ Shared sh;
-  __shared__ LmState st;
-  const NlsProblem& prob = problems[blockIdx.x];
+  __shared__ LmStateT<N> st;
+  __shared__ ImuShared is_storage[FUSED ? 1 : 0 + 1];
+  __shared__ double xfull[16];
+  ImuShared* is = FUSED ? &is_storage[0] : nullptr;
   {
     double x[7], target_t[3], target_q_inv[4];
     setup_problem(opt, prob, sh, x, target_t, target_q_inv);
     if (threadIdx.x == 0) {
       for (int i = 0; i < 7; ++i) st.x[i] = x[i];
+      if (FUSED)
+        for (int i = 7; i < 16; ++i) st.x[i] = initial16[i];
+      for (int i = 0; i < NA; ++i) xfull[i] = st.x[i];
       for (int i = 0; i < 3; ++i) st.target_t[i] = target_t[i];
       for (int i = 0; i < 4; ++i) st.target_q_inv[i] = target_q_inv[i];
-      st.only_yaw = opt.only_yaw != 0;
-      st.nl = st.only_yaw ? 4 : 6;
+      st.only_yaw = FUSED ? 0 : (opt.only_yaw != 0);
+      st.nl = FUSED ? 15 : (st.only_yaw ? 4 : 6);
       st.max_iter = opt.max_iter;
       st.max_nonmono = opt.nonmono ? Lm::max_consecutive_nonmonotonic : 0;
     }
   }
   __syncthreads();
-  evaluate(opt, prob, sh, st.target_q_inv, st.target_t);
-  if (threadIdx.x == 0) lm_iteration_zero(st, sh);
+  auto evaluate_all = [&]() {
+    evaluate(opt, prob, sh, st.target_q_inv, st.target_t);
+    if (FUSED) imu_normal_equations(*imu, xfull, *is);
+  };
+  evaluate_all();
+  if (threadIdx.x == 0) lm_iteration_zero<N>(st, sh, is);
   for (;;) {
     __syncthreads();  // every thread has consumed sh.stop / sh.acc of the previous round
     if (threadIdx.x == 0) {
-      const int stop = lm_prepare_step(st);
+      const int stop = lm_prepare_step<N>(st);
       sh.stop = stop;
-      if (!stop)
+      if (!stop) {
         for (int i = 0; i < 7; ++i) sh.x[i] = st.cand[i];
+        for (int i = 0; i < NA; ++i) xfull[i] = st.cand[i];
+      }
     }
     __syncthreads();
     if (sh.stop) break;
-    evaluate(opt, prob, sh, st.target_q_inv, st.target_t);  // candidate cost + speculative normal equations
-    if (threadIdx.x == 0) sh.stop = lm_process_candidate(st, sh);
+    evaluate_all();  // candidate cost + speculative normal equations
+    if (threadIdx.x == 0) sh.stop = lm_process_candidate<N>(st, sh, is);
     __syncthreads();
     if (sh.stop) break;
   }
   if (threadIdx.x == 0) {
-    NlsOutput& o = outputs[blockIdx.x];
-    for (int i = 0; i < 7; ++i) o.pose[i] = st.best_x[i];
-    o.summary.initial_cost = st.initial_cost;
-    o.summary.final_cost = st.final_cost;
-    o.summary.num_iterations = st.recorded;
-    o.summary.num_successful_steps = st.successful;
-    o.summary.num_unsuccessful_steps = st.unsuccessful;
-    o.summary.termination = st.termination;
-    o.summary.num_evaluations = st.evals;
-    o.summary.reserved = 0;
+    for (int i = 0; i < NA; ++i) pose_out[i] = st.best_x[i];
+    summary->initial_cost = st.initial_cost;
+    summary->final_cost = st.final_cost;
+    summary->num_iterations = st.recorded;
+    summary->num_successful_steps = st.successful;
+    summary->num_unsuccessful_steps = st.unsuccessful;
+    summary->termination = st.termination;
+    summary->num_evaluations = st.evals;
+    summary->reserved = 0;
   }
+}
+
+__global__ void __launch_bounds__(kBlock) nls_solve_kernel(NlsOptions opt, const NlsProblem* __restrict__ problems,
+                                                           NlsOutput* __restrict__ outputs) {
+  NlsOutput& o = outputs[blockIdx.x];
+  solve_body<false>(opt, problems[blockIdx.x], nullptr, nullptr, o.pose, &o.summary);
+}
+
+__global__ void __launch_bounds__(kBlock) nls_fused_kernel(NlsOptions opt, const NlsProblem* __restrict__ problems,
+                                                           const ImuTerm* __restrict__ imu,
+                                                           const double* __restrict__ initial16,
+                                                           FusedOutput* __restrict__ outputs) {
+  FusedOutput& o = outputs[blockIdx.x];
+  solve_body<true>(opt, problems[blockIdx.x], imu + blockIdx.x, initial16 + 16 * blockIdx.x, o.state, &o.summary);
 }
 
 // One evaluation pass at a given pose; writes the 28 reduced doubles (cost, g, H upper triangle).
@@ -575,6 +727,14 @@ int launch_nls(dl_context* ctx, const NlsOptions& opt, const NlsProblem* problem
   if (count <= 0) return DL_OK;
   nls_solve_kernel<<<count, kBlock, 0, ctx->stream>>>(opt, problems_dev, out_dev);
   DL_LAUNCH_CHECK(ctx, "nls_solve_kernel");
+  return DL_OK;
+}
+
+int launch_nls_fused(dl_context* ctx, const NlsOptions& opt, const NlsProblem* problems_dev, const void* imu_terms_dev,
+                     const double* initial16_dev, int count, FusedOutput* out_dev) {
+  if (count <= 0) return DL_OK;
+  nls_fused_kernel<<<count, kBlock, 0, ctx->stream>>>(opt, problems_dev, (const ImuTerm*)imu_terms_dev, initial16_dev, out_dev);
+  DL_LAUNCH_CHECK(ctx, "nls_fused_kernel");
   return DL_OK;
 }
 

@@ -24,7 +24,7 @@ EXPORTS = [
     "dl_context_stream", "dl_context_synchronize", "dl_context_set_profiling", "dl_context_read_profile", "dl_grid_create", "dl_grid_destroy", "dl_grid_set_cells",
     "dl_grid_sync", "dl_grid_resolution", "dl_grid_num_bricks", "dl_grid_lookup", "dl_grid_interpolate",
     "dl_voxel_filter", "dl_voxel_indices", "dl_adaptive_voxel_filter", "dl_rtcsm_match", "dl_ceres_match",
-    "dl_ceres_match_batch", "dl_ceres_normal_equations", "dl_ingest_scan", "dl_frontend_match_batch",
+    "dl_ceres_match_batch", "dl_ceres_normal_equations", "dl_imu_preintegrate", "dl_imu_predict", "dl_fused_match_batch", "dl_ingest_scan", "dl_frontend_match_batch",
     "dl_frontend_match_batch_dev", "dl_frontend_fetch_results", "dl_device_alloc", "dl_device_free",
     "dl_copy_to_device", "dl_copy_to_host",
 ]
@@ -52,6 +52,30 @@ class RtcsmOptions(C.Structure):
 class RtcsmInfo(C.Structure):
     _fields_ = [("best_index", C.c_int64), ("num_candidates", C.c_int64), ("linear_window", C.c_int32),
                 ("angular_window", C.c_int32), ("angular_step", C.c_float), ("max_scan_range", C.c_float)]
+
+
+class ImuNoise(C.Structure):
+    _fields_ = [("acc_n", C.c_double), ("gyr_n", C.c_double), ("acc_w", C.c_double), ("gyr_w", C.c_double)]
+
+
+class Preintegration(C.Structure):
+    _fields_ = [("sum_dt", C.c_double), ("delta_p", C.c_double * 3), ("delta_q", C.c_double * 4),
+                ("delta_v", C.c_double * 3), ("linearized_ba", C.c_double * 3), ("linearized_bg", C.c_double * 3),
+                ("jacobian", C.c_double * 225), ("covariance", C.c_double * 225)]
+
+
+class NavState(C.Structure):
+    _fields_ = [("p", C.c_double * 3), ("q", C.c_double * 4), ("v", C.c_double * 3), ("ba", C.c_double * 3),
+                ("bg", C.c_double * 3)]
+
+    @staticmethod
+    def from16(x):
+        s = NavState()
+        s.p[:], s.q[:], s.v[:], s.ba[:], s.bg[:] = x[0:3], x[3:7], x[7:10], x[10:13], x[13:16]
+        return s
+
+    def to16(self):
+        return np.array(list(self.p) + list(self.q) + list(self.v) + list(self.ba) + list(self.bg))
 
 
 class CeresOptions(C.Structure):
@@ -160,6 +184,11 @@ def lib():
                                        f64p, ip(SolveSummary)]
     L.dl_ceres_normal_equations.argtypes = [vp, ip(CeresOptions), f64p, f64p, f64p, C.c_int32, ip(vp), i64p, ip(vp),
                                             f64p, f64p, f64p]
+    L.dl_imu_preintegrate.argtypes = [vp, ip(ImuNoise), C.c_int32, i32p, f64p, f64p, f64p, f64p, ip(Preintegration)]
+    L.dl_imu_predict.argtypes = [ip(NavState), ip(Preintegration), f64p, ip(NavState)]
+    L.dl_fused_match_batch.argtypes = [vp, ip(CeresOptions), C.c_double, f64p, C.c_int32, C.c_int32, f64p, ip(NavState),
+                                       ip(NavState), ip(Preintegration), ip(vp), i64p, ip(vp), ip(NavState),
+                                       ip(SolveSummary)]
     L.dl_ingest_scan.argtypes = [vp, ip(FrontendOptions), vp, C.c_int64, f32p, C.c_int32, f64p, f64p, i64p, f32p, f32p,
                                  f32p, f32p, i64p]
     L.dl_frontend_match_batch.argtypes = [vp, ip(FrontendOptions), C.c_int32, ip(vp), i64p, f32p, C.c_int32, f64p,
@@ -317,6 +346,42 @@ class Context:
                                                     np.ascontiguousarray(at_pose, np.float64), len(clouds), cp, sizes,
                                                     gp, cost, g, h))
         return cost[0], g, h.reshape(6, 6)
+
+    # ---- IMU
+    def imu_preintegrate(self, noise4, intervals, biases):
+        """intervals: list of (dt[n], acc[n,3], gyr[n,3]); biases: (count, 6). Returns a ctypes array of Preintegration."""
+        count = len(intervals)
+        offsets = np.zeros(count + 1, np.int32)
+        for k, (dt, _, _) in enumerate(intervals):
+            offsets[k + 1] = offsets[k] + len(dt)
+        dt = np.ascontiguousarray(np.concatenate([i[0] for i in intervals]), np.float64)
+        acc = np.ascontiguousarray(np.concatenate([np.asarray(i[1]).reshape(-1, 3) for i in intervals]), np.float64)
+        gyr = np.ascontiguousarray(np.concatenate([np.asarray(i[2]).reshape(-1, 3) for i in intervals]), np.float64)
+        out = (Preintegration * count)()
+        noise = ImuNoise(*noise4)
+        self.check(self.L.dl_imu_preintegrate(self.h, C.byref(noise), count, offsets, dt, acc, gyr,
+                                              np.ascontiguousarray(biases, np.float64).reshape(count, 6), out))
+        return out
+
+    def imu_predict(self, state_i16, m, gravity=(0.0, 0.0, 9.8)):
+        si, sj = NavState.from16(state_i16), NavState()
+        self.check(self.L.dl_imu_predict(C.byref(si), C.byref(m), np.ascontiguousarray(gravity, np.float64), C.byref(sj)))
+        return sj.to16()
+
+    def fused_match_batch(self, problems, grids_per_problem, occ_weights, trans_w, rot_w, submap_poses, states_i,
+                          initial_states_j, preints, imu_weight=1.0, gravity=(0.0, 0.0, 9.8), nonmono=False, max_iter=12):
+        count, num_pairs = len(problems), len(problems[0])
+        clouds, cp, gp, sizes = self._pairs([c for p in problems for c in p], [g for p in grids_per_problem for g in p])
+        opt = CeresOptions.make(occ_weights, trans_w, rot_w, False, nonmono, max_iter)
+        si = (NavState * count)(*[NavState.from16(x) for x in states_i])
+        sj = (NavState * count)(*[NavState.from16(x) for x in initial_states_j])
+        pm = (Preintegration * count)(*preints)
+        out = (NavState * count)()
+        sums = (SolveSummary * count)()
+        self.check(self.L.dl_fused_match_batch(self.h, C.byref(opt), imu_weight, np.ascontiguousarray(gravity, np.float64),
+                                               count, num_pairs, np.ascontiguousarray(submap_poses, np.float64), si, sj,
+                                               pm, cp, sizes, gp, out, sums))
+        return np.array([o.to16() for o in out]), [s.as_dict() for s in sums]
 
     # ---- front end
     def ingest_scan(self, options, ranges, origins, prev_pose, cur_pose):

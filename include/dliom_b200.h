@@ -157,6 +157,40 @@ int dl_ceres_normal_equations(dl_context* ctx, const dl_ceres_options* options, 
                               const float* const* clouds, const int64_t* sizes, const dl_grid* const* grids,
                               double* cost, double* gradient6, double* hessian36);
 
+/* ---- IMU: pre-integration (LocalTrajectoryBuilder3D::AddImuData, LTB:164-201, with the in-repo mid-point integrator
+ *      C/mapping/internal/3d/initialization/integration_base.h:109-265 instead of the un-vendored GTSAM one) and the
+ *      scan match with the pre-integration residual (integration_base.h:267-301) fused into the same solve.
+ *      The fused solve is an EXTENSION asked for by BASELINE.json: the reference chains CeresScanMatcher3D::Match and a
+ *      GTSAM iSAM2 update (LTB:535-555, :693-863). State order everywhere: p, theta, v, b_a, b_g. ------------------- */
+typedef struct dl_imu_noise { /* C/mapping/proto/imu_options.proto: acc_noise, gyr_noise, acc/gyr bias random walk */
+  double acc_n, gyr_n, acc_w, gyr_w;
+} dl_imu_noise;
+typedef struct dl_preintegration {
+  double sum_dt;
+  double delta_p[3], delta_q[4], delta_v[3];  /* delta_q is w x y z */
+  double linearized_ba[3], linearized_bg[3];
+  double jacobian[225], covariance[225];       /* row-major 15 x 15 */
+} dl_preintegration;
+typedef struct dl_nav_state { /* X(k), V(k), B(k) of the reference's window (LTB:708-852) */
+  double p[3], q[4], v[3], ba[3], bg[3];
+} dl_nav_state;
+/* `count` intervals; interval k uses samples [offsets[k], offsets[k+1]) of dt / acc (xyz) / gyr (xyz); the first
+ * sample of an interval only latches the integrator (integration_base.h:111-118). biases: 6 doubles per interval. */
+int dl_imu_preintegrate(dl_context* ctx, const dl_imu_noise* noise, int32_t count, const int32_t* offsets,
+                        const double* dt, const double* acc, const double* gyr, const double* biases,
+                        dl_preintegration* out);
+/* State at the end of the interval (the front end's pose prediction, LTB:188-199). gravity: 3 doubles (+9.8 z). */
+int dl_imu_predict(const dl_nav_state* state_i, const dl_preintegration* m, const double* gravity, dl_nav_state* state_j);
+/* Fused scan match for `count` independent problems: state i fixed, the 15 local parameters of state j estimated
+ * from the occupied-space residuals (+ optional translation / rotation priors of `options`) and the IMU residual
+ * weighted by imu_weight^2 * covariance^-1. States are in the local frame; submap_local_poses (7 doubles each) place
+ * the grids. Arrays indexed like dl_ceres_match_batch. */
+int dl_fused_match_batch(dl_context* ctx, const dl_ceres_options* options, double imu_weight, const double* gravity,
+                         int32_t count, int32_t num_pairs, const double* submap_local_poses,
+                         const dl_nav_state* states_i, const dl_nav_state* initial_states_j,
+                         const dl_preintegration* preintegrations, const float* const* clouds, const int64_t* sizes,
+                         const dl_grid* const* grids, dl_nav_state* states_j_out, dl_solve_summary* summaries);
+
 /* ---- the per-scan front end of LocalTrajectoryBuilder3D::AddRangeData / AddAccumulatedRangeData
  *      (LTB:393-554): voxel filter -> deskew/transform/range gate -> voxel filter -> adaptive filters ->
  *      [RT-CSM] -> Ceres match, for a batch of independent scans against one submap. ---------------------------- */
