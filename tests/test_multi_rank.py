@@ -1,0 +1,64 @@
+"""world_size-2 gloo test (CPU) of the N>1 host logic: the problem list is partitioned across ranks with no overlap
+and no gap, per-rank results gather back in rank order, and the step time is the max over ranks."""
+import os
+import sys
+
+import numpy as np
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, tmp):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "d-liom_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"),
+                    os.path.join(ROOT, "tools")]
+    import torch.distributed as dist
+    from dliom import shard
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import orc
+        from helpers import workload
+        w = workload(beams=16, num_map_scans=4, num_scans=5)
+        mine = shard.shard_range(len(w["scans"]), rank, world)
+        rows = []
+        for s in mine:   # each rank registers only its own scans (with the CPU oracle here: no GPU in this test)
+            ing = orc.ingest_scan(w["opts"], w["scans"][s], w["origin"], w["prev"][s], w["cur"][s])
+            m = orc.match_scan(w["opts"], ing["returns_tracking"], ing["current_pose"].astype(np.float64),
+                               w["submap_pose"], w["hi"], w["lo"])
+            rows.append(np.concatenate([[s], m["pose_estimate_local"]]))
+        gathered = shard.gather_results(dist, np.array(rows).reshape(-1, 8))
+        slowest = shard.max_over_ranks(dist, 10.0 + rank)
+        if rank == 0:
+            np.save(os.path.join(tmp, "gathered.npy"), np.concatenate(gathered))
+            np.save(os.path.join(tmp, "slowest.npy"), np.array([slowest]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partition_is_exact():
+    sys.path.insert(0, os.path.join(ROOT, "d-liom_b200"))
+    from dliom import shard
+    for n in (0, 1, 5, 64, 65, 1000):
+        for world in (1, 2, 3, 8):
+            parts = [list(shard.shard_range(n, r, world)) for r in range(world)]
+            assert sum(parts, []) == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_two_ranks_gloo(tmp_path):
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    g = np.load(tmp_path / "gathered.npy")
+    assert g[:, 0].astype(int).tolist() == [0, 1, 2, 3, 4]     # rank order == scan order, nothing lost or duplicated
+    assert np.load(tmp_path / "slowest.npy")[0] == 11.0          # max over ranks
+    # same poses as a single-process run
+    sys.path[:0] = [os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")]
+    import orc
+    from helpers import workload
+    w = workload(beams=16, num_map_scans=4, num_scans=5)
+    for s in range(5):
+        ing = orc.ingest_scan(w["opts"], w["scans"][s], w["origin"], w["prev"][s], w["cur"][s])
+        m = orc.match_scan(w["opts"], ing["returns_tracking"], ing["current_pose"].astype(np.float64), w["submap_pose"],
+                           w["hi"], w["lo"])
+        assert np.array_equal(g[s, 1:], m["pose_estimate_local"])
