@@ -3,6 +3,7 @@
 // There is deliberately no CPU implementation of anything here: without a CUDA device every call fails.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -119,6 +120,7 @@ int dl_context_create(int device_ordinal, dl_context** out) {
   if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->staging_done, cudaEventDisableTiming)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e);
     delete ctx;
@@ -138,6 +140,7 @@ void dl_context_destroy(dl_context* ctx) {
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->staging_done) cudaEventDestroy(ctx->staging_done);
   delete ctx;
 }
@@ -898,6 +901,7 @@ struct FrontendBuffers {
   int32_t *last_index, *error_flag;
   float* back_pose;
   uint8_t* win;
+  void* pose_table;
   ScanConstants* scans;
   AdaptiveParams* filters;
   double *initial_pose, *target;
@@ -915,7 +919,7 @@ size_t frontend_bytes(int batch, int64_t cap, int num_origins, size_t extra) {
                       B * C * 12, B * C * 12, B * C * 12, B * C * 12, B * C * 12, B * 2 * C * 12, B * 28, (size_t)num_origins * 12,
                       B * 2 * 32 * 4, B * 4, B * C, B * sizeof(ScanConstants), 2 * sizeof(AdaptiveParams), B * 56, B * 24,
                       B * sizeof(NlsProblem), B * sizeof(NlsOutput),
-                      B * (size_t)next_pow2(cap) * 8, B * (size_t)next_pow2(cap) * 4, B * C * 4, B * 4, 64, B * 28, B * C}) + extra + 8192;
+                      B * (size_t)next_pow2(cap) * 8, B * (size_t)next_pow2(cap) * 4, B * C * 4, B * 4, 64, B * 28, B * C, fe_pose_table_bytes(batch)}) + extra + 8192;
 }
 
 void carve(Arena& a, int batch, int64_t cap, int num_origins, FrontendBuffers* f) {
@@ -945,6 +949,7 @@ void carve(Arena& a, int batch, int64_t cap, int num_origins, FrontendBuffers* f
   f->slot2 = a.take<uint32_t>(B * C); f->last_index = a.take<int32_t>(B); f->error_flag = a.take<int32_t>(1);
   f->back_pose = a.take<float>(B * 7);
   f->win = a.take<uint8_t>(B * C);
+  f->pose_table = a.take<char>(fe_pose_table_bytes(batch));
 }
 
 FrontendArgs make_frontend_args(const dl_frontend_options& o, const FrontendBuffers& f, const float* d_ranges,
@@ -959,7 +964,7 @@ FrontendArgs make_frontend_args(const dl_frontend_options& o, const FrontendBuff
   fa.local = f.tmp_points; fa.cls = f.cls; fa.win = f.win; fa.tile_counts = f.tile_counts;
   fa.returns_tracking = f.returns_tracking; fa.misses_tracking = f.misses_tracking;
   fa.n_first = f.n1; fa.n_returns_local = f.n_ret; fa.n_returns = f.n2; fa.n_misses = f.n3; fa.last_index = f.last_index;
-  fa.current_pose = f.current_pose; fa.back_pose = f.back_pose; fa.error_flag = f.error_flag;
+  fa.current_pose = f.current_pose; fa.back_pose = f.back_pose; fa.pose_table = f.pose_table; fa.error_flag = f.error_flag;
   return fa;
 }
 
@@ -1054,9 +1059,11 @@ int frontend_upload_small(dl_context* ctx, const dl_frontend_options& o, const F
   return DL_OK;
 }
 
-// host_ranges != nullptr: the scans are still on the host; they are uploaded on the copy stream in chunks while the
-// first-filter kernel of the previous chunk runs (the raw scans are read exactly once, by that kernel and by the
-// survivors' row reads that follow).
+// The batch is processed as `chunks` sub-batches that alternate between two streams, so that
+//   - with host scans (host_ranges != nullptr) the upload of sub-batch k+1 (copy stream) overlaps the kernels of k;
+//   - the latency-bound tail of sub-batch k (adaptive filter: 2 CTAs per scan, LM solve: 1 CTA per scan) overlaps the
+//     bandwidth-bound front half of sub-batch k+1.
+// Every kernel launcher enqueues on ctx->stream, which is pointed at the sub-batch's stream while it is enqueued.
 int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, float* d_ranges, int64_t in_cap,
                  const void* const* host_ranges, const int64_t* sizes, const float* origins, int num_origins,
                  const double* prev_poses, const double* cur_poses, const double* submap_local_pose, const dl_grid* hi,
@@ -1067,80 +1074,100 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
   DL_TRY(frontend_upload_small(ctx, o, f, sizes, origins, num_origins, prev_poses, cur_poses, hi, lo));
   const FrontendArgs fa = make_frontend_args(o, f, d_ranges, in_cap, rf);
   DL_TRY(launch_fe_prepare(ctx, fa, f.batch));
-  {
-    StageScope st(ctx, "voxel_filter_first");
-    if (host_ranges) {
-      // the upload target may still be in use by kernels of an earlier (asynchronous) call on this context
-      cudaEvent_t idle = ctx->take_event();
-      DL_CUDA(ctx, cudaEventRecord(idle, ctx->stream));
-      DL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, idle, 0));
-      ctx->event_pool.push_back(idle);
-      const int chunk = 8;
-      for (int c0 = 0; c0 < f.batch; c0 += chunk) {
-        const int c1 = std::min(f.batch, c0 + chunk);
-        for (int b = c0; b < c1; ++b)
-          if (sizes[b] > 0)
-            DL_CUDA(ctx, cudaMemcpyAsync(d_ranges + (size_t)b * in_cap * rf, host_ranges[b], (size_t)sizes[b] * rf * 4,
-                                         cudaMemcpyHostToDevice, ctx->copy_stream));
-        cudaEvent_t ev = ctx->take_event();
-        DL_CUDA(ctx, cudaEventRecord(ev, ctx->copy_stream));
-        DL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev, 0));
-        ctx->event_pool.push_back(ev);  // safe to recycle: the wait has been enqueued
-        DL_TRY(launch_fe_first_filter(ctx, fa, c0, c1 - c0));
-      }
-    } else {
-      DL_TRY(launch_fe_first_filter(ctx, fa, 0, f.batch));
-    }
-  }
-  {
-    StageScope st(ctx, "ingest_second_filter");
-    DL_TRY(launch_fe_rest(ctx, fa, f.batch));
-  }
-  // adaptive voxel filters (high, low resolution) on the tracking-frame returns: one CTA per (scan, filter)
-  {
-    StageScope st(ctx, "adaptive_voxel_filter");
-    DL_TRY(launch_adaptive_voxel_filter(ctx, f.returns_tracking, 3, f.cap, f.n2, f.batch, f.filters, 2, f.tableA, f.tcap,
-                                        f.scratchA, f.keepA, f.countsA, f.passesA, f.npassesA, f.croppedA));
-  }
-  DL_TRY(launch_gather_rows(ctx, f.returns_tracking, f.cap, 2, f.keepA, f.countsA, f.cap, f.clouds, 2 * f.batch));
   const Rigidd submap = pose_from7(submap_local_pose);
-  DL_TRY(launch_initial_pose(ctx, f.batch, f.current_pose, inverse(submap), f.initial_pose, f.target));
+  const bool rtcsm = o.use_online_correlative_scan_matching != 0;
+  int chunks = rtcsm ? 1 : (host_ranges ? 4 : 2);
+  if (const char* env = std::getenv(host_ranges ? "DLIOM_CHUNKS_HOST" : "DLIOM_CHUNKS_DEV")) chunks = rtcsm ? 1 : std::max(1, std::atoi(env));
+  if (f.batch < 8 * chunks) chunks = std::max(1, f.batch / 8);
+  cudaStream_t main_stream = ctx->stream;
+  cudaEvent_t prepared = ctx->take_event();
+  DL_CUDA(ctx, cudaEventRecord(prepared, main_stream));
+  DL_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, prepared, 0));
+  if (host_ranges) DL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, prepared, 0));  // the upload target may be in use
+  ctx->event_pool.push_back(prepared);
+  std::vector<float> rtcsm_scores;
   bool have_scores = false;
-  if (o.use_online_correlative_scan_matching) {
-    // The angular window depends on the farthest point of each cloud through acosf, which must be the host's to
-    // stay bit-exact, so this optional stage synchronises once per scan.
-    std::vector<int32_t> countsA(2 * f.batch);
-    std::vector<double> init(7 * f.batch);
-    DL_TRY(d2h(ctx, countsA.data(), f.countsA, 2 * f.batch));
-    DL_TRY(d2h(ctx, init.data(), f.initial_pose, 7 * f.batch));
-    DL_TRY(sync(ctx));
-    std::vector<float> scores(f.batch, 0.f);
-    StageScope st(ctx, "rtcsm");
-    const size_t mark = a.off;
-    for (int b = 0; b < f.batch; ++b) {
-      if (countsA[2 * b] <= 0) continue;
-      a.off = mark;
-      Rigidd best;
-      DL_TRY(rtcsm_device(ctx, o.real_time_correlative_scan_matcher, pose_from7(init.data() + 7 * b),
-                          f.clouds + (size_t)(2 * b) * f.cap * 3, countsA[2 * b], hi, a, &best, &scores[b], nullptr, nullptr));
-      pose_to7(best, init.data() + 7 * b);
-    }
-    DL_TRY(h2d(ctx, f.initial_pose, init.data(), 7 * f.batch));
-    DL_TRY(h2d(ctx, f.rtcsm_scores, scores.data(), f.batch));
-    DL_TRY(sync(ctx));
-    have_scores = true;
+  int status = DL_OK;
+  for (int k = 0; k < chunks && status == DL_OK; ++k) {
+    const int b0 = (int)((int64_t)f.batch * k / chunks), b1 = (int)((int64_t)f.batch * (k + 1) / chunks), nb = b1 - b0;
+    if (nb <= 0) continue;
+    ctx->stream = (k & 1) ? ctx->aux_stream : main_stream;
+    auto run = [&]() -> int {
+      {
+        StageScope st(ctx, "voxel_filter_first");
+        if (host_ranges) {
+          for (int b = b0; b < b1; ++b)
+            if (sizes[b] > 0)
+              DL_CUDA(ctx, cudaMemcpyAsync(d_ranges + (size_t)b * in_cap * rf, host_ranges[b], (size_t)sizes[b] * rf * 4,
+                                           cudaMemcpyHostToDevice, ctx->copy_stream));
+          cudaEvent_t ev = ctx->take_event();
+          DL_CUDA(ctx, cudaEventRecord(ev, ctx->copy_stream));
+          DL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev, 0));
+          ctx->event_pool.push_back(ev);  // safe to recycle: the wait has been enqueued
+        }
+        DL_TRY(launch_fe_first_filter(ctx, fa, b0, nb));
+      }
+      {
+        StageScope st(ctx, "ingest_second_filter");
+        DL_TRY(launch_fe_rest(ctx, fa, b0, nb));
+      }
+      {
+        // adaptive voxel filters (high, low resolution) on the tracking-frame returns: one CTA per (scan, filter)
+        StageScope st(ctx, "adaptive_voxel_filter");
+        DL_TRY(launch_adaptive_voxel_filter(ctx, f.returns_tracking + (size_t)b0 * f.cap * 3, 3, f.cap, f.n2 + b0, nb, f.filters, 2,
+                                            f.tableA + (size_t)2 * b0 * f.tcap, f.tcap, f.scratchA + (size_t)4 * b0 * f.cap,
+                                            f.keepA + (size_t)2 * b0 * f.cap, f.countsA + 2 * b0, f.passesA + 64 * b0,
+                                            f.npassesA + 2 * b0, f.croppedA + 2 * b0));
+      }
+      DL_TRY(launch_gather_rows(ctx, f.returns_tracking + (size_t)b0 * f.cap * 3, f.cap, 2, f.keepA + (size_t)2 * b0 * f.cap,
+                                f.countsA + 2 * b0, f.cap, f.clouds + (size_t)2 * b0 * f.cap * 3, 2 * nb));
+      DL_TRY(launch_initial_pose(ctx, nb, f.current_pose + 7 * b0, inverse(submap), f.initial_pose + 7 * b0, f.target + 3 * b0));
+      if (rtcsm) {
+        // The angular window depends on the farthest point of each cloud through acosf, which must be the host's to
+        // stay bit-exact, so this optional stage synchronises once per scan (and runs unpipelined).
+        std::vector<int32_t> countsA(2 * f.batch);
+        std::vector<double> init(7 * f.batch);
+        DL_TRY(d2h(ctx, countsA.data(), f.countsA, 2 * f.batch));
+        DL_TRY(d2h(ctx, init.data(), f.initial_pose, 7 * f.batch));
+        DL_TRY(sync(ctx));
+        rtcsm_scores.assign(f.batch, 0.f);
+        StageScope st(ctx, "rtcsm");
+        const size_t mark = a.off;
+        for (int b = 0; b < f.batch; ++b) {
+          if (countsA[2 * b] <= 0) continue;
+          a.off = mark;
+          Rigidd best;
+          DL_TRY(rtcsm_device(ctx, o.real_time_correlative_scan_matcher, pose_from7(init.data() + 7 * b),
+                              f.clouds + (size_t)(2 * b) * f.cap * 3, countsA[2 * b], hi, a, &best, &rtcsm_scores[b], nullptr, nullptr));
+          pose_to7(best, init.data() + 7 * b);
+        }
+        DL_TRY(h2d(ctx, f.initial_pose, init.data(), 7 * f.batch));
+        DL_TRY(h2d(ctx, f.rtcsm_scores, rtcsm_scores.data(), f.batch));
+        DL_TRY(sync(ctx));
+        have_scores = true;
+      }
+      {
+        StageScope st(ctx, "nls_solve");
+        DL_TRY(launch_nls(ctx, to_nls_options(o.ceres_scan_matcher, 2), f.problems + b0, nb, f.nls_out + b0));
+      }
+      ResultArgs ra{};
+      ra.batch = nb; ra.first_counts = f.n1 + b0; ra.return_counts = f.n2 + b0; ra.miss_counts = f.n3 + b0;
+      ra.adaptive_counts = f.countsA + 2 * b0; ra.adaptive_cropped = f.croppedA + 2 * b0; ra.adaptive_passes = f.npassesA + 2 * b0;
+      ra.rtcsm_scores = have_scores ? f.rtcsm_scores + b0 : nullptr; ra.nls = f.nls_out + b0; ra.submap = submap;
+      ra.results = d_results + b0; ra.error_flag = f.error_flag;
+      DL_TRY(launch_finalize_results(ctx, ra));
+      return DL_OK;
+    };
+    status = run();
   }
-  {
-    StageScope st(ctx, "nls_solve");
-    DL_TRY(launch_nls(ctx, to_nls_options(o.ceres_scan_matcher, 2), f.problems, f.batch, f.nls_out));
+  ctx->stream = main_stream;
+  if (chunks > 1) {  // later work on the main stream (result copies, the next call) waits for the auxiliary stream
+    cudaEvent_t joined = ctx->take_event();
+    DL_CUDA(ctx, cudaEventRecord(joined, ctx->aux_stream));
+    DL_CUDA(ctx, cudaStreamWaitEvent(main_stream, joined, 0));
+    ctx->event_pool.push_back(joined);
   }
-  ResultArgs ra{};
-  ra.batch = f.batch; ra.first_counts = f.n1; ra.return_counts = f.n2; ra.miss_counts = f.n3; ra.adaptive_counts = f.countsA;
-  ra.adaptive_cropped = f.croppedA; ra.adaptive_passes = f.npassesA;
-  ra.rtcsm_scores = have_scores ? f.rtcsm_scores : nullptr; ra.nls = f.nls_out; ra.submap = submap; ra.results = d_results;
-  ra.error_flag = f.error_flag;
-  DL_TRY(launch_finalize_results(ctx, ra));
-  return DL_OK;
+  return status;
 }
 
 int check_frontend(dl_context* ctx, const dl_frontend_options* o, int num_scans, const int64_t* sizes,
@@ -1248,7 +1275,7 @@ int dl_ingest_scan(dl_context* ctx, const dl_frontend_options* options, const vo
   const FrontendArgs fa = make_frontend_args(*options, f, d_ranges, n, 8);
   DL_TRY(launch_fe_prepare(ctx, fa, 1));
   DL_TRY(launch_fe_first_filter(ctx, fa, 0, 1));
-  DL_TRY(launch_fe_rest(ctx, fa, 1));
+  DL_TRY(launch_fe_rest(ctx, fa, 0, 1));
   int32_t c[4];
   DL_TRY(d2h(ctx, &c[0], f.n1, 1));
   DL_TRY(d2h(ctx, &c[1], f.n_ret, 1));

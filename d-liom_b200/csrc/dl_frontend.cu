@@ -45,8 +45,8 @@ __device__ __forceinline__ Vec3f load_xyz(const float* __restrict__ rows, int ro
 }
 
 // ---------------------------------------------------------------------------------------------------- A
-__global__ void __launch_bounds__(kBlock) fe_first_filter_insert(FrontendArgs a, int first_scan) {
-  const int b = first_scan + blockIdx.y;
+__global__ void __launch_bounds__(kBlock) fe_first_filter_insert(FrontendArgs a) {
+  const int b = a.first_scan + blockIdx.y;
   const int n = a.counts[b];
   const float* rows = a.ranges + (size_t)b * a.in_cap * a.row_floats;
   uint32_t* tab = a.table1 + (size_t)b * a.tcap1;
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kBlock) fe_first_filter_insert(FrontendArgs a,
       if (prev == kEmpty32) break;
       const Int3 o = cell_index(load_xyz(rows, a.row_floats, prev), res);
       if (o.x == c.x && o.y == c.y && o.z == c.z) {
-        atomicMin(tab + h, (uint32_t)i);
+        if ((uint32_t)i < prev) atomicMin(tab + h, (uint32_t)i);  // the owner only ever decreases
         break;
       }
       h = (h + 1) & mask;
@@ -152,7 +152,7 @@ __device__ __forceinline__ int ingest_survivor(const FrontendArgs& a, int b, con
 // it 32 at a time with all lanes busy.
 __global__ void __launch_bounds__(kBlock) fe_ingest_second_insert(FrontendArgs a) {
   __shared__ int queue[kBlock / 32][64];
-  const int b = blockIdx.y;
+  const int b = a.first_scan + blockIdx.y;
   const int n = a.counts[b];
   const int rf = a.row_floats;
   const float* rows = a.ranges + (size_t)b * a.in_cap * rf;
@@ -239,7 +239,7 @@ __device__ __forceinline__ int second_filter_class(const FrontendArgs& a, int b,
 
 // The second filter's survivors are the min-index entries of its non-empty slots: stream the table once.
 __global__ void __launch_bounds__(kBlock) fe_mark_winners(FrontendArgs a) {
-  const int b = blockIdx.y;
+  const int b = a.first_scan + blockIdx.y;
   if (a.counts[b] == 0) return;
   const uint32_t* mins = a.min2 + (size_t)b * a.tcap2;
   uint8_t* win = a.win + (size_t)b * a.cap;
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kBlock) fe_mark_winners(FrontendArgs a) {
 }
 
 __global__ void __launch_bounds__(kBlock) fe_count_tiles(FrontendArgs a) {
-  const int b = blockIdx.y;
+  const int b = a.first_scan + blockIdx.y;
   const int n = a.counts[b];
   if ((int)blockIdx.x * kBlock >= n) {
     if (threadIdx.x == 0) {
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kBlock) fe_count_tiles(FrontendArgs a) {
 
 // Exclusive prefix of the tile counts of one scan (one CTA per scan), in place; totals go to n_returns / n_misses.
 __global__ void __launch_bounds__(kBlock) fe_tile_prefix(FrontendArgs a) {
-  const int b = blockIdx.x;
+  const int b = a.first_scan + blockIdx.x;
   const int n = a.counts[b];
   const int my_tiles = (n + kBlock - 1) / kBlock;
   int32_t* tc = a.tile_counts + (size_t)b * a.tiles * 2;
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(kBlock) fe_tile_prefix(FrontendArgs a) {
 }
 
 __global__ void __launch_bounds__(kBlock) fe_scatter_tracking(FrontendArgs a) {
-  const int b = blockIdx.y;
+  const int b = a.first_scan + blockIdx.y;
   const int n = a.counts[b];
   if ((int)blockIdx.x * kBlock >= n) return;
   const int i = blockIdx.x * kBlock + threadIdx.x;
@@ -329,8 +329,8 @@ __global__ void __launch_bounds__(kBlock) fe_scatter_tracking(FrontendArgs a) {
 
 // current_pose = pose of the LAST first-filter survivor (hits_poses.back(), LTB:476) and its inverse, once per scan.
 __global__ void fe_current_pose(FrontendArgs a, int batch) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= batch) return;
+  const int b = a.first_scan + blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.first_scan + batch) return;
   const int rf = a.row_floats;
   const float* rows = a.ranges + (size_t)b * a.in_cap * rf;
   const int last = a.last_index[b];
@@ -364,6 +364,8 @@ __global__ void fe_reset_counters(FrontendArgs a, int batch) {
 
 }  // namespace
 
+size_t fe_pose_table_bytes(int) { return 256; }  // (a per-time pose cache was tried and measured slower: see DESIGN.md)
+
 int launch_fe_prepare(dl_context* ctx, const FrontendArgs& a, int batch) {
   DL_CUDA(ctx, cudaMemsetAsync(a.table1, 0xFF, (size_t)batch * a.tcap1 * sizeof(uint32_t), ctx->stream));
   DL_CUDA(ctx, cudaMemsetAsync(a.keys2, 0xFF, (size_t)batch * a.tcap2 * sizeof(unsigned long long), ctx->stream));
@@ -376,16 +378,18 @@ int launch_fe_prepare(dl_context* ctx, const FrontendArgs& a, int batch) {
 }
 
 // Kernel A for scans [first_scan, first_scan + num_scans): lets the host overlap the upload of later scans.
-int launch_fe_first_filter(dl_context* ctx, const FrontendArgs& a, int first_scan, int num_scans) {
+int launch_fe_first_filter(dl_context* ctx, FrontendArgs a, int first_scan, int num_scans) {
   if (num_scans <= 0) return DL_OK;
+  a.first_scan = first_scan;
   const int tiles = (int)std::min<int64_t>((a.cap + kBlock - 1) / kBlock, 128);
-  fe_first_filter_insert<<<dim3(tiles, num_scans), kBlock, 0, ctx->stream>>>(a, first_scan);
+  fe_first_filter_insert<<<dim3(tiles, num_scans), kBlock, 0, ctx->stream>>>(a);
   DL_LAUNCH_CHECK(ctx, "fe_first_filter_insert");
   return DL_OK;
 }
 
-int launch_fe_rest(dl_context* ctx, const FrontendArgs& a, int batch) {
+int launch_fe_rest(dl_context* ctx, FrontendArgs a, int first_scan, int batch) {
   if (batch <= 0) return DL_OK;
+  a.first_scan = first_scan;
   const int tiles = (int)std::min<int64_t>((a.cap + kBlock - 1) / kBlock, 128);
   fe_ingest_second_insert<<<dim3(20, batch), kBlock, 0, ctx->stream>>>(a);  // ~400 survivors per warp: the queue drains full
   DL_LAUNCH_CHECK(ctx, "fe_ingest_second_insert");

@@ -46,7 +46,8 @@ __device__ __forceinline__ uint16_t grid_value(const GridView& g, int x, int y, 
 struct dl_context {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaStream_t copy_stream = nullptr;   // uploads of host scans, overlapped with the first-filter kernels
+  cudaStream_t copy_stream = nullptr;   // uploads of host scans, overlapped with the kernels of the previous sub-batch
+  cudaStream_t aux_stream = nullptr;    // odd sub-batches of the front end (see frontend_run)
   cudaEvent_t staging_done = nullptr;   // the pinned staging block of the previous call has been consumed
   std::string error;
   int64_t launches = 0;

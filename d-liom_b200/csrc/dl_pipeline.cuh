@@ -39,6 +39,7 @@ struct FrontendArgs {
   const float* ranges;   // scan b starts at row b * in_cap; rows of row_floats floats (4: x y z t, 8: + u64 origin index)
   int64_t in_cap;
   int row_floats;
+  int first_scan;        // kernels handle scans [first_scan, first_scan + gridDim.y): lets sub-batches pipeline
   const int32_t* counts;
   const ScanConstants* scans;
   const float* origins;
@@ -61,11 +62,13 @@ struct FrontendArgs {
   int32_t *n_first, *n_returns_local, *n_returns, *n_misses, *last_index;
   float* current_pose;
   float* back_pose;              // inverse of current_pose, 7 floats per scan
+  void* pose_table;              // per scan: hash table time -> pose (dl_frontend.cu)
   int32_t* error_flag;
 };
+size_t fe_pose_table_bytes(int batch);
 int launch_fe_prepare(dl_context* ctx, const FrontendArgs& a, int batch);
-int launch_fe_first_filter(dl_context* ctx, const FrontendArgs& a, int first_scan, int num_scans);
-int launch_fe_rest(dl_context* ctx, const FrontendArgs& a, int batch);
+int launch_fe_first_filter(dl_context* ctx, FrontendArgs a, int first_scan, int num_scans);
+int launch_fe_rest(dl_context* ctx, FrontendArgs a, int first_scan, int batch);
 
 struct ResultArgs {
   int batch;
