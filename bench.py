@@ -14,7 +14,7 @@ voxel filters -> adaptive voxel filters -> Levenberg-Marquardt point-to-grid mat
 
 `--impl reference` times that CPU path alone (all host threads) and prints the same line with "impl": "reference".
 Multi-GPU: one process per GPU (torchrun), scans are independent -> sharded across ranks, no data-path collective,
-"scaling": "weak". Inputs per step exceed L2 (64 scans x 4.2 MB = 268 MB > 126 MB), so no explicit L2 flush.
+"scaling": "weak". Inputs per step exceed L2 (148 scans x 2.1 MB = 309 MB > 126 MB), so no explicit L2 flush.
 """
 import argparse
 import ctypes as C
@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="scans per step per GPU")
+    ap.add_argument("--batch", type=int, default=148, help="scans per step per GPU (default: one per SM)")
     ap.add_argument("--beams", type=int, default=64)
     ap.add_argument("--map-scans", type=int, default=40)
     ap.add_argument("--distinct-scans", type=int, default=16)

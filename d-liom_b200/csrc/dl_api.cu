@@ -901,6 +901,7 @@ struct FrontendBuffers {
   int32_t *last_index, *error_flag;
   float* back_pose;
   uint8_t* win;
+  float* local4;
   void* pose_table;
   ScanConstants* scans;
   AdaptiveParams* filters;
@@ -919,7 +920,7 @@ size_t frontend_bytes(int batch, int64_t cap, int num_origins, size_t extra) {
                       B * C * 12, B * C * 12, B * C * 12, B * C * 12, B * C * 12, B * 2 * C * 12, B * 28, (size_t)num_origins * 12,
                       B * 2 * 32 * 4, B * 4, B * C, B * sizeof(ScanConstants), 2 * sizeof(AdaptiveParams), B * 56, B * 24,
                       B * sizeof(NlsProblem), B * sizeof(NlsOutput),
-                      B * (size_t)next_pow2(cap) * 8, B * (size_t)next_pow2(cap) * 4, B * C * 4, B * 4, 64, B * 28, B * C, fe_pose_table_bytes(batch)}) + extra + 8192;
+                      B * (size_t)next_pow2(cap) * 8, B * (size_t)next_pow2(cap) * 4, B * C * 4, B * 4, 64, B * 28, B * C, fe_pose_table_bytes(batch), B * C * 16}) + extra + 8192;
 }
 
 void carve(Arena& a, int batch, int64_t cap, int num_origins, FrontendBuffers* f) {
@@ -949,6 +950,7 @@ void carve(Arena& a, int batch, int64_t cap, int num_origins, FrontendBuffers* f
   f->slot2 = a.take<uint32_t>(B * C); f->last_index = a.take<int32_t>(B); f->error_flag = a.take<int32_t>(1);
   f->back_pose = a.take<float>(B * 7);
   f->win = a.take<uint8_t>(B * C);
+  f->local4 = a.take<float>(B * C * 4);
   f->pose_table = a.take<char>(fe_pose_table_bytes(batch));
 }
 
@@ -961,7 +963,7 @@ FrontendArgs make_frontend_args(const dl_frontend_options& o, const FrontendBuff
   fa.second_resolution = o.voxel_filter_size;        // LTB:479-484
   fa.min_range = o.min_range; fa.max_range = o.max_range; fa.scan_period = o.scan_period;
   fa.table1 = f.table; fa.slot1 = f.slot; fa.keys2 = f.keys2; fa.min2 = f.min2; fa.slot2 = f.slot2;
-  fa.local = f.tmp_points; fa.cls = f.cls; fa.win = f.win; fa.tile_counts = f.tile_counts;
+  fa.local = f.local4; fa.win = f.win; fa.tile_counts = f.tile_counts;
   fa.returns_tracking = f.returns_tracking; fa.misses_tracking = f.misses_tracking;
   fa.n_first = f.n1; fa.n_returns_local = f.n_ret; fa.n_returns = f.n2; fa.n_misses = f.n3; fa.last_index = f.last_index;
   fa.current_pose = f.current_pose; fa.back_pose = f.back_pose; fa.pose_table = f.pose_table; fa.error_flag = f.error_flag;

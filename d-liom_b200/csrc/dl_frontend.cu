@@ -123,8 +123,8 @@ __device__ __forceinline__ int ingest_survivor(const FrontendArgs& a, int b, con
     }
   }
   if (cls) {
-    float* l = a.local + ((size_t)b * a.cap + i) * 3;
-    l[0] = outp.x; l[1] = outp.y; l[2] = outp.z;
+    // one aligned 16-byte record per survivor: local-frame point + class (1 return, 2 miss) in .w
+    ((float4*)a.local)[(size_t)b * a.cap + i] = make_float4(outp.x, outp.y, outp.z, __int_as_float(cls));
     const Int3 c = cell_index(outp, make_divider(a.second_resolution));
     unsigned long long key;
     if (!pack_key(c, cls == 2, &key)) {
@@ -143,7 +143,6 @@ __device__ __forceinline__ int ingest_survivor(const FrontendArgs& a, int b, con
       }
     }
   }
-  a.cls[(size_t)b * a.cap + i] = (uint8_t)cls;
   return cls;
 }
 
@@ -230,11 +229,11 @@ __device__ __forceinline__ int block_exclusive_scan(int value, int* total) {
   return base + inc - value;
 }
 
-// cls[i] is 1/2 for gated first-filter survivors; win[i] is set by fe_mark_winners for the points that own their
-// second-filter voxel. A point is output iff both hold.
+// win[i] is set by fe_mark_winners for the points that own their second-filter voxel; their class (1 return,
+// 2 miss) sits next to the local-frame point in local[i].w.
 __device__ __forceinline__ int second_filter_class(const FrontendArgs& a, int b, int i, int n) {
   if (i >= n) return 0;
-  return a.win[(size_t)b * a.cap + i] ? a.cls[(size_t)b * a.cap + i] : 0;
+  return a.win[(size_t)b * a.cap + i] ? __float_as_int(a.local[((size_t)b * a.cap + i) * 4 + 3]) : 0;
 }
 
 // The second filter's survivors are the min-index entries of its non-empty slots: stream the table once.
@@ -321,8 +320,8 @@ __global__ void __launch_bounds__(kBlock) fe_scatter_tracking(FrontendArgs a) {
   off += __popc((cls == 1 ? br : bm) & lane_mask);
   const float* bp = a.back_pose + 7 * b;
   const Rigidf back{{bp[0], bp[1], bp[2]}, {bp[3], bp[4], bp[5], bp[6]}};
-  const float* l = a.local + ((size_t)b * a.cap + i) * 3;
-  const Vec3f q = apply(back, Vec3f{l[0], l[1], l[2]});
+  const float4 l = ((const float4*)a.local)[(size_t)b * a.cap + i];
+  const Vec3f q = apply(back, Vec3f{l.x, l.y, l.z});
   float* dst = (cls == 1 ? a.returns_tracking : a.misses_tracking) + ((size_t)b * a.cap + off) * 3;
   dst[0] = q.x; dst[1] = q.y; dst[2] = q.z;
 }
@@ -370,7 +369,6 @@ int launch_fe_prepare(dl_context* ctx, const FrontendArgs& a, int batch) {
   DL_CUDA(ctx, cudaMemsetAsync(a.table1, 0xFF, (size_t)batch * a.tcap1 * sizeof(uint32_t), ctx->stream));
   DL_CUDA(ctx, cudaMemsetAsync(a.keys2, 0xFF, (size_t)batch * a.tcap2 * sizeof(unsigned long long), ctx->stream));
   DL_CUDA(ctx, cudaMemsetAsync(a.min2, 0xFF, (size_t)batch * a.tcap2 * sizeof(uint32_t), ctx->stream));
-  DL_CUDA(ctx, cudaMemsetAsync(a.cls, 0, (size_t)batch * a.cap, ctx->stream));
   DL_CUDA(ctx, cudaMemsetAsync(a.win, 0, (size_t)batch * a.cap, ctx->stream));
   fe_reset_counters<<<(batch + 127) / 128, 128, 0, ctx->stream>>>(a, batch);
   DL_LAUNCH_CHECK(ctx, "fe_reset_counters");

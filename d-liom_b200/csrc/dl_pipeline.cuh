@@ -53,8 +53,7 @@ struct FrontendArgs {
   unsigned long long* keys2;     // second filter: slot -> packed voxel key (bit 63 = miss)
   uint32_t* min2;
   uint32_t* slot2;
-  float* local;                  // local-frame point of every first-filter survivor, indexed by input row
-  uint8_t* cls;                  // 0 dropped, 1 return, 2 miss
+  float* local;                  // float4 per input row: local-frame point of a first-filter survivor + class in .w
   uint8_t* win;                  // 1 = owns its second-filter voxel
   int32_t* tile_counts;
   float* returns_tracking;
