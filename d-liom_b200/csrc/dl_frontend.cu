@@ -17,6 +17,8 @@
 //
 // Algorithmic traffic per raw point: A reads 16 B; B reads 4 B slot + 4 B owner (+16 B row, writes 13 B for
 // survivors); C reads 1 B class (+ survivors' 12 B, writes 12 B per output point).
+#include <cstdlib>
+
 #include "dl_internal.cuh"
 #include "dl_pipeline.cuh"
 
@@ -389,7 +391,9 @@ int launch_fe_rest(dl_context* ctx, FrontendArgs a, int first_scan, int batch) {
   if (batch <= 0) return DL_OK;
   a.first_scan = first_scan;
   const int tiles = (int)std::min<int64_t>((a.cap + kBlock - 1) / kBlock, 128);
-  fe_ingest_second_insert<<<dim3(20, batch), kBlock, 0, ctx->stream>>>(a);  // ~400 survivors per warp: the queue drains full
+  int per_scan = 48;  // measured best of {8, 20, 32, 48, 64}: enough CTAs in flight to hide the random-access latency
+  if (const char* env = std::getenv("DLIOM_INGEST_GRID")) per_scan = std::max(1, std::atoi(env));
+  fe_ingest_second_insert<<<dim3(per_scan, batch), kBlock, 0, ctx->stream>>>(a);
   DL_LAUNCH_CHECK(ctx, "fe_ingest_second_insert");
   fe_mark_winners<<<dim3(tiles, batch), kBlock, 0, ctx->stream>>>(a);
   DL_LAUNCH_CHECK(ctx, "fe_mark_winners");
