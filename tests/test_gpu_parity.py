@@ -318,3 +318,58 @@ def test_frontend_batch_matches_oracle(ctx, orc, use_rtcsm):
         # sanity against the synthetic ground truth (the reference's prior weights keep the solve near its start)
         dt, dr = pose_error(np.array(r.pose_estimate_local), w["truth"][s])
         assert dt < 0.2 and dr < 0.02, (s, dt, dr)
+
+
+# ---------------------------------------------------------------- BASELINE.json configs[2] and configs[3] as parity cases
+def test_config2_128_beam_fine_grid_correlative_then_ceres(ctx, orc):
+    """configs[2]: 128-beam (~260k points) scan, 0.05 m HybridGrid, correlative + Ceres refine — the whole front end
+    with use_online_correlative_scan_matching on, against the oracle (456 533 candidates: 7^3 x 11^3)."""
+    import dliom
+    w = workload(beams=128, num_map_scans=6, num_scans=1, hi_res=0.05)
+    opts = orc.FrontEndOptions.defaults(use_rtcsm=1)
+    fo = dliom.FrontendOptions.from_oracle(opts)
+    hi, lo = dev_grid(ctx, w["hi"]), dev_grid(ctx, w["lo"])
+    assert len(w["scans"][0]) > 250000
+    r = ctx.frontend_match_batch(fo, w["scans"], w["origin"], w["prev"], w["cur"], w["submap_pose"], hi, lo)[0]
+    ing = orc.ingest_scan(opts, w["scans"][0], w["origin"], w["prev"][0], w["cur"][0])
+    want = orc.match_scan(opts, ing["returns_tracking"], ing["current_pose"].astype(np.float64), w["submap_pose"],
+                          w["hi"], w["lo"])
+    assert (r.num_first_filter, r.num_returns) == (len(ing["first_keep"]), len(ing["returns_tracking"]))
+    assert (r.num_high_resolution, r.num_low_resolution) == (len(want["hi_keep"]), len(want["lo_keep"]))
+    assert np.float32(r.rtcsm_score) == np.float32(want["rtcsm_score"])      # correlative stage: bit-exact
+    dt, dr = pose_error(np.array(r.pose_estimate_local), want["pose_estimate_local"])
+    assert r.ok == 1 and dt < 1e-7 and dr < 1e-8
+
+
+def test_config3_many_submaps_in_one_batch(ctx, orc):
+    """configs[3] shape: one scan registered against MANY active submaps in a single launch (what ConstraintBuilder3D
+    farms out to its thread pool): 8 different (hi, lo) grid pairs, one problem each, checked against the oracle."""
+    w = workload()
+    ing = orc.ingest_scan(w["opts"], w["scans"][0], w["origin"], w["prev"][0], w["cur"][0])
+    pts = ing["returns_tracking"]
+    hk, _ = orc.adaptive_voxel_filter(pts, 2.0, 150, 15.0)
+    lk, _ = orc.adaptive_voxel_filter(pts, 4.0, 200, 60.0)
+    rng = np.random.RandomState(8)
+    ogrids, dgrids, inits, targets = [], [], [], []
+    for k in range(8):   # submaps = the map grids shifted by whole voxels (different content per problem)
+        shift_hi, shift_lo = rng.randint(-3, 4, 3), rng.randint(-1, 2, 3)
+        pair = []
+        for src, res, sh in ((w["hi"], 0.1, shift_hi), (w["lo"], 0.45, shift_lo)):
+            g = orc.Grid(res)
+            xs, ys, zs, vs = src.export()
+            keep = rng.rand(len(xs)) < 0.8
+            for x, y, z, v in zip(xs[keep], ys[keep], zs[keep], vs[keep]):
+                g.set_value((x + sh[0], y + sh[1], z + sh[2]), v)
+            pair.append(g)
+        ogrids.append(pair)
+        dgrids.append([dev_grid(ctx, pair[0]), dev_grid(ctx, pair[1])])
+        init = w["cur"][0].copy()
+        init[:3] += shift_hi * 0.1
+        inits.append(init)
+        targets.append(init[:3].copy())
+    poses, sums = ctx.ceres_match_batch([[pts[hk], pts[lk]]] * 8, dgrids, [1.0, 6.0], 5.0, 4e2, np.array(targets), np.array(inits))
+    for k in range(8):
+        want, ws = orc.ceres_match([pts[hk], pts[lk]], ogrids[k], [1.0, 6.0], 5.0, 4e2, targets[k], inits[k])
+        dt, dr = pose_error(poses[k], want)
+        assert dt < 1e-7 and dr < 1e-8, k
+        assert sums[k]["num_iterations"] == ws["num_iterations"]
