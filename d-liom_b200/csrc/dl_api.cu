@@ -91,6 +91,23 @@ int ensure_capacity(dl_context* ctx, T** ptr, size_t* cap, size_t need) {
   return DL_OK;
 }
 
+// (Re)allocates a pool to at least `need` elements, preserving the first `used` elements and initialising the rest
+// with `fill` bytes: free node slots must read -1 and free brick slots 0 for the lock-free device-side growth.
+template <typename T>
+int realloc_pool(dl_context* ctx, T** ptr, size_t* cap, size_t need, size_t used, int fill) {
+  if (need <= *cap) return DL_OK;
+  const size_t want = std::max(need + need / 2 + 512, 2 * *cap);
+  T* fresh = nullptr;
+  DL_CUDA(ctx, cudaMalloc((void**)&fresh, want * sizeof(T)));
+  DL_CUDA(ctx, cudaMemsetAsync(fresh, fill, want * sizeof(T), ctx->stream));
+  if (*ptr && used) DL_CUDA(ctx, cudaMemcpyAsync(fresh, *ptr, used * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+  DL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (*ptr) DL_CUDA(ctx, cudaFree(*ptr));
+  *ptr = fresh;
+  *cap = want;
+  return DL_OK;
+}
+
 template <typename T>
 int d2h(dl_context* ctx, T* dst, const T* src, size_t count) {
   if (count == 0) return DL_OK;
@@ -237,12 +254,14 @@ void dl_grid_destroy(dl_grid* g) {
   cudaFree(g->d_top);
   cudaFree(g->d_nodes);
   cudaFree(g->d_bricks);
+  cudaFree(g->d_counters);
   delete g;
 }
 
 float dl_grid_resolution(const dl_grid* g) { return g ? g->resolution : 0.f; }
 int64_t dl_grid_num_bricks(const dl_grid* g) { return g ? (int64_t)(g->bricks.size() / 512) : 0; }
 
+static int grid_download(dl_grid* g);
 static inline size_t top_flat(int x, int y, int z, int bits) { return ((((size_t)z << bits) + y) << bits) + x; }
 
 // Grow(): double every axis, old content moves to the centre (hybrid_grid.h:389-407).
@@ -263,6 +282,10 @@ static int grid_grow(dl_grid* g) {
 int dl_grid_set_cells(dl_grid* g, int64_t n, const int32_t* xs, const int32_t* ys, const int32_t* zs,
                       const uint16_t* values) {
   if (!g || n < 0 || (n > 0 && (!xs || !ys || !zs || !values))) return DL_ERR_ARG;
+  if (g->mirror_stale) {
+    const int st = grid_download(g);
+    if (st != DL_OK) return st;
+  }
   for (int64_t i = 0; i < n; ++i) {
     for (;;) {
       const int gs = 64 << g->bits, half = gs >> 1;
@@ -292,16 +315,43 @@ int dl_grid_set_cells(dl_grid* g, int64_t n, const int32_t* xs, const int32_t* y
   return DL_OK;
 }
 
+// Host mirror <- device (after device-side insertion the device copy is ahead).
+static int grid_download(dl_grid* g) {
+  if (!g->mirror_stale) return DL_OK;
+  dl_context* ctx = g->ctx;
+  int32_t counters[2] = {0, 0};
+  DL_TRY(d2h(ctx, counters, g->d_counters, 2));
+  DL_TRY(sync(ctx));
+  g->top.resize((size_t)1 << (3 * g->bits));
+  g->nodes.resize((size_t)counters[0] * 512);
+  g->bricks.resize((size_t)counters[1] * 512);
+  g->brick_dirty.assign(counters[1], 0);
+  DL_TRY(d2h(ctx, g->top.data(), g->d_top, g->top.size()));
+  DL_TRY(d2h(ctx, g->nodes.data(), g->d_nodes, g->nodes.size()));
+  DL_TRY(d2h(ctx, g->bricks.data(), g->d_bricks, g->bricks.size()));
+  DL_TRY(sync(ctx));
+  g->mirror_stale = false;
+  g->structure_dirty = false;
+  return DL_OK;
+}
+
 int dl_grid_sync(dl_grid* g) {
   if (!g) return DL_ERR_ARG;
   dl_context* ctx = g->ctx;
   DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (g->mirror_stale) return ctx->fail(DL_ERR_ARG, "internal: host mirror is behind the device grid");
   const size_t nbricks = g->bricks.size() / 512;
+  if (!g->d_counters) DL_CUDA(ctx, cudaMalloc((void**)&g->d_counters, 4 * sizeof(int32_t)));
   if (g->structure_dirty) {
-    DL_TRY(ensure_capacity(ctx, &g->d_top, &g->d_top_cap, g->top.size()));
-    DL_TRY(ensure_capacity(ctx, &g->d_nodes, &g->d_nodes_cap, std::max<size_t>(g->nodes.size(), 1)));
+    if (g->top.size() > g->d_top_cap) {
+      if (g->d_top) { DL_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); DL_CUDA(ctx, cudaFree(g->d_top)); }
+      g->d_top = nullptr;
+      DL_CUDA(ctx, cudaMalloc((void**)&g->d_top, g->top.size() * sizeof(int32_t)));
+      g->d_top_cap = g->top.size();
+    }
+    DL_TRY(realloc_pool(ctx, &g->d_nodes, &g->d_nodes_cap, std::max<size_t>(g->nodes.size(), 512), 0, 0xFF));
     const size_t old_cap = g->d_bricks_cap;
-    DL_TRY(ensure_capacity(ctx, &g->d_bricks, &g->d_bricks_cap, std::max<size_t>(g->bricks.size(), 512)));
+    DL_TRY(realloc_pool(ctx, &g->d_bricks, &g->d_bricks_cap, std::max<size_t>(g->bricks.size(), 512), 0, 0));
     if (g->d_bricks_cap != old_cap) std::fill(g->brick_dirty.begin(), g->brick_dirty.end(), 1);  // reallocated
     DL_TRY(h2d(ctx, g->d_top, g->top.data(), g->top.size()));
     DL_TRY(h2d(ctx, g->d_nodes, g->nodes.data(), g->nodes.size()));
@@ -316,6 +366,8 @@ int dl_grid_sync(dl_grid* g) {
     DL_TRY(h2d(ctx, g->d_bricks + b * 512, g->bricks.data() + b * 512, (e - b) * 512));
     b = e;
   }
+  const int32_t counters[4] = {(int32_t)(g->nodes.size() / 512), (int32_t)nbricks, 0, 0};
+  DL_TRY(h2d(ctx, g->d_counters, counters, 4));
   return sync(ctx);
 }
 
@@ -345,6 +397,143 @@ int dl_grid_interpolate(dl_context* ctx, const dl_grid* g, int64_t n, const doub
   DL_TRY(launch_interpolate(ctx, g->view(), n, d_xyz, d_out));
   DL_TRY(d2h(ctx, out, d_out, 4 * n));
   return sync(ctx);
+}
+
+// ------------------------------------------------------------------------------------------------ grid write side
+}  // extern "C"
+
+namespace dl {
+int grid_ensure_device_state(dl_grid* g) {
+  if (g->mirror_stale) return DL_OK;  // the device copy is authoritative and complete
+  bool dirty = g->structure_dirty || !g->d_counters;
+  for (size_t b = 0; b < g->brick_dirty.size() && !dirty; ++b) dirty = g->brick_dirty[b] != 0;
+  return dirty ? dl_grid_sync(g) : DL_OK;
+}
+int grid_reserve_pools(dl_grid* g, size_t add_nodes, size_t add_bricks) {
+  dl_context* ctx = g->ctx;
+  int32_t counters[2] = {0, 0};
+  DL_TRY(d2h(ctx, counters, g->d_counters, 2));
+  DL_TRY(sync(ctx));
+  DL_TRY(realloc_pool(ctx, &g->d_nodes, &g->d_nodes_cap, ((size_t)counters[0] + add_nodes) * 512, (size_t)counters[0] * 512, 0xFF));
+  DL_TRY(realloc_pool(ctx, &g->d_bricks, &g->d_bricks_cap, ((size_t)counters[1] + add_bricks) * 512, (size_t)counters[1] * 512, 0));
+  return DL_OK;
+}
+}  // namespace dl
+
+namespace {
+struct InsertScratch {
+  uint16_t *hit_table, *miss_table;
+  int32_t* bbox;
+  uint32_t* update_list;
+};
+int prepare_insert(dl_context* ctx, Arena& a, const dl_range_data_inserter_options& o, int64_t n, InsertScratch* s) {
+  static thread_local std::vector<uint16_t> tables(65536);
+  static thread_local double cached_hit = -1, cached_miss = -1;
+  if (cached_hit != o.hit_probability || cached_miss != o.miss_probability) {
+    compute_odds_table((float)o.hit_probability, tables.data());           // Odds(options.hit_probability()) takes a float
+    compute_odds_table((float)o.miss_probability, tables.data() + 32768);
+    cached_hit = o.hit_probability;
+    cached_miss = o.miss_probability;
+  }
+  s->hit_table = a.take<uint16_t>(32768);
+  s->miss_table = a.take<uint16_t>(32768);
+  s->bbox = a.take<int32_t>(8);
+  s->update_list = a.take<uint32_t>((size_t)n * (size_t)(1 + std::max(o.num_free_space_voxels, 0)));
+  DL_TRY(h2d(ctx, s->hit_table, tables.data(), 32768));
+  DL_TRY(h2d(ctx, s->miss_table, tables.data() + 32768, 32768));
+  return DL_OK;
+}
+size_t insert_scratch_bytes(const dl_range_data_inserter_options& o, int64_t n) {
+  return arena_bytes({65536, 65536, 64, (size_t)n * (size_t)(1 + std::max(o.num_free_space_voxels, 0)) * 4});
+}
+int check_inserter(dl_context* ctx, const dl_range_data_inserter_options* o) {
+  if (!o) return DL_ERR_ARG;
+  if (!(o->hit_probability > 0.5) || !(o->miss_probability < 0.5) || o->num_free_space_voxels < 0)
+    return ctx->fail(DL_ERR_ARG, "hit_probability must be > 0.5 and miss_probability < 0.5 (CHECK_GT / CHECK_LT)");
+  return DL_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int dl_grid_insert_range_data(dl_context* ctx, dl_grid* grid, const dl_range_data_inserter_options* options,
+                              const float* origin, const float* returns, int64_t n) {
+  if (!ctx || !grid || !origin || n < 0 || n > 0x3fffffff || (n > 0 && !returns)) return DL_ERR_ARG;  // CHECK_NOTNULL(hybrid_grid)
+  DL_TRY(check_inserter(ctx, options));
+  if (n == 0) return DL_OK;
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  DL_TRY(ctx->reserve_device(arena_bytes({(size_t)n * 12}) + insert_scratch_bytes(*options, n)));
+  Arena a(ctx->d_scratch);
+  float* d_returns = a.take<float>(3 * n);
+  DL_TRY(h2d(ctx, d_returns, returns, 3 * n));
+  InsertScratch s;
+  DL_TRY(prepare_insert(ctx, a, *options, n, &s));
+  DL_TRY(grid_insert_device(ctx, grid, Vec3f{origin[0], origin[1], origin[2]}, d_returns, (int)n,
+                            options->num_free_space_voxels, s.hit_table, s.miss_table, s.bbox, s.update_list));
+  return sync(ctx);
+}
+
+int dl_submap_insert_range_data(dl_context* ctx, dl_grid* hi, dl_grid* lo, const dl_range_data_inserter_options* options,
+                                const double* submap_local_pose, int32_t high_resolution_max_range, const float* origin,
+                                const float* returns, int64_t n) {
+  if (!ctx || !hi || !lo || !submap_local_pose || !origin || n < 0 || n > 0x3fffffff || (n > 0 && !returns)) return DL_ERR_ARG;
+  DL_TRY(check_inserter(ctx, options));
+  if (n == 0) return DL_OK;
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t tiles = (size_t)(n + 255) / 256;
+  DL_TRY(ctx->reserve_device(arena_bytes({(size_t)n * 12, (size_t)n * 12, (size_t)n * 12, 64, tiles * 4}) +
+                             insert_scratch_bytes(*options, n)));
+  Arena a(ctx->d_scratch);
+  float* d_in = a.take<float>(3 * n);
+  float* d_all = a.take<float>(3 * n);
+  float* d_near = a.take<float>(3 * n);
+  int32_t* d_near_count = a.take<int32_t>(1);
+  int32_t* d_tiles = a.take<int32_t>(tiles);
+  DL_TRY(h2d(ctx, d_in, returns, 3 * n));
+  // TransformRangeData(range_data, local_pose().inverse().cast<float>())
+  const Rigidf to_submap = to_float(inverse(pose_from7(submap_local_pose)));
+  const Vec3f origin_submap = apply(to_submap, Vec3f{origin[0], origin[1], origin[2]});
+  DL_TRY(launch_transform_filter(ctx, d_in, (int)n, to_submap, origin_submap, (float)high_resolution_max_range, d_all, d_near,
+                                 d_near_count, d_tiles));
+  int32_t near_count = 0;
+  DL_TRY(d2h(ctx, &near_count, d_near_count, 1));
+  DL_TRY(sync(ctx));
+  InsertScratch s;
+  DL_TRY(prepare_insert(ctx, a, *options, n, &s));
+  DL_TRY(grid_insert_device(ctx, hi, origin_submap, d_near, near_count, options->num_free_space_voxels, s.hit_table,
+                            s.miss_table, s.bbox, s.update_list));
+  DL_TRY(grid_insert_device(ctx, lo, origin_submap, d_all, (int)n, options->num_free_space_voxels, s.hit_table, s.miss_table,
+                            s.bbox, s.update_list));
+  return sync(ctx);
+}
+
+int dl_grid_export_cells(dl_grid* g, int64_t capacity, int32_t* xs, int32_t* ys, int32_t* zs, uint16_t* vs, int64_t* n_cells) {
+  if (!g || !n_cells || capacity < 0 || (capacity > 0 && (!xs || !ys || !zs || !vs))) return DL_ERR_ARG;
+  DL_CUDA(g->ctx, cudaSetDevice(g->ctx->device));
+  DL_TRY(grid_download(g));
+  const int bits = g->bits, tmask = (1 << bits) - 1, half_top = (1 << (bits - 1)) * 64;
+  int64_t count = 0;
+  for (size_t t = 0; t < g->top.size(); ++t) {
+    if (g->top[t] < 0) continue;
+    const int tx = (int)t & tmask, ty = ((int)t >> bits) & tmask, tz = ((int)t >> bits) >> bits;
+    const int32_t* node = g->nodes.data() + (size_t)g->top[t] * 512;
+    for (int l = 0; l < 512; ++l) {
+      if (node[l] < 0) continue;
+      const uint16_t* brick = g->bricks.data() + (size_t)node[l] * 512;
+      for (int c = 0; c < 512; ++c) {
+        if (brick[c] == 0) continue;
+        if (count < capacity) {
+          xs[count] = tx * 64 + (l & 7) * 8 + (c & 7) - half_top;
+          ys[count] = ty * 64 + ((l >> 3) & 7) * 8 + ((c >> 3) & 7) - half_top;
+          zs[count] = tz * 64 + (l >> 6) * 8 + (c >> 6) - half_top;
+          vs[count] = brick[c];
+        }
+        ++count;
+      }
+    }
+  }
+  *n_cells = count;
+  return DL_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ voxel filters

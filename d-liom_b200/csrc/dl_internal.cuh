@@ -97,6 +97,8 @@ struct dl_grid {
   int32_t* d_nodes = nullptr;
   uint16_t* d_bricks = nullptr;
   size_t d_top_cap = 0, d_nodes_cap = 0, d_bricks_cap = 0;  // element capacities
+  int32_t* d_counters = nullptr;  // [0] nodes in use, [1] bricks in use, [2] scratch (update-list length)
+  bool mirror_stale = false;      // the device copy was modified by dl_grid_insert_range_data: the host mirror is behind
   dl::GridView view() const { return {d_top, d_nodes, d_bricks, resolution, bits}; }
 };
 
@@ -104,6 +106,12 @@ struct dl_grid {
   do {                                                      \
     cudaError_t e__ = (call);                               \
     if (e__ != cudaSuccess) return (ctx)->cuda_fail(e__, #call); \
+  } while (0)
+
+#define DL_TRY_STATUS(expr)         \
+  do {                              \
+    const int st__ = (expr);        \
+    if (st__ != DL_OK) return st__; \
   } while (0)
 
 #define DL_LAUNCH_CHECK(ctx, name)                          \
@@ -219,6 +227,11 @@ int launch_nls_normal_equations(dl_context* ctx, const NlsOptions& opt, const Nl
                                 const double* at_pose_dev, double* out28_dev);
 int launch_imu_preintegrate(dl_context* ctx, int count, const int32_t* offsets, const double* dts, const double* accs,
                             const double* gyrs, const double* biases, const dl_imu_noise& noise, dl_preintegration* out);
+void compute_odds_table(float probability, uint16_t* table32768);
+int grid_insert_device(dl_context* ctx, dl_grid* g, const Vec3f& origin, const float* d_returns, int n, int num_free,
+                       const uint16_t* d_hit_table, const uint16_t* d_miss_table, int32_t* d_bbox, uint32_t* d_update_list);
+int launch_transform_filter(dl_context* ctx, const float* in, int n, const Rigidf& to_submap, const Vec3f& origin_submap,
+                            float max_range, float* all, float* near, int32_t* near_count, int32_t* tile_counts);
 int launch_interpolate(dl_context* ctx, const GridView& grid, int64_t n, const double* xyz, double* out);
 int launch_grid_lookup(dl_context* ctx, const GridView& grid, int64_t n, const int32_t* xyz, uint16_t* out);
 

@@ -23,6 +23,7 @@ EXPORTS = [
     "dl_context_create", "dl_context_destroy", "dl_last_error", "dl_status_string", "dl_context_kernel_launches",
     "dl_context_stream", "dl_context_synchronize", "dl_context_set_profiling", "dl_context_read_profile", "dl_grid_create", "dl_grid_destroy", "dl_grid_set_cells",
     "dl_grid_sync", "dl_grid_resolution", "dl_grid_num_bricks", "dl_grid_lookup", "dl_grid_interpolate",
+    "dl_grid_insert_range_data", "dl_submap_insert_range_data", "dl_grid_export_cells",
     "dl_voxel_filter", "dl_voxel_indices", "dl_adaptive_voxel_filter", "dl_rtcsm_match", "dl_ceres_match",
     "dl_ceres_match_batch", "dl_ceres_normal_equations", "dl_imu_preintegrate", "dl_imu_predict", "dl_fused_match_batch", "dl_ingest_scan", "dl_frontend_match_batch",
     "dl_frontend_match_batch_dev", "dl_frontend_fetch_results", "dl_device_alloc", "dl_device_free",
@@ -52,6 +53,11 @@ class RtcsmOptions(C.Structure):
 class RtcsmInfo(C.Structure):
     _fields_ = [("best_index", C.c_int64), ("num_candidates", C.c_int64), ("linear_window", C.c_int32),
                 ("angular_window", C.c_int32), ("angular_step", C.c_float), ("max_scan_range", C.c_float)]
+
+
+class RangeDataInserterOptions(C.Structure):
+    _fields_ = [("hit_probability", C.c_double), ("miss_probability", C.c_double), ("num_free_space_voxels", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class ImuNoise(C.Structure):
@@ -173,6 +179,9 @@ def lib():
     L.dl_grid_num_bricks.restype = C.c_int64
     L.dl_grid_lookup.argtypes = [vp, vp, C.c_int64, i32p, u16p]
     L.dl_grid_interpolate.argtypes = [vp, vp, C.c_int64, f64p, f64p]
+    L.dl_grid_insert_range_data.argtypes = [vp, vp, ip(RangeDataInserterOptions), f32p, f32p, C.c_int64]
+    L.dl_submap_insert_range_data.argtypes = [vp, vp, vp, ip(RangeDataInserterOptions), f64p, C.c_int32, f32p, f32p, C.c_int64]
+    L.dl_grid_export_cells.argtypes = [vp, C.c_int64, vp, vp, vp, vp, ip(C.c_int64)]
     L.dl_voxel_filter.argtypes = [vp, f32p, C.c_int64, C.c_int, C.c_float, i64p, ip(C.c_int64)]
     L.dl_voxel_indices.argtypes = [vp, f32p, C.c_int64, C.c_int, C.c_float, i32p]
     L.dl_adaptive_voxel_filter.argtypes = [vp, ip(AdaptiveVoxelFilterOptions), f32p, C.c_int64, C.c_int, i64p,
@@ -426,6 +435,15 @@ class Context:
         self.check(self.L.dl_frontend_fetch_results(self.h, results_dev_ptr, n, results))
         return results
 
+    def submap_insert_range_data(self, hi, lo, submap_local_pose, origin, returns, high_resolution_max_range=20, hit=0.55,
+                                 miss=0.49, num_free=2):
+        returns = np.ascontiguousarray(returns, np.float32).reshape(-1, 3)
+        opt = RangeDataInserterOptions(hit, miss, num_free, 0)
+        self.check(self.L.dl_submap_insert_range_data(self.h, hi.h, lo.h, C.byref(opt),
+                                                      np.ascontiguousarray(submap_local_pose, np.float64),
+                                                      int(high_resolution_max_range), np.ascontiguousarray(origin, np.float32),
+                                                      returns, len(returns)))
+
     def device_alloc(self, nbytes):
         p = C.c_void_p()
         self.check(self.L.dl_device_alloc(self.h, nbytes, C.byref(p)))
@@ -481,6 +499,23 @@ class Grid:
         out = np.zeros((max(len(xyz), 1), 4))
         self.ctx.check(self.ctx.L.dl_grid_interpolate(self.ctx.h, self.h, len(xyz), xyz, out))
         return out[:len(xyz)]
+
+    def insert_range_data(self, origin, returns, hit=0.55, miss=0.49, num_free=2):
+        """RangeDataInserter3D::Insert on the device grid (points already in the grid frame)."""
+        returns = np.ascontiguousarray(returns, np.float32).reshape(-1, 3)
+        opt = RangeDataInserterOptions(hit, miss, num_free, 0)
+        self.ctx.check(self.ctx.L.dl_grid_insert_range_data(self.ctx.h, self.h, C.byref(opt),
+                                                            np.ascontiguousarray(origin, np.float32), returns, len(returns)))
+
+    def export(self):
+        """(x, y, z, value) of every non-zero cell, in the reference's HybridGrid iteration order."""
+        n = C.c_int64(0)
+        self.ctx.check(self.ctx.L.dl_grid_export_cells(self.h, 0, None, None, None, None, C.byref(n)))
+        xs, ys, zs = (np.zeros(max(n.value, 1), np.int32) for _ in range(3))
+        vs = np.zeros(max(n.value, 1), np.uint16)
+        vp = lambda arr: arr.ctypes.data_as(C.c_void_p)
+        self.ctx.check(self.ctx.L.dl_grid_export_cells(self.h, n.value, vp(xs), vp(ys), vp(zs), vp(vs), C.byref(n)))
+        return xs[:n.value], ys[:n.value], zs[:n.value], vs[:n.value]
 
     @staticmethod
     def from_oracle(ctx, oracle_grid):

@@ -75,6 +75,29 @@ int dl_grid_lookup(dl_context* ctx, const dl_grid* grid, int64_t n, const int32_
  * (xyz interleaved doubles), on the device. out: n rows of 4 doubles (value, d/dx, d/dy, d/dz). */
 int dl_grid_interpolate(dl_context* ctx, const dl_grid* grid, int64_t n, const double* xyz, double* out);
 
+/* ---- grid WRITE side: RangeDataInserter3D::Insert (C/mapping/3d/range_data_inserter_3d.cc:76-92, misses
+ *      :27-51), HybridGrid::ApplyLookupTable / FinishUpdate (hybrid_grid.h:494-520) and Submap3D::InsertRangeData
+ *      (C/mapping/3d/submap_3d.cc:264-279) executed ON the device grid, which then is the primary copy (no per-scan host
+ *      insert + upload). Options = proto::RangeDataInserterOptions3D. ------------------------------------------------- */
+typedef struct dl_range_data_inserter_options {
+  double hit_probability;
+  double miss_probability;
+  int32_t num_free_space_voxels;
+  int32_t reserved;
+} dl_range_data_inserter_options;
+/* returns: n x 3 floats already in the grid's (submap) frame; origin: 3 floats in the same frame. */
+int dl_grid_insert_range_data(dl_context* ctx, dl_grid* grid, const dl_range_data_inserter_options* options,
+                              const float* origin, const float* returns, int64_t n);
+/* Submap3D::InsertRangeData: range data in the LOCAL frame is moved into the submap frame (local_pose^-1, float), the
+ * high-resolution grid receives the returns within high_resolution_max_range of the origin, the low-resolution grid all. */
+int dl_submap_insert_range_data(dl_context* ctx, dl_grid* high_resolution_grid, dl_grid* low_resolution_grid,
+                                const dl_range_data_inserter_options* options, const double* submap_local_pose,
+                                int32_t high_resolution_max_range, const float* origin, const float* returns, int64_t n);
+/* HybridGrid iteration (the ToProto order, hybrid_grid.h:530-542) of the grid's CURRENT content, downloading the
+ * device copy first if it is ahead of the host mirror. Call with capacity 0 to query *n_cells. */
+int dl_grid_export_cells(dl_grid* grid, int64_t capacity, int32_t* x, int32_t* y, int32_t* z, uint16_t* value,
+                         int64_t* n_cells);
+
 /* ---- sensor::VoxelFilter::Filter (C/sensor/internal/voxel_filter.h:34-62, voxel_filter.cc:81-131) ------------
  * keep_out receives the input-order indices of the first point in each voxel (capacity n). */
 int dl_voxel_filter(dl_context* ctx, const float* points, int64_t n, int stride, float resolution,
