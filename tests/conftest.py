@@ -11,6 +11,12 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "d-liom_b200"),
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
+    # a fresh checkout has no built artefacts (*.so are git-ignored): build the product library and the oracle once
+    lib = os.path.join(ROOT, "d-liom_b200", "libdliom_b200.so")
+    orc_lib = os.path.join(ROOT, "oracle", "build", "liborc.so")
+    if not (os.path.exists(lib) and os.path.exists(orc_lib)):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 @pytest.fixture(scope="session")
