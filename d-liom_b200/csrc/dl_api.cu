@@ -764,6 +764,69 @@ int dl_rtcsm_match(dl_context* ctx, const dl_rtcsm_options* options, const doubl
   return DL_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ loop-closure coarse matcher
+int dl_fcsm_match_3dof(dl_context* ctx, const dl_fcsm_options* o, const double* guess, const float* hi_pts, int64_t n_hi,
+                       const float* lo_pts, int64_t n_lo, const dl_grid* hi, const dl_grid* lo, float min_score,
+                       dl_fcsm_result* result) {
+  if (!ctx || !o || !guess || !hi || !lo || !result || n_hi < 0 || n_lo < 0 || (n_hi > 0 && !hi_pts) || (n_lo > 0 && !lo_pts))
+    return DL_ERR_ARG;
+  if (n_hi == 0 || n_lo == 0) return ctx->fail(DL_ERR_EMPTY, "empty point cloud");
+  if (o->branch_and_bound_depth < 1 || o->full_resolution_depth < 1)
+    return ctx->fail(DL_ERR_ARG, "branch_and_bound_depth and full_resolution_depth must be >= 1 (CHECK_GE)");
+  if (hi->structure_dirty || lo->structure_dirty) return ctx->fail(DL_ERR_ARG, "dl_grid_sync not called after dl_grid_set_cells");
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::memset(result, 0, sizeof(*result));
+  const float res = hi->resolution;
+  const int wxy = (int)std::lround(o->linear_xy_search_window / res);  // double / float -> double (cc:174-176)
+  const int wz = (int)std::lround(o->linear_z_search_window / res);
+  if (wxy < 0 || wz < 0) return ctx->fail(DL_ERR_ARG, "negative search window");
+  const long long side = 2ll * wxy + 1, K = side * side * (2ll * wz + 1);
+  if (K >= 0xFFFFFFFFll) return ctx->fail(DL_ERR_ARG, "more than 2^32-1 translation candidates");
+  DL_TRY(ctx->reserve_device(arena_bytes({(size_t)n_hi * 12, (size_t)n_lo * 12, (size_t)n_hi * 12, (size_t)K * 4, 64, 64})));
+  Arena a(ctx->d_scratch);
+  float* d_hi = a.take<float>(3 * n_hi);
+  float* d_lo = a.take<float>(3 * n_lo);
+  int* d_cells = a.take<int>(3 * n_hi);
+  float* d_scores = a.take<float>(K);
+  unsigned long long* d_best = a.take<unsigned long long>(1);
+  float* d_gate = a.take<float>(1);
+  DL_TRY(h2d(ctx, d_hi, hi_pts, 3 * n_hi));
+  DL_TRY(h2d(ctx, d_lo, lo_pts, 3 * n_lo));
+  const Rigidf pose = to_float(pose_from7(guess));
+  DL_TRY(launch_fcsm_cells(ctx, d_hi, (int)n_hi, pose, res, d_cells));
+  DL_TRY(launch_fcsm_scores(ctx, hi->view(), d_cells, (int)n_hi, wxy, wz, d_scores));
+  result->num_candidates = K;
+  for (int attempt = 0; attempt < 4096; ++attempt) {
+    DL_TRY(launch_fcsm_argmax(ctx, d_scores, K, min_score, d_best));
+    unsigned long long best = 0;
+    DL_TRY(d2h(ctx, &best, d_best, 1));
+    DL_TRY(sync(ctx));
+    if (best == 0) return DL_OK;  // nothing above min_score (left): the reference returns nullptr
+    const long long idx = (long long)(0xFFFFFFFFull - (best & 0xFFFFFFFFull));
+    const uint32_t bits = (uint32_t)(best >> 32);
+    float score;
+    std::memcpy(&score, &bits, 4);
+    const int ox = (int)(idx % side) - wxy, oy = (int)((idx / side) % side) - wxy, oz = (int)(idx / (side * side)) - wz;
+    // GetPoseFromCandidate: Translation(resolution * offset) * discrete_scan.pose (cc:423-430)
+    const Rigidf candidate = compose(Rigidf{{res * (float)ox, res * (float)oy, res * (float)oz}, {1.f, 0.f, 0.f, 0.f}}, pose);
+    DL_TRY(launch_fcsm_gate(ctx, lo->view(), d_lo, (int)n_lo, candidate, d_gate));
+    float low = 0.f;
+    DL_TRY(d2h(ctx, &low, d_gate, 1));
+    DL_TRY(sync(ctx));
+    if ((double)low >= o->min_low_resolution_score) {
+      result->found = 1;
+      result->score = score;
+      pose_to7(to_double(candidate), result->pose_estimate);
+      result->rotational_score = (float)(o->min_rotational_score + 0.01);  // what MatchWith3DofInitial reports (cc:179-181)
+      result->low_resolution_score = low;
+      result->offset[0] = ox; result->offset[1] = oy; result->offset[2] = oz;
+      return DL_OK;
+    }
+    DL_TRY(launch_fcsm_reject(ctx, d_scores, idx));
+  }
+  return ctx->fail(DL_ERR_ARG, "low-resolution gate rejected 4096 candidates in a row");
+}
+
 // ------------------------------------------------------------------------------------------------ Ceres-equivalent matcher
 static int check_ceres_options(dl_context* ctx, const dl_ceres_options* o, int num_pairs) {
   if (!o) return DL_ERR_ARG;

@@ -227,6 +227,11 @@ int launch_nls_normal_equations(dl_context* ctx, const NlsOptions& opt, const Nl
                                 const double* at_pose_dev, double* out28_dev);
 int launch_imu_preintegrate(dl_context* ctx, int count, const int32_t* offsets, const double* dts, const double* accs,
                             const double* gyrs, const double* biases, const dl_imu_noise& noise, dl_preintegration* out);
+int launch_fcsm_cells(dl_context* ctx, const float* points, int n, const Rigidf& pose, float resolution, int* cells);
+int launch_fcsm_scores(dl_context* ctx, const GridView& grid, const int* cells, int n, int wxy, int wz, float* scores);
+int launch_fcsm_argmax(dl_context* ctx, const float* scores, long long K, float min_score, unsigned long long* best);
+int launch_fcsm_gate(dl_context* ctx, const GridView& lo, const float* points, int n, const Rigidf& pose, float* out);
+int launch_fcsm_reject(dl_context* ctx, float* scores, long long idx);
 void compute_odds_table(float probability, uint16_t* table32768);
 int grid_insert_device(dl_context* ctx, dl_grid* g, const Vec3f& origin, const float* d_returns, int n, int num_free,
                        const uint16_t* d_hit_table, const uint16_t* d_miss_table, int32_t* d_bbox, uint32_t* d_update_list);

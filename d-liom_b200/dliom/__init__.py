@@ -24,7 +24,7 @@ EXPORTS = [
     "dl_context_stream", "dl_context_synchronize", "dl_context_set_profiling", "dl_context_read_profile", "dl_grid_create", "dl_grid_destroy", "dl_grid_set_cells",
     "dl_grid_sync", "dl_grid_resolution", "dl_grid_num_bricks", "dl_grid_lookup", "dl_grid_interpolate",
     "dl_grid_insert_range_data", "dl_submap_insert_range_data", "dl_grid_export_cells",
-    "dl_voxel_filter", "dl_voxel_indices", "dl_adaptive_voxel_filter", "dl_rtcsm_match", "dl_ceres_match",
+    "dl_voxel_filter", "dl_voxel_indices", "dl_adaptive_voxel_filter", "dl_rtcsm_match", "dl_fcsm_match_3dof", "dl_ceres_match",
     "dl_ceres_match_batch", "dl_ceres_normal_equations", "dl_imu_preintegrate", "dl_imu_predict", "dl_fused_match_batch", "dl_ingest_scan", "dl_frontend_match_batch",
     "dl_frontend_match_batch_dev", "dl_frontend_fetch_results", "dl_device_alloc", "dl_device_free",
     "dl_copy_to_device", "dl_copy_to_host",
@@ -82,6 +82,19 @@ class NavState(C.Structure):
 
     def to16(self):
         return np.array(list(self.p) + list(self.q) + list(self.v) + list(self.ba) + list(self.bg))
+
+
+class FcsmOptions(C.Structure):
+    _fields_ = [("branch_and_bound_depth", C.c_int32), ("full_resolution_depth", C.c_int32),
+                ("min_rotational_score", C.c_double), ("min_low_resolution_score", C.c_double),
+                ("linear_xy_search_window", C.c_double), ("linear_z_search_window", C.c_double),
+                ("angular_search_window", C.c_double)]
+
+
+class FcsmResult(C.Structure):
+    _fields_ = [("found", C.c_int32), ("score", C.c_float), ("pose_estimate", C.c_double * 7),
+                ("rotational_score", C.c_float), ("low_resolution_score", C.c_float), ("offset", C.c_int32 * 3),
+                ("reserved", C.c_int32), ("num_candidates", C.c_int64)]
 
 
 class CeresOptions(C.Structure):
@@ -187,6 +200,8 @@ def lib():
     L.dl_adaptive_voxel_filter.argtypes = [vp, ip(AdaptiveVoxelFilterOptions), f32p, C.c_int64, C.c_int, i64p,
                                            ip(C.c_int64), f32p, ip(C.c_int)]
     L.dl_rtcsm_match.argtypes = [vp, ip(RtcsmOptions), f64p, f32p, C.c_int64, vp, f64p, ip(C.c_float), ip(RtcsmInfo), vp]
+    L.dl_fcsm_match_3dof.argtypes = [vp, ip(FcsmOptions), f64p, f32p, C.c_int64, f32p, C.c_int64, vp, vp, C.c_float,
+                                     ip(FcsmResult)]
     L.dl_ceres_match.argtypes = [vp, ip(CeresOptions), f64p, f64p, C.c_int32, ip(vp), i64p, ip(vp), f64p,
                                  ip(SolveSummary)]
     L.dl_ceres_match_batch.argtypes = [vp, ip(CeresOptions), C.c_int32, C.c_int32, f64p, f64p, ip(vp), i64p, ip(vp),
@@ -307,6 +322,17 @@ class Context:
                 "linear": info.linear_window, "angular": info.angular_window, "angular_step": np.float32(info.angular_step),
                 "max_scan_range": np.float32(info.max_scan_range), "num_candidates": info.num_candidates,
                 "scores": scores}
+
+    def fcsm_match_3dof(self, hi_grid, lo_grid, hi_points, lo_points, pose_guess, min_score, xy_window=5.0, z_window=1.0,
+                        min_low_resolution_score=0.55, min_rotational_score=0.77, depth=8, full_depth=3):
+        hi_points = np.ascontiguousarray(hi_points, np.float32).reshape(-1, 3)
+        lo_points = np.ascontiguousarray(lo_points, np.float32).reshape(-1, 3)
+        opt = FcsmOptions(depth, full_depth, min_rotational_score, min_low_resolution_score, xy_window, z_window, 0.26)
+        r = FcsmResult()
+        self.check(self.L.dl_fcsm_match_3dof(self.h, C.byref(opt), np.ascontiguousarray(pose_guess, np.float64), hi_points,
+                                             len(hi_points), lo_points, len(lo_points), hi_grid.h, lo_grid.h,
+                                             np.float32(min_score), C.byref(r)))
+        return r
 
     @staticmethod
     def _pairs(clouds, grids):

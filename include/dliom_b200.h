@@ -140,6 +140,34 @@ int dl_rtcsm_match(dl_context* ctx, const dl_rtcsm_options* options, const doubl
                    const float* points, int64_t n, const dl_grid* grid, double* pose_out, float* score_out,
                    dl_rtcsm_info* info, float* all_scores);
 
+/* ---- scan_matching::FastCorrelativeScanMatcher3D::MatchWith3DofInitial (SM/fast_correlative_scan_matcher_3d.h:110-160,
+ *      .cc:165-196): the loop-closure coarse matcher as this fork calls it (constraint_builder_3d.cc:275-277). The whole
+ *      (x, y, z) window is scored on the device; no precomputation grid stack is built (options' depths are accepted and
+ *      ignored). Options = proto::FastCorrelativeScanMatcherOptions3D. ------------------------------------------------ */
+typedef struct dl_fcsm_options {
+  int32_t branch_and_bound_depth;
+  int32_t full_resolution_depth;
+  double min_rotational_score;
+  double min_low_resolution_score;
+  double linear_xy_search_window;
+  double linear_z_search_window;
+  double angular_search_window;
+} dl_fcsm_options;
+typedef struct dl_fcsm_result { /* FastCorrelativeScanMatcher3D::Result; found == 0 <=> the reference returns nullptr */
+  int32_t found;
+  float score;
+  double pose_estimate[7];
+  float rotational_score;
+  float low_resolution_score;
+  int32_t offset[3];      /* winning translation in cells */
+  int32_t reserved;
+  int64_t num_candidates; /* leaves scored */
+} dl_fcsm_result;
+int dl_fcsm_match_3dof(dl_context* ctx, const dl_fcsm_options* options, const double* pose_in_submap_guess,
+                       const float* high_resolution_points, int64_t n_high, const float* low_resolution_points,
+                       int64_t n_low, const dl_grid* high_resolution_grid, const dl_grid* low_resolution_grid,
+                       float min_score, dl_fcsm_result* result);
+
 /* ---- scan_matching::CeresScanMatcher3D::Match (SM/ceres_scan_matcher_3d.h:41-61, .cc:63-123; options
  *      C/mapping/proto/scan_matching/ceres_scan_matcher_options_3d.proto + C/common/proto/ceres_solver_options.proto)
  * The Levenberg-Marquardt loop (Ceres 1.13 TrustRegionMinimizer semantics) runs entirely on the device. ------ */

@@ -35,6 +35,12 @@ class Preintegration(C.Structure):
                 ("jacobian", C.c_double * 225), ("covariance", C.c_double * 225)]
 
 
+class FcsmResult(C.Structure):
+    _fields_ = [("found", C.c_int), ("score", C.c_float), ("pose", C.c_double * 7), ("rotational_score", C.c_float),
+                ("low_resolution_score", C.c_float), ("offset", C.c_int * 3), ("reserved", C.c_int),
+                ("leaves_scored", C.c_int64)]
+
+
 class FrontEndOptions(C.Structure):
     """Field-for-field the parameters LocalTrajectoryBuilder3D reads on the hot path; defaults =
     configuration_files/trajectory_builder_3d.lua."""
@@ -125,6 +131,8 @@ def lib():
     L.orc_frontend_batch.restype = C.c_double
     L.orc_frontend_batch.argtypes = [C.POINTER(FrontEndOptions), C.c_int, C.POINTER(C.c_void_p), i64p, f32p, f64p,
                                      f64p, f64p, C.c_void_p, C.c_void_p, C.c_int, f64p, i32p]
+    L.orc_fcsm_match_3dof.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                      f64p, f32p, C.c_int64, f32p, C.c_int64, C.c_float, C.POINTER(FcsmResult)]
     L.orc_imu_preintegrate.argtypes = [f64p, f64p, f64p, C.c_int, f64p, f64p, f64p, C.POINTER(Preintegration)]
     L.orc_imu_predict.argtypes = [f64p, C.POINTER(Preintegration), f64p, f64p]
     L.orc_imu_residual.argtypes = [f64p, f64p, C.POINTER(Preintegration), f64p, f64p, C.c_void_p]
@@ -404,3 +412,15 @@ def fused_match(clouds, grids, occ_weights, trans_w, rot_w, target_translation, 
     if not ok:
         raise RuntimeError("pre-integration covariance is not positive definite")
     return out, s.as_dict()
+
+
+def fcsm_match_3dof(hi_grid, lo_grid, hi_points, lo_points, pose_guess, min_score, xy_window=5.0, z_window=1.0,
+                    min_low_resolution_score=0.55, min_rotational_score=0.77, depth=8, full_depth=3):
+    """FastCorrelativeScanMatcher3D::MatchWith3DofInitial with the reference's precomputation stack + branch and bound."""
+    hi_points = np.ascontiguousarray(hi_points, np.float32).reshape(-1, 3)
+    lo_points = np.ascontiguousarray(lo_points, np.float32).reshape(-1, 3)
+    r = FcsmResult()
+    lib().orc_fcsm_match_3dof(hi_grid.h, lo_grid.h, depth, full_depth, min_rotational_score, min_low_resolution_score,
+                              xy_window, z_window, np.ascontiguousarray(pose_guess, np.float64), hi_points, len(hi_points),
+                              lo_points, len(lo_points), np.float32(min_score), C.byref(r))
+    return r

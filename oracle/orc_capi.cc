@@ -5,6 +5,7 @@
 #include <cstring>
 #include <thread>
 
+#include "orc_fcsm.h"
 #include "orc_filters.h"
 #include "orc_frontend.h"
 #include "orc_grid.h"
@@ -126,6 +127,34 @@ float orc_rtcsm_match(void* grid, const float* pts, int64_t n, const double* ini
   if (step_out) { step_out[0] = r.window.angular_step; step_out[1] = r.window.max_scan_range; }
   if (all_scores) std::memcpy(all_scores, scores.data(), scores.size() * sizeof(float));
   return r.score;
+}
+
+// ---- loop-closure coarse matcher (branch and bound)
+struct OrcFcsmResult {
+  int found;
+  float score;
+  double pose[7];
+  float rotational_score, low_resolution_score;
+  int offset[3];
+  int reserved;
+  int64_t leaves_scored;
+};
+void orc_fcsm_match_3dof(void* hi, void* lo, int depth, int full_depth, double min_rot, double min_low, double wxy, double wz,
+                         const double* pose_guess, const float* hi_pts, int64_t n_hi, const float* lo_pts, int64_t n_lo,
+                         float min_score, OrcFcsmResult* out) {
+  FcsmOptions o;
+  o.branch_and_bound_depth = depth; o.full_resolution_depth = full_depth; o.min_rotational_score = min_rot;
+  o.min_low_resolution_score = min_low; o.linear_xy_search_window = wxy; o.linear_z_search_window = wz;
+  FastCorrelativeScanMatcher m(*(HybridGrid*)hi, (const HybridGrid*)lo, o);
+  const FcsmResult r = m.MatchWith3DofInitial(pose_in(pose_guess), hi_pts, n_hi, lo_pts, n_lo, min_score);
+  std::memset(out, 0, sizeof(*out));
+  out->found = r.found ? 1 : 0;
+  out->score = r.score;
+  pose_out(r.pose, out->pose);
+  out->rotational_score = r.rotational_score;
+  out->low_resolution_score = r.low_resolution_score;
+  out->offset[0] = r.offset.x; out->offset[1] = r.offset.y; out->offset[2] = r.offset.z;
+  out->leaves_scored = r.leaves_scored;
 }
 
 // ---- Ceres-equivalent matcher

@@ -1,0 +1,242 @@
+// TEST INFRASTRUCTURE — CPU oracle (see orc_math.h header).
+//
+// Branch-and-bound loop-closure matcher in the form this fork actually calls:
+// FastCorrelativeScanMatcher3D::MatchWith3DofInitial — a single discretised scan at the given pose, search over the
+// (x, y, z) translation window only. Restated from
+//   SM/precomputation_grid_3d.h:25-36 (8-bit grid, ToProbability), precomputation_grid_3d.cc:27-81
+//     (DivideByTwoRoundingTowardsNegativeInfinity, ConvertToPrecomputationGrid, PrecomputeGrid)
+//   SM/fast_correlative_scan_matcher_3d.cc:57-77 (PrecomputationGridStack3D), :79-110 (DiscreteScan3D, Candidate3D),
+//     :165-196 (MatchWith3DofInitial), :253-295 (DiscretizeScan), :351-384 (GenerateLowestResolutionCandidates),
+//     :386-409 (ScoreCandidates), :423-430 (GetPoseFromCandidate), :432-495 (BranchAndBound)
+//   SM/low_resolution_matcher.cc:24-36
+// The 8-bit precomputation grids reuse the HybridGrid container (same three-level geometry; HybridGridBase<uint8>
+// in the reference) and simply store values 0..255.
+#pragma once
+#include <algorithm>
+#include <functional>
+#include <limits>
+#include <memory>
+#include <vector>
+
+#include "orc_grid.h"
+#include "orc_math.h"
+
+namespace orc {
+
+struct FcsmOptions {
+  int branch_and_bound_depth = 8;
+  int full_resolution_depth = 3;
+  double min_rotational_score = 0.77;
+  double min_low_resolution_score = 0.55;
+  double linear_xy_search_window = 5.;
+  double linear_z_search_window = 1.;
+  double angular_search_window = 0.2617993877991494;  // unused by MatchWith3DofInitial
+};
+
+inline float precomp_to_probability(float value) { return kMinProbability + value * ((kMaxProbability - kMinProbability) / 255.f); }
+inline int divide_by_two_rounding_down(int v) { return v >= 0 ? v / 2 : (v - 1) / 2; }
+
+inline std::unique_ptr<HybridGrid> convert_to_precomputation_grid(const HybridGrid& grid) {
+  auto result = std::make_unique<HybridGrid>(grid.resolution());
+  grid.ForEachCell([&](const I3& c, uint16_t v) {
+    const int cell_value =
+        round_to_int((value_to_probability(v) - kMinProbability) * (255.f / (kMaxProbability - kMinProbability)));
+    *result->mutable_value(c) = (uint16_t)cell_value;
+  });
+  return result;
+}
+
+inline std::unique_ptr<HybridGrid> precompute_grid(const HybridGrid& grid, bool half_resolution, const I3& shift) {
+  auto result = std::make_unique<HybridGrid>(grid.resolution());
+  grid.ForEachCell([&](const I3& c, uint16_t v) {
+    for (int i = 0; i != 8; ++i) {
+      I3 ci{c.x - shift.x * (i & 1), c.y - shift.y * ((i >> 1) & 1), c.z - shift.z * ((i >> 2) & 1)};
+      if (half_resolution) ci = {divide_by_two_rounding_down(ci.x), divide_by_two_rounding_down(ci.y), divide_by_two_rounding_down(ci.z)};
+      uint16_t* cell = result->mutable_value(ci);
+      *cell = std::max(v, *cell);
+    }
+  });
+  return result;
+}
+
+class PrecomputationGridStack {
+ public:
+  PrecomputationGridStack(const HybridGrid& grid, const FcsmOptions& o) {
+    grids_.push_back(convert_to_precomputation_grid(grid));
+    int last_width = 1;
+    for (int depth = 1; depth != o.branch_and_bound_depth; ++depth) {
+      const bool half_resolution = depth >= o.full_resolution_depth;
+      const int next_width = 1 << depth;
+      const int full_voxels = 1 << std::max(0, depth - o.full_resolution_depth);
+      const int shift = (next_width - last_width + (full_voxels - 1)) / full_voxels;
+      grids_.push_back(precompute_grid(*grids_.back(), half_resolution, I3{shift, shift, shift}));
+      last_width = next_width;
+    }
+  }
+  const HybridGrid& Get(int depth) const { return *grids_.at(depth); }
+  int max_depth() const { return (int)grids_.size() - 1; }
+
+ private:
+  std::vector<std::unique_ptr<HybridGrid>> grids_;
+};
+
+struct FcsmResult {
+  bool found = false;
+  float score = 0.f;
+  Rigid3d pose;
+  float rotational_score = 0.f;
+  float low_resolution_score = 0.f;
+  I3 offset{0, 0, 0};
+  int64_t leaves_scored = 0;  // work the branch and bound actually did (for the comparison with brute force)
+};
+
+class FastCorrelativeScanMatcher {
+ public:
+  FastCorrelativeScanMatcher(const HybridGrid& hi, const HybridGrid* lo, const FcsmOptions& o)
+      : o_(o), resolution_(hi.resolution()), stack_(hi, o), lo_(lo) {}
+
+  FcsmResult MatchWith3DofInitial(const Rigid3d& pose_in_submap_guess, const float* hi_pts, int64_t n_hi,
+                                  const float* lo_pts, int64_t n_lo, float min_score) const {
+    wxy_ = round_to_int(o_.linear_xy_search_window / resolution_);
+    wz_ = round_to_int(o_.linear_z_search_window / resolution_);
+    lo_pts_ = lo_pts;
+    n_lo_ = n_lo;
+    leaves_ = 0;
+    Discretize(hi_pts, n_hi, cast_f(pose_in_submap_guess));
+    rotational_score_ = (float)(o_.min_rotational_score + 0.01);
+    std::vector<Candidate> lowest = GenerateLowest();
+    Score(stack_.max_depth(), &lowest);
+    const Candidate best = BranchAndBound(lowest, stack_.max_depth(), min_score);
+    FcsmResult r;
+    r.leaves_scored = leaves_;
+    if (best.score > min_score) {
+      r.found = true;
+      r.score = best.score;
+      r.pose = cast_d(PoseFromCandidate(best));
+      r.rotational_score = rotational_score_;
+      r.low_resolution_score = best.low_resolution_score;
+      r.offset = best.offset;
+    }
+    return r;
+  }
+
+ private:
+  struct Candidate {
+    I3 offset{0, 0, 0};
+    float score = -std::numeric_limits<float>::infinity();
+    float low_resolution_score = 0.f;
+    bool operator>(const Candidate& other) const { return score > other.score; }
+    bool operator<(const Candidate& other) const { return score < other.score; }
+  };
+
+  void Discretize(const float* pts, int64_t n, const Rigid3f& pose) const {
+    pose_ = pose;
+    cells_.clear();
+    std::vector<I3> full;
+    for (int64_t i = 0; i < n; ++i)
+      full.push_back(stack_.Get(0).GetCellIndex(apply(pose, V3f{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]})));
+    const int full_depth = std::min(o_.full_resolution_depth, o_.branch_and_bound_depth);
+    for (int i = 0; i != full_depth; ++i) cells_.push_back(full);
+    const int low_depth = o_.branch_and_bound_depth - full_depth;
+    const I3 start{-wxy_, -wxy_, -wz_};
+    for (int i = 0; i != low_depth; ++i) {
+      const int e = i + 1;
+      const I3 low_start{start.x >> e, start.y >> e, start.z >> e};
+      cells_.emplace_back();
+      for (const I3& c : full) {
+        const I3 at_start{c.x + start.x, c.y + start.y, c.z + start.z};
+        cells_.back().push_back(I3{(at_start.x >> e) - low_start.x, (at_start.y >> e) - low_start.y, (at_start.z >> e) - low_start.z});
+      }
+    }
+  }
+
+  std::vector<Candidate> GenerateLowest() const {
+    const int step = 1 << stack_.max_depth();
+    std::vector<Candidate> out;
+    for (int z = -wz_; z <= wz_; z += step)
+      for (int y = -wxy_; y <= wxy_; y += step)
+        for (int x = -wxy_; x <= wxy_; x += step) {
+          Candidate c;
+          c.offset = {x, y, z};
+          out.push_back(c);
+        }
+    return out;
+  }
+
+  void Score(int depth, std::vector<Candidate>* candidates) const {
+    const int e = std::max(0, depth - o_.full_resolution_depth + 1);
+    const HybridGrid& grid = stack_.Get(depth);
+    for (Candidate& c : *candidates) {
+      int sum = 0;
+      const I3 off{c.offset.x >> e, c.offset.y >> e, c.offset.z >> e};
+      for (const I3& cell : cells_[depth]) sum += grid.value(I3{cell.x + off.x, cell.y + off.y, cell.z + off.z});
+      c.score = precomp_to_probability(sum / (float)cells_[depth].size());
+      if (depth == 0) ++leaves_;
+    }
+    std::sort(candidates->begin(), candidates->end(), std::greater<Candidate>());
+  }
+
+  Rigid3f PoseFromCandidate(const Candidate& c) const {
+    const Rigid3f translation{{resolution_ * (float)c.offset.x, resolution_ * (float)c.offset.y, resolution_ * (float)c.offset.z},
+                              {1.f, 0.f, 0.f, 0.f}};
+    return compose(translation, pose_);
+  }
+
+  float LowResolutionScore(const Rigid3f& pose) const {
+    float score = 0.f;
+    for (int64_t i = 0; i < n_lo_; ++i)
+      score += lo_->GetProbability(lo_->GetCellIndex(apply(pose, V3f{lo_pts_[3 * i], lo_pts_[3 * i + 1], lo_pts_[3 * i + 2]})));
+    return score / (float)n_lo_;  // float / size_t
+  }
+
+  Candidate BranchAndBound(const std::vector<Candidate>& candidates, int depth, float min_score) const {
+    if (depth == 0) {
+      for (const Candidate& c : candidates) {
+        if (c.score <= min_score) return Candidate();
+        const float low = LowResolutionScore(PoseFromCandidate(c));
+        if (low >= o_.min_low_resolution_score) {
+          Candidate best = c;
+          best.low_resolution_score = low;
+          return best;
+        }
+      }
+      return Candidate();
+    }
+    Candidate best;
+    best.score = min_score;
+    for (const Candidate& c : candidates) {
+      if (c.score <= min_score) break;
+      std::vector<Candidate> higher;
+      const int half_width = 1 << (depth - 1);
+      for (int z : {0, half_width}) {
+        if (c.offset.z + z > wz_) break;
+        for (int y : {0, half_width}) {
+          if (c.offset.y + y > wxy_) break;
+          for (int x : {0, half_width}) {
+            if (c.offset.x + x > wxy_) break;
+            Candidate h;
+            h.offset = {c.offset.x + x, c.offset.y + y, c.offset.z + z};
+            higher.push_back(h);
+          }
+        }
+      }
+      Score(depth - 1, &higher);
+      const Candidate sub = BranchAndBound(higher, depth - 1, best.score);
+      if (best < sub) best = sub;  // std::max(a, b) keeps a unless a < b
+    }
+    return best;
+  }
+
+  FcsmOptions o_;
+  float resolution_;
+  PrecomputationGridStack stack_;
+  const HybridGrid* lo_;
+  mutable int wxy_ = 0, wz_ = 0;
+  mutable Rigid3f pose_;
+  mutable std::vector<std::vector<I3>> cells_;
+  mutable const float* lo_pts_ = nullptr;
+  mutable int64_t n_lo_ = 0, leaves_ = 0;
+  mutable float rotational_score_ = 0.f;
+};
+
+}  // namespace orc

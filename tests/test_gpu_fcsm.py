@@ -1,0 +1,99 @@
+"""GPU parity of the loop-closure coarse matcher: the device scores the whole translation window;
+the oracle runs the reference's precomputation stack + branch and bound. Scores are integer sums -> bit-exact."""
+import numpy as np
+import pytest
+
+from helpers import workload
+from test_fcsm_oracle import CLOUD, TEST_OPTS, fixture_grid
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import dliom
+    c = dliom.Context(0)
+    yield c
+    c.close()
+
+
+def same(got, want, unique=True):
+    assert bool(got.found) == bool(want.found)
+    if not want.found:
+        return
+    assert np.float32(got.score) == np.float32(want.score)
+    assert np.float32(got.rotational_score) == np.float32(want.rotational_score)
+    if unique:
+        assert tuple(got.offset) == tuple(want.offset)
+        assert np.array_equal(np.array(got.pose_estimate[:]), np.array(want.pose[:]))
+        assert np.float32(got.low_resolution_score) == np.float32(want.low_resolution_score)
+
+
+def test_reference_fixture(ctx, orc):
+    import dliom
+    rng = np.random.default_rng(42)
+    for _ in range(6):
+        shift = (0.7 * rng.uniform(-1, 1, 3)).astype(np.float32)
+        og = fixture_grid(orc, shift)
+        g = dliom.Grid.from_oracle(ctx, og)
+        want = orc.fcsm_match_3dof(og, og, CLOUD, CLOUD, orc.IDENTITY_POSE, 0.1, **TEST_OPTS)
+        got = ctx.fcsm_match_3dof(g, g, CLOUD, CLOUD, orc.IDENTITY_POSE, 0.1, **TEST_OPTS)
+        same(got, want, unique=False)
+        assert np.abs(np.array(got.pose_estimate[:3]) - shift).max() < 0.05
+        assert got.num_candidates == 33 ** 3
+        far = np.array([[42, 42, 42]], np.float32)
+        assert not ctx.fcsm_match_3dof(g, g, CLOUD, far, orc.IDENTITY_POSE, 0.1, **TEST_OPTS).found
+        assert not ctx.fcsm_match_3dof(g, g, CLOUD, CLOUD, orc.IDENTITY_POSE, 0.95, **TEST_OPTS).found
+
+
+def test_scene_submap_pose_graph_options(ctx, orc):
+    """pose_graph.lua's constraint_builder options (5 m x 5 m x 1 m window at 0.1 m: 101 x 101 x 21 leaves, depth 8 /
+    full-resolution depth 3) on a synthetic-scene submap, node displaced by metres."""
+    import dliom
+    w = workload(beams=16, num_map_scans=40, num_scans=3)
+    hi, lo = dliom.Grid.from_oracle(ctx, w["hi"]), dliom.Grid.from_oracle(ctx, w["lo"])
+    rng = np.random.default_rng(5)
+    for k in range(3):
+        pts = orc.ingest_scan(w["opts"], w["scans"][k], w["origin"], w["prev"][k], w["truth"][k])["returns_tracking"]
+        hk, _ = orc.adaptive_voxel_filter(pts, 2.0, 150, 15.0)
+        lk, _ = orc.adaptive_voxel_filter(pts, 4.0, 200, 60.0)
+        guess = np.array(w["truth"][k], np.float64)
+        guess[:3] += rng.uniform(-1, 1, 3) * [2.5, 2.5, 0.5]
+        kw = dict(min_low_resolution_score=0.3)
+        want = orc.fcsm_match_3dof(w["hi"], w["lo"], pts[hk], pts[lk], guess, 0.15, **kw)
+        got = ctx.fcsm_match_3dof(hi, lo, pts[hk], pts[lk], guess, 0.15, **kw)
+        assert want.found
+        same(got, want)
+        assert got.num_candidates == 101 * 101 * 21 and want.leaves_scored < got.num_candidates
+        assert np.abs(np.array(got.pose_estimate[:3]) - w["truth"][k][:3]).max() < 0.3
+        # the stock thresholds (min_score 0.55 is far above what a 16-beam sweep reaches here): both say "no constraint"
+        assert not orc.fcsm_match_3dof(w["hi"], w["lo"], pts[hk], pts[lk], guess, 0.55).found
+        assert not ctx.fcsm_match_3dof(hi, lo, pts[hk], pts[lk], guess, 0.55).found
+
+
+def test_low_resolution_gate_skips_better_scoring_leaves(ctx, orc):
+    """The low-resolution grid disagrees with the high-resolution one by two cells: every leaf around the high-resolution
+    optimum fails the gate and the matcher has to walk down the score order (the reference does this inside the branch
+    and bound, the device by rejecting the arg-max and re-reducing). Equal-score leaves abound here, so only the score
+    and the gate outcome are compared, not which of the tied leaves was reported."""
+    import dliom
+    shift = np.array([0.2, -0.1, 0.15], np.float32)
+    ohi, olo = fixture_grid(orc, shift), fixture_grid(orc, shift - np.array([0.1, 0, 0], np.float32))
+    hi, lo = dliom.Grid.from_oracle(ctx, ohi), dliom.Grid.from_oracle(ctx, olo)
+    opts = dict(TEST_OPTS, min_low_resolution_score=0.5)
+    want = orc.fcsm_match_3dof(ohi, olo, CLOUD, CLOUD, orc.IDENTITY_POSE, 0.1, **opts)
+    got = ctx.fcsm_match_3dof(hi, lo, CLOUD, CLOUD, orc.IDENTITY_POSE, 0.1, **opts)
+    best = orc.fcsm_match_3dof(ohi, ohi, CLOUD, CLOUD, orc.IDENTITY_POSE, 0.1, **TEST_OPTS)
+    assert want.found and want.score < best.score
+    same(got, want, unique=False)
+    assert got.low_resolution_score >= 0.5
+
+
+def test_argument_errors(ctx, orc):
+    import dliom
+    og = fixture_grid(orc, (0, 0, 0))
+    g = dliom.Grid.from_oracle(ctx, og)
+    with pytest.raises(dliom.DlError):
+        ctx.fcsm_match_3dof(g, g, CLOUD[:0], CLOUD, orc.IDENTITY_POSE, 0.1)
+    with pytest.raises(dliom.DlError):
+        ctx.fcsm_match_3dof(g, g, CLOUD, CLOUD, orc.IDENTITY_POSE, 0.1, depth=0)
