@@ -764,69 +764,6 @@ int dl_rtcsm_match(dl_context* ctx, const dl_rtcsm_options* options, const doubl
   return DL_OK;
 }
 
-// ------------------------------------------------------------------------------------------------ loop-closure coarse matcher
-int dl_fcsm_match_3dof(dl_context* ctx, const dl_fcsm_options* o, const double* guess, const float* hi_pts, int64_t n_hi,
-                       const float* lo_pts, int64_t n_lo, const dl_grid* hi, const dl_grid* lo, float min_score,
-                       dl_fcsm_result* result) {
-  if (!ctx || !o || !guess || !hi || !lo || !result || n_hi < 0 || n_lo < 0 || (n_hi > 0 && !hi_pts) || (n_lo > 0 && !lo_pts))
-    return DL_ERR_ARG;
-  if (n_hi == 0 || n_lo == 0) return ctx->fail(DL_ERR_EMPTY, "empty point cloud");
-  if (o->branch_and_bound_depth < 1 || o->full_resolution_depth < 1)
-    return ctx->fail(DL_ERR_ARG, "branch_and_bound_depth and full_resolution_depth must be >= 1 (CHECK_GE)");
-  if (hi->structure_dirty || lo->structure_dirty) return ctx->fail(DL_ERR_ARG, "dl_grid_sync not called after dl_grid_set_cells");
-  DL_CUDA(ctx, cudaSetDevice(ctx->device));
-  std::memset(result, 0, sizeof(*result));
-  const float res = hi->resolution;
-  const int wxy = (int)std::lround(o->linear_xy_search_window / res);  // double / float -> double (cc:174-176)
-  const int wz = (int)std::lround(o->linear_z_search_window / res);
-  if (wxy < 0 || wz < 0) return ctx->fail(DL_ERR_ARG, "negative search window");
-  const long long side = 2ll * wxy + 1, K = side * side * (2ll * wz + 1);
-  if (K >= 0xFFFFFFFFll) return ctx->fail(DL_ERR_ARG, "more than 2^32-1 translation candidates");
-  DL_TRY(ctx->reserve_device(arena_bytes({(size_t)n_hi * 12, (size_t)n_lo * 12, (size_t)n_hi * 12, (size_t)K * 4, 64, 64})));
-  Arena a(ctx->d_scratch);
-  float* d_hi = a.take<float>(3 * n_hi);
-  float* d_lo = a.take<float>(3 * n_lo);
-  int* d_cells = a.take<int>(3 * n_hi);
-  float* d_scores = a.take<float>(K);
-  unsigned long long* d_best = a.take<unsigned long long>(1);
-  float* d_gate = a.take<float>(1);
-  DL_TRY(h2d(ctx, d_hi, hi_pts, 3 * n_hi));
-  DL_TRY(h2d(ctx, d_lo, lo_pts, 3 * n_lo));
-  const Rigidf pose = to_float(pose_from7(guess));
-  DL_TRY(launch_fcsm_cells(ctx, d_hi, (int)n_hi, pose, res, d_cells));
-  DL_TRY(launch_fcsm_scores(ctx, hi->view(), d_cells, (int)n_hi, wxy, wz, d_scores));
-  result->num_candidates = K;
-  for (int attempt = 0; attempt < 4096; ++attempt) {
-    DL_TRY(launch_fcsm_argmax(ctx, d_scores, K, min_score, d_best));
-    unsigned long long best = 0;
-    DL_TRY(d2h(ctx, &best, d_best, 1));
-    DL_TRY(sync(ctx));
-    if (best == 0) return DL_OK;  // nothing above min_score (left): the reference returns nullptr
-    const long long idx = (long long)(0xFFFFFFFFull - (best & 0xFFFFFFFFull));
-    const uint32_t bits = (uint32_t)(best >> 32);
-    float score;
-    std::memcpy(&score, &bits, 4);
-    const int ox = (int)(idx % side) - wxy, oy = (int)((idx / side) % side) - wxy, oz = (int)(idx / (side * side)) - wz;
-    // GetPoseFromCandidate: Translation(resolution * offset) * discrete_scan.pose (cc:423-430)
-    const Rigidf candidate = compose(Rigidf{{res * (float)ox, res * (float)oy, res * (float)oz}, {1.f, 0.f, 0.f, 0.f}}, pose);
-    DL_TRY(launch_fcsm_gate(ctx, lo->view(), d_lo, (int)n_lo, candidate, d_gate));
-    float low = 0.f;
-    DL_TRY(d2h(ctx, &low, d_gate, 1));
-    DL_TRY(sync(ctx));
-    if ((double)low >= o->min_low_resolution_score) {
-      result->found = 1;
-      result->score = score;
-      pose_to7(to_double(candidate), result->pose_estimate);
-      result->rotational_score = (float)(o->min_rotational_score + 0.01);  // what MatchWith3DofInitial reports (cc:179-181)
-      result->low_resolution_score = low;
-      result->offset[0] = ox; result->offset[1] = oy; result->offset[2] = oz;
-      return DL_OK;
-    }
-    DL_TRY(launch_fcsm_reject(ctx, d_scores, idx));
-  }
-  return ctx->fail(DL_ERR_ARG, "low-resolution gate rejected 4096 candidates in a row");
-}
-
 // ------------------------------------------------------------------------------------------------ Ceres-equivalent matcher
 static int check_ceres_options(dl_context* ctx, const dl_ceres_options* o, int num_pairs) {
   if (!o) return DL_ERR_ARG;
@@ -950,6 +887,180 @@ int dl_ceres_normal_equations(dl_context* ctx, const dl_ceres_options* options, 
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------ IMU
+// ------------------------------------------------------------------------------------------------ loop closure
+namespace {
+struct CoarseSearch {  // device state of one chunk of (node, submap) pairs
+  FcsmPair* d_pairs;
+  FcsmPick* d_picks;
+  unsigned long long* d_best;
+  const float* d_hi;  // chunk-relative clouds
+  const float* d_lo;
+};
+int check_fcsm_options(dl_context* ctx, const dl_fcsm_options& o) {
+  if (o.branch_and_bound_depth < 1 || o.full_resolution_depth < 1)
+    return ctx->fail(DL_ERR_ARG, "branch_and_bound_depth and full_resolution_depth must be >= 1 (CHECK_GE)");
+  if (o.linear_xy_search_window < 0 || o.linear_z_search_window < 0) return ctx->fail(DL_ERR_ARG, "negative search window");
+  return DL_OK;
+}
+// Uploads pairs [first, first + n) and runs the coarse search for them; leaves the picks on the device.
+int coarse_search(dl_context* ctx, Arena& a, const dl_fcsm_options& o, float min_score, int first, int n, const double* guesses,
+                  const float* hi_pts, const int64_t* hi_off, const float* lo_pts, const int64_t* lo_off,
+                  const dl_grid* const* hi_grids, const dl_grid* const* lo_grids, float* d_all_scores, CoarseSearch* out) {
+  const int64_t hi0 = hi_off[first], lo0 = lo_off[first];
+  const int64_t n_hi = hi_off[first + n] - hi0, n_lo = lo_off[first + n] - lo0;
+  float* d_hi = a.take<float>(3 * n_hi);
+  float* d_lo = a.take<float>(3 * n_lo);
+  int* d_cells = a.take<int>(3 * n_hi);
+  float* d_rot = a.take<float>(3 * n_lo);
+  out->d_pairs = a.take<FcsmPair>(n);
+  out->d_picks = a.take<FcsmPick>(n);
+  out->d_best = a.take<unsigned long long>(n);
+  out->d_hi = d_hi;
+  out->d_lo = d_lo;
+  DL_TRY(h2d(ctx, d_hi, hi_pts + 3 * hi0, 3 * n_hi));
+  DL_TRY(h2d(ctx, d_lo, lo_pts + 3 * lo0, 3 * n_lo));
+  std::vector<FcsmPair> pairs(n);
+  int max_points = 1;
+  long long max_candidates = 1;
+  for (int k = 0; k < n; ++k) {
+    const int g = first + k;
+    FcsmPair& p = pairs[k];
+    p.hi = hi_grids[g]->view();
+    p.lo = lo_grids[g]->view();
+    p.hi_pts = d_hi + 3 * (hi_off[g] - hi0);
+    p.lo_pts = d_lo + 3 * (lo_off[g] - lo0);
+    p.cells = d_cells + 3 * (hi_off[g] - hi0);
+    p.lo_rot = d_rot + 3 * (lo_off[g] - lo0);
+    p.n_hi = (int)(hi_off[g + 1] - hi_off[g]);
+    p.n_lo = (int)(lo_off[g + 1] - lo_off[g]);
+    p.pose = to_float(pose_from7(guesses + 7 * g));
+    const float res = hi_grids[g]->resolution;
+    p.wxy = (int)std::lround(o.linear_xy_search_window / res);  // double / float -> double, common::RoundToInt (cc:174-176)
+    p.wz = (int)std::lround(o.linear_z_search_window / res);
+    p.min_score = min_score;
+    p.min_low = o.min_low_resolution_score;
+    const long long side = 2ll * p.wxy + 1, K = side * side * (2ll * p.wz + 1);
+    if (K >= 0xFFFFFFFFll) return ctx->fail(DL_ERR_ARG, "more than 2^32-1 translation candidates");
+    max_candidates = std::max(max_candidates, side * (2ll * p.wz + 1) * ((side + kFcsmRun - 1) / kFcsmRun));  // search threads
+    max_points = std::max(max_points, std::max(p.n_hi, p.n_lo));
+  }
+  DL_TRY(h2d(ctx, out->d_pairs, pairs.data(), n));
+  DL_TRY(sync(ctx));  // `pairs` is pageable host memory
+  return launch_fcsm(ctx, out->d_pairs, n, max_points, max_candidates, out->d_best, out->d_picks, d_all_scores);
+}
+int check_pairs(dl_context* ctx, int count, const double* guesses, const float* hi_pts, const int64_t* hi_off, const float* lo_pts,
+                const int64_t* lo_off, const dl_grid* const* hi_grids, const dl_grid* const* lo_grids) {
+  if (!guesses || !hi_off || !lo_off || !hi_grids || !lo_grids || !hi_pts || !lo_pts) return DL_ERR_ARG;
+  for (int k = 0; k < count; ++k) {
+    if (!hi_grids[k] || !lo_grids[k]) return DL_ERR_ARG;
+    if (hi_off[k + 1] < hi_off[k] || lo_off[k + 1] < lo_off[k]) return ctx->fail(DL_ERR_ARG, "offsets must be non-decreasing");
+    if (hi_off[k + 1] == hi_off[k] || lo_off[k + 1] == lo_off[k]) return ctx->fail(DL_ERR_EMPTY, "empty point cloud");
+    if (hi_grids[k]->structure_dirty || lo_grids[k]->structure_dirty)
+      return ctx->fail(DL_ERR_ARG, "dl_grid_sync not called after dl_grid_set_cells");
+  }
+  return DL_OK;
+}
+size_t coarse_bytes(int64_t n_hi, int64_t n_lo, int n) {
+  return arena_bytes({(size_t)n_hi * 12, (size_t)n_lo * 12, (size_t)n_hi * 12, (size_t)n_lo * 12, (size_t)n * sizeof(FcsmPair),
+                      (size_t)n * sizeof(FcsmPick), (size_t)n * 8});
+}
+}  // namespace
+
+extern "C" {
+
+int dl_fcsm_match_3dof(dl_context* ctx, const dl_fcsm_options* o, const double* guess, const float* hi_pts, int64_t n_hi,
+                       const float* lo_pts, int64_t n_lo, const dl_grid* hi, const dl_grid* lo, float min_score,
+                       dl_fcsm_result* result) {
+  if (!ctx || !o || !result || n_hi < 0 || n_lo < 0) return DL_ERR_ARG;
+  const int64_t hi_off[2] = {0, n_hi}, lo_off[2] = {0, n_lo};
+  if (guess && hi && lo && (n_hi == 0 || n_lo == 0)) return ctx->fail(DL_ERR_EMPTY, "empty point cloud");
+  DL_TRY(check_pairs(ctx, 1, guess, hi_pts, hi_off, lo_pts, lo_off, &hi, &lo));
+  DL_TRY(check_fcsm_options(ctx, *o));
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  DL_TRY(ctx->reserve_device(coarse_bytes(n_hi, n_lo, 1)));
+  Arena a(ctx->d_scratch);
+  CoarseSearch cs;
+  DL_TRY(coarse_search(ctx, a, *o, min_score, 0, 1, guess, hi_pts, hi_off, lo_pts, lo_off, &hi, &lo, nullptr, &cs));
+  FcsmPick pick;
+  DL_TRY(d2h(ctx, &pick, cs.d_picks, 1));
+  DL_TRY(sync(ctx));
+  std::memset(result, 0, sizeof(*result));
+  result->num_candidates = pick.num_candidates;
+  if (!pick.found) return DL_OK;  // nothing above min_score passes the low-resolution gate: the reference returns nullptr
+  result->found = 1;
+  result->score = pick.score;
+  std::memcpy(result->pose_estimate, pick.pose, sizeof(pick.pose));
+  result->rotational_score = (float)(o->min_rotational_score + 0.01);  // what MatchWith3DofInitial reports (cc:179-181)
+  result->low_resolution_score = pick.low_resolution_score;
+  std::memcpy(result->offset, pick.offset, sizeof(pick.offset));
+  return DL_OK;
+}
+
+int dl_constraint_search_batch(dl_context* ctx, const dl_constraint_options* options, int32_t count, const double* guesses,
+                               const float* hi_pts, const int64_t* hi_off, const float* lo_pts, const int64_t* lo_off,
+                               const dl_grid* const* hi_grids, const dl_grid* const* lo_grids, dl_constraint* constraints) {
+  if (!ctx || !options || count < 0) return DL_ERR_ARG;
+  if (count == 0) return DL_OK;
+  if (!constraints) return DL_ERR_ARG;
+  DL_TRY(check_pairs(ctx, count, guesses, hi_pts, hi_off, lo_pts, lo_off, hi_grids, lo_grids));
+  DL_TRY(check_fcsm_options(ctx, options->fast_correlative_scan_matcher_3d));
+  DL_TRY(check_ceres_options(ctx, &options->ceres_scan_matcher_3d, 2));
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  const NlsOptions nls = to_nls_options(options->ceres_scan_matcher_3d, 2);
+  constexpr int kChunk = 1024;  // pairs per launch set: bounds the scratch, keeps every grid dimension legal
+  for (int first = 0; first < count; first += kChunk) {
+    const int n = std::min(kChunk, count - first);
+    const int64_t n_hi = hi_off[first + n] - hi_off[first], n_lo = lo_off[first + n] - lo_off[first];
+    DL_TRY(ctx->reserve_device(coarse_bytes(n_hi, n_lo, n) + arena_bytes({(size_t)n * sizeof(NlsProblem), (size_t)n * sizeof(NlsOutput)})));
+    Arena a(ctx->d_scratch);
+    CoarseSearch cs;
+    DL_TRY(coarse_search(ctx, a, options->fast_correlative_scan_matcher_3d, (float)options->min_score, first, n, guesses, hi_pts,
+                         hi_off, lo_pts, lo_off, hi_grids, lo_grids, nullptr, &cs));
+    // refinement: initial pose = translation target = the coarse pose, read from the pick record on the device
+    std::vector<NlsProblem> problems(n);
+    for (int k = 0; k < n; ++k) {
+      const int g = first + k;
+      NlsProblem& p = problems[k];
+      std::memset(&p, 0, sizeof(p));
+      p.cloud[0] = cs.d_hi + 3 * (hi_off[g] - hi_off[first]);
+      p.cloud[1] = cs.d_lo + 3 * (lo_off[g] - lo_off[first]);
+      p.count[0] = (int32_t)(hi_off[g + 1] - hi_off[g]);
+      p.count[1] = (int32_t)(lo_off[g + 1] - lo_off[g]);
+      p.grid[0] = hi_grids[g]->view();
+      p.grid[1] = lo_grids[g]->view();
+      p.initial_dev = cs.d_picks[k].pose;  // address arithmetic only
+      p.enabled_dev = &cs.d_picks[k].found;
+    }
+    NlsProblem* d_problems = a.take<NlsProblem>(n);
+    NlsOutput* d_out = a.take<NlsOutput>(n);
+    DL_TRY(h2d(ctx, d_problems, problems.data(), n));
+    DL_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(NlsOutput) * n, ctx->stream));
+    DL_TRY(launch_nls(ctx, nls, d_problems, n, d_out));
+    std::vector<FcsmPick> picks(n);
+    std::vector<NlsOutput> out(n);
+    DL_TRY(d2h(ctx, picks.data(), cs.d_picks, n));
+    DL_TRY(d2h(ctx, out.data(), d_out, n));
+    DL_TRY(sync(ctx));
+    for (int k = 0; k < n; ++k) {
+      dl_constraint& c = constraints[first + k];
+      std::memset(&c, 0, sizeof(c));
+      std::memcpy(c.coarse_pose, picks[k].pose, sizeof(c.coarse_pose));
+      if (!picks[k].found) continue;
+      c.found = 1;
+      c.score = picks[k].score;
+      c.rotational_score = (float)(options->fast_correlative_scan_matcher_3d.min_rotational_score + 0.01);
+      c.low_resolution_score = picks[k].low_resolution_score;
+      std::memcpy(c.pose, out[k].pose, sizeof(c.pose));
+      c.translation_weight = options->loop_closure_translation_weight;
+      c.rotation_weight = options->loop_closure_rotation_weight;
+      c.summary = out[k].summary;
+    }
+  }
+  return DL_OK;
+}
+
+}  // extern "C"
+
 namespace {
 struct HostImuTerm {  // must match ImuTerm in dl_nls.cu
   double pi[3], qi[4], vi[3], bai[3], bgi[3];

@@ -21,102 +21,194 @@ namespace {
 constexpr int kBlock = 128;
 constexpr int kTile = 1024;
 
-__global__ void fcsm_cells_kernel(const float* __restrict__ points, int n, Rigidf pose, float resolution, int* __restrict__ cells) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const Int3 c = cell_index(apply(pose, Vec3f{points[3 * i], points[3 * i + 1], points[3 * i + 2]}), resolution);
-  cells[3 * i] = c.x; cells[3 * i + 1] = c.y; cells[3 * i + 2] = c.z;
+// GetPoseFromCandidate: Translation(resolution * offset) * discrete_scan.pose (cc:423-430); Rigid3 * Rigid3 re-normalises
+__device__ __forceinline__ Rigidf candidate_pose(const Rigidf& pose, float res, int ox, int oy, int oz) {
+  return compose(Rigidf{{res * (float)ox, res * (float)oy, res * (float)oz}, {1.f, 0.f, 0.f, 0.f}}, pose);
 }
 
-// ConvertToPrecomputationGrid's per-cell expression
+// ConvertToPrecomputationGrid's per-cell expression (precomputation_grid_3d.cc:50-53)
 __device__ __forceinline__ int precomputation_value(uint16_t v) {
   const float kMin = 0.1f, kMax = 1.f - 0.1f;
   return round_to_int((value_to_probability(v) - kMin) * (255.f / (kMax - kMin)));
 }
 
-__global__ void __launch_bounds__(kBlock) fcsm_score_kernel(GridView grid, const int* __restrict__ cells, int n, int wxy,
-                                                            int wz, float* __restrict__ scores) {
-  __shared__ int tile[kTile * 3];
-  const int side = 2 * wxy + 1;
-  const long long K = (long long)side * side * (2 * wz + 1);
-  const long long idx = (long long)blockIdx.x * kBlock + threadIdx.x;
-  const bool active = idx < K;
-  const int ox = active ? (int)(idx % side) - wxy : 0;
-  const int oy = active ? (int)((idx / side) % side) - wxy : 0;
-  const int oz = active ? (int)(idx / ((long long)side * side)) - wz : 0;
-  int sum = 0;
-  for (int base = 0; base < n; base += kTile) {
-    const int count = min(kTile, n - base);
-    __syncthreads();
-    for (int j = threadIdx.x; j < count * 3; j += kBlock) tile[j] = cells[base * 3 + j];
-    __syncthreads();
-    if (active)
-      for (int j = 0; j < count; ++j)
-        sum += precomputation_value(grid_value(grid, tile[3 * j] + ox, tile[3 * j + 1] + oy, tile[3 * j + 2] + oz));
+// DiscretizeScan at full resolution (cc:253-266) + the candidate-independent half of the low-resolution match: every
+// candidate pose shares the rotation, so R * p is formed once per point and a candidate only adds its translation.
+__global__ void fcsm_prepare_kernel(const FcsmPair* __restrict__ pairs) {
+  const FcsmPair& pr = pairs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < pr.n_hi) {
+    const Int3 c = cell_index(apply(pr.pose, Vec3f{pr.hi_pts[3 * i], pr.hi_pts[3 * i + 1], pr.hi_pts[3 * i + 2]}), pr.hi.resolution);
+    pr.cells[3 * i] = c.x; pr.cells[3 * i + 1] = c.y; pr.cells[3 * i + 2] = c.z;
   }
-  if (active) {
-    const float kMin = 0.1f, kMax = 1.f - 0.1f;
-    scores[idx] = kMin + ((float)sum / (float)n) * ((kMax - kMin) / 255.f);  // PrecomputationGrid3D::ToProbability(sum / float(n))
+  if (i < pr.n_lo) {
+    const Quatf q = candidate_pose(pr.pose, pr.hi.resolution, 0, 0, 0).q;
+    const Vec3f r = rotate(q, Vec3f{pr.lo_pts[3 * i], pr.lo_pts[3 * i + 1], pr.lo_pts[3 * i + 2]});
+    pr.lo_rot[3 * i] = r.x; pr.lo_rot[3 * i + 1] = r.y; pr.lo_rot[3 * i + 2] = r.z;
   }
 }
 
-__global__ void fcsm_argmax_kernel(const float* __restrict__ scores, long long K, float min_score, unsigned long long* best) {
-  unsigned long long packed = 0ull;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < K; i += (long long)gridDim.x * blockDim.x) {
-    const float s = scores[i];
-    if (s > min_score && s > 0.f) {
-      const unsigned long long p = ((unsigned long long)__float_as_uint(s) << 32) | (0xFFFFFFFFull - (unsigned long long)i);
-      packed = p > packed ? p : packed;
+// Brick row (8 voxels along x, 16 bytes, 16-byte aligned) that holds shifted cell (sx, sy, sz), or nullptr when the
+// cell is outside the grid or its brick was never allocated (HybridGrid::value() -> 0 in both cases).
+__device__ __forceinline__ const uint4* brick_row(const GridView& g, int sx, int sy, int sz) {
+  const int gs = 64 << g.bits;
+  if ((unsigned)sx >= (unsigned)gs || (unsigned)sy >= (unsigned)gs || (unsigned)sz >= (unsigned)gs) return nullptr;
+  const int node = __ldg(g.top + ((((sz >> 6) << g.bits) + (sy >> 6)) << g.bits) + (sx >> 6));
+  if (node < 0) return nullptr;
+  const int brick = __ldg(g.nodes + (size_t)node * 512 + ((((sz >> 3) & 7) << 6) | (((sy >> 3) & 7) << 3) | ((sx >> 3) & 7)));
+  if (brick < 0) return nullptr;
+  return reinterpret_cast<const uint4*>(g.bricks + (size_t)brick * 512 + (((sz & 7) << 6) | ((sy & 7) << 3)));
+}
+
+constexpr int kRun = 8;  // leaves per thread: one brick-row-aligned span of x offsets
+
+template <int A>
+__device__ __forceinline__ void add_run(const uint4& r0, const uint4& r1, int (&sum)[kRun]) {
+  const unsigned w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+  for (int k = 0; k < kRun; ++k) {
+    const int e = A + k;
+    const unsigned v = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xFFFFu);
+    if (v) sum[k] += precomputation_value((uint16_t)v);
+  }
+}
+
+// One thread per run of 8 consecutive x offsets of the translation window (one (y, z) offset): for every
+// high-resolution cell the 8 leaves read 8 consecutive voxels = at most two 16-byte brick rows, so the three-level
+// walk is paid twice per point instead of eight times and the values arrive as 128-bit loads. The phase of the run
+// inside a brick row depends on the point only (runs start 8 apart), i.e. it is uniform across the block.
+// Integer correlation sums -> score; only leaves above min_score run the low-resolution gate
+// (low_resolution_matcher.cc:24-36: float sum in point order); one packed atomicMax per warp.
+__global__ void __launch_bounds__(kBlock) fcsm_search_kernel(const FcsmPair* __restrict__ pairs, unsigned long long* __restrict__ best,
+                                                             float* __restrict__ all_scores) {
+  __shared__ int tile[kTile * 3];
+  const FcsmPair& pr = pairs[blockIdx.y];
+  const int side = 2 * pr.wxy + 1;
+  const int runs = (side + kRun - 1) / kRun;
+  const int rows = side * (2 * pr.wz + 1);
+  if ((long long)blockIdx.x * kBlock >= (long long)rows * runs) return;
+  const int tid = blockIdx.x * kBlock + threadIdx.x;
+  const bool active = tid < rows * runs;
+  const int run = active ? tid % runs : 0, row = active ? tid / runs : 0;
+  const int ox0 = -pr.wxy + kRun * run, oy = row % side - pr.wxy, oz = row / side - pr.wz;
+  const int half = (64 << pr.hi.bits) >> 1;
+  int sum[kRun] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int base = 0; base < pr.n_hi; base += kTile) {
+    const int count = min(kTile, pr.n_hi - base);
+    __syncthreads();
+    for (int j = threadIdx.x; j < count * 3; j += kBlock) tile[j] = pr.cells[base * 3 + j];
+    __syncthreads();
+    if (active)
+      for (int j = 0; j < count; ++j) {
+        const int sx = tile[3 * j] + ox0 + half, sy = tile[3 * j + 1] + oy + half, sz = tile[3 * j + 2] + oz + half;
+        const int phase = sx & 7;  // block-uniform
+        const uint4* p0 = brick_row(pr.hi, sx - phase, sy, sz);
+        const uint4* p1 = phase ? brick_row(pr.hi, sx - phase + 8, sy, sz) : nullptr;
+        if (!p0 && !p1) continue;
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        const uint4 r0 = p0 ? __ldg(p0) : zero, r1 = p1 ? __ldg(p1) : zero;
+        switch (phase) {
+          case 0: add_run<0>(r0, r1, sum); break;
+          case 1: add_run<1>(r0, r1, sum); break;
+          case 2: add_run<2>(r0, r1, sum); break;
+          case 3: add_run<3>(r0, r1, sum); break;
+          case 4: add_run<4>(r0, r1, sum); break;
+          case 5: add_run<5>(r0, r1, sum); break;
+          case 6: add_run<6>(r0, r1, sum); break;
+          default: add_run<7>(r0, r1, sum); break;
+        }
+      }
+  }
+  const float kMin = 0.1f, kMax = 1.f - 0.1f;
+  float score[kRun];
+  unsigned cand = 0;
+#pragma unroll
+  for (int k = 0; k < kRun; ++k) {
+    score[k] = kMin + ((float)sum[k] / (float)pr.n_hi) * ((kMax - kMin) / 255.f);  // ToProbability(sum / float(n))
+    const bool leaf = active && ox0 + k <= pr.wxy;
+    if (leaf && all_scores) all_scores[((long long)row * side) + (ox0 + k + pr.wxy)] = score[k];
+    if (leaf && score[k] > pr.min_score) cand |= 1u << k;
+  }
+  float low[kRun] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float* ftile = reinterpret_cast<float*>(tile);
+  const bool any = __syncthreads_or(cand != 0);
+  if (!any) return;
+  for (int base = 0; base < pr.n_lo; base += kTile) {
+    const int count = min(kTile, pr.n_lo - base);
+    __syncthreads();
+    for (int j = threadIdx.x; j < count * 3; j += kBlock) ftile[j] = pr.lo_rot[base * 3 + j];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kRun; ++k) {
+      if (!(cand >> k & 1)) continue;
+      const Vec3f t = candidate_pose(pr.pose, pr.hi.resolution, ox0 + k, oy, oz).t;
+      float acc = low[k];
+      for (int j = 0; j < count; ++j) {
+        const Int3 c = cell_index(add(Vec3f{ftile[3 * j], ftile[3 * j + 1], ftile[3 * j + 2]}, t), pr.lo.resolution);
+        acc += value_to_probability(grid_value(pr.lo, c.x, c.y, c.z));
+      }
+      low[k] = acc;
     }
+  }
+  unsigned long long packed = 0ull;
+#pragma unroll
+  for (int k = 0; k < kRun; ++k) {
+    if (!(cand >> k & 1) || !((double)(low[k] / (float)pr.n_lo) >= pr.min_low)) continue;
+    const unsigned long long idx = (unsigned long long)row * side + (ox0 + k + pr.wxy);
+    const unsigned long long p = ((unsigned long long)__float_as_uint(score[k]) << 32) | (0xFFFFFFFFull - idx);
+    packed = p > packed ? p : packed;
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
     const unsigned long long o = __shfl_xor_sync(0xffffffffu, packed, d);
     packed = o > packed ? o : packed;
   }
-  if ((threadIdx.x & 31) == 0 && packed) atomicMax(best, packed);
+  if ((threadIdx.x & 31) == 0 && packed) atomicMax(best + blockIdx.y, packed);
 }
 
-// low_resolution_matcher: mean nearest-voxel probability, float sum in point order (one thread: the order matters)
-__global__ void fcsm_gate_kernel(GridView lo, const float* __restrict__ points, int n, Rigidf pose, float* out) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  float score = 0.f;
-  for (int i = 0; i < n; ++i) {
-    const Int3 c = cell_index(apply(pose, Vec3f{points[3 * i], points[3 * i + 1], points[3 * i + 2]}), lo.resolution);
-    score += value_to_probability(grid_value(lo, c.x, c.y, c.z));
+// Decode the winner of each pair: Result{score, pose_estimate, rotational_score, low_resolution_score} (cc:186-195) and the
+// switch + initial pose the refinement kernel reads.
+__global__ void fcsm_finish_kernel(const FcsmPair* __restrict__ pairs, const unsigned long long* __restrict__ best, int count,
+                                   FcsmPick* __restrict__ picks) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= count) return;
+  const FcsmPair& pr = pairs[p];
+  FcsmPick out{};
+  const int side = 2 * pr.wxy + 1;
+  out.num_candidates = (long long)side * side * (2 * pr.wz + 1);
+  const unsigned long long b = best[p];
+  Rigidf pose = pr.pose;
+  if (b) {
+    const long long idx = (long long)(0xFFFFFFFFull - (b & 0xFFFFFFFFull));
+    out.found = 1;
+    out.score = __uint_as_float((unsigned)(b >> 32));
+    out.offset[0] = (int)(idx % side) - pr.wxy;
+    out.offset[1] = (int)((idx / side) % side) - pr.wxy;
+    out.offset[2] = (int)(idx / ((long long)side * side)) - pr.wz;
+    pose = candidate_pose(pr.pose, pr.hi.resolution, out.offset[0], out.offset[1], out.offset[2]);
+    float low = 0.f;
+    for (int j = 0; j < pr.n_lo; ++j) {
+      const Int3 c = cell_index(add(Vec3f{pr.lo_rot[3 * j], pr.lo_rot[3 * j + 1], pr.lo_rot[3 * j + 2]}, pose.t), pr.lo.resolution);
+      low += value_to_probability(grid_value(pr.lo, c.x, c.y, c.z));
+    }
+    out.low_resolution_score = low / (float)pr.n_lo;
   }
-  *out = score / (float)n;
+  pose_to7(to_double(pose), out.pose);
+  picks[p] = out;
 }
-
-__global__ void fcsm_reject_kernel(float* scores, long long idx) { scores[idx] = -1.f; }
 
 }  // namespace
 
-int launch_fcsm_cells(dl_context* ctx, const float* points, int n, const Rigidf& pose, float resolution, int* cells) {
-  fcsm_cells_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(points, n, pose, resolution, cells);
-  DL_LAUNCH_CHECK(ctx, "fcsm_cells_kernel");
-  return DL_OK;
-}
-int launch_fcsm_scores(dl_context* ctx, const GridView& grid, const int* cells, int n, int wxy, int wz, float* scores) {
-  const long long side = 2 * wxy + 1, K = side * side * (2 * wz + 1);
-  fcsm_score_kernel<<<(unsigned)((K + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(grid, cells, n, wxy, wz, scores);
-  DL_LAUNCH_CHECK(ctx, "fcsm_score_kernel");
-  return DL_OK;
-}
-int launch_fcsm_argmax(dl_context* ctx, const float* scores, long long K, float min_score, unsigned long long* best) {
-  DL_CUDA(ctx, cudaMemsetAsync(best, 0, sizeof(unsigned long long), ctx->stream));
-  fcsm_argmax_kernel<<<(unsigned)std::min<long long>(kNumSMs * 4, (K + 255) / 256), 256, 0, ctx->stream>>>(scores, K, min_score, best);
-  DL_LAUNCH_CHECK(ctx, "fcsm_argmax_kernel");
-  return DL_OK;
-}
-int launch_fcsm_gate(dl_context* ctx, const GridView& lo, const float* points, int n, const Rigidf& pose, float* out) {
-  fcsm_gate_kernel<<<1, 32, 0, ctx->stream>>>(lo, points, n, pose, out);
-  DL_LAUNCH_CHECK(ctx, "fcsm_gate_kernel");
-  return DL_OK;
-}
-int launch_fcsm_reject(dl_context* ctx, float* scores, long long idx) {
-  fcsm_reject_kernel<<<1, 1, 0, ctx->stream>>>(scores, idx);
-  DL_LAUNCH_CHECK(ctx, "fcsm_reject_kernel");
+int launch_fcsm(dl_context* ctx, const FcsmPair* pairs_dev, int count, int max_points, long long max_threads,
+                unsigned long long* best_dev, FcsmPick* picks_dev, float* all_scores_dev) {
+  DL_CUDA(ctx, cudaMemsetAsync(best_dev, 0, sizeof(unsigned long long) * count, ctx->stream));
+  fcsm_prepare_kernel<<<dim3((max_points + 255) / 256, count), 256, 0, ctx->stream>>>(pairs_dev);
+  DL_LAUNCH_CHECK(ctx, "fcsm_prepare_kernel");
+  fcsm_search_kernel<<<dim3((unsigned)((max_threads + kBlock - 1) / kBlock), count), kBlock, 0, ctx->stream>>>(pairs_dev, best_dev,
+                                                                                                           all_scores_dev);
+  DL_LAUNCH_CHECK(ctx, "fcsm_search_kernel");
+  fcsm_finish_kernel<<<(count + 63) / 64, 64, 0, ctx->stream>>>(pairs_dev, best_dev, count, picks_dev);
+  DL_LAUNCH_CHECK(ctx, "fcsm_finish_kernel");
   return DL_OK;
 }
 

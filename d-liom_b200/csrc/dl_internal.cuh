@@ -203,6 +203,7 @@ struct NlsProblem {  // one scan-to-submap registration problem, device pointers
   const double* initial_dev;  // optional: 7 doubles on the device override `initial` (and target_t = its translation
                               // unless target_dev is set)
   const double* target_dev;
+  const int32_t* enabled_dev;  // optional: the problem is skipped (output untouched) when *enabled_dev == 0
 };
 struct NlsOptions {
   int num_pairs;
@@ -227,11 +228,28 @@ int launch_nls_normal_equations(dl_context* ctx, const NlsOptions& opt, const Nl
                                 const double* at_pose_dev, double* out28_dev);
 int launch_imu_preintegrate(dl_context* ctx, int count, const int32_t* offsets, const double* dts, const double* accs,
                             const double* gyrs, const double* biases, const dl_imu_noise& noise, dl_preintegration* out);
-int launch_fcsm_cells(dl_context* ctx, const float* points, int n, const Rigidf& pose, float resolution, int* cells);
-int launch_fcsm_scores(dl_context* ctx, const GridView& grid, const int* cells, int n, int wxy, int wz, float* scores);
-int launch_fcsm_argmax(dl_context* ctx, const float* scores, long long K, float min_score, unsigned long long* best);
-int launch_fcsm_gate(dl_context* ctx, const GridView& lo, const float* points, int n, const Rigidf& pose, float* out);
-int launch_fcsm_reject(dl_context* ctx, float* scores, long long idx);
+struct FcsmPair {  // one (node, submap) loop-closure search, device pointers
+  GridView hi, lo;
+  const float* hi_pts;
+  const float* lo_pts;
+  int* cells;      // 3 * n_hi: full-resolution cell of every high-resolution point at the guess
+  float* lo_rot;   // 3 * n_lo: rotated low-resolution points
+  int n_hi, n_lo;
+  Rigidf pose;     // float cast of the pose guess (cc:171-173)
+  int wxy, wz;     // window half-widths in cells
+  float min_score;
+  double min_low;
+};
+struct FcsmPick {
+  int found;
+  float score, low_resolution_score;
+  int offset[3];
+  long long num_candidates;
+  double pose[7];  // coarse pose (the guess itself when nothing was found)
+};
+constexpr int kFcsmRun = 8;  // x offsets per search thread (dl_fcsm.cu)
+int launch_fcsm(dl_context* ctx, const FcsmPair* pairs_dev, int count, int max_points, long long max_threads,
+                unsigned long long* best_dev, FcsmPick* picks_dev, float* all_scores_dev);
 void compute_odds_table(float probability, uint16_t* table32768);
 int grid_insert_device(dl_context* ctx, dl_grid* g, const Vec3f& origin, const float* d_returns, int n, int num_free,
                        const uint16_t* d_hit_table, const uint16_t* d_miss_table, int32_t* d_bbox, uint32_t* d_update_list);

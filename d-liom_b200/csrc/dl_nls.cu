@@ -681,6 +681,7 @@ __device__ __forceinline__ void solve_body(const NlsOptions& opt, const NlsProbl
 __global__ void __launch_bounds__(kBlock) nls_solve_kernel(NlsOptions opt, const NlsProblem* __restrict__ problems,
                                                            NlsOutput* __restrict__ outputs) {
   NlsOutput& o = outputs[blockIdx.x];
+  if (problems[blockIdx.x].enabled_dev && *problems[blockIdx.x].enabled_dev == 0) return;  // block-uniform
   solve_body<false>(opt, problems[blockIdx.x], nullptr, nullptr, o.pose, &o.summary);
 }
 

@@ -24,7 +24,7 @@ EXPORTS = [
     "dl_context_stream", "dl_context_synchronize", "dl_context_set_profiling", "dl_context_read_profile", "dl_grid_create", "dl_grid_destroy", "dl_grid_set_cells",
     "dl_grid_sync", "dl_grid_resolution", "dl_grid_num_bricks", "dl_grid_lookup", "dl_grid_interpolate",
     "dl_grid_insert_range_data", "dl_submap_insert_range_data", "dl_grid_export_cells",
-    "dl_voxel_filter", "dl_voxel_indices", "dl_adaptive_voxel_filter", "dl_rtcsm_match", "dl_fcsm_match_3dof", "dl_ceres_match",
+    "dl_voxel_filter", "dl_voxel_indices", "dl_adaptive_voxel_filter", "dl_rtcsm_match", "dl_fcsm_match_3dof", "dl_constraint_search_batch", "dl_ceres_match",
     "dl_ceres_match_batch", "dl_ceres_normal_equations", "dl_imu_preintegrate", "dl_imu_predict", "dl_fused_match_batch", "dl_ingest_scan", "dl_frontend_match_batch",
     "dl_frontend_match_batch_dev", "dl_frontend_fetch_results", "dl_device_alloc", "dl_device_free",
     "dl_copy_to_device", "dl_copy_to_host",
@@ -123,6 +123,30 @@ class SolveSummary(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+class ConstraintOptions(C.Structure):
+    _fields_ = [("min_score", C.c_double), ("loop_closure_translation_weight", C.c_double),
+                ("loop_closure_rotation_weight", C.c_double), ("fast_correlative_scan_matcher_3d", FcsmOptions),
+                ("ceres_scan_matcher_3d", CeresOptions)]
+
+    @staticmethod
+    def defaults(**kw):
+        """constraint_builder block of configuration_files/pose_graph.lua:17-73."""
+        o = ConstraintOptions()
+        o.min_score = kw.pop("min_score", 0.55)
+        o.loop_closure_translation_weight, o.loop_closure_rotation_weight = 1.1e4, 1e5
+        o.fast_correlative_scan_matcher_3d = FcsmOptions(8, 3, 0.77, kw.pop("min_low_resolution_score", 0.55),
+                                                         kw.pop("xy_window", 5.0), kw.pop("z_window", 1.0), 0.2617993877991494)
+        o.ceres_scan_matcher_3d = CeresOptions.make([5.0, 30.0], 10.0, 1.0, False, False, 10)
+        assert not kw, kw
+        return o
+
+
+class Constraint(C.Structure):
+    _fields_ = [("found", C.c_int32), ("score", C.c_float), ("rotational_score", C.c_float),
+                ("low_resolution_score", C.c_float), ("coarse_pose", C.c_double * 7), ("pose", C.c_double * 7),
+                ("translation_weight", C.c_double), ("rotation_weight", C.c_double), ("summary", SolveSummary)]
+
+
 class FrontendOptions(C.Structure):
     _fields_ = [("min_range", C.c_float), ("max_range", C.c_float), ("voxel_filter_size", C.c_float),
                 ("high_resolution_adaptive_voxel_filter", AdaptiveVoxelFilterOptions),
@@ -202,6 +226,8 @@ def lib():
     L.dl_rtcsm_match.argtypes = [vp, ip(RtcsmOptions), f64p, f32p, C.c_int64, vp, f64p, ip(C.c_float), ip(RtcsmInfo), vp]
     L.dl_fcsm_match_3dof.argtypes = [vp, ip(FcsmOptions), f64p, f32p, C.c_int64, f32p, C.c_int64, vp, vp, C.c_float,
                                      ip(FcsmResult)]
+    L.dl_constraint_search_batch.argtypes = [vp, ip(ConstraintOptions), C.c_int32, f64p, f32p, i64p, f32p, i64p, C.c_void_p,
+                                             C.c_void_p, ip(Constraint)]
     L.dl_ceres_match.argtypes = [vp, ip(CeresOptions), f64p, f64p, C.c_int32, ip(vp), i64p, ip(vp), f64p,
                                  ip(SolveSummary)]
     L.dl_ceres_match_batch.argtypes = [vp, ip(CeresOptions), C.c_int32, C.c_int32, f64p, f64p, ip(vp), i64p, ip(vp),
@@ -333,6 +359,23 @@ class Context:
                                              len(hi_points), lo_points, len(lo_points), hi_grid.h, lo_grid.h,
                                              np.float32(min_score), C.byref(r)))
         return r
+
+    def constraint_search_batch(self, options, pose_guesses, hi_clouds, lo_clouds, hi_grids, lo_grids):
+        """ConstraintBuilder3D::ComputeConstraint for len(pose_guesses) (node, submap) pairs -> list of Constraint."""
+        count = len(pose_guesses)
+        his = [np.ascontiguousarray(c, np.float32).reshape(-1, 3) for c in hi_clouds]
+        los = [np.ascontiguousarray(c, np.float32).reshape(-1, 3) for c in lo_clouds]
+        hi_off = np.concatenate([[0], np.cumsum([len(c) for c in his])]).astype(np.int64)
+        lo_off = np.concatenate([[0], np.cumsum([len(c) for c in los])]).astype(np.int64)
+        hi_all = np.ascontiguousarray(np.concatenate(his) if count else np.zeros((1, 3), np.float32))
+        lo_all = np.ascontiguousarray(np.concatenate(los) if count else np.zeros((1, 3), np.float32))
+        hg = (C.c_void_p * max(count, 1))(*[g.h for g in hi_grids])
+        lg = (C.c_void_p * max(count, 1))(*[g.h for g in lo_grids])
+        out = (Constraint * max(count, 1))()
+        self.check(self.L.dl_constraint_search_batch(self.h, C.byref(options), count,
+                                                     np.ascontiguousarray(pose_guesses, np.float64).reshape(-1, 7), hi_all,
+                                                     hi_off, lo_all, lo_off, hg, lg, out))
+        return list(out)[:count]
 
     @staticmethod
     def _pairs(clouds, grids):

@@ -36,3 +36,36 @@ def gather_results(dist, local_rows, device=None):
     out = [torch.zeros_like(padded) for _ in range(world)]
     dist.all_gather(out, padded)
     return [o[:int(c[0])].cpu().numpy() for o, c in zip(out, counts)]
+
+
+# ---- loop closure (BASELINE configs[3]/[4]): (node, submap) searches are sharded by SUBMAP OWNER so that every
+# grid is resident on exactly one GPU; the only exchange step is the all-gather of the constraint records every rank
+# needs for the (replicated, host-side) pose graph — ncclAllGather over NVLink on the GPU box, gloo in the CPU tests.
+CONSTRAINT_COLUMNS = ("submap_id", "node_id", "score", "low_resolution_score", "x", "y", "z", "qw", "qx", "qy", "qz",
+                      "translation_weight", "rotation_weight")
+
+
+def owner_of_submap(submap_id, world):
+    return int(submap_id) % world
+
+
+def shard_by_owner(submap_ids, rank, world):
+    """Indices of the pairs this rank searches: those whose submap it owns. Order preserved."""
+    return [i for i, s in enumerate(submap_ids) if owner_of_submap(s, world) == rank]
+
+
+def constraint_rows(submap_ids, node_ids, constraints):
+    """Found constraints (dliom.Constraint or anything with the same attributes) -> float64 rows in CONSTRAINT_COLUMNS
+    order; pruned pairs produce no row, exactly like ComputeConstraint leaving *constraint null."""
+    import numpy as np
+    rows = [[s, n, c.score, c.low_resolution_score, *c.pose[:], c.translation_weight, c.rotation_weight]
+            for s, n, c in zip(submap_ids, node_ids, constraints) if c.found]
+    return np.array(rows, np.float64).reshape(-1, len(CONSTRAINT_COLUMNS))
+
+
+def all_gather_constraints(dist, local_rows, device=None):
+    """Every rank ends up with the same, canonically ordered (submap_id, node_id) constraint table."""
+    import numpy as np
+    rows = np.concatenate(gather_results(dist, local_rows, device))
+    order = np.lexsort((rows[:, 1], rows[:, 0]))
+    return rows[order]

@@ -14,6 +14,7 @@
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <memory>
 #include <vector>
 
 #include "../../include/dliom_b200.h"
@@ -197,5 +198,133 @@ class CeresScanMatcher3D {  // ceres_scan_matcher_3d.h:41-61
   CeresScanMatcherOptions3D options_;
 };
 
+struct FastCorrelativeScanMatcherOptions3D {  // proto::FastCorrelativeScanMatcherOptions3D (pose_graph.lua:49-57)
+  int branch_and_bound_depth = 8, full_resolution_depth = 3;
+  double min_rotational_score = 0.77, min_low_resolution_score = 0.55;
+  double linear_xy_search_window = 5., linear_z_search_window = 1., angular_search_window = 0.2617993877991494;
+  dl_fcsm_options c() const {
+    return {branch_and_bound_depth, full_resolution_depth, min_rotational_score, min_low_resolution_score,
+            linear_xy_search_window, linear_z_search_window, angular_search_window};
+  }
+};
+
+// fast_correlative_scan_matcher_3d.h:59-160, the entry point this fork calls (MatchWith3DofInitial). The constructor takes
+// the two grids like the reference's; no precomputation stack is built — the device scores the whole window.
+class FastCorrelativeScanMatcher3D {
+ public:
+  struct Result {
+    float score;
+    Rigid3d pose_estimate;
+    float rotational_score;
+    float low_resolution_score;
+  };
+  FastCorrelativeScanMatcher3D(Context* ctx, const DeviceHybridGrid& hybrid_grid, const DeviceHybridGrid* low_resolution_hybrid_grid,
+                               const FastCorrelativeScanMatcherOptions3D& options)
+      : ctx_(ctx), hi_(&hybrid_grid), lo_(low_resolution_hybrid_grid), options_(options) {}
+  // nullptr when no leaf above min_score passes the low-resolution gate, like the reference.
+  std::unique_ptr<Result> MatchWith3DofInitial(const Rigid3d& pose_in_submap_guess, const PointCloud& high_resolution_point_cloud,
+                                               const PointCloud& low_resolution_point_cloud, float min_score) const {
+    const dl_fcsm_options o = options_.c();
+    double guess[7];
+    pose_in_submap_guess.to7(guess);
+    dl_fcsm_result r{};
+    ctx_->check(dl_fcsm_match_3dof(ctx_->get(), &o, guess,
+                                   high_resolution_point_cloud.empty() ? nullptr : high_resolution_point_cloud[0].data(),
+                                   (int64_t)high_resolution_point_cloud.size(),
+                                   low_resolution_point_cloud.empty() ? nullptr : low_resolution_point_cloud[0].data(),
+                                   (int64_t)low_resolution_point_cloud.size(), hi_->get(), lo_->get(), min_score, &r));
+    if (!r.found) return nullptr;
+    return std::unique_ptr<Result>(new Result{r.score, Rigid3d::from7(r.pose_estimate), r.rotational_score, r.low_resolution_score});
+  }
+ private:
+  Context* ctx_;
+  const DeviceHybridGrid* hi_;
+  const DeviceHybridGrid* lo_;
+  FastCorrelativeScanMatcherOptions3D options_;
+};
+
 }  // namespace scan_matching
+
+namespace constraints {
+
+struct ConstraintBuilderOptions {  // proto::ConstraintBuilderOptions, the fields ComputeConstraint reads (pose_graph.lua:17-73)
+  double min_score = 0.55;
+  double loop_closure_translation_weight = 1.1e4, loop_closure_rotation_weight = 1e5;
+  scan_matching::FastCorrelativeScanMatcherOptions3D fast_correlative_scan_matcher_options_3d;
+  scan_matching::CeresScanMatcherOptions3D ceres_scan_matcher_options_3d;
+  ConstraintBuilderOptions() {
+    ceres_scan_matcher_options_3d.occupied_space_weight = {5., 30.};
+    ceres_scan_matcher_options_3d.translation_weight = 10.;
+    ceres_scan_matcher_options_3d.rotation_weight = 1.;
+    ceres_scan_matcher_options_3d.max_num_iterations = 10;
+  }
+};
+
+struct Constraint {  // PoseGraphInterface::Constraint (INTER_SUBMAP)
+  int submap_index, node_index;
+  Rigid3d zbar_ij;
+  double translation_weight, rotation_weight;
+  float score, low_resolution_score;
+};
+
+// The compute half of ConstraintBuilder3D (constraint_builder_3d.cc:202-333): queue (node, submap) searches with
+// MaybeAddConstraint, then Compute() runs all of them in one device batch and returns the constraints found
+// (the reference schedules one thread-pool task per pair and collects them in RunWhenDoneCallback, :335-358).
+class ConstraintBuilder3D {
+ public:
+  ConstraintBuilder3D(Context* ctx, const ConstraintBuilderOptions& options) : ctx_(ctx), options_(options) {}
+  void MaybeAddConstraint(int submap_index, const DeviceHybridGrid* high_resolution_grid, const DeviceHybridGrid* low_resolution_grid,
+                          int node_index, const PointCloud& high_resolution_point_cloud,
+                          const PointCloud& low_resolution_point_cloud, const Rigid3d& node_pose_in_submap_guess) {
+    ids_.push_back({submap_index, node_index});
+    hi_grids_.push_back(high_resolution_grid->get());
+    lo_grids_.push_back(low_resolution_grid->get());
+    for (const auto& p : high_resolution_point_cloud) hi_.insert(hi_.end(), p.begin(), p.end());
+    for (const auto& p : low_resolution_point_cloud) lo_.insert(lo_.end(), p.begin(), p.end());
+    hi_off_.push_back((int64_t)hi_.size() / 3);
+    lo_off_.push_back((int64_t)lo_.size() / 3);
+    double g[7];
+    node_pose_in_submap_guess.to7(g);
+    guesses_.insert(guesses_.end(), g, g + 7);
+  }
+  int GetNumQueuedSearches() const { return (int)ids_.size(); }
+  std::vector<Constraint> Compute() {
+    dl_constraint_options o{};
+    o.min_score = options_.min_score;
+    o.loop_closure_translation_weight = options_.loop_closure_translation_weight;
+    o.loop_closure_rotation_weight = options_.loop_closure_rotation_weight;
+    o.fast_correlative_scan_matcher_3d = options_.fast_correlative_scan_matcher_options_3d.c();
+    const auto& c = options_.ceres_scan_matcher_options_3d;
+    o.ceres_scan_matcher_3d.num_occupied_space_weights = (int32_t)c.occupied_space_weight.size();
+    for (size_t i = 0; i < c.occupied_space_weight.size() && i < DL_MAX_PAIRS; ++i)
+      o.ceres_scan_matcher_3d.occupied_space_weight[i] = c.occupied_space_weight[i];
+    o.ceres_scan_matcher_3d.translation_weight = c.translation_weight;
+    o.ceres_scan_matcher_3d.rotation_weight = c.rotation_weight;
+    o.ceres_scan_matcher_3d.only_optimize_yaw = c.only_optimize_yaw;
+    o.ceres_scan_matcher_3d.use_nonmonotonic_steps = c.use_nonmonotonic_steps;
+    o.ceres_scan_matcher_3d.max_num_iterations = c.max_num_iterations;
+    o.ceres_scan_matcher_3d.num_threads = c.num_threads;
+    std::vector<dl_constraint> raw(ids_.size());
+    ctx_->check(dl_constraint_search_batch(ctx_->get(), &o, (int32_t)ids_.size(), guesses_.data(), hi_.data(), hi_off_.data(),
+                                           lo_.data(), lo_off_.data(), hi_grids_.data(), lo_grids_.data(), raw.data()));
+    std::vector<Constraint> out;
+    for (size_t k = 0; k < raw.size(); ++k)
+      if (raw[k].found)
+        out.push_back({ids_[k][0], ids_[k][1], Rigid3d::from7(raw[k].pose), raw[k].translation_weight, raw[k].rotation_weight,
+                       raw[k].score, raw[k].low_resolution_score});
+    ids_.clear(); hi_grids_.clear(); lo_grids_.clear(); hi_.clear(); lo_.clear(); guesses_.clear();
+    hi_off_.assign(1, 0); lo_off_.assign(1, 0);
+    return out;
+  }
+ private:
+  Context* ctx_;
+  ConstraintBuilderOptions options_;
+  std::vector<std::array<int, 2>> ids_;
+  std::vector<const dl_grid*> hi_grids_, lo_grids_;
+  std::vector<float> hi_, lo_;
+  std::vector<int64_t> hi_off_{0}, lo_off_{0};
+  std::vector<double> guesses_;
+};
+
+}  // namespace constraints
 }  // namespace dliom

@@ -37,7 +37,27 @@ int main() {
     const bool ok = summary.final_cost <= 1e-2 && std::fabs(pose.t[0] + 1.) < 3e-2 && std::fabs(pose.t[1]) < 3e-2;
     const PointCloud filtered = sensor::VoxelFilter(&ctx, 2.5f).Filter(cloud);
     std::printf("voxel filter kept %zu of %zu\n", filtered.size(), cloud.size());
-    return ok ? 0 : 1;
+    // loop closure: the same cloud against the same grid from a guess 2 cells off; window 3 m, min_score 0.5
+    constraints::ConstraintBuilderOptions cb;
+    cb.min_score = 0.5;
+    cb.fast_correlative_scan_matcher_options_3d.linear_xy_search_window = 3.;
+    cb.fast_correlative_scan_matcher_options_3d.linear_z_search_window = 3.;
+    cb.fast_correlative_scan_matcher_options_3d.min_low_resolution_score = 0.5;
+    constraints::ConstraintBuilder3D builder(&ctx, cb);
+    Rigid3d guess;
+    guess.t[0] = 1.; guess.t[1] = -1.;
+    builder.MaybeAddConstraint(/*submap*/ 3, &grid, &grid, /*node*/ 17, cloud, cloud, guess);
+    Rigid3d far;
+    far.t[0] = 40.;
+    builder.MaybeAddConstraint(3, &grid, &grid, 18, cloud, cloud, far);
+    const auto found = builder.Compute();
+    std::printf("constraints found %zu", found.size());
+    bool loop_ok = found.size() == 1 && found[0].node_index == 17 && std::fabs(found[0].zbar_ij.t[0] + 1.) < 0.1 &&
+                   std::fabs(found[0].zbar_ij.t[1]) < 0.1 && found[0].translation_weight == 1.1e4;
+    if (!found.empty()) std::printf("  node %d -> %.3f %.3f %.3f score %.3f", found[0].node_index, found[0].zbar_ij.t[0],
+                                    found[0].zbar_ij.t[1], found[0].zbar_ij.t[2], found[0].score);
+    std::printf("\n");
+    return ok && loop_ok ? 0 : 1;
   } catch (const Error& e) {
     std::fprintf(stderr, "dliom error %d: %s\n", e.status, e.what());
     return 2;

@@ -208,6 +208,38 @@ int dl_ceres_normal_equations(dl_context* ctx, const dl_ceres_options* options, 
                               const float* const* clouds, const int64_t* sizes, const dl_grid* const* grids,
                               double* cost, double* gradient6, double* hessian36);
 
+/* ---- constraints::ConstraintBuilder3D::ComputeConstraint from the point where the pose guess is known
+ *      (constraint_builder_3d.cc:261-333): coarse search (MatchWith3DofInitial, min_score prune) -> CeresScanMatcher3D::Match
+ *      with the coarse pose as both initial pose and translation target -> Constraint{pose, weights, INTER_SUBMAP}.
+ *      `count` independent (node, submap) pairs in one call, everything between the upload of the clouds and the download
+ *      of the records stays on the device. Options = proto::ConstraintBuilderOptions (the fields this function reads).
+ *      What stays on the host in the reference and here: SURF submap-to-submap matching and the frame bookkeeping that
+ *      produce `pose_guesses` (:217-259), the sampler and the id maps. ----------------------------------------------- */
+typedef struct dl_constraint_options {
+  double min_score;
+  double loop_closure_translation_weight;
+  double loop_closure_rotation_weight;
+  dl_fcsm_options fast_correlative_scan_matcher_3d;
+  dl_ceres_options ceres_scan_matcher_3d; /* two occupied-space weights: high, low resolution */
+} dl_constraint_options;
+typedef struct dl_constraint { /* PoseGraphInterface::Constraint + the three scores ComputeConstraint histograms */
+  int32_t found;               /* 0 <=> the reference leaves *constraint null */
+  float score;
+  float rotational_score;
+  float low_resolution_score;
+  double coarse_pose[7];       /* match_result->pose_estimate */
+  double pose[7];              /* constraint_transform: submap i <- node j */
+  double translation_weight;
+  double rotation_weight;
+  dl_solve_summary summary;
+} dl_constraint;
+/* Clouds are ragged: pair k uses points [offsets[k], offsets[k+1]) (xyz floats) of the high / low resolution arrays. */
+int dl_constraint_search_batch(dl_context* ctx, const dl_constraint_options* options, int32_t count,
+                               const double* pose_guesses, const float* high_resolution_points,
+                               const int64_t* high_offsets, const float* low_resolution_points,
+                               const int64_t* low_offsets, const dl_grid* const* high_resolution_grids,
+                               const dl_grid* const* low_resolution_grids, dl_constraint* constraints);
+
 /* ---- IMU: pre-integration (LocalTrajectoryBuilder3D::AddImuData, LTB:164-201, with the in-repo mid-point integrator
  *      C/mapping/internal/3d/initialization/integration_base.h:109-265 instead of the un-vendored GTSAM one) and the
  *      scan match with the pre-integration residual (integration_base.h:267-301) fused into the same solve.

@@ -133,6 +133,10 @@ def lib():
                                      f64p, f64p, C.c_void_p, C.c_void_p, C.c_int, f64p, i32p]
     L.orc_fcsm_match_3dof.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                       f64p, f32p, C.c_int64, f32p, C.c_int64, C.c_float, C.POINTER(FcsmResult)]
+    L.orc_fcsm_create.restype = C.c_void_p
+    L.orc_fcsm_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
+    L.orc_fcsm_destroy.argtypes = [C.c_void_p]
+    L.orc_fcsm_match.argtypes = [C.c_void_p, f64p, f32p, C.c_int64, f32p, C.c_int64, C.c_float, C.POINTER(FcsmResult)]
     L.orc_imu_preintegrate.argtypes = [f64p, f64p, f64p, C.c_int, f64p, f64p, f64p, C.POINTER(Preintegration)]
     L.orc_imu_predict.argtypes = [f64p, C.POINTER(Preintegration), f64p, f64p]
     L.orc_imu_residual.argtypes = [f64p, f64p, C.POINTER(Preintegration), f64p, f64p, C.c_void_p]
@@ -424,3 +428,27 @@ def fcsm_match_3dof(hi_grid, lo_grid, hi_points, lo_points, pose_guess, min_scor
                               xy_window, z_window, np.ascontiguousarray(pose_guess, np.float64), hi_points, len(hi_points),
                               lo_points, len(lo_points), np.float32(min_score), C.byref(r))
     return r
+
+
+class FastCorrelativeScanMatcher:
+    """Per-submap matcher object: the precomputation stack is built once (what the reference caches per finished submap);
+    match() may be called from several threads."""
+
+    def __init__(self, hi_grid, lo_grid, xy_window=5.0, z_window=1.0, min_low_resolution_score=0.55, min_rotational_score=0.77,
+                 depth=8, full_depth=3):
+        self.grids = (hi_grid, lo_grid)
+        self.h = lib().orc_fcsm_create(hi_grid.h, lo_grid.h, depth, full_depth, min_rotational_score, min_low_resolution_score,
+                                       xy_window, z_window)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_fcsm_destroy(self.h)
+            self.h = None
+
+    def match(self, hi_points, lo_points, pose_guess, min_score):
+        hi_points = np.ascontiguousarray(hi_points, np.float32).reshape(-1, 3)
+        lo_points = np.ascontiguousarray(lo_points, np.float32).reshape(-1, 3)
+        r = FcsmResult()
+        lib().orc_fcsm_match(self.h, np.ascontiguousarray(pose_guess, np.float64), hi_points, len(hi_points), lo_points,
+                             len(lo_points), np.float32(min_score), C.byref(r))
+        return r

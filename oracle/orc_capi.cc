@@ -139,14 +139,13 @@ struct OrcFcsmResult {
   int reserved;
   int64_t leaves_scored;
 };
-void orc_fcsm_match_3dof(void* hi, void* lo, int depth, int full_depth, double min_rot, double min_low, double wxy, double wz,
-                         const double* pose_guess, const float* hi_pts, int64_t n_hi, const float* lo_pts, int64_t n_lo,
-                         float min_score, OrcFcsmResult* out) {
+static FcsmOptions fcsm_options(int depth, int full_depth, double min_rot, double min_low, double wxy, double wz) {
   FcsmOptions o;
   o.branch_and_bound_depth = depth; o.full_resolution_depth = full_depth; o.min_rotational_score = min_rot;
   o.min_low_resolution_score = min_low; o.linear_xy_search_window = wxy; o.linear_z_search_window = wz;
-  FastCorrelativeScanMatcher m(*(HybridGrid*)hi, (const HybridGrid*)lo, o);
-  const FcsmResult r = m.MatchWith3DofInitial(pose_in(pose_guess), hi_pts, n_hi, lo_pts, n_lo, min_score);
+  return o;
+}
+static void fcsm_out(const FcsmResult& r, OrcFcsmResult* out) {
   std::memset(out, 0, sizeof(*out));
   out->found = r.found ? 1 : 0;
   out->score = r.score;
@@ -155,6 +154,21 @@ void orc_fcsm_match_3dof(void* hi, void* lo, int depth, int full_depth, double m
   out->low_resolution_score = r.low_resolution_score;
   out->offset[0] = r.offset.x; out->offset[1] = r.offset.y; out->offset[2] = r.offset.z;
   out->leaves_scored = r.leaves_scored;
+}
+// Matcher object = what ConstraintBuilder3D keeps per finished submap (precomputation stack built once).
+void* orc_fcsm_create(void* hi, void* lo, int depth, int full_depth, double min_rot, double min_low, double wxy, double wz) {
+  return new FastCorrelativeScanMatcher(*(HybridGrid*)hi, (const HybridGrid*)lo, fcsm_options(depth, full_depth, min_rot, min_low, wxy, wz));
+}
+void orc_fcsm_destroy(void* m) { delete (FastCorrelativeScanMatcher*)m; }
+void orc_fcsm_match(void* m, const double* pose_guess, const float* hi_pts, int64_t n_hi, const float* lo_pts, int64_t n_lo,
+                    float min_score, OrcFcsmResult* out) {
+  fcsm_out(((const FastCorrelativeScanMatcher*)m)->MatchWith3DofInitial(pose_in(pose_guess), hi_pts, n_hi, lo_pts, n_lo, min_score), out);
+}
+void orc_fcsm_match_3dof(void* hi, void* lo, int depth, int full_depth, double min_rot, double min_low, double wxy, double wz,
+                         const double* pose_guess, const float* hi_pts, int64_t n_hi, const float* lo_pts, int64_t n_lo,
+                         float min_score, OrcFcsmResult* out) {
+  FastCorrelativeScanMatcher m(*(HybridGrid*)hi, (const HybridGrid*)lo, fcsm_options(depth, full_depth, min_rot, min_low, wxy, wz));
+  fcsm_out(m.MatchWith3DofInitial(pose_in(pose_guess), hi_pts, n_hi, lo_pts, n_lo, min_score), out);
 }
 
 // ---- Ceres-equivalent matcher

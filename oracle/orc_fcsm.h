@@ -92,28 +92,30 @@ struct FcsmResult {
 
 class FastCorrelativeScanMatcher {
  public:
+  // Builds the precomputation stack once per submap, like the reference's constructor (cc:112-125); Match* is const and
+  // keeps its per-call state in a local Search record, so one matcher serves concurrent callers (the reference's
+  // thread-pool pattern, constraint_builder_3d.cc:189-197).
   FastCorrelativeScanMatcher(const HybridGrid& hi, const HybridGrid* lo, const FcsmOptions& o)
       : o_(o), resolution_(hi.resolution()), stack_(hi, o), lo_(lo) {}
 
   FcsmResult MatchWith3DofInitial(const Rigid3d& pose_in_submap_guess, const float* hi_pts, int64_t n_hi,
                                   const float* lo_pts, int64_t n_lo, float min_score) const {
-    wxy_ = round_to_int(o_.linear_xy_search_window / resolution_);
-    wz_ = round_to_int(o_.linear_z_search_window / resolution_);
-    lo_pts_ = lo_pts;
-    n_lo_ = n_lo;
-    leaves_ = 0;
-    Discretize(hi_pts, n_hi, cast_f(pose_in_submap_guess));
-    rotational_score_ = (float)(o_.min_rotational_score + 0.01);
-    std::vector<Candidate> lowest = GenerateLowest();
-    Score(stack_.max_depth(), &lowest);
-    const Candidate best = BranchAndBound(lowest, stack_.max_depth(), min_score);
+    Search s;
+    s.wxy = round_to_int(o_.linear_xy_search_window / resolution_);
+    s.wz = round_to_int(o_.linear_z_search_window / resolution_);
+    s.lo_pts = lo_pts;
+    s.n_lo = n_lo;
+    Discretize(&s, hi_pts, n_hi, cast_f(pose_in_submap_guess));
+    std::vector<Candidate> lowest = GenerateLowest(s);
+    Score(&s, stack_.max_depth(), &lowest);
+    const Candidate best = BranchAndBound(&s, lowest, stack_.max_depth(), min_score);
     FcsmResult r;
-    r.leaves_scored = leaves_;
+    r.leaves_scored = s.leaves;
     if (best.score > min_score) {
       r.found = true;
       r.score = best.score;
-      r.pose = cast_d(PoseFromCandidate(best));
-      r.rotational_score = rotational_score_;
+      r.pose = cast_d(PoseFromCandidate(s, best));
+      r.rotational_score = (float)(o_.min_rotational_score + 0.01);
       r.low_resolution_score = best.low_resolution_score;
       r.offset = best.offset;
     }
@@ -128,34 +130,40 @@ class FastCorrelativeScanMatcher {
     bool operator>(const Candidate& other) const { return score > other.score; }
     bool operator<(const Candidate& other) const { return score < other.score; }
   };
+  struct Search {  // DiscreteScan3D + the window + counters of one call
+    int wxy = 0, wz = 0;
+    Rigid3f pose;
+    std::vector<std::vector<I3>> cells;
+    const float* lo_pts = nullptr;
+    int64_t n_lo = 0, leaves = 0;
+  };
 
-  void Discretize(const float* pts, int64_t n, const Rigid3f& pose) const {
-    pose_ = pose;
-    cells_.clear();
+  void Discretize(Search* s, const float* pts, int64_t n, const Rigid3f& pose) const {
+    s->pose = pose;
     std::vector<I3> full;
     for (int64_t i = 0; i < n; ++i)
       full.push_back(stack_.Get(0).GetCellIndex(apply(pose, V3f{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]})));
     const int full_depth = std::min(o_.full_resolution_depth, o_.branch_and_bound_depth);
-    for (int i = 0; i != full_depth; ++i) cells_.push_back(full);
+    for (int i = 0; i != full_depth; ++i) s->cells.push_back(full);
     const int low_depth = o_.branch_and_bound_depth - full_depth;
-    const I3 start{-wxy_, -wxy_, -wz_};
+    const I3 start{-s->wxy, -s->wxy, -s->wz};
     for (int i = 0; i != low_depth; ++i) {
       const int e = i + 1;
       const I3 low_start{start.x >> e, start.y >> e, start.z >> e};
-      cells_.emplace_back();
+      s->cells.emplace_back();
       for (const I3& c : full) {
         const I3 at_start{c.x + start.x, c.y + start.y, c.z + start.z};
-        cells_.back().push_back(I3{(at_start.x >> e) - low_start.x, (at_start.y >> e) - low_start.y, (at_start.z >> e) - low_start.z});
+        s->cells.back().push_back(I3{(at_start.x >> e) - low_start.x, (at_start.y >> e) - low_start.y, (at_start.z >> e) - low_start.z});
       }
     }
   }
 
-  std::vector<Candidate> GenerateLowest() const {
+  std::vector<Candidate> GenerateLowest(const Search& s) const {
     const int step = 1 << stack_.max_depth();
     std::vector<Candidate> out;
-    for (int z = -wz_; z <= wz_; z += step)
-      for (int y = -wxy_; y <= wxy_; y += step)
-        for (int x = -wxy_; x <= wxy_; x += step) {
+    for (int z = -s.wz; z <= s.wz; z += step)
+      for (int y = -s.wxy; y <= s.wxy; y += step)
+        for (int x = -s.wxy; x <= s.wxy; x += step) {
           Candidate c;
           c.offset = {x, y, z};
           out.push_back(c);
@@ -163,37 +171,37 @@ class FastCorrelativeScanMatcher {
     return out;
   }
 
-  void Score(int depth, std::vector<Candidate>* candidates) const {
+  void Score(Search* s, int depth, std::vector<Candidate>* candidates) const {
     const int e = std::max(0, depth - o_.full_resolution_depth + 1);
     const HybridGrid& grid = stack_.Get(depth);
     for (Candidate& c : *candidates) {
       int sum = 0;
       const I3 off{c.offset.x >> e, c.offset.y >> e, c.offset.z >> e};
-      for (const I3& cell : cells_[depth]) sum += grid.value(I3{cell.x + off.x, cell.y + off.y, cell.z + off.z});
-      c.score = precomp_to_probability(sum / (float)cells_[depth].size());
-      if (depth == 0) ++leaves_;
+      for (const I3& cell : s->cells[depth]) sum += grid.value(I3{cell.x + off.x, cell.y + off.y, cell.z + off.z});
+      c.score = precomp_to_probability(sum / (float)s->cells[depth].size());
+      if (depth == 0) ++s->leaves;
     }
     std::sort(candidates->begin(), candidates->end(), std::greater<Candidate>());
   }
 
-  Rigid3f PoseFromCandidate(const Candidate& c) const {
+  Rigid3f PoseFromCandidate(const Search& s, const Candidate& c) const {
     const Rigid3f translation{{resolution_ * (float)c.offset.x, resolution_ * (float)c.offset.y, resolution_ * (float)c.offset.z},
                               {1.f, 0.f, 0.f, 0.f}};
-    return compose(translation, pose_);
+    return compose(translation, s.pose);
   }
 
-  float LowResolutionScore(const Rigid3f& pose) const {
+  float LowResolutionScore(const Search& s, const Rigid3f& pose) const {
     float score = 0.f;
-    for (int64_t i = 0; i < n_lo_; ++i)
-      score += lo_->GetProbability(lo_->GetCellIndex(apply(pose, V3f{lo_pts_[3 * i], lo_pts_[3 * i + 1], lo_pts_[3 * i + 2]})));
-    return score / (float)n_lo_;  // float / size_t
+    for (int64_t i = 0; i < s.n_lo; ++i)
+      score += lo_->GetProbability(lo_->GetCellIndex(apply(pose, V3f{s.lo_pts[3 * i], s.lo_pts[3 * i + 1], s.lo_pts[3 * i + 2]})));
+    return score / (float)s.n_lo;  // float / size_t
   }
 
-  Candidate BranchAndBound(const std::vector<Candidate>& candidates, int depth, float min_score) const {
+  Candidate BranchAndBound(Search* s, const std::vector<Candidate>& candidates, int depth, float min_score) const {
     if (depth == 0) {
       for (const Candidate& c : candidates) {
         if (c.score <= min_score) return Candidate();
-        const float low = LowResolutionScore(PoseFromCandidate(c));
+        const float low = LowResolutionScore(*s, PoseFromCandidate(*s, c));
         if (low >= o_.min_low_resolution_score) {
           Candidate best = c;
           best.low_resolution_score = low;
@@ -209,19 +217,19 @@ class FastCorrelativeScanMatcher {
       std::vector<Candidate> higher;
       const int half_width = 1 << (depth - 1);
       for (int z : {0, half_width}) {
-        if (c.offset.z + z > wz_) break;
+        if (c.offset.z + z > s->wz) break;
         for (int y : {0, half_width}) {
-          if (c.offset.y + y > wxy_) break;
+          if (c.offset.y + y > s->wxy) break;
           for (int x : {0, half_width}) {
-            if (c.offset.x + x > wxy_) break;
+            if (c.offset.x + x > s->wxy) break;
             Candidate h;
             h.offset = {c.offset.x + x, c.offset.y + y, c.offset.z + z};
             higher.push_back(h);
           }
         }
       }
-      Score(depth - 1, &higher);
-      const Candidate sub = BranchAndBound(higher, depth - 1, best.score);
+      Score(s, depth - 1, &higher);
+      const Candidate sub = BranchAndBound(s, higher, depth - 1, best.score);
       if (best < sub) best = sub;  // std::max(a, b) keeps a unless a < b
     }
     return best;
@@ -231,12 +239,6 @@ class FastCorrelativeScanMatcher {
   float resolution_;
   PrecomputationGridStack stack_;
   const HybridGrid* lo_;
-  mutable int wxy_ = 0, wz_ = 0;
-  mutable Rigid3f pose_;
-  mutable std::vector<std::vector<I3>> cells_;
-  mutable const float* lo_pts_ = nullptr;
-  mutable int64_t n_lo_ = 0, leaves_ = 0;
-  mutable float rotational_score_ = 0.f;
 };
 
 }  // namespace orc

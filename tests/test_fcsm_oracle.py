@@ -69,3 +69,17 @@ def test_branch_and_bound_equals_brute_force(orc):
 def test_min_score_above_best_returns_nothing(orc):
     g = fixture_grid(orc, (0.1, 0.0, -0.1))
     assert not orc.fcsm_match_3dof(g, g, CLOUD, CLOUD, orc.IDENTITY_POSE, 0.95, **TEST_OPTS).found
+
+
+def test_matcher_object_is_reentrant(orc):
+    """One per-submap matcher (stack built once) queried from several threads gives what fresh matchers give."""
+    from concurrent.futures import ThreadPoolExecutor
+    g = fixture_grid(orc, (0.25, -0.1, 0.05))
+    m = orc.FastCorrelativeScanMatcher(g, g, **TEST_OPTS)
+    rng = np.random.default_rng(9)
+    guesses = [np.array([*(0.2 * rng.uniform(-1, 1, 3)), 1, 0, 0, 0]) for _ in range(16)]
+    with ThreadPoolExecutor(8) as ex:
+        got = list(ex.map(lambda q: m.match(CLOUD, CLOUD, q, 0.1), guesses))
+    for q, r in zip(guesses, got):
+        want = orc.fcsm_match_3dof(g, g, CLOUD, CLOUD, q, 0.1, **TEST_OPTS)
+        assert (r.found, r.score, list(r.offset), list(r.pose)) == (want.found, want.score, list(want.offset), list(want.pose))

@@ -3,7 +3,7 @@ the oracle runs the reference's precomputation stack + branch and bound. Scores 
 import numpy as np
 import pytest
 
-from helpers import workload
+from helpers import pose_error, workload
 from test_fcsm_oracle import CLOUD, TEST_OPTS, fixture_grid
 
 pytestmark = pytest.mark.gpu
@@ -97,3 +97,58 @@ def test_argument_errors(ctx, orc):
         ctx.fcsm_match_3dof(g, g, CLOUD[:0], CLOUD, orc.IDENTITY_POSE, 0.1)
     with pytest.raises(dliom.DlError):
         ctx.fcsm_match_3dof(g, g, CLOUD, CLOUD, orc.IDENTITY_POSE, 0.1, depth=0)
+
+
+def test_constraint_search_batch(ctx, orc):
+    """ConstraintBuilder3D::ComputeConstraint (constraint_builder_3d.cc:261-333) for a batch of (node, submap) pairs in one
+    call: coarse search, min_score prune, refinement seeded with the coarse pose on the device. Pairs mix two submaps,
+    several nodes, a node whose guess is far outside the window (pruned) — the oracle chains its own two matchers."""
+    import dliom
+    w = workload(beams=16, num_map_scans=40, num_scans=3)
+    w2 = workload(beams=16, num_map_scans=12, num_scans=3)
+    subs = [(w["hi"], w["lo"]), (w2["hi"], w2["lo"])]
+    dev = [(dliom.Grid.from_oracle(ctx, h), dliom.Grid.from_oracle(ctx, l)) for h, l in subs]
+    rng = np.random.default_rng(11)
+    guesses, his, los, hg, lg, og = [], [], [], [], [], []
+    for k in range(3):
+        pts = orc.ingest_scan(w["opts"], w["scans"][k], w["origin"], w["prev"][k], w["truth"][k])["returns_tracking"]
+        hk, _ = orc.adaptive_voxel_filter(pts, 2.0, 150, 15.0)
+        lk, _ = orc.adaptive_voxel_filter(pts, 4.0, 200, 60.0)
+        for s in range(2):
+            for far in (False, True):
+                g = np.array(w["truth"][k], np.float64)
+                g[:3] += rng.uniform(-1, 1, 3) * [2.0, 2.0, 0.4] + (np.array([60.0, 0, 0]) if far else 0)
+                guesses.append(g); his.append(pts[hk]); los.append(pts[lk])
+                hg.append(dev[s][0]); lg.append(dev[s][1]); og.append(subs[s])
+    opt = dliom.ConstraintOptions.defaults(min_score=0.15, min_low_resolution_score=0.3)
+    got = ctx.constraint_search_batch(opt, guesses, his, los, hg, lg)
+    assert len(got) == 12
+    found = 0
+    for c, g, h, l, (oh, ol) in zip(got, guesses, his, los, og):
+        coarse = orc.fcsm_match_3dof(oh, ol, h, l, g, 0.15, min_low_resolution_score=0.3)
+        assert bool(c.found) == bool(coarse.found)
+        if not coarse.found:
+            assert c.translation_weight == 0 and not any(c.pose[:])
+            continue
+        found += 1
+        assert np.float32(c.score) == np.float32(coarse.score)
+        assert np.float32(c.low_resolution_score) == np.float32(coarse.low_resolution_score)
+        assert np.array_equal(np.array(c.coarse_pose[:]), np.array(coarse.pose[:]))
+        cp = np.array(coarse.pose[:])
+        want, summary = orc.ceres_match([h, l], [oh, ol], [5.0, 30.0], 10.0, 1.0, cp[:3], cp, max_iter=10)
+        dt, dr = pose_error(np.array(c.pose[:]), want)
+        assert dt < 1e-6 and dr < 1e-7
+        assert c.summary.num_iterations == summary["num_iterations"]
+        assert abs(c.summary.final_cost - summary["final_cost"]) <= 1e-6 * max(1.0, summary["final_cost"])
+        assert (c.translation_weight, c.rotation_weight) == (1.1e4, 1e5)
+    assert 1 <= found <= 6     # the six "far" guesses can never match
+
+
+def test_constraint_search_batch_edge_cases(ctx, orc):
+    import dliom
+    og = fixture_grid(orc, (0, 0, 0))
+    g = dliom.Grid.from_oracle(ctx, og)
+    opt = dliom.ConstraintOptions.defaults()
+    assert ctx.constraint_search_batch(opt, [], [], [], [], []) == []
+    with pytest.raises(dliom.DlError):   # an empty cloud in the batch
+        ctx.constraint_search_batch(opt, [orc.IDENTITY_POSE] * 2, [CLOUD, CLOUD[:0]], [CLOUD, CLOUD], [g, g], [g, g])

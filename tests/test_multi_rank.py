@@ -62,3 +62,49 @@ def test_two_ranks_gloo(tmp_path):
         m = orc.match_scan(w["opts"], ing["returns_tracking"], ing["current_pose"].astype(np.float64), w["submap_pose"],
                            w["hi"], w["lo"])
         assert np.array_equal(g[s, 1:], m["pose_estimate_local"])
+
+
+class _Hit:
+    def __init__(self, found, score, pose):
+        self.found, self.score, self.low_resolution_score, self.pose = found, score, 0.5, list(pose)
+        self.translation_weight, self.rotation_weight = 1.1e4, 1e5
+
+
+def _constraint_worker(rank, world, port, tmp):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "d-liom_b200")]
+    import torch.distributed as dist
+    from dliom import shard
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        submaps, nodes, hits = _constraint_problem()
+        mine = shard.shard_by_owner(submaps, rank, world)
+        assert all(shard.owner_of_submap(submaps[i], world) == rank for i in mine)
+        rows = shard.constraint_rows([submaps[i] for i in mine], [nodes[i] for i in mine], [hits[i] for i in mine])
+        table = shard.all_gather_constraints(dist, rows)
+        np.save(os.path.join(tmp, f"table{rank}.npy"), table)
+    finally:
+        dist.destroy_process_group()
+
+
+def _constraint_problem():
+    rng = np.random.RandomState(7)
+    submaps = [int(s) for s in rng.randint(0, 5, 23)]
+    nodes = list(range(100, 123))
+    hits = [_Hit(bool(rng.rand() < 0.6), float(rng.rand()), rng.randn(7)) for _ in submaps]
+    return submaps, nodes, hits
+
+
+def test_constraint_all_gather_two_ranks_gloo(tmp_path):
+    """Loop-closure sharding: pairs go to the rank that owns the submap, pruned pairs vanish, and after the one exchange
+    step every rank holds the same table a single process would have produced."""
+    sys.path.insert(0, os.path.join(ROOT, "d-liom_b200"))
+    from dliom import shard
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_constraint_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    t0, t1 = np.load(tmp_path / "table0.npy"), np.load(tmp_path / "table1.npy")
+    submaps, nodes, hits = _constraint_problem()
+    single = shard.all_gather_constraints(None, shard.constraint_rows(submaps, nodes, hits))
+    assert np.array_equal(t0, t1) and np.array_equal(t0, single)
+    assert len(single) == sum(h.found for h in hits) and t0.shape[1] == len(shard.CONSTRAINT_COLUMNS)
+    assert np.all(np.diff(t0[:, 0]) >= 0)

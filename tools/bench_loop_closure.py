@@ -1,0 +1,139 @@
+"""Loop-closure search throughput (BASELINE configs[3]/[4] shape): every step searches `nodes x submaps` (node, submap)
+pairs — coarse 5 m x 5 m x 1 m translation search + refinement (ConstraintBuilder3D::ComputeConstraint) — sharded over
+the ranks by submap owner, then all-gathers the constraint records (the path's only collective). One JSON line.
+
+    python tools/bench_loop_closure.py [--submaps 32 --nodes 8 --steps 5 --warmup 2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/bench_loop_closure.py
+"""
+import argparse
+import json
+import os
+import sys
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "d-liom_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"),
+                os.path.join(ROOT, "tools")]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--submaps", type=int, default=32)
+    ap.add_argument("--nodes", type=int, default=8)
+    ap.add_argument("--beams", type=int, default=64)
+    ap.add_argument("--map-scans", type=int, default=20)
+    ap.add_argument("--distinct", type=int, default=4, help="distinct submaps built by the oracle; the rest are device copies")
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--min-score", type=float, default=0.3)
+    ap.add_argument("--cpu-pairs", type=int, default=8192, help="CPU sample: this many searches, cycling through the pair list")
+    args = ap.parse_args()
+
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import dliom
+    import orc
+    from dliom import shard
+    from helpers import workload
+
+    ctx = dliom.Context(local)
+    built = [workload(beams=args.beams, num_map_scans=args.map_scans, num_scans=args.nodes, start=2.0 + 3.0 * d)
+             for d in range(args.distinct)]
+    # nodes: filtered clouds of the sweeps that follow submap 0's map scans; guesses displaced inside the window
+    w0 = built[0]
+    rng = np.random.default_rng(17)
+    node_hi, node_lo, node_truth = [], [], []
+    for k in range(args.nodes):
+        pts = orc.ingest_scan(w0["opts"], w0["scans"][k], w0["origin"], w0["prev"][k], w0["truth"][k])["returns_tracking"]
+        hk, _ = orc.adaptive_voxel_filter(pts, 2.0, 150, 15.0)
+        lk, _ = orc.adaptive_voxel_filter(pts, 4.0, 200, 60.0)
+        node_hi.append(pts[hk]); node_lo.append(pts[lk]); node_truth.append(np.array(w0["truth"][k], np.float64))
+    pairs = [(s, n) for s in range(args.submaps) for n in range(args.nodes)]
+    mine = shard.shard_by_owner([s for s, _ in pairs], rank, world)
+    owned = sorted({pairs[i][0] for i in mine})
+    grids = {s: (dliom.Grid.from_oracle(ctx, built[s % args.distinct]["hi"]),
+                 dliom.Grid.from_oracle(ctx, built[s % args.distinct]["lo"])) for s in owned}
+    guesses = []
+    for s, n in pairs:
+        g = node_truth[n].copy()
+        g[:3] += rng.uniform(-1, 1, 3) * [2.0, 2.0, 0.4]
+        guesses.append(g)
+    opt = dliom.ConstraintOptions.defaults(min_score=args.min_score, min_low_resolution_score=0.3)
+    call = dict(pose_guesses=[guesses[i] for i in mine], hi_clouds=[node_hi[pairs[i][1]] for i in mine],
+                lo_clouds=[node_lo[pairs[i][1]] for i in mine], hi_grids=[grids[pairs[i][0]][0] for i in mine],
+                lo_grids=[grids[pairs[i][0]][1] for i in mine])
+    dev = torch.device("cuda", local)
+
+    def step():
+        t0 = time.perf_counter()
+        cons = ctx.constraint_search_batch(opt, **call)
+        t1 = time.perf_counter()
+        rows = shard.constraint_rows([pairs[i][0] for i in mine], [pairs[i][1] for i in mine], cons)
+        table = shard.all_gather_constraints(dist if world > 1 else None, rows, dev)
+        torch.cuda.synchronize()
+        return t1 - t0, time.perf_counter() - t1, table
+
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    search, gather, table = 0.0, 0.0, None
+    for _ in range(args.steps):
+        a, b, table = step()
+        search += a; gather += b
+    search = shard.max_over_ranks(dist if world > 1 else None, search, dev)
+    gather = shard.max_over_ranks(dist if world > 1 else None, gather, dev)
+    if rank == 0:
+        # CPU: the oracle's branch and bound + its LM solver, one pair per host thread
+        sample = [i % len(pairs) for i in range(args.cpu_pairs)]
+        t0 = time.perf_counter()
+        matchers = [orc.FastCorrelativeScanMatcher(b["hi"], b["lo"], min_low_resolution_score=0.3) for b in built]
+        stack_s = (time.perf_counter() - t0) / len(built)   # once per finished submap in the reference: not in the timed sample
+
+        def cpu_pair(i):
+            s, n = pairs[i]
+            b = built[s % args.distinct]
+            c = matchers[s % args.distinct].match(node_hi[n], node_lo[n], guesses[i], args.min_score)
+            if c.found:
+                cp = np.array(c.pose[:])
+                orc.ceres_match([node_hi[n], node_lo[n]], [b["hi"], b["lo"]], [5.0, 30.0], 10.0, 1.0, cp[:3], cp, max_iter=10)
+            return bool(c.found)
+        t0 = time.perf_counter()
+        cpu_pair(0)
+        one = time.perf_counter() - t0
+        threads = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(threads) as ex:
+            found_cpu = sum(ex.map(cpu_pair, sample))
+        cpu = time.perf_counter() - t0
+        total = (search + gather) / args.steps
+        print(json.dumps({
+            "metric": "loop-closure constraint searches/s (coarse 3-DoF window + refinement), whole job",
+            "value": len(pairs) / total, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total, "search_ms": 1e3 * search / args.steps, "allgather_ms": 1e3 * gather / args.steps,
+            "scaling": "strong", "higher_is_better": True, "data": "synthetic",
+            "config": {"workload": "configs[3] shape: %d submaps x %d nodes (%d-beam), window 5 m x 5 m x 1 m at 0.1 m = 214 221 leaves/pair"
+                                   % (args.submaps, args.nodes, args.beams),
+                       "pairs_per_step": len(pairs), "min_score": args.min_score,
+                       "points_hi": int(np.mean([len(c) for c in node_hi])), "points_lo": int(np.mean([len(c) for c in node_lo])),
+                       "parallelism": "pairs sharded by submap owner over %d gpu(s); all-gather of constraint rows" % world},
+            "constraints_found": int(len(table)),
+            "cpu_baseline": {"value": len(sample) / cpu, "unit": "pairs/s", "cores": threads, "kind": "port",
+                             "sample": "%d searches, one per host thread at a time (%.2f s); single pair on one thread %.3f s; found %d; "
+                                       "precomputation stack (built once per submap, excluded) %.2f s"
+                                       % (len(sample), cpu, one, found_cpu, stack_s)}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
