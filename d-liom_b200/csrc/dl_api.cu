@@ -14,6 +14,7 @@ using namespace dl;
 
 // ------------------------------------------------------------------------------------------------ context
 int dl_context::reserve_device(size_t bytes) {
+  if (in_flight) return fail(DL_ERR_ARG, "a submitted batch is in flight on this context: call dl_frontend_collect first");
   if (bytes <= d_scratch_bytes) return DL_OK;
   if (d_scratch) {
     DL_CUDA(this, cudaStreamSynchronize(stream));
@@ -122,6 +123,13 @@ int sync(dl_context* ctx) {
 
 extern "C" {
 
+static cudaError_t create_high_priority_stream(cudaStream_t* s) {
+  int least = 0, greatest = 0;
+  cudaError_t e = cudaDeviceGetStreamPriorityRange(&least, &greatest);
+  if (e != cudaSuccess) return e;
+  return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, greatest);
+}
+
 int dl_context_create(int device_ordinal, dl_context** out) {
   if (!out) return DL_ERR_ARG;
   *out = nullptr;
@@ -138,6 +146,8 @@ int dl_context_create(int device_ordinal, dl_context** out) {
       (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = create_high_priority_stream(&ctx->tail_stream)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->batch_done, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->staging_done, cudaEventDisableTiming)) != cudaSuccess) {
     g_create_error = cudaGetErrorString(e);
     delete ctx;
@@ -158,6 +168,8 @@ void dl_context_destroy(dl_context* ctx) {
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+  if (ctx->tail_stream) cudaStreamDestroy(ctx->tail_stream);
+  if (ctx->batch_done) cudaEventDestroy(ctx->batch_done);
   if (ctx->staging_done) cudaEventDestroy(ctx->staging_done);
   delete ctx;
 }
@@ -1381,12 +1393,15 @@ int frontend_ingest(dl_context* ctx, const dl_frontend_options& o, const Fronten
 
 // Uploads the small per-call tables (counts, deskew constants, origins, filter options, NLS problem records)
 // through one pinned staging block. No host synchronisation: the block is reused only after `staging_done`.
+size_t frontend_small_bytes(int batch, int num_origins) {
+  const size_t B = (size_t)batch;
+  return arena_bytes({B * 4, B * sizeof(ScanConstants), (size_t)num_origins * 12, 2 * sizeof(AdaptiveParams), B * sizeof(NlsProblem)});
+}
 int frontend_upload_small(dl_context* ctx, const dl_frontend_options& o, const FrontendBuffers& f, const int64_t* sizes,
                           const float* origins, int num_origins, const double* prev_poses, const double* cur_poses,
                           const dl_grid* hi, const dl_grid* lo) {
   const size_t B = (size_t)f.batch;
-  const size_t bytes = arena_bytes({B * 4, B * sizeof(ScanConstants), (size_t)num_origins * 12, 2 * sizeof(AdaptiveParams),
-                                    B * sizeof(NlsProblem)});
+  const size_t bytes = frontend_small_bytes(f.batch, num_origins);
   DL_TRY(ctx->reserve_pinned(bytes));
   DL_CUDA(ctx, cudaEventSynchronize(ctx->staging_done));
   Arena h(ctx->h_pinned);
@@ -1441,30 +1456,65 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
   DL_TRY(launch_fe_prepare(ctx, fa, f.batch));
   const Rigidd submap = pose_from7(submap_local_pose);
   const bool rtcsm = o.use_online_correlative_scan_matching != 0;
-  int chunks = rtcsm ? 1 : (host_ranges ? 4 : 2);
+  int chunks = rtcsm ? 1 : (host_ranges ? 5 : 2);
   if (const char* env = std::getenv(host_ranges ? "DLIOM_CHUNKS_HOST" : "DLIOM_CHUNKS_DEV")) chunks = rtcsm ? 1 : std::max(1, std::atoi(env));
   if (f.batch < 8 * chunks) chunks = std::max(1, f.batch / 8);
+  // Pipeline shape. 1: every front half (bandwidth-bound, thousands of CTAs) runs in order on the main stream and
+  // every back half (latency-bound, one or two CTAs per scan) on a HIGH-PRIORITY stream behind its front half's event, so
+  // the back half of sub-batch k gets SMs the moment CTAs of front half k+1 retire instead of queueing behind that grid.
+  // 0 (default): sub-batches alternate between two equal-priority streams.
+  // (Measured on B200, profiles/r1_pipeline_variants.log: 0 wins — the back half is latency-bound, so serialising all back
+  // halves on one stream costs more than the priority gains; 1 is kept for experiments.)
+  int split = 0;
+  if (const char* env = std::getenv("DLIOM_PIPELINE")) split = rtcsm ? 0 : std::atoi(env);
   cudaStream_t main_stream = ctx->stream;
   cudaEvent_t prepared = ctx->take_event();
   DL_CUDA(ctx, cudaEventRecord(prepared, main_stream));
   DL_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, prepared, 0));
+  DL_CUDA(ctx, cudaStreamWaitEvent(ctx->tail_stream, prepared, 0));
   if (host_ranges) DL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, prepared, 0));  // the upload target may be in use
   ctx->event_pool.push_back(prepared);
   std::vector<float> rtcsm_scores;
   bool have_scores = false;
   int status = DL_OK;
+  // Sub-batch boundaries. Device-resident scans: equal parts. Host scans: the upload is the long pole and the kernels of
+  // the LAST sub-batch are exposed after its copy ends, so the last parts shrink (shares 1 : ... : 1 : 1/2 : 1/4) — their
+  // back halves are latency-bound (~0.6 ms however few scans), so only the front-half time shrinks with them.
+  std::vector<int> bounds(chunks + 1, 0);
+  {
+    std::vector<double> share(chunks, 1.0);
+    if (host_ranges && chunks >= 3 && !std::getenv("DLIOM_EQUAL_CHUNKS")) {
+      share[chunks - 2] = 0.5;
+      share[chunks - 1] = 0.25;
+    }
+    double total = 0, acc = 0;
+    for (double v : share) total += v;
+    for (int k = 0; k < chunks; ++k) {
+      acc += share[k];
+      bounds[k + 1] = k + 1 == chunks ? f.batch : (int)std::lround(f.batch * acc / total);
+    }
+  }
   for (int k = 0; k < chunks && status == DL_OK; ++k) {
-    const int b0 = (int)((int64_t)f.batch * k / chunks), b1 = (int)((int64_t)f.batch * (k + 1) / chunks), nb = b1 - b0;
+    const int b0 = bounds[k], b1 = bounds[k + 1], nb = b1 - b0;
     if (nb <= 0) continue;
-    ctx->stream = (k & 1) ? ctx->aux_stream : main_stream;
+    ctx->stream = split ? main_stream : ((k & 1) ? ctx->aux_stream : main_stream);
     auto run = [&]() -> int {
       {
         StageScope st(ctx, "voxel_filter_first");
-        if (host_ranges) {
+        if (host_ranges && o.host_scan_stride_rows > 0) {
+          int64_t widest = 0;
+          for (int b = b0; b < b1; ++b) widest = std::max(widest, sizes[b]);
+          if (widest > 0)
+            DL_CUDA(ctx, cudaMemcpy2DAsync(d_ranges + (size_t)b0 * in_cap * rf, (size_t)in_cap * rf * 4, host_ranges[b0],
+                                           (size_t)o.host_scan_stride_rows * rf * 4, (size_t)widest * rf * 4, (size_t)nb,
+                                           cudaMemcpyHostToDevice, ctx->copy_stream));
+        } else if (host_ranges) {
           for (int b = b0; b < b1; ++b)
             if (sizes[b] > 0)
               DL_CUDA(ctx, cudaMemcpyAsync(d_ranges + (size_t)b * in_cap * rf, host_ranges[b], (size_t)sizes[b] * rf * 4,
                                            cudaMemcpyHostToDevice, ctx->copy_stream));
+        }
+        if (host_ranges) {
           cudaEvent_t ev = ctx->take_event();
           DL_CUDA(ctx, cudaEventRecord(ev, ctx->copy_stream));
           DL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev, 0));
@@ -1475,6 +1525,13 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
       {
         StageScope st(ctx, "ingest_second_filter");
         DL_TRY(launch_fe_rest(ctx, fa, b0, nb));
+      }
+      if (split) {
+        cudaEvent_t front_done = ctx->take_event();
+        DL_CUDA(ctx, cudaEventRecord(front_done, main_stream));
+        DL_CUDA(ctx, cudaStreamWaitEvent(ctx->tail_stream, front_done, 0));
+        ctx->event_pool.push_back(front_done);
+        ctx->stream = ctx->tail_stream;
       }
       {
         // adaptive voxel filters (high, low resolution) on the tracking-frame returns: one CTA per (scan, filter)
@@ -1526,9 +1583,9 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
     status = run();
   }
   ctx->stream = main_stream;
-  if (chunks > 1) {  // later work on the main stream (result copies, the next call) waits for the auxiliary stream
+  if (chunks > 1 || split) {  // later work on the main stream (result copies, the next call) waits for the other streams
     cudaEvent_t joined = ctx->take_event();
-    DL_CUDA(ctx, cudaEventRecord(joined, ctx->aux_stream));
+    DL_CUDA(ctx, cudaEventRecord(joined, split ? ctx->tail_stream : ctx->aux_stream));
     DL_CUDA(ctx, cudaStreamWaitEvent(main_stream, joined, 0));
     ctx->event_pool.push_back(joined);
   }
@@ -1581,31 +1638,82 @@ int dl_frontend_fetch_results(dl_context* ctx, const dl_scan_result* results_dev
   return sync(ctx);
 }
 
-int dl_frontend_match_batch(dl_context* ctx, const dl_frontend_options* options, int32_t num_scans,
-                            const void* const* ranges, const int64_t* sizes, const float* origins, int32_t num_origins,
-                            const double* prev_poses, const double* predicted_poses, const double* submap_local_pose,
-                            const dl_grid* hi, const dl_grid* lo, dl_scan_result* results) {
-  if (!ctx) return DL_ERR_ARG;
+// Validates, reserves and enqueues one host-buffer batch; on return *d_results_out holds the device results (not yet synchronised).
+static int frontend_enqueue_host(dl_context* ctx, const dl_frontend_options* options, int32_t num_scans, const void* const* ranges,
+                                 const int64_t* sizes, const float* origins, int32_t num_origins, const double* prev_poses,
+                                 const double* predicted_poses, const double* submap_local_pose, const dl_grid* hi,
+                                 const dl_grid* lo, size_t pinned_extra, dl_scan_result** d_results_out) {
   int64_t max_size = 0;
   DL_TRY(check_frontend(ctx, options, num_scans, sizes, hi, lo, &max_size));
-  if (num_scans == 0) return DL_OK;
-  if (!ranges || !origins || num_origins < 1 || !prev_poses || !predicted_poses || !submap_local_pose || !results)
-    return DL_ERR_ARG;
+  if (!ranges || !origins || num_origins < 1 || !prev_poses || !predicted_poses || !submap_local_pose) return DL_ERR_ARG;
+  for (int b = 0; b < num_scans; ++b)
+    if (sizes[b] > 0 && !ranges[b]) return DL_ERR_ARG;
+  if (options->host_scan_stride_rows != 0) {
+    const int64_t stride = options->host_scan_stride_rows;
+    const size_t row_bytes = (size_t)row_floats_of(*options) * 4;
+    if (stride < max_size) return ctx->fail(DL_ERR_ARG, "host_scan_stride_rows is smaller than a scan");
+    for (int b = 0; b < num_scans; ++b)
+      if ((const char*)ranges[b] != (const char*)ranges[0] + (size_t)b * stride * row_bytes)
+        return ctx->fail(DL_ERR_ARG, "host_scan_stride_rows does not describe the ranges pointers");
+  }
   DL_CUDA(ctx, cudaSetDevice(ctx->device));
   const int64_t cap = std::max<int64_t>(max_size, 1);
   const size_t extra = options->use_online_correlative_scan_matching
                            ? rtcsm_scratch_bound(options->real_time_correlative_scan_matcher, hi->resolution, false) : 0;
   DL_TRY(ctx->reserve_device(frontend_bytes(num_scans, cap, num_origins, extra) + (size_t)num_scans * cap * 32 + 256 +
                              (size_t)num_scans * sizeof(dl_scan_result) + 256));
+  if (pinned_extra) DL_TRY(ctx->reserve_pinned(frontend_small_bytes(num_scans, num_origins) + pinned_extra + 256));
   Arena a(ctx->d_scratch);
   float* d_ranges = a.take<float>((size_t)num_scans * cap * 8);
-  dl_scan_result* d_results = a.take<dl_scan_result>(num_scans);
-  for (int b = 0; b < num_scans; ++b)
-    if (sizes[b] > 0 && !ranges[b]) return DL_ERR_ARG;
-  DL_TRY(frontend_run(ctx, *options, num_scans, d_ranges, cap, ranges, sizes, origins, num_origins, prev_poses,
-                      predicted_poses, submap_local_pose, hi, lo, a, d_results));
+  *d_results_out = a.take<dl_scan_result>(num_scans);
+  return frontend_run(ctx, *options, num_scans, d_ranges, cap, ranges, sizes, origins, num_origins, prev_poses,
+                      predicted_poses, submap_local_pose, hi, lo, a, *d_results_out);
+}
+
+int dl_frontend_match_batch(dl_context* ctx, const dl_frontend_options* options, int32_t num_scans,
+                            const void* const* ranges, const int64_t* sizes, const float* origins, int32_t num_origins,
+                            const double* prev_poses, const double* predicted_poses, const double* submap_local_pose,
+                            const dl_grid* hi, const dl_grid* lo, dl_scan_result* results) {
+  if (!ctx) return DL_ERR_ARG;
+  if (num_scans == 0) {
+    int64_t m = 0;
+    return check_frontend(ctx, options, num_scans, sizes, hi, lo, &m);
+  }
+  if (!results) return DL_ERR_ARG;
+  dl_scan_result* d_results = nullptr;
+  DL_TRY(frontend_enqueue_host(ctx, options, num_scans, ranges, sizes, origins, num_origins, prev_poses, predicted_poses,
+                               submap_local_pose, hi, lo, 0, &d_results));
   DL_TRY(d2h(ctx, results, d_results, num_scans));
   return sync(ctx);
+}
+
+int dl_frontend_submit(dl_context* ctx, const dl_frontend_options* options, int32_t num_scans, const void* const* ranges,
+                       const int64_t* sizes, const float* origins, int32_t num_origins, const double* prev_poses,
+                       const double* predicted_poses, const double* submap_local_pose, const dl_grid* hi, const dl_grid* lo) {
+  if (!ctx || num_scans < 1) return DL_ERR_ARG;
+  if (ctx->in_flight) return ctx->fail(DL_ERR_ARG, "a submitted batch is already in flight on this context");
+  dl_scan_result* d_results = nullptr;
+  const size_t result_bytes = (size_t)num_scans * sizeof(dl_scan_result);
+  DL_TRY(frontend_enqueue_host(ctx, options, num_scans, ranges, sizes, origins, num_origins, prev_poses, predicted_poses,
+                               submap_local_pose, hi, lo, result_bytes, &d_results));
+  ctx->results_staging_offset = (frontend_small_bytes(num_scans, num_origins) + 255) & ~size_t(255);
+  DL_CUDA(ctx, cudaMemcpyAsync((char*)ctx->h_pinned + ctx->results_staging_offset, d_results, result_bytes,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+  DL_CUDA(ctx, cudaEventRecord(ctx->batch_done, ctx->stream));
+  ctx->in_flight = num_scans;
+  return DL_OK;
+}
+
+int dl_frontend_collect(dl_context* ctx, int32_t num_scans, dl_scan_result* results) {
+  if (!ctx || !results) return DL_ERR_ARG;
+  if (!ctx->in_flight) return ctx->fail(DL_ERR_ARG, "no submitted batch on this context");
+  if (num_scans != ctx->in_flight) return ctx->fail(DL_ERR_ARG, "num_scans differs from the submitted batch");
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  const cudaError_t e = cudaEventSynchronize(ctx->batch_done);
+  ctx->in_flight = 0;
+  if (e != cudaSuccess) return ctx->cuda_fail(e, "dl_frontend_collect");
+  std::memcpy(results, (const char*)ctx->h_pinned + ctx->results_staging_offset, (size_t)num_scans * sizeof(dl_scan_result));
+  return DL_OK;
 }
 
 int dl_ingest_scan(dl_context* ctx, const dl_frontend_options* options, const void* ranges, int64_t n,

@@ -48,7 +48,11 @@ struct dl_context {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // uploads of host scans, overlapped with the kernels of the previous sub-batch
   cudaStream_t aux_stream = nullptr;    // odd sub-batches of the front end (see frontend_run)
+  cudaStream_t tail_stream = nullptr;   // high priority: the latency-bound back half (adaptive filter, LM solve) of every sub-batch
   cudaEvent_t staging_done = nullptr;   // the pinned staging block of the previous call has been consumed
+  cudaEvent_t batch_done = nullptr;     // dl_frontend_submit: everything of the batch in flight, incl. the result download
+  int in_flight = 0;                    // scans of the submitted, not yet collected batch
+  size_t results_staging_offset = 0;    // where in h_pinned the in-flight batch's results land
   std::string error;
   int64_t launches = 0;
   // growable scratch arenas (device + pinned host), reused across calls

@@ -25,7 +25,7 @@ EXPORTS = [
     "dl_grid_sync", "dl_grid_resolution", "dl_grid_num_bricks", "dl_grid_lookup", "dl_grid_interpolate",
     "dl_grid_insert_range_data", "dl_submap_insert_range_data", "dl_grid_export_cells",
     "dl_voxel_filter", "dl_voxel_indices", "dl_adaptive_voxel_filter", "dl_rtcsm_match", "dl_fcsm_match_3dof", "dl_constraint_search_batch", "dl_ceres_match",
-    "dl_ceres_match_batch", "dl_ceres_normal_equations", "dl_imu_preintegrate", "dl_imu_predict", "dl_fused_match_batch", "dl_ingest_scan", "dl_frontend_match_batch",
+    "dl_ceres_match_batch", "dl_ceres_normal_equations", "dl_imu_preintegrate", "dl_imu_predict", "dl_fused_match_batch", "dl_ingest_scan", "dl_frontend_match_batch", "dl_frontend_submit", "dl_frontend_collect",
     "dl_frontend_match_batch_dev", "dl_frontend_fetch_results", "dl_device_alloc", "dl_device_free",
     "dl_copy_to_device", "dl_copy_to_host",
 ]
@@ -153,7 +153,8 @@ class FrontendOptions(C.Structure):
                 ("low_resolution_adaptive_voxel_filter", AdaptiveVoxelFilterOptions),
                 ("use_online_correlative_scan_matching", C.c_int32), ("range_row_floats", C.c_int32),
                 ("scan_period", C.c_double),
-                ("real_time_correlative_scan_matcher", RtcsmOptions), ("ceres_scan_matcher", CeresOptions)]
+                ("real_time_correlative_scan_matcher", RtcsmOptions), ("ceres_scan_matcher", CeresOptions),
+                ("host_scan_stride_rows", C.c_int64)]
 
     @staticmethod
     def from_oracle(o):
@@ -243,6 +244,8 @@ def lib():
                                  f32p, f32p, i64p]
     L.dl_frontend_match_batch.argtypes = [vp, ip(FrontendOptions), C.c_int32, ip(vp), i64p, f32p, C.c_int32, f64p,
                                           f64p, f64p, vp, vp, ip(ScanResult)]
+    L.dl_frontend_submit.argtypes = [vp, ip(FrontendOptions), C.c_int32, ip(vp), i64p, f32p, C.c_int32, f64p, f64p, f64p, vp, vp]
+    L.dl_frontend_collect.argtypes = [vp, C.c_int32, ip(ScanResult)]
     L.dl_frontend_match_batch_dev.argtypes = [vp, ip(FrontendOptions), C.c_int32, vp, C.c_int64, i64p, f32p, C.c_int32,
                                               f64p, f64p, f64p, vp, vp, vp]
     L.dl_frontend_fetch_results.argtypes = [vp, vp, C.c_int32, ip(ScanResult)]
@@ -252,6 +255,16 @@ def lib():
     L.dl_copy_to_host.argtypes = [vp, vp, vp, C.c_int64]
     _LIB = L
     return L
+
+
+class HostScanBatch:
+    """Per-scan host row arrays + the pointer/size tables the C-ABI takes (built once, reusable across calls)."""
+
+    def __init__(self, ranges_list):
+        self.rows = list(ranges_list)
+        self.n = len(self.rows)
+        self.pointers = (C.c_void_p * max(self.n, 1))(*[r.ctypes.data for r in self.rows])
+        self.sizes = np.array([len(r) for r in self.rows], np.int64)
 
 
 class Context:
@@ -476,16 +489,32 @@ class Context:
                 "returns_tracking": rt[:counts[2]].copy(), "misses_tracking": mt[:counts[3]].copy(), "current_pose": cp}
 
     def frontend_match_batch(self, options, ranges_list, origins, prev_poses, cur_poses, submap_local_pose, hi, lo):
-        n = len(ranges_list)
-        rp = (C.c_void_p * n)(*[r.ctypes.data for r in ranges_list])
-        sizes = np.array([len(r) for r in ranges_list], np.int64)
+        """ranges_list: list of per-scan row arrays, or a HostScanBatch (the pointer table a C++ caller would hold)."""
+        hb = ranges_list if isinstance(ranges_list, HostScanBatch) else HostScanBatch(ranges_list)
         origins = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
-        results = (ScanResult * n)()
-        self.check(self.L.dl_frontend_match_batch(self.h, C.byref(options), n, rp, sizes, origins, len(origins),
+        results = (ScanResult * hb.n)()
+        self.check(self.L.dl_frontend_match_batch(self.h, C.byref(options), hb.n, hb.pointers, hb.sizes, origins, len(origins),
                                                   np.ascontiguousarray(prev_poses, np.float64),
                                                   np.ascontiguousarray(cur_poses, np.float64),
                                                   np.ascontiguousarray(submap_local_pose, np.float64), hi.h, lo.h,
                                                   results))
+        return results
+
+    def frontend_submit(self, options, host_batch, origins, prev_poses, cur_poses, submap_local_pose, hi, lo):
+        """Streaming form: returns as soon as the batch is enqueued; frontend_collect() returns its results."""
+        hb = host_batch if isinstance(host_batch, HostScanBatch) else HostScanBatch(host_batch)
+        origins = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        self.check(self.L.dl_frontend_submit(self.h, C.byref(options), hb.n, hb.pointers, hb.sizes, origins, len(origins),
+                                             np.ascontiguousarray(prev_poses, np.float64),
+                                             np.ascontiguousarray(cur_poses, np.float64),
+                                             np.ascontiguousarray(submap_local_pose, np.float64), hi.h, lo.h))
+        self._submitted = (hb, hb.n)   # keeps the host buffers alive until collect
+
+    def frontend_collect(self):
+        hb, n = self._submitted
+        results = (ScanResult * n)()
+        self.check(self.L.dl_frontend_collect(self.h, n, results))
+        self._submitted = None
         return results
 
     def frontend_match_batch_dev(self, options, ranges_dev_ptr, cap_rows, sizes, origins, prev_poses, cur_poses,

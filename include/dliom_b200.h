@@ -291,6 +291,11 @@ typedef struct dl_frontend_options { /* C/mapping/proto/3d/local_trajectory_buil
   double scan_period;
   dl_rtcsm_options real_time_correlative_scan_matcher;
   dl_ceres_options ceres_scan_matcher;
+  /* Host-buffer calls only. 0: ranges[b] are unrelated buffers, one upload per scan. > 0: the caller guarantees that the
+   * scans sit in ONE allocation at a constant stride, ranges[b] == (char*)ranges[0] + b * stride * row bytes with
+   * stride >= every sizes[b]; each sub-batch is then uploaded by a single strided copy (rows between a scan's end and the
+   * next scan's start are read but ignored). Checked against the pointers; DL_ERR_ARG if they disagree. */
+  int64_t host_scan_stride_rows;
 } dl_frontend_options;
 
 typedef struct dl_scan_result {
@@ -320,6 +325,18 @@ int dl_frontend_match_batch(dl_context* ctx, const dl_frontend_options* options,
                             int32_t num_origins, const double* prev_poses, const double* predicted_poses,
                             const double* submap_local_pose, const dl_grid* high_resolution_grid,
                             const dl_grid* low_resolution_grid, dl_scan_result* results);
+
+/* Streaming form of dl_frontend_match_batch: submit enqueues the uploads, every kernel and the download of the results into
+ * pinned staging and returns WITHOUT waiting; collect blocks until that batch is finished and copies the results out.
+ * One batch may be in flight per context; a caller that wants the upload of batch i+1 to overlap the tail of batch i
+ * alternates between two contexts (grids are shared read-only between contexts of the same device), which is how
+ * bench.py's e2e loop keeps the PCIe link busy. The host buffers must stay valid (and should be pinned) until collect.
+ * Any other call on a context with a batch in flight fails with DL_ERR_ARG. */
+int dl_frontend_submit(dl_context* ctx, const dl_frontend_options* options, int32_t num_scans, const void* const* ranges,
+                       const int64_t* sizes, const float* origins, int32_t num_origins, const double* prev_poses,
+                       const double* predicted_poses, const double* submap_local_pose,
+                       const dl_grid* high_resolution_grid, const dl_grid* low_resolution_grid);
+int dl_frontend_collect(dl_context* ctx, int32_t num_scans, dl_scan_result* results);
 
 /* Device-resident variant: ranges_dev is ONE device buffer of num_scans * cap_rows RangeMeasurement rows; scan s
  * occupies rows [s * cap_rows, s * cap_rows + sizes[s]). Results stay in results_dev (device) until

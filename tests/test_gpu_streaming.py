@@ -1,0 +1,99 @@
+"""dl_frontend_submit / dl_frontend_collect (the streaming form of the host-buffer front end): same results as the blocking
+call, bit for bit; two contexts in flight at once; misuse is refused instead of corrupting the batch in flight."""
+import numpy as np
+import pytest
+
+from helpers import workload
+
+pytestmark = pytest.mark.gpu
+
+
+def rows16(scans):
+    return [np.ascontiguousarray(s.view(np.uint8).reshape(-1, 32)[:, :16]).view(np.float32).reshape(-1, 4) for s in scans]
+
+
+def same(a, b):
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert list(x.pose_estimate_local) == list(y.pose_estimate_local)
+        assert (x.ok, x.num_first_filter, x.num_returns, x.num_high_resolution, x.num_low_resolution) == \
+               (y.ok, y.num_first_filter, y.num_returns, y.num_high_resolution, y.num_low_resolution)
+        assert x.summary.num_iterations == y.summary.num_iterations and x.summary.final_cost == y.summary.final_cost
+
+
+def test_submit_collect_equals_blocking_call(orc):
+    import dliom
+    w = workload(beams=16, num_map_scans=8, num_scans=12)
+    a, b = dliom.Context(0), dliom.Context(0)
+    hi, lo = dliom.Grid.from_oracle(a, w["hi"]), dliom.Grid.from_oracle(a, w["lo"])
+    fo = dliom.FrontendOptions.from_oracle(w["opts"])
+    fo.range_row_floats = 4
+    scans = rows16(w["scans"])
+    args = (w["origin"], w["prev"], w["cur"], w["submap_pose"], hi, lo)
+    want = a.frontend_match_batch(fo, scans, *args)
+    assert all(r.ok for r in want)
+    # one context, submit then collect
+    a.frontend_submit(fo, scans, *args)
+    same(a.frontend_collect(), want)
+    # two contexts in flight at once (grids shared read-only), collected in either order, repeatedly
+    first = (scans[:7], w["prev"][:7], w["cur"][:7])
+    second = (scans[7:], w["prev"][7:], w["cur"][7:])
+    for _ in range(3):
+        a.frontend_submit(fo, first[0], w["origin"], first[1], first[2], w["submap_pose"], hi, lo)
+        b.frontend_submit(fo, second[0], w["origin"], second[1], second[2], w["submap_pose"], hi, lo)
+        rb = b.frontend_collect()
+        ra = a.frontend_collect()
+        same(list(ra) + list(rb), want)
+    a.close(); b.close()
+
+
+def test_submit_misuse_is_refused(orc):
+    import dliom
+    w = workload(beams=16, num_map_scans=8, num_scans=12)
+    c = dliom.Context(0)
+    hi, lo = dliom.Grid.from_oracle(c, w["hi"]), dliom.Grid.from_oracle(c, w["lo"])
+    fo = dliom.FrontendOptions.from_oracle(w["opts"])
+    fo.range_row_floats = 4
+    scans = rows16(w["scans"])
+    args = (w["origin"], w["prev"], w["cur"], w["submap_pose"], hi, lo)
+    with pytest.raises(dliom.DlError):
+        c._submitted = (None, 12)
+        c.frontend_collect()                       # nothing submitted
+    c.frontend_submit(fo, scans, *args)
+    with pytest.raises(dliom.DlError):
+        c.frontend_submit(fo, scans, *args)        # second batch on the same context
+    with pytest.raises(dliom.DlError):
+        c.voxel_filter(np.zeros((10, 3), np.float32), 0.5)   # scratch is owned by the batch in flight
+    assert all(r.ok for r in c.frontend_collect())
+    keep = c.voxel_filter(np.zeros((10, 3), np.float32), 0.5)  # and usable again afterwards
+    assert len(keep) == 1
+    c.close()
+
+
+def test_strided_host_layout_single_copy(orc):
+    """host_scan_stride_rows: scans in one allocation at a constant stride are uploaded with one strided copy per
+    sub-batch; same results as the per-scan copies, and a stride that does not describe the pointers is refused."""
+    import dliom
+    w = workload(beams=16, num_map_scans=8, num_scans=12)
+    c = dliom.Context(0)
+    hi, lo = dliom.Grid.from_oracle(c, w["hi"]), dliom.Grid.from_oracle(c, w["lo"])
+    fo = dliom.FrontendOptions.from_oracle(w["opts"])
+    fo.range_row_floats = 4
+    scans = rows16(w["scans"])
+    args = (w["origin"], w["prev"], w["cur"], w["submap_pose"], hi, lo)
+    want = c.frontend_match_batch(fo, scans, *args)
+    stride = max(len(s) for s in scans) + 5
+    block = np.full((len(scans), stride, 4), np.nan, np.float32)      # NaN padding must never be looked at
+    for b, s in enumerate(scans):
+        block[b, :len(s)] = s
+    views = [block[b, :len(s)] for b, s in enumerate(scans)]
+    fo.host_scan_stride_rows = stride
+    same(c.frontend_match_batch(fo, views, *args), want)
+    c.frontend_submit(fo, views, *args)
+    same(c.frontend_collect(), want)
+    with pytest.raises(dliom.DlError):
+        c.frontend_match_batch(fo, scans, *args)                      # independent buffers, but a stride was promised
+    fo.host_scan_stride_rows = 3
+    with pytest.raises(dliom.DlError):
+        c.frontend_match_batch(fo, views, *args)                      # smaller than a scan
+    c.close()

@@ -1,5 +1,11 @@
-for cd in 1 2; do for ch in 2 4 8; do
-DLIOM_CHUNKS_DEV=$cd DLIOM_CHUNKS_HOST=$ch python bench.py --steps 10 --warmup 3 2>&1 | tail -1 | python -c "
+# A/B of the front-end pipeline shapes on one box: python bench lines reduced to the numbers that matter.
+run() {
+  env "$@" python bench.py --steps 10 --warmup 3 --cpu-sample 8 ${BATCH:+--batch $BATCH} 2>&1 | tail -1 | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('dev_chunks=$cd host_chunks=$ch', 'value %.0f ms %.3f | e2e %.0f ms %.3f' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step']), {k:v['ms_per_step'] for k,v in d['roofline']['stages'].items()})"
-done; done
+d=json.loads(sys.stdin.read()); e=d['e2e']; print('$*', 'batch', d['config']['scans_per_step_per_gpu'], 'value %.0f ms %.3f | e2e(stream) %.0f ms %.3f | sync %.0f ms %.3f | pcie %s copy-only %s same %s' % (d['value'], d['ms_per_step'], e['value'], e['ms_per_step'], e['sync_call']['value'], e['sync_call']['ms_per_step'], e.get('pcie_h2d_gbs'), e.get('copy_only_ms_per_step'), e.get('streaming_equals_sync_results')), d['parity_vs_cpu']['rmse_m'])"
+}
+run DLIOM_BENCH_PER_SCAN_COPIES=1
+run DLIOM_CHUNKS_HOST=5
+run DLIOM_CHUNKS_HOST=4
+run DLIOM_CHUNKS_HOST=8
+BATCH=296 run DLIOM_CHUNKS_HOST=5
