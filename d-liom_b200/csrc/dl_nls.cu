@@ -20,11 +20,19 @@
 // mix exactly, so the piecewise-polynomial pieces are the same ones the CPU path picks.
 //
 // Algorithmic bytes: 12 B point + 8 corners * 2 B = 28 B per point per evaluation.
+#include <cstdlib>
+#include <type_traits>
+
 #include "dl_internal.cuh"
 
 namespace dl {
 namespace {
 
+// Threads per problem. The kernels are written for any multiple of 32 up to kBlock: the evaluation pass strides by
+// blockDim.x and the LM state machine runs on thread 0 either way. A scan-matching problem has only a few hundred points
+// after the adaptive filters; smaller CTAs would let more problems share an SM (registers per problem = 170 x threads),
+// but the evaluation pass (8 dependent-load tree walks per point) then serialises inside each thread and the whole
+// solve gets slower: see nls_block_threads() for the measurement.
 constexpr int kBlock = 256;
 constexpr int kWarps = kBlock / 32;
 constexpr int kRed = 28;  // cost, g[6], H upper triangle [21]
@@ -164,7 +172,7 @@ __device__ void evaluate(const NlsOptions& opt, const NlsProblem& prob, Shared& 
     const double s = sh.scaling[k];
     const float* __restrict__ cloud = prob.cloud[k];
     const GridView g = prob.grid[k];
-    for (int i = threadIdx.x; i < n; i += kBlock) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const Vec3d v{(double)cloud[3 * i], (double)cloud[3 * i + 1], (double)cloud[3 * i + 2]};
       const Vec3d w = add(rotate(q, v), Vec3d{x[0], x[1], x[2]});
       double m, gx, gy, gz;
@@ -211,8 +219,8 @@ __device__ void evaluate(const NlsOptions& opt, const NlsProblem& prob, Shared& 
   __syncthreads();
   if (threadIdx.x < kRed) {
     double v = 0.0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) v += sh.red[w][threadIdx.x];
+    const int warps = blockDim.x >> 5;
+    for (int w = 0; w < warps; ++w) v += sh.red[w][threadIdx.x];
     sh.acc[threadIdx.x] = v;
   }
   __syncthreads();
@@ -316,7 +324,7 @@ __device__ void imu_residual_jacobian(const ImuTerm& m, const double* x /*16*/, 
 __device__ void imu_normal_equations(const ImuTerm& m, const double* x, ImuShared& is) {
   if (threadIdx.x == 0) imu_residual_jacobian(m, x, is);
   __syncthreads();
-  for (int e = threadIdx.x; e < 225; e += kBlock) {
+  for (int e = threadIdx.x; e < 225; e += blockDim.x) {
     const int c = e / 15, b = e % 15;
     double s = 0;
     for (int d = 0; d < 15; ++d) s += m.W[c * 15 + d] * is.J[d][b];
@@ -328,7 +336,7 @@ __device__ void imu_normal_equations(const ImuTerm& m, const double* x, ImuShare
     is.Wr[threadIdx.x] = s;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < 225; e += kBlock) {
+  for (int e = threadIdx.x; e < 225; e += blockDim.x) {
     const int a = e / 15, b = e % 15;
     double s = 0;
     for (int c = 0; c < 15; ++c) s += is.J[c][a] * is.WJ[c][b];
@@ -339,7 +347,7 @@ __device__ void imu_normal_equations(const ImuTerm& m, const double* x, ImuShare
     for (int c = 0; c < 15; ++c) s += is.J[c][threadIdx.x] * is.Wr[c];
     is.g[threadIdx.x] = s;
   }
-  if (threadIdx.x == 32) {
+  if (threadIdx.x == 31) {
     double s = 0;
     for (int c = 0; c < 15; ++c) s += is.r[c] * is.Wr[c];
     is.cost2 = s;
@@ -622,9 +630,9 @@ __device__ __forceinline__ void solve_body(const NlsOptions& opt, const NlsProbl
   constexpr int NA = Dims<N>::ambient;
   __shared__ Shared sh;
   __shared__ LmStateT<N> st;
-  __shared__ ImuShared is_storage[FUSED ? 1 : 0 + 1];
+  __shared__ typename std::conditional<FUSED, ImuShared, int>::type is_storage;  // 7 KiB only when the IMU term is there
   __shared__ double xfull[16];
-  ImuShared* is = FUSED ? &is_storage[0] : nullptr;
+  ImuShared* is = FUSED ? reinterpret_cast<ImuShared*>(&is_storage) : nullptr;
   {
     double x[7], target_t[3], target_q_inv[4];
     setup_problem(opt, prob, sh, x, target_t, target_q_inv);
@@ -724,9 +732,20 @@ __global__ void grid_lookup_kernel(GridView g, int64_t n, const int32_t* __restr
 
 }  // namespace
 
+// Threads per problem (multiple of 32, <= kBlock). DLIOM_NLS_BLOCK overrides for experiments.
+static int nls_block_threads() {
+  static const int threads = [] {
+    int t = kBlock;  // measured on B200 (profiles/r1_pipeline_variants.log): 256 > 128 > 64 > 32 for ~400-point problems
+    if (const char* env = std::getenv("DLIOM_NLS_BLOCK")) t = std::atoi(env);
+    t = (t / 32) * 32;
+    return t < 32 ? 32 : (t > kBlock ? kBlock : t);
+  }();
+  return threads;
+}
+
 int launch_nls(dl_context* ctx, const NlsOptions& opt, const NlsProblem* problems_dev, int count, NlsOutput* out_dev) {
   if (count <= 0) return DL_OK;
-  nls_solve_kernel<<<count, kBlock, 0, ctx->stream>>>(opt, problems_dev, out_dev);
+  nls_solve_kernel<<<count, nls_block_threads(), 0, ctx->stream>>>(opt, problems_dev, out_dev);
   DL_LAUNCH_CHECK(ctx, "nls_solve_kernel");
   return DL_OK;
 }
@@ -734,7 +753,7 @@ int launch_nls(dl_context* ctx, const NlsOptions& opt, const NlsProblem* problem
 int launch_nls_fused(dl_context* ctx, const NlsOptions& opt, const NlsProblem* problems_dev, const void* imu_terms_dev,
                      const double* initial16_dev, int count, FusedOutput* out_dev) {
   if (count <= 0) return DL_OK;
-  nls_fused_kernel<<<count, kBlock, 0, ctx->stream>>>(opt, problems_dev, (const ImuTerm*)imu_terms_dev, initial16_dev, out_dev);
+  nls_fused_kernel<<<count, nls_block_threads(), 0, ctx->stream>>>(opt, problems_dev, (const ImuTerm*)imu_terms_dev, initial16_dev, out_dev);
   DL_LAUNCH_CHECK(ctx, "nls_fused_kernel");
   return DL_OK;
 }

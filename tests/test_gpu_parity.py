@@ -260,6 +260,27 @@ def test_ingest_scan_without_point_times(ctx, orc):
     assert np.array_equal(got["returns_tracking"].view(np.uint32), want["returns_tracking"].view(np.uint32))
 
 
+def test_ingest_scan_any_time_order(ctx, orc):
+    """The deskew pose is shared by runs of equal point times inside 32-point tiles. Orders that defeat the grouping must
+    give the same bits: rows shuffled (hardly any two neighbours share a time), every point with its own time (one
+    pose per point, the table's worst case), and a scan whose size is not a multiple of 32."""
+    import dliom
+    w = workload()
+    fo = dliom.FrontendOptions.from_oracle(w["opts"])
+    rng = np.random.default_rng(12)
+    base = w["scans"][1]
+    shuffled = base[rng.permutation(len(base))].copy()
+    shuffled["t"][-1] = 0.0
+    unique = base[:5003].copy()
+    unique["t"] = np.linspace(-0.1, 0.0, len(unique)).astype(np.float32)
+    for rows in (shuffled, unique, base[:4097].copy()):
+        want = orc.ingest_scan(w["opts"], rows, w["origin"], w["prev"][1], w["cur"][1])
+        got = ctx.ingest_scan(fo, rows, w["origin"], w["prev"][1], w["cur"][1])
+        assert np.array_equal(got["first_keep"], want["first_keep"])
+        for k in ("returns_local", "returns_tracking", "misses_tracking", "current_pose"):
+            assert np.array_equal(got[k].view(np.uint32), want[k].view(np.uint32)), k
+
+
 def test_frontend_batch_timed_point_cloud_rows(ctx, orc):
     """16-byte TimedPointCloud rows (x y z t, single sensor) give exactly the results of the 32-byte RangeMeasurement rows."""
     import dliom
