@@ -170,6 +170,7 @@ void dl_context_destroy(dl_context* ctx) {
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->tail_stream) cudaStreamDestroy(ctx->tail_stream);
   if (ctx->batch_done) cudaEventDestroy(ctx->batch_done);
+  if (ctx->d_fcsm_lut) cudaFree(ctx->d_fcsm_lut);
   if (ctx->staging_done) cudaEventDestroy(ctx->staging_done);
   delete ctx;
 }

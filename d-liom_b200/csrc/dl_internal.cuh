@@ -51,6 +51,7 @@ struct dl_context {
   cudaStream_t tail_stream = nullptr;   // high priority: the latency-bound back half (adaptive filter, LM solve) of every sub-batch
   cudaEvent_t staging_done = nullptr;   // the pinned staging block of the previous call has been consumed
   cudaEvent_t batch_done = nullptr;     // dl_frontend_submit: everything of the batch in flight, incl. the result download
+  uint8_t* d_fcsm_lut = nullptr;        // loop-closure search: cell value -> 8-bit precomputation value (dl_fcsm.cu), built on first use
   int in_flight = 0;                    // scans of the submitted, not yet collected batch
   size_t results_staging_offset = 0;    // where in h_pinned the in-flight batch's results land
   std::string error;

@@ -82,6 +82,9 @@ def _constraint_worker(rank, world, port, tmp):
         assert all(shard.owner_of_submap(submaps[i], world) == rank for i in mine)
         rows = shard.constraint_rows([submaps[i] for i in mine], [nodes[i] for i in mine], [hits[i] for i in mine])
         table = shard.all_gather_constraints(dist, rows)
+        biggest = max(len(shard.shard_by_owner(submaps, r, world)) for r in range(world))
+        one_call = shard.all_gather_constraints(dist, rows, max_rows=biggest)   # single fixed-size collective
+        assert np.array_equal(table, one_call)
         np.save(os.path.join(tmp, f"table{rank}.npy"), table)
     finally:
         dist.destroy_process_group()
@@ -108,3 +111,40 @@ def test_constraint_all_gather_two_ranks_gloo(tmp_path):
     assert np.array_equal(t0, t1) and np.array_equal(t0, single)
     assert len(single) == sum(h.found for h in hits) and t0.shape[1] == len(shard.CONSTRAINT_COLUMNS)
     assert np.all(np.diff(t0[:, 0]) >= 0)
+
+
+def _broadcast_worker(rank, world, port, tmp):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "d-liom_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"),
+                    os.path.join(ROOT, "tools")]
+    import torch.distributed as dist
+    from dliom import shard
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import orc
+        cells = None
+        if rank == 1:   # rank 1 owns the finished submap
+            from helpers import workload
+            cells = workload(beams=16, num_map_scans=3, num_scans=1)["hi"].export()
+        xs, ys, zs, vs = shard.broadcast_cells(dist, cells, src=1)
+        g = orc.Grid(0.1)   # every rank rebuilds the grid from the broadcast cells
+        for x, y, z, v in zip(xs[:2000], ys[:2000], zs[:2000], vs[:2000]):
+            g.set_value((int(x), int(y), int(z)), int(v))
+        ragged = shard.all_gather_ragged(dist, np.full((3 + rank, 2), float(rank), np.float32))
+        np.savez(os.path.join(tmp, f"cells{rank}.npz"), xs=xs, ys=ys, zs=zs, vs=vs,
+                 probe=np.array([g.value((int(xs[i]), int(ys[i]), int(zs[i]))) for i in range(0, 2000, 97)]),
+                 ragged0=ragged[0], ragged1=ragged[1])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_submap_broadcast_two_ranks_gloo(tmp_path):
+    """A finished submap crosses ranks once, as cells in the ToProto layout; ragged node data is all-gathered."""
+    port = 33500 + os.getpid() % 2000
+    mp.spawn(_broadcast_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "cells0.npz"), np.load(tmp_path / "cells1.npz")
+    for k in ("xs", "ys", "zs", "vs", "probe", "ragged0", "ragged1"):
+        assert np.array_equal(a[k], b[k]), k
+    assert len(a["xs"]) > 2000 and a["vs"].dtype == np.uint16 and a["vs"].max() < 32768
+    assert np.array_equal(a["probe"], a["vs"][0:2000:97])
+    assert a["ragged0"].shape == (3, 2) and a["ragged1"].shape == (4, 2) and a["ragged1"][0, 0] == 1.0

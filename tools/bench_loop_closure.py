@@ -58,6 +58,7 @@ def main():
         node_hi.append(pts[hk]); node_lo.append(pts[lk]); node_truth.append(np.array(w0["truth"][k], np.float64))
     pairs = [(s, n) for s in range(args.submaps) for n in range(args.nodes)]
     mine = shard.shard_by_owner([s for s, _ in pairs], rank, world)
+    max_shard = max(len(shard.shard_by_owner([s for s, _ in pairs], r, world)) for r in range(world))
     owned = sorted({pairs[i][0] for i in mine})
     grids = {s: (dliom.Grid.from_oracle(ctx, built[s % args.distinct]["hi"]),
                  dliom.Grid.from_oracle(ctx, built[s % args.distinct]["lo"])) for s in owned}
@@ -77,7 +78,7 @@ def main():
         cons = ctx.constraint_search_batch(opt, **call)
         t1 = time.perf_counter()
         rows = shard.constraint_rows([pairs[i][0] for i in mine], [pairs[i][1] for i in mine], cons)
-        table = shard.all_gather_constraints(dist if world > 1 else None, rows, dev)
+        table = shard.all_gather_constraints(dist if world > 1 else None, rows, dev, max_rows=max_shard)
         torch.cuda.synchronize()
         return t1 - t0, time.perf_counter() - t1, table
 
