@@ -959,6 +959,7 @@ int coarse_search(dl_context* ctx, Arena& a, const dl_fcsm_options& o, float min
   }
   DL_TRY(h2d(ctx, out->d_pairs, pairs.data(), n));
   DL_TRY(sync(ctx));  // `pairs` is pageable host memory
+  StageScope st(ctx, "loop_closure_search");
   return launch_fcsm(ctx, out->d_pairs, n, max_points, max_candidates, out->d_best, out->d_picks, d_all_scores);
 }
 int check_pairs(dl_context* ctx, int count, const double* guesses, const float* hi_pts, const int64_t* hi_off, const float* lo_pts,
@@ -1048,7 +1049,10 @@ int dl_constraint_search_batch(dl_context* ctx, const dl_constraint_options* opt
     NlsOutput* d_out = a.take<NlsOutput>(n);
     DL_TRY(h2d(ctx, d_problems, problems.data(), n));
     DL_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(NlsOutput) * n, ctx->stream));
-    DL_TRY(launch_nls(ctx, nls, d_problems, n, d_out));
+    {
+      StageScope st(ctx, "loop_closure_refine");
+      DL_TRY(launch_nls(ctx, nls, d_problems, n, d_out));
+    }
     std::vector<FcsmPick> picks(n);
     std::vector<NlsOutput> out(n);
     DL_TRY(d2h(ctx, picks.data(), cs.d_picks, n));

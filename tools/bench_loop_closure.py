@@ -87,10 +87,26 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    ctx.set_profiling(True)
+    ctx.read_profile()
     search, gather, table = 0.0, 0.0, None
     for _ in range(args.steps):
         a, b, table = step()
         search += a; gather += b
+    profile = ctx.read_profile()
+    ctx.set_profiling(False)
+    # how long a bare small collective takes here (the exchange is latency, not bandwidth)
+    small_ms = None
+    if world > 1:
+        x = torch.zeros(16, dtype=torch.float64, device=dev)
+        for _ in range(3):
+            dist.all_reduce(x)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            dist.all_reduce(x)
+        torch.cuda.synchronize()
+        small_ms = (time.perf_counter() - t0) * 100.0
     search = shard.max_over_ranks(dist if world > 1 else None, search, dev)
     gather = shard.max_over_ranks(dist if world > 1 else None, gather, dev)
     if rank == 0:
@@ -121,6 +137,8 @@ def main():
             "metric": "loop-closure constraint searches/s (coarse 3-DoF window + refinement), whole job",
             "value": len(pairs) / total, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total, "search_ms": 1e3 * search / args.steps, "allgather_ms": 1e3 * gather / args.steps,
+            "device_ms_rank0": {k: round(v[0] / max(v[1], 1), 3) for k, v in profile.items()},
+            "nccl_small_allreduce_ms": small_ms,
             "scaling": "strong", "higher_is_better": True, "data": "synthetic",
             "config": {"workload": "configs[3] shape: %d submaps x %d nodes (%d-beam), window 5 m x 5 m x 1 m at 0.1 m = 214 221 leaves/pair"
                                    % (args.submaps, args.nodes, args.beams),
