@@ -138,7 +138,9 @@ __device__ __forceinline__ int ingest_survivor(const FrontendArgs& a, int b, con
       for (;;) {
         const unsigned long long prev = atomicCAS(keys + hh, kEmpty64, key);
         if (prev == kEmpty64 || prev == key) {
-          atomicMin(mins + hh, (uint32_t)i);
+          // (index << 1) | miss: ordered by index (a voxel key holds one class only), and the winner's class reaches
+          // the compaction kernels through the byte map without a second look at the survivor record
+          atomicMin(mins + hh, ((uint32_t)i << 1) | (cls == 2 ? 1u : 0u));
           break;
         }
         hh = (hh + 1) & mask2;
@@ -231,11 +233,10 @@ __device__ __forceinline__ int block_exclusive_scan(int value, int* total) {
   return base + inc - value;
 }
 
-// win[i] is set by fe_mark_winners for the points that own their second-filter voxel; their class (1 return,
-// 2 miss) sits next to the local-frame point in local[i].w.
+// win[i] is set by fe_mark_winners for the points that own their second-filter voxel: 1 return, 2 miss, 0 neither.
 __device__ __forceinline__ int second_filter_class(const FrontendArgs& a, int b, int i, int n) {
   if (i >= n) return 0;
-  return a.win[(size_t)b * a.cap + i] ? __float_as_int(a.local[((size_t)b * a.cap + i) * 4 + 3]) : 0;
+  return a.win[(size_t)b * a.cap + i];
 }
 
 // The second filter's survivors are the min-index entries of its non-empty slots: stream the table once.
@@ -245,8 +246,8 @@ __global__ void __launch_bounds__(kBlock) fe_mark_winners(FrontendArgs a) {
   const uint32_t* mins = a.min2 + (size_t)b * a.tcap2;
   uint8_t* win = a.win + (size_t)b * a.cap;
   for (int h = blockIdx.x * kBlock + threadIdx.x; h < (int)a.tcap2; h += gridDim.x * kBlock) {
-    const uint32_t i = __ldcg(mins + h);
-    if (i != kEmpty32) win[i] = 1;  // store only: no read-modify-write latency
+    const uint32_t m = __ldcg(mins + h);
+    if (m != kEmpty32) win[m >> 1] = (uint8_t)(1 + (m & 1u));  // store only: no read-modify-write latency
   }
 }
 

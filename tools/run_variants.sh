@@ -2,10 +2,11 @@
 run() {
   env "$@" python bench.py --steps 10 --warmup 3 --cpu-sample 8 ${BATCH:+--batch $BATCH} 2>&1 | tail -1 | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); e=d['e2e']; print('$*', 'batch', d['config']['scans_per_step_per_gpu'], 'value %.0f ms %.3f | e2e(stream) %.0f ms %.3f | sync %.0f ms %.3f' % (d['value'], d['ms_per_step'], e['value'], e['ms_per_step'], e['sync_call']['value'], e['sync_call']['ms_per_step']), {k:v['ms_per_step'] for k,v in d['roofline']['stages'].items()}, d['parity_vs_cpu']['rmse_m'], d['parity_vs_cpu']['max_m'])"
+d=json.loads(sys.stdin.read()); e=d['e2e']; print('$*', 'batch', d['config']['scans_per_step_per_gpu'], 'value %.0f ms %.3f | e2e(stream) %.0f ms %.3f | sync %.0f ms %.3f | pcie %s' % (d['value'], d['ms_per_step'], e['value'], e['ms_per_step'], e['sync_call']['value'], e['sync_call']['ms_per_step'], e['pcie_h2d_gbs']), {k:v['ms_per_step'] for k,v in d['roofline']['stages'].items()}, d['parity_vs_cpu']['rmse_m'])"
 }
-run DLIOM_BENCH_ONE_CONTEXT=1
 run A=1
-run DLIOM_INGEST_GRID=32
-run DLIOM_INGEST_GRID=64
-run DLIOM_INGEST_GRID=96
+run DLIOM_CHUNKS_DEV=1
+BATCH=296 run A=1
+BATCH=296 run DLIOM_CHUNKS_DEV=4
+BATCH=592 run DLIOM_CHUNKS_DEV=4
+BATCH=592 run DLIOM_CHUNKS_DEV=8
