@@ -1118,6 +1118,40 @@ bool information_matrix(const double* sigma, double weight, double* W) {
     }
   return true;
 }
+// One pre-integration factor in the submap frame (the grids live there and the solve is frame-invariant) + the initial
+// 16-vector of state j. False if the covariance is not positive definite.
+bool build_imu_term(const Rigidd& to_submap, const dl_nav_state& si, const dl_nav_state& sj, const dl_preintegration& m,
+                    const double* gravity, double imu_weight, HostImuTerm* t, double* x16) {
+  const Rigidd pose_i = compose(to_submap, Rigidd{{si.p[0], si.p[1], si.p[2]}, {si.q[0], si.q[1], si.q[2], si.q[3]}});
+  const Rigidd pose_j = compose(to_submap, Rigidd{{sj.p[0], sj.p[1], sj.p[2]}, {sj.q[0], sj.q[1], sj.q[2], sj.q[3]}});
+  const Vec3d vi = rotate(to_submap.q, Vec3d{si.v[0], si.v[1], si.v[2]});
+  const Vec3d vj = rotate(to_submap.q, Vec3d{sj.v[0], sj.v[1], sj.v[2]});
+  const Vec3d G = rotate(to_submap.q, Vec3d{gravity[0], gravity[1], gravity[2]});
+  t->pi[0] = pose_i.t.x; t->pi[1] = pose_i.t.y; t->pi[2] = pose_i.t.z;
+  t->qi[0] = pose_i.q.w; t->qi[1] = pose_i.q.x; t->qi[2] = pose_i.q.y; t->qi[3] = pose_i.q.z;
+  t->vi[0] = vi.x; t->vi[1] = vi.y; t->vi[2] = vi.z;
+  for (int k = 0; k < 3; ++k) {
+    t->bai[k] = si.ba[k]; t->bgi[k] = si.bg[k];
+    t->dp[k] = m.delta_p[k]; t->dv[k] = m.delta_v[k];
+  }
+  for (int k = 0; k < 4; ++k) t->dq[k] = m.delta_q[k];
+  t->G[0] = G.x; t->G[1] = G.y; t->G[2] = G.z;
+  t->sum_dt = m.sum_dt;
+  if (!information_matrix(m.covariance, imu_weight, t->W)) return false;
+  pose_to7(pose_j, x16);
+  x16[7] = vj.x; x16[8] = vj.y; x16[9] = vj.z;
+  for (int k = 0; k < 3; ++k) { x16[10 + k] = sj.ba[k]; x16[13 + k] = sj.bg[k]; }
+  return true;
+}
+// Solver state (submap frame) -> dl_nav_state in the local frame.
+void state_to_local(const Rigidd& submap, const double* x, dl_nav_state* o) {
+  const Rigidd pose = compose(submap, pose_from7(x));
+  const Vec3d v = rotate(submap.q, Vec3d{x[7], x[8], x[9]});
+  o->p[0] = pose.t.x; o->p[1] = pose.t.y; o->p[2] = pose.t.z;
+  o->q[0] = pose.q.w; o->q[1] = pose.q.x; o->q[2] = pose.q.y; o->q[3] = pose.q.z;
+  o->v[0] = v.x; o->v[1] = v.y; o->v[2] = v.z;
+  for (int k = 0; k < 3; ++k) { o->ba[k] = x[10 + k]; o->bg[k] = x[13 + k]; }
+}
 }  // namespace
 
 extern "C" {
@@ -1194,32 +1228,10 @@ int dl_fused_match_batch(dl_context* ctx, const dl_ceres_options* options, doubl
   std::vector<HostImuTerm> terms(count);
   std::vector<double> init16((size_t)count * 16);
   for (int c = 0; c < count; ++c) {
-    // everything is moved into the submap frame: the grids live there and the solve is frame-invariant
     const Rigidd to_submap = inverse(pose_from7(submap_local_poses + 7 * c));
-    const dl_nav_state& si = states_i[c];
-    const dl_nav_state& sj = initial_states_j[c];
-    const Rigidd pose_i = compose(to_submap, Rigidd{{si.p[0], si.p[1], si.p[2]}, {si.q[0], si.q[1], si.q[2], si.q[3]}});
-    const Rigidd pose_j = compose(to_submap, Rigidd{{sj.p[0], sj.p[1], sj.p[2]}, {sj.q[0], sj.q[1], sj.q[2], sj.q[3]}});
-    const Vec3d vi = rotate(to_submap.q, Vec3d{si.v[0], si.v[1], si.v[2]});
-    const Vec3d vj = rotate(to_submap.q, Vec3d{sj.v[0], sj.v[1], sj.v[2]});
-    const Vec3d G = rotate(to_submap.q, Vec3d{gravity[0], gravity[1], gravity[2]});
-    HostImuTerm& t = terms[c];
-    t.pi[0] = pose_i.t.x; t.pi[1] = pose_i.t.y; t.pi[2] = pose_i.t.z;
-    t.qi[0] = pose_i.q.w; t.qi[1] = pose_i.q.x; t.qi[2] = pose_i.q.y; t.qi[3] = pose_i.q.z;
-    t.vi[0] = vi.x; t.vi[1] = vi.y; t.vi[2] = vi.z;
-    for (int k = 0; k < 3; ++k) {
-      t.bai[k] = si.ba[k]; t.bgi[k] = si.bg[k];
-      t.dp[k] = preints[c].delta_p[k]; t.dv[k] = preints[c].delta_v[k];
-    }
-    for (int k = 0; k < 4; ++k) t.dq[k] = preints[c].delta_q[k];
-    t.G[0] = G.x; t.G[1] = G.y; t.G[2] = G.z;
-    t.sum_dt = preints[c].sum_dt;
-    if (!information_matrix(preints[c].covariance, imu_weight, t.W))
-      return ctx->fail(DL_ERR_ARG, "pre-integration covariance is not positive definite");
     double* x = init16.data() + 16 * c;
-    pose_to7(pose_j, x);
-    x[7] = vj.x; x[8] = vj.y; x[9] = vj.z;
-    for (int k = 0; k < 3; ++k) { x[10 + k] = sj.ba[k]; x[13 + k] = sj.bg[k]; }
+    if (!build_imu_term(to_submap, states_i[c], initial_states_j[c], preints[c], gravity, imu_weight, &terms[c], x))
+      return ctx->fail(DL_ERR_ARG, "pre-integration covariance is not positive definite");
     NlsProblem& p = problems[c];
     std::memset(&p, 0, sizeof(p));
     for (int k = 0; k < num_pairs; ++k) {
@@ -1245,15 +1257,7 @@ int dl_fused_match_batch(dl_context* ctx, const dl_ceres_options* options, doubl
   DL_TRY(d2h(ctx, out.data(), d_out, count));
   DL_TRY(sync(ctx));
   for (int c = 0; c < count; ++c) {
-    const Rigidd submap = pose_from7(submap_local_poses + 7 * c);
-    const double* x = out[c].state;
-    const Rigidd pose = compose(submap, pose_from7(x));
-    const Vec3d v = rotate(submap.q, Vec3d{x[7], x[8], x[9]});
-    dl_nav_state& o = states_j_out[c];
-    o.p[0] = pose.t.x; o.p[1] = pose.t.y; o.p[2] = pose.t.z;
-    o.q[0] = pose.q.w; o.q[1] = pose.q.x; o.q[2] = pose.q.y; o.q[3] = pose.q.z;
-    o.v[0] = v.x; o.v[1] = v.y; o.v[2] = v.z;
-    for (int k = 0; k < 3; ++k) { o.ba[k] = x[10 + k]; o.bg[k] = x[13 + k]; }
+    state_to_local(pose_from7(submap_local_poses + 7 * c), out[c].state, &states_j_out[c]);
     if (summaries) summaries[c] = out[c].summary;
   }
   return DL_OK;
@@ -1452,9 +1456,31 @@ int frontend_upload_small(dl_context* ctx, const dl_frontend_options& o, const F
 int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, float* d_ranges, int64_t in_cap,
                  const void* const* host_ranges, const int64_t* sizes, const float* origins, int num_origins,
                  const double* prev_poses, const double* cur_poses, const double* submap_local_pose, const dl_grid* hi,
-                 const dl_grid* lo, Arena& a, dl_scan_result* d_results) {
+                 const dl_grid* lo, Arena& a, dl_scan_result* d_results, const dl_frontend_imu* imu = nullptr,
+                 FusedOutput** d_fused_out = nullptr) {
   FrontendBuffers f;
   carve(a, num_scans, in_cap, num_origins, &f);
+  // optional IMU coupling: one pre-integration factor per scan, the 15-parameter solve instead of the 6-parameter one
+  HostImuTerm* d_terms = nullptr;
+  double* d_init16 = nullptr;
+  FusedOutput* d_fused = nullptr;
+  if (imu) {
+    d_terms = a.take<HostImuTerm>(num_scans);
+    d_init16 = a.take<double>((size_t)num_scans * 16);
+    d_fused = a.take<FusedOutput>(num_scans);
+    if (d_fused_out) *d_fused_out = d_fused;
+    std::vector<HostImuTerm> terms(num_scans);
+    std::vector<double> init16((size_t)num_scans * 16);
+    const Rigidd to_submap = inverse(pose_from7(submap_local_pose));
+    for (int b = 0; b < num_scans; ++b)
+      if (!build_imu_term(to_submap, imu->states_i[b], imu->predicted_states[b], imu->preintegrations[b], imu->gravity,
+                          imu->imu_weight, &terms[b], init16.data() + 16 * b))
+        return ctx->fail(DL_ERR_ARG, "pre-integration covariance is not positive definite");
+    DL_TRY(h2d(ctx, d_terms, terms.data(), num_scans));
+    DL_TRY(h2d(ctx, d_init16, init16.data(), (size_t)num_scans * 16));
+    DL_CUDA(ctx, cudaMemsetAsync(d_fused, 0, sizeof(FusedOutput) * num_scans, ctx->stream));
+    DL_TRY(sync(ctx));  // the staging vectors are pageable and local
+  }
   const int rf = row_floats_of(o);
   DL_TRY(frontend_upload_small(ctx, o, f, sizes, origins, num_origins, prev_poses, cur_poses, hi, lo));
   const FrontendArgs fa = make_frontend_args(o, f, d_ranges, in_cap, rf);
@@ -1575,12 +1601,16 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
       }
       {
         StageScope st(ctx, "nls_solve");
-        DL_TRY(launch_nls(ctx, to_nls_options(o.ceres_scan_matcher, 2), f.problems + b0, nb, f.nls_out + b0));
+        if (imu)  // pose part of the initial state comes from problems[].initial_dev like the plain solve's
+          DL_TRY(launch_nls_fused(ctx, to_nls_options(o.ceres_scan_matcher, 2), f.problems + b0, d_terms + b0, d_init16 + 16 * b0, nb,
+                                  d_fused + b0));
+        else
+          DL_TRY(launch_nls(ctx, to_nls_options(o.ceres_scan_matcher, 2), f.problems + b0, nb, f.nls_out + b0));
       }
       ResultArgs ra{};
       ra.batch = nb; ra.first_counts = f.n1 + b0; ra.return_counts = f.n2 + b0; ra.miss_counts = f.n3 + b0;
       ra.adaptive_counts = f.countsA + 2 * b0; ra.adaptive_cropped = f.croppedA + 2 * b0; ra.adaptive_passes = f.npassesA + 2 * b0;
-      ra.rtcsm_scores = have_scores ? f.rtcsm_scores + b0 : nullptr; ra.nls = f.nls_out + b0; ra.submap = submap;
+      ra.rtcsm_scores = have_scores ? f.rtcsm_scores + b0 : nullptr; ra.nls = f.nls_out + b0; ra.fused = imu ? d_fused + b0 : nullptr; ra.submap = submap;
       ra.results = d_results + b0; ra.error_flag = f.error_flag;
       DL_TRY(launch_finalize_results(ctx, ra));
       return DL_OK;
@@ -1647,7 +1677,8 @@ int dl_frontend_fetch_results(dl_context* ctx, const dl_scan_result* results_dev
 static int frontend_enqueue_host(dl_context* ctx, const dl_frontend_options* options, int32_t num_scans, const void* const* ranges,
                                  const int64_t* sizes, const float* origins, int32_t num_origins, const double* prev_poses,
                                  const double* predicted_poses, const double* submap_local_pose, const dl_grid* hi,
-                                 const dl_grid* lo, size_t pinned_extra, dl_scan_result** d_results_out) {
+                                 const dl_grid* lo, size_t pinned_extra, dl_scan_result** d_results_out,
+                                 const dl_frontend_imu* imu = nullptr, FusedOutput** d_fused_out = nullptr, size_t device_extra = 0) {
   int64_t max_size = 0;
   DL_TRY(check_frontend(ctx, options, num_scans, sizes, hi, lo, &max_size));
   if (!ranges || !origins || num_origins < 1 || !prev_poses || !predicted_poses || !submap_local_pose) return DL_ERR_ARG;
@@ -1666,13 +1697,13 @@ static int frontend_enqueue_host(dl_context* ctx, const dl_frontend_options* opt
   const size_t extra = options->use_online_correlative_scan_matching
                            ? rtcsm_scratch_bound(options->real_time_correlative_scan_matcher, hi->resolution, false) : 0;
   DL_TRY(ctx->reserve_device(frontend_bytes(num_scans, cap, num_origins, extra) + (size_t)num_scans * cap * 32 + 256 +
-                             (size_t)num_scans * sizeof(dl_scan_result) + 256));
+                             (size_t)num_scans * sizeof(dl_scan_result) + 256 + device_extra));
   if (pinned_extra) DL_TRY(ctx->reserve_pinned(frontend_small_bytes(num_scans, num_origins) + pinned_extra + 256));
   Arena a(ctx->d_scratch);
   float* d_ranges = a.take<float>((size_t)num_scans * cap * 8);
   *d_results_out = a.take<dl_scan_result>(num_scans);
   return frontend_run(ctx, *options, num_scans, d_ranges, cap, ranges, sizes, origins, num_origins, prev_poses,
-                      predicted_poses, submap_local_pose, hi, lo, a, *d_results_out);
+                      predicted_poses, submap_local_pose, hi, lo, a, *d_results_out, imu, d_fused_out);
 }
 
 int dl_frontend_match_batch(dl_context* ctx, const dl_frontend_options* options, int32_t num_scans,
@@ -1690,6 +1721,40 @@ int dl_frontend_match_batch(dl_context* ctx, const dl_frontend_options* options,
                                submap_local_pose, hi, lo, 0, &d_results));
   DL_TRY(d2h(ctx, results, d_results, num_scans));
   return sync(ctx);
+}
+
+int dl_frontend_match_batch_imu(dl_context* ctx, const dl_frontend_options* options, const dl_frontend_imu* imu,
+                                int32_t num_scans, const void* const* ranges, const int64_t* sizes, const float* origins,
+                                int32_t num_origins, const double* submap_local_pose, const dl_grid* hi, const dl_grid* lo,
+                                dl_scan_result* results) {
+  if (!ctx || !imu) return DL_ERR_ARG;
+  if (num_scans == 0) return DL_OK;
+  if (num_scans < 0 || !results || !imu->states_i || !imu->predicted_states || !imu->preintegrations || !imu->states_out ||
+      !(imu->imu_weight >= 0.))
+    return DL_ERR_ARG;
+  if (options && options->ceres_scan_matcher.only_optimize_yaw)
+    return ctx->fail(DL_ERR_ARG, "only_optimize_yaw is not supported by the fused solve");
+  if (options && options->use_online_correlative_scan_matching)
+    return ctx->fail(DL_ERR_ARG, "the correlative pre-match is not combined with the fused solve");
+  std::vector<double> prev((size_t)num_scans * 7), pred((size_t)num_scans * 7);
+  for (int b = 0; b < num_scans; ++b) {
+    const dl_nav_state& si = imu->states_i[b];
+    const dl_nav_state& sj = imu->predicted_states[b];
+    for (int k = 0; k < 3; ++k) { prev[7 * b + k] = si.p[k]; pred[7 * b + k] = sj.p[k]; }
+    for (int k = 0; k < 4; ++k) { prev[7 * b + 3 + k] = si.q[k]; pred[7 * b + 3 + k] = sj.q[k]; }
+  }
+  dl_scan_result* d_results = nullptr;
+  FusedOutput* d_fused = nullptr;
+  const size_t extra = (size_t)num_scans * (sizeof(HostImuTerm) + 128 + sizeof(FusedOutput)) + 1024;
+  DL_TRY(frontend_enqueue_host(ctx, options, num_scans, ranges, sizes, origins, num_origins, prev.data(), pred.data(),
+                               submap_local_pose, hi, lo, 0, &d_results, imu, &d_fused, extra));
+  std::vector<FusedOutput> fused(num_scans);
+  DL_TRY(d2h(ctx, results, d_results, num_scans));
+  DL_TRY(d2h(ctx, fused.data(), d_fused, num_scans));
+  DL_TRY(sync(ctx));
+  const Rigidd submap = pose_from7(submap_local_pose);
+  for (int b = 0; b < num_scans; ++b) state_to_local(submap, fused[b].state, &imu->states_out[b]);
+  return DL_OK;
 }
 
 int dl_frontend_submit(dl_context* ctx, const dl_frontend_options* options, int32_t num_scans, const void* const* ranges,

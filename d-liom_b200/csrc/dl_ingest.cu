@@ -208,10 +208,10 @@ __global__ void finalize_results_kernel(ResultArgs a) {
   // the reference drops the scan when any of the three clouds is empty (LTB:497-500, :510-513, :531-534)
   r.ok = (a.return_counts[b] > 0 && n_hi > 0 && n_lo > 0) ? 1 : 0;
   if (a.error_flag && *a.error_flag) r.ok = -1;  // a point fell outside +-2^20 voxels: results are not valid
-  const NlsOutput& o = a.nls[b];
-  r.summary = o.summary;
-  for (int i = 0; i < 7; ++i) r.pose_observation_in_submap[i] = o.pose[i];
-  const Rigidd est = compose(a.submap, pose_from7(o.pose));  // LTB:553-554
+  const double* pose = a.fused ? a.fused[b].state : a.nls[b].pose;
+  r.summary = a.fused ? a.fused[b].summary : a.nls[b].summary;
+  for (int i = 0; i < 7; ++i) r.pose_observation_in_submap[i] = pose[i];
+  const Rigidd est = compose(a.submap, pose_from7(pose));  // LTB:553-554
   pose_to7(est, r.pose_estimate_local);
 }
 

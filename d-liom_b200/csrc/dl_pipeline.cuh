@@ -79,6 +79,7 @@ struct ResultArgs {
   const int32_t* adaptive_passes;
   const float* rtcsm_scores;       // optional
   const NlsOutput* nls;
+  const FusedOutput* fused;        // optional: the fused (IMU) solve's output replaces `nls`
   Rigidd submap;
   const int32_t* error_flag;       // set by the fused front half when a voxel key could not be packed
   dl_scan_result* results;

@@ -25,7 +25,7 @@ EXPORTS = [
     "dl_grid_sync", "dl_grid_resolution", "dl_grid_num_bricks", "dl_grid_lookup", "dl_grid_interpolate",
     "dl_grid_insert_range_data", "dl_submap_insert_range_data", "dl_grid_export_cells",
     "dl_voxel_filter", "dl_voxel_indices", "dl_adaptive_voxel_filter", "dl_rtcsm_match", "dl_fcsm_match_3dof", "dl_constraint_search_batch", "dl_ceres_match",
-    "dl_ceres_match_batch", "dl_ceres_normal_equations", "dl_imu_preintegrate", "dl_imu_predict", "dl_fused_match_batch", "dl_ingest_scan", "dl_frontend_match_batch", "dl_frontend_submit", "dl_frontend_collect",
+    "dl_ceres_match_batch", "dl_ceres_normal_equations", "dl_imu_preintegrate", "dl_imu_predict", "dl_fused_match_batch", "dl_ingest_scan", "dl_frontend_match_batch", "dl_frontend_match_batch_imu", "dl_frontend_submit", "dl_frontend_collect",
     "dl_frontend_match_batch_dev", "dl_frontend_fetch_results", "dl_device_alloc", "dl_device_free",
     "dl_copy_to_device", "dl_copy_to_host",
 ]
@@ -121,6 +121,11 @@ class SolveSummary(C.Structure):
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+class FrontendImu(C.Structure):
+    _fields_ = [("imu_weight", C.c_double), ("gravity", C.c_double * 3), ("states_i", C.c_void_p),
+                ("predicted_states", C.c_void_p), ("preintegrations", C.c_void_p), ("states_out", C.c_void_p)]
 
 
 class ConstraintOptions(C.Structure):
@@ -244,6 +249,8 @@ def lib():
                                  f32p, f32p, i64p]
     L.dl_frontend_match_batch.argtypes = [vp, ip(FrontendOptions), C.c_int32, ip(vp), i64p, f32p, C.c_int32, f64p,
                                           f64p, f64p, vp, vp, ip(ScanResult)]
+    L.dl_frontend_match_batch_imu.argtypes = [vp, ip(FrontendOptions), ip(FrontendImu), C.c_int32, ip(vp), i64p, f32p, C.c_int32,
+                                              f64p, vp, vp, ip(ScanResult)]
     L.dl_frontend_submit.argtypes = [vp, ip(FrontendOptions), C.c_int32, ip(vp), i64p, f32p, C.c_int32, f64p, f64p, f64p, vp, vp]
     L.dl_frontend_collect.argtypes = [vp, C.c_int32, ip(ScanResult)]
     L.dl_frontend_match_batch_dev.argtypes = [vp, ip(FrontendOptions), C.c_int32, vp, C.c_int64, i64p, f32p, C.c_int32,
@@ -499,6 +506,24 @@ class Context:
                                                   np.ascontiguousarray(submap_local_pose, np.float64), hi.h, lo.h,
                                                   results))
         return results
+
+    def frontend_match_batch_imu(self, options, ranges_list, origins, states_i, predicted_states, preints, submap_local_pose,
+                                 hi, lo, imu_weight=1.0, gravity=(0.0, 0.0, 9.8)):
+        """Front end with the IMU residual fused into each scan's solve -> (results, estimated states as 16-vectors)."""
+        hb = ranges_list if isinstance(ranges_list, HostScanBatch) else HostScanBatch(ranges_list)
+        n = hb.n
+        origins = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        si = (NavState * n)(*[NavState.from16(x) for x in states_i])
+        sj = (NavState * n)(*[NavState.from16(x) for x in predicted_states])
+        pm = (Preintegration * n)(*preints)
+        out = (NavState * n)()
+        imu = FrontendImu(imu_weight, (C.c_double * 3)(*gravity), C.cast(si, C.c_void_p), C.cast(sj, C.c_void_p),
+                          C.cast(pm, C.c_void_p), C.cast(out, C.c_void_p))
+        results = (ScanResult * n)()
+        self.check(self.L.dl_frontend_match_batch_imu(self.h, C.byref(options), C.byref(imu), n, hb.pointers, hb.sizes, origins,
+                                                      len(origins), np.ascontiguousarray(submap_local_pose, np.float64), hi.h,
+                                                      lo.h, results))
+        return results, np.array([o.to16() for o in out])
 
     def frontend_submit(self, options, host_batch, origins, prev_poses, cur_poses, submap_local_pose, hi, lo):
         """Streaming form: returns as soon as the batch is enqueued; frontend_collect() returns its results."""

@@ -326,6 +326,25 @@ int dl_frontend_match_batch(dl_context* ctx, const dl_frontend_options* options,
                             const double* submap_local_pose, const dl_grid* high_resolution_grid,
                             const dl_grid* low_resolution_grid, dl_scan_result* results);
 
+/* dl_frontend_match_batch with the IMU pre-integration residual fused into every scan's solve (dl_fused_match_batch's
+ * 15-parameter problem behind the same ingest / filter front half): scan k starts from state states_i[k] at the previous
+ * scan, predicted_states[k] = dl_imu_predict(states_i[k], preintegrations[k]) provides the pose prediction (its pose is what
+ * the plain call takes as predicted_poses; prev_poses[k] is states_i[k]'s pose) and the initial velocity and biases.
+ * states_out[k] receives the estimated state of scan k (local frame); results[k] as in the plain call, with the pose part
+ * of the state. An EXTENSION like dl_fused_match_batch: the reference chains the plain match and a GTSAM update. */
+typedef struct dl_frontend_imu {
+  double imu_weight;
+  double gravity[3];
+  const dl_nav_state* states_i;
+  const dl_nav_state* predicted_states;
+  const dl_preintegration* preintegrations;
+  dl_nav_state* states_out;
+} dl_frontend_imu;
+int dl_frontend_match_batch_imu(dl_context* ctx, const dl_frontend_options* options, const dl_frontend_imu* imu,
+                                int32_t num_scans, const void* const* ranges, const int64_t* sizes, const float* origins,
+                                int32_t num_origins, const double* submap_local_pose, const dl_grid* high_resolution_grid,
+                                const dl_grid* low_resolution_grid, dl_scan_result* results);
+
 /* Streaming form of dl_frontend_match_batch: submit enqueues the uploads, every kernel and the download of the results into
  * pinned staging and returns WITHOUT waiting; collect blocks until that batch is finished and copies the results out.
  * One batch may be in flight per context; a caller that wants the upload of batch i+1 to overlap the tail of batch i

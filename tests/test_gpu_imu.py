@@ -112,3 +112,39 @@ def test_fused_match_in_a_rotated_submap_frame(ctx, orc):
     dtn, drn = pose_error(moved[0][:7], want[:7])
     assert dtn < 1e-6 and drn < 1e-7
     assert np.allclose(moved[0][7:10], want[7:10], atol=1e-6)
+
+
+def test_frontend_batch_with_fused_imu_solve(ctx, orc):
+    """dl_frontend_match_batch_imu = the batched front half (ingest, filters) + the 15-parameter fused solve. Checked against
+    the oracle's own chain: ingest -> adaptive filters -> fused_scan_match seeded with the IMU prediction, per scan."""
+    import dliom
+    w = workload()
+    hi, lo = dliom.Grid.from_oracle(ctx, w["hi"]), dliom.Grid.from_oracle(ctx, w["lo"])
+    fo = dliom.FrontendOptions.from_oracle(w["opts"])
+    o = w["opts"]
+    scans, states_i, preds, preints, wants = [], [], [], [], []
+    for s in range(len(w["scans"])):
+        t1 = w["times"][s]
+        dt, acc, gyr = imu_synth.samples(t1 - 0.1, t1, noise=(3.99e-2, 1.56e-2), seed=30 + s)
+        m = orc.imu_preintegrate(NOISE, [0, 0, 0], [0, 0, 0], dt, acc, gyr)
+        si = imu_synth.state(t1 - 0.1)
+        pred = orc.imu_predict(si, m)
+        ing = orc.ingest_scan(o, w["scans"][s], w["origin"], si[:7], pred[:7])
+        pts = ing["returns_tracking"]
+        hk, _ = orc.adaptive_voxel_filter(pts, o.hi_max_length, o.hi_min_num_points, o.hi_max_range)
+        lk, _ = orc.adaptive_voxel_filter(pts, o.lo_max_length, o.lo_min_num_points, o.lo_max_range)
+        init = pred.copy()
+        init[:7] = np.concatenate([ing["current_pose"][:3].astype(np.float64), ing["current_pose"][3:].astype(np.float64)])
+        want, ws = orc.fused_match([pts[hk], pts[lk]], [w["hi"], w["lo"]], [o.occ_w0, o.occ_w1], o.trans_w, o.rot_w, init[:3], si,
+                                   init, m, imu_weight=0.7, max_iter=o.max_iter)
+        scans.append(w["scans"][s]); states_i.append(si); preds.append(pred); wants.append((want, ws))
+        preints.append(ctx.imu_preintegrate(NOISE, [(dt, acc, gyr)], np.zeros((1, 6)))[0])
+    res, states = ctx.frontend_match_batch_imu(fo, scans, w["origin"], states_i, preds, preints, w["submap_pose"], hi, lo,
+                                               imu_weight=0.7)
+    for r, x, (want, ws) in zip(res, states, wants):
+        assert r.ok == 1
+        dtn, drn = pose_error(x[:7], want[:7])
+        assert dtn < 1e-6 and drn < 1e-7, (dtn, drn)
+        assert np.allclose(x[7:], want[7:], atol=1e-6)
+        assert np.allclose(np.array(r.pose_estimate_local[:]), x[:7], atol=1e-12)
+        assert r.summary.num_iterations == ws["num_iterations"]
