@@ -1281,12 +1281,11 @@ struct FrontendBuffers {
   // fused front half
   int64_t tcap2 = 0;
   unsigned long long* keys2;
-  uint32_t *min2, *slot2;
+  uint32_t* min2;
   int32_t *last_index, *error_flag;
   float* back_pose;
   uint8_t* win;
   float* local4;
-  void* pose_table;
   ScanConstants* scans;
   AdaptiveParams* filters;
   double *initial_pose, *target;
@@ -1304,7 +1303,7 @@ size_t frontend_bytes(int batch, int64_t cap, int num_origins, size_t extra) {
                       B * C * 12, B * C * 12, B * C * 12, B * C * 12, B * C * 12, B * 2 * C * 12, B * 28, (size_t)num_origins * 12,
                       B * 2 * 32 * 4, B * 4, B * C, B * sizeof(ScanConstants), 2 * sizeof(AdaptiveParams), B * 56, B * 24,
                       B * sizeof(NlsProblem), B * sizeof(NlsOutput),
-                      B * (size_t)next_pow2(cap) * 8, B * (size_t)next_pow2(cap) * 4, B * C * 4, B * 4, 64, B * 28, B * C, fe_pose_table_bytes(batch), B * C * 16}) + extra + 8192;
+                      B * (size_t)next_pow2(cap) * 8, B * (size_t)next_pow2(cap) * 4, B * 4, 64, B * 28, B * C, B * C * 16}) + extra + 8192;
 }
 
 void carve(Arena& a, int batch, int64_t cap, int num_origins, FrontendBuffers* f) {
@@ -1331,11 +1330,10 @@ void carve(Arena& a, int batch, int64_t cap, int num_origins, FrontendBuffers* f
   f->problems = a.take<NlsProblem>(B); f->nls_out = a.take<NlsOutput>(B);
   f->tcap2 = next_pow2(cap);
   f->keys2 = a.take<unsigned long long>(B * f->tcap2); f->min2 = a.take<uint32_t>(B * f->tcap2);
-  f->slot2 = a.take<uint32_t>(B * C); f->last_index = a.take<int32_t>(B); f->error_flag = a.take<int32_t>(1);
+  f->last_index = a.take<int32_t>(B); f->error_flag = a.take<int32_t>(1);
   f->back_pose = a.take<float>(B * 7);
   f->win = a.take<uint8_t>(B * C);
   f->local4 = a.take<float>(B * C * 4);
-  f->pose_table = a.take<char>(fe_pose_table_bytes(batch));
 }
 
 FrontendArgs make_frontend_args(const dl_frontend_options& o, const FrontendBuffers& f, const float* d_ranges,
@@ -1346,11 +1344,11 @@ FrontendArgs make_frontend_args(const dl_frontend_options& o, const FrontendBuff
   fa.first_resolution = 0.5f * o.voxel_filter_size;  // LTB:394
   fa.second_resolution = o.voxel_filter_size;        // LTB:479-484
   fa.min_range = o.min_range; fa.max_range = o.max_range; fa.scan_period = o.scan_period;
-  fa.table1 = f.table; fa.slot1 = f.slot; fa.keys2 = f.keys2; fa.min2 = f.min2; fa.slot2 = f.slot2;
+  fa.table1 = f.table; fa.keys2 = f.keys2; fa.min2 = f.min2;
   fa.local = f.local4; fa.win = f.win; fa.tile_counts = f.tile_counts;
   fa.returns_tracking = f.returns_tracking; fa.misses_tracking = f.misses_tracking;
   fa.n_first = f.n1; fa.n_returns_local = f.n_ret; fa.n_returns = f.n2; fa.n_misses = f.n3; fa.last_index = f.last_index;
-  fa.current_pose = f.current_pose; fa.back_pose = f.back_pose; fa.pose_table = f.pose_table; fa.error_flag = f.error_flag;
+  fa.current_pose = f.current_pose; fa.back_pose = f.back_pose; fa.error_flag = f.error_flag;
   return fa;
 }
 
@@ -1784,6 +1782,72 @@ int dl_frontend_collect(dl_context* ctx, int32_t num_scans, dl_scan_result* resu
   if (e != cudaSuccess) return ctx->cuda_fail(e, "dl_frontend_collect");
   std::memcpy(results, (const char*)ctx->h_pinned + ctx->results_staging_offset, (size_t)num_scans * sizeof(dl_scan_result));
   return DL_OK;
+}
+
+namespace {
+int decode_common(dl_context* ctx, const dl_point_cloud2_layout* l, const void* data_host, const void* data_dev, int64_t n,
+                  const double* sensor_to_tracking, float* rows_host, float* rows_dev, int64_t* num_rows_out,
+                  double* stamp_offset_seconds) {
+  if (!ctx || !l || !sensor_to_tracking || !num_rows_out || !stamp_offset_seconds || n < 0 || n >= (1ll << 31)) return DL_ERR_ARG;
+  const int time_bytes = l->time_type == DL_TIME_FLOAT64_SECONDS ? 8 : (l->time_type == DL_TIME_NONE ? 0 : 4);
+  if (l->time_type < DL_TIME_NONE || l->time_type > DL_TIME_FLOAT64_SECONDS) return ctx->fail(DL_ERR_ARG, "unknown time_type");
+  if (l->point_step < 12 || l->offset_x < 0 || l->offset_y < 0 || l->offset_z < 0 || l->offset_x + 4 > l->point_step ||
+      l->offset_y + 4 > l->point_step || l->offset_z + 4 > l->point_step ||
+      (time_bytes && (l->offset_time < 0 || l->offset_time + time_bytes > l->point_step)))
+    return ctx->fail(DL_ERR_ARG, "field offsets do not fit point_step");
+  *num_rows_out = 0;
+  *stamp_offset_seconds = 0.;
+  if (n == 0) return DL_OK;
+  if ((!data_host && !data_dev) || (!rows_host && !rows_dev)) return DL_ERR_ARG;
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)n * l->point_step;
+  const size_t tiles = (size_t)((n + 255) / 256);
+  DL_TRY(ctx->reserve_device(arena_bytes({data_host ? bytes : 0, rows_host ? (size_t)n * 16 : 0, tiles * 4, 64, 64})));
+  Arena a(ctx->d_scratch);
+  DecodeArgs d{};
+  if (data_host) {
+    uint8_t* up = a.take<uint8_t>(bytes);
+    DL_TRY(h2d(ctx, up, (const uint8_t*)data_host, bytes));
+    d.data = up;
+  } else {
+    d.data = (const uint8_t*)data_dev;
+  }
+  d.rows_out = rows_host ? a.take<float>((size_t)n * 4) : rows_dev;
+  if (((uintptr_t)d.rows_out & 15) != 0) return ctx->fail(DL_ERR_ARG, "rows_out must be 16-byte aligned");
+  d.tile_counts = a.take<int32_t>(tiles);
+  d.num_out = a.take<int32_t>(1);
+  d.stamp_offset = a.take<double>(1);
+  d.n = n;
+  d.point_step = l->point_step; d.offset_x = l->offset_x; d.offset_y = l->offset_y; d.offset_z = l->offset_z;
+  d.offset_time = l->offset_time; d.time_type = l->time_type;
+  const bool base4 = ((uintptr_t)d.data & 3) == 0 && l->point_step % 4 == 0;
+  d.xyz_aligned = base4 && l->offset_x % 4 == 0 && l->offset_y % 4 == 0 && l->offset_z % 4 == 0;
+  d.time_aligned = time_bytes == 8 ? (((uintptr_t)d.data & 7) == 0 && l->point_step % 8 == 0 && l->offset_time % 8 == 0)
+                                   : (base4 && l->offset_time % 4 == 0);
+  d.sensor_to_tracking = to_float(pose_from7(sensor_to_tracking));  // sensor_to_tracking->cast<float>()
+  DL_TRY(launch_decode_point_cloud2(ctx, d));
+  int32_t kept = 0;
+  DL_TRY(d2h(ctx, &kept, d.num_out, 1));
+  DL_TRY(d2h(ctx, stamp_offset_seconds, d.stamp_offset, 1));
+  DL_TRY(sync(ctx));
+  *num_rows_out = kept;
+  if (rows_host && kept > 0) {
+    DL_TRY(d2h(ctx, rows_host, d.rows_out, (size_t)kept * 4));
+    DL_TRY(sync(ctx));
+  }
+  return DL_OK;
+}
+}  // namespace
+
+int dl_decode_point_cloud2(dl_context* ctx, const dl_point_cloud2_layout* layout, const void* data, int64_t num_points,
+                           const double* sensor_to_tracking, float* rows_out, int64_t* num_rows_out, double* stamp_offset_seconds) {
+  return decode_common(ctx, layout, data, nullptr, num_points, sensor_to_tracking, rows_out, nullptr, num_rows_out, stamp_offset_seconds);
+}
+int dl_decode_point_cloud2_dev(dl_context* ctx, const dl_point_cloud2_layout* layout, const void* data_dev, int64_t num_points,
+                               const double* sensor_to_tracking, float* rows_out_dev, int64_t* num_rows_out,
+                               double* stamp_offset_seconds) {
+  return decode_common(ctx, layout, nullptr, data_dev, num_points, sensor_to_tracking, nullptr, rows_out_dev, num_rows_out,
+                       stamp_offset_seconds);
 }
 
 int dl_ingest_scan(dl_context* ctx, const dl_frontend_options* options, const void* ranges, int64_t n,

@@ -1,4 +1,4 @@
-// Fused scan front half for the batched front end: 4 kernels instead of the 11 of the stage-wise path
+// Fused scan front half for the batched front end: 7 launches per sub-batch instead of the 11 of the stage-wise path
 // (dl_voxel.cu + dl_ingest.cu, which stay as the standalone filter API and as a cross-check in the tests).
 //
 //   A  fe_first_filter_insert   first voxel filter (LTB:393-395): every point proposes its index for its voxel
@@ -134,7 +134,6 @@ __device__ __forceinline__ int ingest_survivor(const FrontendArgs& a, int b, con
       cls = 0;
     } else {
       uint32_t hh = (hash_cell(c) ^ (cls == 2 ? 0x9e3779b9u : 0u)) & mask2;
-      (void)0;
       for (;;) {
         const unsigned long long prev = atomicCAS(keys + hh, kEmpty64, key);
         if (prev == kEmpty64 || prev == key) {
@@ -365,8 +364,6 @@ __global__ void fe_reset_counters(FrontendArgs a, int batch) {
 }
 
 }  // namespace
-
-size_t fe_pose_table_bytes(int) { return 256; }  // (a per-time pose cache was tried and measured slower: see DESIGN.md)
 
 int launch_fe_prepare(dl_context* ctx, const FrontendArgs& a, int batch) {
   DL_CUDA(ctx, cudaMemsetAsync(a.table1, 0xFF, (size_t)batch * a.tcap1 * sizeof(uint32_t), ctx->stream));

@@ -233,6 +233,18 @@ int launch_nls_normal_equations(dl_context* ctx, const NlsOptions& opt, const Nl
                                 const double* at_pose_dev, double* out28_dev);
 int launch_imu_preintegrate(dl_context* ctx, int count, const int32_t* offsets, const double* dts, const double* accs,
                             const double* gyrs, const double* biases, const dl_imu_noise& noise, dl_preintegration* out);
+struct DecodeArgs {  // one sensor_msgs/PointCloud2 message (dl_decode.cu)
+  const uint8_t* data;
+  int64_t n;
+  int point_step, offset_x, offset_y, offset_z, offset_time, time_type;
+  bool xyz_aligned, time_aligned;  // fields readable with aligned loads
+  Rigidf sensor_to_tracking;
+  int32_t* tile_counts;  // ceil(n / 256)
+  float* rows_out;
+  int32_t* num_out;
+  double* stamp_offset;
+};
+int launch_decode_point_cloud2(dl_context* ctx, const DecodeArgs& a);
 struct FcsmPair {  // one (node, submap) loop-closure search, device pointers
   GridView hi, lo;
   const float* hi_pts;

@@ -49,10 +49,8 @@ struct FrontendArgs {
   float first_resolution, second_resolution, min_range, max_range;
   double scan_period;
   uint32_t* table1;              // first filter: slot -> min point index
-  uint32_t* slot1;
   unsigned long long* keys2;     // second filter: slot -> packed voxel key (bit 63 = miss)
   uint32_t* min2;
-  uint32_t* slot2;
   float* local;                  // float4 per input row: local-frame point of a first-filter survivor + class in .w
   uint8_t* win;                  // 1 = owns its second-filter voxel
   int32_t* tile_counts;
@@ -61,10 +59,8 @@ struct FrontendArgs {
   int32_t *n_first, *n_returns_local, *n_returns, *n_misses, *last_index;
   float* current_pose;
   float* back_pose;              // inverse of current_pose, 7 floats per scan
-  void* pose_table;              // per scan: hash table time -> pose (dl_frontend.cu)
   int32_t* error_flag;
 };
-size_t fe_pose_table_bytes(int batch);
 int launch_fe_prepare(dl_context* ctx, const FrontendArgs& a, int batch);
 int launch_fe_first_filter(dl_context* ctx, FrontendArgs a, int first_scan, int num_scans);
 int launch_fe_rest(dl_context* ctx, FrontendArgs a, int first_scan, int batch);

@@ -25,7 +25,7 @@ EXPORTS = [
     "dl_grid_sync", "dl_grid_resolution", "dl_grid_num_bricks", "dl_grid_lookup", "dl_grid_interpolate",
     "dl_grid_insert_range_data", "dl_submap_insert_range_data", "dl_grid_export_cells",
     "dl_voxel_filter", "dl_voxel_indices", "dl_adaptive_voxel_filter", "dl_rtcsm_match", "dl_fcsm_match_3dof", "dl_constraint_search_batch", "dl_ceres_match",
-    "dl_ceres_match_batch", "dl_ceres_normal_equations", "dl_imu_preintegrate", "dl_imu_predict", "dl_fused_match_batch", "dl_ingest_scan", "dl_frontend_match_batch", "dl_frontend_match_batch_imu", "dl_frontend_submit", "dl_frontend_collect",
+    "dl_ceres_match_batch", "dl_ceres_normal_equations", "dl_imu_preintegrate", "dl_imu_predict", "dl_fused_match_batch", "dl_ingest_scan", "dl_decode_point_cloud2", "dl_decode_point_cloud2_dev", "dl_frontend_match_batch", "dl_frontend_match_batch_imu", "dl_frontend_submit", "dl_frontend_collect",
     "dl_frontend_match_batch_dev", "dl_frontend_fetch_results", "dl_device_alloc", "dl_device_free",
     "dl_copy_to_device", "dl_copy_to_host",
 ]
@@ -121,6 +121,14 @@ class SolveSummary(C.Structure):
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+class PointCloud2Layout(C.Structure):
+    _fields_ = [("point_step", C.c_int32), ("offset_x", C.c_int32), ("offset_y", C.c_int32), ("offset_z", C.c_int32),
+                ("offset_time", C.c_int32), ("time_type", C.c_int32)]
+
+
+TIME_NONE, TIME_FLOAT32_SECONDS, TIME_UINT32_NANOSECONDS, TIME_FLOAT64_SECONDS = 0, 1, 2, 3
 
 
 class FrontendImu(C.Structure):
@@ -249,6 +257,8 @@ def lib():
                                  f32p, f32p, i64p]
     L.dl_frontend_match_batch.argtypes = [vp, ip(FrontendOptions), C.c_int32, ip(vp), i64p, f32p, C.c_int32, f64p,
                                           f64p, f64p, vp, vp, ip(ScanResult)]
+    L.dl_decode_point_cloud2.argtypes = [vp, ip(PointCloud2Layout), vp, C.c_int64, f64p, f32p, ip(C.c_int64), ip(C.c_double)]
+    L.dl_decode_point_cloud2_dev.argtypes = [vp, ip(PointCloud2Layout), vp, C.c_int64, f64p, vp, ip(C.c_int64), ip(C.c_double)]
     L.dl_frontend_match_batch_imu.argtypes = [vp, ip(FrontendOptions), ip(FrontendImu), C.c_int32, ip(vp), i64p, f32p, C.c_int32,
                                               f64p, vp, vp, ip(ScanResult)]
     L.dl_frontend_submit.argtypes = [vp, ip(FrontendOptions), C.c_int32, ip(vp), i64p, f32p, C.c_int32, f64p, f64p, f64p, vp, vp]
@@ -506,6 +516,25 @@ class Context:
                                                   np.ascontiguousarray(submap_local_pose, np.float64), hi.h, lo.h,
                                                   results))
         return results
+
+    def decode_point_cloud2(self, data, point_step, offsets, time_type, sensor_to_tracking):
+        """Raw sensor_msgs/PointCloud2 bytes -> (TimedPointCloud rows [k, 4] in the tracking frame, stamp offset seconds)."""
+        data = np.ascontiguousarray(data, np.uint8).reshape(-1)
+        n = len(data) // point_step
+        lay = PointCloud2Layout(point_step, *[int(v) for v in offsets], int(time_type))
+        rows = np.zeros((max(n, 1), 4), np.float32)
+        k, off = C.c_int64(0), C.c_double(0)
+        self.check(self.L.dl_decode_point_cloud2(self.h, C.byref(lay), data.ctypes.data_as(C.c_void_p), n,
+                                                 np.ascontiguousarray(sensor_to_tracking, np.float64), rows, C.byref(k), C.byref(off)))
+        return rows[:k.value].copy(), off.value
+
+    def decode_point_cloud2_dev(self, data_dev_ptr, num_points, point_step, offsets, time_type, sensor_to_tracking, rows_dev_ptr):
+        lay = PointCloud2Layout(point_step, *[int(v) for v in offsets], int(time_type))
+        k, off = C.c_int64(0), C.c_double(0)
+        self.check(self.L.dl_decode_point_cloud2_dev(self.h, C.byref(lay), data_dev_ptr, num_points,
+                                                     np.ascontiguousarray(sensor_to_tracking, np.float64), rows_dev_ptr,
+                                                     C.byref(k), C.byref(off)))
+        return k.value, off.value
 
     def frontend_match_batch_imu(self, options, ranges_list, origins, states_i, predicted_states, preints, submap_local_pose,
                                  hi, lo, imu_weight=1.0, gravity=(0.0, 0.0, 9.8)):

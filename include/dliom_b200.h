@@ -311,6 +311,33 @@ typedef struct dl_scan_result {
   int32_t reserved;
 } dl_scan_result;
 
+/* ---- wire format -> TimedPointCloud rows (SensorBridge::HandlePointCloud2Message + HandleRangefinder,
+ *      cartographer_ros/sensor_bridge.cc:176-240, :286-300): decodes the points of a sensor_msgs/PointCloud2 message
+ *      (`num_points` records of `point_step` bytes; x / y / z float32 at their field offsets), drops NaN / Inf points,
+ *      makes the per-point time relative to the LAST point of the message and moves the points into the tracking frame.
+ *      time_type follows the reference's sensor types: FLOAT32_SECONDS = "velodyne" (field `time`), UINT32_NANOSECONDS =
+ *      "ouster" (field `t`), FLOAT64_SECONDS = "robosense" (field `timestamp`), NONE = anything else (t = 0).
+ *      Output rows are {x, y, z, t} floats = the 16-byte layout dl_frontend_* take with range_row_floats = 4.
+ *      *stamp_offset_seconds is what the reference adds to the message stamp (velodyne / ouster: time of the last point). */
+#define DL_TIME_NONE 0
+#define DL_TIME_FLOAT32_SECONDS 1
+#define DL_TIME_UINT32_NANOSECONDS 2
+#define DL_TIME_FLOAT64_SECONDS 3
+typedef struct dl_point_cloud2_layout {
+  int32_t point_step;
+  int32_t offset_x, offset_y, offset_z, offset_time;
+  int32_t time_type;
+} dl_point_cloud2_layout;
+/* Host message in, host rows out (capacity num_points rows). */
+int dl_decode_point_cloud2(dl_context* ctx, const dl_point_cloud2_layout* layout, const void* data, int64_t num_points,
+                           const double* sensor_to_tracking, float* rows_out, int64_t* num_rows_out,
+                           double* stamp_offset_seconds);
+/* Device message in (e.g. uploaded as it arrived), device rows out: rows_out_dev has capacity num_points rows and can be
+ * a slice of the buffer dl_frontend_match_batch_dev reads. The row count and stamp offset come back to the host. */
+int dl_decode_point_cloud2_dev(dl_context* ctx, const dl_point_cloud2_layout* layout, const void* data_dev,
+                               int64_t num_points, const double* sensor_to_tracking, float* rows_out_dev,
+                               int64_t* num_rows_out, double* stamp_offset_seconds);
+
 /* Scan ingest only (LTB:393-487). ranges: n RangeMeasurement rows (32 bytes: x y z t + uint64 origin index);
  * origins: 3 floats per sensor. Outputs have capacity n rows. counts_out[4] = {first filter survivors,
  * returns (local frame, before 2nd filter), returns in tracking frame, misses in tracking frame}. */

@@ -133,6 +133,8 @@ def lib():
                                      f64p, f64p, C.c_void_p, C.c_void_p, C.c_int, f64p, i32p]
     L.orc_fcsm_match_3dof.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                       f64p, f32p, C.c_int64, f32p, C.c_int64, C.c_float, C.POINTER(FcsmResult)]
+    L.orc_decode_point_cloud2.restype = C.c_int64
+    L.orc_decode_point_cloud2.argtypes = [C.c_int] * 6 + [C.c_void_p, C.c_int64, f64p, f32p, C.POINTER(C.c_double)]
     L.orc_fcsm_create.restype = C.c_void_p
     L.orc_fcsm_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
     L.orc_fcsm_destroy.argtypes = [C.c_void_p]
@@ -452,3 +454,18 @@ class FastCorrelativeScanMatcher:
         lib().orc_fcsm_match(self.h, np.ascontiguousarray(pose_guess, np.float64), hi_points, len(hi_points), lo_points,
                              len(lo_points), np.float32(min_score), C.byref(r))
         return r
+
+
+TIME_NONE, TIME_FLOAT32_SECONDS, TIME_UINT32_NANOSECONDS, TIME_FLOAT64_SECONDS = 0, 1, 2, 3
+
+
+def decode_point_cloud2(data, point_step, offsets, time_type, sensor_to_tracking):
+    """SensorBridge::HandlePointCloud2Message + HandleRangefinder on raw message bytes -> (rows [k, 4], stamp offset s).
+    offsets = (x, y, z, time) byte offsets inside a point."""
+    data = np.ascontiguousarray(data, np.uint8).reshape(-1)
+    n = len(data) // point_step
+    rows = np.zeros((max(n, 1), 4), np.float32)
+    off = C.c_double(0)
+    k = lib().orc_decode_point_cloud2(point_step, *[int(v) for v in offsets], int(time_type), data.ctypes.data_as(C.c_void_p), n,
+                                      np.ascontiguousarray(sensor_to_tracking, np.float64), rows, C.byref(off))
+    return rows[:k].copy(), off.value

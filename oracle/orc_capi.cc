@@ -5,6 +5,7 @@
 #include <cstring>
 #include <thread>
 
+#include "orc_decode.h"
 #include "orc_fcsm.h"
 #include "orc_filters.h"
 #include "orc_frontend.h"
@@ -127,6 +128,13 @@ float orc_rtcsm_match(void* grid, const float* pts, int64_t n, const double* ini
   if (step_out) { step_out[0] = r.window.angular_step; step_out[1] = r.window.max_scan_range; }
   if (all_scores) std::memcpy(all_scores, scores.data(), scores.size() * sizeof(float));
   return r.score;
+}
+
+// ---- wire format -> TimedPointCloud
+int64_t orc_decode_point_cloud2(int point_step, int off_x, int off_y, int off_z, int off_t, int time_type, const uint8_t* data,
+                                int64_t n, const double* sensor_to_tracking, float* rows_out, double* stamp_offset) {
+  return decode_point_cloud2(PointCloud2Layout{point_step, off_x, off_y, off_z, off_t, time_type}, data, n,
+                             pose_in(sensor_to_tracking), rows_out, stamp_offset);
 }
 
 // ---- loop-closure coarse matcher (branch and bound)
