@@ -233,6 +233,9 @@ def main():
     dev_lanes = [(ctx, results_dev), (ctx2, results_dev2)]
     if os.environ.get("DLIOM_BENCH_ONE_CONTEXT"):
         dev_lanes = [dev_lanes[0]]
+    for _ in range(int(os.environ.get("DLIOM_BENCH_CONTEXTS", "2")) - 2):   # experiments: deeper rotation of contexts
+        dev_lanes.append((dliom.Context(local_rank), torch.zeros_like(results_dev)))
+    extra_ctx = [c for c, _ in dev_lanes[2:]]
 
     def step_dev(i=0):
         """One pass of the hot path over the HBM-resident batch. Successive steps alternate between two contexts (own
@@ -263,6 +266,8 @@ def main():
         torch.cuda.synchronize()
         ctx.synchronize()
         ctx2.synchronize()
+        for c in extra_ctx:
+            c.synchronize()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
@@ -281,25 +286,27 @@ def main():
     ctx.read_profile()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = ctx.launches + ctx2.launches
+    launches0 = ctx.launches + ctx2.launches + sum(c.launches for c in extra_ctx)
     barrier()
     # CUDA events on the launching streams: the first context's stream opens the region; the closing event is recorded on
     # the same stream after it has been made to wait for the other context's stream (an event wait, no host sync).
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stream2 = torch.cuda.ExternalStream(ctx2.stream, device=f"cuda:{local_rank}")
+    others = [torch.cuda.ExternalStream(c.stream, device=f"cuda:{local_rank}") for c in [ctx2] + extra_ctx]
     gate = torch.cuda.Event()
     gate.record(stream)
-    stream2.wait_event(gate)          # neither context starts before e0
+    for s2 in others:
+        s2.wait_event(gate)           # no context starts before e0
     e0.record(stream)
     for k in range(args.steps):
         step_dev(k)
-    tail2 = torch.cuda.Event()
-    tail2.record(stream2)
-    stream.wait_event(tail2)
+    for s2 in others:
+        tail = torch.cuda.Event()
+        tail.record(s2)
+        stream.wait_event(tail)
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
-    launches = ctx.launches + ctx2.launches - launches0
+    launches = ctx.launches + ctx2.launches + sum(c.launches for c in extra_ctx) - launches0
     profile = ctx.read_profile()
     ctx.set_profiling(False)
     # ---- timed: end to end (host buffers in, results out)
