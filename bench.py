@@ -324,6 +324,14 @@ def main():
                        a.num_returns == c.num_returns for a, c in zip(res_stream, res_e2e))
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    # ---- latency of ONE scan through the blocking call (what a 10 Hz single-trajectory node sees)
+    one = dliom.HostScanBatch([host[0, :int(sizes[0])].numpy()])
+    lat = []
+    for _ in range(25):
+        t1 = time.perf_counter()
+        ctx.frontend_match_batch(fo, one, w["origin"], w["prev"][:1], w["cur"][:1], w["submap_pose"], hi, lo)
+        lat.append((time.perf_counter() - t1) * 1e3)
+    single_scan_ms = float(np.median(lat[5:]))
     # ---- the PCIe ceiling of the e2e number: the same pinned bytes copied with nothing else running
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dev.copy_(host, non_blocking=True)
@@ -413,6 +421,9 @@ def main():
                         "streaming_equals_sync_results": stream_equal,
                         "pcie_h2d_gbs": round(h2d_gbs, 2), "copy_only_ms_per_step": round(h2d / h2d_gbs / 1e6, 3),
                         "pcie_note": "plain pinned cudaMemcpyAsync of the same buffers, measured in this run: the floor of e2e"},
+                "latency": {"single_scan_ms": round(single_scan_ms, 3),
+                            "note": "median wall time of dl_frontend_match_batch on ONE 64-beam scan (2.1 MB upload, 13 launches, result "
+                                    "download); the CPU path takes 1000 / cpu_baseline.single_thread_value ms"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity_vs_cpu": parity,
                 "clocks": sampler.summary()}
         print(json.dumps(line))
