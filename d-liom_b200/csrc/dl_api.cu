@@ -4,7 +4,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <climits>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "dl_internal.cuh"
@@ -264,6 +266,7 @@ void dl_grid_destroy(dl_grid* g) {
   if (!g) return;
   cudaSetDevice(g->ctx->device);
   cudaStreamSynchronize(g->ctx->stream);
+  cudaFree(g->d_m8);
   cudaFree(g->d_top);
   cudaFree(g->d_nodes);
   cudaFree(g->d_bricks);
@@ -294,6 +297,7 @@ static int grid_grow(dl_grid* g) {
 
 int dl_grid_set_cells(dl_grid* g, int64_t n, const int32_t* xs, const int32_t* ys, const int32_t* zs,
                       const uint16_t* values) {
+  if (g) g->version++;
   if (!g || n < 0 || (n > 0 && (!xs || !ys || !zs || !values))) return DL_ERR_ARG;
   if (g->mirror_stale) {
     const int st = grid_download(g);
@@ -349,6 +353,7 @@ static int grid_download(dl_grid* g) {
 }
 
 int dl_grid_sync(dl_grid* g) {
+  if (g) g->version++;
   if (!g) return DL_ERR_ARG;
   dl_context* ctx = g->ctx;
   DL_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -915,6 +920,60 @@ int check_fcsm_options(dl_context* ctx, const dl_fcsm_options& o) {
   if (o.linear_xy_search_window < 0 || o.linear_z_search_window < 0) return ctx->fail(DL_ERR_ARG, "negative search window");
   return DL_OK;
 }
+// Loop-closure search index of a grid (dense sliding 8^3 maximum over the bounding box of its bricks), cached in the grid
+// and rebuilt when the grid changed. Returns false (no error) when the grid is empty or the volume would be unreasonably
+// large: the caller then searches exhaustively.
+int ensure_search_index(dl_context* ctx, dl_grid* g, bool* have) {
+  std::lock_guard<std::mutex> lock(g->index_mutex);  // grids are shared read-only between contexts: build once
+  *have = false;
+  if (g->m8_version == g->version && g->d_m8) {
+    *have = true;
+    return DL_OK;
+  }
+  if (g->mirror_stale) DL_TRY(grid_download(g));
+  const int side = 1 << g->bits;
+  int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+  for (int tz = 0; tz < side; ++tz)
+    for (int ty = 0; ty < side; ++ty)
+      for (int tx = 0; tx < side; ++tx) {
+        const int node = g->top[top_flat(tx, ty, tz, g->bits)];
+        if (node < 0) continue;
+        for (int k = 0; k < 512; ++k) {
+          if (g->nodes[(size_t)node * 512 + k] < 0) continue;
+          const int b[3] = {(tx << 3) | (k & 7), (ty << 3) | ((k >> 3) & 7), (tz << 3) | (k >> 6)};  // brick coordinates
+          for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], b[a]); hi[a] = std::max(hi[a], b[a]); }
+        }
+      }
+  if (hi[0] < lo[0]) return DL_OK;  // empty grid
+  const int half = (64 << g->bits) >> 1;
+  int org[3], dim[3];
+  for (int a = 0; a < 3; ++a) {
+    org[a] = lo[a] * 8 - half - 8;                 // one brick of margin below: M8 is non-zero from 7 cells before the data
+    dim[a] = (hi[a] - lo[a] + 1) * 8 + 8;           // (org + half) % 8 == 0 and dim % 8 == 0 by construction
+  }
+  const size_t bytes = (size_t)dim[0] * dim[1] * dim[2];
+  if (bytes > ((size_t)3 << 30)) return DL_OK;    // > 3 GiB per submap: stay exhaustive
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (g->d_m8_bytes < bytes) {
+    DL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (g->d_m8) DL_CUDA(ctx, cudaFree(g->d_m8));
+    g->d_m8 = nullptr;
+    g->d_m8_bytes = 0;
+    DL_CUDA(ctx, cudaMalloc(&g->d_m8, bytes));
+    g->d_m8_bytes = bytes;
+  }
+  uint8_t* tmp = nullptr;
+  DL_CUDA(ctx, cudaMalloc(&tmp, bytes));
+  const int st = launch_fcsm_index(ctx, g->view(), org[0], org[1], org[2], dim[0], dim[1], dim[2], tmp, g->d_m8);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(tmp);
+  DL_TRY(st);
+  for (int a = 0; a < 3; ++a) { g->m8_org[a] = org[a]; g->m8_dim[a] = dim[a]; }
+  g->m8_version = g->version;
+  *have = true;
+  return DL_OK;
+}
+
 // Uploads pairs [first, first + n) and runs the coarse search for them; leaves the picks on the device.
 int coarse_search(dl_context* ctx, Arena& a, const dl_fcsm_options& o, float min_score, int first, int n, const double* guesses,
                   const float* hi_pts, const int64_t* hi_off, const float* lo_pts, const int64_t* lo_off,
@@ -933,11 +992,19 @@ int coarse_search(dl_context* ctx, Arena& a, const dl_fcsm_options& o, float min
   DL_TRY(h2d(ctx, d_hi, hi_pts + 3 * hi0, 3 * n_hi));
   DL_TRY(h2d(ctx, d_lo, lo_pts + 3 * lo0, 3 * n_lo));
   std::vector<FcsmPair> pairs(n);
-  int max_points = 1;
+  int max_points = 1, max_blocks = 1;
   long long max_candidates = 1;
+  // pruned search needs the index of every high-resolution grid of the chunk (DLIOM_FCSM_EXHAUSTIVE=1 forces the fallback)
+  bool pruned = std::getenv("DLIOM_FCSM_EXHAUSTIVE") == nullptr && d_all_scores == nullptr;
+  for (int k = 0; k < n && pruned; ++k) {
+    bool have = false;
+    DL_TRY(ensure_search_index(ctx, const_cast<dl_grid*>(hi_grids[first + k]), &have));
+    pruned = have;
+  }
   for (int k = 0; k < n; ++k) {
     const int g = first + k;
     FcsmPair& p = pairs[k];
+    std::memset(&p, 0, sizeof(p));
     p.hi = hi_grids[g]->view();
     p.lo = lo_grids[g]->view();
     p.hi_pts = d_hi + 3 * (hi_off[g] - hi0);
@@ -954,12 +1021,26 @@ int coarse_search(dl_context* ctx, Arena& a, const dl_fcsm_options& o, float min
     p.min_low = o.min_low_resolution_score;
     const long long side = 2ll * p.wxy + 1, K = side * side * (2ll * p.wz + 1);
     if (K >= 0xFFFFFFFFll) return ctx->fail(DL_ERR_ARG, "more than 2^32-1 translation candidates");
+    if (pruned) {
+      p.m8 = hi_grids[g]->d_m8;
+      for (int a3 = 0; a3 < 3; ++a3) { p.m8_org[a3] = hi_grids[g]->m8_org[a3]; p.m8_dim[a3] = hi_grids[g]->m8_dim[a3]; }
+      const long long bxy = (side + 7) / 8, bz = (2ll * p.wz + 1 + 7) / 8;
+      if (bxy * bxy * bz > 60000) pruned = false;  // one CTA per block and pair in grid.x
+      max_blocks = (int)std::max<long long>(max_blocks, bxy * bxy * bz);
+    }
     max_candidates = std::max(max_candidates, side * (2ll * p.wz + 1) * ((side + kFcsmRun - 1) / kFcsmRun));  // search threads
     max_points = std::max(max_points, std::max(p.n_hi, p.n_lo));
   }
+  if (!pruned)
+    for (FcsmPair& p : pairs) p.m8 = nullptr;
   DL_TRY(h2d(ctx, out->d_pairs, pairs.data(), n));
   DL_TRY(sync(ctx));  // `pairs` is pageable host memory
   StageScope st(ctx, "loop_closure_search");
+  if (pruned) {
+    int* d_bounds = a.take<int>((size_t)n * max_blocks);
+    int* d_max_bound = a.take<int>(n);
+    return launch_fcsm_pruned(ctx, out->d_pairs, n, max_points, max_blocks, d_bounds, d_max_bound, out->d_best, out->d_picks);
+  }
   return launch_fcsm(ctx, out->d_pairs, n, max_points, max_candidates, out->d_best, out->d_picks, d_all_scores);
 }
 int check_pairs(dl_context* ctx, int count, const double* guesses, const float* hi_pts, const int64_t* hi_off, const float* lo_pts,
@@ -976,7 +1057,7 @@ int check_pairs(dl_context* ctx, int count, const double* guesses, const float* 
 }
 size_t coarse_bytes(int64_t n_hi, int64_t n_lo, int n) {
   return arena_bytes({(size_t)n_hi * 12, (size_t)n_lo * 12, (size_t)n_hi * 12, (size_t)n_lo * 12, (size_t)n * sizeof(FcsmPair),
-                      (size_t)n * sizeof(FcsmPick), (size_t)n * 8});
+                      (size_t)n * sizeof(FcsmPick), (size_t)n * 8, (size_t)n * 60000 * 4, (size_t)n * 4});
 }
 }  // namespace
 

@@ -13,6 +13,14 @@
 //   result     argmax_o s(o) subject to s(o) > min_score and the low-resolution gate (low_resolution_matcher.cc:24-36),
 //              lowest linear index (z, y, x order) among equal scores; the reference's own tie order is that of an
 //              unstable std::sort.
+//
+// Pruned form (default when the submap has a search index): the reference's depth-3 bound, kept exact. For a block of
+// 8 x 8 x 8 translations starting at o0 the sum over points of M8[c_i + o0], M8[x] = max of V8 over [x, x + 8)^3 (the
+// sliding maximum PrecomputeGrid builds, stored here as one dense byte volume per finished submap), dominates every leaf
+// sum of the block. Blocks are opened in two rounds — first those within 1/8 of the largest bound, then every remaining
+// block whose bound still reaches the best leaf found (>=, so equal-score leaves with a lower index are not lost) — and
+// everything else is provably below the answer. On street scenes ~3-5 % of the blocks are opened
+// (tools/fcsm_pruning_study.py); results are identical to the exhaustive kernel, which stays as the fallback.
 #include "dl_internal.cuh"
 
 namespace dl {
@@ -177,6 +185,200 @@ __global__ void __launch_bounds__(kBlock) fcsm_search_kernel(const FcsmPair* __r
   if ((threadIdx.x & 31) == 0 && packed) atomicMax(best + blockIdx.y, packed);
 }
 
+// ------------------------------------------------------------------------------------------- search index (per submap)
+// pass X: A[x, y, z] = max of V8 over x .. x+7 (grid read through brick rows: 16 cells -> 8 outputs per thread)
+__global__ void __launch_bounds__(256) m8_pass_x_kernel(GridView g, const uint8_t* __restrict__ lut, int ox, int oy, int oz, int nx,
+                                                        int ny, int nz, uint8_t* __restrict__ out) {
+  // ox is chosen so that (ox + half) % 8 == 0: every thread's 8 outputs start on a brick-row boundary
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int runs = nx / 8;
+  if (t >= (long long)runs * ny * nz) return;
+  const int rx = (int)(t % runs), y = (int)((t / runs) % ny), z = (int)(t / ((long long)runs * ny));
+  const int half = (64 << g.bits) >> 1;
+  const int sx = ox + 8 * rx + half, sy = oy + y + half, sz = oz + z + half;
+  const uint4* p0 = brick_row(g, sx, sy, sz);
+  const uint4* p1 = brick_row(g, sx + 8, sy, sz);
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  const uint4 r0 = p0 ? __ldg(p0) : zero, r1 = p1 ? __ldg(p1) : zero;
+  const unsigned w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+  int v[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const unsigned c = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xFFFFu);
+    v[e] = c ? (int)__ldg(lut + (c & (kLutSize - 1))) : 0;
+  }
+#pragma unroll
+  for (int e = 0; e < 15; ++e) v[e] = max(v[e], v[e + 1]);   // window 2
+#pragma unroll
+  for (int e = 0; e < 13; ++e) v[e] = max(v[e], v[e + 2]);   // window 4
+#pragma unroll
+  for (int e = 0; e < 9; ++e) v[e] = max(v[e], v[e + 4]);    // window 8
+  unsigned lo = 0, hi = 0;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    lo |= (unsigned)v[e] << (8 * e);
+    hi |= (unsigned)v[4 + e] << (8 * e);
+  }
+  uint2* dst = reinterpret_cast<uint2*>(out + ((size_t)z * ny + y) * nx + 8 * rx);
+  *dst = make_uint2(lo, hi);
+}
+
+// pass along a strided axis: out[i] = max(in[i], in[i + stride], ..., in[i + 7 stride]) with zeros past the end
+__global__ void __launch_bounds__(256) m8_pass_axis_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, long long total,
+                                                           long long stride, int extent_index_div, int extent) {
+  // element i has coordinate (i / extent_index_div) % extent along the axis being filtered
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)((i / extent_index_div) % extent);
+  int m = 0;
+#pragma unroll
+  for (int d = 0; d < 8; ++d)
+    if (c + d < extent) m = max(m, (int)in[i + d * stride]);
+  out[i] = (uint8_t)m;
+}
+
+// ------------------------------------------------------------------------------------------- pruned search
+constexpr int kSub = 8;  // block edge
+
+__device__ __forceinline__ float sum_to_score(int sum, int n) {
+  const float kMin = 0.1f, kMax = 1.f - 0.1f;
+  return kMin + ((float)sum / (float)n) * ((kMax - kMin) / 255.f);  // PrecomputationGrid3D::ToProbability(sum / float(n))
+}
+
+__device__ __forceinline__ void block_dims(const FcsmPair& pr, int* bx, int* by, int* bz) {
+  *bx = (2 * pr.wxy + 1 + kSub - 1) / kSub;
+  *by = *bx;
+  *bz = (2 * pr.wz + 1 + kSub - 1) / kSub;
+}
+
+// bound of every 8^3 block of the window: sum over points of the sliding maximum at the block's first offset
+__global__ void __launch_bounds__(128) fcsm_bounds_kernel(const FcsmPair* __restrict__ pairs, int* __restrict__ bounds, int stride,
+                                                          int* __restrict__ max_bound) {
+  const FcsmPair& pr = pairs[blockIdx.y];
+  int bx, by, bz;
+  block_dims(pr, &bx, &by, &bz);
+  const int blocks = bx * by * bz;
+  const int b = blockIdx.x * 128 + threadIdx.x;
+  int sum = 0;
+  if (b < blocks) {
+    const int ox = -pr.wxy + kSub * (b % bx), oy = -pr.wxy + kSub * ((b / bx) % by), oz = -pr.wz + kSub * (b / (bx * by));
+    for (int i = 0; i < pr.n_hi; ++i) {
+      const int x = pr.cells[3 * i] + ox - pr.m8_org[0], y = pr.cells[3 * i + 1] + oy - pr.m8_org[1], z = pr.cells[3 * i + 2] + oz - pr.m8_org[2];
+      if ((unsigned)x < (unsigned)pr.m8_dim[0] && (unsigned)y < (unsigned)pr.m8_dim[1] && (unsigned)z < (unsigned)pr.m8_dim[2])
+        sum += __ldg(pr.m8 + ((size_t)z * pr.m8_dim[1] + y) * pr.m8_dim[0] + x);
+    }
+    bounds[(size_t)blockIdx.y * stride + b] = sum;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum = max(sum, __shfl_xor_sync(0xffffffffu, sum, d));
+  if ((threadIdx.x & 31) == 0 && sum > 0) atomicMax(max_bound + blockIdx.y, sum);
+}
+
+// One CTA (64 threads) per (block, pair): thread = one (y, z) offset of the block with its 8 x offsets. round 0 opens the
+// blocks within 1/8 of the pair's largest bound; round 1 every other block whose bound still reaches the best leaf so far.
+__global__ void __launch_bounds__(64) fcsm_block_kernel(const FcsmPair* __restrict__ pairs, const int* __restrict__ bounds, int stride,
+                                                        const int* __restrict__ max_bound, unsigned long long* __restrict__ best,
+                                                        const uint8_t* __restrict__ lut, int round) {
+  __shared__ int tile[kTile * 3];
+  const FcsmPair& pr = pairs[blockIdx.y];
+  int bx, by, bz;
+  block_dims(pr, &bx, &by, &bz);
+  const int b = blockIdx.x;
+  if (b >= bx * by * bz) return;
+  __shared__ int skip;
+  if (threadIdx.x == 0) {  // one decision for the whole CTA: `best` moves while the round runs
+    const int bound = bounds[(size_t)blockIdx.y * stride + b];
+    const int top = max_bound[blockIdx.y];
+    const bool first_round = bound >= top - (top >> 3);
+    const float bound_score = sum_to_score(bound, pr.n_hi);
+    bool s = !(bound_score > pr.min_score);  // no leaf of the block can exceed min_score
+    if (round == 0) {
+      s = s || !first_round;
+    } else {
+      const unsigned long long cur = *reinterpret_cast<volatile const unsigned long long*>(best + blockIdx.y);
+      // strictly below the best leaf so far: nothing in the block can win or tie
+      s = s || first_round || (cur != 0ull && bound_score < __uint_as_float((unsigned)(cur >> 32)));
+    }
+    skip = s ? 1 : 0;
+  }
+  __syncthreads();
+  if (skip) return;
+  const int side = 2 * pr.wxy + 1;
+  const int ox0 = -pr.wxy + kSub * (b % bx);
+  const int oy = -pr.wxy + kSub * ((b / bx) % by) + (threadIdx.x & 7);
+  const int oz = -pr.wz + kSub * (b / (bx * by)) + (threadIdx.x >> 3);
+  const bool active = oy <= pr.wxy && oz <= pr.wz;
+  const int half = (64 << pr.hi.bits) >> 1;
+  int sum[kRun] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int base = 0; base < pr.n_hi; base += kTile) {
+    const int count = min(kTile, pr.n_hi - base);
+    __syncthreads();
+    for (int j = threadIdx.x; j < count * 3; j += 64) tile[j] = pr.cells[base * 3 + j];
+    __syncthreads();
+    if (active)
+      for (int j = 0; j < count; ++j) {
+        const int sx = tile[3 * j] + ox0 + half, sy = tile[3 * j + 1] + oy + half, sz = tile[3 * j + 2] + oz + half;
+        const int phase = sx & 7;  // block-uniform
+        const uint4* p0 = brick_row(pr.hi, sx - phase, sy, sz);
+        const uint4* p1 = phase ? brick_row(pr.hi, sx - phase + 8, sy, sz) : nullptr;
+        if (!p0 && !p1) continue;
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        const uint4 r0 = p0 ? __ldg(p0) : zero, r1 = p1 ? __ldg(p1) : zero;
+        switch (phase) {
+          case 0: add_run<0>(r0, r1, lut, sum); break;
+          case 1: add_run<1>(r0, r1, lut, sum); break;
+          case 2: add_run<2>(r0, r1, lut, sum); break;
+          case 3: add_run<3>(r0, r1, lut, sum); break;
+          case 4: add_run<4>(r0, r1, lut, sum); break;
+          case 5: add_run<5>(r0, r1, lut, sum); break;
+          case 6: add_run<6>(r0, r1, lut, sum); break;
+          default: add_run<7>(r0, r1, lut, sum); break;
+        }
+      }
+  }
+  float score[kRun];
+  unsigned cand = 0;
+#pragma unroll
+  for (int k = 0; k < kRun; ++k) {
+    score[k] = sum_to_score(sum[k], pr.n_hi);
+    if (active && ox0 + k <= pr.wxy && score[k] > pr.min_score) cand |= 1u << k;
+  }
+  float low[kRun] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float* ftile = reinterpret_cast<float*>(tile);
+  if (!__syncthreads_or(cand != 0)) return;
+  for (int base = 0; base < pr.n_lo; base += kTile) {
+    const int count = min(kTile, pr.n_lo - base);
+    __syncthreads();
+    for (int j = threadIdx.x; j < count * 3; j += 64) ftile[j] = pr.lo_rot[base * 3 + j];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kRun; ++k) {
+      if (!(cand >> k & 1)) continue;
+      const Vec3f t = candidate_pose(pr.pose, pr.hi.resolution, ox0 + k, oy, oz).t;
+      float acc = low[k];
+      for (int j = 0; j < count; ++j) {
+        const Int3 c = cell_index(add(Vec3f{ftile[3 * j], ftile[3 * j + 1], ftile[3 * j + 2]}, t), pr.lo.resolution);
+        acc += value_to_probability(grid_value(pr.lo, c.x, c.y, c.z));
+      }
+      low[k] = acc;
+    }
+  }
+  unsigned long long packed = 0ull;
+#pragma unroll
+  for (int k = 0; k < kRun; ++k) {
+    if (!(cand >> k & 1) || !((double)(low[k] / (float)pr.n_lo) >= pr.min_low)) continue;
+    const unsigned long long idx = ((unsigned long long)(oz + pr.wz) * side + (oy + pr.wxy)) * side + (ox0 + k + pr.wxy);
+    const unsigned long long p = ((unsigned long long)__float_as_uint(score[k]) << 32) | (0xFFFFFFFFull - idx);
+    packed = p > packed ? p : packed;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, packed, d);
+    packed = o > packed ? o : packed;
+  }
+  if ((threadIdx.x & 31) == 0 && packed) atomicMax(best + blockIdx.y, packed);
+}
+
 // Decode the winner of each pair: Result{score, pose_estimate, rotational_score, low_resolution_score} (cc:186-195) and the
 // switch + initial pose the refinement kernel reads.
 __global__ void fcsm_finish_kernel(const FcsmPair* __restrict__ pairs, const unsigned long long* __restrict__ best, int count,
@@ -210,13 +412,52 @@ __global__ void fcsm_finish_kernel(const FcsmPair* __restrict__ pairs, const uns
 
 }  // namespace
 
-int launch_fcsm(dl_context* ctx, const FcsmPair* pairs_dev, int count, int max_points, long long max_threads,
-                unsigned long long* best_dev, FcsmPick* picks_dev, float* all_scores_dev) {
+int ensure_fcsm_lut(dl_context* ctx) {
   if (!ctx->d_fcsm_lut) {
     DL_CUDA(ctx, cudaMalloc(&ctx->d_fcsm_lut, kLutSize));
     fcsm_lut_kernel<<<kLutSize / 256, 256, 0, ctx->stream>>>(ctx->d_fcsm_lut);
     DL_LAUNCH_CHECK(ctx, "fcsm_lut_kernel");
   }
+  return DL_OK;
+}
+
+// Dense sliding-maximum volume of one grid: out has nx * ny * nz bytes, element (0, 0, 0) = cell (ox, oy, oz); tmp same size.
+// nx is a multiple of 8 and (ox + grid_size / 2) % 8 == 0.
+int launch_fcsm_index(dl_context* ctx, const GridView& g, int ox, int oy, int oz, int nx, int ny, int nz, uint8_t* tmp, uint8_t* out) {
+  DL_TRY_STATUS(ensure_fcsm_lut(ctx));
+  const long long total = (long long)nx * ny * nz, runs = total / 8;
+  m8_pass_x_kernel<<<(unsigned)((runs + 255) / 256), 256, 0, ctx->stream>>>(g, ctx->d_fcsm_lut, ox, oy, oz, nx, ny, nz, out);
+  DL_LAUNCH_CHECK(ctx, "m8_pass_x_kernel");
+  m8_pass_axis_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(out, tmp, total, nx, nx, ny);
+  DL_LAUNCH_CHECK(ctx, "m8_pass_axis_kernel(y)");
+  m8_pass_axis_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(tmp, out, total, (long long)nx * ny, nx * ny, nz);
+  DL_LAUNCH_CHECK(ctx, "m8_pass_axis_kernel(z)");
+  return DL_OK;
+}
+
+// Pruned search: bounds of every 8^3 block, then two rounds of block evaluation. bounds_dev: count * stride ints.
+int launch_fcsm_pruned(dl_context* ctx, const FcsmPair* pairs_dev, int count, int max_points, int max_blocks, int* bounds_dev,
+                       int* max_bound_dev, unsigned long long* best_dev, FcsmPick* picks_dev) {
+  DL_TRY_STATUS(ensure_fcsm_lut(ctx));
+  DL_CUDA(ctx, cudaMemsetAsync(best_dev, 0, sizeof(unsigned long long) * count, ctx->stream));
+  DL_CUDA(ctx, cudaMemsetAsync(max_bound_dev, 0, sizeof(int) * count, ctx->stream));
+  fcsm_prepare_kernel<<<dim3((max_points + 255) / 256, count), 256, 0, ctx->stream>>>(pairs_dev);
+  DL_LAUNCH_CHECK(ctx, "fcsm_prepare_kernel");
+  fcsm_bounds_kernel<<<dim3((max_blocks + 127) / 128, count), 128, 0, ctx->stream>>>(pairs_dev, bounds_dev, max_blocks, max_bound_dev);
+  DL_LAUNCH_CHECK(ctx, "fcsm_bounds_kernel");
+  for (int round = 0; round < 2; ++round) {
+    fcsm_block_kernel<<<dim3(max_blocks, count), 64, 0, ctx->stream>>>(pairs_dev, bounds_dev, max_blocks, max_bound_dev, best_dev,
+                                                                       ctx->d_fcsm_lut, round);
+    DL_LAUNCH_CHECK(ctx, "fcsm_block_kernel");
+  }
+  fcsm_finish_kernel<<<(count + 63) / 64, 64, 0, ctx->stream>>>(pairs_dev, best_dev, count, picks_dev);
+  DL_LAUNCH_CHECK(ctx, "fcsm_finish_kernel");
+  return DL_OK;
+}
+
+int launch_fcsm(dl_context* ctx, const FcsmPair* pairs_dev, int count, int max_points, long long max_threads,
+                unsigned long long* best_dev, FcsmPick* picks_dev, float* all_scores_dev) {
+  DL_TRY_STATUS(ensure_fcsm_lut(ctx));
   DL_CUDA(ctx, cudaMemsetAsync(best_dev, 0, sizeof(unsigned long long) * count, ctx->stream));
   fcsm_prepare_kernel<<<dim3((max_points + 255) / 256, count), 256, 0, ctx->stream>>>(pairs_dev);
   DL_LAUNCH_CHECK(ctx, "fcsm_prepare_kernel");

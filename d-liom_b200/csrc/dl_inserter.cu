@@ -264,6 +264,7 @@ int grid_insert_device(dl_context* ctx, dl_grid* g, const Vec3f& origin, const f
   ins_finish_kernel<<<blocks, kBlock, 0, ctx->stream>>>(a);
   DL_LAUNCH_CHECK(ctx, "ins_finish_kernel");
   g->mirror_stale = true;
+  g->version++;
   return DL_OK;
 }
 

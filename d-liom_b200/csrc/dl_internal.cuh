@@ -4,6 +4,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -104,6 +105,13 @@ struct dl_grid {
   size_t d_top_cap = 0, d_nodes_cap = 0, d_bricks_cap = 0;  // element capacities
   int32_t* d_counters = nullptr;  // [0] nodes in use, [1] bricks in use, [2] scratch (update-list length)
   bool mirror_stale = false;      // the device copy was modified by dl_grid_insert_range_data: the host mirror is behind
+  uint64_t version = 1;           // bumped by every modification (cells set, sync, device insert)
+  // loop-closure search index (dl_fcsm.cu), built on first use and rebuilt when `version` moved on
+  uint8_t* d_m8 = nullptr;
+  size_t d_m8_bytes = 0;
+  uint64_t m8_version = 0;        // 0 = none
+  int m8_org[3] = {0, 0, 0}, m8_dim[3] = {0, 0, 0};
+  std::mutex index_mutex;
   dl::GridView view() const { return {d_top, d_nodes, d_bricks, resolution, bits}; }
 };
 
@@ -256,6 +264,9 @@ struct FcsmPair {  // one (node, submap) loop-closure search, device pointers
   int wxy, wz;     // window half-widths in cells
   float min_score;
   double min_low;
+  // search index of the high-resolution grid (dense sliding 8^3 maximum of the 8-bit values); null = exhaustive search
+  const uint8_t* m8;
+  int m8_org[3], m8_dim[3];
 };
 struct FcsmPick {
   int found;
@@ -265,6 +276,9 @@ struct FcsmPick {
   double pose[7];  // coarse pose (the guess itself when nothing was found)
 };
 constexpr int kFcsmRun = 8;  // x offsets per search thread (dl_fcsm.cu)
+int launch_fcsm_index(dl_context* ctx, const GridView& g, int ox, int oy, int oz, int nx, int ny, int nz, uint8_t* tmp, uint8_t* out);
+int launch_fcsm_pruned(dl_context* ctx, const FcsmPair* pairs_dev, int count, int max_points, int max_blocks, int* bounds_dev,
+                       int* max_bound_dev, unsigned long long* best_dev, FcsmPick* picks_dev);
 int launch_fcsm(dl_context* ctx, const FcsmPair* pairs_dev, int count, int max_points, long long max_threads,
                 unsigned long long* best_dev, FcsmPick* picks_dev, float* all_scores_dev);
 void compute_odds_table(float probability, uint16_t* table32768);

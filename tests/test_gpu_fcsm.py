@@ -152,3 +152,47 @@ def test_constraint_search_batch_edge_cases(ctx, orc):
     assert ctx.constraint_search_batch(opt, [], [], [], [], []) == []
     with pytest.raises(dliom.DlError):   # an empty cloud in the batch
         ctx.constraint_search_batch(opt, [orc.IDENTITY_POSE] * 2, [CLOUD, CLOUD[:0]], [CLOUD, CLOUD], [g, g], [g, g])
+
+
+def test_pruned_search_equals_exhaustive(ctx, orc):
+    """The default search opens only the 8^3 blocks whose exact bound (sliding maximum of the 8-bit grid) can still reach the
+    best leaf; DLIOM_FCSM_EXHAUSTIVE=1 scores every leaf. Same answer, bit for bit — also after the grid changed (the search
+    index is rebuilt from the grid's version) and for windows that are not multiples of the block size."""
+    import os
+    import dliom
+    w = workload(beams=16, num_map_scans=40, num_scans=3)
+    hi, lo = dliom.Grid.from_oracle(ctx, w["hi"]), dliom.Grid.from_oracle(ctx, w["lo"])
+    rng = np.random.default_rng(21)
+
+    def both(pts_hi, pts_lo, guess, min_score, **kw):
+        got = ctx.fcsm_match_3dof(hi, lo, pts_hi, pts_lo, guess, min_score, **kw)
+        os.environ["DLIOM_FCSM_EXHAUSTIVE"] = "1"
+        try:
+            want = ctx.fcsm_match_3dof(hi, lo, pts_hi, pts_lo, guess, min_score, **kw)
+        finally:
+            del os.environ["DLIOM_FCSM_EXHAUSTIVE"]
+        assert (got.found, got.score, got.low_resolution_score, list(got.offset), list(got.pose_estimate)) == \
+               (want.found, want.score, want.low_resolution_score, list(want.offset), list(want.pose_estimate))
+        return got
+
+    clouds = []
+    for k in range(3):
+        pts = orc.ingest_scan(w["opts"], w["scans"][k], w["origin"], w["prev"][k], w["truth"][k])["returns_tracking"]
+        hk, _ = orc.adaptive_voxel_filter(pts, 2.0, 150, 15.0)
+        lk, _ = orc.adaptive_voxel_filter(pts, 4.0, 200, 60.0)
+        clouds.append((pts[hk], pts[lk]))
+        for window in ((5.0, 1.0), (3.3, 0.7), (0.4, 0.4)):
+            guess = np.array(w["truth"][k], np.float64)
+            guess[:3] += rng.uniform(-1, 1, 3) * [window[0] * 0.5, window[0] * 0.5, window[1] * 0.5]
+            for ms, ml in ((0.15, 0.3), (0.05, 0.05), (0.6, 0.55)):
+                both(pts[hk], pts[lk], guess, ms, xy_window=window[0], z_window=window[1], min_low_resolution_score=ml)
+    # the grid changes (host cells, then a device-side insert): the index follows
+    before = both(*clouds[0], w["truth"][0], 0.15, min_low_resolution_score=0.3)
+    cell = w["hi"].cell_index(w["truth"][0][:3].astype(np.float32) + np.float32([3.0, 0.5, 0.2]))
+    xs = np.arange(cell[0], cell[0] + 40, dtype=np.int32)
+    hi.set_cells(xs, np.full(40, cell[1], np.int32), np.full(40, cell[2], np.int32), np.full(40, 32767, np.uint16))
+    both(*clouds[0], w["truth"][0], 0.15, min_low_resolution_score=0.3)
+    ctx.submap_insert_range_data(hi, lo, orc.IDENTITY_POSE, w["truth"][1][:3].astype(np.float32),
+                                 clouds[1][0] + np.float32([0.3, 0.0, 0.0]), high_resolution_max_range=20)
+    after = both(*clouds[0], w["truth"][0], 0.15, min_low_resolution_score=0.3)
+    assert before.found and after.found
