@@ -135,6 +135,11 @@ def lib():
                                       f64p, f32p, C.c_int64, f32p, C.c_int64, C.c_float, C.POINTER(FcsmResult)]
     L.orc_decode_point_cloud2.restype = C.c_int64
     L.orc_decode_point_cloud2.argtypes = [C.c_int] * 6 + [C.c_void_p, C.c_int64, f64p, f32p, C.POINTER(C.c_double)]
+    L.orc_fcsm_match_full.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                      C.c_double, f64p, f64p, f32p, C.c_int64, f32p, C.c_int64, C.c_void_p, C.c_int, C.c_float,
+                                      C.POINTER(FcsmResult), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.orc_rotational_match.argtypes = [f32p, C.c_int, C.c_float, f32p, C.c_float, f32p, C.c_int, f32p]
+    L.orc_compute_histogram.argtypes = [f32p, C.c_int64, C.c_int, f32p]
     L.orc_fcsm_create.restype = C.c_void_p
     L.orc_fcsm_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
     L.orc_fcsm_destroy.argtypes = [C.c_void_p]
@@ -469,3 +474,36 @@ def decode_point_cloud2(data, point_step, offsets, time_type, sensor_to_tracking
     k = lib().orc_decode_point_cloud2(point_step, *[int(v) for v in offsets], int(time_type), data.ctypes.data_as(C.c_void_p), n,
                                       np.ascontiguousarray(sensor_to_tracking, np.float64), rows, C.byref(off))
     return rows[:k].copy(), off.value
+
+
+def fcsm_match_full(hi_grid, lo_grid, hi_points, lo_points, node_pose, submap_pose, min_score, xy_window=5.0, z_window=1.0,
+                    angular_window=0.2617993877991494, min_low_resolution_score=0.55, min_rotational_score=0.77, depth=8,
+                    full_depth=3, histogram=None, histogram_size=10):
+    """FastCorrelativeScanMatcher3D::Match: yaw steps inside the angular window x the translation window."""
+    hi_points = np.ascontiguousarray(hi_points, np.float32).reshape(-1, 3)
+    lo_points = np.ascontiguousarray(lo_points, np.float32).reshape(-1, 3)
+    r = FcsmResult()
+    si, ns = C.c_int(0), C.c_int(0)
+    hist = None if histogram is None else np.ascontiguousarray(histogram, np.float32)
+    lib().orc_fcsm_match_full(hi_grid.h, lo_grid.h, depth, full_depth, min_rotational_score, min_low_resolution_score, xy_window,
+                              z_window, angular_window, np.ascontiguousarray(node_pose, np.float64),
+                              np.ascontiguousarray(submap_pose, np.float64), hi_points, len(hi_points), lo_points, len(lo_points),
+                              None if hist is None else hist.ctypes.data_as(C.c_void_p), histogram_size if hist is None else len(hist),
+                              np.float32(min_score), C.byref(r), C.byref(si), C.byref(ns))
+    return r, si.value, ns.value
+
+
+def rotational_match(submap_histogram, histogram, initial_angle, angles, submap_angle=0.0):
+    sh = np.ascontiguousarray(submap_histogram, np.float32)
+    h = np.ascontiguousarray(histogram, np.float32)
+    a = np.ascontiguousarray(angles, np.float32)
+    out = np.zeros(len(a), np.float32)
+    lib().orc_rotational_match(sh, len(sh), np.float32(submap_angle), h, np.float32(initial_angle), a, len(a), out)
+    return out
+
+
+def compute_histogram(points, size):
+    p = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    out = np.zeros(size, np.float32)
+    lib().orc_compute_histogram(p, len(p), size, out)
+    return out

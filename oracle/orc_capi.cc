@@ -172,6 +172,33 @@ void orc_fcsm_match(void* m, const double* pose_guess, const float* hi_pts, int6
                     float min_score, OrcFcsmResult* out) {
   fcsm_out(((const FastCorrelativeScanMatcher*)m)->MatchWith3DofInitial(pose_in(pose_guess), hi_pts, n_hi, lo_pts, n_lo, min_score), out);
 }
+// Full Match (with the yaw search); histogram may be null (= the zero histogram of the reference's own test fixture).
+void orc_fcsm_match_full(void* hi, void* lo, int depth, int full_depth, double min_rot, double min_low, double wxy, double wz,
+                         double angular_window, const double* node_pose, const double* submap_pose, const float* hi_pts,
+                         int64_t n_hi, const float* lo_pts, int64_t n_lo, const float* histogram, int histogram_size,
+                         float min_score, OrcFcsmResult* out, int* scan_index, int* num_scans) {
+  FcsmOptions o = fcsm_options(depth, full_depth, min_rot, min_low, wxy, wz);
+  o.angular_search_window = angular_window;
+  FastCorrelativeScanMatcher m(*(HybridGrid*)hi, (const HybridGrid*)lo, o, {{Histogram(histogram_size, 0.f), 0.f}});
+  Histogram h(histogram_size, 0.f);
+  if (histogram)
+    for (int i = 0; i < histogram_size; ++i) h[i] = histogram[i];
+  const FcsmResult r = m.Match(pose_in(node_pose), pose_in(submap_pose), hi_pts, n_hi, lo_pts, n_lo, h, Quatd{1., 0., 0., 0.}, min_score);
+  fcsm_out(r, out);
+  *scan_index = r.scan_index;
+  *num_scans = r.num_scans;
+}
+// RotationalScanMatcher: one submap histogram at angle 0, scores of `histogram` at the given angles
+void orc_rotational_match(const float* submap_histogram, int size, float submap_angle, const float* histogram, float initial_angle,
+                          const float* angles, int num_angles, float* scores_out) {
+  RotationalScanMatcher m({{Histogram(submap_histogram, submap_histogram + size), submap_angle}});
+  const std::vector<float> s = m.Match(Histogram(histogram, histogram + size), initial_angle, std::vector<float>(angles, angles + num_angles));
+  for (int i = 0; i < num_angles; ++i) scores_out[i] = s[i];
+}
+void orc_compute_histogram(const float* pts, int64_t n, int size, float* out) {
+  const Histogram h = compute_histogram(pts, n, size);
+  for (int i = 0; i < size; ++i) out[i] = h[i];
+}
 void orc_fcsm_match_3dof(void* hi, void* lo, int depth, int full_depth, double min_rot, double min_low, double wxy, double wz,
                          const double* pose_guess, const float* hi_pts, int64_t n_hi, const float* lo_pts, int64_t n_lo,
                          float min_score, OrcFcsmResult* out) {

@@ -20,6 +20,7 @@
 
 #include "orc_grid.h"
 #include "orc_math.h"
+#include "orc_rotational.h"
 
 namespace orc {
 
@@ -88,15 +89,25 @@ struct FcsmResult {
   float low_resolution_score = 0.f;
   I3 offset{0, 0, 0};
   int64_t leaves_scored = 0;  // work the branch and bound actually did (for the comparison with brute force)
+  int scan_index = 0, num_scans = 1;  // which yaw step won, of how many (full Match only)
 };
+
+// Eigen::Quaternion::inverse(): conjugate divided by the squared norm (not just the conjugate)
+template <typename T>
+inline Quat<T> eigen_inverse(const Quat<T>& q) {
+  const T n2 = qsquared_norm(q);
+  return {q.w / n2, -q.x / n2, -q.y / n2, -q.z / n2};
+}
 
 class FastCorrelativeScanMatcher {
  public:
-  // Builds the precomputation stack once per submap, like the reference's constructor (cc:112-125); Match* is const and
+  // Builds the precomputation stack once per submap, like the reference's constructor (cc:129-141); Match* is const and
   // keeps its per-call state in a local Search record, so one matcher serves concurrent callers (the reference's
-  // thread-pool pattern, constraint_builder_3d.cc:189-197).
-  FastCorrelativeScanMatcher(const HybridGrid& hi, const HybridGrid* lo, const FcsmOptions& o)
-      : o_(o), resolution_(hi.resolution()), stack_(hi, o), lo_(lo) {}
+  // thread-pool pattern, constraint_builder_3d.cc:189-197). `histograms_at_angles` feeds the rotational matcher
+  // (HistogramsAtAnglesFromNodes, cc:114-127); the 3-DoF entry point does not use it.
+  FastCorrelativeScanMatcher(const HybridGrid& hi, const HybridGrid* lo, const FcsmOptions& o,
+                             const std::vector<std::pair<Histogram, float>>& histograms_at_angles = {{Histogram(10, 0.f), 0.f}})
+      : o_(o), resolution_(hi.resolution()), stack_(hi, o), lo_(lo), rotational_(histograms_at_angles) {}
 
   FcsmResult MatchWith3DofInitial(const Rigid3d& pose_in_submap_guess, const float* hi_pts, int64_t n_hi,
                                   const float* lo_pts, int64_t n_lo, float min_score) const {
@@ -105,69 +116,119 @@ class FastCorrelativeScanMatcher {
     s.wz = round_to_int(o_.linear_z_search_window / resolution_);
     s.lo_pts = lo_pts;
     s.n_lo = n_lo;
-    Discretize(&s, hi_pts, n_hi, cast_f(pose_in_submap_guess));
-    std::vector<Candidate> lowest = GenerateLowest(s);
-    Score(&s, stack_.max_depth(), &lowest);
-    const Candidate best = BranchAndBound(&s, lowest, stack_.max_depth(), min_score);
-    FcsmResult r;
-    r.leaves_scored = s.leaves;
-    if (best.score > min_score) {
-      r.found = true;
-      r.score = best.score;
-      r.pose = cast_d(PoseFromCandidate(s, best));
-      r.rotational_score = (float)(o_.min_rotational_score + 0.01);
-      r.low_resolution_score = best.low_resolution_score;
-      r.offset = best.offset;
+    s.scans.push_back(Discretize(s, hi_pts, n_hi, cast_f(pose_in_submap_guess), (float)(o_.min_rotational_score + 0.01)));
+    return Finish(&s, min_score);
+  }
+
+  // Match (cc:145-162) -> MatchWithSearchParameters (:221-250): one discrete scan per yaw step inside the angular window
+  // that passes the rotational score, then the same branch and bound over (scan, x, y, z).
+  FcsmResult Match(const Rigid3d& global_node_pose, const Rigid3d& global_submap_pose, const float* hi_pts, int64_t n_hi,
+                   const float* lo_pts, int64_t n_lo, const Histogram& scan_histogram, const Quatd& gravity_alignment,
+                   float min_score) const {
+    Search s;
+    s.wxy = round_to_int(o_.linear_xy_search_window / resolution_);
+    s.wz = round_to_int(o_.linear_z_search_window / resolution_);
+    s.lo_pts = lo_pts;
+    s.n_lo = n_lo;
+    const Rigid3f node = cast_f(global_node_pose), submap = cast_f(global_submap_pose);
+    // GenerateDiscreteScans (cc:296-350)
+    float max_scan_range = 3.f * resolution_;
+    for (int64_t i = 0; i < n_hi; ++i) max_scan_range = std::max(norm(V3f{hi_pts[3 * i], hi_pts[3 * i + 1], hi_pts[3 * i + 2]}), max_scan_range);
+    const float kSafetyMargin = 1.f - 1e-2f;
+    const float angular_step_size =
+        kSafetyMargin * std::acos(1.f - (resolution_ * resolution_) / (2.f * (max_scan_range * max_scan_range)));
+    const int angular_window_size = round_to_int(o_.angular_search_window / angular_step_size);  // double / float -> double
+    std::vector<float> angles;
+    for (int rz = -angular_window_size; rz <= angular_window_size; ++rz) angles.push_back(rz * angular_step_size);
+    const Rigid3f node_to_submap = compose(inverse(submap), node);
+    const Quatd ga_inv_d = eigen_inverse(gravity_alignment);  // .inverse().cast<float>()
+    const Quatf ga_inv{(float)ga_inv_d.w, (float)ga_inv_d.x, (float)ga_inv_d.y, (float)ga_inv_d.z};
+    const V3f dir = rotate(qmul(node_to_submap.q, ga_inv), V3f{1.f, 0.f, 0.f});  // GetYaw(rotation): atan2 of rotated UnitX
+    const std::vector<float> scores = rotational_.Match(scan_histogram, std::atan2(dir.y, dir.x), angles);
+    for (size_t i = 0; i != angles.size(); ++i) {
+      if (scores[i] < o_.min_rotational_score) continue;
+      const Quatf q = qmul(qmul(eigen_inverse(submap.q), angle_axis_to_quat(V3f{0.f, 0.f, angles[i]})), node.q);
+      s.scans.push_back(Discretize(s, hi_pts, n_hi, Rigid3f{node_to_submap.t, q}, scores[i]));
     }
-    return r;
+    if (s.scans.empty()) return FcsmResult();
+    return Finish(&s, min_score);
   }
 
  private:
   struct Candidate {
+    int scan_index = 0;
     I3 offset{0, 0, 0};
     float score = -std::numeric_limits<float>::infinity();
     float low_resolution_score = 0.f;
     bool operator>(const Candidate& other) const { return score > other.score; }
     bool operator<(const Candidate& other) const { return score < other.score; }
   };
-  struct Search {  // DiscreteScan3D + the window + counters of one call
-    int wxy = 0, wz = 0;
+  struct Scan {  // DiscreteScan3D
     Rigid3f pose;
     std::vector<std::vector<I3>> cells;
+    float rotational_score = 0.f;
+  };
+  struct Search {  // the discrete scans + the window + counters of one call
+    int wxy = 0, wz = 0;
+    std::vector<Scan> scans;
     const float* lo_pts = nullptr;
     int64_t n_lo = 0, leaves = 0;
   };
 
-  void Discretize(Search* s, const float* pts, int64_t n, const Rigid3f& pose) const {
-    s->pose = pose;
+  FcsmResult Finish(Search* s, float min_score) const {
+    std::vector<Candidate> lowest = GenerateLowest(*s);
+    Score(s, stack_.max_depth(), &lowest);
+    const Candidate best = BranchAndBound(s, lowest, stack_.max_depth(), min_score);
+    FcsmResult r;
+    r.leaves_scored = s->leaves;
+    if (best.score > min_score) {
+      r.found = true;
+      r.score = best.score;
+      r.pose = cast_d(PoseFromCandidate(*s, best));
+      r.rotational_score = s->scans[best.scan_index].rotational_score;
+      r.low_resolution_score = best.low_resolution_score;
+      r.offset = best.offset;
+      r.scan_index = best.scan_index;
+      r.num_scans = (int)s->scans.size();
+    }
+    return r;
+  }
+
+  Scan Discretize(const Search& s, const float* pts, int64_t n, const Rigid3f& pose, float rotational_score) const {
+    Scan scan;
+    scan.pose = pose;
+    scan.rotational_score = rotational_score;
     std::vector<I3> full;
     for (int64_t i = 0; i < n; ++i)
       full.push_back(stack_.Get(0).GetCellIndex(apply(pose, V3f{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]})));
     const int full_depth = std::min(o_.full_resolution_depth, o_.branch_and_bound_depth);
-    for (int i = 0; i != full_depth; ++i) s->cells.push_back(full);
+    for (int i = 0; i != full_depth; ++i) scan.cells.push_back(full);
     const int low_depth = o_.branch_and_bound_depth - full_depth;
-    const I3 start{-s->wxy, -s->wxy, -s->wz};
+    const I3 start{-s.wxy, -s.wxy, -s.wz};
     for (int i = 0; i != low_depth; ++i) {
       const int e = i + 1;
       const I3 low_start{start.x >> e, start.y >> e, start.z >> e};
-      s->cells.emplace_back();
+      scan.cells.emplace_back();
       for (const I3& c : full) {
         const I3 at_start{c.x + start.x, c.y + start.y, c.z + start.z};
-        s->cells.back().push_back(I3{(at_start.x >> e) - low_start.x, (at_start.y >> e) - low_start.y, (at_start.z >> e) - low_start.z});
+        scan.cells.back().push_back(I3{(at_start.x >> e) - low_start.x, (at_start.y >> e) - low_start.y, (at_start.z >> e) - low_start.z});
       }
     }
+    return scan;
   }
 
   std::vector<Candidate> GenerateLowest(const Search& s) const {
     const int step = 1 << stack_.max_depth();
     std::vector<Candidate> out;
-    for (int z = -s.wz; z <= s.wz; z += step)
-      for (int y = -s.wxy; y <= s.wxy; y += step)
-        for (int x = -s.wxy; x <= s.wxy; x += step) {
-          Candidate c;
-          c.offset = {x, y, z};
-          out.push_back(c);
-        }
+    for (int scan_index = 0; scan_index != (int)s.scans.size(); ++scan_index)
+      for (int z = -s.wz; z <= s.wz; z += step)
+        for (int y = -s.wxy; y <= s.wxy; y += step)
+          for (int x = -s.wxy; x <= s.wxy; x += step) {
+            Candidate c;
+            c.scan_index = scan_index;
+            c.offset = {x, y, z};
+            out.push_back(c);
+          }
     return out;
   }
 
@@ -177,8 +238,9 @@ class FastCorrelativeScanMatcher {
     for (Candidate& c : *candidates) {
       int sum = 0;
       const I3 off{c.offset.x >> e, c.offset.y >> e, c.offset.z >> e};
-      for (const I3& cell : s->cells[depth]) sum += grid.value(I3{cell.x + off.x, cell.y + off.y, cell.z + off.z});
-      c.score = precomp_to_probability(sum / (float)s->cells[depth].size());
+      const std::vector<I3>& cells = s->scans[c.scan_index].cells[depth];
+      for (const I3& cell : cells) sum += grid.value(I3{cell.x + off.x, cell.y + off.y, cell.z + off.z});
+      c.score = precomp_to_probability(sum / (float)cells.size());
       if (depth == 0) ++s->leaves;
     }
     std::sort(candidates->begin(), candidates->end(), std::greater<Candidate>());
@@ -187,7 +249,7 @@ class FastCorrelativeScanMatcher {
   Rigid3f PoseFromCandidate(const Search& s, const Candidate& c) const {
     const Rigid3f translation{{resolution_ * (float)c.offset.x, resolution_ * (float)c.offset.y, resolution_ * (float)c.offset.z},
                               {1.f, 0.f, 0.f, 0.f}};
-    return compose(translation, s.pose);
+    return compose(translation, s.scans[c.scan_index].pose);
   }
 
   float LowResolutionScore(const Search& s, const Rigid3f& pose) const {
@@ -223,6 +285,7 @@ class FastCorrelativeScanMatcher {
           for (int x : {0, half_width}) {
             if (c.offset.x + x > s->wxy) break;
             Candidate h;
+            h.scan_index = c.scan_index;
             h.offset = {c.offset.x + x, c.offset.y + y, c.offset.z + z};
             higher.push_back(h);
           }
@@ -239,6 +302,7 @@ class FastCorrelativeScanMatcher {
   float resolution_;
   PrecomputationGridStack stack_;
   const HybridGrid* lo_;
+  RotationalScanMatcher rotational_;
 };
 
 }  // namespace orc
