@@ -1091,6 +1091,116 @@ int dl_fcsm_match_3dof(dl_context* ctx, const dl_fcsm_options* o, const double* 
   return DL_OK;
 }
 
+namespace {
+// RotateHistogram / MatchHistograms (rotational_scan_matcher.cc:123-155), float arithmetic in the reference's order
+std::vector<float> rotate_histogram(const float* h, int n, float angle) {
+  const float rotate_by_buckets = (float)(-angle * n / M_PI);
+  int full_buckets = (int)std::lround(rotate_by_buckets - 0.5f);
+  const float fraction = rotate_by_buckets - full_buckets;
+  while (full_buckets < 0) full_buckets += n;
+  std::vector<float> out(n);
+  for (int i = 0; i < n; ++i) out[i] = fraction * h[(i + 1 + full_buckets) % n] + (1.f - fraction) * h[(i + full_buckets) % n];
+  return out;
+}
+float match_histograms(const float* submap, const float* scan, int n) {
+  float ss = 0.f, sm = 0.f, dot = 0.f;
+  for (int i = 0; i < n; ++i) ss += scan[i] * scan[i];
+  for (int i = 0; i < n; ++i) sm += submap[i] * submap[i];
+  const float normalization = std::sqrt(ss) * std::sqrt(sm);
+  if (normalization < 1e-3f) return 1.f;
+  for (int i = 0; i < n; ++i) dot += submap[i] * scan[i];
+  return dot / normalization;
+}
+Quatf eigen_quaternion_inverse_f(const Quatf& q) {  // Eigen::Quaternion::inverse(): conjugate / squared norm
+  const float n2 = (q.x * q.x + q.y * q.y) + (q.z * q.z + q.w * q.w);
+  return {q.w / n2, -q.x / n2, -q.y / n2, -q.z / n2};
+}
+Quatd eigen_quaternion_inverse_d(const Quatd& q) {
+  const double n2 = (q.x * q.x + q.y * q.y) + (q.z * q.z + q.w * q.w);
+  return {q.w / n2, -q.x / n2, -q.y / n2, -q.z / n2};
+}
+}  // namespace
+
+int dl_fcsm_match(dl_context* ctx, const dl_fcsm_options* o, const float* submap_histogram, const float* scan_histogram,
+                  int32_t histogram_size, const double* global_node_pose, const double* global_submap_pose,
+                  const double* gravity_alignment, const float* hi_pts, int64_t n_hi, const float* lo_pts, int64_t n_lo,
+                  const dl_grid* hi, const dl_grid* lo, float min_score, dl_fcsm_result* result) {
+  if (!ctx || !o || !result || !submap_histogram || !scan_histogram || histogram_size < 1 || !global_node_pose ||
+      !global_submap_pose || !gravity_alignment || !hi || !lo || n_hi < 0 || n_lo < 0 || (n_hi > 0 && !hi_pts) || (n_lo > 0 && !lo_pts))
+    return DL_ERR_ARG;
+  if (n_hi == 0 || n_lo == 0) return ctx->fail(DL_ERR_EMPTY, "empty point cloud");
+  DL_TRY(check_fcsm_options(ctx, *o));
+  std::memset(result, 0, sizeof(*result));
+  const float res = hi->resolution;
+  const Rigidf node = to_float(pose_from7(global_node_pose)), submap = to_float(pose_from7(global_submap_pose));
+  // GenerateDiscreteScans (cc:296-350)
+  float max_scan_range = 3.f * res;
+  for (int64_t i = 0; i < n_hi; ++i) max_scan_range = std::max(norm3(Vec3f{hi_pts[3 * i], hi_pts[3 * i + 1], hi_pts[3 * i + 2]}), max_scan_range);
+  const float angular_step_size = (1.f - 1e-2f) * std::acos(1.f - (res * res) / (2.f * (max_scan_range * max_scan_range)));
+  const int angular_window_size = (int)std::lround(o->angular_search_window / angular_step_size);
+  if (angular_window_size < 0 || angular_window_size > 100000) return ctx->fail(DL_ERR_ARG, "angular window out of range");
+  const Rigidf node_to_submap = compose(inverse(submap), node);
+  const Quatd ga_inv_d = eigen_quaternion_inverse_d(Quatd{gravity_alignment[0], gravity_alignment[1], gravity_alignment[2], gravity_alignment[3]});
+  const Quatf ga_inv{(float)ga_inv_d.w, (float)ga_inv_d.x, (float)ga_inv_d.y, (float)ga_inv_d.z};
+  const Vec3f dir = rotate(qmul(node_to_submap.q, ga_inv), Vec3f{1.f, 0.f, 0.f});
+  const float initial_angle = std::atan2(dir.y, dir.x);  // transform::GetYaw
+  std::vector<double> guesses;
+  std::vector<float> scores;
+  for (int rz = -angular_window_size; rz <= angular_window_size; ++rz) {
+    const float angle = rz * angular_step_size;
+    const std::vector<float> rotated = rotate_histogram(scan_histogram, histogram_size, initial_angle + angle);
+    const float score = match_histograms(submap_histogram, rotated.data(), histogram_size);
+    if (score < o->min_rotational_score) continue;
+    const Quatf q = qmul(qmul(eigen_quaternion_inverse_f(submap.q), angle_axis_to_quat(Vec3f{0.f, 0.f, angle})), node.q);
+    const double g[7] = {node_to_submap.t.x, node_to_submap.t.y, node_to_submap.t.z, q.w, q.x, q.y, q.z};  // floats widen exactly
+    guesses.insert(guesses.end(), g, g + 7);
+    scores.push_back(score);
+  }
+  const int n = (int)scores.size();
+  if (n == 0) return DL_OK;  // no yaw step passes the rotational score: the reference returns nullptr
+  std::vector<float> hi_all((size_t)n * n_hi * 3), lo_all((size_t)n * n_lo * 3);
+  std::vector<int64_t> hi_off(n + 1), lo_off(n + 1);
+  std::vector<const dl_grid*> his(n, hi), los(n, lo);
+  for (int k = 0; k < n; ++k) {
+    std::memcpy(hi_all.data() + (size_t)k * n_hi * 3, hi_pts, (size_t)n_hi * 12);
+    std::memcpy(lo_all.data() + (size_t)k * n_lo * 3, lo_pts, (size_t)n_lo * 12);
+    hi_off[k] = k * n_hi; lo_off[k] = k * n_lo;
+  }
+  hi_off[n] = n * n_hi; lo_off[n] = n * n_lo;
+  DL_TRY(check_pairs(ctx, n, guesses.data(), hi_all.data(), hi_off.data(), lo_all.data(), lo_off.data(), his.data(), los.data()));
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  FcsmPick best{};
+  int best_scan = -1;
+  constexpr int kChunk = 1024;
+  for (int first = 0; first < n; first += kChunk) {
+    const int m = std::min(kChunk, n - first);
+    DL_TRY(ctx->reserve_device(coarse_bytes((int64_t)m * n_hi, (int64_t)m * n_lo, m)));
+    Arena a(ctx->d_scratch);
+    CoarseSearch cs;
+    DL_TRY(coarse_search(ctx, a, *o, min_score, first, m, guesses.data(), hi_all.data(), hi_off.data(), lo_all.data(), lo_off.data(),
+                         his.data(), los.data(), nullptr, &cs));
+    std::vector<FcsmPick> picks(m);
+    DL_TRY(d2h(ctx, picks.data(), cs.d_picks, m));
+    DL_TRY(sync(ctx));
+    for (int k = 0; k < m; ++k) {
+      result->num_candidates += picks[k].num_candidates;
+      if (picks[k].found && (best_scan < 0 || picks[k].score > best.score)) {  // first of equal scores: lowest yaw step
+        best = picks[k];
+        best_scan = first + k;
+      }
+    }
+  }
+  if (best_scan < 0) return DL_OK;
+  result->found = 1;
+  result->score = best.score;
+  std::memcpy(result->pose_estimate, best.pose, sizeof(best.pose));
+  result->rotational_score = scores[best_scan];
+  result->low_resolution_score = best.low_resolution_score;
+  std::memcpy(result->offset, best.offset, sizeof(best.offset));
+  result->scan_index = best_scan;
+  return DL_OK;
+}
+
 int dl_constraint_search_batch(dl_context* ctx, const dl_constraint_options* options, int32_t count, const double* guesses,
                                const float* hi_pts, const int64_t* hi_off, const float* lo_pts, const int64_t* lo_off,
                                const dl_grid* const* hi_grids, const dl_grid* const* lo_grids, dl_constraint* constraints) {

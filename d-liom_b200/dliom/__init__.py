@@ -24,7 +24,7 @@ EXPORTS = [
     "dl_context_stream", "dl_context_synchronize", "dl_context_set_profiling", "dl_context_read_profile", "dl_grid_create", "dl_grid_destroy", "dl_grid_set_cells",
     "dl_grid_sync", "dl_grid_resolution", "dl_grid_num_bricks", "dl_grid_lookup", "dl_grid_interpolate",
     "dl_grid_insert_range_data", "dl_submap_insert_range_data", "dl_grid_export_cells",
-    "dl_voxel_filter", "dl_voxel_indices", "dl_adaptive_voxel_filter", "dl_rtcsm_match", "dl_fcsm_match_3dof", "dl_constraint_search_batch", "dl_ceres_match",
+    "dl_voxel_filter", "dl_voxel_indices", "dl_adaptive_voxel_filter", "dl_rtcsm_match", "dl_fcsm_match_3dof", "dl_fcsm_match", "dl_constraint_search_batch", "dl_ceres_match",
     "dl_ceres_match_batch", "dl_ceres_normal_equations", "dl_imu_preintegrate", "dl_imu_predict", "dl_fused_match_batch", "dl_ingest_scan", "dl_decode_point_cloud2", "dl_decode_point_cloud2_dev", "dl_frontend_match_batch", "dl_frontend_match_batch_imu", "dl_frontend_submit", "dl_frontend_collect",
     "dl_frontend_match_batch_dev", "dl_frontend_fetch_results", "dl_device_alloc", "dl_device_free",
     "dl_copy_to_device", "dl_copy_to_host",
@@ -94,7 +94,7 @@ class FcsmOptions(C.Structure):
 class FcsmResult(C.Structure):
     _fields_ = [("found", C.c_int32), ("score", C.c_float), ("pose_estimate", C.c_double * 7),
                 ("rotational_score", C.c_float), ("low_resolution_score", C.c_float), ("offset", C.c_int32 * 3),
-                ("reserved", C.c_int32), ("num_candidates", C.c_int64)]
+                ("scan_index", C.c_int32), ("num_candidates", C.c_int64)]
 
 
 class CeresOptions(C.Structure):
@@ -240,6 +240,8 @@ def lib():
     L.dl_rtcsm_match.argtypes = [vp, ip(RtcsmOptions), f64p, f32p, C.c_int64, vp, f64p, ip(C.c_float), ip(RtcsmInfo), vp]
     L.dl_fcsm_match_3dof.argtypes = [vp, ip(FcsmOptions), f64p, f32p, C.c_int64, f32p, C.c_int64, vp, vp, C.c_float,
                                      ip(FcsmResult)]
+    L.dl_fcsm_match.argtypes = [vp, ip(FcsmOptions), f32p, f32p, C.c_int32, f64p, f64p, f64p, f32p, C.c_int64, f32p, C.c_int64, vp, vp,
+                                C.c_float, ip(FcsmResult)]
     L.dl_constraint_search_batch.argtypes = [vp, ip(ConstraintOptions), C.c_int32, f64p, f32p, i64p, f32p, i64p, C.c_void_p,
                                              C.c_void_p, ip(Constraint)]
     L.dl_ceres_match.argtypes = [vp, ip(CeresOptions), f64p, f64p, C.c_int32, ip(vp), i64p, ip(vp), f64p,
@@ -388,6 +390,23 @@ class Context:
         self.check(self.L.dl_fcsm_match_3dof(self.h, C.byref(opt), np.ascontiguousarray(pose_guess, np.float64), hi_points,
                                              len(hi_points), lo_points, len(lo_points), hi_grid.h, lo_grid.h,
                                              np.float32(min_score), C.byref(r)))
+        return r
+
+    def fcsm_match(self, hi_grid, lo_grid, hi_points, lo_points, node_pose, submap_pose, min_score, submap_histogram=None,
+                   scan_histogram=None, histogram_size=10, gravity_alignment=(1.0, 0.0, 0.0, 0.0), xy_window=5.0, z_window=1.0,
+                   angular_window=0.2617993877991494, min_low_resolution_score=0.55, min_rotational_score=0.77, depth=8,
+                   full_depth=3):
+        """FastCorrelativeScanMatcher3D::Match (yaw search x translation window)."""
+        hi_points = np.ascontiguousarray(hi_points, np.float32).reshape(-1, 3)
+        lo_points = np.ascontiguousarray(lo_points, np.float32).reshape(-1, 3)
+        sh = np.zeros(histogram_size, np.float32) if submap_histogram is None else np.ascontiguousarray(submap_histogram, np.float32)
+        nh = np.zeros(len(sh), np.float32) if scan_histogram is None else np.ascontiguousarray(scan_histogram, np.float32)
+        opt = FcsmOptions(depth, full_depth, min_rotational_score, min_low_resolution_score, xy_window, z_window, angular_window)
+        r = FcsmResult()
+        self.check(self.L.dl_fcsm_match(self.h, C.byref(opt), sh, nh, len(sh), np.ascontiguousarray(node_pose, np.float64),
+                                        np.ascontiguousarray(submap_pose, np.float64), np.ascontiguousarray(gravity_alignment, np.float64),
+                                        hi_points, len(hi_points), lo_points, len(lo_points), hi_grid.h, lo_grid.h,
+                                        np.float32(min_score), C.byref(r)))
         return r
 
     def constraint_search_batch(self, options, pose_guesses, hi_clouds, lo_clouds, hi_grids, lo_grids):

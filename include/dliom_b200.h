@@ -160,13 +160,26 @@ typedef struct dl_fcsm_result { /* FastCorrelativeScanMatcher3D::Result; found =
   float rotational_score;
   float low_resolution_score;
   int32_t offset[3];      /* winning translation in cells */
-  int32_t reserved;
+  int32_t scan_index;     /* dl_fcsm_match: which of the yaw steps that passed the rotational score won (0 otherwise) */
   int64_t num_candidates; /* leaves scored */
 } dl_fcsm_result;
 int dl_fcsm_match_3dof(dl_context* ctx, const dl_fcsm_options* options, const double* pose_in_submap_guess,
                        const float* high_resolution_points, int64_t n_high, const float* low_resolution_points,
                        int64_t n_low, const dl_grid* high_resolution_grid, const dl_grid* low_resolution_grid,
                        float min_score, dl_fcsm_result* result);
+
+/* FastCorrelativeScanMatcher3D::Match (SM/fast_correlative_scan_matcher_3d.cc:145-162, :221-250, :296-350): the yaw search
+ * around the node's orientation x the translation window. The yaw steps, the rotational scores (RotationalScanMatcher::Match on
+ * the two histograms, rotational_scan_matcher.cc:123-155, :181-192) and the per-step poses are formed on the host exactly as the
+ * reference does; every step that passes min_rotational_score becomes one translation search of the same device batch.
+ * submap_histogram: the matcher's accumulated histogram (sum of the nodes' histograms rotated to the submap frame,
+ * rotational_scan_matcher.cc:172-179); scan_histogram: the node's (TrajectoryNode::Data::rotational_scan_matcher_histogram);
+ * gravity_alignment: quaternion w x y z. The fork's constraint builder calls dl_fcsm_match_3dof's form instead. */
+int dl_fcsm_match(dl_context* ctx, const dl_fcsm_options* options, const float* submap_histogram, const float* scan_histogram,
+                  int32_t histogram_size, const double* global_node_pose, const double* global_submap_pose,
+                  const double* gravity_alignment, const float* high_resolution_points, int64_t n_high,
+                  const float* low_resolution_points, int64_t n_low, const dl_grid* high_resolution_grid,
+                  const dl_grid* low_resolution_grid, float min_score, dl_fcsm_result* result);
 
 /* ---- scan_matching::CeresScanMatcher3D::Match (SM/ceres_scan_matcher_3d.h:41-61, .cc:63-123; options
  *      C/mapping/proto/scan_matching/ceres_scan_matcher_options_3d.proto + C/common/proto/ceres_solver_options.proto)

@@ -137,7 +137,7 @@ def lib():
     L.orc_decode_point_cloud2.argtypes = [C.c_int] * 6 + [C.c_void_p, C.c_int64, f64p, f32p, C.POINTER(C.c_double)]
     L.orc_fcsm_match_full.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                       C.c_double, f64p, f64p, f32p, C.c_int64, f32p, C.c_int64, C.c_void_p, C.c_int, C.c_float,
-                                      C.POINTER(FcsmResult), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+                                      C.POINTER(FcsmResult), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
     L.orc_rotational_match.argtypes = [f32p, C.c_int, C.c_float, f32p, C.c_float, f32p, C.c_int, f32p]
     L.orc_compute_histogram.argtypes = [f32p, C.c_int64, C.c_int, f32p]
     L.orc_fcsm_create.restype = C.c_void_p
@@ -478,18 +478,20 @@ def decode_point_cloud2(data, point_step, offsets, time_type, sensor_to_tracking
 
 def fcsm_match_full(hi_grid, lo_grid, hi_points, lo_points, node_pose, submap_pose, min_score, xy_window=5.0, z_window=1.0,
                     angular_window=0.2617993877991494, min_low_resolution_score=0.55, min_rotational_score=0.77, depth=8,
-                    full_depth=3, histogram=None, histogram_size=10):
+                    full_depth=3, histogram=None, histogram_size=10, submap_histogram=None):
     """FastCorrelativeScanMatcher3D::Match: yaw steps inside the angular window x the translation window."""
     hi_points = np.ascontiguousarray(hi_points, np.float32).reshape(-1, 3)
     lo_points = np.ascontiguousarray(lo_points, np.float32).reshape(-1, 3)
     r = FcsmResult()
     si, ns = C.c_int(0), C.c_int(0)
     hist = None if histogram is None else np.ascontiguousarray(histogram, np.float32)
+    sub = None if submap_histogram is None else np.ascontiguousarray(submap_histogram, np.float32)
     lib().orc_fcsm_match_full(hi_grid.h, lo_grid.h, depth, full_depth, min_rotational_score, min_low_resolution_score, xy_window,
                               z_window, angular_window, np.ascontiguousarray(node_pose, np.float64),
                               np.ascontiguousarray(submap_pose, np.float64), hi_points, len(hi_points), lo_points, len(lo_points),
                               None if hist is None else hist.ctypes.data_as(C.c_void_p), histogram_size if hist is None else len(hist),
-                              np.float32(min_score), C.byref(r), C.byref(si), C.byref(ns))
+                              np.float32(min_score), C.byref(r), C.byref(si), C.byref(ns),
+                              None if sub is None else sub.ctypes.data_as(C.c_void_p))
     return r, si.value, ns.value
 
 

@@ -176,10 +176,13 @@ void orc_fcsm_match(void* m, const double* pose_guess, const float* hi_pts, int6
 void orc_fcsm_match_full(void* hi, void* lo, int depth, int full_depth, double min_rot, double min_low, double wxy, double wz,
                          double angular_window, const double* node_pose, const double* submap_pose, const float* hi_pts,
                          int64_t n_hi, const float* lo_pts, int64_t n_lo, const float* histogram, int histogram_size,
-                         float min_score, OrcFcsmResult* out, int* scan_index, int* num_scans) {
+                         float min_score, OrcFcsmResult* out, int* scan_index, int* num_scans, const float* submap_histogram) {
   FcsmOptions o = fcsm_options(depth, full_depth, min_rot, min_low, wxy, wz);
   o.angular_search_window = angular_window;
-  FastCorrelativeScanMatcher m(*(HybridGrid*)hi, (const HybridGrid*)lo, o, {{Histogram(histogram_size, 0.f), 0.f}});
+  Histogram sh(histogram_size, 0.f);
+  if (submap_histogram)
+    for (int i = 0; i < histogram_size; ++i) sh[i] = submap_histogram[i];
+  FastCorrelativeScanMatcher m(*(HybridGrid*)hi, (const HybridGrid*)lo, o, {{sh, 0.f}});
   Histogram h(histogram_size, 0.f);
   if (histogram)
     for (int i = 0; i < histogram_size; ++i) h[i] = histogram[i];

@@ -196,3 +196,52 @@ def test_pruned_search_equals_exhaustive(ctx, orc):
                                  clouds[1][0] + np.float32([0.3, 0.0, 0.0]), high_resolution_max_range=20)
     after = both(*clouds[0], w["truth"][0], 0.15, min_low_resolution_score=0.3)
     assert before.found and after.found
+
+
+def test_full_match_with_yaw_search(ctx, orc):
+    """dl_fcsm_match = FastCorrelativeScanMatcher3D::Match: yaw steps and rotational scores on the host, one translation search
+    per passing step in a single device batch. Against the oracle's full matcher: the reference's fixture (zero histograms,
+    rotated poses) and scene scans with real histograms where min_rotational_score removes most steps."""
+    import dliom
+    from helpers import apply_pose
+    opts = dict(xy_window=0.8, z_window=0.8, angular_window=0.3, min_low_resolution_score=0.15, min_rotational_score=0.1, depth=6,
+                full_depth=6)
+    rng = np.random.default_rng(4)
+    for _ in range(3):
+        t = (0.7 * rng.uniform(-1, 1, 3)).astype(np.float32)
+        theta = np.float32(0.2 * rng.uniform(-1, 1))
+        expected = np.array([*t, np.cos(theta / 2), 0, 0, np.sin(theta / 2)], np.float64)
+        og = orc.Grid(0.05)
+        og.insert_range_data(t, apply_pose(expected, CLOUD.astype(np.float64)).astype(np.float32), hit=0.7, miss=0.4, num_free=5)
+        g = dliom.Grid.from_oracle(ctx, og)
+        want, ws, wn = orc.fcsm_match_full(og, og, CLOUD, CLOUD, orc.IDENTITY_POSE, orc.IDENTITY_POSE, 0.1, **opts)
+        got = ctx.fcsm_match(g, g, CLOUD, CLOUD, orc.IDENTITY_POSE, orc.IDENTITY_POSE, 0.1, **opts)
+        assert want.found and got.found
+        assert np.float32(got.score) == np.float32(want.score) and np.float32(got.rotational_score) == np.float32(want.rotational_score)
+        if got.scan_index == ws:
+            assert list(got.pose_estimate) == list(want.pose) and np.float32(got.low_resolution_score) == np.float32(want.low_resolution_score)
+        assert np.abs(np.array(got.pose_estimate[:3]) - t).max() < 0.05
+    w = workload(beams=16, num_map_scans=40, num_scans=3)
+    hi, lo = dliom.Grid.from_oracle(ctx, w["hi"]), dliom.Grid.from_oracle(ctx, w["lo"])
+    for k in range(2):
+        pts = orc.ingest_scan(w["opts"], w["scans"][k], w["origin"], w["prev"][k], w["truth"][k])["returns_tracking"]
+        hk, _ = orc.adaptive_voxel_filter(pts, 2.0, 150, 15.0)
+        lk, _ = orc.adaptive_voxel_filter(pts, 4.0, 200, 60.0)
+        scan_hist = orc.compute_histogram(pts, 120)
+        submap_hist = orc.compute_histogram(apply_pose(np.concatenate([[0, 0, 0], w["truth"][k][3:]]), pts.astype(np.float64)).astype(np.float32), 120)
+        node = np.array(w["truth"][k], np.float64)
+        node[:3] += [0.4, -0.3, 0.05]
+        half = 0.04 * (1 if k == 0 else -1)     # a yaw error of 0.08 rad for the search to undo
+        dq = np.array([np.cos(half), 0, 0, np.sin(half)])
+        a, b = dq, node[3:].copy()
+        node[3:] = [a[0] * b[0] - a[3] * b[3], a[0] * b[1] - a[3] * b[2], a[0] * b[2] + a[3] * b[1], a[0] * b[3] + a[3] * b[0]]
+        kw = dict(xy_window=1.0, z_window=0.3, angular_window=0.2, min_low_resolution_score=0.3, min_rotational_score=0.77)
+        want, ws, wn = orc.fcsm_match_full(w["hi"], w["lo"], pts[hk], pts[lk], node, orc.IDENTITY_POSE, 0.15, histogram=scan_hist,
+                                           submap_histogram=submap_hist, **kw)
+        got = ctx.fcsm_match(hi, lo, pts[hk], pts[lk], node, orc.IDENTITY_POSE, 0.15, submap_histogram=submap_hist,
+                             scan_histogram=scan_hist, **kw)
+        assert bool(got.found) == bool(want.found)
+        if want.found:
+            assert np.float32(got.score) == np.float32(want.score)
+            if got.scan_index == ws:
+                assert list(got.pose_estimate) == list(want.pose) and np.float32(got.rotational_score) == np.float32(want.rotational_score)
