@@ -23,24 +23,31 @@ def main():
     prob = np.array([orc.lib().orc_value_to_probability(int(v)) for v in np.unique(vs)], f)
     lut = dict(zip(np.unique(vs).tolist(), np.rint((prob - f(0.1)) * (f(255.0) / f(0.8))).astype(np.int64).tolist()))
     v8 = np.array([lut[int(v)] for v in vs], np.uint8)
-    lo3 = np.array([xs.min(), ys.min(), zs.min()]) - 64
-    shape = np.array([xs.max(), ys.max(), zs.max()]) + 64 - lo3 + 1
+    lo3 = np.array([xs.min(), ys.min(), zs.min()]) - 200
+    shape = np.array([xs.max(), ys.max(), zs.max()]) + 200 - lo3 + 1
     vol = np.zeros(shape, np.uint8)
     vol[xs - lo3[0], ys - lo3[1], zs - lo3[2]] = v8
     wxy, wz, res = 50, 10, 0.1
     rng = np.random.default_rng(5)
-    for k in range(3):
-        pts = orc.ingest_scan(w["opts"], w["scans"][k], w["origin"], w["prev"][k], w["truth"][k])["returns_tracking"]
+    min_score = 0.3
+    for k in range(5):
+        unmatched = k >= 3     # last cases: the node is 12 m (across the street) / 6 m (along it) away from where it really was
+        kk = min(k, 2)
+        shift = {3: [0.0, 12.0, 0.0], 4: [6.0, 0.0, 0.0]}.get(k, [0.0, 0.0, 0.0])
+        pts = orc.ingest_scan(w["opts"], w["scans"][kk], w["origin"], w["prev"][kk], w["truth"][kk])["returns_tracking"]
         hk, _ = orc.adaptive_voxel_filter(pts, 2.0, 150, 15.0)
-        guess = np.array(w["truth"][k], np.float64)
-        guess[:3] += rng.uniform(-1, 1, 3) * [2.0, 2.0, 0.4]
+        guess = np.array(w["truth"][kk], np.float64)
+        guess[:3] += rng.uniform(-1, 1, 3) * [2.0, 2.0, 0.4] + np.array(shift)
         cells = np.array([w["hi"].cell_index(p) for p in apply_pose(guess, pts[hk].astype(np.float64)).astype(np.float32)]) - lo3
         n = len(cells)
         sums = np.zeros((2 * wxy + 1, 2 * wxy + 1, 2 * wz + 1), np.int64)
         for c in cells:
             sums += vol[c[0] - wxy:c[0] + wxy + 1, c[1] - wxy:c[1] + wxy + 1, c[2] - wz:c[2] + wz + 1]
         best = sums.max()
-        line = [f"pair {k}: N={n} best leaf sum/N = {best / n:.1f} (score {0.1 + best / n * 0.8 / 255:.3f}); leaves {sums.size}"]
+        floor = (min_score - 0.1) / 0.8 * 255 * n     # a leaf needs sum > floor to exceed min_score
+        thr = max(best, floor) if best > floor else floor
+        line = [f"pair {k}{' (unmatched)' if unmatched else ''}: N={n} best leaf sum/N = {best / n:.1f} (score {0.1 + best / n * 0.8 / 255:.3f}); "
+                f"threshold = {'best leaf' if best > floor else 'min_score %.2f' % min_score}; leaves {sums.size}"]
         for b in (8, 4, 2):
             # bound of the block of offsets [o, o+b)^3 = sum_i max over that window of vol around c_i  (exact sliding max)
             m = maximum_filter(vol, size=b, origin=-(b // 2) if b % 2 == 0 else 0, mode="constant")   # window [x, x+b)
@@ -52,8 +59,8 @@ def main():
             chk = sums[:b * (sums.shape[0] // b), :b * (sums.shape[1] // b), :b * (sums.shape[2] // b)]
             blk = chk.reshape(chk.shape[0] // b, b, chk.shape[1] // b, b, chk.shape[2] // b, b).max(axis=(1, 3, 5))
             assert np.all(bounds[:blk.shape[0], :blk.shape[1], :blk.shape[2]] >= blk)
-            open_blocks = int((bounds >= best).sum())
-            line.append(f"  block {b}^3: {bounds.size} blocks, {open_blocks} with bound >= best ({100.0 * open_blocks / bounds.size:.1f}%)"
+            open_blocks = int((bounds >= thr).sum())
+            line.append(f"  block {b}^3: {bounds.size} blocks, {open_blocks} with bound >= threshold ({100.0 * open_blocks / bounds.size:.1f}%)"
                         f" -> {open_blocks * b ** 3} leaves ({100.0 * open_blocks * b ** 3 / sums.size:.1f}% of brute force)")
         print("\n".join(line))
 
