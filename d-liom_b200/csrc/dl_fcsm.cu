@@ -338,10 +338,13 @@ __global__ void __launch_bounds__(64) fcsm_block_kernel(const FcsmPair* __restri
   }
   float score[kRun];
   unsigned cand = 0;
+  // a leaf below the best passing leaf found so far cannot win (an equal one still can, on the index): skip its gate
+  const unsigned long long seen = *reinterpret_cast<volatile const unsigned long long*>(best + blockIdx.y);
+  const float seen_score = seen ? __uint_as_float((unsigned)(seen >> 32)) : -1.f;
 #pragma unroll
   for (int k = 0; k < kRun; ++k) {
     score[k] = sum_to_score(sum[k], pr.n_hi);
-    if (active && ox0 + k <= pr.wxy && score[k] > pr.min_score) cand |= 1u << k;
+    if (active && ox0 + k <= pr.wxy && score[k] > pr.min_score && score[k] >= seen_score) cand |= 1u << k;
   }
   float low[kRun] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float* ftile = reinterpret_cast<float*>(tile);

@@ -59,6 +59,11 @@ def main():
             chk = sums[:b * (sums.shape[0] // b), :b * (sums.shape[1] // b), :b * (sums.shape[2] // b)]
             blk = chk.reshape(chk.shape[0] // b, b, chk.shape[1] // b, b, chk.shape[2] // b, b).max(axis=(1, 3, 5))
             assert np.all(bounds[:blk.shape[0], :blk.shape[1], :blk.shape[2]] >= blk)
+            if b == 8:
+                top = bounds.max()
+                line.append(f"  8^3 bounds: max {top / n:.1f}, blocks within 1/8 of it: {int((bounds >= top - top // 8).sum())}, within 1/64: "
+                            f"{int((bounds >= top - top // 64).sum())}, equal to it: {int((bounds == top).sum())}; best leaf inside the top block: "
+                            f"{blk[np.unravel_index(np.argmax(bounds[:blk.shape[0], :blk.shape[1], :blk.shape[2]]), blk.shape)] / n:.1f}")
             open_blocks = int((bounds >= thr).sum())
             line.append(f"  block {b}^3: {bounds.size} blocks, {open_blocks} with bound >= threshold ({100.0 * open_blocks / bounds.size:.1f}%)"
                         f" -> {open_blocks * b ** 3} leaves ({100.0 * open_blocks * b ** 3 / sums.size:.1f}% of brute force)")
