@@ -182,7 +182,9 @@ void orc_fcsm_match_full(void* hi, void* lo, int depth, int full_depth, double m
   Histogram sh(histogram_size, 0.f);
   if (submap_histogram)
     for (int i = 0; i < histogram_size; ++i) sh[i] = submap_histogram[i];
-  FastCorrelativeScanMatcher m(*(HybridGrid*)hi, (const HybridGrid*)lo, o, {{sh, 0.f}});
+  std::vector<std::pair<Histogram, float>> at_angles;
+  at_angles.emplace_back(sh, 0.f);
+  FastCorrelativeScanMatcher m(*(HybridGrid*)hi, (const HybridGrid*)lo, o, at_angles);
   Histogram h(histogram_size, 0.f);
   if (histogram)
     for (int i = 0; i < histogram_size; ++i) h[i] = histogram[i];
@@ -194,7 +196,9 @@ void orc_fcsm_match_full(void* hi, void* lo, int depth, int full_depth, double m
 // RotationalScanMatcher: one submap histogram at angle 0, scores of `histogram` at the given angles
 void orc_rotational_match(const float* submap_histogram, int size, float submap_angle, const float* histogram, float initial_angle,
                           const float* angles, int num_angles, float* scores_out) {
-  RotationalScanMatcher m({{Histogram(submap_histogram, submap_histogram + size), submap_angle}});
+  std::vector<std::pair<Histogram, float>> at_angles;
+  at_angles.emplace_back(Histogram(submap_histogram, submap_histogram + size), submap_angle);
+  RotationalScanMatcher m(at_angles);
   const std::vector<float> s = m.Match(Histogram(histogram, histogram + size), initial_angle, std::vector<float>(angles, angles + num_angles));
   for (int i = 0; i < num_angles; ++i) scores_out[i] = s[i];
 }

@@ -106,8 +106,14 @@ class FastCorrelativeScanMatcher {
   // thread-pool pattern, constraint_builder_3d.cc:189-197). `histograms_at_angles` feeds the rotational matcher
   // (HistogramsAtAnglesFromNodes, cc:114-127); the 3-DoF entry point does not use it.
   FastCorrelativeScanMatcher(const HybridGrid& hi, const HybridGrid* lo, const FcsmOptions& o,
-                             const std::vector<std::pair<Histogram, float>>& histograms_at_angles = {{Histogram(10, 0.f), 0.f}})
+                             const std::vector<std::pair<Histogram, float>>& histograms_at_angles = zero_histogram())
       : o_(o), resolution_(hi.resolution()), stack_(hi, o), lo_(lo), rotational_(histograms_at_angles) {}
+
+  static std::vector<std::pair<Histogram, float>> zero_histogram() {  // the reference's own test fixture: Zero(10) at angle 0
+    std::vector<std::pair<Histogram, float>> v;
+    v.emplace_back(Histogram(10, 0.f), 0.f);
+    return v;
+  }
 
   FcsmResult MatchWith3DofInitial(const Rigid3d& pose_in_submap_guess, const float* hi_pts, int64_t n_hi,
                                   const float* lo_pts, int64_t n_lo, float min_score) const {
