@@ -236,6 +236,28 @@ class FastCorrelativeScanMatcher3D {
     if (!r.found) return nullptr;
     return std::unique_ptr<Result>(new Result{r.score, Rigid3d::from7(r.pose_estimate), r.rotational_score, r.low_resolution_score});
   }
+  // fast_correlative_scan_matcher_3d.h:85-95: the full search (yaw steps x translation window). `submap_histogram` is what the
+  // reference's RotationalScanMatcher accumulates from the submap's nodes; `scan_histogram` / `gravity_alignment` (w x y z) come
+  // from the node's TrajectoryNode::Data.
+  std::unique_ptr<Result> Match(const Rigid3d& global_node_pose, const Rigid3d& global_submap_pose,
+                                const std::vector<float>& submap_histogram, const std::vector<float>& scan_histogram,
+                                const std::array<double, 4>& gravity_alignment, const PointCloud& high_resolution_point_cloud,
+                                const PointCloud& low_resolution_point_cloud, float min_score) const {
+    if (submap_histogram.size() != scan_histogram.size() || submap_histogram.empty()) throw Error(DL_ERR_ARG, "histogram sizes differ");
+    const dl_fcsm_options o = options_.c();
+    double node[7], submap[7];
+    global_node_pose.to7(node);
+    global_submap_pose.to7(submap);
+    dl_fcsm_result r{};
+    ctx_->check(dl_fcsm_match(ctx_->get(), &o, submap_histogram.data(), scan_histogram.data(), (int32_t)scan_histogram.size(), node,
+                              submap, gravity_alignment.data(),
+                              high_resolution_point_cloud.empty() ? nullptr : high_resolution_point_cloud[0].data(),
+                              (int64_t)high_resolution_point_cloud.size(),
+                              low_resolution_point_cloud.empty() ? nullptr : low_resolution_point_cloud[0].data(),
+                              (int64_t)low_resolution_point_cloud.size(), hi_->get(), lo_->get(), min_score, &r));
+    if (!r.found) return nullptr;
+    return std::unique_ptr<Result>(new Result{r.score, Rigid3d::from7(r.pose_estimate), r.rotational_score, r.low_resolution_score});
+  }
  private:
   Context* ctx_;
   const DeviceHybridGrid* hi_;
