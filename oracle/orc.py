@@ -135,6 +135,9 @@ def lib():
                                       f64p, f32p, C.c_int64, f32p, C.c_int64, C.c_float, C.POINTER(FcsmResult)]
     L.orc_decode_point_cloud2.restype = C.c_int64
     L.orc_decode_point_cloud2.argtypes = [C.c_int] * 6 + [C.c_void_p, C.c_int64, f64p, f32p, C.POINTER(C.c_double)]
+    L.orc_pose_graph_solve.argtypes = [C.c_int, C.c_int, f64p, C.c_int, np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS"), f64p, f64p,
+                                       C.c_int, C.c_int, C.POINTER(SolveSummary)]
+    L.orc_spa_residual.argtypes = [f64p, f64p, f64p, C.c_double, C.c_double, f64p, f64p]
     L.orc_fcsm_match_full.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                       C.c_double, f64p, f64p, f32p, C.c_int64, f32p, C.c_int64, C.c_void_p, C.c_int, C.c_float,
                                       C.POINTER(FcsmResult), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
@@ -509,3 +512,26 @@ def compute_histogram(points, size):
     out = np.zeros(size, np.float32)
     lib().orc_compute_histogram(p, len(p), size, out)
     return out
+
+
+def pose_graph_solve(submap_poses, node_poses, constraints, fix_z=False, max_iter=50):
+    """OptimizationProblem3D::Solve reduced to what this fork keeps active: SPA constraints only.
+    constraints: iterable of (submap_index, node_index, zbar_ij pose7, translation_weight, rotation_weight).
+    Returns (submap poses, node poses, summary dict)."""
+    S, N = len(submap_poses), len(node_poses)
+    poses = np.ascontiguousarray(np.concatenate([np.asarray(submap_poses, np.float64).reshape(S, 7),
+                                                 np.asarray(node_poses, np.float64).reshape(N, 7)]))
+    cs = list(constraints)
+    idx = np.ascontiguousarray([[c[0], c[1]] for c in cs], np.int32).reshape(-1, 2)
+    zbar = np.ascontiguousarray([c[2] for c in cs], np.float64).reshape(-1, 7)
+    w = np.ascontiguousarray([[c[3], c[4]] for c in cs], np.float64).reshape(-1, 2)
+    s = SolveSummary()
+    lib().orc_pose_graph_solve(S, N, poses, len(cs), idx, zbar, w, int(fix_z), max_iter, C.byref(s))
+    return poses[:S].copy(), poses[S:].copy(), s.as_dict()
+
+
+def spa_residual(pose_i, pose_j, zbar, translation_weight, rotation_weight):
+    e, jac = np.zeros(6), np.zeros(84)
+    lib().orc_spa_residual(np.ascontiguousarray(pose_i, np.float64), np.ascontiguousarray(pose_j, np.float64),
+                           np.ascontiguousarray(zbar, np.float64), translation_weight, rotation_weight, e, jac)
+    return e, jac.reshape(6, 14)

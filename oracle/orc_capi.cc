@@ -12,6 +12,7 @@
 #include "orc_grid.h"
 #include "orc_imu.h"
 #include "orc_nls.h"
+#include "orc_posegraph.h"
 #include "orc_rtcsm.h"
 
 using namespace orc;
@@ -251,6 +252,35 @@ void orc_ceres_match(int n_pairs, const float* const* clouds, const int64_t* siz
   }
   if (iteration_costs)
     for (size_t i = 0; i < s.iterations.size(); ++i) iteration_costs[i] = s.iterations[i].cost;
+}
+
+// ---- sparse pose adjustment (the fork's OptimizationProblem3D::Solve without landmarks / fixed frames)
+// poses7: num_submaps + num_nodes rows (t xyz, q wxyz), in-out. constraints: per row submap index, node index; zbar 7 doubles;
+// weights 2 doubles. Returns residuals at the solution when residuals_out != null (6 per constraint).
+void orc_pose_graph_solve(int num_submaps, int num_nodes, double* poses7, int num_constraints, const int32_t* submap_node,
+                          const double* zbar7, const double* weights2, int fix_z, int max_iter, OrcSolveSummary* summary) {
+  std::vector<SpaConstraint> cs(num_constraints);
+  for (int i = 0; i < num_constraints; ++i)
+    cs[i] = {submap_node[2 * i], submap_node[2 * i + 1], pose_in(zbar7 + 7 * i), weights2[2 * i], weights2[2 * i + 1]};
+  SolveSummary s;
+  solve_pose_graph(num_submaps, num_nodes, poses7, cs, fix_z != 0, max_iter, &s);
+  if (summary)
+    *summary = {s.initial_cost, s.final_cost, (int)s.iterations.size(), s.num_successful_steps, s.num_unsuccessful_steps,
+                s.termination, s.num_residual_evaluations, s.num_jacobian_evaluations};
+}
+// One SPA residual (6) and its 6 x 14 ambient Jacobian (d / d [q_i(4) t_i(3) q_j(4) t_j(3)], row-major) for finite-difference checks
+void orc_spa_residual(const double* pose_i7, const double* pose_j7, const double* zbar7, double tw, double rw, double* e6,
+                      double* jac84) {
+  const SpaConstraint c{0, 0, pose_in(zbar7), tw, rw};
+  using J = JetN<14>;
+  J qi[4], ti[3], qj[4], tj[3], e[6];
+  for (int k = 0; k < 4; ++k) { qi[k] = J::variable(pose_i7[3 + k], k); qj[k] = J::variable(pose_j7[3 + k], 7 + k); }
+  for (int k = 0; k < 3; ++k) { ti[k] = J::variable(pose_i7[k], 4 + k); tj[k] = J::variable(pose_j7[k], 11 + k); }
+  spa_residual(c, qi, ti, qj, tj, e);
+  for (int r = 0; r < 6; ++r) {
+    e6[r] = e[r].a;
+    for (int k = 0; k < 14; ++k) jac84[14 * r + k] = e[r].v[k];
+  }
 }
 
 // Cost, local gradient (6) and local Gauss-Newton matrix J^T J (6x6 row-major) at a pose: the quantities
