@@ -54,6 +54,20 @@ def compute(orc):
     f = orc.fcsm_match_3dof(g, g, CLOUD, CLOUD, orc.IDENTITY_POSE, 0.1, **TEST_OPTS)
     rec["loop_closure_fixture"] = {"score": float(f.score), "offset": [int(v) for v in f.offset],
                                    "low_resolution_score": float(f.low_resolution_score), "pose": [float(v) for v in f.pose]}
+    full, scan_index, num_scans = orc.fcsm_match_full(g, g, CLOUD, CLOUD, [0, 0, 0, 0.9987502603949663, 0, 0, 0.04997916927067833],
+                                                      orc.IDENTITY_POSE, 0.1, xy_window=0.8, z_window=0.8, angular_window=0.3,
+                                                      min_low_resolution_score=0.15, min_rotational_score=0.1, depth=6, full_depth=6)
+    rec["loop_closure_full_match"] = {"score": float(full.score), "scan_index": int(scan_index), "num_scans": int(num_scans),
+                                      "pose": [float(v) for v in full.pose]}
+    # sparse pose adjustment: 2 submaps, 6 nodes on a circle, constraints from both submaps with fixed pseudo-noise
+    ang = np.linspace(0, 2 * np.pi, 6, endpoint=False)
+    nodes = [np.array([3 * np.cos(a), 3 * np.sin(a), 0.1 * k, np.cos(a / 2), 0, 0, np.sin(a / 2)]) for k, a in enumerate(ang)]
+    submaps = [np.array([0, 0, 0, 1.0, 0, 0, 0]), np.array([1.0, 0.5, 0, np.cos(0.2), 0, 0, np.sin(0.2)])]
+    cons = [(sid, k, nodes[k] + np.array([0.01 * ((k + sid) % 3 - 1), -0.02 * ((k * 2 + sid) % 3 - 1), 0.005 * k, 0, 0, 0, 0]), 1.0 + sid, 2.0)
+            for sid in range(2) for k in range(6)]
+    so, no, summ = orc.pose_graph_solve(submaps, [n + np.array([0.05, -0.05, 0.02, 0, 0, 0, 0]) for n in nodes], cons)
+    rec["pose_graph"] = {"final_cost": float(summ["final_cost"]), "num_iterations": int(summ["num_iterations"]),
+                         "node0": [float(v) for v in no[0]], "submap1": [float(v) for v in so[1]]}
     rec["decode"] = {}
     for name in LAYOUTS:
         data, step, offs, tt, _ = message(name, 4097, 11, last_is_bad=(name == "ouster48"))

@@ -19,6 +19,11 @@ def test_oracle_reproduces_the_golden_vectors(orc):
     assert now["grid_hi_cells"] == GOLDEN["grid_hi_cells"] and now["grid_lo_cells"] == GOLDEN["grid_lo_cells"]
     assert now["decode"] == GOLDEN["decode"]
     assert now["loop_closure_fixture"] == GOLDEN["loop_closure_fixture"]
+    assert now["loop_closure_full_match"] == GOLDEN["loop_closure_full_match"]
+    assert now["pose_graph"]["num_iterations"] == GOLDEN["pose_graph"]["num_iterations"]
+    for k in ("node0", "submap1"):
+        assert np.allclose(now["pose_graph"][k], GOLDEN["pose_graph"][k], rtol=0, atol=1e-12)
+    assert abs(now["pose_graph"]["final_cost"] - GOLDEN["pose_graph"]["final_cost"]) <= 1e-15
     for a, b in zip(now["scans"], GOLDEN["scans"]):
         for k in ("input_rows", "num_points", "first_keep", "num_first", "returns_local", "returns_tracking", "num_returns",
                   "misses_tracking", "current_pose", "adaptive_high", "adaptive_low", "num_iterations"):
