@@ -140,3 +140,31 @@ def test_fix_z_keeps_heights(orc):
     lifted = [t + np.array([0.2, -0.1, 0.4, 0, 0, 0, 0]) for t in truth]
     _, n_out, summary = orc.pose_graph_solve([ident], lifted, cons, fix_z=True)
     assert all(a[2] == b[2] for a, b in zip(n_out, lifted)) and summary["final_cost"] < summary["initial_cost"]
+
+
+def test_solution_is_a_local_minimum(orc):
+    """Independent of the solver: at the returned poses no small perturbation of any node (translation or rotation) lowers
+    the total SPA cost, and the cost equals the summary's final_cost."""
+    rng = np.random.default_rng(8)
+    ident = np.array([0, 0, 0, 1.0, 0, 0, 0])
+    submaps = [ident, np.array([2.0, -1.0, 0.3, *aa_to_q([0.05, -0.02, 0.7])])]
+    truth = [np.array([*rng.uniform(-6, 6, 3), *aa_to_q(rng.uniform(-0.8, 0.8, 3))]) for _ in range(8)]
+    cons = []
+    for s in range(2):
+        for k in range(8):
+            z = compose(compose(inverse(submaps[s]), truth[k]), np.array([*rng.normal(0, 0.05, 3), *aa_to_q(rng.normal(0, 0.03, 3))]))
+            cons.append((s, k, z, 1.0 + s, 3.0))
+    s_out, n_out, summary = orc.pose_graph_solve(submaps, truth, cons)
+
+    def cost(sub, nodes):
+        return 0.5 * sum(float(np.sum(orc.spa_residual(sub[c[0]], nodes[c[1]], c[2], c[3], c[4])[0] ** 2)) for c in cons)
+    base = cost(s_out, n_out)
+    assert abs(base - summary["final_cost"]) <= 1e-12 * max(1.0, base) and summary["termination"] == 0
+    for _ in range(60):
+        k = rng.integers(8)
+        moved = [p.copy() for p in n_out]
+        if rng.random() < 0.5:
+            moved[k][:3] += rng.normal(0, 1e-3, 3)
+        else:
+            moved[k][3:] = qmul(aa_to_q(rng.normal(0, 1e-3, 3)), moved[k][3:])
+        assert cost(s_out, moved) >= base - 1e-12
