@@ -136,7 +136,7 @@ def lib():
     L.orc_decode_point_cloud2.restype = C.c_int64
     L.orc_decode_point_cloud2.argtypes = [C.c_int] * 6 + [C.c_void_p, C.c_int64, f64p, f32p, C.POINTER(C.c_double)]
     L.orc_pose_graph_solve.argtypes = [C.c_int, C.c_int, f64p, C.c_int, np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS"), f64p, f64p,
-                                       C.c_int, C.c_int, C.POINTER(SolveSummary)]
+                                       C.c_int, C.c_int, C.POINTER(SolveSummary), C.c_int]
     L.orc_spa_residual.argtypes = [f64p, f64p, f64p, C.c_double, C.c_double, f64p, f64p]
     L.orc_fcsm_match_full.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                       C.c_double, f64p, f64p, f32p, C.c_int64, f32p, C.c_int64, C.c_void_p, C.c_int, C.c_float,
@@ -514,7 +514,7 @@ def compute_histogram(points, size):
     return out
 
 
-def pose_graph_solve(submap_poses, node_poses, constraints, fix_z=False, max_iter=50):
+def pose_graph_solve(submap_poses, node_poses, constraints, fix_z=False, max_iter=50, linear_solver="normal_cholesky"):
     """OptimizationProblem3D::Solve reduced to what this fork keeps active: SPA constraints only.
     constraints: iterable of (submap_index, node_index, zbar_ij pose7, translation_weight, rotation_weight).
     Returns (submap poses, node poses, summary dict)."""
@@ -526,7 +526,8 @@ def pose_graph_solve(submap_poses, node_poses, constraints, fix_z=False, max_ite
     zbar = np.ascontiguousarray([c[2] for c in cs], np.float64).reshape(-1, 7)
     w = np.ascontiguousarray([[c[3], c[4]] for c in cs], np.float64).reshape(-1, 2)
     s = SolveSummary()
-    lib().orc_pose_graph_solve(S, N, poses, len(cs), idx, zbar, w, int(fix_z), max_iter, C.byref(s))
+    lib().orc_pose_graph_solve(S, N, poses, len(cs), idx, zbar, w, int(fix_z), max_iter, C.byref(s),
+                               {"dense_qr": 0, "normal_cholesky": 1}[linear_solver])
     return poses[:S].copy(), poses[S:].copy(), s.as_dict()
 
 

@@ -258,12 +258,13 @@ void orc_ceres_match(int n_pairs, const float* const* clouds, const int64_t* siz
 // poses7: num_submaps + num_nodes rows (t xyz, q wxyz), in-out. constraints: per row submap index, node index; zbar 7 doubles;
 // weights 2 doubles. Returns residuals at the solution when residuals_out != null (6 per constraint).
 void orc_pose_graph_solve(int num_submaps, int num_nodes, double* poses7, int num_constraints, const int32_t* submap_node,
-                          const double* zbar7, const double* weights2, int fix_z, int max_iter, OrcSolveSummary* summary) {
+                          const double* zbar7, const double* weights2, int fix_z, int max_iter, OrcSolveSummary* summary,
+                          int linear_solver) {
   std::vector<SpaConstraint> cs(num_constraints);
   for (int i = 0; i < num_constraints; ++i)
     cs[i] = {submap_node[2 * i], submap_node[2 * i + 1], pose_in(zbar7 + 7 * i), weights2[2 * i], weights2[2 * i + 1]};
   SolveSummary s;
-  solve_pose_graph(num_submaps, num_nodes, poses7, cs, fix_z != 0, max_iter, &s);
+  solve_pose_graph(num_submaps, num_nodes, poses7, cs, fix_z != 0, max_iter, &s, linear_solver ? kNormalCholesky : kDenseQr);
   if (summary)
     *summary = {s.initial_cost, s.final_cost, (int)s.iterations.size(), s.num_successful_steps, s.num_unsuccessful_steps,
                 s.termination, s.num_residual_evaluations, s.num_jacobian_evaluations};

@@ -316,9 +316,41 @@ struct LmConstants {
   int max_consecutive_nonmonotonic_steps = 5;
 };
 
+// Dense Cholesky solve of the symmetric positive definite system A y = b (A row-major n x n, destroyed). False if a pivot is
+// not positive. The linear algebra of ceres' *_NORMAL_CHOLESKY solvers, without their sparsity.
+inline bool cholesky_solve_dense(double* A, const double* b, int n, double* y) {
+  for (int j = 0; j < n; ++j) {
+    double d = A[(size_t)j * n + j];
+    for (int k = 0; k < j; ++k) d -= A[(size_t)j * n + k] * A[(size_t)j * n + k];
+    if (!(d > 0.)) return false;
+    d = std::sqrt(d);
+    A[(size_t)j * n + j] = d;
+    for (int i = j + 1; i < n; ++i) {
+      double s = A[(size_t)i * n + j];
+      for (int k = 0; k < j; ++k) s -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+      A[(size_t)i * n + j] = s / d;
+    }
+  }
+  std::vector<double> z(n);
+  for (int i = 0; i < n; ++i) {
+    double s = b[i];
+    for (int k = 0; k < i; ++k) s -= A[(size_t)i * n + k] * z[k];
+    z[i] = s / A[(size_t)i * n + i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = z[i];
+    for (int k = i + 1; k < n; ++k) s -= A[(size_t)k * n + i] * y[k];
+    y[i] = s / A[(size_t)i * n + i];
+  }
+  return true;
+}
+
+enum LinearSolver { kDenseQr = 0, kNormalCholesky = 1 };
+
 template <typename Problem>
 inline void solve_trust_region(const Problem& problem, bool use_nonmonotonic_steps, int max_num_iterations,
-                               double* parameters /*ambient size, in-out*/, SolveSummary* summary) {
+                               double* parameters /*ambient size, in-out*/, SolveSummary* summary,
+                               LinearSolver linear_solver = kDenseQr) {
   const LmConstants c;
   const int m = problem.num_residuals();
   const int n = problem.num_local();
@@ -412,12 +444,27 @@ inline void solve_trust_region(const Problem& problem, bool use_nonmonotonic_ste
       }
     }
     for (int j = 0; j < n; ++j) lmdiag[j] = std::sqrt(diag[j] / radius);
-    std::copy(J.begin(), J.end(), Jaug.begin());
-    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) Jaug[(size_t)(m + i) * n + j] = (i == j) ? lmdiag[j] : 0.0;
-    for (int i = 0; i < m; ++i) rhs[i] = res[i];
-    for (int i = 0; i < n; ++i) rhs[m + i] = 0;
-    householder_qr_solve(Jaug.data(), rhs.data(), m + n, n, step.data());
     bool step_ok = true;
+    if (linear_solver == kNormalCholesky) {
+      // (J^T J + D^T D) y = J^T r, the system the *_NORMAL_CHOLESKY solvers factor (J is the column-scaled Jacobian)
+      std::vector<double> H((size_t)n * n, 0.0), b(n, 0.0);
+      for (int i = 0; i < m; ++i) {
+        const double* row = J.data() + (size_t)i * n;
+        for (int a = 0; a < n; ++a) {
+          if (row[a] == 0.0) continue;
+          b[a] += row[a] * res[i];
+          for (int c2 = 0; c2 <= a; ++c2) H[(size_t)a * n + c2] += row[a] * row[c2];
+        }
+      }
+      for (int a = 0; a < n; ++a) H[(size_t)a * n + a] += lmdiag[a] * lmdiag[a];
+      step_ok = cholesky_solve_dense(H.data(), b.data(), n, step.data());
+    } else {
+      std::copy(J.begin(), J.end(), Jaug.begin());
+      for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) Jaug[(size_t)(m + i) * n + j] = (i == j) ? lmdiag[j] : 0.0;
+      for (int i = 0; i < m; ++i) rhs[i] = res[i];
+      for (int i = 0; i < n; ++i) rhs[m + i] = 0;
+      householder_qr_solve(Jaug.data(), rhs.data(), m + n, n, step.data());
+    }
     for (int j = 0; j < n; ++j) { if (!std::isfinite(step[j])) step_ok = false; step[j] = -step[j]; }
     reuse_diagonal = true;
 

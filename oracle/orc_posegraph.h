@@ -11,8 +11,8 @@
 //               ComputeUnscaledError(zbar_ij, c_i, c_j)) (cost_helpers_impl.h:58-100) with
 //               RotationQuaternionToAngleAxisVector (transform/transform.h:59-83), 6 per constraint, autodiff Jacobians
 //   solver      ceres::Solve with pose_graph.lua's options (LM, 50 iterations, no non-monotonic steps); the linear solver
-//               there is SPARSE_NORMAL_CHOLESKY, here the dense QR of orc_nls.h's trust-region loop: the same LM step in
-//               exact arithmetic.
+//               there is SPARSE_NORMAL_CHOLESKY: here the normal equations are formed and factored densely (default), or the
+//               dense QR of the scan matcher's loop is used as a cross-check: the same LM step in exact arithmetic.
 // Jets use one summation order for norms (x^2 + y^2 + z^2 + w^2 left to right) in both the double and the Jet instantiation;
 // Eigen would pair the doubles differently (1 ulp). Pinned to the reference's own test of this function
 // (optimization_problem_3d_test.cc:106-196, a statistical property) in tests/test_posegraph_oracle.py.
@@ -213,7 +213,8 @@ class PoseGraphProblem {
 
 // OptimizationProblem3D::Solve for the SPA-only problem. poses: S submaps then N nodes, 7 doubles each (t xyz, q wxyz), in-out.
 inline void solve_pose_graph(int num_submaps, int num_nodes, double* poses7, const std::vector<SpaConstraint>& constraints,
-                             bool fix_z, int max_num_iterations, SolveSummary* summary) {
+                             bool fix_z, int max_num_iterations, SolveSummary* summary,
+                             LinearSolver linear_solver = kNormalCholesky) {
   PoseGraphProblem problem(num_submaps, num_nodes, V3d{poses7[0], poses7[1], poses7[2]}, constraints, fix_z);
   std::vector<double> x(problem.num_ambient());
   for (int p = 0; p < num_submaps + num_nodes; ++p) {
@@ -225,7 +226,7 @@ inline void solve_pose_graph(int num_submaps, int num_nodes, double* poses7, con
       t[0] = s[0]; t[1] = s[1]; t[2] = s[2];
     }
   }
-  solve_trust_region(problem, /*use_nonmonotonic_steps=*/false, max_num_iterations, x.data(), summary);
+  solve_trust_region(problem, /*use_nonmonotonic_steps=*/false, max_num_iterations, x.data(), summary, linear_solver);
   for (int p = 0; p < num_submaps + num_nodes; ++p) {
     double* s = poses7 + 7 * p;
     const double* q = x.data() + problem.rotation_offset(p);

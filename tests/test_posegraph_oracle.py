@@ -168,3 +168,21 @@ def test_solution_is_a_local_minimum(orc):
         else:
             moved[k][3:] = qmul(aa_to_q(rng.normal(0, 1e-3, 3)), moved[k][3:])
         assert cost(s_out, moved) >= base - 1e-12
+
+
+def test_normal_cholesky_and_dense_qr_agree(orc):
+    """The two linear solvers behind the same trust-region loop (the reference's SPARSE_NORMAL_CHOLESKY forms and factors the
+    normal equations; the scan matcher's DENSE_QR factors the augmented Jacobian) take the same steps: same iteration
+    counts, poses equal to 1e-9."""
+    rng = np.random.default_rng(12)
+    ident = np.array([0, 0, 0, 1.0, 0, 0, 0])
+    submaps = [ident, np.array([3.0, 2.0, -0.1, *aa_to_q([0.01, 0.02, -0.4])]), np.array([-2.0, 1.0, 0.2, *aa_to_q([0, 0, 2.0])])]
+    truth = [np.array([*rng.uniform(-8, 8, 3), *aa_to_q(rng.uniform(-1, 1, 3))]) for _ in range(15)]
+    cons = [(s, k, compose(compose(inverse(submaps[s]), truth[k]), np.array([*rng.normal(0, 0.1, 3), *aa_to_q(rng.normal(0, 0.05, 3))])),
+             1.0, 2.0) for s in range(3) for k in range(15) if (s + k) % 2 == 0 or s == 0]
+    start = [compose(t, np.array([*rng.normal(0, 0.3, 3), *aa_to_q(rng.normal(0, 0.1, 3))])) for t in truth]
+    sa, na, qa = orc.pose_graph_solve(submaps, start, cons, linear_solver="dense_qr")
+    sb, nb, qb = orc.pose_graph_solve(submaps, start, cons, linear_solver="normal_cholesky")
+    assert qa["num_iterations"] == qb["num_iterations"] and qa["termination"] == qb["termination"] == 0
+    assert abs(qa["final_cost"] - qb["final_cost"]) <= 1e-12 * max(1.0, qa["final_cost"])
+    assert np.abs(na - nb).max() < 1e-9 and np.abs(sa - sb).max() < 1e-9
