@@ -135,6 +135,12 @@ def lib():
                                       f64p, f32p, C.c_int64, f32p, C.c_int64, C.c_float, C.POINTER(FcsmResult)]
     L.orc_decode_point_cloud2.restype = C.c_int64
     L.orc_decode_point_cloud2.argtypes = [C.c_int] * 6 + [C.c_void_p, C.c_int64, f64p, f32p, C.POINTER(C.c_double)]
+    L.orc_angle_of_angle_axis_f.restype = C.c_float
+    L.orc_angle_of_angle_axis_f.argtypes = [f32p]
+    L.orc_rotation_delta_cost.restype = C.c_double
+    L.orc_rotation_delta_cost.argtypes = [C.c_double, f64p, f64p]
+    L.orc_precomputation_values.argtypes = [C.c_void_p, C.c_int, C.c_int64, np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS"),
+                                            np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")]
     L.orc_pose_graph_solve.argtypes = [C.c_int, C.c_int, f64p, C.c_int, np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS"), f64p, f64p,
                                        C.c_int, C.c_int, C.POINTER(SolveSummary), C.c_int]
     L.orc_spa_residual.argtypes = [f64p, f64p, f64p, C.c_double, C.c_double, f64p, f64p]
@@ -536,3 +542,18 @@ def spa_residual(pose_i, pose_j, zbar, translation_weight, rotation_weight):
     lib().orc_spa_residual(np.ascontiguousarray(pose_i, np.float64), np.ascontiguousarray(pose_j, np.float64),
                            np.ascontiguousarray(zbar, np.float64), translation_weight, rotation_weight, e, jac)
     return e, jac.reshape(6, 14)
+
+
+def rotation_delta_cost(scale, target_q, q):
+    return lib().orc_rotation_delta_cost(float(scale), np.ascontiguousarray(target_q, np.float64), np.ascontiguousarray(q, np.float64))
+
+
+def precomputation_values(grid, depth, cells):
+    xyz = np.ascontiguousarray(cells, np.int32).reshape(-1, 3)
+    out = np.zeros(len(xyz), np.int32)
+    lib().orc_precomputation_values(grid.h, depth, len(xyz), xyz, out)
+    return out
+
+
+def angle_of_angle_axis_f(aa):
+    return float(lib().orc_angle_of_angle_axis_f(np.ascontiguousarray(aa, np.float32)))

@@ -254,6 +254,33 @@ void orc_ceres_match(int n_pairs, const float* const* clouds, const int64_t* siz
     for (size_t i = 0; i < s.iterations.size(); ++i) iteration_costs[i] = s.iterations[i].cost;
 }
 
+// transform::GetAngle(Rigid3f::Rotation(AngleAxisVectorToRotationQuaternion(aa))) in float (transform.h:33-37, :85-99)
+float orc_angle_of_angle_axis_f(const float* aa) { return rotation_angle(angle_axis_to_quat(V3f{aa[0], aa[1], aa[2]})); }
+
+// RotationDeltaCostFunctor3D alone (rotation_delta_cost_functor_3d.h:42-53): sum of squared residuals at rotation q for a
+// functor built with `scale` and `target` — the quantity the reference's own unit test checks.
+double orc_rotation_delta_cost(double scale, const double* target_q, const double* q) {
+  CeresMatcherOptions o;
+  o.translation_weight = 0.;
+  o.rotation_weight = scale;
+  const Rigid3d initial{{0., 0., 0.}, {target_q[0], target_q[1], target_q[2], target_q[3]}};
+  ScanMatchProblem p(o, {0., 0., 0.}, initial, {});
+  const double x[7] = {0., 0., 0., q[0], q[1], q[2], q[3]};
+  double r[3] = {0., 0., 0.};
+  p.Evaluate(x, r, nullptr);
+  return r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+}
+// PrecomputeGrid chain of precomputation_grid_3d_test.cc: depth 0 = ConvertToPrecomputationGrid, depth d = PrecomputeGrid(
+// previous, false, (1 << (d - 1)) * Ones): value (0..255) at the queried cells of the depth-`depth` grid.
+void orc_precomputation_values(void* grid, int depth, int64_t n, const int32_t* xyz, int32_t* out) {
+  std::unique_ptr<HybridGrid> g = convert_to_precomputation_grid(*(HybridGrid*)grid);
+  for (int d = 1; d <= depth; ++d) {
+    const int s = 1 << (d - 1);
+    g = precompute_grid(*g, false, I3{s, s, s});
+  }
+  for (int64_t i = 0; i < n; ++i) out[i] = g->value(I3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]});
+}
+
 // ---- sparse pose adjustment (the fork's OptimizationProblem3D::Solve without landmarks / fixed frames)
 // poses7: num_submaps + num_nodes rows (t xyz, q wxyz), in-out. constraints: per row submap index, node index; zbar 7 doubles;
 // weights 2 doubles. Returns residuals at the solution when residuals_out != null (6 per constraint).

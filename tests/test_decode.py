@@ -75,6 +75,17 @@ def test_oracle_decode_semantics(orc, name):
         assert rows[-1, 3] == 0.0 and np.all(rows[:, 3] <= 0)          # CHECK_LE(ranges.back().time, 0) downstream
 
 
+def test_transform_timed_point_cloud_reference_fixture(orc):
+    """sensor/point_cloud_test.cc:28-51 (TransformPointCloud / TransformTimedPointCloud): a quarter turn about z maps
+    (0.5, 0.5, 1) to (-0.5, 0.5, 1) and (3.5, 0.5, 42) to (-0.5, 3.5, 42) within 1e-6; times pass through."""
+    dt, offs, tt = LAYOUTS["xyzi16"]
+    pts = np.zeros(2, dt)
+    pts["x"], pts["y"], pts["z"] = [0.5, 3.5], [0.5, 0.5], [1.0, 42.0]
+    quarter = np.array([0, 0, 0, np.cos(np.pi / 4), 0, 0, np.sin(np.pi / 4)])     # Embed3D(Rigid2f::Rotation(M_PI_2))
+    rows, _ = orc.decode_point_cloud2(pts.view(np.uint8).reshape(-1), dt.itemsize, offs, tt, quarter)
+    assert np.abs(rows[:, :3] - [[-0.5, 0.5, 1.0], [-0.5, 3.5, 42.0]]).max() < 1e-6 and np.all(rows[:, 3] == 0)
+
+
 def rot(p):
     w, x, y, z = p[3:]
     return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],

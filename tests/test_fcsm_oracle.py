@@ -163,3 +163,22 @@ def test_compute_histogram_of_a_room(orc):
         h = orc.compute_histogram(pts, 10)
         assert h.sum() > 10
         assert sum(h[k] for k in peaks) > 0.85 * h.sum()
+
+
+def test_precomputation_grid_against_naive_maximum(orc):
+    """SM/precomputation_grid_3d_test.cc:31-78 (TestAgainstNaiveAlgorithm): 1 000 random cells of a 2 m grid set to random
+    probabilities; for depths 0..3 the precomputed value at a random cell equals (to 1e-2, the 8-bit quantisation) the largest
+    probability inside the 2^depth cube that starts there."""
+    rng = np.random.default_rng(23847)
+    g = orc.Grid(2.0)
+    for _ in range(1000):
+        g.set_probability(tuple(int(v) for v in rng.integers(-50, 50, 3)), float(rng.uniform(0.1, 0.9)))
+    for depth in range(4):
+        width = 1 << depth
+        cells = rng.integers(-50, 50, (100, 3))
+        values = orc.precomputation_values(g, depth, cells)
+        for c, v in zip(cells, values):
+            naive = max(g.probability((int(c[0]) + dx, int(c[1]) + dy, int(c[2]) + dz))
+                        for dx in range(width) for dy in range(width) for dz in range(width))
+            naive = max(naive, 0.0)
+            assert abs(naive - (0.1 + v * (0.8 / 255.0))) < 1e-2

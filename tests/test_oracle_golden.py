@@ -346,3 +346,50 @@ def test_ceres_normal_equations_consistent(orc):
         e[a] = h
         fd = (cost_at(e) - cost_at(-e)) / (2 * h)
         assert abs(fd - grad[a]) < 1e-6 * max(1.0, abs(fd)), (a, fd, grad[a])
+
+
+# ---- rotation_delta_cost_functor_3d_test.cc -----------------------------------------------------------------------------------
+def _aa_q(angle, axis):
+    axis = np.asarray(axis, np.float64) / np.linalg.norm(axis)
+    return np.array([np.cos(angle / 2), *(np.sin(angle / 2) * axis)])
+
+
+def _qmul(a, b):
+    return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                     a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]])
+
+
+def test_rotation_delta_same_rotation_gives_zero_cost(orc):  # :47-57
+    ident = np.array([1.0, 0, 0, 0])
+    assert abs(orc.rotation_delta_cost(1.0, ident, ident)) < 1e-8
+    r = _aa_q(0.9, [0.2, 0.1, 0.3])
+    assert abs(orc.rotation_delta_cost(1.0, r, r)) < 1e-8
+
+
+def test_rotation_delta_computes_correct_cost(orc):  # :59-80
+    scale, angle = 1.2, 0.8
+    rotation = _aa_q(angle, [0.2, 0.1, 0.8])
+    target = _aa_q(0.2, [-0.5, 0.3, 0.4])
+    expected = (scale * np.sin(angle / 2)) ** 2
+    assert abs(orc.rotation_delta_cost(scale, [1.0, 0, 0, 0], rotation) - expected) < 1e-8
+    assert abs(orc.rotation_delta_cost(scale, target, _qmul(target, rotation)) - expected) < 1e-8
+    assert abs(orc.rotation_delta_cost(scale, target, _qmul(rotation, target)) - expected) < 1e-8
+
+
+# ---- transform/transform_test.cc:29-46 (GetAngle) ---------------------------------------------------------------------------
+def test_get_angle_of_angle_axis_round_trip(orc):
+    """100 draws of std::mt19937(42): angle ~ U(0, pi), axis = normalised U(-1, 1)^3, all float; GetAngle(Rotation(
+    AngleAxisVectorToRotationQuaternion(angle * axis))) returns the angle to 1e-6."""
+    f = np.float32
+    raw = iter(np.random.RandomState(42).randint(0, 2 ** 32, size=400, dtype=np.uint64))
+
+    def uniform(a, b):      # libstdc++: generate_canonical<float, 24> then (b - a) * c + a, float arithmetic
+        c = f(next(raw)) / f(4294967296.0)
+        if c >= f(1.0):
+            c = np.nextafter(f(1.0), f(0.0))
+        return f(c * f(b - a)) + f(a)
+    for _ in range(100):
+        angle = uniform(f(0.0), f(np.pi))
+        v = np.array([uniform(f(-1), f(1)) for _ in range(3)], f)
+        axis = v / f(np.sqrt(f(v[0] * v[0] + f(v[1] * v[1] + v[2] * v[2]))))
+        assert abs(orc.angle_of_angle_axis_f(angle * axis) - angle) < 1e-6
