@@ -222,6 +222,62 @@ def test_ceres_scene_two_grids_and_batch(ctx, orc):
         assert dt < 1e-7 and dr < 1e-8
 
 
+@pytest.mark.parametrize("angle,axis,rot_w", [(0.2, (0, 0, 1), 0.0), (0.05, (0.3, 0.1, 0.9), 0.1), (0.03, (1, 0, 0), 0.1)])
+def test_ceres_only_optimize_yaw(ctx, orc, angle, axis, rot_w):
+    """YawOnlyQuaternionPlus (rotation_parameterization.h:27-39; ceres_pose.cc:23-44): 4 local parameters on the device as in
+    the oracle — same iterates, and the result is a z rotation times the start."""
+    og = seven_point_grid(orc, 1.0)
+    g = dev_grid(ctx, og)
+    init = orc.angle_axis_pose((-0.95, 0.05, 0.1), angle, axis)
+    want, ws = orc.ceres_match([SEVEN], [og], [1.0], 0.01, rot_w, init[:3], init, only_yaw=True, nonmono=True, max_iter=25)
+    got, gs = ctx.ceres_match([SEVEN], [g], [1.0], 0.01, rot_w, init[:3], init, only_yaw=True, nonmono=True, max_iter=25)
+    dt, dr = pose_error(got, want)
+    assert dt < 1e-7 and dr < 1e-7, (got, want)
+    assert gs["num_iterations"] == ws["num_iterations"] and gs["termination"] == ws["termination"]
+    assert gs["num_successful_steps"] == ws["num_successful_steps"]
+    assert abs(gs["final_cost"] - ws["final_cost"]) < 1e-10
+    qi, q = init[3:], got[3:]
+    d = np.array([q[0] * qi[0] + q[1] * qi[1] + q[2] * qi[2] + q[3] * qi[3],          # q (x) qi^-1
+                  -q[0] * qi[1] + q[1] * qi[0] - q[2] * qi[3] + q[3] * qi[2],
+                  -q[0] * qi[2] + q[1] * qi[3] + q[2] * qi[0] - q[3] * qi[1],
+                  -q[0] * qi[3] - q[1] * qi[2] + q[2] * qi[1] + q[3] * qi[0]])
+    assert abs(d[1]) < 1e-12 and abs(d[2]) < 1e-12
+
+
+def test_ceres_only_optimize_yaw_scene(ctx, orc):
+    w = workload()
+    hi, lo = dev_grid(ctx, w["hi"]), dev_grid(ctx, w["lo"])
+    ing = orc.ingest_scan(w["opts"], w["scans"][1], w["origin"], w["prev"][1], w["cur"][1])
+    pts = ing["returns_tracking"]
+    hk, _ = orc.adaptive_voxel_filter(pts, 2.0, 150, 15.0)
+    lk, _ = orc.adaptive_voxel_filter(pts, 4.0, 200, 60.0)
+    init = w["cur"][1]
+    want, ws = orc.ceres_match([pts[hk], pts[lk]], [w["hi"], w["lo"]], [1.0, 6.0], 5.0, 4e2, init[:3], init, only_yaw=True)
+    got, gs = ctx.ceres_match([pts[hk], pts[lk]], [hi, lo], [1.0, 6.0], 5.0, 4e2, init[:3], init, only_yaw=True)
+    dt, dr = pose_error(got, want)
+    assert dt < 1e-7 and dr < 1e-8 and gs["num_iterations"] == ws["num_iterations"]
+
+
+@pytest.mark.parametrize("tw,rw", [(0.0, 0.0), (-3.0, -7.0), (2.0, 0.0), (0.0, 2.0), (-1.0, 5.0)])
+def test_ceres_non_positive_weights_drop_the_terms(ctx, orc, tw, rw):
+    """ceres_scan_matcher_3d.cc:104-118 (fork): the delta residual blocks exist only for weights > 0."""
+    og = seven_point_grid(orc, 1.0)
+    g = dev_grid(ctx, og)
+    init = orc.angle_axis_pose((-0.9, -0.2, 0.2), 0.02, (0.2, 0.5, 0.8))
+    target = np.array([-5.0, 3.0, 1.0])
+    want, ws = orc.ceres_match([SEVEN], [og], [1.0], tw, rw, target, init, nonmono=True, max_iter=10)
+    got, gs = ctx.ceres_match([SEVEN], [g], [1.0], tw, rw, target, init, nonmono=True, max_iter=10)
+    dt, dr = pose_error(got, want)
+    assert dt < 1e-7 and dr < 1e-7
+    assert abs(gs["initial_cost"] - ws["initial_cost"]) < 1e-13 and gs["num_iterations"] == ws["num_iterations"]
+    wc, wg, wh = orc.ceres_normal_equations([SEVEN], [og], [1.0], tw, rw, target, init, init)
+    c, gr, h = ctx.ceres_normal_equations([SEVEN], [g], [1.0], tw, rw, target, init, init)
+    assert abs(c - wc) < 1e-13 and np.max(np.abs(gr - wg)) < 1e-12 and np.max(np.abs(h - wh)) < 1e-11
+    if tw <= 0 and rw <= 0:   # identical to the problem without the two blocks
+        z, zs = ctx.ceres_match([SEVEN], [g], [1.0], 0.0, 0.0, target, init, nonmono=True, max_iter=10)
+        assert np.array_equal(z, got) and zs["initial_cost"] == gs["initial_cost"]
+
+
 def test_ceres_argument_checks(ctx, orc):
     import dliom
     og = seven_point_grid(orc, 1.0)

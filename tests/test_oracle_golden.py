@@ -393,3 +393,67 @@ def test_get_angle_of_angle_axis_round_trip(orc):
         v = np.array([uniform(f(-1), f(1)) for _ in range(3)], f)
         axis = v / f(np.sqrt(f(v[0] * v[0] + f(v[1] * v[1] + v[2] * v[2]))))
         assert abs(orc.angle_of_angle_axis_f(angle * axis) - angle) < 1e-6
+
+
+# ---------------------------------------------------------------- parameterisation / optional terms
+def _yaw_of(q):
+    w, x, y, z = q
+    return np.arctan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z))
+
+
+def test_ceres_only_optimize_yaw_keeps_roll_pitch(orc):
+    """YawOnlyQuaternionPlus (rotation_parameterization.h:27-39, selected by ceres_pose.cc:23-44 when only_optimize_yaw):
+    the update is q_delta(yaw) (x) q, so whatever the data asks for, the solution is a z-rotation times the start."""
+    og = seven_point_grid(orc, 1.0)
+    # start: small roll AND a yaw error; the truth is the identity rotation, so the full solve removes both ...
+    init = orc.angle_axis_pose((-1.0, 0.0, 0.0), 0.0, (0, 0, 1))
+    roll = orc.angle_axis_pose((0, 0, 0), 0.04, (1, 0, 0))[3:]
+    yaw = orc.angle_axis_pose((0, 0, 0), 0.03, (0, 0, 1))[3:]
+
+    def qmul(a, b):
+        return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                         a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]])
+    init[3:] = qmul(yaw, roll)
+    full, fs = orc.ceres_match([SEVEN], [og], [1.0], 0.01, 0.1, init[:3], init, nonmono=True, max_iter=30)
+    only, os_ = orc.ceres_match([SEVEN], [og], [1.0], 0.01, 0.1, init[:3], init, only_yaw=True, nonmono=True, max_iter=30)
+    # ... while the yaw-only solve leaves q_result (x) q_init^-1 a pure z rotation
+    qi_inv = init[3:] * np.array([1, -1, -1, -1])
+    d = qmul(only[3:], qi_inv)
+    d /= np.linalg.norm(d)
+    assert abs(d[1]) < 1e-12 and abs(d[2]) < 1e-12
+    assert abs(np.linalg.norm(only[3:]) - 1.0) < 1e-12
+    assert only_sane(os_) and os_["final_cost"] < os_["initial_cost"]
+    # the full parameterisation does move roll / pitch on the same data
+    df = qmul(full[3:], qi_inv)
+    assert np.hypot(df[1], df[2]) > 1e-4 and only_sane(fs)
+    # 4 local parameters are enough to remove a pure yaw error (0.2 rad -> below the fixture's 3e-2 tolerance); z never moves
+    init2 = orc.angle_axis_pose((-1.0, 0.0, 0.0), 0.2, (0, 0, 1))
+    a, sa = orc.ceres_match([SEVEN], [og], [1.0], 0.01, 0.0, init2[:3], init2, only_yaw=True, nonmono=True, max_iter=50)
+    assert abs(_yaw_of(a[3:])) < 3e-2 and sa["final_cost"] < 1e-2 and a[4] == 0.0 and a[5] == 0.0
+
+
+def only_sane(s):
+    return s["termination"] in (0, 1) and np.isfinite(s["final_cost"])
+
+
+def test_ceres_non_positive_weights_drop_the_terms(orc):
+    """The fork adds the translation / rotation residual blocks only for weights > 0 (ceres_scan_matcher_3d.cc:104-118):
+    a zero and a negative weight give the same problem, its cost is the occupied-space cost alone, and the result
+    differs from the weighted solve."""
+    og = seven_point_grid(orc, 1.0)
+    init = orc.angle_axis_pose((-0.9, -0.2, 0.2), 0.02, (0.2, 0.5, 0.8))
+    target = np.array([-5.0, 3.0, 1.0])          # far away: a weighted translation term must show up
+    zero, zs = orc.ceres_match([SEVEN], [og], [1.0], 0.0, 0.0, target, init, nonmono=True, max_iter=10)
+    neg, ns = orc.ceres_match([SEVEN], [og], [1.0], -3.0, -7.0, target, init, nonmono=True, max_iter=10)
+    assert np.array_equal(zero, neg) and zs["initial_cost"] == ns["initial_cost"] and zs["num_iterations"] == ns["num_iterations"]
+    c0, g0, h0 = orc.ceres_normal_equations([SEVEN], [og], [1.0], 0.0, 0.0, target, init, init)
+    c1, g1, h1 = orc.ceres_normal_equations([SEVEN], [og], [1.0], 2.0, 0.0, target, init, init)
+    c2, g2, h2 = orc.ceres_normal_equations([SEVEN], [og], [1.0], 0.0, 2.0, target, init, init)
+    assert abs(zs["initial_cost"] - c0) < 1e-15
+    # translation term alone: + 1/2 * w^2 |t - target|^2, Hessian + w^2 I on the translation block only
+    assert abs((c1 - c0) - 0.5 * 4.0 * np.sum((init[:3] - target) ** 2)) < 1e-9
+    assert np.allclose(h1[:3, :3] - h0[:3, :3], 4.0 * np.eye(3), atol=1e-9) and np.allclose(h1[3:, 3:], h0[3:, 3:], atol=1e-12)
+    # rotation term alone at the reference rotation: zero residual, Hessian only on the rotation block
+    assert abs(c2 - c0) < 1e-15 and np.allclose(h2[:3, :], h0[:3, :], atol=1e-12) and not np.allclose(h2[3:, 3:], h0[3:, 3:])
+    with_t, _ = orc.ceres_match([SEVEN], [og], [1.0], 2.0, 0.0, target, init, nonmono=True, max_iter=10)
+    assert np.linalg.norm(with_t[:3] - zero[:3]) > 1e-3
