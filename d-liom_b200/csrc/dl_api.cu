@@ -1270,14 +1270,7 @@ int dl_constraint_search_batch(dl_context* ctx, const dl_constraint_options* opt
 }  // extern "C"
 
 namespace {
-struct HostImuTerm {  // must match ImuTerm in dl_nls.cu
-  double pi[3], qi[4], vi[3], bai[3], bgi[3];
-  double dp[3], dq[4], dv[3];
-  double G[3];
-  double sum_dt;
-  double W[225];
-};
-static_assert(sizeof(HostImuTerm) == kImuTermDoubles * sizeof(double), "ImuTerm layout");
+using HostImuTerm = dl::ImuTerm;  // prepared here on the host for the calls that take finished pre-integrations
 
 // W = weight^2 * Sigma^-1 by Cholesky (Sigma = L L^T, W = L^-T L^-1). False if Sigma is not positive definite.
 bool information_matrix(const double* sigma, double weight, double* W) {
@@ -1370,7 +1363,7 @@ int dl_imu_preintegrate(dl_context* ctx, const dl_imu_noise* noise, int32_t coun
   DL_TRY(h2d(ctx, d_acc, acc, 3 * n));
   DL_TRY(h2d(ctx, d_gyr, gyr, 3 * n));
   DL_TRY(h2d(ctx, d_bias, biases, 6 * (size_t)count));
-  DL_TRY(launch_imu_preintegrate(ctx, count, d_off, d_dt, d_acc, d_gyr, d_bias, *noise, d_out));
+  DL_TRY(launch_imu_preintegrate(ctx, count, d_off, d_dt, d_acc, d_gyr, d_bias, 6, *noise, d_out));
   DL_TRY(d2h(ctx, out, d_out, count));
   return sync(ctx);
 }
@@ -1545,20 +1538,8 @@ FrontendArgs make_frontend_args(const dl_frontend_options& o, const FrontendBuff
 
 int row_floats_of(const dl_frontend_options& o) { return o.range_row_floats == 4 ? 4 : 8; }
 
-// Per-scan constants of the deskew (LTB:426-428 and the scan-constant half of Eigen's slerp), host double math.
-ScanConstants make_scan_constants(const double* prev7, const double* cur7) {
-  ScanConstants c;
-  c.prev = pose_from7(prev7);
-  c.cur = pose_from7(cur7);
-  c.rel = compose(inverse(c.prev), c.cur);
-  const double d = (0.0 * c.rel.q.x + 0.0 * c.rel.q.y) + (0.0 * c.rel.q.z + 1.0 * c.rel.q.w);  // Identity.dot(rel.q)
-  const double abs_d = std::fabs(d);
-  const double one = 1.0 - 2.220446049250313e-16;
-  c.linear_slerp = abs_d >= one;
-  c.negative_dot = d < 0;
-  c.theta = c.linear_slerp ? 0.0 : std::acos(abs_d);
-  c.sin_theta = c.linear_slerp ? 1.0 : std::sin(c.theta);
-  return c;
+ScanConstants make_scan_constants(const double* prev7, const double* cur7) {  // dl_pipeline.cuh has the arithmetic
+  return dl::make_scan_constants(pose_from7(prev7), pose_from7(cur7));
 }
 
 // Stages 1-3: first voxel filter, deskew/transform/gate, second voxel filters, back to the tracking frame.
@@ -1597,7 +1578,7 @@ size_t frontend_small_bytes(int batch, int num_origins) {
 }
 int frontend_upload_small(dl_context* ctx, const dl_frontend_options& o, const FrontendBuffers& f, const int64_t* sizes,
                           const float* origins, int num_origins, const double* prev_poses, const double* cur_poses,
-                          const dl_grid* hi, const dl_grid* lo) {
+                          const dl_grid* hi, const dl_grid* lo, const int32_t* enabled_dev = nullptr) {
   const size_t B = (size_t)f.batch;
   const size_t bytes = frontend_small_bytes(f.batch, num_origins);
   DL_TRY(ctx->reserve_pinned(bytes));
@@ -1610,7 +1591,7 @@ int frontend_upload_small(dl_context* ctx, const dl_frontend_options& o, const F
   NlsProblem* problems = h.take<NlsProblem>(B);
   for (int b = 0; b < f.batch; ++b) {
     counts[b] = (int32_t)sizes[b];
-    sc[b] = make_scan_constants(prev_poses + 7 * b, cur_poses + 7 * b);
+    if (prev_poses) sc[b] = make_scan_constants(prev_poses + 7 * b, cur_poses + 7 * b);
     NlsProblem& p = problems[b];
     std::memset(&p, 0, sizeof(p));
     if (hi && lo) {
@@ -1621,6 +1602,7 @@ int frontend_upload_small(dl_context* ctx, const dl_frontend_options& o, const F
       }
       p.initial_dev = f.initial_pose + 7 * b;
       p.target_dev = f.target + 3 * b;
+      if (enabled_dev) p.enabled_dev = enabled_dev + b;  // scans whose IMU factor could not be formed are not solved
     }
   }
   std::memcpy(org, origins, (size_t)num_origins * 12);
@@ -1629,12 +1611,33 @@ int frontend_upload_small(dl_context* ctx, const dl_frontend_options& o, const F
   filt[1] = {o.low_resolution_adaptive_voxel_filter.max_length, o.low_resolution_adaptive_voxel_filter.min_num_points,
              o.low_resolution_adaptive_voxel_filter.max_range};
   DL_TRY(h2d(ctx, f.counts0, counts, B));
-  DL_TRY(h2d(ctx, f.scans, sc, B));
+  if (prev_poses) DL_TRY(h2d(ctx, f.scans, sc, B));  // otherwise imu_prepare_kernel writes them on the device
   DL_TRY(h2d(ctx, f.origins, org, (size_t)num_origins * 3));
   DL_TRY(h2d(ctx, f.filters, filt, 2));
   DL_TRY(h2d(ctx, f.problems, problems, B));
   DL_CUDA(ctx, cudaEventRecord(ctx->staging_done, ctx->stream));
   return DL_OK;
+}
+
+// IMU coupling of one front-end run: either finished pre-integrations (`host`, factors built on the host) or raw samples
+// (`samples`, everything on the device). frontend_run fills in where the device outputs are.
+struct ImuRun {
+  const dl_frontend_imu* host = nullptr;
+  const dl_frontend_imu_samples* samples = nullptr;
+  dl_nav_state* d_states_out = nullptr;  // in: optional caller-provided device buffer for the estimated states
+  FusedOutput* d_fused = nullptr;        // out
+  dl_nav_state* d_states = nullptr;      // out: estimated states, local frame
+  dl_nav_state* d_predicted = nullptr;   // out (samples only): predicted states, local frame
+};
+size_t imu_run_device_bytes(int num_scans, const dl_frontend_imu_samples* raw) {
+  const size_t B = (size_t)num_scans;
+  size_t bytes = arena_bytes({B * sizeof(HostImuTerm), B * 128, B * sizeof(FusedOutput), B * sizeof(dl_nav_state)});
+  if (raw) {
+    const size_t ns = (size_t)raw->offsets[num_scans];
+    bytes += arena_bytes({(B + 1) * 4, ns * 8, ns * 24, ns * 24, B * sizeof(dl_nav_state), B * sizeof(dl_preintegration),
+                          B * sizeof(dl_nav_state), B * 4});
+  }
+  return bytes + 1024;
 }
 
 // The batch is processed as `chunks` sub-batches that alternate between two streams, so that
@@ -1645,19 +1648,53 @@ int frontend_upload_small(dl_context* ctx, const dl_frontend_options& o, const F
 int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, float* d_ranges, int64_t in_cap,
                  const void* const* host_ranges, const int64_t* sizes, const float* origins, int num_origins,
                  const double* prev_poses, const double* cur_poses, const double* submap_local_pose, const dl_grid* hi,
-                 const dl_grid* lo, Arena& a, dl_scan_result* d_results, const dl_frontend_imu* imu = nullptr,
-                 FusedOutput** d_fused_out = nullptr) {
+                 const dl_grid* lo, Arena& a, dl_scan_result* d_results, ImuRun* imu_run = nullptr) {
   FrontendBuffers f;
   carve(a, num_scans, in_cap, num_origins, &f);
   // optional IMU coupling: one pre-integration factor per scan, the 15-parameter solve instead of the 6-parameter one
+  const dl_frontend_imu* imu = imu_run ? imu_run->host : nullptr;
+  const dl_frontend_imu_samples* raw = imu_run ? imu_run->samples : nullptr;
   HostImuTerm* d_terms = nullptr;
   double* d_init16 = nullptr;
   FusedOutput* d_fused = nullptr;
-  if (imu) {
+  int32_t* d_imu_ok = nullptr;
+  dl_nav_state* d_states_out = nullptr;
+  if (imu || raw) {
     d_terms = a.take<HostImuTerm>(num_scans);
     d_init16 = a.take<double>((size_t)num_scans * 16);
     d_fused = a.take<FusedOutput>(num_scans);
-    if (d_fused_out) *d_fused_out = d_fused;
+    d_states_out = imu_run->d_states_out ? imu_run->d_states_out : a.take<dl_nav_state>(num_scans);
+    imu_run->d_fused = d_fused;
+    imu_run->d_states = d_states_out;
+  }
+  if (raw) {
+    // Raw samples: pre-integration, prediction, deskew constants, factor and information matrix all on the device; the
+    // only host work is the upload of the samples and of the states at the previous scans.
+    StageScope st(ctx, "imu_preintegrate_predict");
+    const size_t ns = (size_t)raw->offsets[num_scans];
+    int32_t* d_off = a.take<int32_t>(num_scans + 1);
+    double* d_dt = a.take<double>(ns);
+    double* d_acc = a.take<double>(3 * ns);
+    double* d_gyr = a.take<double>(3 * ns);
+    dl_nav_state* d_si = a.take<dl_nav_state>(num_scans);
+    dl_preintegration* d_pre = a.take<dl_preintegration>(num_scans);
+    dl_nav_state* d_pred = a.take<dl_nav_state>(num_scans);
+    d_imu_ok = a.take<int32_t>(num_scans);
+    imu_run->d_predicted = d_pred;
+    DL_TRY(h2d(ctx, d_off, raw->offsets, (size_t)num_scans + 1));
+    DL_TRY(h2d(ctx, d_dt, raw->dt, ns));
+    DL_TRY(h2d(ctx, d_acc, raw->acc, 3 * ns));
+    DL_TRY(h2d(ctx, d_gyr, raw->gyr, 3 * ns));
+    DL_TRY(h2d(ctx, d_si, raw->states_i, (size_t)num_scans));
+    DL_TRY(launch_imu_preintegrate(ctx, num_scans, d_off, d_dt, d_acc, d_gyr, (const double*)d_si + 10, 16, raw->noise, d_pre));
+    ImuPrepareArgs pa{};
+    pa.count = num_scans; pa.preint = d_pre; pa.states_i = d_si; pa.to_submap = inverse(pose_from7(submap_local_pose));
+    for (int k = 0; k < 3; ++k) pa.gravity[k] = raw->gravity[k];
+    pa.imu_weight = raw->imu_weight; pa.scans = f.scans; pa.terms = d_terms; pa.init16 = d_init16; pa.predicted = d_pred;
+    pa.ok = d_imu_ok;
+    DL_TRY(launch_imu_prepare(ctx, pa));
+  }
+  if (imu) {
     std::vector<HostImuTerm> terms(num_scans);
     std::vector<double> init16((size_t)num_scans * 16);
     const Rigidd to_submap = inverse(pose_from7(submap_local_pose));
@@ -1667,11 +1704,12 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
         return ctx->fail(DL_ERR_ARG, "pre-integration covariance is not positive definite");
     DL_TRY(h2d(ctx, d_terms, terms.data(), num_scans));
     DL_TRY(h2d(ctx, d_init16, init16.data(), (size_t)num_scans * 16));
-    DL_CUDA(ctx, cudaMemsetAsync(d_fused, 0, sizeof(FusedOutput) * num_scans, ctx->stream));
     DL_TRY(sync(ctx));  // the staging vectors are pageable and local
   }
+  if (imu || raw) DL_CUDA(ctx, cudaMemsetAsync(d_fused, 0, sizeof(FusedOutput) * num_scans, ctx->stream));
   const int rf = row_floats_of(o);
-  DL_TRY(frontend_upload_small(ctx, o, f, sizes, origins, num_origins, prev_poses, cur_poses, hi, lo));
+  DL_TRY(frontend_upload_small(ctx, o, f, sizes, origins, num_origins, raw ? nullptr : prev_poses, cur_poses, hi, lo,
+                               d_imu_ok));
   const FrontendArgs fa = make_frontend_args(o, f, d_ranges, in_cap, rf);
   DL_TRY(launch_fe_prepare(ctx, fa, f.batch));
   const Rigidd submap = pose_from7(submap_local_pose);
@@ -1790,7 +1828,7 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
       }
       {
         StageScope st(ctx, "nls_solve");
-        if (imu)  // pose part of the initial state comes from problems[].initial_dev like the plain solve's
+        if (imu || raw)  // pose part of the initial state comes from problems[].initial_dev like the plain solve's
           DL_TRY(launch_nls_fused(ctx, to_nls_options(o.ceres_scan_matcher, 2), f.problems + b0, d_terms + b0, d_init16 + 16 * b0, nb,
                                   d_fused + b0));
         else
@@ -1799,8 +1837,9 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
       ResultArgs ra{};
       ra.batch = nb; ra.first_counts = f.n1 + b0; ra.return_counts = f.n2 + b0; ra.miss_counts = f.n3 + b0;
       ra.adaptive_counts = f.countsA + 2 * b0; ra.adaptive_cropped = f.croppedA + 2 * b0; ra.adaptive_passes = f.npassesA + 2 * b0;
-      ra.rtcsm_scores = have_scores ? f.rtcsm_scores + b0 : nullptr; ra.nls = f.nls_out + b0; ra.fused = imu ? d_fused + b0 : nullptr; ra.submap = submap;
+      ra.rtcsm_scores = have_scores ? f.rtcsm_scores + b0 : nullptr; ra.nls = f.nls_out + b0; ra.fused = (imu || raw) ? d_fused + b0 : nullptr; ra.submap = submap;
       ra.results = d_results + b0; ra.error_flag = f.error_flag;
+      ra.imu_ok = d_imu_ok ? d_imu_ok + b0 : nullptr; ra.states_out = d_states_out ? d_states_out + b0 : nullptr;
       DL_TRY(launch_finalize_results(ctx, ra));
       return DL_OK;
     };
@@ -1866,11 +1905,11 @@ int dl_frontend_fetch_results(dl_context* ctx, const dl_scan_result* results_dev
 static int frontend_enqueue_host(dl_context* ctx, const dl_frontend_options* options, int32_t num_scans, const void* const* ranges,
                                  const int64_t* sizes, const float* origins, int32_t num_origins, const double* prev_poses,
                                  const double* predicted_poses, const double* submap_local_pose, const dl_grid* hi,
-                                 const dl_grid* lo, size_t pinned_extra, dl_scan_result** d_results_out,
-                                 const dl_frontend_imu* imu = nullptr, FusedOutput** d_fused_out = nullptr, size_t device_extra = 0) {
+                                 const dl_grid* lo, size_t pinned_extra, dl_scan_result** d_results_out, ImuRun* imu = nullptr) {
   int64_t max_size = 0;
   DL_TRY(check_frontend(ctx, options, num_scans, sizes, hi, lo, &max_size));
-  if (!ranges || !origins || num_origins < 1 || !prev_poses || !predicted_poses || !submap_local_pose) return DL_ERR_ARG;
+  const bool raw = imu && imu->samples;
+  if (!ranges || !origins || num_origins < 1 || (!raw && (!prev_poses || !predicted_poses)) || !submap_local_pose) return DL_ERR_ARG;
   for (int b = 0; b < num_scans; ++b)
     if (sizes[b] > 0 && !ranges[b]) return DL_ERR_ARG;
   if (options->host_scan_stride_rows != 0) {
@@ -1885,6 +1924,7 @@ static int frontend_enqueue_host(dl_context* ctx, const dl_frontend_options* opt
   const int64_t cap = std::max<int64_t>(max_size, 1);
   const size_t extra = options->use_online_correlative_scan_matching
                            ? rtcsm_scratch_bound(options->real_time_correlative_scan_matcher, hi->resolution, false) : 0;
+  const size_t device_extra = imu ? imu_run_device_bytes(num_scans, imu->samples) : 0;
   DL_TRY(ctx->reserve_device(frontend_bytes(num_scans, cap, num_origins, extra) + (size_t)num_scans * cap * 32 + 256 +
                              (size_t)num_scans * sizeof(dl_scan_result) + 256 + device_extra));
   if (pinned_extra) DL_TRY(ctx->reserve_pinned(frontend_small_bytes(num_scans, num_origins) + pinned_extra + 256));
@@ -1892,7 +1932,7 @@ static int frontend_enqueue_host(dl_context* ctx, const dl_frontend_options* opt
   float* d_ranges = a.take<float>((size_t)num_scans * cap * 8);
   *d_results_out = a.take<dl_scan_result>(num_scans);
   return frontend_run(ctx, *options, num_scans, d_ranges, cap, ranges, sizes, origins, num_origins, prev_poses,
-                      predicted_poses, submap_local_pose, hi, lo, a, *d_results_out, imu, d_fused_out);
+                      predicted_poses, submap_local_pose, hi, lo, a, *d_results_out, imu);
 }
 
 int dl_frontend_match_batch(dl_context* ctx, const dl_frontend_options* options, int32_t num_scans,
@@ -1912,6 +1952,14 @@ int dl_frontend_match_batch(dl_context* ctx, const dl_frontend_options* options,
   return sync(ctx);
 }
 
+static int check_imu_options(dl_context* ctx, const dl_frontend_options* options) {
+  if (options && options->ceres_scan_matcher.only_optimize_yaw)
+    return ctx->fail(DL_ERR_ARG, "only_optimize_yaw is not supported by the fused solve");
+  if (options && options->use_online_correlative_scan_matching)
+    return ctx->fail(DL_ERR_ARG, "the correlative pre-match is not combined with the fused solve");
+  return DL_OK;
+}
+
 int dl_frontend_match_batch_imu(dl_context* ctx, const dl_frontend_options* options, const dl_frontend_imu* imu,
                                 int32_t num_scans, const void* const* ranges, const int64_t* sizes, const float* origins,
                                 int32_t num_origins, const double* submap_local_pose, const dl_grid* hi, const dl_grid* lo,
@@ -1921,10 +1969,7 @@ int dl_frontend_match_batch_imu(dl_context* ctx, const dl_frontend_options* opti
   if (num_scans < 0 || !results || !imu->states_i || !imu->predicted_states || !imu->preintegrations || !imu->states_out ||
       !(imu->imu_weight >= 0.))
     return DL_ERR_ARG;
-  if (options && options->ceres_scan_matcher.only_optimize_yaw)
-    return ctx->fail(DL_ERR_ARG, "only_optimize_yaw is not supported by the fused solve");
-  if (options && options->use_online_correlative_scan_matching)
-    return ctx->fail(DL_ERR_ARG, "the correlative pre-match is not combined with the fused solve");
+  DL_TRY(check_imu_options(ctx, options));
   std::vector<double> prev((size_t)num_scans * 7), pred((size_t)num_scans * 7);
   for (int b = 0; b < num_scans; ++b) {
     const dl_nav_state& si = imu->states_i[b];
@@ -1933,17 +1978,86 @@ int dl_frontend_match_batch_imu(dl_context* ctx, const dl_frontend_options* opti
     for (int k = 0; k < 4; ++k) { prev[7 * b + 3 + k] = si.q[k]; pred[7 * b + 3 + k] = sj.q[k]; }
   }
   dl_scan_result* d_results = nullptr;
-  FusedOutput* d_fused = nullptr;
-  const size_t extra = (size_t)num_scans * (sizeof(HostImuTerm) + 128 + sizeof(FusedOutput)) + 1024;
+  ImuRun run;
+  run.host = imu;
   DL_TRY(frontend_enqueue_host(ctx, options, num_scans, ranges, sizes, origins, num_origins, prev.data(), pred.data(),
-                               submap_local_pose, hi, lo, 0, &d_results, imu, &d_fused, extra));
-  std::vector<FusedOutput> fused(num_scans);
+                               submap_local_pose, hi, lo, 0, &d_results, &run));
   DL_TRY(d2h(ctx, results, d_results, num_scans));
-  DL_TRY(d2h(ctx, fused.data(), d_fused, num_scans));
-  DL_TRY(sync(ctx));
-  const Rigidd submap = pose_from7(submap_local_pose);
-  for (int b = 0; b < num_scans; ++b) state_to_local(submap, fused[b].state, &imu->states_out[b]);
+  DL_TRY(d2h(ctx, imu->states_out, run.d_states, num_scans));
+  return sync(ctx);
+}
+
+static int check_imu_samples(dl_context* ctx, const dl_frontend_options* options, const dl_frontend_imu_samples* imu, int num_scans) {
+  if (!imu || num_scans < 0) return DL_ERR_ARG;
+  if (num_scans == 0) return DL_OK;
+  if (!imu->states_i || !imu->offsets || !(imu->imu_weight >= 0.)) return DL_ERR_ARG;
+  if (imu->offsets[0] != 0) return ctx->fail(DL_ERR_ARG, "offsets[0] must be 0");
+  for (int k = 0; k < num_scans; ++k)
+    if (imu->offsets[k + 1] < imu->offsets[k]) return ctx->fail(DL_ERR_ARG, "offsets must be non-decreasing");
+  if (imu->offsets[num_scans] > 0 && (!imu->dt || !imu->acc || !imu->gyr)) return DL_ERR_ARG;
+  return check_imu_options(ctx, options);
+}
+
+int dl_frontend_match_batch_imu_samples(dl_context* ctx, const dl_frontend_options* options, const dl_frontend_imu_samples* imu,
+                                        int32_t num_scans, const void* const* ranges, const int64_t* sizes, const float* origins,
+                                        int32_t num_origins, const double* submap_local_pose, const dl_grid* hi,
+                                        const dl_grid* lo, dl_scan_result* results, dl_nav_state* states_out,
+                                        dl_nav_state* predicted_states_out) {
+  if (!ctx) return DL_ERR_ARG;
+  DL_TRY(check_imu_samples(ctx, options, imu, num_scans));
+  if (num_scans == 0) return DL_OK;
+  if (!results || !states_out) return DL_ERR_ARG;
+  dl_scan_result* d_results = nullptr;
+  ImuRun run;
+  run.samples = imu;
+  DL_TRY(frontend_enqueue_host(ctx, options, num_scans, ranges, sizes, origins, num_origins, nullptr, nullptr,
+                               submap_local_pose, hi, lo, 0, &d_results, &run));
+  DL_TRY(d2h(ctx, results, d_results, num_scans));
+  DL_TRY(d2h(ctx, states_out, run.d_states, num_scans));
+  if (predicted_states_out) DL_TRY(d2h(ctx, predicted_states_out, run.d_predicted, num_scans));
+  return sync(ctx);
+}
+
+int dl_frontend_match_batch_imu_samples_dev(dl_context* ctx, const dl_frontend_options* options,
+                                            const dl_frontend_imu_samples* imu, int32_t num_scans, const void* ranges_dev,
+                                            int64_t cap_rows, const int64_t* sizes, const float* origins, int32_t num_origins,
+                                            const double* submap_local_pose, const dl_grid* hi, const dl_grid* lo,
+                                            dl_scan_result* results_dev, dl_nav_state* states_out_dev) {
+  if (!ctx) return DL_ERR_ARG;
+  DL_TRY(check_imu_samples(ctx, options, imu, num_scans));
+  int64_t max_size = 0;
+  DL_TRY(check_frontend(ctx, options, num_scans, sizes, hi, lo, &max_size));
+  if (num_scans == 0) return DL_OK;
+  if (!ranges_dev || !origins || num_origins < 1 || !submap_local_pose || !results_dev || !states_out_dev || cap_rows < max_size ||
+      cap_rows < 1)
+    return DL_ERR_ARG;
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  DL_TRY(ctx->reserve_device(frontend_bytes(num_scans, cap_rows, num_origins, 0) + imu_run_device_bytes(num_scans, imu)));
+  Arena a(ctx->d_scratch);
+  ImuRun run;
+  run.samples = imu;
+  run.d_states_out = states_out_dev;
+  return frontend_run(ctx, *options, num_scans, (float*)ranges_dev, cap_rows, nullptr, sizes, origins, num_origins, nullptr,
+                      nullptr, submap_local_pose, hi, lo, a, results_dev, &run);
+}
+
+// Tail of a submit: the results (and, with the IMU, the estimated states) go to pinned staging behind the batch.
+static int submit_finish(dl_context* ctx, int num_scans, int num_origins, const dl_scan_result* d_results,
+                         const dl_nav_state* d_states) {
+  const size_t result_bytes = (size_t)num_scans * sizeof(dl_scan_result);
+  ctx->results_staging_offset = (frontend_small_bytes(num_scans, num_origins) + 255) & ~size_t(255);
+  char* dst = (char*)ctx->h_pinned + ctx->results_staging_offset;
+  DL_CUDA(ctx, cudaMemcpyAsync(dst, d_results, result_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (d_states)
+    DL_CUDA(ctx, cudaMemcpyAsync(dst + ((result_bytes + 255) & ~size_t(255)), d_states, (size_t)num_scans * sizeof(dl_nav_state),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+  DL_CUDA(ctx, cudaEventRecord(ctx->batch_done, ctx->stream));
+  ctx->in_flight = num_scans;
+  ctx->in_flight_states = d_states != nullptr;
   return DL_OK;
+}
+static size_t submit_pinned_bytes(int num_scans) {
+  return (((size_t)num_scans * sizeof(dl_scan_result) + 255) & ~size_t(255)) + (size_t)num_scans * sizeof(dl_nav_state) + 256;
 }
 
 int dl_frontend_submit(dl_context* ctx, const dl_frontend_options* options, int32_t num_scans, const void* const* ranges,
@@ -1952,27 +2066,46 @@ int dl_frontend_submit(dl_context* ctx, const dl_frontend_options* options, int3
   if (!ctx || num_scans < 1) return DL_ERR_ARG;
   if (ctx->in_flight) return ctx->fail(DL_ERR_ARG, "a submitted batch is already in flight on this context");
   dl_scan_result* d_results = nullptr;
-  const size_t result_bytes = (size_t)num_scans * sizeof(dl_scan_result);
   DL_TRY(frontend_enqueue_host(ctx, options, num_scans, ranges, sizes, origins, num_origins, prev_poses, predicted_poses,
-                               submap_local_pose, hi, lo, result_bytes, &d_results));
-  ctx->results_staging_offset = (frontend_small_bytes(num_scans, num_origins) + 255) & ~size_t(255);
-  DL_CUDA(ctx, cudaMemcpyAsync((char*)ctx->h_pinned + ctx->results_staging_offset, d_results, result_bytes,
-                               cudaMemcpyDeviceToHost, ctx->stream));
-  DL_CUDA(ctx, cudaEventRecord(ctx->batch_done, ctx->stream));
-  ctx->in_flight = num_scans;
-  return DL_OK;
+                               submap_local_pose, hi, lo, submit_pinned_bytes(num_scans), &d_results));
+  return submit_finish(ctx, num_scans, num_origins, d_results, nullptr);
 }
 
-int dl_frontend_collect(dl_context* ctx, int32_t num_scans, dl_scan_result* results) {
+int dl_frontend_submit_imu_samples(dl_context* ctx, const dl_frontend_options* options, const dl_frontend_imu_samples* imu,
+                                   int32_t num_scans, const void* const* ranges, const int64_t* sizes, const float* origins,
+                                   int32_t num_origins, const double* submap_local_pose, const dl_grid* hi, const dl_grid* lo) {
+  if (!ctx || num_scans < 1) return DL_ERR_ARG;
+  if (ctx->in_flight) return ctx->fail(DL_ERR_ARG, "a submitted batch is already in flight on this context");
+  DL_TRY(check_imu_samples(ctx, options, imu, num_scans));
+  dl_scan_result* d_results = nullptr;
+  ImuRun run;
+  run.samples = imu;
+  DL_TRY(frontend_enqueue_host(ctx, options, num_scans, ranges, sizes, origins, num_origins, nullptr, nullptr, submap_local_pose,
+                               hi, lo, submit_pinned_bytes(num_scans), &d_results, &run));
+  return submit_finish(ctx, num_scans, num_origins, d_results, run.d_states);
+}
+
+static int collect_common(dl_context* ctx, int32_t num_scans, dl_scan_result* results, dl_nav_state* states_out) {
   if (!ctx || !results) return DL_ERR_ARG;
   if (!ctx->in_flight) return ctx->fail(DL_ERR_ARG, "no submitted batch on this context");
   if (num_scans != ctx->in_flight) return ctx->fail(DL_ERR_ARG, "num_scans differs from the submitted batch");
+  if (states_out && !ctx->in_flight_states) return ctx->fail(DL_ERR_ARG, "the submitted batch carries no IMU states");
   DL_CUDA(ctx, cudaSetDevice(ctx->device));
   const cudaError_t e = cudaEventSynchronize(ctx->batch_done);
   ctx->in_flight = 0;
   if (e != cudaSuccess) return ctx->cuda_fail(e, "dl_frontend_collect");
-  std::memcpy(results, (const char*)ctx->h_pinned + ctx->results_staging_offset, (size_t)num_scans * sizeof(dl_scan_result));
+  const size_t result_bytes = (size_t)num_scans * sizeof(dl_scan_result);
+  const char* src = (const char*)ctx->h_pinned + ctx->results_staging_offset;
+  std::memcpy(results, src, result_bytes);
+  if (states_out) std::memcpy(states_out, src + ((result_bytes + 255) & ~size_t(255)), (size_t)num_scans * sizeof(dl_nav_state));
   return DL_OK;
+}
+int dl_frontend_collect(dl_context* ctx, int32_t num_scans, dl_scan_result* results) {
+  return collect_common(ctx, num_scans, results, nullptr);
+}
+int dl_frontend_collect_imu(dl_context* ctx, int32_t num_scans, dl_scan_result* results, dl_nav_state* states_out) {
+  if (!states_out) return DL_ERR_ARG;
+  return collect_common(ctx, num_scans, results, states_out);
 }
 
 namespace {

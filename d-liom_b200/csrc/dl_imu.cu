@@ -7,6 +7,7 @@
 // (b) inside a step: the three 15x15 products F*J, F*P*F^T, V*N*V^T are spread over the 32 lanes. The state lives in
 // shared memory (4 warps per CTA, 9.6 KB each). Row/column order: delta_p, delta_theta, delta_v, b_a, b_g.
 #include "dl_internal.cuh"
+#include "dl_pipeline.cuh"
 
 namespace dl {
 namespace {
@@ -37,8 +38,8 @@ __device__ __forceinline__ void mul33(const double A[3][3], const double B[3][3]
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) imu_preintegrate_kernel(
     int count, const int32_t* __restrict__ offsets /* count + 1 */, const double* __restrict__ dts,
-    const double* __restrict__ accs, const double* __restrict__ gyrs, const double* __restrict__ biases /* 6 per scan */,
-    double acc_n, double gyr_n, double acc_w, double gyr_w, dl_preintegration* __restrict__ out) {
+    const double* __restrict__ accs, const double* __restrict__ gyrs,
+    const double* __restrict__ biases /* ba, bg of scan k at biases + k * bias_stride */, int bias_stride, double acc_n, double gyr_n, double acc_w, double gyr_w, dl_preintegration* __restrict__ out) {
   __shared__ WarpState states[kWarpsPerBlock];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int scan = blockIdx.x * kWarpsPerBlock + warp;
@@ -48,8 +49,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) imu_preintegrate_kernel(
     st.J[e] = (e / 15 == e % 15) ? 1.0 : 0.0;
     st.P[e] = 0.0;
   }
-  const Vec3d ba{biases[6 * scan], biases[6 * scan + 1], biases[6 * scan + 2]};
-  const Vec3d bg{biases[6 * scan + 3], biases[6 * scan + 4], biases[6 * scan + 5]};
+  const double* bias = biases + (size_t)bias_stride * scan;
+  const Vec3d ba{bias[0], bias[1], bias[2]};
+  const Vec3d bg{bias[3], bias[4], bias[5]};
   Vec3d dp{0, 0, 0}, dv{0, 0, 0};
   Quatd dq{1, 0, 0, 0};
   double sum_dt = 0;
@@ -166,13 +168,112 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) imu_preintegrate_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Everything between the pre-integration and the fused solve, on the device, so that a batch of scans with their raw
+// IMU samples needs no host round trip: state prediction (dl_imu_predict's arithmetic = the front end's
+// pose prediction, LTB:188-199), the deskew constants of LTB:426-428, the pre-integration factor moved into the submap
+// frame, and its information matrix W = weight^2 * Sigma^-1 (Sigma = L L^T, W = L^-T L^-1; the same operation order as the
+// host path in dl_api.cu, so both produce the same bits). One warp per scan; lane i owns row / column i of the 15x15 work.
+struct PrepareShared {
+  double L[15][15], Li[15][15];
+};
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) imu_prepare_kernel(ImuPrepareArgs a) {
+  __shared__ PrepareShared shared[kWarpsPerBlock];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kWarpsPerBlock + warp;
+  if (b >= a.count) return;
+  PrepareShared& sh = shared[warp];
+  const dl_preintegration& m = a.preint[b];
+  const dl_nav_state& si = a.states_i[b];
+  ImuTerm& t = a.terms[b];
+  if (lane == 0) {
+    // prediction at the end of the interval
+    const double T = m.sum_dt;
+    const Quatd qi{si.q[0], si.q[1], si.q[2], si.q[3]};
+    const Vec3d G{a.gravity[0], a.gravity[1], a.gravity[2]};
+    const Vec3d pi{si.p[0], si.p[1], si.p[2]}, vi{si.v[0], si.v[1], si.v[2]};
+    const Vec3d pj = add(sub(add(pi, mul(T, vi)), mul(0.5 * T * T, G)), rotate(qi, Vec3d{m.delta_p[0], m.delta_p[1], m.delta_p[2]}));
+    const Vec3d vj = add(sub(vi, mul(T, G)), rotate(qi, Vec3d{m.delta_v[0], m.delta_v[1], m.delta_v[2]}));
+    const Quatd qj = qnormalized(qmul(qi, Quatd{m.delta_q[0], m.delta_q[1], m.delta_q[2], m.delta_q[3]}));
+    if (a.predicted) {
+      dl_nav_state& o = a.predicted[b];
+      o = si;
+      o.p[0] = pj.x; o.p[1] = pj.y; o.p[2] = pj.z;
+      o.v[0] = vj.x; o.v[1] = vj.y; o.v[2] = vj.z;
+      o.q[0] = qj.w; o.q[1] = qj.x; o.q[2] = qj.y; o.q[3] = qj.z;
+    }
+    const Rigidd prev{pi, qi}, cur{pj, qj};
+    a.scans[b] = make_scan_constants(prev, cur);
+    // the factor in the submap frame (the grids live there and the solve is frame-invariant)
+    const Rigidd pose_i = compose(a.to_submap, prev), pose_j = compose(a.to_submap, cur);
+    const Vec3d wi = rotate(a.to_submap.q, vi), wj = rotate(a.to_submap.q, vj), Gs = rotate(a.to_submap.q, G);
+    t.pi[0] = pose_i.t.x; t.pi[1] = pose_i.t.y; t.pi[2] = pose_i.t.z;
+    t.qi[0] = pose_i.q.w; t.qi[1] = pose_i.q.x; t.qi[2] = pose_i.q.y; t.qi[3] = pose_i.q.z;
+    t.vi[0] = wi.x; t.vi[1] = wi.y; t.vi[2] = wi.z;
+    for (int k = 0; k < 3; ++k) {
+      t.bai[k] = si.ba[k]; t.bgi[k] = si.bg[k];
+      t.dp[k] = m.delta_p[k]; t.dv[k] = m.delta_v[k];
+    }
+    for (int k = 0; k < 4; ++k) t.dq[k] = m.delta_q[k];
+    t.G[0] = Gs.x; t.G[1] = Gs.y; t.G[2] = Gs.z;
+    t.sum_dt = m.sum_dt;
+    double* x = a.init16 + 16 * (size_t)b;
+    pose_to7(pose_j, x);
+    x[7] = wj.x; x[8] = wj.y; x[9] = wj.z;
+    for (int k = 0; k < 3; ++k) { x[10 + k] = si.ba[k]; x[13 + k] = si.bg[k]; }
+  }
+  // Cholesky of the covariance, column by column (lane = row)
+  const bool row = lane < 15;
+  bool pd = true;
+  for (int j = 0; j < 15; ++j) {
+    double s = 0.0;
+    if (row && lane >= j) {
+      s = m.covariance[lane * 15 + j];
+      for (int k = 0; k < j; ++k) s -= sh.L[lane][k] * sh.L[j][k];
+    }
+    const double pivot = __shfl_sync(0xffffffffu, s, j);
+    if (!(pivot > 0)) { pd = false; break; }
+    const double d = sqrt(pivot);
+    if (row && lane >= j) sh.L[lane][j] = lane == j ? d : s / d;
+    __syncwarp();
+  }
+  if (lane == 0) a.ok[b] = pd ? 1 : 0;
+  if (!pd) return;
+  // L^-1 (lower): lane c solves column c
+  if (row) {
+    const int c = lane;
+    for (int i = 0; i < c; ++i) sh.Li[i][c] = 0.0;
+    for (int i = c; i < 15; ++i) {
+      double s = i == c ? 1.0 : 0.0;
+      for (int k = c; k < i; ++k) s -= sh.L[i][k] * sh.Li[k][c];
+      sh.Li[i][c] = s / sh.L[i][i];
+    }
+  }
+  __syncwarp();
+  for (int e = lane; e < 225; e += 32) {
+    const int r = e / 15, c = e % 15;
+    double s = 0;
+    for (int k = (r > c ? r : c); k < 15; ++k) s += sh.Li[k][r] * sh.Li[k][c];
+    t.W[e] = a.imu_weight * a.imu_weight * s;
+  }
+}
+
 }  // namespace
 
+int launch_imu_prepare(dl_context* ctx, const ImuPrepareArgs& a) {
+  if (a.count <= 0) return DL_OK;
+  imu_prepare_kernel<<<(a.count + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, ctx->stream>>>(a);
+  DL_LAUNCH_CHECK(ctx, "imu_prepare_kernel");
+  return DL_OK;
+}
+
 int launch_imu_preintegrate(dl_context* ctx, int count, const int32_t* offsets, const double* dts, const double* accs,
-                            const double* gyrs, const double* biases, const dl_imu_noise& noise, dl_preintegration* out) {
+                            const double* gyrs, const double* biases, int bias_stride, const dl_imu_noise& noise,
+                            dl_preintegration* out) {
   if (count <= 0) return DL_OK;
   imu_preintegrate_kernel<<<(count + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, ctx->stream>>>(
-      count, offsets, dts, accs, gyrs, biases, noise.acc_n, noise.gyr_n, noise.acc_w, noise.gyr_w, out);
+      count, offsets, dts, accs, gyrs, biases, bias_stride, noise.acc_n, noise.gyr_n, noise.acc_w, noise.gyr_w, out);
   DL_LAUNCH_CHECK(ctx, "imu_preintegrate_kernel");
   return DL_OK;
 }

@@ -208,11 +208,20 @@ __global__ void finalize_results_kernel(ResultArgs a) {
   // the reference drops the scan when any of the three clouds is empty (LTB:497-500, :510-513, :531-534)
   r.ok = (a.return_counts[b] > 0 && n_hi > 0 && n_lo > 0) ? 1 : 0;
   if (a.error_flag && *a.error_flag) r.ok = -1;  // a point fell outside +-2^20 voxels: results are not valid
+  if (a.imu_ok && a.imu_ok[b] == 0) r.ok = -2;   // no IMU factor (no samples / covariance not positive definite): no solve ran
   const double* pose = a.fused ? a.fused[b].state : a.nls[b].pose;
   r.summary = a.fused ? a.fused[b].summary : a.nls[b].summary;
   for (int i = 0; i < 7; ++i) r.pose_observation_in_submap[i] = pose[i];
   const Rigidd est = compose(a.submap, pose_from7(pose));  // LTB:553-554
   pose_to7(est, r.pose_estimate_local);
+  if (a.fused && a.states_out) {  // solver state (submap frame) -> dl_nav_state in the local frame
+    dl_nav_state& o = a.states_out[b];
+    const Vec3d v = rotate(a.submap.q, Vec3d{pose[7], pose[8], pose[9]});
+    o.p[0] = est.t.x; o.p[1] = est.t.y; o.p[2] = est.t.z;
+    o.q[0] = est.q.w; o.q[1] = est.q.x; o.q[2] = est.q.y; o.q[3] = est.q.z;
+    o.v[0] = v.x; o.v[1] = v.y; o.v[2] = v.z;
+    for (int k = 0; k < 3; ++k) { o.ba[k] = pose[10 + k]; o.bg[k] = pose[13 + k]; }
+  }
 }
 
 }  // namespace

@@ -54,6 +54,7 @@ struct dl_context {
   cudaEvent_t batch_done = nullptr;     // dl_frontend_submit: everything of the batch in flight, incl. the result download
   uint8_t* d_fcsm_lut = nullptr;        // loop-closure search: cell value -> 8-bit precomputation value (dl_fcsm.cu), built on first use
   int in_flight = 0;                    // scans of the submitted, not yet collected batch
+  bool in_flight_states = false;        // ... and whether it also stages the estimated IMU states
   size_t results_staging_offset = 0;    // where in h_pinned the in-flight batch's results land
   std::string error;
   int64_t launches = 0;
@@ -233,14 +234,24 @@ struct FusedOutput {
   double state[16];  // p(3) q(4 wxyz) v(3) ba(3) bg(3)
   dl_solve_summary summary;
 };
-// Host-side mirror of the device ImuTerm (dl_nls.cu): 3+4+3+3+3 + 3+4+3 + 3 + 1 + 225 doubles.
+// IMU term of the fused solve in the SUBMAP frame (built by dl_api.cu on the host or by imu_prepare_kernel on the device):
+// state i (fixed), the pre-integrated deltas, gravity, and W = weight^2 * Sigma^-1 (row-major 15x15, order p, theta, v, ba, bg).
+struct ImuTerm {
+  double pi[3], qi[4], vi[3], bai[3], bgi[3];
+  double dp[3], dq[4], dv[3];
+  double G[3];
+  double sum_dt;
+  double W[225];
+};
 constexpr int kImuTermDoubles = 16 + 10 + 3 + 1 + 225;
-int launch_nls_fused(dl_context* ctx, const NlsOptions& opt, const NlsProblem* problems_dev, const void* imu_terms_dev,
+static_assert(sizeof(ImuTerm) == kImuTermDoubles * sizeof(double), "ImuTerm layout");
+int launch_nls_fused(dl_context* ctx, const NlsOptions& opt, const NlsProblem* problems_dev, const ImuTerm* imu_terms_dev,
                      const double* initial16_dev, int count, FusedOutput* out_dev);
 int launch_nls_normal_equations(dl_context* ctx, const NlsOptions& opt, const NlsProblem* problems_dev,
                                 const double* at_pose_dev, double* out28_dev);
 int launch_imu_preintegrate(dl_context* ctx, int count, const int32_t* offsets, const double* dts, const double* accs,
-                            const double* gyrs, const double* biases, const dl_imu_noise& noise, dl_preintegration* out);
+                            const double* gyrs, const double* biases, int bias_stride, const dl_imu_noise& noise,
+                            dl_preintegration* out);
 struct DecodeArgs {  // one sensor_msgs/PointCloud2 message (dl_decode.cu)
   const uint8_t* data;
   int64_t n;

@@ -11,7 +11,8 @@
 // one thread, or 8 at a time in the loop-closure thread pool). Each evaluation is a single fused pass
 //   transform (fp64) -> float cell selection -> 8 voxel reads -> smoothstep interpolation -> analytic gradient ->
 //   chain rule to the 6 local parameters -> J^T J (21) / J^T r (6) / cost (1) accumulation
-// reduced with warp shuffles in a fixed order (bit-reproducible run to run). The N x 6 Jacobian the reference
+// reduced with a butterfly reduce-scatter over the warp (31 shuffles for all 28 quantities) and then over the warps in
+// index order (fixed order: bit-reproducible run to run). The N x 6 Jacobian the reference
 // materialises (N x 7 doubles, then QR) never exists: the normal equations carry everything the LM loop needs —
 // Jacobi scaling, the LM diagonal, the step (6x6 Cholesky of S J^T J S + D^2, algebraically the stacked QR
 // solution), the model cost change and the projected gradient. Candidate points are evaluated speculatively
@@ -28,11 +29,11 @@
 namespace dl {
 namespace {
 
-// Threads per problem. The kernels are written for any multiple of 32 up to kBlock: the evaluation pass strides by
-// blockDim.x and the LM state machine runs on thread 0 either way. A scan-matching problem has only a few hundred points
-// after the adaptive filters; smaller CTAs would let more problems share an SM (registers per problem = 170 x threads),
-// but the evaluation pass (8 dependent-load tree walks per point) then serialises inside each thread and the whole
-// solve gets slower: see nls_block_threads() for the measurement.
+// Threads per problem. The kernels are written for any multiple of 32 up to kBlock: the evaluation pass strides by the
+// number of point threads, WARP 0 drives the LM state machine between passes (lane i owns row i of the 6x6 / 15x15 systems,
+// all matrices in shared memory — round 1 ran it on thread 0 with the matrices in local memory: 7.5 KB of stack for the
+// fused kernel, ~2/3 of the solve's time), and with the IMU term the last warp evaluates that term while the others
+// walk the points. A scan-matching problem has only a few hundred points after the adaptive filters.
 constexpr int kBlock = 256;
 constexpr int kWarps = kBlock / 32;
 constexpr int kRed = 28;  // cost, g[6], H upper triangle [21]
@@ -145,17 +146,35 @@ __device__ __forceinline__ void plus(const double* x, const double* delta, bool 
 }
 
 struct Shared {
-  double red[kWarps][kRed];
-  double acc[kRed];      // block total of the last evaluation
-  double x[7];           // evaluation point broadcast
+  double red[kWarps][32];  // per-warp partial sums of the 28 reduced quantities (lane l holds quantity l)
+  double acc[32];          // block total of the last evaluation: cost*2, J^T r (6), J^T J upper triangle (21)
+  double x[7];             // evaluation point broadcast
   int n[DL_MAX_PAIRS];
   double scaling[DL_MAX_PAIRS];
   int stop;
 };
 
-// Fused evaluation pass at sh.x: leaves cost*2, J^T r and J^T J (local parameterisation) in sh.acc.
-__device__ void evaluate(const NlsOptions& opt, const NlsProblem& prob, Shared& sh, const double* target_q_inv,
-                         const double* target_t) {
+// Butterfly reduce-scatter of 32 per-lane values over the warp: 31 double shuffles instead of the 5 x 28 of a plain
+// xor tree per quantity. On return lane l holds the warp total of v[l] in v[0]. Fixed order -> run-to-run reproducible.
+__device__ __forceinline__ double warp_reduce_scatter32(double (&v)[32], int lane) {
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const double send = up ? v[i] : v[i + h];
+      const double keep = up ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  return v[0];
+}
+
+// Point pass of one evaluation at sh.x: every participating thread accumulates cost*2, J^T r and J^T J (local
+// parameterisation) over its points; each warp leaves its partial sums in sh.red[warp][0..27].
+// Threads [0, point_threads) take part (whole warps); the caller synchronises the block afterwards.
+__device__ __forceinline__ void evaluate_points(const NlsOptions& opt, const NlsProblem& prob, Shared& sh, int point_threads) {
+  if ((int)threadIdx.x >= point_threads) return;
   double x[7];
 #pragma unroll
   for (int i = 0; i < 7; ++i) x[i] = sh.x[i];
@@ -163,16 +182,16 @@ __device__ void evaluate(const NlsOptions& opt, const NlsProblem& prob, Shared& 
   plus_jacobian(x, opt.only_yaw != 0, P);
   const Quatd q{x[3], x[4], x[5], x[6]};
   const Vec3d a{x[4], x[5], x[6]};
-  double acc[kRed];
+  double acc[32];
 #pragma unroll
-  for (int i = 0; i < kRed; ++i) acc[i] = 0.0;
+  for (int i = 0; i < 32; ++i) acc[i] = 0.0;
 
   for (int k = 0; k < opt.num_pairs; ++k) {
     const int n = sh.n[k];
     const double s = sh.scaling[k];
     const float* __restrict__ cloud = prob.cloud[k];
     const GridView g = prob.grid[k];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = threadIdx.x; i < n; i += point_threads) {
       const Vec3d v{(double)cloud[3 * i], (double)cloud[3 * i + 1], (double)cloud[3 * i + 2]};
       const Vec3d w = add(rotate(q, v), Vec3d{x[0], x[1], x[2]});
       double m, gx, gy, gz;
@@ -207,54 +226,64 @@ __device__ void evaluate(const NlsOptions& opt, const NlsProblem& prob, Shared& 
         for (int d = c; d < 6; ++d) acc[t++] += J[c] * J[d];
     }
   }
-  // fixed-order reduction: lanes (xor tree), then warps in index order
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int i = 0; i < kRed; ++i) {
-    double v = acc[i];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    if (lane == 0) sh.red[warp][i] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < kRed) {
-    double v = 0.0;
-    const int warps = blockDim.x >> 5;
-    for (int w = 0; w < warps; ++w) v += sh.red[w][threadIdx.x];
-    sh.acc[threadIdx.x] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    // the two 3-residual blocks (translation_delta_cost_functor_3d.h:38-44, rotation_delta_cost_functor_3d.h:42-53)
-    if (opt.trans_weight > 0.) {
-      const double s = opt.trans_weight;
+  sh.red[warp][lane] = warp_reduce_scatter32(acc, lane);
+}
+
+// Warp 0, after the block barrier that follows evaluate_points: warps are summed in index order, then the two
+// 3-residual blocks (translation_delta_cost_functor_3d.h:38-44, rotation_delta_cost_functor_3d.h:42-53) are added.
+// Leaves the totals in sh.acc (visible to warp 0 after the trailing __syncwarp).
+__device__ __forceinline__ void finish_points(const NlsOptions& opt, Shared& sh, int point_warps, const double* target_q_inv,
+                                              const double* target_t, int lane) {
+  double v = 0.0;
+  for (int w = 0; w < point_warps; ++w) v += sh.red[w][lane];
+  const double* x = sh.x;
+  if (opt.trans_weight > 0.) {
+    const double s = opt.trans_weight;
+    if (lane == 0) {
+      double c2 = 0;
       for (int c = 0; c < 3; ++c) {
         const double r = s * (x[c] - target_t[c]);
-        sh.acc[0] += r * r;
-        sh.acc[1 + c] += s * r;
-        sh.acc[7 + tri(c, c)] += s * s;
+        c2 += r * r;
       }
-    }
-    if (opt.rot_weight > 0.) {
-      const double s = opt.rot_weight;
-      const double zw = target_q_inv[0], zx = target_q_inv[1], zy = target_q_inv[2], zz = target_q_inv[3];
-      const double* w = x + 3;
-      const double d[3] = {zw * w[1] + zx * w[0] + zy * w[3] - zz * w[2], zw * w[2] - zx * w[3] + zy * w[0] + zz * w[1],
-                           zw * w[3] + zx * w[2] - zy * w[1] + zz * w[0]};
-      const double dd[3][4] = {{zx, zw, -zz, zy}, {zy, zz, zw, -zx}, {zz, -zy, zx, zw}};
-      for (int c = 0; c < 3; ++c) {
-        const double r = s * d[c];
-        double J[6] = {0, 0, 0, 0, 0, 0};
-        for (int j = 0; j < 3; ++j)
-          J[3 + j] = s * (dd[c][0] * P[0][j] + dd[c][1] * P[1][j] + dd[c][2] * P[2][j] + dd[c][3] * P[3][j]);
-        sh.acc[0] += r * r;
-        for (int e = 3; e < 6; ++e) sh.acc[1 + e] += J[e] * r;
-        for (int e = 3; e < 6; ++e)
-          for (int f = e; f < 6; ++f) sh.acc[7 + tri(e, f)] += J[e] * J[f];
-      }
+      v += c2;
+    } else if (lane >= 1 && lane <= 3) {
+      v += s * (s * (x[lane - 1] - target_t[lane - 1]));
+    } else if (lane == 7 + tri(0, 0) || lane == 7 + tri(1, 1) || lane == 7 + tri(2, 2)) {
+      v += s * s;
     }
   }
-  __syncthreads();
+  if (opt.rot_weight > 0.) {
+    const double s = opt.rot_weight;
+    double P[4][3];
+    plus_jacobian(x, opt.only_yaw != 0, P);
+    const double zw = target_q_inv[0], zx = target_q_inv[1], zy = target_q_inv[2], zz = target_q_inv[3];
+    const double* w = x + 3;
+    const double d[3] = {zw * w[1] + zx * w[0] + zy * w[3] - zz * w[2], zw * w[2] - zx * w[3] + zy * w[0] + zz * w[1],
+                         zw * w[3] + zx * w[2] - zy * w[1] + zz * w[0]};
+    const double dd[3][4] = {{zx, zw, -zz, zy}, {zy, zz, zw, -zx}, {zz, -zy, zx, zw}};
+    double Jr[3][3];  // residual c, rotation parameter j
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        Jr[c][j] = s * (dd[c][0] * P[0][j] + dd[c][1] * P[1][j] + dd[c][2] * P[2][j] + dd[c][3] * P[3][j]);
+    if (lane == 0) {
+      for (int c = 0; c < 3; ++c) v += (s * d[c]) * (s * d[c]);
+    } else if (lane >= 4 && lane <= 6) {
+      const int e = lane - 4;
+      for (int c = 0; c < 3; ++c) v += Jr[c][e] * (s * d[c]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 3; ++e)
+#pragma unroll
+        for (int f = e; f < 3; ++f)
+          if (lane == 7 + tri(3 + e, 3 + f))
+            for (int c = 0; c < 3; ++c) v += Jr[c][e] * Jr[c][f];
+    }
+  }
+  sh.acc[lane] = v;
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -263,147 +292,107 @@ __device__ void evaluate(const NlsOptions& opt, const NlsProblem& prob, Shared& 
 //   N = 15  the fused solve: pose + velocity + accelerometer / gyroscope biases of state j (ambient size 16), with
 //           the IMU pre-integration residual of integration_base.h:267-301 added to the normal equations.
 template <int N>
-struct EvalT {
-  double cost;
-  double g[N];
-  double H[N][N];
-};
-template <int N>
 struct Dims {
   static constexpr int ambient = N == 15 ? 16 : 7;
 };
 
-// IMU term of the fused solve, prepared on the host in the SUBMAP frame (dl_api.cu): state i (fixed), the
-// pre-integrated deltas, gravity, and W = weight^2 * Sigma^-1 (row-major 15x15, order p, theta, v, ba, bg).
-struct ImuTerm {
-  double pi[3], qi[4], vi[3], bai[3], bgi[3];
-  double dp[3], dq[4], dv[3];
-  double G[3];
-  double sum_dt;
-  double W[225];
-};
+// The Jacobian of the residual w.r.t. the local parameters of state j is block diagonal: R_i^T for p and v, a 3x3
+// block that depends on q_j for theta, identity for the biases. Only the three 3x3 blocks are stored.
 struct ImuShared {
+  double W[225];
   double r[15], Wr[15];
-  double J[15][15], WJ[15][15];
+  double B[3][3][3];  // B[blk][row][col]: J[3 blk + row][3 blk + col], blk = 0 (p), 1 (theta), 2 (v)
+  double WJ[15][15];
   double H[15][15], g[15], cost2;
 };
 
-// Residual (15) and Jacobian (15 x 15) w.r.t. the local parameters of state j, thread 0 only.
-__device__ void imu_residual_jacobian(const ImuTerm& m, const double* x /*16*/, ImuShared& is) {
-  const double T = m.sum_dt;
-  const Quatd qi_inv{m.qi[0], -m.qi[1], -m.qi[2], -m.qi[3]};
-  const Vec3d G{m.G[0], m.G[1], m.G[2]};
-  const Vec3d pj{x[0], x[1], x[2]}, vj{x[7], x[8], x[9]};
-  const Vec3d pi{m.pi[0], m.pi[1], m.pi[2]}, vi{m.vi[0], m.vi[1], m.vi[2]};
-  const Quatd qj{x[3], x[4], x[5], x[6]};
-  const Vec3d rp = sub(rotate(qi_inv, sub(sub(add(mul(0.5 * T * T, G), pj), pi), mul(T, vi))), Vec3d{m.dp[0], m.dp[1], m.dp[2]});
-  const Quatd A = qmul(Quatd{m.dq[0], -m.dq[1], -m.dq[2], -m.dq[3]}, qi_inv);
-  const Quatd e = qmul(A, qj);
-  const Vec3d rv = sub(rotate(qi_inv, sub(add(mul(T, G), vj), vi)), Vec3d{m.dv[0], m.dv[1], m.dv[2]});
-  is.r[0] = rp.x; is.r[1] = rp.y; is.r[2] = rp.z;
-  is.r[3] = 2 * e.x; is.r[4] = 2 * e.y; is.r[5] = 2 * e.z;
-  is.r[6] = rv.x; is.r[7] = rv.y; is.r[8] = rv.z;
-  for (int a = 0; a < 3; ++a) {
-    is.r[9 + a] = x[10 + a] - m.bai[a];
-    is.r[12 + a] = x[13 + a] - m.bgi[a];
-  }
-  for (int a = 0; a < 15; ++a)
-    for (int b = 0; b < 15; ++b) is.J[a][b] = 0.0;
-  // R_i^T = rotation matrix of qi_inv, column by column
-  for (int b = 0; b < 3; ++b) {
+// One warp: residual, block Jacobian, then H = J^T W J, g = J^T W r, cost2 = r^T W r. The sums skip the structural
+// zeros of J, everything else is the dense formula.
+__device__ void imu_normal_equations(const ImuTerm& m, const double* x /*16*/, ImuShared& is, int lane) {
+  if (lane == 0) {
+    const double T = m.sum_dt;
+    const Quatd qi_inv{m.qi[0], -m.qi[1], -m.qi[2], -m.qi[3]};
+    const Vec3d G{m.G[0], m.G[1], m.G[2]};
+    const Vec3d pj{x[0], x[1], x[2]}, vj{x[7], x[8], x[9]};
+    const Vec3d pi{m.pi[0], m.pi[1], m.pi[2]}, vi{m.vi[0], m.vi[1], m.vi[2]};
+    const Vec3d rp = sub(rotate(qi_inv, sub(sub(add(mul(0.5 * T * T, G), pj), pi), mul(T, vi))), Vec3d{m.dp[0], m.dp[1], m.dp[2]});
+    const Vec3d rv = sub(rotate(qi_inv, sub(add(mul(T, G), vj), vi)), Vec3d{m.dv[0], m.dv[1], m.dv[2]});
+    is.r[0] = rp.x; is.r[1] = rp.y; is.r[2] = rp.z;
+    is.r[6] = rv.x; is.r[7] = rv.y; is.r[8] = rv.z;
+  } else if (lane == 1) {
+    const Quatd qi_inv{m.qi[0], -m.qi[1], -m.qi[2], -m.qi[3]};
+    const Quatd qj{x[3], x[4], x[5], x[6]};
+    const Quatd A = qmul(Quatd{m.dq[0], -m.dq[1], -m.dq[2], -m.dq[3]}, qi_inv);
+    const Quatd e = qmul(A, qj);
+    is.r[3] = 2 * e.x; is.r[4] = 2 * e.y; is.r[5] = 2 * e.z;
+  } else if (lane >= 2 && lane < 5) {
+    const int b = lane - 2;  // column b of R_i^T (blocks 0 and 2) and of the theta block
+    const Quatd qi_inv{m.qi[0], -m.qi[1], -m.qi[2], -m.qi[3]};
+    const Quatd qj{x[3], x[4], x[5], x[6]};
     const Vec3d col = rotate(qi_inv, Vec3d{b == 0 ? 1.0 : 0.0, b == 1 ? 1.0 : 0.0, b == 2 ? 1.0 : 0.0});
-    is.J[0][b] = col.x; is.J[1][b] = col.y; is.J[2][b] = col.z;
-    is.J[6][6 + b] = col.x; is.J[7][6 + b] = col.y; is.J[8][6 + b] = col.z;
+    is.B[0][0][b] = col.x; is.B[0][1][b] = col.y; is.B[0][2][b] = col.z;
+    is.B[2][0][b] = col.x; is.B[2][1][b] = col.y; is.B[2][2][b] = col.z;
+    const Quatd A = qmul(Quatd{m.dq[0], -m.dq[1], -m.dq[2], -m.dq[3]}, qi_inv);
     const Quatd c = qmul(qmul(A, Quatd{0.0, b == 0 ? 1.0 : 0.0, b == 1 ? 1.0 : 0.0, b == 2 ? 1.0 : 0.0}), qj);
-    is.J[3][3 + b] = 2 * c.x; is.J[4][3 + b] = 2 * c.y; is.J[5][3 + b] = 2 * c.z;
+    is.B[1][0][b] = 2 * c.x; is.B[1][1][b] = 2 * c.y; is.B[1][2][b] = 2 * c.z;
+  } else if (lane >= 5 && lane < 11) {
+    const int a = lane - 5;
+    is.r[9 + a] = x[10 + a] - (a < 3 ? m.bai[a] : m.bgi[a - 3]);
   }
-  for (int a = 0; a < 6; ++a) is.J[9 + a][9 + a] = 1.0;
-}
-
-// All threads: is.H = J^T W J, is.g = J^T W r, is.cost2 = r^T W r.
-__device__ void imu_normal_equations(const ImuTerm& m, const double* x, ImuShared& is) {
-  if (threadIdx.x == 0) imu_residual_jacobian(m, x, is);
-  __syncthreads();
-  for (int e = threadIdx.x; e < 225; e += blockDim.x) {
+  __syncwarp();
+  // WJ[c][b] = sum_d W[c][d] J[d][b]
+  for (int e = lane; e < 225; e += 32) {
     const int c = e / 15, b = e % 15;
-    double s = 0;
-    for (int d = 0; d < 15; ++d) s += m.W[c * 15 + d] * is.J[d][b];
+    double s;
+    if (b < 9) {
+      const int blk = b / 3, col = b % 3;
+      s = 0;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) s += is.W[c * 15 + 3 * blk + d] * is.B[blk][d][col];
+    } else {
+      s = is.W[c * 15 + b];
+    }
     is.WJ[c][b] = s;
   }
-  if (threadIdx.x < 15) {
+  if (lane < 15) {
     double s = 0;
-    for (int d = 0; d < 15; ++d) s += m.W[threadIdx.x * 15 + d] * is.r[d];
-    is.Wr[threadIdx.x] = s;
+    for (int d = 0; d < 15; ++d) s += is.W[lane * 15 + d] * is.r[d];
+    is.Wr[lane] = s;
   }
-  __syncthreads();
-  for (int e = threadIdx.x; e < 225; e += blockDim.x) {
+  __syncwarp();
+  // H[a][b] = sum_c J[c][a] WJ[c][b]
+  for (int e = lane; e < 225; e += 32) {
     const int a = e / 15, b = e % 15;
-    double s = 0;
-    for (int c = 0; c < 15; ++c) s += is.J[c][a] * is.WJ[c][b];
+    double s;
+    if (a < 9) {
+      const int blk = a / 3, col = a % 3;
+      s = 0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) s += is.B[blk][c][col] * is.WJ[3 * blk + c][b];
+    } else {
+      s = is.WJ[a][b];
+    }
     is.H[a][b] = s;
   }
-  if (threadIdx.x < 15) {
-    double s = 0;
-    for (int c = 0; c < 15; ++c) s += is.J[c][threadIdx.x] * is.Wr[c];
-    is.g[threadIdx.x] = s;
+  if (lane < 15) {
+    const int a = lane;
+    double s;
+    if (a < 9) {
+      const int blk = a / 3, col = a % 3;
+      s = 0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) s += is.B[blk][c][col] * is.Wr[3 * blk + c];
+    } else {
+      s = is.Wr[a];
+    }
+    is.g[a] = s;
   }
-  if (threadIdx.x == 31) {
+  if (lane == 31) {
     double s = 0;
     for (int c = 0; c < 15; ++c) s += is.r[c] * is.Wr[c];
     is.cost2 = s;
   }
-  __syncthreads();
-}
-
-template <int N>
-__device__ __forceinline__ void load_eval(const Shared& sh, const ImuShared* is, EvalT<N>* e) {
-  double c2 = sh.acc[0];
-  for (int c = 0; c < N; ++c) {
-    e->g[c] = c < 6 ? sh.acc[1 + c] : 0.0;
-    for (int d = 0; d < N; ++d) e->H[c][d] = 0.0;
-  }
-  for (int c = 0; c < 6; ++c)
-    for (int d = c; d < 6; ++d) e->H[c][d] = e->H[d][c] = sh.acc[7 + tri(c, d)];
-  if (N == 15 && is) {
-    c2 += is->cost2;
-    for (int c = 0; c < N; ++c) {
-      e->g[c] += is->g[c];
-      for (int d = 0; d < N; ++d) e->H[c][d] += is->H[c][d];
-    }
-  }
-  e->cost = 0.5 * c2;
-}
-
-// Solves A y = b for symmetric positive definite A (n <= N) by Cholesky; false if not PD / not finite.
-template <int N>
-__device__ bool cholesky_solve(int n, double A[N][N], const double* b, double* y) {
-  double Lm[N][N];
-  for (int i = 0; i < n; ++i) {
-    for (int j = 0; j <= i; ++j) {
-      double s = A[i][j];
-      for (int k = 0; k < j; ++k) s -= Lm[i][k] * Lm[j][k];
-      if (i == j) {
-        if (!(s > 0.0)) return false;
-        Lm[i][i] = sqrt(s);
-      } else {
-        Lm[i][j] = s / Lm[j][j];
-      }
-    }
-  }
-  double z[N];
-  for (int i = 0; i < n; ++i) {
-    double s = b[i];
-    for (int k = 0; k < i; ++k) s -= Lm[i][k] * z[k];
-    z[i] = s / Lm[i][i];
-  }
-  for (int i = n - 1; i >= 0; --i) {
-    double s = z[i];
-    for (int k = i + 1; k < n; ++k) s -= Lm[k][i] * y[k];
-    y[i] = s / Lm[i][i];
-  }
-  for (int i = 0; i < n; ++i)
-    if (!isfinite(y[i])) return false;
-  return true;
+  __syncwarp();
 }
 
 __device__ __forceinline__ void setup_problem(const NlsOptions& opt, const NlsProblem& prob, Shared& sh, double* x0,
@@ -430,20 +419,24 @@ __device__ __forceinline__ void setup_problem(const NlsOptions& opt, const NlsPr
 }
 
 // Trust-region state of one problem (names follow Ceres 1.13 TrustRegionMinimizer / LevenbergMarquardtStrategy /
-// TrustRegionStepEvaluator members). Lives in shared memory and is touched by thread 0 only, so the evaluation
-// pass keeps the registers.
+// TrustRegionStepEvaluator members). Lives in shared memory and is driven by WARP 0: lane i owns row i of every
+// N x N matrix (Jacobi scaling, LM diagonal, Cholesky, triangular solves, model cost), lane 0 the scalar bookkeeping.
+// The accepted point's and the candidate's normal equations sit in two buffers that swap on a successful step.
 template <int N>
 struct LmStateT {
   static constexpr int NA = Dims<N>::ambient;
-  EvalT<N> cur;
+  double H[2][N][N], g[2][N], cost[2];
+  double A[N][N];  // scaled + damped system, overwritten by its Cholesky factor (lower triangle; diagonal = 1 / L[j][j])
+  double gs[N], step[N], scale[N], diag[N];
   double x[NA], cand[NA], best_x[NA], target_t[3], target_q_inv[4];
-  double scale[N], diag[N];
   double x_norm, minimum_cost, radius, decrease_factor, gradient_max_norm, initial_cost, final_cost, last_cost;
   double model_cost_change;
   double ev_minimum, ev_current, ev_reference, ev_candidate, ev_acc_ref, ev_acc_cand;
   int ev_num_nonmono, max_nonmono;
+  int cur;  // which buffer holds the accepted point
   int reuse_diagonal, last_successful, num_invalid, iteration, recorded, successful, unsuccessful, termination, evals;
   int nl, only_yaw, max_iter;
+  int flag;  // lane 0 -> warp broadcast of the state machine's decisions
 };
 
 template <int NA>
@@ -471,157 +464,262 @@ __device__ double projected_gradient_max_norm(const double* at, const double* g,
   return mx;
 }
 
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// Assembles the normal equations of the last evaluation (sh.acc [+ the IMU term]) into buffer `buf`. Warp 0.
 template <int N>
-__device__ __noinline__ void lm_iteration_zero(LmStateT<N>& st, const Shared& sh, const ImuShared* is) {
-  load_eval<N>(sh, is, &st.cur);
-  st.evals = 1;
-  for (int j = 0; j < st.nl; ++j) st.scale[j] = 1.0 / (1.0 + sqrt(st.cur.H[j][j]));
-  for (int j = st.nl; j < N; ++j) st.scale[j] = 0.0;
-  st.x_norm = norm_ambient<Dims<N>::ambient>(st.x);
-  st.gradient_max_norm = projected_gradient_max_norm<N>(st.x, st.cur.g, st.only_yaw);
-  st.initial_cost = st.final_cost = st.last_cost = st.cur.cost;
-  st.ev_minimum = st.ev_current = st.ev_reference = st.ev_candidate = st.cur.cost;
-  st.ev_acc_ref = st.ev_acc_cand = 0;
-  st.ev_num_nonmono = 0;
-  st.minimum_cost = 1.7976931348623157e308;
-  st.radius = Lm::initial_radius;
-  st.decrease_factor = 2.0;
-  st.reuse_diagonal = 0;
-  st.last_successful = 1;
-  st.num_invalid = st.iteration = st.recorded = st.successful = st.unsuccessful = 0;
-  st.termination = 1;
+__device__ __forceinline__ void load_eval(LmStateT<N>& st, const Shared& sh, const ImuShared* is, int buf, int lane) {
+  if (lane < N) {
+    const int c = lane;
+    double gv = c < 6 ? sh.acc[1 + c] : 0.0;
+    if (N == 15 && is) gv += is->g[c];
+    st.g[buf][c] = gv;
+    for (int d = 0; d < N; ++d) {
+      double h = (c < 6 && d < 6) ? sh.acc[7 + (c <= d ? tri(c, d) : tri(d, c))] : 0.0;
+      if (N == 15 && is) h += is->H[c][d];
+      st.H[buf][c][d] = h;
+    }
+  }
+  if (lane == 0) {
+    double c2 = sh.acc[0];
+    if (N == 15 && is) c2 += is->cost2;
+    st.cost[buf] = 0.5 * c2;
+  }
+  __syncwarp();
+}
+
+template <int N>
+__device__ void lm_iteration_zero(LmStateT<N>& st, const Shared& sh, const ImuShared* is, int lane) {
+  load_eval<N>(st, sh, is, 0, lane);
+  if (lane < N) st.scale[lane] = lane < st.nl ? 1.0 / (1.0 + sqrt(st.H[0][lane][lane])) : 0.0;
+  if (lane == 0) {
+    st.cur = 0;
+    st.evals = 1;
+    const double c = st.cost[0];
+    st.x_norm = norm_ambient<Dims<N>::ambient>(st.x);
+    st.gradient_max_norm = projected_gradient_max_norm<N>(st.x, st.g[0], st.only_yaw);
+    st.initial_cost = st.final_cost = st.last_cost = c;
+    st.ev_minimum = st.ev_current = st.ev_reference = st.ev_candidate = c;
+    st.ev_acc_ref = st.ev_acc_cand = 0;
+    st.ev_num_nonmono = 0;
+    st.minimum_cost = 1.7976931348623157e308;
+    st.radius = Lm::initial_radius;
+    st.decrease_factor = 2.0;
+    st.reuse_diagonal = 0;
+    st.last_successful = 1;
+    st.num_invalid = st.iteration = st.recorded = st.successful = st.unsuccessful = 0;
+    st.termination = 1;
+  }
+  __syncwarp();
+}
+
+// LevenbergMarquardtStrategy::ComputeStep on the Jacobi-scaled system, warp-cooperative. Returns (warp-uniform) whether the
+// step is valid; on success st.step holds the scaled step and st.model_cost_change the predicted decrease.
+template <int N>
+__device__ __forceinline__ bool lm_compute_step(LmStateT<N>& st, int lane) {
+  const int nl = st.nl, cur = st.cur;
+  const bool row = lane < nl;
+  const double radius = st.radius;
+  if (row) {
+    const double sc = st.scale[lane];
+    st.gs[lane] = sc * st.g[cur][lane];
+    for (int d = 0; d < nl; ++d) st.A[lane][d] = sc * st.H[cur][lane][d] * st.scale[d];
+    if (!st.reuse_diagonal) st.diag[lane] = fmin(fmax(st.A[lane][lane], Lm::min_lm_diagonal), Lm::max_lm_diagonal);
+    st.A[lane][lane] += st.diag[lane] / radius;
+  }
+  __syncwarp();
+  // Cholesky, left-looking by columns; lane i owns row i. The factor overwrites the lower triangle of A.
+  bool valid = true;
+  for (int j = 0; j < nl; ++j) {
+    double s = 0.0;
+    if (row && lane >= j) {
+      s = st.A[lane][j];
+      for (int k = 0; k < j; ++k) s -= st.A[lane][k] * st.A[j][k];
+    }
+    const double pivot = __shfl_sync(0xffffffffu, s, j);
+    if (!(pivot > 0.0)) { valid = false; break; }
+    // one reciprocal square root per column instead of a square root and a division on the critical path
+    // (fp64 rsqrt: 1 ulp); the diagonal slot keeps 1 / L[j][j], which is what the triangular solves need
+    const double rinv = rsqrt(pivot);
+    if (row && lane >= j) st.A[lane][j] = lane == j ? rinv : s * rinv;
+    __syncwarp();
+  }
+  if (valid) {
+    // L z = gs (forward), L^T y = z (backward); lane i carries the running right-hand side of row i
+    const double inv_diag = row ? st.A[lane][lane] : 0.0;
+    double rhs = row ? st.gs[lane] : 0.0;
+    for (int k = 0; k < nl; ++k) {
+      const double zk = __shfl_sync(0xffffffffu, rhs * inv_diag, k);
+      if (lane == k) rhs = zk;
+      else if (row && lane > k) rhs -= st.A[lane][k] * zk;
+    }
+    for (int k = nl - 1; k >= 0; --k) {
+      const double yk = __shfl_sync(0xffffffffu, rhs * inv_diag, k);
+      if (lane == k) rhs = yk;
+      else if (row && lane < k) rhs -= st.A[k][lane] * yk;
+    }
+    const double y = rhs;
+    valid = __all_sync(0xffffffffu, !row || isfinite(y));
+    if (valid) {
+      const double stp = row ? -y : 0.0;
+      if (row) st.step[lane] = stp;
+      __syncwarp();
+      double lin = 0.0, quad = 0.0;
+      if (row) {
+        lin = stp * st.gs[lane];
+        const double sc = st.scale[lane];
+        double r = 0;
+        for (int d = 0; d < nl; ++d) r += (sc * st.H[cur][lane][d] * st.scale[d]) * st.step[d];
+        quad = stp * r;
+      }
+      lin = warp_sum(lin);
+      quad = warp_sum(quad);
+      const double mcc = -(lin + 0.5 * quad);
+      if (lane == 0) st.model_cost_change = mcc;
+      valid = mcc > 0.0;
+    }
+  }
+  if (lane == 0) st.reuse_diagonal = 1;
+  __syncwarp();
+  return valid;
 }
 
 // FinalizeIterationAndCheckIfMinimizerCanContinue + ComputeTrustRegionStep (+ HandleInvalidStep retries).
-// Returns 1 to stop; otherwise st.cand holds the candidate point.
+// Returns 1 to stop; otherwise st.cand holds the candidate point. Warp 0, warp-uniform result.
 template <int N>
-__device__ __noinline__ int lm_prepare_step(LmStateT<N>& st) {
+__device__ int lm_prepare_step(LmStateT<N>& st, int lane) {
   constexpr int NA = Dims<N>::ambient;
-  if (st.last_successful) {
-    ++st.successful;
-    if (st.cur.cost < st.minimum_cost) {
-      st.minimum_cost = st.cur.cost;
-      for (int i = 0; i < NA; ++i) st.best_x[i] = st.x[i];
+  if (lane == 0) {
+    int stop = 0;
+    if (st.last_successful) {
+      ++st.successful;
+      if (st.cost[st.cur] < st.minimum_cost) {
+        st.minimum_cost = st.cost[st.cur];
+        for (int i = 0; i < NA; ++i) st.best_x[i] = st.x[i];
+      }
+    } else {
+      ++st.unsuccessful;
     }
-  } else {
-    ++st.unsuccessful;
+    ++st.recorded;
+    st.final_cost = fmin(st.final_cost, st.last_cost);
+    if (st.iteration >= st.max_iter) { st.termination = 1; stop = 1; }
+    else if (st.last_successful && st.gradient_max_norm <= Lm::gradient_tolerance) { st.termination = 0; stop = 1; }
+    else if (st.radius <= Lm::min_radius) { st.termination = 0; stop = 1; }
+    st.flag = stop;
   }
-  ++st.recorded;
-  st.final_cost = fmin(st.final_cost, st.last_cost);
-  if (st.iteration >= st.max_iter) { st.termination = 1; return 1; }
-  if (st.last_successful && st.gradient_max_norm <= Lm::gradient_tolerance) { st.termination = 0; return 1; }
-  if (st.radius <= Lm::min_radius) { st.termination = 0; return 1; }
-  const int nl = st.nl;
+  __syncwarp();
+  if (st.flag) return 1;
   for (;;) {
-    ++st.iteration;
-    // LevenbergMarquardtStrategy::ComputeStep on the Jacobi-scaled system
-    double A[N][N], Hs[N][N], gs[N], y[N], step[N];
-    for (int c = 0; c < nl; ++c) {
-      gs[c] = st.scale[c] * st.cur.g[c];
-      for (int d = 0; d < nl; ++d) Hs[c][d] = A[c][d] = st.scale[c] * st.cur.H[c][d] * st.scale[d];
-    }
-    if (!st.reuse_diagonal)
-      for (int c = 0; c < nl; ++c) st.diag[c] = fmin(fmax(A[c][c], Lm::min_lm_diagonal), Lm::max_lm_diagonal);
-    for (int c = 0; c < nl; ++c) A[c][c] += st.diag[c] / st.radius;
-    bool valid = cholesky_solve<N>(nl, A, gs, y);
-    st.reuse_diagonal = 1;
-    if (valid) {
-      double lin = 0, quad = 0;
-      for (int c = 0; c < nl; ++c) {
-        step[c] = -y[c];
-        lin += step[c] * gs[c];
+    if (lane == 0) ++st.iteration;
+    __syncwarp();
+    if (lm_compute_step<N>(st, lane)) {
+      if (lane == 0) {
+        st.num_invalid = 0;
+        double delta[N];
+        for (int c = 0; c < N; ++c) delta[c] = c < st.nl ? st.step[c] * st.scale[c] : 0.0;
+        plus_n<N>(st.x, delta, st.only_yaw, st.cand);
       }
-      for (int c = 0; c < nl; ++c) {
-        double row = 0;
-        for (int d = 0; d < nl; ++d) row += Hs[c][d] * step[d];
-        quad += step[c] * row;
-      }
-      st.model_cost_change = -(lin + 0.5 * quad);
-      valid = st.model_cost_change > 0.0;
-    }
-    if (valid) {
-      st.num_invalid = 0;
-      double delta[N];
-      for (int c = 0; c < N; ++c) delta[c] = c < nl ? step[c] * st.scale[c] : 0.0;
-      plus_n<N>(st.x, delta, st.only_yaw, st.cand);
+      __syncwarp();
       return 0;
     }
     // HandleInvalidStep, then finalize that iteration and retry with the smaller radius
-    if (++st.num_invalid >= Lm::max_consecutive_invalid) { st.termination = 2; return 1; }
-    st.radius *= 0.5;
-    st.last_successful = 0;
-    st.last_cost = st.cur.cost;
-    ++st.unsuccessful;
-    ++st.recorded;
-    if (st.iteration >= st.max_iter) { st.termination = 1; return 1; }
-    if (st.radius <= Lm::min_radius) { st.termination = 0; return 1; }
+    if (lane == 0) {
+      int stop = 0;
+      if (++st.num_invalid >= Lm::max_consecutive_invalid) { st.termination = 2; stop = 1; }
+      else {
+        st.radius *= 0.5;
+        st.last_successful = 0;
+        st.last_cost = st.cost[st.cur];
+        ++st.unsuccessful;
+        ++st.recorded;
+        if (st.iteration >= st.max_iter) { st.termination = 1; stop = 1; }
+        else if (st.radius <= Lm::min_radius) { st.termination = 0; stop = 1; }
+      }
+      st.flag = stop;
+    }
+    __syncwarp();
+    if (st.flag) return 1;
   }
 }
 
-// Tolerance tests, step acceptance and trust-region update for the evaluated candidate. Returns 1 to stop.
+// Tolerance tests, step acceptance and trust-region update for the evaluated candidate. Returns 1 to stop. Warp 0.
 template <int N>
-__device__ __noinline__ int lm_process_candidate(LmStateT<N>& st, const Shared& sh, const ImuShared* is) {
+__device__ int lm_process_candidate(LmStateT<N>& st, const Shared& sh, const ImuShared* is, int lane) {
   constexpr int NA = Dims<N>::ambient;
-  EvalT<N> ce;
-  load_eval<N>(sh, is, &ce);
-  ++st.evals;
-  double candidate_cost = ce.cost;
-  if (!isfinite(candidate_cost)) candidate_cost = 1.7976931348623157e308;
-  // ParameterToleranceReached
-  double sn = 0;
-  for (int i = 0; i < NA; ++i) sn += (st.x[i] - st.cand[i]) * (st.x[i] - st.cand[i]);
-  if (sqrt(sn) <= Lm::parameter_tolerance * (st.x_norm + Lm::parameter_tolerance)) { st.termination = 0; return 1; }
-  // FunctionToleranceReached
-  if (fabs(st.cur.cost - candidate_cost) <= Lm::function_tolerance * st.cur.cost) { st.termination = 0; return 1; }
-  const double relative = (st.ev_current - candidate_cost) / st.model_cost_change;
-  const double historical = (st.ev_reference - candidate_cost) / (st.ev_acc_ref + st.model_cost_change);
-  const double relative_decrease = fmax(relative, historical);
-  if (relative_decrease > Lm::min_relative_decrease) {
-    // HandleSuccessfulStep (the candidate's normal equations were computed speculatively in the same pass)
-    for (int i = 0; i < NA; ++i) st.x[i] = st.cand[i];
-    st.x_norm = norm_ambient<NA>(st.x);
-    st.cur = ce;
-    st.cur.cost = candidate_cost;
-    st.gradient_max_norm = projected_gradient_max_norm<N>(st.x, st.cur.g, st.only_yaw);
-    st.last_successful = 1;
-    st.last_cost = candidate_cost;
-    const double t = 2.0 * relative_decrease - 1.0;
-    st.radius = st.radius / fmax(1.0 / 3.0, 1.0 - t * t * t);
-    st.radius = fmin(Lm::max_radius, st.radius);
-    st.decrease_factor = 2.0;
-    st.reuse_diagonal = 0;
-    st.ev_current = candidate_cost;
-    st.ev_acc_cand += st.model_cost_change;
-    st.ev_acc_ref += st.model_cost_change;
-    if (st.ev_current < st.ev_minimum) {
-      st.ev_minimum = st.ev_current;
-      st.ev_num_nonmono = 0;
-      st.ev_candidate = st.ev_current;
-      st.ev_acc_cand = 0;
-    } else {
-      ++st.ev_num_nonmono;
-      if (st.ev_current > st.ev_candidate) {
-        st.ev_candidate = st.ev_current;
-        st.ev_acc_cand = 0;
+  const int nb = st.cur ^ 1;
+  load_eval<N>(st, sh, is, nb, lane);  // the candidate's normal equations were computed speculatively in the same pass
+  if (lane == 0) {
+    int stop = 0;
+    ++st.evals;
+    double candidate_cost = st.cost[nb];
+    if (!isfinite(candidate_cost)) candidate_cost = 1.7976931348623157e308;
+    const double cur_cost = st.cost[st.cur];
+    // ParameterToleranceReached
+    double sn = 0;
+    for (int i = 0; i < NA; ++i) sn += (st.x[i] - st.cand[i]) * (st.x[i] - st.cand[i]);
+    if (sqrt(sn) <= Lm::parameter_tolerance * (st.x_norm + Lm::parameter_tolerance)) { st.termination = 0; stop = 1; }
+    // FunctionToleranceReached
+    else if (fabs(cur_cost - candidate_cost) <= Lm::function_tolerance * cur_cost) { st.termination = 0; stop = 1; }
+    else {
+      const double relative = (st.ev_current - candidate_cost) / st.model_cost_change;
+      const double historical = (st.ev_reference - candidate_cost) / (st.ev_acc_ref + st.model_cost_change);
+      const double relative_decrease = fmax(relative, historical);
+      if (relative_decrease > Lm::min_relative_decrease) {
+        // HandleSuccessfulStep
+        for (int i = 0; i < NA; ++i) st.x[i] = st.cand[i];
+        st.x_norm = norm_ambient<NA>(st.x);
+        st.cur = nb;
+        st.cost[nb] = candidate_cost;
+        st.gradient_max_norm = projected_gradient_max_norm<N>(st.x, st.g[nb], st.only_yaw);
+        st.last_successful = 1;
+        st.last_cost = candidate_cost;
+        const double t = 2.0 * relative_decrease - 1.0;
+        st.radius = st.radius / fmax(1.0 / 3.0, 1.0 - t * t * t);
+        st.radius = fmin(Lm::max_radius, st.radius);
+        st.decrease_factor = 2.0;
+        st.reuse_diagonal = 0;
+        st.ev_current = candidate_cost;
+        st.ev_acc_cand += st.model_cost_change;
+        st.ev_acc_ref += st.model_cost_change;
+        if (st.ev_current < st.ev_minimum) {
+          st.ev_minimum = st.ev_current;
+          st.ev_num_nonmono = 0;
+          st.ev_candidate = st.ev_current;
+          st.ev_acc_cand = 0;
+        } else {
+          ++st.ev_num_nonmono;
+          if (st.ev_current > st.ev_candidate) {
+            st.ev_candidate = st.ev_current;
+            st.ev_acc_cand = 0;
+          }
+        }
+        if (st.ev_num_nonmono == st.max_nonmono) {
+          st.ev_reference = st.ev_candidate;
+          st.ev_acc_ref = st.ev_acc_cand;
+        }
+      } else {
+        // HandleUnsuccessfulStep
+        st.last_successful = 0;
+        st.last_cost = candidate_cost;
+        st.radius = st.radius / st.decrease_factor;
+        st.decrease_factor *= 2.0;
+        st.reuse_diagonal = 1;
       }
     }
-    if (st.ev_num_nonmono == st.max_nonmono) {
-      st.ev_reference = st.ev_candidate;
-      st.ev_acc_ref = st.ev_acc_cand;
-    }
-  } else {
-    // HandleUnsuccessfulStep
-    st.last_successful = 0;
-    st.last_cost = candidate_cost;
-    st.radius = st.radius / st.decrease_factor;
-    st.decrease_factor *= 2.0;
-    st.reuse_diagonal = 1;
+    st.flag = stop;
   }
-  return 0;
+  __syncwarp();
+  return st.flag;
 }
 
-// The trust-region loop of Ceres 1.13 (TrustRegionMinimizer::Minimize): thread 0 drives the state machine between
-// evaluation passes in which every thread takes part. FUSED adds the IMU term (15 local parameters).
+// The trust-region loop of Ceres 1.13 (TrustRegionMinimizer::Minimize). Per round: one evaluation pass by every warp
+// (with FUSED the last warp computes the IMU term instead of points, concurrently), one block barrier, then warp 0 alone
+// finishes the reduction and runs the state machine up to the next candidate, one block barrier. FUSED adds the IMU
+// term (15 local parameters).
 template <bool FUSED>
 __device__ __forceinline__ void solve_body(const NlsOptions& opt, const NlsProblem& prob, const ImuTerm* imu,
                                            const double* initial16, double* pose_out /*7 or 16*/,
@@ -630,9 +728,13 @@ __device__ __forceinline__ void solve_body(const NlsOptions& opt, const NlsProbl
   constexpr int NA = Dims<N>::ambient;
   __shared__ Shared sh;
   __shared__ LmStateT<N> st;
-  __shared__ typename std::conditional<FUSED, ImuShared, int>::type is_storage;  // 7 KiB only when the IMU term is there
+  __shared__ typename std::conditional<FUSED, ImuShared, int>::type is_storage;
   __shared__ double xfull[16];
   ImuShared* is = FUSED ? reinterpret_cast<ImuShared*>(&is_storage) : nullptr;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  // with the IMU term and more than one warp, the last warp is the IMU warp and the others take the points
+  const int imu_warp = FUSED ? warps - 1 : -1;
+  const int point_warps = (FUSED && warps > 1) ? warps - 1 : warps;
   {
     double x[7], target_t[3], target_q_inv[4];
     setup_problem(opt, prob, sh, x, target_t, target_q_inv);
@@ -648,29 +750,31 @@ __device__ __forceinline__ void solve_body(const NlsOptions& opt, const NlsProbl
       st.max_iter = opt.max_iter;
       st.max_nonmono = opt.nonmono ? Lm::max_consecutive_nonmonotonic : 0;
     }
+    if (FUSED)
+      for (int e = threadIdx.x; e < 225; e += blockDim.x) is->W[e] = imu->W[e];
   }
   __syncthreads();
-  auto evaluate_all = [&]() {
-    evaluate(opt, prob, sh, st.target_q_inv, st.target_t);
-    if (FUSED) imu_normal_equations(*imu, xfull, *is);
-  };
-  evaluate_all();
-  if (threadIdx.x == 0) lm_iteration_zero<N>(st, sh, is);
+  bool first = true;
   for (;;) {
-    __syncthreads();  // every thread has consumed sh.stop / sh.acc of the previous round
-    if (threadIdx.x == 0) {
-      const int stop = lm_prepare_step<N>(st);
-      sh.stop = stop;
-      if (!stop) {
-        for (int i = 0; i < 7; ++i) sh.x[i] = st.cand[i];
-        for (int i = 0; i < NA; ++i) xfull[i] = st.cand[i];
+    evaluate_points(opt, prob, sh, point_warps * 32);
+    if (FUSED && warp == imu_warp) imu_normal_equations(*imu, xfull, *is, lane);
+    __syncthreads();  // partial sums (and the IMU term) are in shared memory
+    if (warp == 0) {
+      finish_points(opt, sh, point_warps, st.target_q_inv, st.target_t, lane);
+      int stop = 0;
+      if (first) lm_iteration_zero<N>(st, sh, is, lane);
+      else stop = lm_process_candidate<N>(st, sh, is, lane);
+      if (!stop) stop = lm_prepare_step<N>(st, lane);
+      if (lane == 0) {
+        sh.stop = stop;
+        if (!stop) {
+          for (int i = 0; i < 7; ++i) sh.x[i] = st.cand[i];
+          for (int i = 0; i < NA; ++i) xfull[i] = st.cand[i];
+        }
       }
     }
-    __syncthreads();
-    if (sh.stop) break;
-    evaluate_all();  // candidate cost + speculative normal equations
-    if (threadIdx.x == 0) sh.stop = lm_process_candidate<N>(st, sh, is);
-    __syncthreads();
+    first = false;
+    __syncthreads();  // the next evaluation point (or the stop flag) is visible to everyone
     if (sh.stop) break;
   }
   if (threadIdx.x == 0) {
@@ -698,6 +802,7 @@ __global__ void __launch_bounds__(kBlock) nls_fused_kernel(NlsOptions opt, const
                                                            const double* __restrict__ initial16,
                                                            FusedOutput* __restrict__ outputs) {
   FusedOutput& o = outputs[blockIdx.x];
+  if (problems[blockIdx.x].enabled_dev && *problems[blockIdx.x].enabled_dev == 0) return;  // block-uniform
   solve_body<true>(opt, problems[blockIdx.x], imu + blockIdx.x, initial16 + 16 * blockIdx.x, o.state, &o.summary);
 }
 
@@ -706,14 +811,25 @@ __global__ void __launch_bounds__(kBlock) nls_normal_equations_kernel(NlsOptions
                                                                       const double* at_pose, double* out28) {
   __shared__ Shared sh;
   const NlsProblem& prob = problems[blockIdx.x];
-  double x[7], target_t[3], target_q_inv[4];
-  setup_problem(opt, prob, sh, x, target_t, target_q_inv);
+  __shared__ double target_t[3], target_q_inv[4];
+  {
+    double x[7], tt[3], tq[4];
+    setup_problem(opt, prob, sh, x, tt, tq);
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < 3; ++i) target_t[i] = tt[i];
+      for (int i = 0; i < 4; ++i) target_q_inv[i] = tq[i];
+    }
+  }
   __syncthreads();
   if (threadIdx.x == 0)
     for (int i = 0; i < 7; ++i) sh.x[i] = at_pose[i];
   __syncthreads();
-  evaluate(opt, prob, sh, target_q_inv, target_t);
-  if (threadIdx.x < kRed) out28[blockIdx.x * kRed + threadIdx.x] = threadIdx.x == 0 ? 0.5 * sh.acc[0] : sh.acc[threadIdx.x];
+  evaluate_points(opt, prob, sh, blockDim.x);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    finish_points(opt, sh, blockDim.x >> 5, target_q_inv, target_t, threadIdx.x);
+    if (threadIdx.x < kRed) out28[blockIdx.x * kRed + threadIdx.x] = threadIdx.x == 0 ? 0.5 * sh.acc[0] : sh.acc[threadIdx.x];
+  }
 }
 
 __global__ void interpolate_kernel(GridView g, int64_t n, const double* __restrict__ xyz, double* __restrict__ out) {
@@ -750,10 +866,10 @@ int launch_nls(dl_context* ctx, const NlsOptions& opt, const NlsProblem* problem
   return DL_OK;
 }
 
-int launch_nls_fused(dl_context* ctx, const NlsOptions& opt, const NlsProblem* problems_dev, const void* imu_terms_dev,
+int launch_nls_fused(dl_context* ctx, const NlsOptions& opt, const NlsProblem* problems_dev, const ImuTerm* imu_terms_dev,
                      const double* initial16_dev, int count, FusedOutput* out_dev) {
   if (count <= 0) return DL_OK;
-  nls_fused_kernel<<<count, nls_block_threads(), 0, ctx->stream>>>(opt, problems_dev, (const ImuTerm*)imu_terms_dev, initial16_dev, out_dev);
+  nls_fused_kernel<<<count, nls_block_threads(), 0, ctx->stream>>>(opt, problems_dev, imu_terms_dev, initial16_dev, out_dev);
   DL_LAUNCH_CHECK(ctx, "nls_fused_kernel");
   return DL_OK;
 }

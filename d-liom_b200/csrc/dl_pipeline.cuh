@@ -13,6 +13,40 @@ struct ScanConstants {
   int linear_slerp, negative_dot;
 };
 
+// LTB:426-428 and the scan-constant half of Eigen's slerp, in the reference's double arithmetic. Host and device.
+DL_HD ScanConstants make_scan_constants(const Rigidd& prev, const Rigidd& cur) {
+  ScanConstants c;
+  c.prev = prev;
+  c.cur = cur;
+  c.rel = compose(inverse(c.prev), c.cur);
+  const double d = (0.0 * c.rel.q.x + 0.0 * c.rel.q.y) + (0.0 * c.rel.q.z + 1.0 * c.rel.q.w);  // Identity.dot(rel.q)
+  const double abs_d = fabs(d);
+  const double one = 1.0 - 2.220446049250313e-16;
+  c.linear_slerp = abs_d >= one;
+  c.negative_dot = d < 0;
+  c.theta = c.linear_slerp ? 0.0 : acos(abs_d);
+  c.sin_theta = c.linear_slerp ? 1.0 : sin(c.theta);
+  return c;
+}
+
+// Device-side preparation of the IMU-coupled front end (dl_imu.cu), one warp per scan: from the pre-integration of the
+// samples since the previous scan and the state there -> the predicted state (LTB:188-199), the deskew constants, the
+// factor of the fused solve in the submap frame (incl. the 15x15 information matrix) and the solve's initial state.
+struct ImuPrepareArgs {
+  int count;
+  const dl_preintegration* preint;
+  const dl_nav_state* states_i;  // local frame
+  Rigidd to_submap;              // inverse of the submap's local pose
+  double gravity[3];
+  double imu_weight;
+  ScanConstants* scans;
+  ImuTerm* terms;
+  double* init16;                // 16 doubles per scan: p q v ba bg of the prediction, submap frame
+  dl_nav_state* predicted;       // local frame
+  int32_t* ok;                   // 0: the pre-integration covariance is not positive definite (or no samples)
+};
+int launch_imu_prepare(dl_context* ctx, const ImuPrepareArgs& a);
+
 struct IngestArgs {
   const float* ranges;        // all scans, RangeMeasurement rows (8 floats); scan b starts at row b * in_cap
   int64_t in_cap;
@@ -78,6 +112,8 @@ struct ResultArgs {
   const FusedOutput* fused;        // optional: the fused (IMU) solve's output replaces `nls`
   Rigidd submap;
   const int32_t* error_flag;       // set by the fused front half when a voxel key could not be packed
+  const int32_t* imu_ok;           // optional: 0 = the scan's IMU factor could not be formed (result ok = -2)
+  dl_nav_state* states_out;        // optional (fused solve): the estimated state in the LOCAL frame
   dl_scan_result* results;
 };
 

@@ -197,6 +197,33 @@ class ScanResult(C.Structure):
                 ("num_passes_low", C.c_int32), ("reserved", C.c_int32)]
 
 
+class ImuSamples:
+    """dl_frontend_imu_samples + the arrays it points to (kept alive with the object). intervals: per scan (dt[n], acc[n,3],
+    gyr[n,3]); states_i: per scan 16-vectors (p q v ba bg) at the previous scan."""
+
+    class Struct(C.Structure):
+        _fields_ = [("noise", ImuNoise), ("imu_weight", C.c_double), ("gravity", C.c_double * 3), ("states_i", C.c_void_p),
+                    ("offsets", C.c_void_p), ("dt", C.c_void_p), ("acc", C.c_void_p), ("gyr", C.c_void_p)]
+
+    def __init__(self, noise4, intervals, states_i, imu_weight=1.0, gravity=(0.0, 0.0, 9.8), pin=False):
+        n = len(intervals)
+        self.n = n
+        self.offsets = np.zeros(n + 1, np.int32)
+        for k, (dt, _, _) in enumerate(intervals):
+            self.offsets[k + 1] = self.offsets[k] + len(dt)
+        cat = lambda i, w: (np.ascontiguousarray(np.concatenate([np.asarray(iv[i], np.float64).reshape(-1, w) for iv in intervals]))
+                            if n and self.offsets[-1] else np.zeros((0, w)))
+        self.dt, self.acc, self.gyr = cat(0, 1).reshape(-1), cat(1, 3), cat(2, 3)
+        self.states = np.ascontiguousarray(np.asarray(states_i, np.float64).reshape(n, 16))
+        if pin:   # page-lock the arrays so the streaming submit's uploads are truly asynchronous
+            import torch
+            self._pinned = [torch.from_numpy(a).pin_memory() for a in (self.dt, self.acc, self.gyr, self.states)]
+            self.dt, self.acc, self.gyr, self.states = [t.numpy() for t in self._pinned]
+        self.struct = ImuSamples.Struct(ImuNoise(*[float(v) for v in noise4]), float(imu_weight), (C.c_double * 3)(*gravity),
+                                        self.states.ctypes.data, self.offsets.ctypes.data, self.dt.ctypes.data,
+                                        self.acc.ctypes.data, self.gyr.ctypes.data)
+
+
 def lib():
     global _LIB
     if _LIB is not None:
@@ -263,6 +290,12 @@ def lib():
     L.dl_decode_point_cloud2_dev.argtypes = [vp, ip(PointCloud2Layout), vp, C.c_int64, f64p, vp, ip(C.c_int64), ip(C.c_double)]
     L.dl_frontend_match_batch_imu.argtypes = [vp, ip(FrontendOptions), ip(FrontendImu), C.c_int32, ip(vp), i64p, f32p, C.c_int32,
                                               f64p, vp, vp, ip(ScanResult)]
+    L.dl_frontend_match_batch_imu_samples.argtypes = [vp, ip(FrontendOptions), vp, C.c_int32, ip(vp), i64p, f32p, C.c_int32, f64p,
+                                                      vp, vp, ip(ScanResult), vp, vp]
+    L.dl_frontend_match_batch_imu_samples_dev.argtypes = [vp, ip(FrontendOptions), vp, C.c_int32, vp, C.c_int64, i64p, f32p,
+                                                          C.c_int32, f64p, vp, vp, vp, vp]
+    L.dl_frontend_submit_imu_samples.argtypes = [vp, ip(FrontendOptions), vp, C.c_int32, ip(vp), i64p, f32p, C.c_int32, f64p, vp, vp]
+    L.dl_frontend_collect_imu.argtypes = [vp, C.c_int32, ip(ScanResult), vp]
     L.dl_frontend_submit.argtypes = [vp, ip(FrontendOptions), C.c_int32, ip(vp), i64p, f32p, C.c_int32, f64p, f64p, f64p, vp, vp]
     L.dl_frontend_collect.argtypes = [vp, C.c_int32, ip(ScanResult)]
     L.dl_frontend_match_batch_dev.argtypes = [vp, ip(FrontendOptions), C.c_int32, vp, C.c_int64, i64p, f32p, C.c_int32,
@@ -573,6 +606,45 @@ class Context:
                                                       lo.h, results))
         return results, np.array([o.to16() for o in out])
 
+    def frontend_match_batch_imu_samples(self, options, ranges_list, origins, imu, submap_local_pose, hi, lo):
+        """Front end fed with raw IMU samples (ImuSamples): pre-integration, prediction and fused solve on the device.
+        -> (results, estimated states [n,16], predicted states [n,16])."""
+        hb = ranges_list if isinstance(ranges_list, HostScanBatch) else HostScanBatch(ranges_list)
+        n = hb.n
+        origins = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        out, pred = np.zeros((n, 16)), np.zeros((n, 16))
+        results = (ScanResult * n)()
+        self.check(self.L.dl_frontend_match_batch_imu_samples(self.h, C.byref(options), C.addressof(imu.struct), n, hb.pointers,
+                                                              hb.sizes, origins, len(origins),
+                                                              np.ascontiguousarray(submap_local_pose, np.float64), hi.h, lo.h,
+                                                              results, out.ctypes.data, pred.ctypes.data))
+        return results, out, pred
+
+    def frontend_match_batch_imu_samples_dev(self, options, imu, ranges_dev_ptr, cap_rows, sizes, origins, submap_local_pose, hi,
+                                             lo, results_dev_ptr, states_dev_ptr):
+        sizes = np.ascontiguousarray(sizes, np.int64)
+        origins = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        self.check(self.L.dl_frontend_match_batch_imu_samples_dev(self.h, C.byref(options), C.addressof(imu.struct), len(sizes),
+                                                                  ranges_dev_ptr, cap_rows, sizes, origins, len(origins),
+                                                                  np.ascontiguousarray(submap_local_pose, np.float64), hi.h,
+                                                                  lo.h, results_dev_ptr, states_dev_ptr))
+
+    def frontend_submit_imu_samples(self, options, host_batch, origins, imu, submap_local_pose, hi, lo):
+        hb = host_batch if isinstance(host_batch, HostScanBatch) else HostScanBatch(host_batch)
+        origins = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        self.check(self.L.dl_frontend_submit_imu_samples(self.h, C.byref(options), C.addressof(imu.struct), hb.n, hb.pointers,
+                                                         hb.sizes, origins, len(origins),
+                                                         np.ascontiguousarray(submap_local_pose, np.float64), hi.h, lo.h))
+        self._submitted = (hb, hb.n, imu)   # keeps the host buffers alive until collect
+
+    def frontend_collect_imu(self):
+        n = self._submitted[1]
+        results = (ScanResult * n)()
+        states = np.zeros((n, 16))
+        self.check(self.L.dl_frontend_collect_imu(self.h, n, results, states.ctypes.data))
+        self._submitted = None
+        return results, states
+
     def frontend_submit(self, options, host_batch, origins, prev_poses, cur_poses, submap_local_pose, hi, lo):
         """Streaming form: returns as soon as the batch is enqueued; frontend_collect() returns its results."""
         hb = host_batch if isinstance(host_batch, HostScanBatch) else HostScanBatch(host_batch)
@@ -584,7 +656,7 @@ class Context:
         self._submitted = (hb, hb.n)   # keeps the host buffers alive until collect
 
     def frontend_collect(self):
-        hb, n = self._submitted
+        n = self._submitted[1]
         results = (ScanResult * n)()
         self.check(self.L.dl_frontend_collect(self.h, n, results))
         self._submitted = None

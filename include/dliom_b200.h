@@ -317,7 +317,8 @@ typedef struct dl_scan_result {
   dl_solve_summary summary;
   float rtcsm_score;
   int32_t ok;                             /* 0 = dropped (empty cloud), like the reference's nullptr; -1 = a point lay
-                                             outside +-2^20 voxels of the fused front half (results invalid) */
+                                             outside +-2^20 voxels of the fused front half (results invalid); -2 = no IMU
+                                             factor could be formed for this scan (dl_frontend_*_imu_samples) */
   int32_t num_first_filter, num_returns, num_misses, num_high_resolution, num_low_resolution;
   /* adaptive filter bookkeeping: points inside max_range and voxel passes run, per filter (high, low) */
   int32_t num_cropped_high, num_cropped_low, num_passes_high, num_passes_low;
@@ -384,6 +385,44 @@ int dl_frontend_match_batch_imu(dl_context* ctx, const dl_frontend_options* opti
                                 int32_t num_scans, const void* const* ranges, const int64_t* sizes, const float* origins,
                                 int32_t num_origins, const double* submap_local_pose, const dl_grid* high_resolution_grid,
                                 const dl_grid* low_resolution_grid, dl_scan_result* results);
+
+/* The same front end fed with the RAW IMU samples between consecutive scans (configs[1]: 64-beam + 200 Hz IMU): the
+ * pre-integration (LocalTrajectoryBuilder3D::AddImuData, LTB:164-201, integration_base.h:109-265), the state prediction that
+ * seeds the pose and the deskew (LTB:188-199, :426-428), the factor's information matrix and the fused solve all run on the
+ * device — nothing IMU-related is computed on the host. Scan k uses samples [offsets[k], offsets[k+1]) of dt / acc (xyz) /
+ * gyr (xyz); the first sample of an interval only latches the integrator; states_i[k] is the optimised state at the previous
+ * scan (its biases are the linearisation point). Result ok = -2 marks a scan whose interval has no usable samples
+ * (covariance not positive definite): no solve ran for it. An EXTENSION like dl_fused_match_batch. */
+typedef struct dl_frontend_imu_samples {
+  dl_imu_noise noise;
+  double imu_weight;
+  double gravity[3];
+  const dl_nav_state* states_i;
+  const int32_t* offsets; /* num_scans + 1, offsets[0] == 0 */
+  const double* dt;
+  const double* acc;
+  const double* gyr;
+} dl_frontend_imu_samples;
+/* Host scans in, results + estimated states (+ optionally the predicted states) out; blocking. */
+int dl_frontend_match_batch_imu_samples(dl_context* ctx, const dl_frontend_options* options, const dl_frontend_imu_samples* imu,
+                                        int32_t num_scans, const void* const* ranges, const int64_t* sizes, const float* origins,
+                                        int32_t num_origins, const double* submap_local_pose, const dl_grid* high_resolution_grid,
+                                        const dl_grid* low_resolution_grid, dl_scan_result* results, dl_nav_state* states_out,
+                                        dl_nav_state* predicted_states_out);
+/* Device-resident scans (layout as dl_frontend_match_batch_dev); results and states stay on the device. Only the IMU samples
+ * and states_i (about 1.3 kB per scan) are uploaded. */
+int dl_frontend_match_batch_imu_samples_dev(dl_context* ctx, const dl_frontend_options* options,
+                                            const dl_frontend_imu_samples* imu, int32_t num_scans, const void* ranges_dev,
+                                            int64_t cap_rows, const int64_t* sizes, const float* origins, int32_t num_origins,
+                                            const double* submap_local_pose, const dl_grid* high_resolution_grid,
+                                            const dl_grid* low_resolution_grid, dl_scan_result* results_dev,
+                                            dl_nav_state* states_out_dev);
+/* Streaming form (see dl_frontend_submit): the sample arrays must stay valid until the collect. */
+int dl_frontend_submit_imu_samples(dl_context* ctx, const dl_frontend_options* options, const dl_frontend_imu_samples* imu,
+                                   int32_t num_scans, const void* const* ranges, const int64_t* sizes, const float* origins,
+                                   int32_t num_origins, const double* submap_local_pose, const dl_grid* high_resolution_grid,
+                                   const dl_grid* low_resolution_grid);
+int dl_frontend_collect_imu(dl_context* ctx, int32_t num_scans, dl_scan_result* results, dl_nav_state* states_out);
 
 /* Streaming form of dl_frontend_match_batch: submit enqueues the uploads, every kernel and the download of the results into
  * pinned staging and returns WITHOUT waiting; collect blocks until that batch is finished and copies the results out.

@@ -386,6 +386,36 @@ def frontend_batch(opts, ranges_list, origin, prev_poses, cur_poses, submap_loca
     return secs, poses, ok
 
 
+def frontend_batch_imu(opts, ranges_list, origin, noise4, states_i, intervals, submap_local_pose, hi_grid, lo_grid, threads,
+                       imu_weight=1.0, gravity=(0.0, 0.0, 9.8)):
+    """CPU restatement of dl_frontend_match_batch_imu_samples (pre-integrate -> predict -> ingest -> filters -> fused solve) for
+    independent scans on `threads` pooled host threads. intervals: per scan (dt[n], acc[n,3], gyr[n,3]).
+    -> (seconds, states [n,16], predicted [n,16], ok [n], iterations [n])."""
+    n = len(ranges_list)
+    rp = (C.c_void_p * n)(*[r.ctypes.data for r in ranges_list])
+    sizes = np.array([len(r) for r in ranges_list], np.int64)
+    offsets = np.zeros(n + 1, np.int32)
+    for k, iv in enumerate(intervals):
+        offsets[k + 1] = offsets[k] + len(iv[0])
+    cat = lambda i, w: (np.ascontiguousarray(np.concatenate([np.asarray(iv[i], np.float64).reshape(-1, w) for iv in intervals]))
+                        if offsets[-1] else np.zeros((0, w)))
+    dt, acc, gyr = cat(0, 1).reshape(-1), cat(1, 3), cat(2, 3)
+    states, pred = np.zeros((n, 16)), np.zeros((n, 16))
+    ok, iters = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    f = lib().orc_frontend_batch_imu
+    f.restype = C.c_double
+    secs = f(C.byref(opts), C.c_int(n), rp, sizes.ctypes.data_as(C.c_void_p),
+             np.ascontiguousarray(origin, np.float32).ctypes.data_as(C.c_void_p),
+             np.ascontiguousarray(noise4, np.float64).ctypes.data_as(C.c_void_p),
+             np.ascontiguousarray(gravity, np.float64).ctypes.data_as(C.c_void_p), C.c_double(imu_weight),
+             np.ascontiguousarray(np.asarray(states_i, np.float64).reshape(n, 16)).ctypes.data_as(C.c_void_p),
+             offsets.ctypes.data_as(C.c_void_p), dt.ctypes.data_as(C.c_void_p), acc.ctypes.data_as(C.c_void_p),
+             gyr.ctypes.data_as(C.c_void_p), np.ascontiguousarray(submap_local_pose, np.float64).ctypes.data_as(C.c_void_p),
+             hi_grid.h, lo_grid.h, C.c_int(threads), states.ctypes.data_as(C.c_void_p), pred.ctypes.data_as(C.c_void_p),
+             ok.ctypes.data_as(C.c_void_p), iters.ctypes.data_as(C.c_void_p))
+    return secs, states, pred, ok, iters
+
+
 # ---------------------------------------------------------------- IMU (orc_imu.h)
 GRAVITY = np.array([0.0, 0.0, 9.8])
 

@@ -1,7 +1,11 @@
 // TEST INFRASTRUCTURE — CPU oracle (see orc_math.h header). Flat C interface for ctypes
 // (tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl reference only).
 // Poses cross this interface as 7 doubles: t.x t.y t.z q.w q.x q.y q.z.
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cstring>
 #include <thread>
 
@@ -484,6 +488,72 @@ int orc_match_scan(const OrcFrontEndOptions* o, const float* returns_tracking, i
   return 1;
 }
 
+}  // extern "C"
+
+// Persistent worker pool for the CPU baseline: threads are created once and reused by every call; the scans of a batch
+// are handed out one at a time from an atomic counter (a work queue), so a batch that is not a multiple of the thread
+// count does not leave a strided tail. This is the loop-closure thread-pool pattern of the reference
+// (C/common/thread_pool.cc:37-107) applied to independent scans.
+namespace {
+class WorkerPool {
+ public:
+  static WorkerPool& get() {
+    static WorkerPool* pool = new WorkerPool;  // never destroyed: the workers sleep on its condition variable until exit
+    return *pool;
+  }
+  // Runs f(item) for item in [0, n) on `threads` threads (the caller is one of them); returns when all are done.
+  void run(int threads, int n, const std::function<void(int)>& f) {
+    threads = std::max(1, std::min(threads, n));
+    std::unique_lock<std::mutex> lock(mu_);
+    while ((int)workers_.size() < threads - 1) workers_.emplace_back([this, id = (int)workers_.size()] { loop(id); });
+    f_ = &f;
+    n_ = n;
+    next_.store(0);
+    active_ = threads - 1;
+    pending_ = threads - 1;
+    ++generation_;
+    lock.unlock();
+    cv_.notify_all();
+    drain();
+    lock.lock();
+    done_.wait(lock, [this] { return pending_ == 0; });
+    f_ = nullptr;
+  }
+
+ private:
+  void drain() {
+    for (;;) {
+      const int i = next_.fetch_add(1);
+      if (i >= n_) break;
+      (*f_)(i);
+    }
+  }
+  void loop(int id) {
+    uint64_t seen = 0;
+    for (;;) {
+      std::unique_lock<std::mutex> lock(mu_);
+      cv_.wait(lock, [&] { return generation_ != seen; });
+      seen = generation_;
+      const bool mine = id < active_;
+      lock.unlock();
+      if (!mine) continue;
+      drain();
+      lock.lock();
+      if (--pending_ == 0) done_.notify_all();
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  std::vector<std::thread> workers_;
+  const std::function<void(int)>* f_ = nullptr;
+  int n_ = 0, active_ = 0, pending_ = 0;
+  uint64_t generation_ = 0;
+  std::atomic<int> next_{0};
+};
+}  // namespace
+
+extern "C" {
+
 // Whole per-scan hot path (ingest + match) for a batch of independent scans on `threads` host threads:
 // the CPU baseline. scans share the option block and the submap. Returns wall seconds.
 double orc_frontend_batch(const OrcFrontEndOptions* o, int num_scans, const void* const* ranges, const int64_t* sizes,
@@ -492,21 +562,76 @@ double orc_frontend_batch(const OrcFrontEndOptions* o, int num_scans, const void
                           double* poses_out /* 7 per scan */, int* ok_out) {
   const FrontEndOptions fe = make_frontend(*o);
   const auto t0 = std::chrono::steady_clock::now();
-  auto work = [&](int tid) {
-    for (int s = tid; s < num_scans; s += threads) {
-      const ScanIngest ing = ingest_scan(fe, (const RangeMeasurement*)ranges[s], sizes[s], (const V3f*)origin,
-                                         pose_in(prev_poses + 7 * s), pose_in(cur_poses + 7 * s));
-      const ScanMatchOutput r =
-          match_scan(fe, ing.returns_tracking.data(), (int64_t)ing.returns_tracking.size() / 3,
-                     cast_d(ing.current_pose), pose_in(submap_local_pose), *(HybridGrid*)hi_grid, *(HybridGrid*)lo_grid);
-      ok_out[s] = r.ok ? 1 : 0;
-      if (r.ok) pose_out(r.pose_estimate_local, poses_out + 7 * s);
+  WorkerPool::get().run(threads, num_scans, [&](int s) {
+    const ScanIngest ing = ingest_scan(fe, (const RangeMeasurement*)ranges[s], sizes[s], (const V3f*)origin,
+                                       pose_in(prev_poses + 7 * s), pose_in(cur_poses + 7 * s));
+    const ScanMatchOutput r =
+        match_scan(fe, ing.returns_tracking.data(), (int64_t)ing.returns_tracking.size() / 3,
+                   cast_d(ing.current_pose), pose_in(submap_local_pose), *(HybridGrid*)hi_grid, *(HybridGrid*)lo_grid);
+    ok_out[s] = r.ok ? 1 : 0;
+    if (r.ok) pose_out(r.pose_estimate_local, poses_out + 7 * s);
+  });
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// The same with the IMU in the loop (BASELINE configs[1]: 64-beam + 200 Hz IMU), restating what dl_frontend_match_batch_imu_samples
+// computes: per scan, pre-integrate the samples since the previous scan (integration_base.h:109-265), predict the state
+// (LTB:188-199), ingest with that prediction (LTB:393-487), adaptive filters (LTB:506-530), then the scan match with the
+// pre-integration residual in the same solve (the north-star's fused form; the reference chains a GTSAM update instead).
+// states: 16 doubles each, LOCAL frame. ok_out: 1, 0 (scan dropped) or -2 (no IMU factor).
+double orc_frontend_batch_imu(const OrcFrontEndOptions* o, int num_scans, const void* const* ranges, const int64_t* sizes,
+                              const float* origin, const double* noise4, const double* gravity, double imu_weight,
+                              const double* states_i, const int32_t* offsets, const double* dt, const double* acc,
+                              const double* gyr, const double* submap_local_pose, void* hi_grid, void* lo_grid, int threads,
+                              double* states_out, double* predicted_out, int* ok_out, int* iterations_out) {
+  const FrontEndOptions fe = make_frontend(*o);
+  const ImuNoise noise{noise4[0], noise4[1], noise4[2], noise4[3]};
+  const V3d G{gravity[0], gravity[1], gravity[2]};
+  const Rigid3d submap = pose_in(submap_local_pose), to_submap = inverse(submap);
+  const HybridGrid& hi = *(HybridGrid*)hi_grid;
+  const HybridGrid& lo = *(HybridGrid*)lo_grid;
+  const auto t0 = std::chrono::steady_clock::now();
+  WorkerPool::get().run(threads, num_scans, [&](int s) {
+    const NavState si = FusedProblem::unpack(states_i + 16 * s);
+    Preintegration m;
+    preint_reset(&m, si.ba, si.bg);
+    for (int k = offsets[s]; k < offsets[s + 1]; ++k)
+      preint_push(&m, dt[k], {acc[3 * k], acc[3 * k + 1], acc[3 * k + 2]}, {gyr[3 * k], gyr[3 * k + 1], gyr[3 * k + 2]}, noise);
+    const NavState pred = imu_predict(si, m, G);
+    if (predicted_out) FusedProblem::pack(pred, predicted_out + 16 * s);
+    ok_out[s] = 0;
+    if (iterations_out) iterations_out[s] = 0;
+    const ScanIngest ing = ingest_scan(fe, (const RangeMeasurement*)ranges[s], sizes[s], (const V3f*)origin, Rigid3d{si.p, si.q},
+                                       Rigid3d{pred.p, pred.q});
+    const float* pts = ing.returns_tracking.data();
+    const int64_t n = (int64_t)ing.returns_tracking.size() / 3;
+    if (n == 0) return;
+    const std::vector<int64_t> hk = AdaptiveVoxelFilter(fe.hi_filter, pts, n, 3);
+    if (hk.empty()) return;
+    const std::vector<int64_t> lk = AdaptiveVoxelFilter(fe.lo_filter, pts, n, 3);
+    if (lk.empty()) return;
+    std::vector<float> hc, lc;
+    for (int64_t i : hk) hc.insert(hc.end(), pts + 3 * i, pts + 3 * i + 3);
+    for (int64_t i : lk) lc.insert(lc.end(), pts + 3 * i, pts + 3 * i + 3);
+    // everything the solve sees lives in the submap frame
+    const Rigid3d pose_i = compose(to_submap, Rigid3d{si.p, si.q});
+    const Rigid3d init_pose = compose(to_submap, cast_d(ing.current_pose));
+    NavState a = si, b = pred;
+    a.p = pose_i.t; a.q = pose_i.q; a.v = rotate(to_submap.q, si.v);
+    b.p = init_pose.t; b.q = init_pose.q; b.v = rotate(to_submap.q, pred.v);
+    NavState out;
+    SolveSummary sum;
+    if (!fused_scan_match(fe.ceres, init_pose.t, a, b, m, rotate(to_submap.q, G), imu_weight,
+                          {{hc.data(), (int64_t)hk.size(), &hi}, {lc.data(), (int64_t)lk.size(), &lo}}, &out, &sum)) {
+      ok_out[s] = -2;
+      return;
     }
-  };
-  std::vector<std::thread> pool;
-  for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
-  work(0);
-  for (auto& t : pool) t.join();
+    const Rigid3d est = compose(submap, Rigid3d{out.p, out.q});
+    out.p = est.t; out.q = est.q; out.v = rotate(submap.q, out.v);
+    FusedProblem::pack(out, states_out + 16 * s);
+    ok_out[s] = 1;
+    if (iterations_out) iterations_out[s] = (int)sum.iterations.size();
+  });
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 

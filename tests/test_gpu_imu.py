@@ -148,3 +148,116 @@ def test_frontend_batch_with_fused_imu_solve(ctx, orc):
         assert np.allclose(x[7:], want[7:], atol=1e-6)
         assert np.allclose(np.array(r.pose_estimate_local[:]), x[:7], atol=1e-12)
         assert r.summary.num_iterations == ws["num_iterations"]
+
+
+def _imu_batch(w, orc):
+    intervals, states_i = [], []
+    for s in range(len(w["scans"])):
+        t1 = w["times"][s]
+        intervals.append(imu_synth.samples(t1 - 0.1, t1, noise=(3.99e-2, 1.56e-2), seed=30 + s))
+        states_i.append(imu_synth.state(t1 - 0.1, ba=(0.01, -0.02, 0.005), bg=(1e-3, -2e-3, 5e-4)))
+    return intervals, states_i
+
+
+def test_frontend_imu_samples_device_chain(ctx, orc):
+    """dl_frontend_match_batch_imu_samples: raw samples in, pre-integration + prediction + deskew constants + information
+    matrix + fused solve on the device. Against (a) the oracle chain and (b) the host-prepared chain of the same library."""
+    import dliom
+    w = workload()
+    hi, lo = dliom.Grid.from_oracle(ctx, w["hi"]), dliom.Grid.from_oracle(ctx, w["lo"])
+    fo = dliom.FrontendOptions.from_oracle(w["opts"])
+    o = w["opts"]
+    intervals, states_i = _imu_batch(w, orc)
+    imu = dliom.ImuSamples(NOISE, intervals, states_i, imu_weight=0.7)
+    res, states, predicted = ctx.frontend_match_batch_imu_samples(fo, w["scans"], w["origin"], imu, w["submap_pose"], hi, lo)
+    preds, preints = [], []
+    for s in range(len(w["scans"])):
+        dt, acc, gyr = intervals[s]
+        si = states_i[s]
+        m = orc.imu_preintegrate(NOISE, si[10:13], si[13:16], dt, acc, gyr)
+        pred = orc.imu_predict(si, m)
+        # prediction: no transcendental function involved -> the device reproduces the oracle to rounding
+        assert np.allclose(predicted[s], pred, rtol=0, atol=1e-11)
+        ing = orc.ingest_scan(o, w["scans"][s], w["origin"], si[:7], pred[:7])
+        pts = ing["returns_tracking"]
+        hk, _ = orc.adaptive_voxel_filter(pts, o.hi_max_length, o.hi_min_num_points, o.hi_max_range)
+        lk, _ = orc.adaptive_voxel_filter(pts, o.lo_max_length, o.lo_min_num_points, o.lo_max_range)
+        init = pred.copy()
+        init[:7] = np.concatenate([ing["current_pose"][:3].astype(np.float64), ing["current_pose"][3:].astype(np.float64)])
+        want, ws = orc.fused_match([pts[hk], pts[lk]], [w["hi"], w["lo"]], [o.occ_w0, o.occ_w1], o.trans_w, o.rot_w, init[:3], si,
+                                   init, m, imu_weight=0.7, max_iter=o.max_iter)
+        r, x = res[s], states[s]
+        assert r.ok == 1
+        assert r.num_returns == len(pts) and r.num_high_resolution == len(hk) and r.num_low_resolution == len(lk)
+        dtn, drn = pose_error(x[:7], want[:7])
+        assert dtn < 1e-6 and drn < 1e-7, (dtn, drn)
+        assert np.allclose(x[7:], want[7:], atol=1e-6)
+        assert np.allclose(np.array(r.pose_estimate_local[:]), x[:7], atol=1e-12)
+        assert r.summary.num_iterations == ws["num_iterations"]
+        preds.append(pred)
+        preints.append(ctx.imu_preintegrate(NOISE, [(dt, acc, gyr)], np.array([si[10:16]]))[0])
+    # (b) same library, factors prepared on the host from finished pre-integrations: the two chains share every operation
+    res_h, states_h = ctx.frontend_match_batch_imu(fo, w["scans"], w["origin"], states_i, preds, preints, w["submap_pose"], hi, lo,
+                                                   imu_weight=0.7)
+    for s in range(len(w["scans"])):
+        assert res_h[s].summary.num_iterations == res[s].summary.num_iterations
+        assert np.allclose(states_h[s], states[s], rtol=0, atol=1e-9)
+
+
+def test_frontend_imu_samples_streaming_and_device_resident(ctx, orc):
+    import ctypes as C
+    import dliom
+    w = workload()
+    hi, lo = dliom.Grid.from_oracle(ctx, w["hi"]), dliom.Grid.from_oracle(ctx, w["lo"])
+    fo = dliom.FrontendOptions.from_oracle(w["opts"])
+    intervals, states_i = _imu_batch(w, orc)
+    imu = dliom.ImuSamples(NOISE, intervals, states_i, imu_weight=0.7)
+    res, states, _ = ctx.frontend_match_batch_imu_samples(fo, w["scans"], w["origin"], imu, w["submap_pose"], hi, lo)
+    # streaming
+    ctx.frontend_submit_imu_samples(fo, w["scans"], w["origin"], imu, w["submap_pose"], hi, lo)
+    with pytest.raises(dliom.DlError):   # one batch in flight per context
+        ctx.frontend_submit_imu_samples(fo, w["scans"], w["origin"], imu, w["submap_pose"], hi, lo)
+    res_s, states_s = ctx.frontend_collect_imu()
+    assert np.array_equal(states_s, states)
+    assert all(list(a.pose_estimate_local) == list(b.pose_estimate_local) and a.ok == b.ok for a, b in zip(res_s, res))
+    # device-resident scans, results and states
+    n = len(w["scans"])
+    sizes = np.array([len(s) for s in w["scans"]], np.int64)
+    cap = int(sizes.max())
+    rows = np.zeros((n, cap, 8), np.float32)
+    for b, sc in enumerate(w["scans"]):
+        rows[b, :len(sc)] = sc.view(np.float32).reshape(-1, 8)
+    d_rows = ctx.device_alloc(rows.nbytes)
+    d_res = ctx.device_alloc(n * C.sizeof(dliom.ScanResult))
+    d_states = ctx.device_alloc(n * 16 * 8)
+    ctx.copy_to_device(d_rows, rows)
+    ctx.frontend_match_batch_imu_samples_dev(fo, imu, d_rows, cap, sizes, w["origin"], w["submap_pose"], hi, lo, d_res, d_states)
+    res_d = ctx.fetch_results(d_res, n)
+    states_d = np.zeros((n, 16))
+    ctx.check(ctx.L.dl_copy_to_host(ctx.h, states_d.ctypes.data, d_states, states_d.nbytes))
+    assert np.array_equal(states_d, states)
+    assert all(list(a.pose_estimate_local) == list(b.pose_estimate_local) for a, b in zip(res_d, res))
+    for p in (d_rows, d_res, d_states):
+        ctx.device_free(p)
+
+
+def test_frontend_imu_samples_without_samples_marks_scan(ctx, orc):
+    """An interval without usable samples has no factor: ok = -2, the other scans of the batch are unaffected."""
+    import dliom
+    w = workload()
+    hi, lo = dliom.Grid.from_oracle(ctx, w["hi"]), dliom.Grid.from_oracle(ctx, w["lo"])
+    fo = dliom.FrontendOptions.from_oracle(w["opts"])
+    intervals, states_i = _imu_batch(w, orc)
+    full = dliom.ImuSamples(NOISE, intervals, states_i, imu_weight=0.7)
+    res, states, _ = ctx.frontend_match_batch_imu_samples(fo, w["scans"], w["origin"], full, w["submap_pose"], hi, lo)
+    holed = list(intervals)
+    holed[1] = (np.zeros(0), np.zeros((0, 3)), np.zeros((0, 3)))
+    imu = dliom.ImuSamples(NOISE, holed, states_i, imu_weight=0.7)
+    res2, states2, _ = ctx.frontend_match_batch_imu_samples(fo, w["scans"], w["origin"], imu, w["submap_pose"], hi, lo)
+    assert res2[1].ok == -2
+    for s in (0, 2, 3):
+        assert res2[s].ok == 1 and np.array_equal(states2[s], states[s])
+    bad = dliom.ImuSamples(NOISE, intervals, states_i, imu_weight=0.7)
+    bad.offsets[0] = 1
+    with pytest.raises(dliom.DlError):
+        ctx.frontend_match_batch_imu_samples(fo, w["scans"], w["origin"], bad, w["submap_pose"], hi, lo)

@@ -106,3 +106,48 @@ def test_fused_solve_stays_consistent_with_imu_and_scan(orc):
     out2, _ = orc.fused_match(clouds, [w["hi"], w["lo"]], [1.0, 6.0], 0.0, 0.0, init[:3], si, init, m, imu_weight=1e3,
                               max_iter=50)
     assert np.linalg.norm(out2[:3] - pred[:3]) < 1e-3 and np.linalg.norm(out2[7:10] - pred[7:10]) < 1e-2
+
+
+def test_frontend_batch_imu_equals_the_stepwise_chain():
+    """orc_frontend_batch_imu (the pooled CPU baseline of the IMU-coupled front end) = pre-integrate -> predict -> ingest ->
+    adaptive filters -> fused match done call by call; identical for 1 and many threads (work queue, no shared state)."""
+    import orc
+    from helpers import workload
+    import imu_synth
+    w = workload()
+    o = w["opts"]
+    noise = [3.99e-2, 1.56e-2, 6.4e-5, 3.6e-5]
+    intervals, states_i = [], []
+    for s in range(len(w["scans"])):
+        t1 = w["times"][s]
+        intervals.append(imu_synth.samples(t1 - 0.1, t1, noise=(3.99e-2, 1.56e-2), seed=30 + s))
+        states_i.append(imu_synth.state(t1 - 0.1, ba=(0.01, -0.02, 0.005), bg=(1e-3, -2e-3, 5e-4)))
+    secs, states, pred, ok, iters = orc.frontend_batch_imu(o, w["scans"], w["origin"], noise, states_i, intervals, w["submap_pose"],
+                                                           w["hi"], w["lo"], 3, imu_weight=0.7)
+    _, states1, _, ok1, _ = orc.frontend_batch_imu(o, w["scans"], w["origin"], noise, states_i, intervals, w["submap_pose"],
+                                                   w["hi"], w["lo"], 1, imu_weight=0.7)
+    assert np.array_equal(states, states1) and np.array_equal(ok, ok1) and all(ok == 1) and secs > 0
+    for s in range(len(w["scans"])):
+        dt, acc, gyr = intervals[s]
+        si = states_i[s]
+        m = orc.imu_preintegrate(noise, si[10:13], si[13:16], dt, acc, gyr)
+        p = orc.imu_predict(si, m)
+        assert np.array_equal(p, pred[s])
+        ing = orc.ingest_scan(o, w["scans"][s], w["origin"], si[:7], p[:7])
+        pts = ing["returns_tracking"]
+        hk, _ = orc.adaptive_voxel_filter(pts, o.hi_max_length, o.hi_min_num_points, o.hi_max_range)
+        lk, _ = orc.adaptive_voxel_filter(pts, o.lo_max_length, o.lo_min_num_points, o.lo_max_range)
+        init = p.copy()
+        init[:7] = ing["current_pose"].astype(np.float64)
+        want, ws = orc.fused_match([pts[hk], pts[lk]], [w["hi"], w["lo"]], [o.occ_w0, o.occ_w1], o.trans_w, o.rot_w, init[:3], si,
+                                   init, m, imu_weight=0.7, max_iter=o.max_iter)
+        # the batch chain renormalises the float-cast pose when it composes it with the submap pose (as the device does)
+        from helpers import pose_error
+        dtn, drn = pose_error(states[s][:7], want[:7])
+        assert dtn < 1e-9 and drn < 1e-8 and np.allclose(states[s][7:], want[7:], rtol=0, atol=1e-9)
+        assert iters[s] == ws["num_iterations"]
+    # an empty interval has no factor
+    holed = list(intervals)
+    holed[2] = (np.zeros(0), np.zeros((0, 3)), np.zeros((0, 3)))
+    _, _, _, ok2, _ = orc.frontend_batch_imu(o, w["scans"], w["origin"], noise, states_i, holed, w["submap_pose"], w["hi"], w["lo"], 2)
+    assert ok2.tolist() == [1, 1, -2, 1]
