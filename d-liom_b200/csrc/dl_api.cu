@@ -1269,6 +1269,85 @@ int dl_constraint_search_batch(dl_context* ctx, const dl_constraint_options* opt
 
 }  // extern "C"
 
+extern "C" {
+
+int dl_constraint_search_exchange(dl_context* ctx, dl_comm* comm, const dl_constraint_options* options, int32_t count,
+                                  int32_t capacity, const int32_t* submap_ids, const int32_t* node_ids, const double* guesses,
+                                  const float* hi_pts, const int64_t* hi_off, const float* lo_pts, const int64_t* lo_off,
+                                  const dl_grid* const* hi_grids, const dl_grid* const* lo_grids, dl_constraint_row* table,
+                                  dl_exchange_info* info) {
+  if (!ctx || !comm || !options || count < 0 || capacity < 1 || count > capacity || !table) return DL_ERR_ARG;
+  if (capacity > 1024) return ctx->fail(DL_ERR_ARG, "capacity > 1024 pairs per rank and exchange: split the call");
+  if (count > 0 && (!submap_ids || !node_ids)) return DL_ERR_ARG;
+  if (count > 0) DL_TRY(check_pairs(ctx, count, guesses, hi_pts, hi_off, lo_pts, lo_off, hi_grids, lo_grids));
+  DL_TRY(check_fcsm_options(ctx, options->fast_correlative_scan_matcher_3d));
+  DL_TRY(check_ceres_options(ctx, &options->ceres_scan_matcher_3d, 2));
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int world = dl_comm_world_size(comm), rank = dl_comm_rank(comm);
+  const size_t row_bytes = sizeof(dl_constraint_row), block = (size_t)capacity * row_bytes;
+  DL_TRY(comm_reserve(comm, block));
+  dl_constraint_row* d_send = (dl_constraint_row*)comm_send_buffer(comm);
+  dl_constraint_row* d_recv = (dl_constraint_row*)comm_recv_buffer(comm);
+  // padding rows: found = -1 (every int32 of the row is -1; the doubles are NaN and never read)
+  DL_CUDA(ctx, cudaMemsetAsync(d_send, 0xFF, block, ctx->stream));
+  if (count > 0) {
+    const NlsOptions nls = to_nls_options(options->ceres_scan_matcher_3d, 2);
+    const int n = count;
+    const int64_t n_hi = hi_off[n] - hi_off[0], n_lo = lo_off[n] - lo_off[0];
+    DL_TRY(ctx->reserve_device(coarse_bytes(n_hi, n_lo, n) +
+                               arena_bytes({(size_t)n * sizeof(NlsProblem), (size_t)n * sizeof(NlsOutput), (size_t)n * 8})));
+    Arena a(ctx->d_scratch);
+    CoarseSearch cs;
+    DL_TRY(coarse_search(ctx, a, options->fast_correlative_scan_matcher_3d, (float)options->min_score, 0, n, guesses, hi_pts,
+                         hi_off, lo_pts, lo_off, hi_grids, lo_grids, nullptr, &cs));
+    std::vector<NlsProblem> problems(n);
+    for (int k = 0; k < n; ++k) {
+      NlsProblem& p = problems[k];
+      std::memset(&p, 0, sizeof(p));
+      p.cloud[0] = cs.d_hi + 3 * (hi_off[k] - hi_off[0]);
+      p.cloud[1] = cs.d_lo + 3 * (lo_off[k] - lo_off[0]);
+      p.count[0] = (int32_t)(hi_off[k + 1] - hi_off[k]);
+      p.count[1] = (int32_t)(lo_off[k + 1] - lo_off[k]);
+      p.grid[0] = hi_grids[k]->view();
+      p.grid[1] = lo_grids[k]->view();
+      p.initial_dev = cs.d_picks[k].pose;  // address arithmetic only
+      p.enabled_dev = &cs.d_picks[k].found;
+    }
+    NlsProblem* d_problems = a.take<NlsProblem>(n);
+    NlsOutput* d_out = a.take<NlsOutput>(n);
+    int32_t* d_ids = a.take<int32_t>(2 * (size_t)n);
+    DL_TRY(h2d(ctx, d_problems, problems.data(), n));
+    DL_TRY(h2d(ctx, d_ids, submap_ids, n));
+    DL_TRY(h2d(ctx, d_ids + n, node_ids, n));
+    DL_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(NlsOutput) * n, ctx->stream));
+    {
+      StageScope st(ctx, "loop_closure_refine");
+      DL_TRY(launch_nls(ctx, nls, d_problems, n, d_out));
+    }
+    DL_TRY(launch_pack_constraint_rows(ctx, n, cs.d_picks, d_out, d_ids, d_ids + n, options->loop_closure_translation_weight,
+                                       options->loop_closure_rotation_weight, rank, d_send));
+    DL_TRY(sync(ctx));  // `problems` is pageable host memory; also keeps the search out of the collective's timing
+  }
+  float ms = 0.f;
+  {
+    StageScope st(ctx, "constraint_all_gather");
+    DL_TRY(comm_all_gather(comm, d_send, d_recv, block, &ms));
+  }
+  DL_TRY(d2h(ctx, table, d_recv, (size_t)world * capacity));
+  DL_TRY(sync(ctx));
+  if (info) {
+    info->bytes_sent = (int64_t)block;
+    info->bytes_received = (int64_t)block * world;
+    info->collective_ms = ms;
+    int found = 0;
+    for (int i = 0; i < world * capacity; ++i) found += table[i].found == 1;
+    info->found_total = found;
+  }
+  return DL_OK;
+}
+
+}  // extern "C"
+
 namespace {
 using HostImuTerm = dl::ImuTerm;  // prepared here on the host for the calls that take finished pre-integrations
 

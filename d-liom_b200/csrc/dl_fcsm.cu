@@ -458,6 +458,38 @@ int launch_fcsm_pruned(dl_context* ctx, const FcsmPair* pairs_dev, int count, in
   return DL_OK;
 }
 
+namespace {
+// Constraint{submap_id, node_id, pose, weights} (constraint_builder_3d.cc:328-333) for every searched pair, written where the
+// all-gather reads it: no host round trip between the refinement and the exchange.
+__global__ void pack_constraint_rows_kernel(int n, const FcsmPick* __restrict__ picks, const NlsOutput* __restrict__ refined,
+                                            const int32_t* __restrict__ submap_ids, const int32_t* __restrict__ node_ids,
+                                            double translation_weight, double rotation_weight, int rank, dl_constraint_row* rows) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  dl_constraint_row r;
+  r.submap_id = submap_ids[k];
+  r.node_id = node_ids[k];
+  r.found = picks[k].found ? 1 : 0;
+  r.rank = rank;
+  r.score = picks[k].found ? picks[k].score : 0.f;
+  r.low_resolution_score = picks[k].found ? picks[k].low_resolution_score : 0.f;
+  for (int i = 0; i < 7; ++i) r.pose[i] = picks[k].found ? refined[k].pose[i] : picks[k].pose[i];
+  r.translation_weight = translation_weight;
+  r.rotation_weight = rotation_weight;
+  rows[k] = r;
+}
+}  // namespace
+
+int launch_pack_constraint_rows(dl_context* ctx, int n, const FcsmPick* picks, const NlsOutput* refined, const int32_t* submap_ids,
+                                const int32_t* node_ids, double translation_weight, double rotation_weight, int rank,
+                                dl_constraint_row* rows) {
+  if (n <= 0) return DL_OK;
+  pack_constraint_rows_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, picks, refined, submap_ids, node_ids, translation_weight,
+                                                                         rotation_weight, rank, rows);
+  DL_LAUNCH_CHECK(ctx, "pack_constraint_rows_kernel");
+  return DL_OK;
+}
+
 int launch_fcsm(dl_context* ctx, const FcsmPair* pairs_dev, int count, int max_points, long long max_threads,
                 unsigned long long* best_dev, FcsmPick* picks_dev, float* all_scores_dev) {
   DL_TRY_STATUS(ensure_fcsm_lut(ctx));

@@ -297,6 +297,15 @@ int grid_insert_device(dl_context* ctx, dl_grid* g, const Vec3f& origin, const f
                        const uint16_t* d_hit_table, const uint16_t* d_miss_table, int32_t* d_bbox, uint32_t* d_update_list);
 int launch_transform_filter(dl_context* ctx, const float* in, int n, const Rigidf& to_submap, const Vec3f& origin_submap,
                             float max_range, float* all, float* near, int32_t* near_count, int32_t* tile_counts);
+// dl_comm.cu: staging buffers of the constraint exchange and the timed all-gather
+int comm_reserve(dl_comm* c, size_t bytes_per_rank);
+void* comm_send_buffer(dl_comm* c);
+void* comm_recv_buffer(dl_comm* c);
+int comm_all_gather(dl_comm* c, const void* send_dev, void* recv_dev, size_t bytes, float* ms);
+// dl_fcsm.cu: one dl_constraint_row per searched pair from the coarse picks and the refinement's output
+int launch_pack_constraint_rows(dl_context* ctx, int n, const FcsmPick* picks, const NlsOutput* refined, const int32_t* submap_ids,
+                                const int32_t* node_ids, double translation_weight, double rotation_weight, int rank,
+                                dl_constraint_row* rows);
 int launch_interpolate(dl_context* ctx, const GridView& grid, int64_t n, const double* xyz, double* out);
 int launch_grid_lookup(dl_context* ctx, const GridView& grid, int64_t n, const int32_t* xyz, uint16_t* out);
 

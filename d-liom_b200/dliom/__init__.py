@@ -28,6 +28,10 @@ EXPORTS = [
     "dl_ceres_match_batch", "dl_ceres_normal_equations", "dl_imu_preintegrate", "dl_imu_predict", "dl_fused_match_batch", "dl_ingest_scan", "dl_decode_point_cloud2", "dl_decode_point_cloud2_dev", "dl_frontend_match_batch", "dl_frontend_match_batch_imu", "dl_frontend_submit", "dl_frontend_collect",
     "dl_frontend_match_batch_dev", "dl_frontend_fetch_results", "dl_device_alloc", "dl_device_free",
     "dl_copy_to_device", "dl_copy_to_host",
+    "dl_frontend_match_batch_imu_samples", "dl_frontend_match_batch_imu_samples_dev", "dl_frontend_submit_imu_samples",
+    "dl_frontend_collect_imu",
+    "dl_comm_unique_id", "dl_comm_create", "dl_comm_destroy", "dl_comm_rank", "dl_comm_world_size", "dl_comm_last_error",
+    "dl_comm_all_gather_dev", "dl_comm_all_reduce_f64_dev", "dl_comm_broadcast_dev", "dl_constraint_search_exchange",
 ]
 
 
@@ -158,6 +162,17 @@ class Constraint(C.Structure):
     _fields_ = [("found", C.c_int32), ("score", C.c_float), ("rotational_score", C.c_float),
                 ("low_resolution_score", C.c_float), ("coarse_pose", C.c_double * 7), ("pose", C.c_double * 7),
                 ("translation_weight", C.c_double), ("rotation_weight", C.c_double), ("summary", SolveSummary)]
+
+
+class ConstraintRow(C.Structure):   # dl_constraint_row, 96 bytes
+    _fields_ = [("submap_id", C.c_int32), ("node_id", C.c_int32), ("found", C.c_int32), ("rank", C.c_int32),
+                ("score", C.c_float), ("low_resolution_score", C.c_float), ("pose", C.c_double * 7),
+                ("translation_weight", C.c_double), ("rotation_weight", C.c_double)]
+
+
+class ExchangeInfo(C.Structure):
+    _fields_ = [("bytes_sent", C.c_int64), ("bytes_received", C.c_int64), ("collective_ms", C.c_float),
+                ("found_total", C.c_int32)]
 
 
 class FrontendOptions(C.Structure):
@@ -296,6 +311,18 @@ def lib():
                                                           C.c_int32, f64p, vp, vp, vp, vp]
     L.dl_frontend_submit_imu_samples.argtypes = [vp, ip(FrontendOptions), vp, C.c_int32, ip(vp), i64p, f32p, C.c_int32, f64p, vp, vp]
     L.dl_frontend_collect_imu.argtypes = [vp, C.c_int32, ip(ScanResult), vp]
+    L.dl_comm_unique_id.argtypes = [vp]
+    L.dl_comm_create.argtypes = [vp, vp, C.c_int32, C.c_int32, ip(vp)]
+    L.dl_comm_destroy.argtypes = [vp]
+    L.dl_comm_destroy.restype = None
+    L.dl_comm_rank.argtypes = [vp]
+    L.dl_comm_world_size.argtypes = [vp]
+    L.dl_comm_last_error.restype = C.c_char_p
+    L.dl_comm_all_gather_dev.argtypes = [vp, vp, vp, C.c_int64]
+    L.dl_comm_all_reduce_f64_dev.argtypes = [vp, vp, C.c_int64]
+    L.dl_comm_broadcast_dev.argtypes = [vp, vp, C.c_int64, C.c_int32]
+    L.dl_constraint_search_exchange.argtypes = [vp, vp, ip(ConstraintOptions), C.c_int32, C.c_int32, i32p, i32p, f64p, f32p, i64p,
+                                                f32p, i64p, C.c_void_p, C.c_void_p, ip(ConstraintRow), ip(ExchangeInfo)]
     L.dl_frontend_submit.argtypes = [vp, ip(FrontendOptions), C.c_int32, ip(vp), i64p, f32p, C.c_int32, f64p, f64p, f64p, vp, vp]
     L.dl_frontend_collect.argtypes = [vp, C.c_int32, ip(ScanResult)]
     L.dl_frontend_match_batch_dev.argtypes = [vp, ip(FrontendOptions), C.c_int32, vp, C.c_int64, i64p, f32p, C.c_int32,
@@ -458,6 +485,28 @@ class Context:
                                                      np.ascontiguousarray(pose_guesses, np.float64).reshape(-1, 7), hi_all,
                                                      hi_off, lo_all, lo_off, hg, lg, out))
         return list(out)[:count]
+
+    def constraint_search_exchange(self, comm, options, capacity, submap_ids, node_ids, pose_guesses, hi_clouds, lo_clouds,
+                                   hi_grids, lo_grids):
+        """This rank's (node, submap) searches + the ncclAllGather of the constraint rows -> (table of world * capacity
+        ConstraintRow, ExchangeInfo). Pruned pairs have found == 0, unused slots found == -1."""
+        count = len(pose_guesses)
+        his = [np.ascontiguousarray(c, np.float32).reshape(-1, 3) for c in hi_clouds]
+        los = [np.ascontiguousarray(c, np.float32).reshape(-1, 3) for c in lo_clouds]
+        hi_off = np.concatenate([[0], np.cumsum([len(c) for c in his])]).astype(np.int64)
+        lo_off = np.concatenate([[0], np.cumsum([len(c) for c in los])]).astype(np.int64)
+        hi_all = np.ascontiguousarray(np.concatenate(his) if count else np.zeros((1, 3), np.float32))
+        lo_all = np.ascontiguousarray(np.concatenate(los) if count else np.zeros((1, 3), np.float32))
+        hg = (C.c_void_p * max(count, 1))(*[g.h for g in hi_grids])
+        lg = (C.c_void_p * max(count, 1))(*[g.h for g in lo_grids])
+        table = (ConstraintRow * (comm.world * capacity))()
+        info = ExchangeInfo()
+        self.check(self.L.dl_constraint_search_exchange(self.h, comm.h, C.byref(options), count, capacity,
+                                                        np.ascontiguousarray(submap_ids, np.int32),
+                                                        np.ascontiguousarray(node_ids, np.int32),
+                                                        np.ascontiguousarray(pose_guesses, np.float64).reshape(-1, 7), hi_all,
+                                                        hi_off, lo_all, lo_off, hg, lg, table, C.byref(info)))
+        return table, info
 
     @staticmethod
     def _pairs(clouds, grids):
@@ -698,6 +747,39 @@ class Context:
     def copy_to_device(self, dst, src_array):
         src_array = np.ascontiguousarray(src_array)
         self.check(self.L.dl_copy_to_device(self.h, dst, src_array.ctypes.data_as(C.c_void_p), src_array.nbytes))
+
+
+def comm_unique_id():
+    """128 bytes from ncclGetUniqueId (rank 0 calls this and distributes the bytes)."""
+    buf = (C.c_uint8 * 128)()
+    st = lib().dl_comm_unique_id(C.cast(buf, C.c_void_p))
+    if st != 0:
+        raise DlError(st, (lib().dl_comm_last_error() or b"").decode())
+    return bytes(buf)
+
+
+class Comm:
+    """NCCL communicator owned by the C-ABI library (dl_comm), bound to one Context (its stream carries the collectives)."""
+
+    def __init__(self, ctx, unique_id, rank, world):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.h = C.c_void_p()
+        idbuf = (C.c_uint8 * 128)(*unique_id)
+        ctx.check(ctx.L.dl_comm_create(ctx.h, C.cast(idbuf, C.c_void_p), rank, world, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.ctx.L.dl_comm_destroy(self.h)
+            self.h = None
+
+    def all_gather_dev(self, send_ptr, recv_ptr, bytes_per_rank):
+        self.ctx.check(self.ctx.L.dl_comm_all_gather_dev(self.h, send_ptr, recv_ptr, bytes_per_rank))
+
+    def all_reduce_f64_dev(self, ptr, count):
+        self.ctx.check(self.ctx.L.dl_comm_all_reduce_f64_dev(self.h, ptr, count))
+
+    def broadcast_dev(self, ptr, nbytes, root):
+        self.ctx.check(self.ctx.L.dl_comm_broadcast_dev(self.h, ptr, nbytes, root))
 
 
 class Grid:

@@ -253,6 +253,50 @@ int dl_constraint_search_batch(dl_context* ctx, const dl_constraint_options* opt
                                const int64_t* low_offsets, const dl_grid* const* high_resolution_grids,
                                const dl_grid* const* low_resolution_grids, dl_constraint* constraints);
 
+/* ---- multi-GPU exchange steps (BASELINE configs[3], [4]). One process per GPU. The reference farms the loop-closure
+ *      searches out to a thread pool (constraint_builder_3d.cc:189-197) and hands every found constraint to the pose graph
+ *      (:328-333); here the pairs are partitioned by SUBMAP OWNER (each grid resident on one GPU), every rank runs
+ *      ConstraintBuilder3D::ComputeConstraint for its pairs on its device, and the constraint records are exchanged with ONE
+ *      ncclAllGather over NVLink so that all ranks hold the same table. NCCL is loaded at run time (libnccl.so.2); the
+ *      communicator is made from a 128-byte unique id the host program distributes (rank 0 calls dl_comm_unique_id). ----------- */
+#define DL_COMM_ID_BYTES 128
+typedef struct dl_comm dl_comm;
+int dl_comm_unique_id(uint8_t* id128);
+int dl_comm_create(dl_context* ctx, const uint8_t* id128, int32_t rank, int32_t world_size, dl_comm** out);
+void dl_comm_destroy(dl_comm* comm);
+int32_t dl_comm_rank(const dl_comm* comm);
+int32_t dl_comm_world_size(const dl_comm* comm);
+const char* dl_comm_last_error(void); /* errors of the calls that have no context (unique id) */
+/* Thin device-buffer collectives on the communicator's context stream (asynchronous; dl_context_synchronize to wait). */
+int dl_comm_all_gather_dev(dl_comm* comm, const void* send_dev, void* recv_dev, int64_t bytes_per_rank);
+int dl_comm_all_reduce_f64_dev(dl_comm* comm, double* buffer_dev, int64_t count);
+int dl_comm_broadcast_dev(dl_comm* comm, void* buffer_dev, int64_t bytes, int32_t root);
+
+typedef struct dl_constraint_row { /* 96 bytes; PoseGraphInterface::Constraint as it crosses NVLink */
+  int32_t submap_id, node_id;
+  int32_t found;                  /* 1 found, 0 searched and pruned (the reference's null constraint), -1 padding */
+  int32_t rank;                   /* who searched it */
+  float score, low_resolution_score;
+  double pose[7];                 /* constraint_transform: submap <- node */
+  double translation_weight, rotation_weight;
+} dl_constraint_row;
+typedef struct dl_exchange_info {
+  int64_t bytes_sent;             /* per rank: capacity * sizeof(dl_constraint_row) */
+  int64_t bytes_received;         /* world_size * bytes_sent */
+  float collective_ms;            /* device time of the ncclAllGather alone (CUDA events on the context's stream) */
+  int32_t found_total;
+} dl_exchange_info;
+/* dl_constraint_search_batch for this rank's `count` pairs (count <= capacity; capacity is the same on every rank, e.g. the
+ * largest shard), then the all-gather. table receives world_size * capacity rows, rank r's at [r * capacity, (r+1) * capacity),
+ * unused slots with found = -1; identical on every rank. Between the upload of the clouds and the download of the table
+ * everything stays on the device; the rows are packed by a kernel straight into the all-gather's send buffer. */
+int dl_constraint_search_exchange(dl_context* ctx, dl_comm* comm, const dl_constraint_options* options, int32_t count,
+                                  int32_t capacity, const int32_t* submap_ids, const int32_t* node_ids, const double* pose_guesses,
+                                  const float* high_resolution_points, const int64_t* high_offsets,
+                                  const float* low_resolution_points, const int64_t* low_offsets,
+                                  const dl_grid* const* high_resolution_grids, const dl_grid* const* low_resolution_grids,
+                                  dl_constraint_row* table, dl_exchange_info* info);
+
 /* ---- IMU: pre-integration (LocalTrajectoryBuilder3D::AddImuData, LTB:164-201, with the in-repo mid-point integrator
  *      C/mapping/internal/3d/initialization/integration_base.h:109-265 instead of the un-vendored GTSAM one) and the
  *      scan match with the pre-integration residual (integration_base.h:267-301) fused into the same solve.
