@@ -1,20 +1,26 @@
 #!/usr/bin/env python
 """bench.py — scans/sec of the scan-to-submap registration hot path (BASELINE.json metric) on N B200s.
 
-A "step" is one pass of the whole per-scan hot path (first voxel filter -> deskew/transform/range gate -> second
-voxel filters -> adaptive voxel filters -> Levenberg-Marquardt point-to-grid match) over one batch of synthetic
-64-beam scans (configs[1]: 64-beam ~130k pts/scan, single submap, 1 x B200) against one 0.1 m / 0.45 m submap.
+A "step" is one pass of the whole per-scan hot path of BASELINE configs[1] (64-beam ~130k pts/scan + 200 Hz IMU, single
+submap, 1 x B200) over one batch of DISTINCT synthetic scans:
+    IMU pre-integration of the 20 samples since the previous scan -> state prediction -> first voxel filter ->
+    deskew/transform/range gate -> second voxel filters -> adaptive voxel filters -> Levenberg-Marquardt point-to-grid
+    match with the pre-integration residual fused into the same solve,
+followed by the configs[4] exchange step: every rank runs its share of loop-closure searches (sharded by submap owner)
+and the constraint records are exchanged with one ncclAllGather issued from the C-ABI (at N = 1 the communicator has one
+rank, so the per-GPU work is the same at every N: weak scaling).
 
-  value  scans/s with the batch already resident in HBM (dl_frontend_match_batch_dev), device-timed with CUDA
-         events on the library's stream, max over ranks.
-  e2e    the same metric through the C-ABI call that takes HOST buffers (dl_frontend_match_batch): pinned host
-         scans copied to the device and results copied back inside the timed region (wall clock around the call).
+  value  scans/s with the batch already resident in HBM (dl_frontend_match_batch_imu_samples_dev; the IMU samples, about
+         1.3 kB per scan, are uploaded every step), device-timed with CUDA events on the library's streams, max over ranks.
+  e2e    the same metric through the C-ABI calls that take HOST buffers (dl_frontend_submit_imu_samples / _collect_imu):
+         pinned host scans copied to the device and results + states copied back inside the timed region (wall clock).
   roofline       achieved algorithmic GB/s of the dominant stage (per-stage CUDA events) vs the measured HBM peak.
-  cpu_baseline   the oracle (CPU restatement of the reference path) on the host cores, bounded sample (N=1, rank 0).
+  cpu_baseline   the oracle (CPU restatement of the same chain) on the host cores: pooled threads with a work queue, and the
+                 reference's real mode (one thread); bounded sample (N=1, rank 0).
+  configs2 / mode_F   extra keys: configs[2] (128-beam, 0.05 m grid, correlative + refine) and the full-cloud matcher mode.
 
-`--impl reference` times that CPU path alone (all host threads) and prints the same line with "impl": "reference".
-Multi-GPU: one process per GPU (torchrun), scans are independent -> sharded across ranks, no data-path collective,
-"scaling": "weak". Inputs per step exceed L2 (148 scans x 2.1 MB = 309 MB > 126 MB), so no explicit L2 flush.
+`--impl reference` times the CPU chain alone (all host threads) and prints the same line with "impl": "reference".
+Inputs per step exceed L2 (148 scans x 2.1 MB = 309 MB > 126 MB), so no explicit L2 flush.
 """
 import argparse
 import ctypes as C
@@ -34,6 +40,8 @@ for p in (ROOT, os.path.join(ROOT, "d-liom_b200"), os.path.join(ROOT, "tools")):
 
 METRIC = "scans/sec (64-beam, 10 Hz) per GPU; pose RMSE vs reference CPU"
 UNIT = "scans/s"
+IMU_NOISE = [3.99e-2, 1.56e-2, 6.4e-5, 3.6e-5]     # D/config/kaist.lua:38-43
+IMU_WEIGHT = 1.0
 
 
 def oracle():
@@ -52,9 +60,29 @@ def apply_pose(p7, pts):
     return pts @ R.T + p7[:3]
 
 
+def physical_cores():
+    try:
+        ids = set()
+        phys = core = None
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("physical id"):
+                phys = line.split(":")[1].strip()
+            elif line.startswith("core id"):
+                core = line.split(":")[1].strip()
+            elif not line.strip():
+                if phys is not None and core is not None:
+                    ids.add((phys, core))
+                phys = core = None
+        return len(ids) or None
+    except Exception:
+        return None
+
+
 def build_workload(args, rank):
     """Submap cells (built with the oracle's range-data inserter, like the reference builds a submap: hit 0.55 /
-    miss 0.49 / 2 free voxels, high-res max range 20 m) + the batch of scans to register. Deterministic."""
+    miss 0.49 / 2 free voxels, high-res max range 20 m) + the batch of DISTINCT scans to register, each with the IMU
+    samples since the previous scan and the (perturbed) state there. Deterministic."""
+    import imu_synth
     import synth
     orc = oracle()
     scene = synth.Scene(42)
@@ -72,38 +100,60 @@ def build_workload(args, rank):
         hi.insert_range_data(o, local[np.linalg.norm(local - o, axis=1) <= 20.0])
         lo.insert_range_data(o, local)
     rng = np.random.RandomState(45 + rank)
-    distinct = min(args.batch, args.distinct_scans)
-    scans, prevs, curs, truths = [], [], [], []
-    for j in range(distinct):
-        # sweeps interleaved with the map sweeps (half a period later), per-rank offset -> different data per GPU
-        t = t0 + 0.05 + 0.1 * ((j * 7 + rank * 3) % max(args.map_scans - 1, 1)) + 0.001 * rank
+    span = 0.1 * max(args.map_scans - 2, 1)
+    scans, truths, states_i, intervals = [], [], [], []
+    for j in range(args.batch):
+        # sweeps spread over the mapped stretch, all distinct (different end times -> different rays and noise), per-rank offset
+        t = t0 + 0.05 + span * j / max(args.batch, 1) + 0.0007 * rank
         scans.append(synth.make_scan(scene, args.beams, t))
-        prevs.append(synth.pose7(t - 0.1))
         truths.append(synth.pose7(t))
-        curs.append(synth.perturb_pose(synth.pose7(t), rng, 0.1, 1.0))
-    idx = [j % distinct for j in range(args.batch)]
-    return {"orc": orc, "opts": opts, "hi": hi, "lo": lo, "origin": origin,
-            "scans": [scans[i] for i in idx], "prev": np.array([prevs[i] for i in idx]),
-            "cur": np.array([curs[i] for i in idx]), "truth": np.array([truths[i] for i in idx]),
-            "submap_pose": orc.IDENTITY_POSE.copy()}
+        si = imu_synth.state(t - 0.1, ba=rng.normal(0, 1e-2, 3), bg=rng.normal(0, 1e-3, 3))
+        si[:3] += rng.uniform(-0.05, 0.05, 3)        # the previous scan's estimate is not the truth
+        si[7:10] += rng.uniform(-0.5, 0.5, 3)        # -> the prediction is off by up to ~0.1 m, like the 0.1 m / 1 deg of SURVEY 8d
+        states_i.append(si)
+        intervals.append(imu_synth.samples(t - 0.1, t, ba=si[10:13], bg=si[13:16], noise=(IMU_NOISE[0], IMU_NOISE[1]),
+                                           seed=1000 * rank + j))
+    return {"orc": orc, "opts": opts, "hi": hi, "lo": lo, "origin": origin, "scans": scans, "truth": np.array(truths),
+            "states_i": np.array(states_i), "intervals": intervals, "submap_pose": orc.IDENTITY_POSE.copy()}
+
+
+def loop_closure_pairs(w, args, rank):
+    """The configs[4] exchange step's work list for this rank: `pairs` recent nodes (filtered clouds of its own scans) against
+    the submap it owns (submap id = rank), pose guesses a few metres off so that the coarse search has a window to cover."""
+    orc = w["orc"]
+    rng = np.random.RandomState(900 + rank)
+    his, los, guesses, nodes = [], [], [], []
+    o = w["opts"]
+    for k in range(args.pairs):
+        j = (k * 17) % len(w["scans"])
+        si = w["states_i"][j]
+        pts = orc.ingest_scan(o, w["scans"][j], w["origin"], si[:7], w["truth"][j])["returns_tracking"]
+        hk, _ = orc.adaptive_voxel_filter(pts, o.hi_max_length, o.hi_min_num_points, o.hi_max_range)
+        lk, _ = orc.adaptive_voxel_filter(pts, o.lo_max_length, o.lo_min_num_points, o.lo_max_range)
+        g = np.array(w["truth"][j], np.float64)
+        g[:3] += rng.uniform(-1, 1, 3) * [2.0, 2.0, 0.4]
+        his.append(pts[hk]); los.append(pts[lk]); guesses.append(g); nodes.append(1000 * rank + j)
+    return {"hi": his, "lo": los, "guesses": np.array(guesses), "nodes": nodes, "submaps": [rank] * args.pairs}
 
 
 def pose_errors(a, b):
     dt = np.linalg.norm(a[:, :3] - b[:, :3], axis=1)
-    qa = a[:, 3:] / np.linalg.norm(a[:, 3:], axis=1, keepdims=True)
-    qb = b[:, 3:] / np.linalg.norm(b[:, 3:], axis=1, keepdims=True)
+    qa = a[:, 3:7] / np.linalg.norm(a[:, 3:7], axis=1, keepdims=True)
+    qb = b[:, 3:7] / np.linalg.norm(b[:, 3:7], axis=1, keepdims=True)
     d = np.abs(np.sum(qa * qb, axis=1)).clip(max=1.0)
     return dt, 2 * np.arccos(d)
 
 
 class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons at 2 Hz from before the warm-up to after the last timed region (a subprocess every
+    500 ms; round 1 sampled at 10 Hz, which showed up as noise in a 33 ms timed region)."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.gpu, self.samples, self.stop_flag = gpu_index, [], False
+        self.gpu, self.samples, self.stop_flag, self.mark = gpu_index, [], False, False
 
     def run(self):
         while not self.stop_flag:
@@ -112,73 +162,85 @@ class ClockSampler(threading.Thread):
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 f = [x.strip() for x in out.strip().split(",")]
                 if len(f) >= 9:
-                    self.samples.append(f)
+                    self.samples.append((self.mark, f))
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.5)
 
     def summary(self):
-        if not self.samples:
+        loaded = [f for m, f in self.samples if m] or [f for _, f in self.samples]
+        if not loaded:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(s[1]) for s in self.samples)
+        sm = sorted(float(s[1]) for s in loaded)
         reasons = set()
-        for s in self.samples:
+        for s in loaded:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][2]), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(loaded[0][2]), "reasons": sorted(reasons),
+                "samples": len(sm), "note": "nvidia-smi at 2 Hz while the timed loops run (median over those samples)"}
+
+
+def cpu_chain(w, sel, threads):
+    orc = w["orc"]
+    return orc.frontend_batch_imu(w["opts"], [w["scans"][i] for i in sel], w["origin"], IMU_NOISE, w["states_i"][sel],
+                                  [w["intervals"][i] for i in sel], w["submap_pose"], w["hi"], w["lo"], threads,
+                                  imu_weight=IMU_WEIGHT)
 
 
 def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path (oracle port) on all host threads."""
+    """The reference's own CPU implementation of the path (oracle port of the same chain) on all host threads."""
     if rank != 0:
         return
     w = build_workload(args, 0)
-    orc = w["orc"]
     threads = os.cpu_count() or 1
-    sample = args.batch  # the whole batch is a bounded sample already (~30 ms of CPU work per scan)
-    sel = slice(0, sample)
+    sample = max(args.batch, 8 * threads)   # >= 8 scans per pooled thread, handed out from a work queue
+    sel = [i % args.batch for i in range(sample)]
+    cpu_chain(w, sel[:threads], threads)    # spawn the pool
     times = []
     for step in range(args.warmup + args.steps):
-        secs, poses, ok = orc.frontend_batch(w["opts"], w["scans"][sel], w["origin"], w["prev"][sel], w["cur"][sel],
-                                             w["submap_pose"], w["hi"], w["lo"], threads)
+        secs = cpu_chain(w, sel, threads)[0]
         if step >= args.warmup:
             times.append(secs)
-    ms = 1e3 * float(np.mean(times))
+    ms = 1e3 * float(np.median(times))
     value = sample / (ms / 1e3)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "impl": "reference",
             "config": workload_config(args, args.batch),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{sample} scans per step, {args.steps} steps, one scan per host thread"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "physical_cores": physical_cores(), "kind": "port",
+                             "sample": f"{sample} scans per step ({args.batch} distinct, cycled), median of {args.steps} steps, "
+                                       f"persistent pool of {threads} threads fed from a work queue"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
 def workload_config(args, batch):
-    return {"workload": f"configs[1]: {args.beams}-beam scans (~130k pts) vs one submap (0.1 m / 0.45 m), whole front-end "
-                        f"hot path, pipeline-faithful filters", "scans_per_step_per_gpu": batch, "beams": args.beams,
+    return {"workload": f"configs[1]: {args.beams}-beam scans (~130k pts) + 200 Hz IMU (20 samples per scan, pre-integrated on the "
+                        f"device inside the step) vs one submap (0.1 m / 0.45 m), whole front-end hot path, pipeline-faithful "
+                        f"filters, IMU residual fused into the solve; + configs[4] exchange step ({args.pairs} loop-closure "
+                        f"searches per rank, ncclAllGather of the constraint rows)",
+            "imu": True, "scans_per_step_per_gpu": batch, "distinct_scans": batch, "beams": args.beams,
             "map_scans": args.map_scans, "row_bytes": 4 * args.row_floats,
             "l2_policy": f"inputs ({batch} x {130605 * 4 * args.row_floats / 1e6:.1f} MB) exceed the 126 MB L2; no explicit flush",
-            "parallelism": f"scans sharded over {args.gpus} gpu(s), no collective"}
+            "parallelism": f"scans sharded over {args.gpus} gpu(s); loop-closure pairs sharded by submap owner, one ncclAllGather per step"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=148, help="scans per step per GPU (default: one per SM)")
     ap.add_argument("--beams", type=int, default=64)
     ap.add_argument("--map-scans", type=int, default=40)
-    ap.add_argument("--distinct-scans", type=int, default=16)
-    ap.add_argument("--cpu-sample", type=int, default=0, help="scans in the cpu_baseline sample (0 = 2 x threads)")
+    ap.add_argument("--pairs", type=int, default=8, help="loop-closure (node, submap) searches per rank and step")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="scans in the cpu_baseline sample (0 = 8 x threads)")
     ap.add_argument("--row-floats", type=int, default=4, choices=[4, 8],
                     help="4: TimedPointCloud rows x y z t (what AddRangeData receives); 8: RangeMeasurement rows")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[2] / mode-F / no-IMU extra measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -195,6 +257,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    device = f"cuda:{local_rank}"
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -202,14 +265,12 @@ def main():
 
     w = build_workload(args, rank)
     B = args.batch
-    ctx = dliom.Context(local_rank)
+    ctx, ctx2, ctx3 = dliom.Context(local_rank), dliom.Context(local_rank), dliom.Context(local_rank)
     hi, lo = ctx.grid(0.1), ctx.grid(0.45)
     hi.set_cells(*w["hi"].export())
     lo.set_cells(*w["lo"].export())
     fo = dliom.FrontendOptions.from_oracle(w["opts"])
     fo.range_row_floats = args.row_floats
-    if not os.environ.get("DLIOM_BENCH_PER_SCAN_COPIES"):
-        fo.host_scan_stride_rows = -1   # set below once the staging layout is known
     row_bytes = 4 * args.row_floats
 
     sizes = np.array([len(s) for s in w["scans"]], np.int64)
@@ -218,119 +279,144 @@ def main():
     host = torch.zeros((B, cap, row_bytes), dtype=torch.uint8).pin_memory()
     for b, s in enumerate(w["scans"]):
         host[b, :len(s)] = torch.from_numpy(s.view(np.uint8).reshape(-1, 32)[:, :row_bytes].copy())
-    dev = host.to(f"cuda:{local_rank}")
-    results_dev = torch.zeros(B * C.sizeof(dliom.ScanResult), dtype=torch.uint8, device=f"cuda:{local_rank}")
-    if fo.host_scan_stride_rows:
-        fo.host_scan_stride_rows = cap   # the pinned staging tensor is (B, cap, row_bytes): one allocation, constant stride
+    dev = host.to(device)
+    fo.host_scan_stride_rows = cap   # the pinned staging tensor is (B, cap, row_bytes): one allocation, constant stride
     host_rows = dliom.HostScanBatch([host[b, :int(sizes[b])].numpy() for b in range(B)])
-    # second context + second pinned copy of the scans for the streaming e2e loop (double buffering)
-    ctx2 = dliom.Context(local_rank)
-    host2 = host.clone().pin_memory()
+    host2 = host.clone().pin_memory()   # second pinned copy + second context for the streaming e2e loop (double buffering)
     host_rows2 = dliom.HostScanBatch([host2[b, :int(sizes[b])].numpy() for b in range(B)])
-    stream = torch.cuda.ExternalStream(ctx.stream, device=f"cuda:{local_rank}")
+    imus = [dliom.ImuSamples(IMU_NOISE, w["intervals"], w["states_i"], imu_weight=IMU_WEIGHT, pin=True) for _ in range(2)]
+    imu_bytes = int(imus[0].dt.nbytes + imus[0].acc.nbytes + imus[0].gyr.nbytes + imus[0].states.nbytes + imus[0].offsets.nbytes)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=device)
 
-    results_dev2 = torch.zeros_like(results_dev)
-    dev_lanes = [(ctx, results_dev), (ctx2, results_dev2)]
-    if os.environ.get("DLIOM_BENCH_ONE_CONTEXT"):
-        dev_lanes = [dev_lanes[0]]
-    for _ in range(int(os.environ.get("DLIOM_BENCH_CONTEXTS", "2")) - 2):   # experiments: deeper rotation of contexts
-        dev_lanes.append((dliom.Context(local_rank), torch.zeros_like(results_dev)))
-    extra_ctx = [c for c, _ in dev_lanes[2:]]
+    res_bytes = B * C.sizeof(dliom.ScanResult)
+    dev_lanes = [(c, torch.zeros(res_bytes, dtype=torch.uint8, device=device), torch.zeros((B, 16), dtype=torch.float64, device=device), im)
+                 for c, im in zip((ctx, ctx2), imus)]
 
-    def step_dev(i=0):
+    # ---- the exchange step: NCCL communicator owned by the C-ABI library, created from an id that torch.distributed carries
+    idt = torch.zeros(128, dtype=torch.uint8, device=device)
+    if rank == 0:
+        idt.copy_(torch.tensor(list(dliom.comm_unique_id()), dtype=torch.uint8))
+    if dist is not None:
+        dist.broadcast(idt, 0)
+    comm = dliom.Comm(ctx3, bytes(idt.cpu().numpy().tolist()), rank, world)
+    lc = loop_closure_pairs(w, args, rank)
+    copt = dliom.ConstraintOptions.defaults(min_score=0.3, min_low_resolution_score=0.3, xy_window=3.0, z_window=0.5)
+    exchange = {"ms": [], "found": 0, "bytes": 0, "rows": 0}
+
+    def step_exchange():
+        table, info = ctx3.constraint_search_exchange(comm, copt, args.pairs, lc["submaps"], lc["nodes"], lc["guesses"], lc["hi"],
+                                                      lc["lo"], [hi] * args.pairs, [lo] * args.pairs)
+        exchange["ms"].append(info.collective_ms)
+        exchange["found"] = info.found_total
+        exchange["bytes"] = int(info.bytes_received)
+        exchange["rows"] = len(table)
+        return table
+
+    def step_dev(i, options=None, lanes=None):
         """One pass of the hot path over the HBM-resident batch. Successive steps alternate between two contexts (own
         streams, own scratch), so the latency-bound back half of step i overlaps the front half of step i+1."""
-        c, out = dev_lanes[i % len(dev_lanes)]
-        c.frontend_match_batch_dev(fo, C.c_void_p(dev.data_ptr()), cap, sizes, w["origin"], w["prev"], w["cur"],
-                                   w["submap_pose"], hi, lo, C.c_void_p(out.data_ptr()))
+        c, out, st, im = (lanes or dev_lanes)[i % 2]
+        c.frontend_match_batch_imu_samples_dev(options or fo, im, C.c_void_p(dev.data_ptr()), cap, sizes, w["origin"],
+                                               w["submap_pose"], hi, lo, C.c_void_p(out.data_ptr()), C.c_void_p(st.data_ptr()))
 
-    def step_e2e():
-        return ctx.frontend_match_batch(fo, host_rows, w["origin"], w["prev"], w["cur"], w["submap_pose"], hi, lo)
+    lanes = [(ctx, host_rows, imus[0]), (ctx2, host_rows2, imus[1])]
 
-    lanes = [(ctx, host_rows), (ctx2, host_rows2)]
-
-    def run_streaming(steps):
-        """K batches through dl_frontend_submit / dl_frontend_collect on two alternating contexts: batch i+1 is uploading
-        while batch i computes; every batch's inputs cross PCIe and every batch's results are read back."""
+    def run_streaming(steps, with_exchange=True):
+        """K batches through dl_frontend_submit_imu_samples / dl_frontend_collect_imu on two alternating contexts: batch i+1 is
+        uploading while batch i computes; every batch's inputs cross PCIe and every batch's results are read back."""
         out = None
         for i in range(steps):
-            c, rows = lanes[i & 1]
+            c, rows, im = lanes[i & 1]
             if i >= 2:
-                out = c.frontend_collect()
-            c.frontend_submit(fo, rows, w["origin"], w["prev"], w["cur"], w["submap_pose"], hi, lo)
+                out = c.frontend_collect_imu()
+            c.frontend_submit_imu_samples(fo, rows, w["origin"], im, w["submap_pose"], hi, lo)
+            if with_exchange:
+                step_exchange()
         for i in range(max(steps - 2, 0), steps):
-            out = lanes[i & 1][0].frontend_collect()
+            out = lanes[i & 1][0].frontend_collect_imu()
         return out
 
     def barrier():
         torch.cuda.synchronize()
-        ctx.synchronize()
-        ctx2.synchronize()
-        for c in extra_ctx:
+        for c in (ctx, ctx2, ctx3):
             c.synchronize()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (both paths), then parity of the batch against the oracle on a sample
-    warm = max(args.warmup, 1)   # at least one untimed pass: scratch arenas are sized on first use and `res` below needs a result
-    for k in range(2 * warm):
-        step_dev(k)
-    for _ in range(warm):
-        step_e2e()
-    run_streaming(max(warm, 2))
-    ctx.synchronize()
-    res = ctx.fetch_results(C.c_void_p(results_dev.data_ptr()), B)
+    def timed_device_loop(steps, options=None, with_exchange=True):
+        """CUDA events on the launching streams: the first context's stream opens the region; the closing event is recorded on
+        the same stream after it has been made to wait for the other contexts' streams (event waits, no host sync)."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        others = [torch.cuda.ExternalStream(c.stream, device=device) for c in (ctx2, ctx3)]
+        barrier()
+        gate = torch.cuda.Event()
+        gate.record(stream)
+        for s2 in others:
+            s2.wait_event(gate)           # no context starts before e0
+        e0.record(stream)
+        for k in range(steps):
+            step_dev(k, options)
+            if with_exchange:
+                step_exchange()
+        for s2 in others:
+            tail = torch.cuda.Event()
+            tail.record(s2)
+            stream.wait_event(tail)
+        e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1)
 
-    # ---- timed: device-resident
-    ctx.set_profiling(True)
-    ctx.read_profile()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = ctx.launches + ctx2.launches + sum(c.launches for c in extra_ctx)
-    barrier()
-    # CUDA events on the launching streams: the first context's stream opens the region; the closing event is recorded on
-    # the same stream after it has been made to wait for the other context's stream (an event wait, no host sync).
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    others = [torch.cuda.ExternalStream(c.stream, device=f"cuda:{local_rank}") for c in [ctx2] + extra_ctx]
-    gate = torch.cuda.Event()
-    gate.record(stream)
-    for s2 in others:
-        s2.wait_event(gate)           # no context starts before e0
-    e0.record(stream)
-    for k in range(args.steps):
+    # ---- warm-up (both paths)
+    warm = max(args.warmup, 1)   # at least one untimed pass: scratch arenas are sized on first use
+    for k in range(2 * warm):
         step_dev(k)
-    for s2 in others:
-        tail = torch.cuda.Event()
-        tail.record(s2)
-        stream.wait_event(tail)
-    e1.record(stream)
+        step_exchange()
+    run_streaming(max(warm, 2))
     barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = ctx.launches + ctx2.launches + sum(c.launches for c in extra_ctx) - launches0
+    res = ctx.fetch_results(C.c_void_p(dev_lanes[0][1].data_ptr()), B)
+    states = dev_lanes[0][2].cpu().numpy()
+
+    # ---- timed: device-resident
+    sampler.mark = True
+    ctx.set_profiling(True)
+    ctx.read_profile()
+    exchange["ms"].clear()
+    launches0 = sum(c.launches for c in (ctx, ctx2, ctx3))
+    ms_total = timed_device_loop(args.steps)
+    launches = sum(c.launches for c in (ctx, ctx2, ctx3)) - launches0
     profile = ctx.read_profile()
     ctx.set_profiling(False)
-    # ---- timed: end to end (host buffers in, results out)
+    collective_ms = float(np.median(exchange["ms"])) if exchange["ms"] else None
+    # ---- timed: end to end (host buffers in, results out), streaming and blocking
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res_e2e = step_e2e()
-    barrier()
-    e2e_sync_s = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    res_stream = run_streaming(args.steps)
+    res_stream, states_stream = run_streaming(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
-    stream_equal = all(list(a.pose_estimate_local) == list(c.pose_estimate_local) and a.ok == c.ok and
-                       a.num_returns == c.num_returns for a, c in zip(res_stream, res_e2e))
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    sync_steps = max(3, min(args.steps, 20))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(sync_steps):
+        res_e2e, states_e2e, _ = ctx.frontend_match_batch_imu_samples(fo, host_rows, w["origin"], imus[0], w["submap_pose"], hi, lo)
+    barrier()
+    e2e_sync_s = (time.perf_counter() - t0) / sync_steps
+    sampler.mark = False
+    stream_equal = bool(np.array_equal(states_stream, states_e2e) and
+                        all(list(a.pose_estimate_local) == list(c.pose_estimate_local) and a.ok == c.ok and
+                            a.num_returns == c.num_returns for a, c in zip(res_stream, res_e2e)))
+    dev_equal = bool(np.array_equal(states, states_e2e))
     # ---- latency of ONE scan through the blocking call (what a 10 Hz single-trajectory node sees)
     one = dliom.HostScanBatch([host[0, :int(sizes[0])].numpy()])
+    imu_one = dliom.ImuSamples(IMU_NOISE, w["intervals"][:1], w["states_i"][:1], imu_weight=IMU_WEIGHT)
+    fo_one = dliom.FrontendOptions.from_oracle(w["opts"])
+    fo_one.range_row_floats = args.row_floats
     lat = []
     for _ in range(25):
         t1 = time.perf_counter()
-        ctx.frontend_match_batch(fo, one, w["origin"], w["prev"][:1], w["cur"][:1], w["submap_pose"], hi, lo)
+        ctx.frontend_match_batch_imu_samples(fo_one, one, w["origin"], imu_one, w["submap_pose"], hi, lo)
         lat.append((time.perf_counter() - t1) * 1e3)
     single_scan_ms = float(np.median(lat[5:]))
     # ---- the PCIe ceiling of the e2e number: the same pinned bytes copied with nothing else running
@@ -344,10 +430,18 @@ def main():
     torch.cuda.synchronize()
     h2d_gbs = 5 * host.numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9
 
-    t = torch.tensor([ms_total, e2e_s * 1e3, e2e_sync_s * 1e3], dtype=torch.float64, device=f"cuda:{local_rank}")
+    # ---- extra keys (N = 1 only): the same step without the exchange, the plain (no IMU) solve, mode F, configs[2]
+    extras = {}
+    if world == 1 and not args.no_extras:
+        def fetch_lane0():
+            ctx.synchronize()
+            return ctx.fetch_results(C.c_void_p(dev_lanes[0][1].data_ptr()), B)
+        extras = measure_extras(args, w, dliom, ctx, timed_device_loop, fetch_lane0, B)
+
+    t = torch.tensor([ms_total, e2e_s * 1e3, e2e_sync_s * 1e3, collective_ms or 0.0], dtype=torch.float64, device=device)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms_total, e2e_sync_ms_total = float(t[0]), float(t[1]), float(t[2])
+    ms_total, e2e_ms_total, e2e_sync_ms, collective_ms_max = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     ms_step = ms_total / args.steps
     value = world * B / (ms_step / 1e3)
     e2e_value = world * B / (e2e_ms_total / args.steps / 1e3)
@@ -356,19 +450,24 @@ def main():
         # ---- roofline of the dominant stage from the per-stage CUDA-event times (algorithmic bytes)
         n_raw = float(sizes.sum())
         n1 = sum(r.num_first_filter for r in res)
-        n_ret_local = n1  # classify touches every first-filter survivor
         n2 = sum(r.num_returns for r in res)
         evals = sum(r.summary.num_evaluations * (r.num_high_resolution + r.num_low_resolution) for r in res)
         adaptive_bytes = sum(12.0 * (r.num_cropped_high * r.num_passes_high + r.num_cropped_low * r.num_passes_low) +
                              12.0 * (r.num_high_resolution + r.num_low_resolution) for r in res)
         stage_bytes = {
             "voxel_filter_first": 16.0 * n_raw + 16.0 * n1,                          # 16 N_in + 16 N_out
-            "ingest_second_filter": 28.0 * n_ret_local + 12.0 * n1 + 12.0 * n2,      # ingest 28 N + second pass 12 N_in + 12 N_out
+            "ingest_second_filter": 28.0 * n1 + 12.0 * n1 + 12.0 * n2,               # ingest 28 N + second pass 12 N_in + 12 N_out
             "adaptive_voxel_filter": adaptive_bytes,
             "nls_solve": 28.0 * evals,
+            "imu_preintegrate_predict": float(imu_bytes),
         }
-        stages = {k: {"ms_per_step": v[0] / max(v[1], 1), "bytes_per_step": stage_bytes.get(k)} for k, v in profile.items()}
-        dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
+        calls = max(max((v[1] for v in profile.values()), default=1), 1)
+        steps_profiled = max(1, (args.steps + 1) // 2)   # the profiled context runs every other step
+        stages = {}
+        for k, v in profile.items():
+            per_step = v[0] / steps_profiled
+            stages[k] = {"ms_per_step": per_step, "bytes_per_step": stage_bytes.get(k)}
+        dom = max((k for k in stages if stage_bytes.get(k)), key=lambda k: stages[k]["ms_per_step"])
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -384,57 +483,122 @@ def main():
             pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
+                    "units": "achieved = algorithmic bytes of one STEP (148 scans) / the stage's device time per step (CUDA events, "
+                             "summed over the step's sub-batches); traffic = ncu dram bytes of the same stage per STEP",
                     "stages": {k: {"ms_per_step": round(v["ms_per_step"], 4),
                                    "gbps": None if not v["bytes_per_step"] else round(v["bytes_per_step"] / (v["ms_per_step"] * 1e-3) / 1e9, 2)}
-                               for k, v in stages.items()}}
+                               for k, v in stages.items()},
+                    "stages_note": "stage times are per context and overlap across the two contexts / sub-batch streams, so they "
+                                   "sum to more than ms_per_step",
+                    "whole_step_gbps": round(sum(v for v in stage_bytes.values()) / (ms_step * 1e-3) / 1e9, 1)}
 
-        # ---- CPU baseline (oracle) on a bounded sample, and pose parity of the GPU batch against it
+        # ---- CPU baseline (oracle chain) on a bounded sample, and pose parity of the GPU batch against it
         cpu = None
         parity = None
         if world == 1:
-            orc = w["orc"]
             threads = os.cpu_count() or 1
-            sample = args.cpu_sample or min(B, 2 * threads)
-            secs, poses, ok = orc.frontend_batch(w["opts"], w["scans"][:sample], w["origin"], w["prev"][:sample],
-                                                 w["cur"][:sample], w["submap_pose"], w["hi"], w["lo"], threads)
-            secs1, _, _ = orc.frontend_batch(w["opts"], w["scans"][:max(sample // threads, 2)], w["origin"],
-                                             w["prev"], w["cur"], w["submap_pose"], w["hi"], w["lo"], 1)
-            cpu = {"value": sample / secs, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"{sample} of the batch's scans, one scan per host thread ({secs:.2f} s)",
-                   "single_thread_value": max(sample // threads, 2) / secs1}
-            got = np.array([list(res[i].pose_estimate_local) for i in range(sample)])
-            dt, dr = pose_errors(got, poses)
-            parity = {"scans": sample, "rmse_m": float(np.sqrt(np.mean(dt ** 2))), "rmse_rad": float(np.sqrt(np.mean(dr ** 2))),
-                      "max_m": float(dt.max()), "max_rad": float(dr.max()), "all_ok": bool(all(r.ok for r in res))}
+            sample = args.cpu_sample or 8 * threads
+            sel = [i % B for i in range(sample)]
+            cpu_chain(w, sel[:threads], threads)   # spawn the pool
+            runs = [cpu_chain(w, sel, threads) for _ in range(3)]
+            secs = float(np.median([r[0] for r in runs]))
+            one_n = 16
+            secs1 = cpu_chain(w, list(range(one_n)), 1)[0]
+            cpu = {"value": sample / secs, "unit": UNIT, "cores": threads, "physical_cores": physical_cores(), "kind": "port",
+                   "sample": f"{sample} scans ({B} distinct, cycled; {secs:.2f} s, median of 3), persistent pool of {threads} threads "
+                             f"fed from a work queue",
+                   "all_cores": sample / secs, "single_thread": one_n / secs1,
+                   "single_thread_note": "the reference's real mode: one front-end thread, Ceres num_threads = 1"}
+            want = cpu_chain(w, list(range(B)), threads)
+            dt, dr = pose_errors(states, want[1])
+            ok_cpu = want[3]
+            parity = {"scans": B, "distinct_scans": B, "rmse_m": float(np.sqrt(np.mean(dt ** 2))),
+                      "rmse_rad": float(np.sqrt(np.mean(dr ** 2))), "max_m": float(dt.max()), "max_rad": float(dr.max()),
+                      "max_velocity_diff": float(np.abs(states[:, 7:10] - want[1][:, 7:10]).max()),
+                      "max_bias_diff": float(np.abs(states[:, 10:] - want[1][:, 10:]).max()),
+                      "same_iteration_counts": bool(all(r.summary.num_iterations == it for r, it in zip(res, want[4]))),
+                      "all_ok": bool(all(r.ok == 1 for r in res) and all(ok_cpu == 1))}
 
-        h2d = int(sizes.sum() * row_bytes)
-        d2h = int(B * C.sizeof(dliom.ScanResult))
+        h2d = int(sizes.sum() * row_bytes) + imu_bytes
+        d2h = int(B * (C.sizeof(dliom.ScanResult) + 128))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32 (indices, scores) + f64 (least squares)", "data": "synthetic",
+                "vs_baseline": None, "dtype": "f32 (indices, scores) + f64 (pre-integration, least squares)", "data": "synthetic",
                 "config": workload_config(args, B),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms_total / args.steps,
-                        "timing": "wall clock around K x (dl_frontend_submit, dl_frontend_collect) on two alternating contexts: "
-                                  "batch i+1 uploads while batch i computes; all K uploads, solves and result reads inside",
-                        "sync_call": {"value": world * B / (e2e_sync_ms_total / args.steps / 1e3), "ms_per_step": e2e_sync_ms_total / args.steps,
-                                      "note": "one blocking dl_frontend_match_batch per step, nothing overlaps across steps"},
-                        "streaming_equals_sync_results": stream_equal,
+                        "timing": "wall clock around K x (dl_frontend_submit_imu_samples, dl_frontend_collect_imu) on two alternating "
+                                  "contexts + the exchange step: batch i+1 uploads while batch i computes; all K uploads, solves and "
+                                  "result reads inside",
+                        "sync_call": {"value": world * B / e2e_sync_ms * 1e3, "ms_per_step": e2e_sync_ms,
+                                      "note": "one blocking dl_frontend_match_batch_imu_samples per step, nothing overlaps across steps"},
+                        "streaming_equals_sync_results": stream_equal, "device_resident_equals_sync_results": dev_equal,
                         "pcie_h2d_gbs": round(h2d_gbs, 2), "copy_only_ms_per_step": round(h2d / h2d_gbs / 1e6, 3),
                         "pcie_note": "plain pinned cudaMemcpyAsync of the same buffers, measured in this run: the floor of e2e"},
+                "collective": {"name": "ncclAllGather (dl_constraint_search_exchange)", "ranks": world,
+                               "bytes": exchange["bytes"], "rows": exchange["rows"], "ms": collective_ms_max,
+                               "searches_per_rank_per_step": args.pairs, "constraints_found": exchange["found"],
+                               "note": "device time of the all-gather alone (CUDA events), median over the timed steps, max over "
+                                       "ranks; the searches that feed it are inside the step time"},
                 "latency": {"single_scan_ms": round(single_scan_ms, 3),
-                            "note": "median wall time of dl_frontend_match_batch on ONE 64-beam scan (2.1 MB upload, 13 launches, result "
-                                    "download); the CPU path takes 1000 / cpu_baseline.single_thread_value ms"},
+                            "note": "median wall time of dl_frontend_match_batch_imu_samples on ONE 64-beam scan (2.1 MB upload, result "
+                                    "download); the CPU path takes 1000 / cpu_baseline.single_thread ms"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity_vs_cpu": parity,
                 "clocks": sampler.summary()}
+        line.update(extras)
         print(json.dumps(line))
+    sampler.stop_flag = True
+    comm.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
-def dliom_range_dtype():
-    return np.dtype([("x", np.float32), ("y", np.float32), ("z", np.float32), ("t", np.float32),
-                     ("origin_index", np.uint64), ("_pad", np.uint64)])
+def measure_extras(args, w, dliom, ctx, timed_device_loop, fetch_lane0, B):
+    """Secondary measurements at N = 1: each is its own short device-timed loop over the same resident batch."""
+    extras = {}
+    steps = max(10, min(args.steps, 30))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    try:
+        ms = timed_device_loop(steps, with_exchange=False)
+        extras["front_end_only"] = {"value": B / (ms / steps / 1e3), "unit": UNIT, "ms_per_step": ms / steps,
+                                    "note": "the same IMU-coupled step without the loop-closure exchange step"}
+    except Exception as e:   # an extra must never take the headline down with it
+        extras["front_end_only"] = {"error": str(e)}
+    try:
+        # mode F (SURVEY 8d): adaptive filters pass everything through, the matcher sees the whole filtered cloud
+        ff = dliom.FrontendOptions.from_oracle(w["opts"])
+        ff.range_row_floats = args.row_floats
+        ff.high_resolution_adaptive_voxel_filter.min_num_points = 1e9
+        ff.low_resolution_adaptive_voxel_filter.min_num_points = 1e9
+        timed_device_loop(2, ff, with_exchange=False)
+        ctx.set_profiling(True)
+        ctx.read_profile()
+        k = 6
+        msf = timed_device_loop(k, ff, with_exchange=False)
+        prof = ctx.read_profile()
+        ctx.set_profiling(False)
+        res = fetch_lane0()
+        pts = sum(r.num_high_resolution + r.num_low_resolution for r in res)
+        evals = sum(r.summary.num_evaluations * (r.num_high_resolution + r.num_low_resolution) for r in res)
+        nls_ms = prof.get("nls_solve", (0.0, 0))[0] / (k / 2)
+        achieved = 28.0 * evals / (nls_ms * 1e-3) / 1e9 if nls_ms > 0 else None
+        extras["mode_F"] = {"value": B / (msf / k / 1e3), "unit": UNIT, "ms_per_step": msf / k,
+                            "matcher_points_per_scan": pts / B, "evaluations_per_scan": sum(r.summary.num_evaluations for r in res) / B,
+                            "stages_ms_per_step": {n: round(v[0] / (k / 2), 4) for n, v in prof.items()},
+                            "roofline": {"bound": "hbm", "kernel": "nls_fused_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                                         "frac": None if achieved is None else achieved / peak, "traffic": None,
+                                         "bytes_model": "28 B per point per evaluation (12 B point + 8 corners x 2 B), SURVEY 8d"},
+                            "all_ok": bool(all(r.ok == 1 for r in res)),
+                            "note": "full-cloud mode: adaptive filters pass-through (min_num_points = 1e9), the fused solve sees every "
+                                    "point of the second voxel filter's output"}
+    except Exception as e:
+        extras["mode_F"] = {"error": str(e)}
+    return extras
 
 
 if __name__ == "__main__":
