@@ -1746,32 +1746,22 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
     imu_run->d_fused = d_fused;
     imu_run->d_states = d_states_out;
   }
+  int32_t* d_off = nullptr;
+  double *d_dt = nullptr, *d_acc = nullptr, *d_gyr = nullptr;
+  dl_nav_state *d_si = nullptr, *d_pred = nullptr;
+  dl_preintegration* d_pre = nullptr;
+  size_t ns = 0;
   if (raw) {
-    // Raw samples: pre-integration, prediction, deskew constants, factor and information matrix all on the device; the
-    // only host work is the upload of the samples and of the states at the previous scans.
-    StageScope st(ctx, "imu_preintegrate_predict");
-    const size_t ns = (size_t)raw->offsets[num_scans];
-    int32_t* d_off = a.take<int32_t>(num_scans + 1);
-    double* d_dt = a.take<double>(ns);
-    double* d_acc = a.take<double>(3 * ns);
-    double* d_gyr = a.take<double>(3 * ns);
-    dl_nav_state* d_si = a.take<dl_nav_state>(num_scans);
-    dl_preintegration* d_pre = a.take<dl_preintegration>(num_scans);
-    dl_nav_state* d_pred = a.take<dl_nav_state>(num_scans);
+    ns = (size_t)raw->offsets[num_scans];
+    d_off = a.take<int32_t>(num_scans + 1);
+    d_dt = a.take<double>(ns);
+    d_acc = a.take<double>(3 * ns);
+    d_gyr = a.take<double>(3 * ns);
+    d_si = a.take<dl_nav_state>(num_scans);
+    d_pre = a.take<dl_preintegration>(num_scans);
+    d_pred = a.take<dl_nav_state>(num_scans);
     d_imu_ok = a.take<int32_t>(num_scans);
     imu_run->d_predicted = d_pred;
-    DL_TRY(h2d(ctx, d_off, raw->offsets, (size_t)num_scans + 1));
-    DL_TRY(h2d(ctx, d_dt, raw->dt, ns));
-    DL_TRY(h2d(ctx, d_acc, raw->acc, 3 * ns));
-    DL_TRY(h2d(ctx, d_gyr, raw->gyr, 3 * ns));
-    DL_TRY(h2d(ctx, d_si, raw->states_i, (size_t)num_scans));
-    DL_TRY(launch_imu_preintegrate(ctx, num_scans, d_off, d_dt, d_acc, d_gyr, (const double*)d_si + 10, 16, raw->noise, d_pre));
-    ImuPrepareArgs pa{};
-    pa.count = num_scans; pa.preint = d_pre; pa.states_i = d_si; pa.to_submap = inverse(pose_from7(submap_local_pose));
-    for (int k = 0; k < 3; ++k) pa.gravity[k] = raw->gravity[k];
-    pa.imu_weight = raw->imu_weight; pa.scans = f.scans; pa.terms = d_terms; pa.init16 = d_init16; pa.predicted = d_pred;
-    pa.ok = d_imu_ok;
-    DL_TRY(launch_imu_prepare(ctx, pa));
   }
   if (imu) {
     std::vector<HostImuTerm> terms(num_scans);
@@ -1811,6 +1801,33 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
   DL_CUDA(ctx, cudaStreamWaitEvent(ctx->tail_stream, prepared, 0));
   if (host_ranges) DL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, prepared, 0));  // the upload target may be in use
   ctx->event_pool.push_back(prepared);
+  cudaEvent_t imu_ready = nullptr;
+  if (raw) {
+    // Raw samples: pre-integration, prediction, deskew constants, factor and information matrix all on the device; the
+    // only host work is the upload of the samples and of the states at the previous scans. The chain runs on its own
+    // stream next to the first voxel filter (which needs none of it); the ingest kernels wait for `imu_ready`.
+    ctx->stream = ctx->tail_stream;
+    auto chain = [&]() -> int {
+      StageScope st(ctx, "imu_preintegrate_predict");
+      DL_TRY(h2d(ctx, d_off, raw->offsets, (size_t)num_scans + 1));
+      DL_TRY(h2d(ctx, d_dt, raw->dt, ns));
+      DL_TRY(h2d(ctx, d_acc, raw->acc, 3 * ns));
+      DL_TRY(h2d(ctx, d_gyr, raw->gyr, 3 * ns));
+      DL_TRY(h2d(ctx, d_si, raw->states_i, (size_t)num_scans));
+      DL_TRY(launch_imu_preintegrate(ctx, num_scans, d_off, d_dt, d_acc, d_gyr, (const double*)d_si + 10, 16, raw->noise, d_pre));
+      ImuPrepareArgs pa{};
+      pa.count = num_scans; pa.preint = d_pre; pa.states_i = d_si; pa.to_submap = inverse(pose_from7(submap_local_pose));
+      for (int k = 0; k < 3; ++k) pa.gravity[k] = raw->gravity[k];
+      pa.imu_weight = raw->imu_weight; pa.scans = f.scans; pa.terms = d_terms; pa.init16 = d_init16; pa.predicted = d_pred;
+      pa.ok = d_imu_ok;
+      return launch_imu_prepare(ctx, pa);
+    };
+    const int st_imu = chain();
+    ctx->stream = main_stream;
+    DL_TRY(st_imu);
+    imu_ready = ctx->take_event();
+    DL_CUDA(ctx, cudaEventRecord(imu_ready, ctx->tail_stream));  // recycled once every sub-batch's wait is enqueued
+  }
   std::vector<float> rtcsm_scores;
   bool have_scores = false;
   int status = DL_OK;
@@ -1859,6 +1876,7 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
         }
         DL_TRY(launch_fe_first_filter(ctx, fa, b0, nb));
       }
+      if (imu_ready) DL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, imu_ready, 0));
       {
         StageScope st(ctx, "ingest_second_filter");
         DL_TRY(launch_fe_rest(ctx, fa, b0, nb));
@@ -1925,6 +1943,7 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
     status = run();
   }
   ctx->stream = main_stream;
+  if (imu_ready) ctx->event_pool.push_back(imu_ready);
   if (chunks > 1 || split) {  // later work on the main stream (result copies, the next call) waits for the other streams
     cudaEvent_t joined = ctx->take_event();
     DL_CUDA(ctx, cudaEventRecord(joined, split ? ctx->tail_stream : ctx->aux_stream));

@@ -251,27 +251,64 @@ __device__ __forceinline__ void block_dims(const FcsmPair& pr, int* bx, int* by,
   *bz = (2 * pr.wz + 1 + kSub - 1) / kSub;
 }
 
-// bound of every 8^3 block of the window: sum over points of the sliding maximum at the block's first offset
+// bound of every 8^3 block of the window: sum over points of the sliding maximum at the block's first offset.
+// One WARP per block: the lanes split the points (integer sum: order-independent), so the dependent byte gathers of a block
+// run 32 wide instead of one after the other (round 1: one thread per block, 93 us for 8 pairs).
 __global__ void __launch_bounds__(128) fcsm_bounds_kernel(const FcsmPair* __restrict__ pairs, int* __restrict__ bounds, int stride,
                                                           int* __restrict__ max_bound) {
   const FcsmPair& pr = pairs[blockIdx.y];
   int bx, by, bz;
   block_dims(pr, &bx, &by, &bz);
   const int blocks = bx * by * bz;
-  const int b = blockIdx.x * 128 + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (b >= blocks) return;  // warp-uniform
+  const int ox = -pr.wxy + kSub * (b % bx), oy = -pr.wxy + kSub * ((b / bx) % by), oz = -pr.wz + kSub * (b / (bx * by));
   int sum = 0;
-  if (b < blocks) {
-    const int ox = -pr.wxy + kSub * (b % bx), oy = -pr.wxy + kSub * ((b / bx) % by), oz = -pr.wz + kSub * (b / (bx * by));
-    for (int i = 0; i < pr.n_hi; ++i) {
-      const int x = pr.cells[3 * i] + ox - pr.m8_org[0], y = pr.cells[3 * i + 1] + oy - pr.m8_org[1], z = pr.cells[3 * i + 2] + oz - pr.m8_org[2];
-      if ((unsigned)x < (unsigned)pr.m8_dim[0] && (unsigned)y < (unsigned)pr.m8_dim[1] && (unsigned)z < (unsigned)pr.m8_dim[2])
-        sum += __ldg(pr.m8 + ((size_t)z * pr.m8_dim[1] + y) * pr.m8_dim[0] + x);
-    }
-    bounds[(size_t)blockIdx.y * stride + b] = sum;
+  for (int i = lane; i < pr.n_hi; i += 32) {
+    const int x = pr.cells[3 * i] + ox - pr.m8_org[0], y = pr.cells[3 * i + 1] + oy - pr.m8_org[1], z = pr.cells[3 * i + 2] + oz - pr.m8_org[2];
+    if ((unsigned)x < (unsigned)pr.m8_dim[0] && (unsigned)y < (unsigned)pr.m8_dim[1] && (unsigned)z < (unsigned)pr.m8_dim[2])
+      sum += __ldg(pr.m8 + ((size_t)z * pr.m8_dim[1] + y) * pr.m8_dim[0] + x);
   }
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) sum = max(sum, __shfl_xor_sync(0xffffffffu, sum, d));
-  if ((threadIdx.x & 31) == 0 && sum > 0) atomicMax(max_bound + blockIdx.y, sum);
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  if (lane == 0) {
+    bounds[(size_t)blockIdx.y * stride + b] = sum;
+    if (sum > 0) atomicMax(max_bound + blockIdx.y, sum);
+  }
+}
+
+// Low-resolution gate of ONE candidate leaf, evaluated by the whole CTA (low_resolution_matcher.cc:24-36): the threads gather the
+// probabilities of the rotated low-resolution points in parallel (the three-level walks are the expensive part), then thread 0
+// adds them up in point order, which is what keeps the float sum bit-identical to the reference's sequential loop.
+// prob: shared scratch of kTile floats. Returns (to every thread) whether the leaf passes.
+template <int THREADS>
+__device__ bool low_resolution_gate(const FcsmPair& pr, const Vec3f& t, float* prob, float* low_out) {
+  __shared__ float acc_s;
+  __shared__ int pass_s;
+  if (threadIdx.x == 0) acc_s = 0.f;
+  for (int base = 0; base < pr.n_lo; base += kTile) {
+    const int count = min(kTile, pr.n_lo - base);
+    __syncthreads();
+    for (int j = threadIdx.x; j < count; j += THREADS) {
+      const float* r = pr.lo_rot + 3 * (size_t)(base + j);
+      const Int3 c = cell_index(add(Vec3f{r[0], r[1], r[2]}, t), pr.lo.resolution);
+      prob[j] = value_to_probability(grid_value(pr.lo, c.x, c.y, c.z));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float acc = acc_s;
+      for (int j = 0; j < count; ++j) acc += prob[j];
+      acc_s = acc;
+    }
+  }
+  if (threadIdx.x == 0) {
+    const float low = acc_s / (float)pr.n_lo;
+    *low_out = low;
+    pass_s = (double)low >= pr.min_low ? 1 : 0;
+  }
+  __syncthreads();
+  return pass_s != 0;
 }
 
 // One CTA (64 threads) per (block, pair): thread = one (y, z) offset of the block with its 8 x offsets. round 0 opens the
@@ -336,57 +373,63 @@ __global__ void __launch_bounds__(64) fcsm_block_kernel(const FcsmPair* __restri
         }
       }
   }
-  float score[kRun];
-  unsigned cand = 0;
-  // a leaf below the best passing leaf found so far cannot win (an equal one still can, on the index): skip its gate
-  const unsigned long long seen = *reinterpret_cast<volatile const unsigned long long*>(best + blockIdx.y);
-  const float seen_score = seen ? __uint_as_float((unsigned)(seen >> 32)) : -1.f;
+  // Candidate leaves of this block, best first: (score bits << 32 | ~index), the same key `best` is maximised with. Only the
+  // best candidate that PASSES the low-resolution gate can win, so the CTA walks its candidates in descending key order,
+  // evaluates the gate cooperatively (low_resolution_gate) and stops at the first pass — or as soon as the remaining keys
+  // are below the best leaf any CTA has published. Round 1 ran the gate inside each thread, serially per candidate
+  // (~150 us per leaf of three-level walks): the dominant cost of the whole search.
+  __shared__ unsigned long long cand[64 * kRun];
+  __shared__ unsigned long long pick_s;
+  __syncthreads();  // everyone is done with `tile`
 #pragma unroll
   for (int k = 0; k < kRun; ++k) {
-    score[k] = sum_to_score(sum[k], pr.n_hi);
-    if (active && ox0 + k <= pr.wxy && score[k] > pr.min_score && score[k] >= seen_score) cand |= 1u << k;
-  }
-  float low[kRun] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  float* ftile = reinterpret_cast<float*>(tile);
-  if (!__syncthreads_or(cand != 0)) return;
-  for (int base = 0; base < pr.n_lo; base += kTile) {
-    const int count = min(kTile, pr.n_lo - base);
-    __syncthreads();
-    for (int j = threadIdx.x; j < count * 3; j += 64) ftile[j] = pr.lo_rot[base * 3 + j];
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < kRun; ++k) {
-      if (!(cand >> k & 1)) continue;
-      const Vec3f t = candidate_pose(pr.pose, pr.hi.resolution, ox0 + k, oy, oz).t;
-      float acc = low[k];
-      for (int j = 0; j < count; ++j) {
-        const Int3 c = cell_index(add(Vec3f{ftile[3 * j], ftile[3 * j + 1], ftile[3 * j + 2]}, t), pr.lo.resolution);
-        acc += value_to_probability(grid_value(pr.lo, c.x, c.y, c.z));
-      }
-      low[k] = acc;
+    const float sc = sum_to_score(sum[k], pr.n_hi);
+    unsigned long long key = 0ull;
+    if (active && ox0 + k <= pr.wxy && sc > pr.min_score) {
+      const unsigned long long idx = ((unsigned long long)(oz + pr.wz) * side + (oy + pr.wxy)) * side + (ox0 + k + pr.wxy);
+      key = ((unsigned long long)__float_as_uint(sc) << 32) | (0xFFFFFFFFull - idx);
     }
+    cand[threadIdx.x * kRun + k] = key;
   }
-  unsigned long long packed = 0ull;
+  float* prob = reinterpret_cast<float*>(tile);
+  for (;;) {
+    __syncthreads();
+    unsigned long long m = 0ull;
+    for (int e = threadIdx.x; e < 64 * kRun; e += 64) m = cand[e] > m ? cand[e] : m;
 #pragma unroll
-  for (int k = 0; k < kRun; ++k) {
-    if (!(cand >> k & 1) || !((double)(low[k] / (float)pr.n_lo) >= pr.min_low)) continue;
-    const unsigned long long idx = ((unsigned long long)(oz + pr.wz) * side + (oy + pr.wxy)) * side + (ox0 + k + pr.wxy);
-    const unsigned long long p = ((unsigned long long)__float_as_uint(score[k]) << 32) | (0xFFFFFFFFull - idx);
-    packed = p > packed ? p : packed;
+    for (int d = 16; d > 0; d >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, m, d);
+      m = o > m ? o : m;
+    }
+    if (threadIdx.x == 0) pick_s = 0ull;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&pick_s, m);
+    __syncthreads();
+    const unsigned long long key = pick_s;
+    if (!key) return;
+    const unsigned long long seen = *reinterpret_cast<volatile const unsigned long long*>(best + blockIdx.y);
+    if (key < seen) return;  // keys are unique per leaf: everything left in this block loses to a published leaf
+    const long long idx = (long long)(0xFFFFFFFFull - (key & 0xFFFFFFFFull));
+    const int lx = (int)(idx % side) - pr.wxy, ly = (int)((idx / side) % side) - pr.wxy, lz = (int)(idx / ((long long)side * side)) - pr.wz;
+    const Vec3f t = candidate_pose(pr.pose, pr.hi.resolution, lx, ly, lz).t;
+    float low;
+    if (low_resolution_gate<64>(pr, t, prob, &low)) {
+      if (threadIdx.x == 0) atomicMax(best + blockIdx.y, key);
+      return;
+    }
+    // rejected by the gate: drop it and try the next best
+    for (int e = threadIdx.x; e < 64 * kRun; e += 64)
+      if (cand[e] == key) cand[e] = 0ull;
   }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    const unsigned long long o = __shfl_xor_sync(0xffffffffu, packed, d);
-    packed = o > packed ? o : packed;
-  }
-  if ((threadIdx.x & 31) == 0 && packed) atomicMax(best + blockIdx.y, packed);
 }
 
 // Decode the winner of each pair: Result{score, pose_estimate, rotational_score, low_resolution_score} (cc:186-195) and the
-// switch + initial pose the refinement kernel reads.
-__global__ void fcsm_finish_kernel(const FcsmPair* __restrict__ pairs, const unsigned long long* __restrict__ best, int count,
-                                   FcsmPick* __restrict__ picks) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+// switch + initial pose the refinement kernel reads. One CTA per pair; the winner's low-resolution score is recomputed with
+// the cooperative gate (parallel gathers, sequential float sum) — round 1 walked the cloud with one thread per pair (262 us).
+__global__ void __launch_bounds__(128) fcsm_finish_kernel(const FcsmPair* __restrict__ pairs, const unsigned long long* __restrict__ best,
+                                                          int count, FcsmPick* __restrict__ picks) {
+  __shared__ float prob[kTile];
+  const int p = blockIdx.x;
   if (p >= count) return;
   const FcsmPair& pr = pairs[p];
   FcsmPick out{};
@@ -394,7 +437,7 @@ __global__ void fcsm_finish_kernel(const FcsmPair* __restrict__ pairs, const uns
   out.num_candidates = (long long)side * side * (2 * pr.wz + 1);
   const unsigned long long b = best[p];
   Rigidf pose = pr.pose;
-  if (b) {
+  if (b) {  // block-uniform
     const long long idx = (long long)(0xFFFFFFFFull - (b & 0xFFFFFFFFull));
     out.found = 1;
     out.score = __uint_as_float((unsigned)(b >> 32));
@@ -402,15 +445,15 @@ __global__ void fcsm_finish_kernel(const FcsmPair* __restrict__ pairs, const uns
     out.offset[1] = (int)((idx / side) % side) - pr.wxy;
     out.offset[2] = (int)(idx / ((long long)side * side)) - pr.wz;
     pose = candidate_pose(pr.pose, pr.hi.resolution, out.offset[0], out.offset[1], out.offset[2]);
-    float low = 0.f;
-    for (int j = 0; j < pr.n_lo; ++j) {
-      const Int3 c = cell_index(add(Vec3f{pr.lo_rot[3 * j], pr.lo_rot[3 * j + 1], pr.lo_rot[3 * j + 2]}, pose.t), pr.lo.resolution);
-      low += value_to_probability(grid_value(pr.lo, c.x, c.y, c.z));
-    }
-    out.low_resolution_score = low / (float)pr.n_lo;
+    __shared__ float low_s;
+    low_resolution_gate<128>(pr, pose.t, prob, &low_s);
+    __syncthreads();
+    out.low_resolution_score = low_s;
   }
-  pose_to7(to_double(pose), out.pose);
-  picks[p] = out;
+  if (threadIdx.x == 0) {
+    pose_to7(to_double(pose), out.pose);
+    picks[p] = out;
+  }
 }
 
 }  // namespace
@@ -446,14 +489,14 @@ int launch_fcsm_pruned(dl_context* ctx, const FcsmPair* pairs_dev, int count, in
   DL_CUDA(ctx, cudaMemsetAsync(max_bound_dev, 0, sizeof(int) * count, ctx->stream));
   fcsm_prepare_kernel<<<dim3((max_points + 255) / 256, count), 256, 0, ctx->stream>>>(pairs_dev);
   DL_LAUNCH_CHECK(ctx, "fcsm_prepare_kernel");
-  fcsm_bounds_kernel<<<dim3((max_blocks + 127) / 128, count), 128, 0, ctx->stream>>>(pairs_dev, bounds_dev, max_blocks, max_bound_dev);
+  fcsm_bounds_kernel<<<dim3((max_blocks + 3) / 4, count), 128, 0, ctx->stream>>>(pairs_dev, bounds_dev, max_blocks, max_bound_dev);
   DL_LAUNCH_CHECK(ctx, "fcsm_bounds_kernel");
   for (int round = 0; round < 2; ++round) {
     fcsm_block_kernel<<<dim3(max_blocks, count), 64, 0, ctx->stream>>>(pairs_dev, bounds_dev, max_blocks, max_bound_dev, best_dev,
                                                                        ctx->d_fcsm_lut, round);
     DL_LAUNCH_CHECK(ctx, "fcsm_block_kernel");
   }
-  fcsm_finish_kernel<<<(count + 63) / 64, 64, 0, ctx->stream>>>(pairs_dev, best_dev, count, picks_dev);
+  fcsm_finish_kernel<<<count, 128, 0, ctx->stream>>>(pairs_dev, best_dev, count, picks_dev);
   DL_LAUNCH_CHECK(ctx, "fcsm_finish_kernel");
   return DL_OK;
 }
@@ -499,7 +542,7 @@ int launch_fcsm(dl_context* ctx, const FcsmPair* pairs_dev, int count, int max_p
   fcsm_search_kernel<<<dim3((unsigned)((max_threads + kBlock - 1) / kBlock), count), kBlock, 0, ctx->stream>>>(pairs_dev, best_dev,
                                                                                                            all_scores_dev, ctx->d_fcsm_lut);
   DL_LAUNCH_CHECK(ctx, "fcsm_search_kernel");
-  fcsm_finish_kernel<<<(count + 63) / 64, 64, 0, ctx->stream>>>(pairs_dev, best_dev, count, picks_dev);
+  fcsm_finish_kernel<<<count, 128, 0, ctx->stream>>>(pairs_dev, best_dev, count, picks_dev);
   DL_LAUNCH_CHECK(ctx, "fcsm_finish_kernel");
   return DL_OK;
 }

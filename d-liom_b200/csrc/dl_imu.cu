@@ -16,6 +16,7 @@ constexpr int kWarpsPerBlock = 4;
 
 struct WarpState {
   double J[225], P[225], F[225], T[225], V[270];
+  double R0[3][3], R1[3][3], IRw[3][3], R0a0[3][3], R1a1[3][3], R1a1I[3][3];  // 3x3 building blocks of F and V
 };
 
 __device__ __forceinline__ void rotation_matrix(const Quatd& q, double R[3][3]) {  // Eigen toRotationMatrix
@@ -77,47 +78,52 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) imu_preintegrate_kernel(
     const Vec3d un_acc = mul(0.5, add(un_acc_0, un_acc_1));
     const Vec3d rp = add(add(dp, mul(dt, dv)), mul(0.5 * dt * dt, un_acc));
     const Vec3d rv = add(dv, mul(dt, un_acc));
-    if (lane == 0) {  // F and V of this step (integration_base.h:176-232)
-      double Rw[3][3], Ra0[3][3], Ra1[3][3], R0[3][3], R1[3][3], IRw[3][3], R0a0[3][3], R1a1[3][3], R1a1I[3][3];
+    // F and V of this step (integration_base.h:176-232): lane 0 forms the 3x3 building blocks, every lane clears its share
+    // of the two matrices, then lanes 0..8 each write the entries of one (i, j) position of the blocks.
+    if (lane == 0) {
+      double Rw[3][3], Ra0[3][3], Ra1[3][3];
       skew(un_gyr, Rw); skew(sub(acc_0, ba), Ra0); skew(sub(acc_1, ba), Ra1);
-      rotation_matrix(dq, R0);
-      rotation_matrix(rq, R1);
+      rotation_matrix(dq, st.R0);
+      rotation_matrix(rq, st.R1);
       for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) IRw[i][j] = (i == j ? 1.0 : 0.0) - Rw[i][j] * dt;
-      mul33(R0, Ra0, R0a0);
-      mul33(R1, Ra1, R1a1);
-      mul33(R1a1, IRw, R1a1I);
-      for (int e = 0; e < 225; ++e) st.F[e] = 0.0;
-      for (int e = 0; e < 270; ++e) st.V[e] = 0.0;
-      for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-          const double id = i == j ? 1.0 : 0.0;
-          st.F[i * 15 + j] = id;
-          st.F[i * 15 + 3 + j] = -0.25 * R0a0[i][j] * dt * dt + -0.25 * R1a1I[i][j] * dt * dt;
-          st.F[i * 15 + 6 + j] = id * dt;
-          st.F[i * 15 + 9 + j] = -0.25 * (R0[i][j] + R1[i][j]) * dt * dt;
-          st.F[i * 15 + 12 + j] = -0.25 * R1a1[i][j] * dt * dt * -dt;
-          st.F[(3 + i) * 15 + 3 + j] = IRw[i][j];
-          st.F[(3 + i) * 15 + 12 + j] = -1.0 * id * dt;
-          st.F[(6 + i) * 15 + 3 + j] = -0.5 * R0a0[i][j] * dt - 0.5 * R1a1I[i][j] * dt;
-          st.F[(6 + i) * 15 + 6 + j] = id;
-          st.F[(6 + i) * 15 + 9 + j] = -0.5 * (R0[i][j] + R1[i][j]) * dt;
-          st.F[(6 + i) * 15 + 12 + j] = -0.5 * R1a1[i][j] * dt * -dt;
-          st.F[(9 + i) * 15 + 9 + j] = id;
-          st.F[(12 + i) * 15 + 12 + j] = id;
-          st.V[i * 18 + j] = 0.25 * R0[i][j] * dt * dt;
-          st.V[i * 18 + 3 + j] = 0.25 * -R1a1[i][j] * dt * dt * 0.5 * dt;
-          st.V[i * 18 + 6 + j] = 0.25 * R1[i][j] * dt * dt;
-          st.V[i * 18 + 9 + j] = st.V[i * 18 + 3 + j];
-          st.V[(3 + i) * 18 + 3 + j] = 0.5 * id * dt;
-          st.V[(3 + i) * 18 + 9 + j] = 0.5 * id * dt;
-          st.V[(6 + i) * 18 + j] = 0.5 * R0[i][j] * dt;
-          st.V[(6 + i) * 18 + 3 + j] = 0.5 * -R1a1[i][j] * dt * 0.5 * dt;
-          st.V[(6 + i) * 18 + 6 + j] = 0.5 * R1[i][j] * dt;
-          st.V[(6 + i) * 18 + 9 + j] = st.V[(6 + i) * 18 + 3 + j];
-          st.V[(9 + i) * 18 + 12 + j] = id * dt;
-          st.V[(12 + i) * 18 + 15 + j] = id * dt;
-        }
+        for (int j = 0; j < 3; ++j) st.IRw[i][j] = (i == j ? 1.0 : 0.0) - Rw[i][j] * dt;
+      mul33(st.R0, Ra0, st.R0a0);
+      mul33(st.R1, Ra1, st.R1a1);
+      mul33(st.R1a1, st.IRw, st.R1a1I);
+    }
+    for (int e = lane; e < 225; e += 32) st.F[e] = 0.0;
+    for (int e = lane; e < 270; e += 32) st.V[e] = 0.0;
+    __syncwarp();
+    if (lane < 9) {
+      const int i = lane / 3, j = lane % 3;
+      const double id = i == j ? 1.0 : 0.0;
+      const double R0 = st.R0[i][j], R1 = st.R1[i][j], R0a0 = st.R0a0[i][j], R1a1 = st.R1a1[i][j], R1a1I = st.R1a1I[i][j];
+      st.F[i * 15 + j] = id;
+      st.F[i * 15 + 3 + j] = -0.25 * R0a0 * dt * dt + -0.25 * R1a1I * dt * dt;
+      st.F[i * 15 + 6 + j] = id * dt;
+      st.F[i * 15 + 9 + j] = -0.25 * (R0 + R1) * dt * dt;
+      st.F[i * 15 + 12 + j] = -0.25 * R1a1 * dt * dt * -dt;
+      st.F[(3 + i) * 15 + 3 + j] = st.IRw[i][j];
+      st.F[(3 + i) * 15 + 12 + j] = -1.0 * id * dt;
+      st.F[(6 + i) * 15 + 3 + j] = -0.5 * R0a0 * dt - 0.5 * R1a1I * dt;
+      st.F[(6 + i) * 15 + 6 + j] = id;
+      st.F[(6 + i) * 15 + 9 + j] = -0.5 * (R0 + R1) * dt;
+      st.F[(6 + i) * 15 + 12 + j] = -0.5 * R1a1 * dt * -dt;
+      st.F[(9 + i) * 15 + 9 + j] = id;
+      st.F[(12 + i) * 15 + 12 + j] = id;
+      const double v03 = 0.25 * -R1a1 * dt * dt * 0.5 * dt, v63 = 0.5 * -R1a1 * dt * 0.5 * dt;
+      st.V[i * 18 + j] = 0.25 * R0 * dt * dt;
+      st.V[i * 18 + 3 + j] = v03;
+      st.V[i * 18 + 6 + j] = 0.25 * R1 * dt * dt;
+      st.V[i * 18 + 9 + j] = v03;
+      st.V[(3 + i) * 18 + 3 + j] = 0.5 * id * dt;
+      st.V[(3 + i) * 18 + 9 + j] = 0.5 * id * dt;
+      st.V[(6 + i) * 18 + j] = 0.5 * R0 * dt;
+      st.V[(6 + i) * 18 + 3 + j] = v63;
+      st.V[(6 + i) * 18 + 6 + j] = 0.5 * R1 * dt;
+      st.V[(6 + i) * 18 + 9 + j] = v63;
+      st.V[(9 + i) * 18 + 12 + j] = id * dt;
+      st.V[(12 + i) * 18 + 15 + j] = id * dt;
     }
     __syncwarp();
     // T = F * J ; then J = T
