@@ -613,13 +613,14 @@ int dl_adaptive_voxel_filter(dl_context* ctx, const dl_adaptive_voxel_filter_opt
   if (n > 0x7fffffff) return ctx->fail(DL_ERR_ARG, "more than 2^31-1 points");
   DL_CUDA(ctx, cudaSetDevice(ctx->device));
   const int64_t tcap = next_pow2(2 * n);
-  DL_TRY(ctx->reserve_device(arena_bytes({(size_t)n * stride * 4, (size_t)tcap * 4, (size_t)n * 8, (size_t)n * 4, 64,
-                                          sizeof(AdaptiveParams), 32 * 4, 64})));
+  DL_TRY(ctx->reserve_device(arena_bytes({(size_t)n * stride * 4, (size_t)tcap * 4, (size_t)n * 8, (size_t)n * 4,
+                                          adaptive_first_pass_bytes(1, n), 64, sizeof(AdaptiveParams), 32 * 4, 64})));
   Arena a(ctx->d_scratch);
   float* d_pts = a.take<float>(n * stride);
   uint32_t* d_table = a.take<uint32_t>(tcap);
   uint32_t* d_scratch = a.take<uint32_t>(2 * n);
   int32_t* d_keep = a.take<int32_t>(n);
+  uint8_t* d_first = a.take<uint8_t>(adaptive_first_pass_bytes(1, n));
   int32_t* d_counts = a.take<int32_t>(3);  // n, survivors, passes
   AdaptiveParams* d_params = a.take<AdaptiveParams>(1);
   float* d_passes = a.take<float>(32);
@@ -629,7 +630,7 @@ int dl_adaptive_voxel_filter(dl_context* ctx, const dl_adaptive_voxel_filter_opt
   DL_TRY(h2d(ctx, d_counts, &n32, 1));
   DL_TRY(h2d(ctx, d_params, &params, 1));
   DL_TRY(launch_adaptive_voxel_filter(ctx, d_pts, stride, n, d_counts, 1, d_params, 1, d_table, tcap, d_scratch, d_keep,
-                                      d_counts + 1, d_passes, d_counts + 2, nullptr));
+                                      d_counts + 1, d_passes, d_counts + 2, nullptr, d_first));
   int32_t res[2] = {0, 0};
   float passes[32];
   DL_TRY(d2h(ctx, res, d_counts + 1, 2));
@@ -1549,6 +1550,7 @@ struct FrontendBuffers {
   float* back_pose;
   uint8_t* win;
   float* local4;
+  uint8_t* adaptive_first;  // scratch of the adaptive filters' grid-wide first pass (dl_voxel.cu)
   ScanConstants* scans;
   AdaptiveParams* filters;
   double *initial_pose, *target;
@@ -1556,20 +1558,25 @@ struct FrontendBuffers {
   NlsOutput* nls_out;
 };
 
-size_t frontend_bytes(int batch, int64_t cap, int num_origins, size_t extra) {
+// Device scratch of one front-end run. The stage-wise buffers (one voxel-filter pass per launch: dl_voxel.cu / dl_ingest.cu)
+// exist only for dl_ingest_scan, which cross-checks the fused front half against them; the batched path does not carve them
+// (round 1 did: ~150 B x cap x batch of dead scratch per context).
+size_t frontend_bytes(int batch, int64_t cap, int num_origins, size_t extra, bool stagewise = false) {
   const size_t B = (size_t)batch, C = (size_t)cap;
   const size_t tcap = (size_t)next_pow2(2 * cap);
   const size_t tiles = (C + 255) / 256;
-  return arena_bytes({B * 4, B * 4, B * 4, B * 4, B * 4, B * 4, B * 8, B * 8, B * 8, B * tiles * 4, B * tiles * 8,
-                      B * tcap * 4, B * C * 4, B * 2 * tcap * 4, B * 4 * C * 4,
-                      B * C * 4, B * C * 4, B * C * 4, B * 2 * C * 4,
-                      B * C * 12, B * C * 12, B * C * 12, B * C * 12, B * C * 12, B * 2 * C * 12, B * 28, (size_t)num_origins * 12,
-                      B * 2 * 32 * 4, B * 4, B * C, B * sizeof(ScanConstants), 2 * sizeof(AdaptiveParams), B * 56, B * 24,
-                      B * sizeof(NlsProblem), B * sizeof(NlsOutput),
-                      B * (size_t)next_pow2(cap) * 8, B * (size_t)next_pow2(cap) * 4, B * 4, 64, B * 28, B * C, B * C * 16}) + extra + 8192;
+  size_t bytes = arena_bytes({B * 4, B * 4, B * 4, B * 4, B * 4, B * 4, B * 8, B * 8, B * 8, B * tiles * 8,
+                              B * tcap * 4, B * 2 * tcap * 4, B * 4 * C * 4, B * 2 * C * 4,
+                              B * C * 12, B * C * 12, B * 2 * C * 12, B * 28, (size_t)num_origins * 12,
+                              B * 2 * 32 * 4, B * 4, B * sizeof(ScanConstants), 2 * sizeof(AdaptiveParams), B * 56, B * 24,
+                              B * sizeof(NlsProblem), B * sizeof(NlsOutput),
+                              B * (size_t)next_pow2(cap) * 8, B * (size_t)next_pow2(cap) * 4, B * 4, 64, B * 28, B * C, B * C * 16,
+                              adaptive_first_pass_bytes(2 * batch, cap) + 16 * 1024});
+  if (stagewise) bytes += arena_bytes({B * tiles * 4, B * C * 4, B * C * 4, B * C * 4, B * C * 4, B * C * 12, B * C * 12, B * C * 12, B * C});
+  return bytes + extra + 8192;
 }
 
-void carve(Arena& a, int batch, int64_t cap, int num_origins, FrontendBuffers* f) {
+void carve(Arena& a, int batch, int64_t cap, int num_origins, FrontendBuffers* f, bool stagewise = false) {
   const size_t B = (size_t)batch, C = (size_t)cap;
   f->batch = batch;
   f->cap = cap;
@@ -1578,16 +1585,13 @@ void carve(Arena& a, int batch, int64_t cap, int num_origins, FrontendBuffers* f
   f->counts0 = a.take<int32_t>(B); f->n1 = a.take<int32_t>(B); f->n_ret = a.take<int32_t>(B); f->n_miss = a.take<int32_t>(B);
   f->n2 = a.take<int32_t>(B); f->n3 = a.take<int32_t>(B); f->countsA = a.take<int32_t>(2 * B); f->npassesA = a.take<int32_t>(2 * B);
   f->croppedA = a.take<int32_t>(2 * B);
-  f->block_counts = a.take<int32_t>(B * f->tiles); f->tile_counts = a.take<int32_t>(B * f->tiles * 2);
-  f->table = a.take<uint32_t>(B * f->tcap); f->slot = a.take<uint32_t>(B * C);
+  f->tile_counts = a.take<int32_t>(B * f->tiles * 2);
+  f->table = a.take<uint32_t>(B * f->tcap);
   f->tableA = a.take<uint32_t>(B * 2 * f->tcap); f->scratchA = a.take<uint32_t>(B * 4 * C);
-  f->keep1 = a.take<int32_t>(B * C); f->keep2 = a.take<int32_t>(B * C); f->keep3 = a.take<int32_t>(B * C);
   f->keepA = a.take<int32_t>(B * 2 * C);
-  f->tmp_points = a.take<float>(B * C * 3); f->returns_local = a.take<float>(B * C * 3); f->misses_local = a.take<float>(B * C * 3);
   f->returns_tracking = a.take<float>(B * C * 3); f->misses_tracking = a.take<float>(B * C * 3);
   f->clouds = a.take<float>(B * 2 * C * 3); f->current_pose = a.take<float>(B * 7); f->origins = a.take<float>((size_t)num_origins * 3);
   f->passesA = a.take<float>(B * 2 * 32); f->rtcsm_scores = a.take<float>(B);
-  f->cls = a.take<uint8_t>(B * C);
   f->scans = a.take<ScanConstants>(B); f->filters = a.take<AdaptiveParams>(2);
   f->initial_pose = a.take<double>(B * 7); f->target = a.take<double>(B * 3);
   f->problems = a.take<NlsProblem>(B); f->nls_out = a.take<NlsOutput>(B);
@@ -1597,6 +1601,16 @@ void carve(Arena& a, int batch, int64_t cap, int num_origins, FrontendBuffers* f
   f->back_pose = a.take<float>(B * 7);
   f->win = a.take<uint8_t>(B * C);
   f->local4 = a.take<float>(B * C * 4);
+  f->adaptive_first = a.take<uint8_t>(adaptive_first_pass_bytes(2 * batch, cap) + 16 * 1024);
+  f->block_counts = nullptr; f->slot = nullptr; f->keep1 = f->keep2 = f->keep3 = nullptr;
+  f->tmp_points = f->returns_local = f->misses_local = nullptr; f->cls = nullptr;
+  if (stagewise) {
+    f->block_counts = a.take<int32_t>(B * f->tiles);
+    f->slot = a.take<uint32_t>(B * C);
+    f->keep1 = a.take<int32_t>(B * C); f->keep2 = a.take<int32_t>(B * C); f->keep3 = a.take<int32_t>(B * C);
+    f->tmp_points = a.take<float>(B * C * 3); f->returns_local = a.take<float>(B * C * 3); f->misses_local = a.take<float>(B * C * 3);
+    f->cls = a.take<uint8_t>(B * C);
+  }
 }
 
 FrontendArgs make_frontend_args(const dl_frontend_options& o, const FrontendBuffers& f, const float* d_ranges,
@@ -1894,7 +1908,8 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
         DL_TRY(launch_adaptive_voxel_filter(ctx, f.returns_tracking + (size_t)b0 * f.cap * 3, 3, f.cap, f.n2 + b0, nb, f.filters, 2,
                                             f.tableA + (size_t)2 * b0 * f.tcap, f.tcap, f.scratchA + (size_t)4 * b0 * f.cap,
                                             f.keepA + (size_t)2 * b0 * f.cap, f.countsA + 2 * b0, f.passesA + 64 * b0,
-                                            f.npassesA + 2 * b0, f.croppedA + 2 * b0));
+                                            f.npassesA + 2 * b0, f.croppedA + 2 * b0,
+                                            f.adaptive_first + adaptive_first_pass_bytes(2 * b0, f.cap) + (size_t)k * 1024));
       }
       DL_TRY(launch_gather_rows(ctx, f.returns_tracking + (size_t)b0 * f.cap * 3, f.cap, 2, f.keepA + (size_t)2 * b0 * f.cap,
                                 f.countsA + 2 * b0, f.cap, f.clouds + (size_t)2 * b0 * f.cap * 3, 2 * nb));
@@ -2280,12 +2295,12 @@ int dl_ingest_scan(dl_context* ctx, const dl_frontend_options* options, const vo
       !counts_out)
     return DL_ERR_ARG;
   DL_CUDA(ctx, cudaSetDevice(ctx->device));
-  DL_TRY(ctx->reserve_device(frontend_bytes(1, n, num_origins, 0) + (size_t)n * 32 + 256));
+  DL_TRY(ctx->reserve_device(frontend_bytes(1, n, num_origins, 0, true) + (size_t)n * 32 + 256));
   Arena a(ctx->d_scratch);
   float* d_ranges = a.take<float>((size_t)n * 8);
   DL_TRY(h2d(ctx, d_ranges, (const float*)ranges, (size_t)n * 8));
   FrontendBuffers f;
-  carve(a, 1, n, num_origins, &f);
+  carve(a, 1, n, num_origins, &f, true);
   if (row_floats_of(*options) != 8) return ctx->fail(DL_ERR_ARG, "dl_ingest_scan takes RangeMeasurement rows (range_row_floats = 8)");
   DL_TRY(frontend_upload_small(ctx, *options, f, &n, origins, num_origins, prev_pose, predicted_pose, nullptr, nullptr));
   // stage-wise kernels (first_keep, returns_local) ...

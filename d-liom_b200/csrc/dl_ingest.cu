@@ -8,6 +8,8 @@
 // composition with the previous state in double, narrowing to float exactly where the reference narrows) and
 // applies it. Survivors are compacted in input order, because the voxel filter that follows keeps the FIRST point
 // of every voxel. Algorithmic traffic: 16 B in + 12 B out per point.
+#include <algorithm>
+
 #include "dl_internal.cuh"
 #include "dl_pipeline.cuh"
 
@@ -168,11 +170,13 @@ __global__ void __launch_bounds__(kBlock) gather_rows_kernel(const float* __rest
                                                              int64_t cap_out, float* __restrict__ out) {
   const int pair = blockIdx.y;
   const int b = pair / pairs_per_cloud;
-  const int j = blockIdx.x * kBlock + threadIdx.x;
-  if (j >= keep_counts[pair]) return;
-  const float* p = in + ((size_t)b * cap_in + keep[(size_t)pair * cap_in + j]) * 3;
-  float* o = out + ((size_t)pair * cap_out + j) * 3;
-  o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+  const int count = keep_counts[pair];
+  // grid-stride: the survivors are a few hundred rows, so a handful of CTAs per cloud replaces one per 256 rows of capacity
+  for (int j = blockIdx.x * kBlock + threadIdx.x; j < count; j += gridDim.x * kBlock) {
+    const float* p = in + ((size_t)b * cap_in + keep[(size_t)pair * cap_in + j]) * 3;
+    float* o = out + ((size_t)pair * cap_out + j) * 3;
+    o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+  }
 }
 
 // initial_ceres_pose = submap.local_pose^-1 * pose_prediction, pose_prediction = current_pose.cast<double>() (LTB:476-487, :504-505)
@@ -248,7 +252,7 @@ int launch_gather_to_tracking(dl_context* ctx, const float* in, int64_t cap, con
 int launch_gather_rows(dl_context* ctx, const float* in, int64_t cap_in, int pairs_per_cloud, const int32_t* keep,
                        const int32_t* keep_counts, int64_t cap_out, float* out, int pairs) {
   if (pairs <= 0) return DL_OK;
-  const dim3 grid((unsigned)((cap_out + kBlock - 1) / kBlock), pairs);
+  const dim3 grid((unsigned)std::min<int64_t>((cap_out + kBlock - 1) / kBlock, 8), pairs);
   gather_rows_kernel<<<grid, kBlock, 0, ctx->stream>>>(in, cap_in, pairs_per_cloud, keep, keep_counts, cap_out, out);
   DL_LAUNCH_CHECK(ctx, "gather_rows_kernel");
   return DL_OK;

@@ -190,7 +190,9 @@ int launch_adaptive_voxel_filter(dl_context* ctx, const float* points, int strid
                                  int batch, const AdaptiveParams* filters_dev, int num_filters, uint32_t* table,
                                  int64_t table_cap, uint32_t* scratch /* pairs * 2 * cap */, int32_t* keep, int32_t* keep_counts,
                                  float* passes /* (batch*num_filters) * 32 */, int32_t* num_passes,
-                                 int32_t* cropped_counts /* optional, batch*num_filters */);
+                                 int32_t* cropped_counts /* optional, batch*num_filters */,
+                                 void* first_pass_scratch /* optional, adaptive_first_pass_bytes(batch * num_filters, cap) */);
+size_t adaptive_first_pass_bytes(int pairs, int64_t cap);
 
 struct RtcsmLaunch {
   const float* points;  // n x 3

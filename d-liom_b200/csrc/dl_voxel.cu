@@ -11,6 +11,9 @@
 //
 // HBM traffic per pass (algorithmic): read stride*4 B per point, write 4 B per survivor. The table (8 B per
 // point) lives in L2. Compile with -fmad=false: index = lroundf(x / resolution) must match the CPU bit for bit.
+#include <algorithm>
+#include <cstdlib>
+
 #include "dl_internal.cuh"
 
 namespace dl {
@@ -323,11 +326,12 @@ __global__ void __launch_bounds__(kAdaptiveBlock) adaptive_voxel_kernel(
     const float* __restrict__ points, int stride, int64_t cap, const int32_t* __restrict__ counts,
     const AdaptiveParams* __restrict__ filters, int num_filters, uint32_t* table, int64_t table_cap,
     uint32_t* scratch /* per pair: cap cropped rows + cap slots */, int32_t* keep, int32_t* keep_counts,
-    float* passes, int32_t* num_passes, int32_t* cropped_counts) {
+    float* passes, int32_t* num_passes, int32_t* cropped_counts, const int32_t* __restrict__ need) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastTable& fast = *reinterpret_cast<FastTable*>(smem_raw);
   __shared__ int fail_flag;
   const int pair = blockIdx.x;
+  if (need && need[4 * pair] == 0) return;  // EdgeMeta::need of this pair: the grid-wide first pass already produced its result
   const int b = pair / num_filters;
   const AdaptiveParams opt = filters[pair % num_filters];
   const int n = counts[b];
@@ -474,6 +478,165 @@ __global__ void __launch_bounds__(kAdaptiveBlock) adaptive_voxel_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------- adaptive filter, common case
+// In the front end the FIRST pass of the search (edge = max_length) almost always yields >= min_num_points voxels: the result
+// is then simply the voxel filter at max_length of the range-cropped cloud. That case needs no bisection and no single-CTA
+// sequencing, so it runs grid-wide for every (cloud, filter) pair of the batch: crop + insert (packed 63-bit key, min index),
+// mark the winners, count per tile, prefix per pair, ordered scatter. adaptive_voxel_kernel (one CTA per pair, whole
+// search) then runs only for the pairs whose first pass fell short, whose table overflowed or whose keys do not pack.
+// Round 1 ran every pair through the single CTA: 190 us per 74 scans, mostly barrier latency of its 1024-id compaction rounds.
+constexpr int kEdgeSlots = 8192;  // slots of the first-pass table per pair (keys 8 B + min index 4 B)
+struct EdgeMeta {
+  int32_t cropped, voxels, fail, need;
+};
+__device__ __forceinline__ unsigned long long* edge_keys(uint32_t* table, int64_t table_cap, int pair) {
+  return reinterpret_cast<unsigned long long*>(table + (size_t)pair * table_cap);
+}
+__device__ __forceinline__ uint32_t* edge_mins(uint32_t* table, int64_t table_cap, int pair) {
+  return table + (size_t)pair * table_cap + 2 * kEdgeSlots;
+}
+
+__global__ void __launch_bounds__(kBlock) adaptive_first_insert_kernel(const float* __restrict__ points, int stride, int64_t cap,
+                                                                       const int32_t* __restrict__ counts,
+                                                                       const AdaptiveParams* __restrict__ filters, int num_filters,
+                                                                       uint32_t* table, int64_t table_cap, uint8_t* win, EdgeMeta* meta) {
+  const int pair = blockIdx.y, b = pair / num_filters;
+  const AdaptiveParams opt = filters[pair % num_filters];
+  const int n = counts[b];
+  const float* pts = points + (size_t)b * cap * stride;
+  unsigned long long* keys = edge_keys(table, table_cap, pair);
+  uint32_t* mins = edge_mins(table, table_cap, pair);
+  uint8_t* w = win + (size_t)pair * cap;
+  const CellDivider edge = make_divider(opt.max_length);
+  int cropped = 0;
+  for (int base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock) {
+    const int i = base + threadIdx.x;
+    bool in = false;
+    Vec3f p{0.f, 0.f, 0.f};
+    if (i < n) {
+      const float* q = pts + (size_t)i * stride;
+      p = {q[0], q[1], q[2]};
+      in = norm3(p) <= opt.max_range;  // FilterByMaxRange (voxel_filter.cc:28-38)
+      w[i] = in ? 2 : 0;
+    }
+    cropped += in;
+    if (in) {
+      unsigned long long key;
+      if (!pack_cell(cell_index(p, edge), &key)) {
+        meta[pair].fail = 1;
+      } else {
+        uint32_t h = hash_key(key) & (kEdgeSlots - 1);
+        int probes = 0;
+        for (;;) {
+          const unsigned long long prev = atomicCAS(keys + h, kEmptyKey, key);
+          if (prev == kEmptyKey || prev == key) {
+            atomicMin(mins + h, (uint32_t)i);
+            break;
+          }
+          h = (h + 1) & (kEdgeSlots - 1);
+          if (++probes >= kEdgeSlots) {
+            meta[pair].fail = 1;
+            break;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) cropped += __shfl_xor_sync(0xffffffffu, cropped, d);
+  if ((threadIdx.x & 31) == 0 && cropped) atomicAdd(&meta[pair].cropped, cropped);
+}
+
+__global__ void __launch_bounds__(kBlock) adaptive_first_mark_kernel(uint32_t* table, int64_t table_cap, int64_t cap, uint8_t* win,
+                                                                     EdgeMeta* meta) {
+  const int pair = blockIdx.y;
+  const uint32_t* mins = edge_mins(table, table_cap, pair);
+  const int h = blockIdx.x * kBlock + threadIdx.x;
+  const uint32_t m = __ldcg(mins + h);
+  const bool used = m != kEmpty;
+  if (used) win[(size_t)pair * cap + m] = 3;  // cropped + owner of its voxel; one writer per point
+  const int c = __syncthreads_count(used);
+  if (threadIdx.x == 0 && c) atomicAdd(&meta[pair].voxels, c);
+}
+
+// 1 = keep. Decided per pair from the finished counts: sparse enough already -> every cropped point; first pass sufficient ->
+// the voxel owners; otherwise nothing here (the single-CTA search takes over).
+__device__ __forceinline__ int edge_mode(const EdgeMeta& m, const AdaptiveParams& opt) {
+  if (m.fail) return 0;
+  if ((float)m.cropped <= opt.min_num_points) return 2;
+  if ((float)m.voxels >= opt.min_num_points) return 1;
+  return 0;
+}
+
+__global__ void __launch_bounds__(kBlock) adaptive_first_count_kernel(const int32_t* __restrict__ counts,
+                                                                      const AdaptiveParams* __restrict__ filters, int num_filters,
+                                                                      int64_t cap, const uint8_t* __restrict__ win,
+                                                                      const EdgeMeta* __restrict__ meta, int32_t* tile_counts, int tiles) {
+  const int pair = blockIdx.y, b = pair / num_filters;
+  const int n = counts[b];
+  if ((int)blockIdx.x * kBlock >= n) return;
+  const int mode = edge_mode(meta[pair], filters[pair % num_filters]);
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  const int wv = i < n ? win[(size_t)pair * cap + i] : 0;
+  const int c = __syncthreads_count(mode && (wv & mode) != 0);
+  if (threadIdx.x == 0) tile_counts[(size_t)pair * tiles + blockIdx.x] = c;
+}
+
+// One CTA per pair: exclusive prefix of the tile counts (in place) and the pair's bookkeeping.
+__global__ void __launch_bounds__(kBlock) adaptive_first_prefix_kernel(const int32_t* __restrict__ counts,
+                                                                       const AdaptiveParams* __restrict__ filters, int num_filters,
+                                                                       EdgeMeta* meta, int32_t* tile_counts, int tiles,
+                                                                       int32_t* keep_counts, float* passes, int32_t* num_passes,
+                                                                       int32_t* cropped_counts) {
+  const int pair = blockIdx.x, b = pair / num_filters;
+  const AdaptiveParams opt = filters[pair % num_filters];
+  const int n = counts[b];
+  const int mode = edge_mode(meta[pair], opt);
+  if (mode == 0) {  // falls through to adaptive_voxel_kernel, which writes all of this pair's outputs
+    if (threadIdx.x == 0) meta[pair].need = 1;
+    return;
+  }
+  const int my_tiles = (n + kBlock - 1) / kBlock;
+  int32_t* tc = tile_counts + (size_t)pair * tiles;
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < my_tiles; base += kBlock) {
+    const int t = base + threadIdx.x;
+    const int v = t < my_tiles ? tc[t] : 0;
+    int total;
+    const int ex = block_exclusive_scan(v, &total);
+    if (t < my_tiles) tc[t] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    meta[pair].need = 0;
+    keep_counts[pair] = carry;
+    num_passes[pair] = mode == 2 ? 0 : 1;
+    if (mode == 1) passes[(size_t)pair * 32] = opt.max_length;
+    if (cropped_counts) cropped_counts[pair] = meta[pair].cropped;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) adaptive_first_scatter_kernel(const int32_t* __restrict__ counts,
+                                                                        const AdaptiveParams* __restrict__ filters, int num_filters,
+                                                                        int64_t cap, const uint8_t* __restrict__ win,
+                                                                        const EdgeMeta* __restrict__ meta,
+                                                                        const int32_t* __restrict__ tile_counts, int tiles, int32_t* keep) {
+  const int pair = blockIdx.y, b = pair / num_filters;
+  const int n = counts[b];
+  if ((int)blockIdx.x * kBlock >= n || meta[pair].need) return;
+  const int mode = edge_mode(meta[pair], filters[pair % num_filters]);
+  const int i = blockIdx.x * kBlock + threadIdx.x;
+  const int wv = i < n ? win[(size_t)pair * cap + i] : 0;
+  const int flag = (wv & mode) != 0;
+  int total;
+  const int off = block_exclusive_scan(flag, &total);
+  if (flag) keep[(size_t)pair * cap + tile_counts[(size_t)pair * tiles + blockIdx.x] + off] = i;
+}
+
 }  // namespace
 
 int launch_voxel_filter(dl_context* ctx, const float* points, int stride, int64_t cap, const int32_t* counts, int batch,
@@ -500,15 +663,50 @@ int launch_voxel_indices(dl_context* ctx, const float* points, int stride, int64
   return DL_OK;
 }
 
+size_t adaptive_first_pass_bytes(int pairs, int64_t cap) {
+  const size_t tiles = (size_t)((cap + kBlock - 1) / kBlock);
+  return (((size_t)pairs * cap + 255) & ~size_t(255)) + (size_t)pairs * tiles * 4 + (size_t)pairs * sizeof(EdgeMeta) + 256;
+}
+
 int launch_adaptive_voxel_filter(dl_context* ctx, const float* points, int stride, int64_t cap, const int32_t* counts,
                                  int batch, const AdaptiveParams* filters_dev, int num_filters, uint32_t* table,
                                  int64_t table_cap, uint32_t* scratch, int32_t* keep, int32_t* keep_counts,
-                                 float* passes, int32_t* num_passes, int32_t* cropped_counts) {
+                                 float* passes, int32_t* num_passes, int32_t* cropped_counts, void* first_pass_scratch) {
   if (batch <= 0 || num_filters <= 0) return DL_OK;
+  const int pairs = batch * num_filters;
+  const int tiles = (int)((cap + kBlock - 1) / kBlock);
+  // The grid-wide first pass keeps its keys + min indices in the head of each pair's table region (the single-CTA search only
+  // touches that region afterwards, for its own pair) and its winner bytes, tile counts and bookkeeping in first_pass_scratch
+  // (adaptive_first_pass_bytes). Tables too small for it (tiny clouds) go straight to the single-CTA search.
+  const bool first_pass = first_pass_scratch && (size_t)table_cap * 4 >= (size_t)kEdgeSlots * 12 && !std::getenv("DLIOM_ADAPTIVE_SINGLE_CTA");
+  const int32_t* need = nullptr;
+  if (first_pass) {
+    uint8_t* win = reinterpret_cast<uint8_t*>(first_pass_scratch);                        // pairs * cap bytes
+    int32_t* tile_counts = reinterpret_cast<int32_t*>(win + (((size_t)pairs * cap + 255) & ~size_t(255)));  // pairs * tiles
+    EdgeMeta* meta = reinterpret_cast<EdgeMeta*>(tile_counts + (size_t)pairs * tiles);
+    DL_CUDA(ctx, cudaMemset2DAsync(table, (size_t)table_cap * 4, 0xFF, (size_t)kEdgeSlots * 12, (size_t)pairs, ctx->stream));
+    DL_CUDA(ctx, cudaMemsetAsync(meta, 0, sizeof(EdgeMeta) * pairs, ctx->stream));
+    const int insert_tiles = std::min(tiles, 96);
+    adaptive_first_insert_kernel<<<dim3(insert_tiles, pairs), kBlock, 0, ctx->stream>>>(points, stride, cap, counts, filters_dev,
+                                                                                         num_filters, table, table_cap, win, meta);
+    DL_LAUNCH_CHECK(ctx, "adaptive_first_insert_kernel");
+    adaptive_first_mark_kernel<<<dim3(kEdgeSlots / kBlock, pairs), kBlock, 0, ctx->stream>>>(table, table_cap, cap, win, meta);
+    DL_LAUNCH_CHECK(ctx, "adaptive_first_mark_kernel");
+    adaptive_first_count_kernel<<<dim3(tiles, pairs), kBlock, 0, ctx->stream>>>(counts, filters_dev, num_filters, cap, win, meta,
+                                                                                 tile_counts, tiles);
+    DL_LAUNCH_CHECK(ctx, "adaptive_first_count_kernel");
+    adaptive_first_prefix_kernel<<<pairs, kBlock, 0, ctx->stream>>>(counts, filters_dev, num_filters, meta, tile_counts, tiles,
+                                                                    keep_counts, passes, num_passes, cropped_counts);
+    DL_LAUNCH_CHECK(ctx, "adaptive_first_prefix_kernel");
+    adaptive_first_scatter_kernel<<<dim3(tiles, pairs), kBlock, 0, ctx->stream>>>(counts, filters_dev, num_filters, cap, win, meta,
+                                                                                   tile_counts, tiles, keep);
+    DL_LAUNCH_CHECK(ctx, "adaptive_first_scatter_kernel");
+    need = &meta->need;  // stride sizeof(EdgeMeta): see the kernel's indexing below
+  }
   DL_CUDA(ctx, cudaFuncSetAttribute(adaptive_voxel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastTable)));
-  adaptive_voxel_kernel<<<batch * num_filters, kAdaptiveBlock, sizeof(FastTable), ctx->stream>>>(
+  adaptive_voxel_kernel<<<pairs, kAdaptiveBlock, sizeof(FastTable), ctx->stream>>>(
       points, stride, cap, counts, filters_dev, num_filters, table, table_cap, scratch, keep, keep_counts, passes,
-      num_passes, cropped_counts);
+      num_passes, cropped_counts, need);
   DL_LAUNCH_CHECK(ctx, "adaptive_voxel_kernel");
   return DL_OK;
 }
