@@ -173,6 +173,8 @@ void dl_context_destroy(dl_context* ctx) {
   if (ctx->tail_stream) cudaStreamDestroy(ctx->tail_stream);
   if (ctx->batch_done) cudaEventDestroy(ctx->batch_done);
   if (ctx->d_fcsm_lut) cudaFree(ctx->d_fcsm_lut);
+  if (ctx->h_adaptive_stats) cudaFreeHost(ctx->h_adaptive_stats);
+  if (ctx->d_adaptive_stats) cudaFree(ctx->d_adaptive_stats);
   if (ctx->staging_done) cudaEventDestroy(ctx->staging_done);
   delete ctx;
 }

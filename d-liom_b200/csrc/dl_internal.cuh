@@ -52,6 +52,11 @@ struct dl_context {
   cudaStream_t tail_stream = nullptr;   // high priority: the latency-bound back half (adaptive filter, LM solve) of every sub-batch
   cudaEvent_t staging_done = nullptr;   // the pinned staging block of the previous call has been consumed
   cudaEvent_t batch_done = nullptr;     // dl_frontend_submit: everything of the batch in flight, incl. the result download
+  // adaptive voxel filter: how many (cloud, filter) pairs of the last probed launch needed the single-CTA search
+  // ([0] pairs that fell through, [1] pairs probed); pinned host copy of a device counter, read without synchronising
+  int32_t* h_adaptive_stats = nullptr;
+  int32_t* d_adaptive_stats = nullptr;
+  int64_t adaptive_calls = 0;
   uint8_t* d_fcsm_lut = nullptr;        // loop-closure search: cell value -> 8-bit precomputation value (dl_fcsm.cu), built on first use
   int in_flight = 0;                    // scans of the submitted, not yet collected batch
   bool in_flight_states = false;        // ... and whether it also stages the estimated IMU states

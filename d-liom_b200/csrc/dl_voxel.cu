@@ -587,11 +587,15 @@ __global__ void __launch_bounds__(kBlock) adaptive_first_prefix_kernel(const int
                                                                        const AdaptiveParams* __restrict__ filters, int num_filters,
                                                                        EdgeMeta* meta, int32_t* tile_counts, int tiles,
                                                                        int32_t* keep_counts, float* passes, int32_t* num_passes,
-                                                                       int32_t* cropped_counts) {
+                                                                       int32_t* cropped_counts, int32_t* stats) {
   const int pair = blockIdx.x, b = pair / num_filters;
   const AdaptiveParams opt = filters[pair % num_filters];
   const int n = counts[b];
   const int mode = edge_mode(meta[pair], opt);
+  if (threadIdx.x == 0 && stats) {
+    atomicAdd(stats + 1, 1);
+    if (mode == 0) atomicAdd(stats, 1);
+  }
   if (mode == 0) {  // falls through to adaptive_voxel_kernel, which writes all of this pair's outputs
     if (threadIdx.x == 0) meta[pair].need = 1;
     return;
@@ -678,7 +682,26 @@ int launch_adaptive_voxel_filter(dl_context* ctx, const float* points, int strid
   // The grid-wide first pass keeps its keys + min indices in the head of each pair's table region (the single-CTA search only
   // touches that region afterwards, for its own pair) and its winner bytes, tile counts and bookkeeping in first_pass_scratch
   // (adaptive_first_pass_bytes). Tables too small for it (tiny clouds) go straight to the single-CTA search.
-  const bool first_pass = first_pass_scratch && (size_t)table_cap * 4 >= (size_t)kEdgeSlots * 12 && !std::getenv("DLIOM_ADAPTIVE_SINGLE_CTA");
+  bool first_pass = first_pass_scratch && (size_t)table_cap * 4 >= (size_t)kEdgeSlots * 12 && !std::getenv("DLIOM_ADAPTIVE_SINGLE_CTA");
+  // Self-tuning: the grid-wide pass only pays when the first edge usually suffices. The share of pairs that fell through to the
+  // single-CTA search in the last probed launch is read from a pinned counter (no synchronisation: a stale or half-updated
+  // value only changes which of two exact paths runs); when most pairs fall through, skip the pass and re-probe every 16th call.
+  if (first_pass && !ctx->h_adaptive_stats) {
+    if (cudaMallocHost((void**)&ctx->h_adaptive_stats, 2 * sizeof(int32_t)) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->d_adaptive_stats, 2 * sizeof(int32_t)) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->h_adaptive_stats = nullptr;
+    } else {
+      ctx->h_adaptive_stats[0] = ctx->h_adaptive_stats[1] = 0;
+    }
+  }
+  int32_t* stats = nullptr;
+  if (first_pass && ctx->h_adaptive_stats) {
+    const int32_t fell = ctx->h_adaptive_stats[0], probed = ctx->h_adaptive_stats[1];
+    const bool probe = (ctx->adaptive_calls++ % 16) == 0;
+    if (!probe && probed > 0 && 2 * fell > probed) first_pass = false;
+    if (first_pass && probe) stats = ctx->d_adaptive_stats;
+  }
   const int32_t* need = nullptr;
   if (first_pass) {
     uint8_t* win = reinterpret_cast<uint8_t*>(first_pass_scratch);                        // pairs * cap bytes
@@ -686,6 +709,7 @@ int launch_adaptive_voxel_filter(dl_context* ctx, const float* points, int strid
     EdgeMeta* meta = reinterpret_cast<EdgeMeta*>(tile_counts + (size_t)pairs * tiles);
     DL_CUDA(ctx, cudaMemset2DAsync(table, (size_t)table_cap * 4, 0xFF, (size_t)kEdgeSlots * 12, (size_t)pairs, ctx->stream));
     DL_CUDA(ctx, cudaMemsetAsync(meta, 0, sizeof(EdgeMeta) * pairs, ctx->stream));
+    if (stats) DL_CUDA(ctx, cudaMemsetAsync(stats, 0, 2 * sizeof(int32_t), ctx->stream));
     const int insert_tiles = std::min(tiles, 96);
     adaptive_first_insert_kernel<<<dim3(insert_tiles, pairs), kBlock, 0, ctx->stream>>>(points, stride, cap, counts, filters_dev,
                                                                                          num_filters, table, table_cap, win, meta);
@@ -696,8 +720,10 @@ int launch_adaptive_voxel_filter(dl_context* ctx, const float* points, int strid
                                                                                  tile_counts, tiles);
     DL_LAUNCH_CHECK(ctx, "adaptive_first_count_kernel");
     adaptive_first_prefix_kernel<<<pairs, kBlock, 0, ctx->stream>>>(counts, filters_dev, num_filters, meta, tile_counts, tiles,
-                                                                    keep_counts, passes, num_passes, cropped_counts);
+                                                                    keep_counts, passes, num_passes, cropped_counts, stats);
     DL_LAUNCH_CHECK(ctx, "adaptive_first_prefix_kernel");
+    if (stats)
+      DL_CUDA(ctx, cudaMemcpyAsync(ctx->h_adaptive_stats, stats, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     adaptive_first_scatter_kernel<<<dim3(tiles, pairs), kBlock, 0, ctx->stream>>>(counts, filters_dev, num_filters, cap, win, meta,
                                                                                    tile_counts, tiles, keep);
     DL_LAUNCH_CHECK(ctx, "adaptive_first_scatter_kernel");
