@@ -99,7 +99,7 @@ int ensure_capacity(dl_context* ctx, T** ptr, size_t* cap, size_t need) {
 template <typename T>
 int realloc_pool(dl_context* ctx, T** ptr, size_t* cap, size_t need, size_t used, int fill) {
   if (need <= *cap) return DL_OK;
-  const size_t want = std::max(need + need / 2 + 512, 2 * *cap);
+  const size_t want = need + need / 4 + 16 * 512;  // exact need + 25 % headroom (the callers count what they add)
   T* fresh = nullptr;
   DL_CUDA(ctx, cudaMalloc((void**)&fresh, want * sizeof(T)));
   DL_CUDA(ctx, cudaMemsetAsync(fresh, fill, want * sizeof(T), ctx->stream));
@@ -361,7 +361,7 @@ int dl_grid_sync(dl_grid* g) {
   DL_CUDA(ctx, cudaSetDevice(ctx->device));
   if (g->mirror_stale) return ctx->fail(DL_ERR_ARG, "internal: host mirror is behind the device grid");
   const size_t nbricks = g->bricks.size() / 512;
-  if (!g->d_counters) DL_CUDA(ctx, cudaMalloc((void**)&g->d_counters, 4 * sizeof(int32_t)));
+  if (!g->d_counters) DL_CUDA(ctx, cudaMalloc((void**)&g->d_counters, 8 * sizeof(int32_t)));
   if (g->structure_dirty) {
     if (g->top.size() > g->d_top_cap) {
       if (g->d_top) { DL_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); DL_CUDA(ctx, cudaFree(g->d_top)); }
@@ -386,8 +386,8 @@ int dl_grid_sync(dl_grid* g) {
     DL_TRY(h2d(ctx, g->d_bricks + b * 512, g->bricks.data() + b * 512, (e - b) * 512));
     b = e;
   }
-  const int32_t counters[4] = {(int32_t)(g->nodes.size() / 512), (int32_t)nbricks, 0, 0};
-  DL_TRY(h2d(ctx, g->d_counters, counters, 4));
+  const int32_t counters[8] = {(int32_t)(g->nodes.size() / 512), (int32_t)nbricks, 0, 0, 0, 0, 0, 0};
+  DL_TRY(h2d(ctx, g->d_counters, counters, 8));
   return sync(ctx);
 }
 
@@ -429,14 +429,17 @@ int grid_ensure_device_state(dl_grid* g) {
   for (size_t b = 0; b < g->brick_dirty.size() && !dirty; ++b) dirty = g->brick_dirty[b] != 0;
   return dirty ? dl_grid_sync(g) : DL_OK;
 }
-int grid_reserve_pools(dl_grid* g, size_t add_nodes, size_t add_bricks) {
+// Grows the node pool (level 0) or the brick pool (level 1) by exactly the number of entries the running Insert marked
+// (counters[pending_counter], written by ins_claim_kernel<level, 0>).
+int grid_reserve_pools(dl_grid* g, int pending_counter, int level) {
   dl_context* ctx = g->ctx;
-  int32_t counters[2] = {0, 0};
-  DL_TRY(d2h(ctx, counters, g->d_counters, 2));
+  int32_t counters[5] = {0, 0, 0, 0, 0};
+  DL_TRY(d2h(ctx, counters, g->d_counters, 5));
   DL_TRY(sync(ctx));
-  DL_TRY(realloc_pool(ctx, &g->d_nodes, &g->d_nodes_cap, ((size_t)counters[0] + add_nodes) * 512, (size_t)counters[0] * 512, 0xFF));
-  DL_TRY(realloc_pool(ctx, &g->d_bricks, &g->d_bricks_cap, ((size_t)counters[1] + add_bricks) * 512, (size_t)counters[1] * 512, 0));
-  return DL_OK;
+  const size_t add = (size_t)counters[pending_counter];
+  if (level == 0)
+    return realloc_pool(ctx, &g->d_nodes, &g->d_nodes_cap, ((size_t)counters[0] + add) * 512, (size_t)counters[0] * 512, 0xFF);
+  return realloc_pool(ctx, &g->d_bricks, &g->d_bricks_cap, ((size_t)counters[1] + add) * 512, (size_t)counters[1] * 512, 0);
 }
 }  // namespace dl
 
@@ -701,39 +704,102 @@ void build_rtcsm_tables(const dl_rtcsm_options& opt, float resolution, float max
       }
 }
 
-// Runs the search for a cloud already on the device. Leaves the best pose in pose_out.
+// One batched correlative search. Clouds are on the device: cloud k = points[k] with counts[k] rows (host-known). The tables
+// of every scan (R rotations, L translations, their penalties) are built on the host with the reference's float operations
+// — the angular window depends on each cloud's farthest point through acosf, which must be the host's to stay bit-exact —
+// and go up in ONE copy; one launch scores all (scan, rotation, translation) candidates.
+struct RtcsmBatchItem {
+  const float* d_points;
+  int64_t n;
+  Rigidd initial;
+  float max_scan_range;
+  float* d_scores;  // optional
+};
+struct RtcsmBatchPlan {
+  std::vector<RtcsmTables> tables;
+  RtcsmScan* d_scans = nullptr;
+  unsigned long long* d_best = nullptr;
+};
+int rtcsm_batch_device(dl_context* ctx, const dl_rtcsm_options& opt, const dl_grid* grid, const std::vector<RtcsmBatchItem>& items,
+                       Arena& a, RtcsmBatchPlan* plan) {
+  const int B = (int)items.size();
+  if (B == 0) return DL_OK;
+  plan->tables.resize(B);
+  size_t blob = 0;
+  auto align16 = [](size_t v) { return (v + 15) & ~size_t(15); };
+  std::vector<size_t> off_q(B), off_t(B), off_pr(B), off_pt(B);
+  std::vector<int32_t> prefix(B + 1, 0);
+  for (int k = 0; k < B; ++k) {
+    build_rtcsm_tables(opt, grid->resolution, items[k].max_scan_range, to_float(items[k].initial), &plan->tables[k]);
+    const RtcsmTables& t = plan->tables[k];
+    const int64_t R = (int64_t)t.cand_q.size(), L = (int64_t)t.cand_t.size();
+    if (R * L >= 0xFFFFFFFFll) return ctx->fail(DL_ERR_ARG, "more than 2^32-1 correlative candidates");
+    off_q[k] = blob; blob = align16(blob + R * sizeof(Quatf));
+    off_t[k] = blob; blob = align16(blob + L * sizeof(Vec3f));
+    off_pr[k] = blob; blob = align16(blob + R * sizeof(double));
+    off_pt[k] = blob; blob = align16(blob + L * sizeof(double));
+    prefix[k + 1] = prefix[k] + rtcsm_ctas_for(R, L);
+  }
+  const size_t off_scans = blob; blob = align16(blob + (size_t)B * sizeof(RtcsmScan));
+  const size_t off_prefix = blob; blob = align16(blob + (size_t)(B + 1) * sizeof(int32_t));
+  unsigned char* d_blob = a.take<unsigned char>(blob);
+  unsigned long long* d_best = a.take<unsigned long long>(B);
+  if (a.off > ctx->d_scratch_bytes) return ctx->fail(DL_ERR_ARG, "internal: RT-CSM scratch underestimated");
+  std::vector<unsigned char> host(blob);
+  for (int k = 0; k < B; ++k) {
+    const RtcsmTables& t = plan->tables[k];
+    std::memcpy(host.data() + off_q[k], t.cand_q.data(), t.cand_q.size() * sizeof(Quatf));
+    std::memcpy(host.data() + off_t[k], t.cand_t.data(), t.cand_t.size() * sizeof(Vec3f));
+    std::memcpy(host.data() + off_pr[k], t.pen_r.data(), t.pen_r.size() * sizeof(double));
+    std::memcpy(host.data() + off_pt[k], t.pen_t.data(), t.pen_t.size() * sizeof(double));
+    RtcsmScan sc{};
+    sc.points = items[k].d_points;
+    sc.n = (int32_t)items[k].n;
+    sc.cand_q = (const Quatf*)(d_blob + off_q[k]);
+    sc.cand_t = (const Vec3f*)(d_blob + off_t[k]);
+    sc.pen_r = (const double*)(d_blob + off_pr[k]);
+    sc.pen_t = (const double*)(d_blob + off_pt[k]);
+    sc.R = (int32_t)t.cand_q.size();
+    sc.L = (int32_t)t.cand_t.size();
+    sc.scores = items[k].d_scores;
+    sc.best = d_best + k;
+    std::memcpy(host.data() + off_scans + (size_t)k * sizeof(RtcsmScan), &sc, sizeof(sc));
+  }
+  std::memcpy(host.data() + off_prefix, prefix.data(), (size_t)(B + 1) * sizeof(int32_t));
+  DL_TRY(h2d(ctx, d_blob, host.data(), blob));
+  DL_CUDA(ctx, cudaMemsetAsync(d_best, 0, sizeof(unsigned long long) * B, ctx->stream));
+  DL_TRY(sync(ctx));  // `host` is pageable and local
+  plan->d_scans = (RtcsmScan*)(d_blob + off_scans);
+  plan->d_best = d_best;
+  return launch_rtcsm_batch(ctx, grid->view(), plan->d_scans, (const int32_t*)(d_blob + off_prefix), B, prefix[B]);
+}
+
+// Runs the search for ONE cloud already on the device (the standalone matcher call). Leaves the best pose in pose_out.
 int rtcsm_device(dl_context* ctx, const dl_rtcsm_options& opt, const Rigidd& initial, const float* d_points, int64_t n,
                  const dl_grid* grid, Arena& a, Rigidd* pose_out, float* score_out, dl_rtcsm_info* info,
                  float* all_scores_host) {
   float* d_max = a.take<float>(1);
-  DL_TRY(launch_max_range(ctx, d_points, n, 3.f * grid->resolution, d_max));
+  int32_t* d_n = a.take<int32_t>(1);
+  const int32_t n32 = (int32_t)n;
+  DL_TRY(h2d(ctx, d_n, &n32, 1));
+  DL_TRY(launch_max_range_batch(ctx, d_points, 0, d_n, 0, 1, 3.f * grid->resolution, d_max));
   float max_scan_range = 0.f;
   DL_TRY(d2h(ctx, &max_scan_range, d_max, 1));
   DL_TRY(sync(ctx));
-  RtcsmTables t;
-  const Rigidf initial_f = to_float(initial);
-  build_rtcsm_tables(opt, grid->resolution, max_scan_range, initial_f, &t);
-  const int64_t R = (int64_t)t.cand_q.size(), L = (int64_t)t.cand_t.size(), K = R * L;
+  // size of the score cube is known once the tables are: build them here once to size the optional score buffer
+  RtcsmTables probe;
+  build_rtcsm_tables(opt, grid->resolution, max_scan_range, to_float(initial), &probe);
+  const int64_t R = (int64_t)probe.cand_q.size(), L = (int64_t)probe.cand_t.size(), K = R * L;
   if (K >= 0xFFFFFFFFll) return ctx->fail(DL_ERR_ARG, "more than 2^32-1 correlative candidates");
-  Quatf* d_q = a.take<Quatf>(R);
-  Vec3f* d_t = a.take<Vec3f>(L);
-  double* d_pr = a.take<double>(R);
-  double* d_pt = a.take<double>(L);
-  unsigned long long* d_best = a.take<unsigned long long>(1);
   float* d_scores = all_scores_host ? a.take<float>(K) : nullptr;
-  if (a.off > ctx->d_scratch_bytes) return ctx->fail(DL_ERR_ARG, "internal: RT-CSM scratch underestimated");
-  DL_TRY(h2d(ctx, d_q, t.cand_q.data(), R));
-  DL_TRY(h2d(ctx, d_t, t.cand_t.data(), L));
-  DL_TRY(h2d(ctx, d_pr, t.pen_r.data(), R));
-  DL_TRY(h2d(ctx, d_pt, t.pen_t.data(), L));
-  DL_CUDA(ctx, cudaMemsetAsync(d_best, 0, sizeof(unsigned long long), ctx->stream));
-  RtcsmLaunch p{d_points, n, d_q, d_t, d_pr, d_pt, R, L, d_scores, d_best};
-  DL_TRY(launch_rtcsm(ctx, grid->view(), p));
+  RtcsmBatchPlan plan;
+  DL_TRY(rtcsm_batch_device(ctx, opt, grid, {RtcsmBatchItem{d_points, n, initial, max_scan_range, d_scores}}, a, &plan));
   unsigned long long best = 0;
-  DL_TRY(d2h(ctx, &best, d_best, 1));
+  DL_TRY(d2h(ctx, &best, plan.d_best, 1));
   if (all_scores_host) DL_TRY(d2h(ctx, all_scores_host, d_scores, K));
   DL_TRY(sync(ctx));
   if (best == 0) return ctx->fail(DL_ERR_SCORE, "no candidate with a positive score (CHECK_GT(score, 0))");
+  const RtcsmTables& t = plan.tables[0];
   const uint32_t score_bits = (uint32_t)(best >> 32);
   const int64_t index = (int64_t)(0xFFFFFFFFull - (best & 0xFFFFFFFFull));
   float score;
@@ -761,7 +827,7 @@ size_t rtcsm_scratch_bound(const dl_rtcsm_options& opt, float resolution, bool s
   const float step = 0.999f * std::acos(1.f - (resolution * resolution) / (2.f * r * r));
   const int A1 = 2 * (int)std::lround(opt.angular_search_window / step) + 1;
   const size_t R = (size_t)A1 * A1 * A1, L = (size_t)L1 * L1 * L1;
-  return arena_bytes({64, R * 16, L * 12, R * 8, L * 8, 64, scores ? R * L * 4 : 0}) + 4096;
+  return arena_bytes({64, 64, R * 16 + L * 12 + R * 8 + L * 8 + 256 + sizeof(RtcsmScan) + 64, 64, scores ? R * L * 4 : 0}) + 4096;
 }
 
 }  // namespace
@@ -1917,27 +1983,36 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
                                 f.countsA + 2 * b0, f.cap, f.clouds + (size_t)2 * b0 * f.cap * 3, 2 * nb));
       DL_TRY(launch_initial_pose(ctx, nb, f.current_pose + 7 * b0, inverse(submap), f.initial_pose + 7 * b0, f.target + 3 * b0));
       if (rtcsm) {
-        // The angular window depends on the farthest point of each cloud through acosf, which must be the host's to
-        // stay bit-exact, so this optional stage synchronises once per scan (and runs unpipelined).
+        // The angular window depends on the farthest point of each cloud through acosf, which must be the host's to stay
+        // bit-exact: ONE synchronisation per batch brings back the clouds' sizes, farthest points and initial poses; the
+        // candidate tables of all scans then go up in one copy and one launch scores every (scan, rotation, translation).
+        // The best poses are written into f.initial_pose on the device, where the solve reads them.
         std::vector<int32_t> countsA(2 * f.batch);
         std::vector<double> init(7 * f.batch);
+        std::vector<float> far(f.batch);
+        float* d_far = a.take<float>(f.batch);
+        DL_TRY(launch_max_range_batch(ctx, f.clouds, (int64_t)2 * f.cap * 3, f.countsA, 2, f.batch, 3.f * hi->resolution, d_far));
         DL_TRY(d2h(ctx, countsA.data(), f.countsA, 2 * f.batch));
         DL_TRY(d2h(ctx, init.data(), f.initial_pose, 7 * f.batch));
+        DL_TRY(d2h(ctx, far.data(), d_far, f.batch));
         DL_TRY(sync(ctx));
-        rtcsm_scores.assign(f.batch, 0.f);
         StageScope st(ctx, "rtcsm");
-        const size_t mark = a.off;
+        std::vector<RtcsmBatchItem> items;
+        std::vector<int32_t> slots;
         for (int b = 0; b < f.batch; ++b) {
           if (countsA[2 * b] <= 0) continue;
-          a.off = mark;
-          Rigidd best;
-          DL_TRY(rtcsm_device(ctx, o.real_time_correlative_scan_matcher, pose_from7(init.data() + 7 * b),
-                              f.clouds + (size_t)(2 * b) * f.cap * 3, countsA[2 * b], hi, a, &best, &rtcsm_scores[b], nullptr, nullptr));
-          pose_to7(best, init.data() + 7 * b);
+          items.push_back(RtcsmBatchItem{f.clouds + (size_t)(2 * b) * f.cap * 3, countsA[2 * b], pose_from7(init.data() + 7 * b), far[b], nullptr});
+          slots.push_back(b);
         }
-        DL_TRY(h2d(ctx, f.initial_pose, init.data(), 7 * f.batch));
-        DL_TRY(h2d(ctx, f.rtcsm_scores, rtcsm_scores.data(), f.batch));
-        DL_TRY(sync(ctx));
+        DL_CUDA(ctx, cudaMemsetAsync(f.rtcsm_scores, 0, sizeof(float) * f.batch, ctx->stream));
+        if (!items.empty()) {
+          RtcsmBatchPlan plan;
+          DL_TRY(rtcsm_batch_device(ctx, o.real_time_correlative_scan_matcher, hi, items, a, &plan));
+          int32_t* d_slots = a.take<int32_t>(items.size());
+          DL_TRY(h2d(ctx, d_slots, slots.data(), slots.size()));
+          DL_TRY(launch_rtcsm_pick(ctx, plan.d_scans, (int)items.size(), f.initial_pose, d_slots, f.rtcsm_scores, d_slots));
+          DL_TRY(sync(ctx));  // `slots` is pageable and local
+        }
         have_scores = true;
       }
       {
@@ -2002,7 +2077,7 @@ int dl_frontend_match_batch_dev(dl_context* ctx, const dl_frontend_options* opti
     return DL_ERR_ARG;
   DL_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t extra = options->use_online_correlative_scan_matching
-                           ? rtcsm_scratch_bound(options->real_time_correlative_scan_matcher, hi->resolution, false) : 0;
+                           ? (size_t)num_scans * rtcsm_scratch_bound(options->real_time_correlative_scan_matcher, hi->resolution, false) : 0;
   DL_TRY(ctx->reserve_device(frontend_bytes(num_scans, cap_rows, num_origins, extra)));
   Arena a(ctx->d_scratch);
   return frontend_run(ctx, *options, num_scans, (float*)ranges_dev, cap_rows, nullptr, sizes, origins, num_origins,
@@ -2038,7 +2113,7 @@ static int frontend_enqueue_host(dl_context* ctx, const dl_frontend_options* opt
   DL_CUDA(ctx, cudaSetDevice(ctx->device));
   const int64_t cap = std::max<int64_t>(max_size, 1);
   const size_t extra = options->use_online_correlative_scan_matching
-                           ? rtcsm_scratch_bound(options->real_time_correlative_scan_matcher, hi->resolution, false) : 0;
+                           ? (size_t)num_scans * rtcsm_scratch_bound(options->real_time_correlative_scan_matcher, hi->resolution, false) : 0;
   const size_t device_extra = imu ? imu_run_device_bytes(num_scans, imu->samples) : 0;
   DL_TRY(ctx->reserve_device(frontend_bytes(num_scans, cap, num_origins, extra) + (size_t)num_scans * cap * 32 + 256 +
                              (size_t)num_scans * sizeof(dl_scan_result) + 256 + device_extra));

@@ -31,7 +31,7 @@ struct InsertArgs {
   int32_t* top;
   int32_t* nodes;
   uint16_t* bricks;
-  int32_t* counters;     // [0] nodes in use, [1] bricks in use, [2] update-list length
+  int32_t* counters;     // [0] nodes in use, [1] bricks in use, [2] update-list length, [3] nodes / [4] bricks this Insert adds
   int32_t* bbox;         // min xyz, max xyz
   uint32_t* update_list;
   const uint16_t* hit_table;
@@ -94,8 +94,12 @@ __device__ __forceinline__ void shifted(const InsertArgs& a, const Int3& c, unsi
   *sx = (unsigned)(c.x + half); *sy = (unsigned)(c.y + half); *sz = (unsigned)(c.z + half);
 }
 
-// level 0: make sure the top entry has a node; level 1: make sure the node entry has a brick.
-template <int LEVEL>
+// level 0: make sure the top entry has a node; level 1: make sure the node entry has a brick. Two passes per level so that the
+// pools are reserved for EXACTLY the entries this Insert creates (round 1 reserved the worst case, one node and one brick per
+// touched cell: ~400 MB per grid for a 30k-point scan with two free-space voxels, a few hundred bricks actually used):
+//   ASSIGN = 0  mark every missing entry this Insert touches (-1 -> -2) and count them in counters[3 + LEVEL];
+//   ASSIGN = 1  after the host has grown the pool by that count: give every marked entry its slot (-2 -> index).
+template <int LEVEL, int ASSIGN>
 __global__ void __launch_bounds__(kBlock) ins_claim_kernel(InsertArgs a, int phase) {
   for (int i = blockIdx.x * kBlock + threadIdx.x; i < a.n; i += gridDim.x * kBlock) {
     for_each_cell(a, i, phase, [&](const Int3& c) {
@@ -103,12 +107,16 @@ __global__ void __launch_bounds__(kBlock) ins_claim_kernel(InsertArgs a, int pha
       shifted(a, c, &sx, &sy, &sz);
       int32_t* entry = a.top + ((((sz >> 6) << a.bits) + (sy >> 6)) << a.bits) + (sx >> 6);
       if (LEVEL == 1) {
-        const int node = *(volatile int32_t*)entry;  // allocated by the previous kernel
+        const int node = *(volatile int32_t*)entry;  // assigned by the previous level
         entry = a.nodes + (size_t)node * 512 + ((((sz >> 3) & 7) << 6) | (((sy >> 3) & 7) << 3) | ((sx >> 3) & 7));
       }
-      if (*(volatile int32_t*)entry == -1 && atomicCAS(entry, -1, -2) == -1) {
-        const int idx = atomicAdd(a.counters + LEVEL, 1);  // pool slots are pre-initialised (-1 nodes / 0 bricks)
-        *(volatile int32_t*)entry = idx;
+      if (ASSIGN == 0) {
+        if (*(volatile int32_t*)entry == -1 && atomicCAS(entry, -1, -2) == -1) atomicAdd(a.counters + 3 + LEVEL, 1);
+      } else {
+        if (*(volatile int32_t*)entry == -2 && atomicCAS(entry, -2, -3) == -2) {
+          const int idx = atomicAdd(a.counters + LEVEL, 1);  // pool slots are pre-initialised (-1 nodes / 0 bricks)
+          *(volatile int32_t*)entry = idx;
+        }
       }
     });
   }
@@ -203,7 +211,7 @@ void compute_odds_table(float probability, uint16_t* table) {
   }
 }
 
-int grid_reserve_pools(dl_grid* g, size_t nodes, size_t bricks);
+int grid_reserve_pools(dl_grid* g, int pending_counter, int level);
 int grid_ensure_device_state(dl_grid* g);
 
 // One RangeDataInserter3D::Insert on the device grid. `d_returns` (n x 3 floats, grid frame) is device memory.
@@ -241,19 +249,37 @@ int grid_insert_device(dl_context* ctx, dl_grid* g, const Vec3f& origin, const f
     g->d_top = grown;
     g->d_top_cap = new_size;
     g->bits += 1;
+    // from here on the device copy is ahead of the host mirror, whatever happens next: a later failure (range, out of
+    // memory) must not leave g->bits describing a host `top` of the old size
+    g->mirror_stale = true;
+    g->version++;
   }
-  // 2. pools big enough for the worst case of this Insert (every touched cell in a new brick of a new node)
-  const size_t touched = (size_t)n * (size_t)(1 + std::max(num_free, 0));
-  DL_TRY_STATUS(grid_reserve_pools(g, touched, touched));
+  // 2. structure growth with exact reservations: mark + count the missing nodes, grow the node pool by that count, assign;
+  //    then the same for the bricks (whose node entries now exist)
   a.bits = g->bits; a.top = g->d_top; a.nodes = g->d_nodes; a.bricks = g->d_bricks; a.counters = g->d_counters;
-  DL_CUDA(ctx, cudaMemsetAsync(g->d_counters + 2, 0, sizeof(int32_t), ctx->stream));
-  for (int phase = 0; phase < (num_free > 0 ? 2 : 1); ++phase) {
-    ins_claim_kernel<0><<<blocks, kBlock, 0, ctx->stream>>>(a, phase);
-    DL_LAUNCH_CHECK(ctx, "ins_claim_kernel<0>");
+  DL_CUDA(ctx, cudaMemsetAsync(g->d_counters + 2, 0, 3 * sizeof(int32_t), ctx->stream));
+  const int phases = num_free > 0 ? 2 : 1;
+  for (int phase = 0; phase < phases; ++phase) {
+    ins_claim_kernel<0, 0><<<blocks, kBlock, 0, ctx->stream>>>(a, phase);
+    DL_LAUNCH_CHECK(ctx, "ins_claim_kernel<0,0>");
   }
-  for (int phase = 0; phase < (num_free > 0 ? 2 : 1); ++phase) {
-    ins_claim_kernel<1><<<blocks, kBlock, 0, ctx->stream>>>(a, phase);
-    DL_LAUNCH_CHECK(ctx, "ins_claim_kernel<1>");
+  g->mirror_stale = true;  // top entries are marked: the device copy is the only consistent one until the Insert completes
+  g->version++;
+  DL_TRY_STATUS(grid_reserve_pools(g, 3, 0));
+  a.nodes = g->d_nodes;
+  for (int phase = 0; phase < phases; ++phase) {
+    ins_claim_kernel<0, 1><<<blocks, kBlock, 0, ctx->stream>>>(a, phase);
+    DL_LAUNCH_CHECK(ctx, "ins_claim_kernel<0,1>");
+  }
+  for (int phase = 0; phase < phases; ++phase) {
+    ins_claim_kernel<1, 0><<<blocks, kBlock, 0, ctx->stream>>>(a, phase);
+    DL_LAUNCH_CHECK(ctx, "ins_claim_kernel<1,0>");
+  }
+  DL_TRY_STATUS(grid_reserve_pools(g, 4, 1));
+  a.bricks = g->d_bricks;
+  for (int phase = 0; phase < phases; ++phase) {
+    ins_claim_kernel<1, 1><<<blocks, kBlock, 0, ctx->stream>>>(a, phase);
+    DL_LAUNCH_CHECK(ctx, "ins_claim_kernel<1,1>");
   }
   ins_apply_kernel<<<blocks, kBlock, 0, ctx->stream>>>(a, 0);
   DL_LAUNCH_CHECK(ctx, "ins_apply_kernel(hits)");

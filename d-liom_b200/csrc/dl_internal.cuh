@@ -199,19 +199,24 @@ int launch_adaptive_voxel_filter(dl_context* ctx, const float* points, int strid
                                  void* first_pass_scratch /* optional, adaptive_first_pass_bytes(batch * num_filters, cap) */);
 size_t adaptive_first_pass_bytes(int pairs, int64_t cap);
 
-struct RtcsmLaunch {
+struct RtcsmScan {  // one scan of a batched correlative search (dl_rtcsm.cu), device pointers
   const float* points;  // n x 3
-  int64_t n;
+  int32_t n;
   const Quatf* cand_q;  // R rotations (composed with the initial pose, normalised)
   const Vec3f* cand_t;  // L translations (composed with the initial pose)
   const double* pen_r;  // R: angle * rotation_delta_cost_weight
   const double* pen_t;  // L: |t| * translation_delta_cost_weight
-  int64_t R, L;
+  int32_t R, L;
   float* scores;                     // optional, R * L
-  unsigned long long* best_packed;   // (score bits << 32) | ~index
+  unsigned long long* best;          // (score bits << 32) | ~index, zeroed before the launch
 };
-int launch_rtcsm(dl_context* ctx, const GridView& grid, const RtcsmLaunch& p);
-int launch_max_range(dl_context* ctx, const float* points, int64_t n, float init, float* out);
+int rtcsm_ctas_for(int64_t R, int64_t L);
+int launch_rtcsm_batch(dl_context* ctx, const GridView& grid, const RtcsmScan* scans_dev, const int32_t* cta_prefix_dev, int num_scans,
+                       int total_ctas);
+int launch_rtcsm_pick(dl_context* ctx, const RtcsmScan* scans_dev, int num_scans, double* pose_out, const int32_t* pose_slot,
+                      float* score_out, const int32_t* score_slot);
+int launch_max_range_batch(dl_context* ctx, const float* points, int64_t stride_floats, const int32_t* counts, int count_stride,
+                           int batch, float init, float* out);
 
 // ---- NLS
 struct NlsProblem {  // one scan-to-submap registration problem, device pointers
