@@ -598,7 +598,98 @@ def measure_extras(args, w, dliom, ctx, timed_device_loop, fetch_lane0, B):
                                     "point of the second voxel filter's output"}
     except Exception as e:
         extras["mode_F"] = {"error": str(e)}
+    try:
+        extras["configs2"] = measure_configs2(args, w, dliom, ctx, peak)
+    except Exception as e:
+        extras["configs2"] = {"error": repr(e)}
     return extras
+
+
+def measure_configs2(args, w, dliom, ctx, peak, num_scans=16, map_scans=12, steps=3):
+    """BASELINE configs[2]: 128-beam scans (~256k pts) against a 0.05 m submap, correlative search (RT-CSM, 0.15 m / 1 deg
+    window -> 7^3 x 11^3 = 456 533 candidates per scan) + least-squares refine, device-resident batch, plain (no IMU) solve."""
+    import torch
+    import synth
+    orc = w["orc"]
+    scene = synth.Scene(42)
+    opts = orc.FrontEndOptions.defaults()
+    origin = np.zeros((1, 3), np.float32)
+    hi, lo = ctx.grid(0.05), ctx.grid(0.45)
+    og = orc.Grid(0.05)
+    ident = orc.IDENTITY_POSE.copy()
+    t0 = 2.0
+    for k in range(map_scans):       # the submap is built ON THE DEVICE (dl_submap_insert_range_data, bit-exact vs the oracle's inserter)
+        t = t0 + 0.1 * k
+        rows = synth.make_scan(scene, 128, t)
+        cur = synth.pose7(t)
+        ing = orc.ingest_scan(opts, rows, origin, synth.pose7(t - 0.1), cur)
+        local = apply_pose(cur, ing["returns_tracking"].astype(np.float64)).astype(np.float32)
+        ctx.submap_insert_range_data(hi, lo, ident, cur[:3].astype(np.float32), local, high_resolution_max_range=20)
+        o3 = cur[:3].astype(np.float32)
+        og.insert_range_data(o3, local[np.linalg.norm(local - o3, axis=1) <= 20.0])   # the checker's copy, for parity_scan0
+    rng = np.random.RandomState(77)
+    scans, prevs, curs = [], [], []
+    for j in range(num_scans):
+        t = t0 + 0.05 + 0.1 * (map_scans - 2) * j / num_scans
+        scans.append(synth.make_scan(scene, 128, t))
+        prevs.append(synth.pose7(t - 0.1))
+        curs.append(synth.perturb_pose(synth.pose7(t), rng, 0.1, 0.5))
+    prevs, curs = np.array(prevs), np.array(curs)
+    fo = dliom.FrontendOptions.from_oracle(opts)
+    fo.range_row_floats = 4
+    fo.use_online_correlative_scan_matching = 1
+    fo.real_time_correlative_scan_matcher = dliom.RtcsmOptions(0.15, np.deg2rad(1.0), 1e-1, 1e-1)
+    sizes = np.array([len(s) for s in scans], np.int64)
+    cap = int(sizes.max())
+    host = torch.zeros((num_scans, cap, 16), dtype=torch.uint8)
+    for b, sc in enumerate(scans):
+        host[b, :len(sc)] = torch.from_numpy(sc.view(np.uint8).reshape(-1, 32)[:, :16].copy())
+    dev = host.cuda()
+    out = torch.zeros(num_scans * C.sizeof(dliom.ScanResult), dtype=torch.uint8, device="cuda")
+
+    def step():
+        ctx.frontend_match_batch_dev(fo, C.c_void_p(dev.data_ptr()), cap, sizes, origin, prevs, curs, ident, hi, lo,
+                                     C.c_void_p(out.data_ptr()))
+    step()
+    ctx.synchronize()
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    ctx.set_profiling(True)
+    ctx.read_profile()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    ctx.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    prof = ctx.read_profile()
+    ctx.set_profiling(False)
+    res = ctx.fetch_results(C.c_void_p(out.data_ptr()), num_scans)
+    # algorithmic bytes of the correlative stage: R (12 N + 2 N L) per scan (SURVEY 8d) with the window the library derived
+    n_hi = np.array([r.num_high_resolution for r in res], np.float64)
+    R, L = 11 ** 3, 7 ** 3
+    csm_bytes = float(np.sum(R * (12.0 * n_hi + 2.0 * n_hi * L)))
+    csm_ms = prof.get("rtcsm", (0.0, 0))[0] / steps
+    achieved = csm_bytes / (csm_ms * 1e-3) / 1e9 if csm_ms > 0 else None
+    # one scan against the oracle's exhaustive search (bit-exact score, same pose), ~seconds of CPU
+    ing = orc.ingest_scan(opts, scans[0], origin, prevs[0], curs[0])
+    pts = ing["returns_tracking"]
+    hk, _ = orc.adaptive_voxel_filter(pts, opts.hi_max_length, opts.hi_min_num_points, opts.hi_max_range)
+    init = np.concatenate([ing["current_pose"][:3].astype(np.float64), ing["current_pose"][3:].astype(np.float64)])
+    want = orc.rtcsm_match(og, pts[hk], init, 0.15, np.deg2rad(1.0), 1e-1, 1e-1)
+    return {"value": num_scans / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "scans_per_step": num_scans,
+            "workload": "configs[2]: 128-beam scans (~256k pts), 0.05 m / 0.45 m submap built on the device, RT-CSM 0.15 m / 1 deg "
+                        "(456 533 candidates per scan) + least-squares refine, plain solve",
+            "points_per_scan": float(sizes.mean()), "correlative_points_per_scan": float(n_hi.mean()),
+            "candidates_per_scan": R * L, "stages_ms_per_step": {n: round(v[0] / steps, 4) for n, v in prof.items()},
+            "roofline": {"bound": "hbm", "kernel": "rtcsm_score_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": None if achieved is None else achieved / peak, "traffic": None,
+                         "bytes_model": "R (12 N + 2 N L) per scan: the cloud once per rotation + one 2-byte voxel per (point, translation)",
+                         "note": "voxel reads are L1/L2 hits by design (a translation window touches <= 8 bricks): the kernel is "
+                                 "issue-bound, not HBM-bound; see profiles/"},
+            "all_ok": bool(all(r.ok == 1 for r in res)),
+            "parity_scan0": {"rtcsm_score_equal": bool(np.float32(res[0].rtcsm_score) == np.float32(want["score"])),
+                             "gpu_score": float(res[0].rtcsm_score), "oracle_score": float(want["score"])}}
 
 
 if __name__ == "__main__":
