@@ -1809,9 +1809,11 @@ size_t imu_run_device_bytes(int num_scans, const dl_frontend_imu_samples* raw) {
 int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, float* d_ranges, int64_t in_cap,
                  const void* const* host_ranges, const int64_t* sizes, const float* origins, int num_origins,
                  const double* prev_poses, const double* cur_poses, const double* submap_local_pose, const dl_grid* hi,
-                 const dl_grid* lo, Arena& a, dl_scan_result* d_results, ImuRun* imu_run = nullptr) {
+                 const dl_grid* lo, Arena& a, dl_scan_result* d_results, ImuRun* imu_run = nullptr,
+                 FrontendBuffers* buffers_out = nullptr) {
   FrontendBuffers f;
   carve(a, num_scans, in_cap, num_origins, &f);
+  if (buffers_out) *buffers_out = f;
   // optional IMU coupling: one pre-integration factor per scan, the 15-parameter solve instead of the 6-parameter one
   const dl_frontend_imu* imu = imu_run ? imu_run->host : nullptr;
   const dl_frontend_imu_samples* raw = imu_run ? imu_run->samples : nullptr;
@@ -2095,7 +2097,8 @@ int dl_frontend_fetch_results(dl_context* ctx, const dl_scan_result* results_dev
 static int frontend_enqueue_host(dl_context* ctx, const dl_frontend_options* options, int32_t num_scans, const void* const* ranges,
                                  const int64_t* sizes, const float* origins, int32_t num_origins, const double* prev_poses,
                                  const double* predicted_poses, const double* submap_local_pose, const dl_grid* hi,
-                                 const dl_grid* lo, size_t pinned_extra, dl_scan_result** d_results_out, ImuRun* imu = nullptr) {
+                                 const dl_grid* lo, size_t pinned_extra, dl_scan_result** d_results_out, ImuRun* imu = nullptr,
+                                 FrontendBuffers* buffers_out = nullptr) {
   int64_t max_size = 0;
   DL_TRY(check_frontend(ctx, options, num_scans, sizes, hi, lo, &max_size));
   const bool raw = imu && imu->samples;
@@ -2122,7 +2125,7 @@ static int frontend_enqueue_host(dl_context* ctx, const dl_frontend_options* opt
   float* d_ranges = a.take<float>((size_t)num_scans * cap * 8);
   *d_results_out = a.take<dl_scan_result>(num_scans);
   return frontend_run(ctx, *options, num_scans, d_ranges, cap, ranges, sizes, origins, num_origins, prev_poses,
-                      predicted_poses, submap_local_pose, hi, lo, a, *d_results_out, imu);
+                      predicted_poses, submap_local_pose, hi, lo, a, *d_results_out, imu, buffers_out);
 }
 
 int dl_frontend_match_batch(dl_context* ctx, const dl_frontend_options* options, int32_t num_scans,
@@ -2412,6 +2415,331 @@ int dl_ingest_scan(dl_context* ctx, const dl_frontend_options* options, const vo
   DL_TRY(sync(ctx));
   if (first_keep_out)
     for (int i = 0; i < c[0]; ++i) first_keep_out[i] = keep32[i];
+  return DL_OK;
+}
+
+}  // extern "C"
+
+
+// ------------------------------------------------------------------------------------------------ rotational histogram
+extern "C" int dl_rotational_histogram(dl_context* ctx, const float* points, int64_t n, int32_t size, float* histogram_out) {
+  if (!ctx || n < 0 || (n > 0 && !points) || !histogram_out) return DL_ERR_ARG;
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  DL_TRY(ctx->reserve_device(arena_bytes({(size_t)n * 12, (size_t)size * 4}) + rotational_histogram_scratch_bytes(n)));
+  Arena a(ctx->d_scratch);
+  float* d_pts = a.take<float>(3 * (size_t)std::max<int64_t>(n, 1));
+  float* d_hist = a.take<float>(std::max(size, 1));
+  DL_TRY(h2d(ctx, d_pts, points, 3 * (size_t)n));
+  int32_t* d_err = nullptr;
+  DL_TRY(launch_rotational_histogram(ctx, a, d_pts, n, size, d_hist, &d_err));
+  int32_t err = 0;
+  DL_TRY(d2h(ctx, histogram_out, d_hist, (size_t)size));
+  DL_TRY(d2h(ctx, &err, d_err, 1));
+  DL_TRY(sync(ctx));
+  if (err) return ctx->fail(DL_ERR_ARG, "a point lies outside +-2^19 slices of 0.2 m");
+  return DL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ LocalTrajectoryBuilder3D
+// The per-trajectory object of the reference front end (local_trajectory_builder_3d.h:81-113) over the device path:
+// AddImuData buffers the samples of the running interval, AddRangeData runs ONE scan through the IMU-coupled front end
+// against the matching submap (active_submaps_.submaps().front(), LTB:502-505), then does what AddAccumulatedRangeData /
+// InsertIntoSubmap do after the match: motion filter (motion_filter.cc:37-57), insertion into both active submaps on the
+// device (submap_3d.cc:264-279, :300-326 incl. the submap hand-over), rotational histogram of the inserted scan (LTB:605-610).
+// Differences, all stated in the header: the fused solve replaces the match + GTSAM window (so `local_pose` is the solve's
+// pose), num_accumulated_range_data = 1, a single range sensor (the synchroniser for several is the host-side
+// dliom::sensor::RangeDataSynchronizer of the C++ shim), initialisation = InitializeStatic or a state given by the caller.
+struct LtbSubmap {
+  dl_grid* hi = nullptr;
+  dl_grid* lo = nullptr;
+  Rigidd local_pose{{0, 0, 0}, {1, 0, 0, 0}};
+  int num_range_data = 0;
+  int finished = 0;
+  int index = 0;
+};
+struct dl_local_trajectory_builder {
+  dl_context* ctx = nullptr;
+  dl_ltb_options opt{};
+  bool initialized = false;
+  int accumulated_frames = 0;
+  std::vector<double> init_acc, init_gyr;  // xyz per sample
+  dl_nav_state prev_state{};
+  double last_imu_time = -1.0;
+  std::vector<double> dt, acc, gyr;        // the running interval; sample 0 is the latch
+  std::vector<LtbSubmap> active, finished;
+  int next_index = 0;
+  int64_t motion_total = 0;
+  double motion_last_time = 0;
+  Rigidd motion_last_pose{{0, 0, 0}, {1, 0, 0, 0}};
+  std::vector<float> clouds[4];            // returns / misses in the local frame, high / low resolution cloud in the tracking frame
+  std::vector<float> histogram;
+};
+
+namespace {
+int ltb_add_submap(dl_local_trajectory_builder* b, const Rigidd& pose) {
+  if (b->active.size() > 1) {  // ActiveSubmaps3D::AddSubmap (submap_3d.cc:315-326)
+    b->active.front().finished = 1;
+    b->finished.push_back(b->active.front());
+    b->active.erase(b->active.begin());
+  }
+  LtbSubmap s;
+  s.local_pose = pose;
+  s.index = b->next_index++;
+  DL_TRY(dl_grid_create(b->ctx, b->opt.high_resolution, &s.hi));
+  DL_TRY(dl_grid_create(b->ctx, b->opt.low_resolution, &s.lo));
+  DL_TRY(dl_grid_sync(s.hi));
+  DL_TRY(dl_grid_sync(s.lo));
+  b->active.push_back(s);
+  return DL_OK;
+}
+double rotation_angle_d(const Quatd& q) {  // transform::GetAngle (transform.h:33-37)
+  return 2.0 * std::atan2(std::sqrt(q.x * q.x + q.y * q.y + q.z * q.z), std::fabs(q.w));
+}
+}  // namespace
+
+extern "C" {
+
+int dl_ltb_create(dl_context* ctx, const dl_ltb_options* options, dl_local_trajectory_builder** out) {
+  if (!ctx || !options || !out) return DL_ERR_ARG;
+  if (!(options->high_resolution > 0.f) || !(options->low_resolution > 0.f) || options->num_range_data < 1 ||
+      options->rotational_histogram_size < 1 || options->rotational_histogram_size > 1024)
+    return ctx->fail(DL_ERR_ARG, "dl_ltb_options: resolutions, num_range_data or rotational_histogram_size out of range");
+  DL_TRY(check_ceres_options(ctx, &options->frontend.ceres_scan_matcher, 2));
+  DL_TRY(check_inserter(ctx, &options->range_data_inserter));
+  DL_TRY(check_imu_options(ctx, &options->frontend));
+  dl_local_trajectory_builder* b = new dl_local_trajectory_builder;
+  b->ctx = ctx;
+  b->opt = *options;
+  b->opt.frontend.range_row_floats = 4;
+  b->opt.frontend.host_scan_stride_rows = 0;
+  // "We always want to have at least one submap ... create it at the origin" (submap_3d.cc:286-295)
+  const int st = ltb_add_submap(b, Rigidd{{0, 0, 0}, {1, 0, 0, 0}});
+  if (st != DL_OK) {
+    dl_ltb_destroy(b);
+    return st;
+  }
+  *out = b;
+  return DL_OK;
+}
+
+void dl_ltb_destroy(dl_local_trajectory_builder* b) {
+  if (!b) return;
+  for (auto* list : {&b->active, &b->finished})
+    for (LtbSubmap& s : *list) {
+      dl_grid_destroy(s.hi);
+      dl_grid_destroy(s.lo);
+    }
+  delete b;
+}
+
+int dl_ltb_set_initial_state(dl_local_trajectory_builder* b, const dl_nav_state* state) {
+  if (!b || !state) return DL_ERR_ARG;
+  b->prev_state = *state;
+  b->initialized = true;
+  b->dt.clear(); b->acc.clear(); b->gyr.clear();
+  return DL_OK;
+}
+
+int dl_ltb_add_imu_data(dl_local_trajectory_builder* b, double time, const double* linear_acceleration, const double* angular_velocity) {
+  if (!b || !linear_acceleration || !angular_velocity) return DL_ERR_ARG;
+  if (!b->initialized) {  // init_imu_buffer_opt_ (LTB:165-176)
+    b->init_acc.insert(b->init_acc.end(), linear_acceleration, linear_acceleration + 3);
+    b->init_gyr.insert(b->init_gyr.end(), angular_velocity, angular_velocity + 3);
+    return DL_OK;
+  }
+  const double dt = b->last_imu_time < 0 ? 1.0 / 500.0 : time - b->last_imu_time;  // LTB:183-185
+  b->last_imu_time = time;
+  b->dt.push_back(dt);
+  b->acc.insert(b->acc.end(), linear_acceleration, linear_acceleration + 3);
+  b->gyr.insert(b->gyr.end(), angular_velocity, angular_velocity + 3);
+  return DL_OK;
+}
+
+int dl_ltb_add_range_data(dl_local_trajectory_builder* b, double time, const float* xyzt, int64_t n, const float* origin,
+                          dl_matching_result* out) {
+  if (!b || !out || n < 0 || (n > 0 && !xyzt) || !origin) return DL_ERR_ARG;
+  dl_context* ctx = b->ctx;
+  std::memset(out, 0, sizeof(*out));
+  out->time = time;
+  if (n == 0) return DL_OK;  // "Range data collator filling buffer" (LTB:366-369)
+  if (!b->initialized) {
+    // InitializeStatic after frames_for_static_initialization scans (LTB:372-381, :203-229): the mean specific force
+    // fixes roll / pitch, the residual of the two the accelerometer bias, the mean rate the gyroscope bias.
+    if (b->accumulated_frames++ > b->opt.frames_for_static_initialization && !b->init_acc.empty()) {
+      const size_t m = b->init_acc.size() / 3;
+      double am[3] = {0, 0, 0}, gm[3] = {0, 0, 0};
+      for (size_t k = 0; k < m; ++k)
+        for (int c = 0; c < 3; ++c) { am[c] += b->init_acc[3 * k + c]; gm[c] += b->init_gyr[3 * k + c]; }
+      for (int c = 0; c < 3; ++c) { am[c] /= (double)m; gm[c] /= (double)m; }
+      // R = FromTwoVectors(accel_mean, (0, 0, g)): the rotation taking the measured up direction to +z
+      const double an = std::sqrt(am[0] * am[0] + am[1] * am[1] + am[2] * am[2]);
+      Quatd q{1, 0, 0, 0};
+      if (an > 0) {
+        const Vec3d u{am[0] / an, am[1] / an, am[2] / an}, v{0, 0, 1};
+        const double c = dot3(u, v);
+        if (c > -1.0 + 1e-12) {
+          const Vec3d ax = cross3(u, v);
+          const double s2 = std::sqrt((1.0 + c) * 2.0);
+          q = qnormalized(Quatd{s2 * 0.5, ax.x / s2, ax.y / s2, ax.z / s2});
+        } else {
+          q = Quatd{0, 1, 0, 0};
+        }
+      }
+      dl_nav_state st{};
+      st.q[0] = q.w; st.q[1] = q.x; st.q[2] = q.y; st.q[3] = q.z;
+      const Vec3d g_body = rotate(qconj(q), Vec3d{0, 0, -b->opt.gravity});  // R^T g_vec
+      st.ba[0] = g_body.x + am[0]; st.ba[1] = g_body.y + am[1]; st.ba[2] = g_body.z + am[2];
+      for (int c = 0; c < 3; ++c) st.bg[c] = gm[c];
+      b->prev_state = st;
+      b->initialized = true;
+      b->init_acc.clear(); b->init_gyr.clear();
+    }
+    return DL_OK;
+  }
+  if (b->dt.size() < 2) return DL_OK;  // predicted_states_.empty() (LTB:426): no IMU since the last scan
+  const dl_frontend_options& fo = b->opt.frontend;
+  dl_frontend_imu_samples imu{};
+  imu.noise = b->opt.imu_noise;
+  imu.imu_weight = b->opt.imu_weight;
+  imu.gravity[0] = 0; imu.gravity[1] = 0; imu.gravity[2] = b->opt.gravity;
+  imu.states_i = &b->prev_state;
+  const int32_t offsets[2] = {0, (int32_t)b->dt.size()};
+  imu.offsets = offsets;
+  imu.dt = b->dt.data(); imu.acc = b->acc.data(); imu.gyr = b->gyr.data();
+  const LtbSubmap& matching = b->active.front();
+  double submap_pose[7];
+  pose_to7(matching.local_pose, submap_pose);
+  const void* ranges[1] = {xyzt};
+  const int64_t sizes[1] = {n};
+  DL_TRY(check_imu_samples(ctx, &fo, &imu, 1));
+  dl_scan_result* d_results = nullptr;
+  ImuRun run;
+  run.samples = &imu;
+  FrontendBuffers f;
+  DL_TRY(frontend_enqueue_host(ctx, &fo, 1, ranges, sizes, origin, 1, nullptr, nullptr, submap_pose, matching.hi, matching.lo, 0,
+                               &d_results, &run, &f));
+  dl_scan_result r{};
+  dl_nav_state state{};
+  float cur7[7];
+  DL_TRY(d2h(ctx, &r, d_results, 1));
+  DL_TRY(d2h(ctx, &state, run.d_states, 1));
+  DL_TRY(d2h(ctx, cur7, f.current_pose, 7));
+  DL_TRY(sync(ctx));
+  out->scan = r;
+  if (r.ok != 1) return DL_OK;  // dropped like the reference's nullptr (LTB:497-534); the interval keeps integrating
+  std::vector<float> returns_tracking((size_t)r.num_returns * 3), misses_tracking((size_t)r.num_misses * 3);
+  b->clouds[2].resize((size_t)r.num_high_resolution * 3);
+  b->clouds[3].resize((size_t)r.num_low_resolution * 3);
+  DL_TRY(d2h(ctx, returns_tracking.data(), f.returns_tracking, returns_tracking.size()));
+  DL_TRY(d2h(ctx, misses_tracking.data(), f.misses_tracking, misses_tracking.size()));
+  DL_TRY(d2h(ctx, b->clouds[2].data(), f.clouds, b->clouds[2].size()));
+  DL_TRY(d2h(ctx, b->clouds[3].data(), f.clouds + (size_t)f.cap * 3, b->clouds[3].size()));
+  DL_TRY(sync(ctx));
+  // the estimate becomes the previous state; the last sample of the interval latches the next one
+  b->prev_state = state;
+  {
+    const size_t last = b->dt.size() - 1;
+    const double ldt = b->dt[last];
+    const double la[3] = {b->acc[3 * last], b->acc[3 * last + 1], b->acc[3 * last + 2]};
+    const double lg[3] = {b->gyr[3 * last], b->gyr[3 * last + 1], b->gyr[3 * last + 2]};
+    b->dt.assign(1, ldt);
+    b->acc.assign(la, la + 3);
+    b->gyr.assign(lg, lg + 3);
+  }
+  out->has_result = 1;
+  out->state = state;
+  const Rigidd opt_pose{{state.p[0], state.p[1], state.p[2]}, {state.q[0], state.q[1], state.q[2], state.q[3]}};
+  pose_to7(opt_pose, out->local_pose);
+  // filtered_range_data_in_local = TransformRangeData(filtered_range_data_in_tracking, opt_pose.cast<float>()) (LTB:559-560)
+  const Rigidf opt_f = to_float(opt_pose);
+  const Rigidf cur{{cur7[0], cur7[1], cur7[2]}, {cur7[3], cur7[4], cur7[5], cur7[6]}};
+  const Vec3f origin_tracking = apply(inverse(cur), cur.t);  // LTB:485-487: the origin back in the tracking frame
+  const Vec3f origin_local = apply(opt_f, origin_tracking);
+  for (int which = 0; which < 2; ++which) {
+    const std::vector<float>& in = which == 0 ? returns_tracking : misses_tracking;
+    std::vector<float>& o = b->clouds[which];
+    o.resize(in.size());
+    for (size_t k = 0; k + 2 < in.size(); k += 3) {
+      const Vec3f p = apply(opt_f, Vec3f{in[k], in[k + 1], in[k + 2]});
+      o[k] = p.x; o[k + 1] = p.y; o[k + 2] = p.z;
+    }
+  }
+  out->origin_in_local[0] = origin_local.x; out->origin_in_local[1] = origin_local.y; out->origin_in_local[2] = origin_local.z;
+  out->num_returns = r.num_returns; out->num_misses = r.num_misses;
+  out->num_high_resolution = r.num_high_resolution; out->num_low_resolution = r.num_low_resolution;
+  // MotionFilter::IsSimilar (motion_filter.cc:37-57)
+  ++b->motion_total;
+  if (b->motion_total > 1 && time - b->motion_last_time <= b->opt.motion_filter_max_time_seconds &&
+      norm3(sub(opt_pose.t, b->motion_last_pose.t)) <= b->opt.motion_filter_max_distance_meters &&
+      rotation_angle_d(compose(inverse(opt_pose), b->motion_last_pose).q) <= b->opt.motion_filter_max_angle_radians)
+    return DL_OK;  // insertion_result == nullptr
+  b->motion_last_time = time;
+  b->motion_last_pose = opt_pose;
+  // InsertIntoSubmap (LTB:584-622): the insertion submaps are queried BEFORE the insert
+  out->num_insertion_submaps = (int32_t)b->active.size();
+  for (size_t k = 0; k < b->active.size() && k < 2; ++k) out->insertion_submap_index[k] = b->active[k].index;
+  const float org[3] = {origin_local.x, origin_local.y, origin_local.z};
+  for (LtbSubmap& sm : b->active) {
+    double sp[7];
+    pose_to7(sm.local_pose, sp);
+    DL_TRY(dl_submap_insert_range_data(ctx, sm.hi, sm.lo, &b->opt.range_data_inserter, sp, b->opt.high_resolution_max_range, org,
+                                       b->clouds[0].data(), (int64_t)r.num_returns));
+    sm.num_range_data++;
+  }
+  if (b->active.back().num_range_data == b->opt.num_range_data)  // ActiveSubmaps3D::InsertRangeData (submap_3d.cc:300-313)
+    DL_TRY(ltb_add_submap(b, Rigidd{{(double)origin_local.x, (double)origin_local.y, (double)origin_local.z}, opt_pose.q}));
+  // ComputeHistogram(TransformPointCloud(returns in tracking, Rotation(gravity_alignment.cast<float>())), size) on the device
+  {
+    const Quatf gq{(float)opt_pose.q.w, (float)opt_pose.q.x, (float)opt_pose.q.y, (float)opt_pose.q.z};
+    const Rigidf rot{{0.f, 0.f, 0.f}, gq};
+    std::vector<float> aligned(returns_tracking.size());
+    for (size_t k = 0; k + 2 < returns_tracking.size(); k += 3) {
+      const Vec3f p = apply(rot, Vec3f{returns_tracking[k], returns_tracking[k + 1], returns_tracking[k + 2]});
+      aligned[k] = p.x; aligned[k + 1] = p.y; aligned[k + 2] = p.z;
+    }
+    b->histogram.assign(b->opt.rotational_histogram_size, 0.f);
+    DL_TRY(dl_rotational_histogram(ctx, aligned.data(), (int64_t)r.num_returns, b->opt.rotational_histogram_size, b->histogram.data()));
+  }
+  out->inserted = 1;
+  return DL_OK;
+}
+
+int dl_ltb_get_cloud(const dl_local_trajectory_builder* b, int32_t which, float* out, int64_t capacity_points, int64_t* num_points) {
+  if (!b || which < 0 || which > 3 || !num_points) return DL_ERR_ARG;
+  const std::vector<float>& c = b->clouds[which];
+  *num_points = (int64_t)c.size() / 3;
+  if (out && capacity_points >= *num_points) std::memcpy(out, c.data(), c.size() * sizeof(float));
+  return DL_OK;
+}
+
+int dl_ltb_get_histogram(const dl_local_trajectory_builder* b, float* out, int32_t capacity) {
+  if (!b || !out || capacity < (int32_t)b->histogram.size()) return DL_ERR_ARG;
+  std::memcpy(out, b->histogram.data(), b->histogram.size() * sizeof(float));
+  return DL_OK;
+}
+
+int32_t dl_ltb_num_submaps(const dl_local_trajectory_builder* b) { return b ? (int32_t)(b->finished.size() + b->active.size()) : 0; }
+
+int dl_ltb_get_submap(dl_local_trajectory_builder* b, int32_t index, dl_grid** high_resolution_grid, dl_grid** low_resolution_grid,
+                      double* local_pose, int32_t* num_range_data, int32_t* finished) {
+  if (!b) return DL_ERR_ARG;
+  for (auto* list : {&b->finished, &b->active})
+    for (LtbSubmap& s : *list)
+      if (s.index == index) {
+        if (high_resolution_grid) *high_resolution_grid = s.hi;
+        if (low_resolution_grid) *low_resolution_grid = s.lo;
+        if (local_pose) pose_to7(s.local_pose, local_pose);
+        if (num_range_data) *num_range_data = s.num_range_data;
+        if (finished) *finished = s.finished;
+        return DL_OK;
+      }
+  return b->ctx->fail(DL_ERR_ARG, "no submap with this index");
+}
+
+int dl_ltb_get_state(const dl_local_trajectory_builder* b, dl_nav_state* state, int32_t* initialized) {
+  if (!b) return DL_ERR_ARG;
+  if (state) *state = b->prev_state;
+  if (initialized) *initialized = b->initialized ? 1 : 0;
   return DL_OK;
 }
 

@@ -309,6 +309,10 @@ int grid_insert_device(dl_context* ctx, dl_grid* g, const Vec3f& origin, const f
                        const uint16_t* d_hit_table, const uint16_t* d_miss_table, int32_t* d_bbox, uint32_t* d_update_list);
 int launch_transform_filter(dl_context* ctx, const float* in, int n, const Rigidf& to_submap, const Vec3f& origin_submap,
                             float max_range, float* all, float* near, int32_t* near_count, int32_t* tile_counts);
+// dl_histogram.cu
+size_t rotational_histogram_scratch_bytes(int64_t n);
+int launch_rotational_histogram(dl_context* ctx, Arena& a, const float* d_points, int64_t n, int size, float* d_histogram,
+                                int32_t** d_error_out);
 // dl_comm.cu: staging buffers of the constraint exchange and the timed all-gather
 int comm_reserve(dl_comm* c, size_t bytes_per_rank);
 void* comm_send_buffer(dl_comm* c);

@@ -32,6 +32,8 @@ EXPORTS = [
     "dl_frontend_collect_imu",
     "dl_comm_unique_id", "dl_comm_create", "dl_comm_destroy", "dl_comm_rank", "dl_comm_world_size", "dl_comm_last_error",
     "dl_comm_all_gather_dev", "dl_comm_all_reduce_f64_dev", "dl_comm_broadcast_dev", "dl_constraint_search_exchange",
+    "dl_rotational_histogram", "dl_ltb_create", "dl_ltb_destroy", "dl_ltb_set_initial_state", "dl_ltb_add_imu_data",
+    "dl_ltb_add_range_data", "dl_ltb_get_cloud", "dl_ltb_get_histogram", "dl_ltb_num_submaps", "dl_ltb_get_submap", "dl_ltb_get_state",
 ]
 
 
@@ -239,6 +241,40 @@ class ImuSamples:
                                         self.acc.ctypes.data, self.gyr.ctypes.data)
 
 
+class LtbOptions(C.Structure):   # dl_ltb_options
+    _fields_ = [("frontend", FrontendOptions), ("imu_noise", ImuNoise), ("imu_weight", C.c_double), ("gravity", C.c_double),
+                ("high_resolution", C.c_float), ("low_resolution", C.c_float), ("num_range_data", C.c_int32),
+                ("high_resolution_max_range", C.c_int32), ("range_data_inserter", RangeDataInserterOptions),
+                ("motion_filter_max_time_seconds", C.c_double), ("motion_filter_max_distance_meters", C.c_double),
+                ("motion_filter_max_angle_radians", C.c_double), ("rotational_histogram_size", C.c_int32),
+                ("frames_for_static_initialization", C.c_int32)]
+
+    @staticmethod
+    def defaults(frontend, noise4, **kw):
+        """trajectory_builder_3d.lua defaults: submaps 0.1 / 0.45 m, 20 m, 160 range data; motion filter 0.5 s / 0.1 m / 0.004 rad."""
+        o = LtbOptions()
+        o.frontend = frontend
+        o.imu_noise = ImuNoise(*[float(v) for v in noise4])
+        o.imu_weight, o.gravity = kw.pop("imu_weight", 1.0), kw.pop("gravity", 9.8)
+        o.high_resolution, o.low_resolution = kw.pop("high_resolution", 0.1), kw.pop("low_resolution", 0.45)
+        o.num_range_data, o.high_resolution_max_range = kw.pop("num_range_data", 160), kw.pop("high_resolution_max_range", 20)
+        o.range_data_inserter = RangeDataInserterOptions(kw.pop("hit", 0.55), kw.pop("miss", 0.49), kw.pop("num_free", 2), 0)
+        o.motion_filter_max_time_seconds = kw.pop("max_time_seconds", 0.5)
+        o.motion_filter_max_distance_meters = kw.pop("max_distance_meters", 0.1)
+        o.motion_filter_max_angle_radians = kw.pop("max_angle_radians", 0.004)
+        o.rotational_histogram_size = kw.pop("rotational_histogram_size", 120)
+        o.frames_for_static_initialization = kw.pop("frames_for_static_initialization", 7)
+        assert not kw, kw
+        return o
+
+
+class MatchingResult(C.Structure):   # dl_matching_result
+    _fields_ = [("has_result", C.c_int32), ("inserted", C.c_int32), ("time", C.c_double), ("local_pose", C.c_double * 7),
+                ("state", NavState), ("scan", ScanResult), ("origin_in_local", C.c_float * 3), ("num_returns", C.c_int32),
+                ("num_misses", C.c_int32), ("num_high_resolution", C.c_int32), ("num_low_resolution", C.c_int32),
+                ("num_insertion_submaps", C.c_int32), ("insertion_submap_index", C.c_int32 * 2), ("reserved", C.c_int32)]
+
+
 def lib():
     global _LIB
     if _LIB is not None:
@@ -323,6 +359,18 @@ def lib():
     L.dl_comm_broadcast_dev.argtypes = [vp, vp, C.c_int64, C.c_int32]
     L.dl_constraint_search_exchange.argtypes = [vp, vp, ip(ConstraintOptions), C.c_int32, C.c_int32, i32p, i32p, f64p, f32p, i64p,
                                                 f32p, i64p, C.c_void_p, C.c_void_p, ip(ConstraintRow), ip(ExchangeInfo)]
+    L.dl_rotational_histogram.argtypes = [vp, f32p, C.c_int64, C.c_int32, f32p]
+    L.dl_ltb_create.argtypes = [vp, ip(LtbOptions), ip(vp)]
+    L.dl_ltb_destroy.argtypes = [vp]
+    L.dl_ltb_destroy.restype = None
+    L.dl_ltb_set_initial_state.argtypes = [vp, ip(NavState)]
+    L.dl_ltb_add_imu_data.argtypes = [vp, C.c_double, f64p, f64p]
+    L.dl_ltb_add_range_data.argtypes = [vp, C.c_double, f32p, C.c_int64, f32p, ip(MatchingResult)]
+    L.dl_ltb_get_cloud.argtypes = [vp, C.c_int32, vp, C.c_int64, ip(C.c_int64)]
+    L.dl_ltb_get_histogram.argtypes = [vp, f32p, C.c_int32]
+    L.dl_ltb_num_submaps.argtypes = [vp]
+    L.dl_ltb_get_submap.argtypes = [vp, C.c_int32, ip(vp), ip(vp), f64p, ip(C.c_int32), ip(C.c_int32)]
+    L.dl_ltb_get_state.argtypes = [vp, ip(NavState), ip(C.c_int32)]
     L.dl_frontend_submit.argtypes = [vp, ip(FrontendOptions), C.c_int32, ip(vp), i64p, f32p, C.c_int32, f64p, f64p, f64p, vp, vp]
     L.dl_frontend_collect.argtypes = [vp, C.c_int32, ip(ScanResult)]
     L.dl_frontend_match_batch_dev.argtypes = [vp, ip(FrontendOptions), C.c_int32, vp, C.c_int64, i64p, f32p, C.c_int32,
@@ -749,6 +797,64 @@ class Context:
         self.check(self.L.dl_copy_to_device(self.h, dst, src_array.ctypes.data_as(C.c_void_p), src_array.nbytes))
 
 
+class LocalTrajectoryBuilder:
+    """mapping::LocalTrajectoryBuilder3D over the device path (dl_ltb_*): add_imu_data / add_range_data -> MatchingResult."""
+
+    def __init__(self, ctx, options):
+        self.ctx, self.options = ctx, options
+        self.h = C.c_void_p()
+        ctx.check(ctx.L.dl_ltb_create(ctx.h, C.byref(options), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.ctx.L.dl_ltb_destroy(self.h)
+            self.h = None
+
+    def set_initial_state(self, state16):
+        s = NavState.from16(state16)
+        self.ctx.check(self.ctx.L.dl_ltb_set_initial_state(self.h, C.byref(s)))
+
+    def add_imu_data(self, time, acc, gyr):
+        self.ctx.check(self.ctx.L.dl_ltb_add_imu_data(self.h, float(time), np.ascontiguousarray(acc, np.float64),
+                                                      np.ascontiguousarray(gyr, np.float64)))
+
+    def add_range_data(self, time, xyzt, origin=(0.0, 0.0, 0.0)):
+        rows = np.ascontiguousarray(xyzt, np.float32).reshape(-1, 4)
+        out = MatchingResult()
+        self.ctx.check(self.ctx.L.dl_ltb_add_range_data(self.h, float(time), rows, len(rows), np.ascontiguousarray(origin, np.float32),
+                                                        C.byref(out)))
+        return out
+
+    def cloud(self, which):
+        n = C.c_int64(0)
+        self.ctx.check(self.ctx.L.dl_ltb_get_cloud(self.h, which, None, 0, C.byref(n)))
+        out = np.zeros((max(n.value, 1), 3), np.float32)
+        self.ctx.check(self.ctx.L.dl_ltb_get_cloud(self.h, which, out.ctypes.data, n.value, C.byref(n)))
+        return out[:n.value]
+
+    def histogram(self):
+        out = np.zeros(self.options.rotational_histogram_size, np.float32)
+        self.ctx.check(self.ctx.L.dl_ltb_get_histogram(self.h, out, len(out)))
+        return out
+
+    def num_submaps(self):
+        return self.ctx.L.dl_ltb_num_submaps(self.h)
+
+    def submap(self, index):
+        """-> (hi Grid view, lo Grid view, local pose, num_range_data, finished); the grids stay owned by the builder."""
+        hi, lo = C.c_void_p(), C.c_void_p()
+        pose = np.zeros(7)
+        n, fin = C.c_int32(0), C.c_int32(0)
+        self.ctx.check(self.ctx.L.dl_ltb_get_submap(self.h, index, C.byref(hi), C.byref(lo), pose, C.byref(n), C.byref(fin)))
+        return Grid.borrowed(self.ctx, hi), Grid.borrowed(self.ctx, lo), pose, n.value, bool(fin.value)
+
+    def state(self):
+        s = NavState()
+        init = C.c_int32(0)
+        self.ctx.check(self.ctx.L.dl_ltb_get_state(self.h, C.byref(s), C.byref(init)))
+        return s.to16(), bool(init.value)
+
+
 def comm_unique_id():
     """128 bytes from ncclGetUniqueId (rank 0 calls this and distributes the bytes)."""
     buf = (C.c_uint8 * 128)()
@@ -791,8 +897,15 @@ class Grid:
         ctx.check(ctx.L.dl_grid_create(ctx.h, np.float32(resolution), C.byref(h)))
         self.h = h
 
+    @classmethod
+    def borrowed(cls, ctx, handle):
+        """A view of a grid owned by someone else (a LocalTrajectoryBuilder's submap): never destroyed from here."""
+        g = cls.__new__(cls)
+        g.ctx, g.h, g._borrowed = ctx, handle, True
+        return g
+
     def close(self):
-        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None) and not getattr(self, "_borrowed", False):
             self.ctx.L.dl_grid_destroy(self.h)
         self.h = None
 

@@ -492,6 +492,66 @@ int dl_frontend_match_batch_dev(dl_context* ctx, const dl_frontend_options* opti
 int dl_frontend_fetch_results(dl_context* ctx, const dl_scan_result* results_dev, int32_t num_scans,
                               dl_scan_result* results);
 
+/* ---- scan_matching::RotationalScanMatcher::ComputeHistogram (SM/rotational_scan_matcher.cc:31-121, :159-170) on the device: the
+ *      histogram LocalTrajectoryBuilder3D::InsertIntoSubmap stores with every inserted node (LTB:605-610). points: n x 3 floats,
+ *      already rotated by the node's gravity alignment. Float sums keep the reference's order; atan2f is the device's, so the
+ *      result agrees with the CPU to float tolerance, not bit for bit. size <= 1024. ------------------------------------------ */
+int dl_rotational_histogram(dl_context* ctx, const float* points, int64_t n, int32_t size, float* histogram_out);
+
+/* ---- mapping::LocalTrajectoryBuilder3D (C/mapping/internal/3d/local_trajectory_builder_3d.h:81-113): the per-trajectory front-end
+ *      object. AddImuData / AddRangeData -> MatchingResult{time, local_pose, range_data_in_local, InsertionResult}. Behind it:
+ *      the IMU-coupled front end above against the matching submap (active submaps' front, LTB:502-505), the motion filter
+ *      (C/mapping/internal/motion_filter.cc:37-57), Submap3D::InsertRangeData into both active submaps and the submap hand-over
+ *      (C/mapping/3d/submap_3d.cc:264-279, :300-326) on the DEVICE grids, and the rotational histogram of the inserted scan.
+ *      Deliberate differences from the reference: the pose comes from the fused scan-match + IMU solve instead of the match
+ *      followed by the GTSAM window (LTB:535-555); num_accumulated_range_data = 1; one range sensor per builder (several are
+ *      merged on the host by dliom::sensor::RangeDataSynchronizer, host/dliom_b200.hpp); initialisation = InitializeStatic
+ *      (LTB:203-229) or dl_ltb_set_initial_state instead of the PCL NDT variant. ------------------------------------------- */
+typedef struct dl_local_trajectory_builder dl_local_trajectory_builder;
+typedef struct dl_ltb_options { /* proto::LocalTrajectoryBuilderOptions3D, the fields this path reads */
+  dl_frontend_options frontend;                    /* ranges, voxel filters, adaptive filters, ceres options, scan_period */
+  dl_imu_noise imu_noise;                          /* imu_options: acc / gyr noise and bias random walk */
+  double imu_weight;                               /* weight of the pre-integration residual in the fused solve */
+  double gravity;                                  /* imu_options.gravity (9.8) */
+  float high_resolution, low_resolution;           /* submaps: 0.1 / 0.45 */
+  int32_t num_range_data;                          /* submaps.num_range_data */
+  int32_t high_resolution_max_range;               /* submaps.high_resolution_max_range */
+  dl_range_data_inserter_options range_data_inserter;
+  double motion_filter_max_time_seconds, motion_filter_max_distance_meters, motion_filter_max_angle_radians;
+  int32_t rotational_histogram_size;
+  int32_t frames_for_static_initialization;        /* 7 in the reference (LTB:376) */
+} dl_ltb_options;
+typedef struct dl_matching_result {
+  int32_t has_result;                              /* 0 <=> the reference returns nullptr (initialising, no IMU yet, scan dropped) */
+  int32_t inserted;                                /* 0 <=> insertion_result == nullptr (motion filter) */
+  double time;
+  double local_pose[7];
+  dl_nav_state state;                              /* pose + velocity + biases of the node (the reference's prev_state_ / prev_bias_) */
+  dl_scan_result scan;                             /* the front end's bookkeeping for this scan */
+  float origin_in_local[3];                        /* range_data_in_local.origin */
+  int32_t num_returns, num_misses, num_high_resolution, num_low_resolution;
+  int32_t num_insertion_submaps;                   /* insertion_submaps, queried before the insert (LTB:592-597) */
+  int32_t insertion_submap_index[2];
+  int32_t reserved;
+} dl_matching_result;
+int dl_ltb_create(dl_context* ctx, const dl_ltb_options* options, dl_local_trajectory_builder** out);
+void dl_ltb_destroy(dl_local_trajectory_builder* builder);
+int dl_ltb_set_initial_state(dl_local_trajectory_builder* builder, const dl_nav_state* state);
+int dl_ltb_add_imu_data(dl_local_trajectory_builder* builder, double time, const double* linear_acceleration,
+                        const double* angular_velocity);
+/* xyzt: n TimedPointCloud rows (x y z t, t <= 0 relative to `time`, the last point's acquisition); origin: 3 floats (tracking frame). */
+int dl_ltb_add_range_data(dl_local_trajectory_builder* builder, double time, const float* xyzt, int64_t n, const float* origin,
+                          dl_matching_result* result);
+/* Clouds of the last scan that produced a result. which: 0 returns / 1 misses of range_data_in_local, 2 / 3 the high / low
+ * resolution point clouds in the tracking frame (TrajectoryNode::Data). Pass out = NULL to query *num_points. */
+int dl_ltb_get_cloud(const dl_local_trajectory_builder* builder, int32_t which, float* out, int64_t capacity_points, int64_t* num_points);
+int dl_ltb_get_histogram(const dl_local_trajectory_builder* builder, float* out, int32_t capacity);
+int32_t dl_ltb_num_submaps(const dl_local_trajectory_builder* builder);
+/* Submap `index` (0 = the first ever created): its device grids (owned by the builder), local pose, insert count, finished flag. */
+int dl_ltb_get_submap(dl_local_trajectory_builder* builder, int32_t index, dl_grid** high_resolution_grid,
+                      dl_grid** low_resolution_grid, double* local_pose, int32_t* num_range_data, int32_t* finished);
+int dl_ltb_get_state(const dl_local_trajectory_builder* builder, dl_nav_state* state, int32_t* initialized);
+
 /* Device memory helpers so a host language without CUDA bindings can stage buffers. */
 int dl_device_alloc(dl_context* ctx, int64_t bytes, void** out_dev);
 int dl_device_free(dl_context* ctx, void* dev);

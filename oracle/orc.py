@@ -207,6 +207,15 @@ class Grid:
         if self.L.orc_grid_set_value(self.h, int(idx[0]), int(idx[1]), int(idx[2]), int(v)):
             raise RuntimeError("grid growth limit")
 
+    def set_cells(self, xs, ys, zs, values):
+        """Bulk set_value from the ToProto layout (what Grid.export() of either implementation returns)."""
+        xs, ys, zs = (np.ascontiguousarray(a, np.int32) for a in (xs, ys, zs))
+        values = np.ascontiguousarray(values, np.uint16)
+        f = self.L.orc_grid_set_cells
+        if f(self.h, C.c_int64(len(xs)), xs.ctypes.data_as(C.c_void_p), ys.ctypes.data_as(C.c_void_p),
+             zs.ctypes.data_as(C.c_void_p), values.ctypes.data_as(C.c_void_p)):
+            raise RuntimeError("grid growth limit")
+
     def value(self, idx):
         return self.L.orc_grid_value(self.h, int(idx[0]), int(idx[1]), int(idx[2]))
 

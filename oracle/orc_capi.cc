@@ -55,6 +55,13 @@ int orc_grid_set_value(void* g, int x, int y, int z, uint16_t v) {
   try { *((HybridGrid*)g)->mutable_value({x, y, z}) = v; } catch (...) { return 1; }
   return 0;
 }
+// Bulk form of orc_grid_set_value (the HybridGrid::ToProto layout: parallel x / y / z / value arrays). Returns 1 past the growth limit.
+int orc_grid_set_cells(void* g, int64_t n, const int32_t* x, const int32_t* y, const int32_t* z, const uint16_t* v) {
+  try {
+    for (int64_t i = 0; i < n; ++i) *((HybridGrid*)g)->mutable_value({x[i], y[i], z[i]}) = v[i];
+  } catch (...) { return 1; }
+  return 0;
+}
 uint16_t orc_grid_value(void* g, int x, int y, int z) { return ((HybridGrid*)g)->value({x, y, z}); }
 float orc_grid_probability(void* g, int x, int y, int z) { return ((HybridGrid*)g)->GetProbability({x, y, z}); }
 void orc_grid_cell_index(void* g, const float* p, int* out) {

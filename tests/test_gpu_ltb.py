@@ -1,0 +1,195 @@
+"""mapping::LocalTrajectoryBuilder3D over the device path (dl_ltb_*; reference interface local_trajectory_builder_3d.h:81-113):
+a synthetic drive fed sample by sample (200 Hz IMU, 10 Hz 16-beam scans). Every scan is checked against the oracle chain run on
+the builder's OWN state and maps at that scan (its submap grids are exported and loaded into oracle grids), so the comparison
+is per call and does not fork: pose / velocity / biases of the fused solve, the node's point clouds bit for bit, the device
+histogram, the submap bookkeeping of ActiveSubmaps3D and the inserted grids cell for cell."""
+import numpy as np
+import pytest
+
+import imu_synth
+from helpers import apply_pose, pose_error
+
+pytestmark = pytest.mark.gpu
+NOISE = [3.99e-2, 1.56e-2, 6.4e-5, 3.6e-5]
+
+
+def drive(n):
+    import synth
+    scene = synth.Scene(42)
+    times = [2.0 + 0.1 * k for k in range(n)]
+    return times, [synth.make_scan(scene, 16, t) for t in times]
+
+
+def make_builder(ctx, orc, **kw):
+    import dliom
+    fo = dliom.FrontendOptions.from_oracle(orc.FrontEndOptions.defaults())
+    return dliom.LocalTrajectoryBuilder(ctx, dliom.LtbOptions.defaults(fo, NOISE, imu_weight=0.7, **kw))
+
+
+def oracle_grids(orc, hi, lo):
+    ohi, olo = orc.Grid(0.1), orc.Grid(0.45)
+    ohi.set_cells(*hi.export())
+    olo.set_cells(*lo.export())
+    return ohi, olo
+
+
+def cells(export):
+    return {(int(x), int(y), int(z)): int(v) for x, y, z, v in zip(*export)}
+
+
+def test_builder_follows_the_oracle_chain_scan_by_scan(orc):
+    import dliom
+    ctx = dliom.Context(0)
+    opts = orc.FrontEndOptions.defaults()
+    times, scans = drive(12)
+    b = make_builder(ctx, orc, num_range_data=5, max_time_seconds=0.05)   # 0.1 s between scans: the motion filter never drops
+    b.set_initial_state(imu_synth.state(times[0] - 0.1))
+    origin = np.zeros((1, 3), np.float32)
+    last_t = None
+    latch = None
+    submap0_returns = []
+    inserted = 0
+    matching_index = 0
+    for k, (t1, rows) in enumerate(zip(times, scans)):
+        dt, acc, gyr = imu_synth.samples(t1 - 0.1, t1)
+        ts = t1 - 0.1 + np.arange(len(dt)) / 200.0
+        first = 0 if k == 0 else 1          # sample 0 of an interval is the last sample of the previous one
+        iv_dt, iv_acc, iv_gyr = ([latch[0]] if latch else []), ([latch[1]] if latch else []), ([latch[2]] if latch else [])
+        for j in range(first, len(dt)):
+            b.add_imu_data(ts[j], acc[j], gyr[j])
+            d = 1.0 / 500.0 if last_t is None else ts[j] - last_t
+            last_t = ts[j]
+            iv_dt.append(d); iv_acc.append(acc[j]); iv_gyr.append(gyr[j])
+        latch = (iv_dt[-1], iv_acc[-1], iv_gyr[-1])
+        state_i, init = b.state()
+        assert init
+        hi, lo, sp, nrd, fin = b.submap(matching_index)
+        ohi, olo = oracle_grids(orc, hi, lo)
+        xyzt = np.stack([rows["x"], rows["y"], rows["z"], rows["t"]], 1)
+        r = b.add_range_data(t1, xyzt)
+        assert r.has_result == 1 and r.inserted == 1 and r.scan.ok == 1
+        secs, want, pred, ok, iters = orc.frontend_batch_imu(opts, [rows], origin, NOISE, [state_i], [(np.array(iv_dt), np.array(iv_acc), np.array(iv_gyr))],
+                                                             sp, ohi, olo, 1, imu_weight=0.7)
+        assert ok[0] == 1
+        got = NavStateVec(r.state)
+        dtn, drn = pose_error(got[:7], want[0][:7])
+        assert dtn < 1e-6 and drn < 1e-7, (k, dtn, drn)
+        assert np.allclose(got[7:], want[0][7:], atol=1e-6)
+        assert np.allclose(np.array(r.local_pose[:]), got[:7], atol=0)
+        assert r.scan.summary.num_iterations == iters[0]
+        # the node's clouds: adaptive filter outputs of the returns in the tracking frame, bit for bit
+        ing = orc.ingest_scan(opts, rows, origin, state_i[:7], pred[0][:7])
+        pts = ing["returns_tracking"]
+        hk, _ = orc.adaptive_voxel_filter(pts, opts.hi_max_length, opts.hi_min_num_points, opts.hi_max_range)
+        lk, _ = orc.adaptive_voxel_filter(pts, opts.lo_max_length, opts.lo_min_num_points, opts.lo_max_range)
+        assert np.array_equal(b.cloud(2).view(np.uint32), pts[hk].view(np.uint32))
+        assert np.array_equal(b.cloud(3).view(np.uint32), pts[lk].view(np.uint32))
+        assert (r.num_returns, r.num_high_resolution, r.num_low_resolution) == (len(pts), len(hk), len(lk))
+        # range_data_in_local = opt_pose.cast<float>() * returns (float transform; compared to the double one to float accuracy)
+        local = b.cloud(0)
+        assert len(local) == len(pts) and np.abs(local - apply_pose(got[:7], pts.astype(np.float64))).max() < 2e-4
+        assert len(b.cloud(1)) == r.num_misses
+        # rotational histogram of the gravity-aligned returns (device atan2f: tolerance, not bits)
+        aligned = apply_pose(np.concatenate([[0, 0, 0], got[3:7]]), pts.astype(np.float64)).astype(np.float32)
+        wh = orc.compute_histogram(aligned, 120)
+        gh = b.histogram()
+        assert abs(gh.sum() - wh.sum()) <= 2e-3 * wh.sum() + 1e-3
+        assert np.abs(gh - wh).sum() <= 0.02 * wh.sum() + 1e-3
+        # ActiveSubmaps3D bookkeeping (submap_3d.cc:300-326)
+        inserted += 1
+        expect_insertion = [0] if inserted <= 5 else ([0, 1] if inserted <= 10 else [1, 2])
+        assert [r.insertion_submap_index[i] for i in range(r.num_insertion_submaps)] == expect_insertion
+        if inserted <= 10:
+            submap0_returns.append((np.array(r.origin_in_local[:], np.float32), local.copy()))
+        if inserted == 10:
+            matching_index = 1          # submap 0 finished when submap 2 was added; submap 1 is the matching submap now
+    assert b.num_submaps() == 3
+    _, _, p0, n0, f0 = b.submap(0)
+    _, _, p1, n1, f1 = b.submap(1)
+    _, _, p2, n2, f2 = b.submap(2)
+    assert (n0, f0, n1, f1, n2, f2) == (10, True, 7, False, 2, False)
+    assert np.array_equal(p0, orc.IDENTITY_POSE) and np.linalg.norm(p1[:3]) > 0.3
+    # submap 0 lives at the identity: its grids must equal the oracle inserter fed with the same ten range data
+    ohi, olo = orc.Grid(0.1), orc.Grid(0.45)
+    for o, local in submap0_returns:
+        d = local - o
+        r2 = (d[:, 0] * d[:, 0] + (d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2])).astype(np.float32)
+        ohi.insert_range_data(o, local[np.sqrt(r2).astype(np.float32) <= np.float32(20.0)])
+        olo.insert_range_data(o, local)
+    hi0, lo0, *_ = b.submap(0)
+    assert cells(hi0.export()) == cells(ohi.export()) and cells(lo0.export()) == cells(olo.export())
+    b.close()
+    ctx.close()
+
+
+def NavStateVec(s):
+    return np.array(list(s.p) + list(s.q) + list(s.v) + list(s.ba) + list(s.bg))
+
+
+def test_builder_initialisation_motion_filter_and_drops(orc):
+    """InitializeStatic from the buffered IMU (LTB:203-229), the motion filter (motion_filter.cc:37-57), no-IMU and empty scans."""
+    import dliom
+    ctx = dliom.Context(0)
+    times, scans = drive(4)
+    xyzt = [np.stack([r["x"], r["y"], r["z"], r["t"]], 1) for r in scans]
+    b = make_builder(ctx, orc, frames_for_static_initialization=1, max_time_seconds=5.0, max_distance_meters=50.0, max_angle_radians=3.0)
+    # a tilted, resting IMU: specific force = R^T (0, 0, 9.8) + bias_a; rate = bias_g
+    tilt = imu_synth.state(0.0)
+    roll = 0.05
+    Rt_g = np.array([0.0, 9.8 * np.sin(roll), 9.8 * np.cos(roll)])
+    for j in range(200):
+        b.add_imu_data(j / 200.0, Rt_g, [1e-3, -2e-3, 5e-4])
+    for k in range(3):     # LTB:376: `accumulated_frame_num++ > frames` -> the third scan initialises, none of them is matched
+        r = b.add_range_data(1.0 + 0.1 * k, xyzt[0])
+        assert r.has_result == 0
+    st, init = b.state()
+    assert init
+    # gravity alignment: R takes the measured up direction (0, sin, cos) to +z -> +0.05 about x; biases: gyro mean, accelerometer ~ 0
+    assert np.allclose(st[3:7], [np.cos(roll / 2), np.sin(roll / 2), 0, 0], atol=1e-9)
+    assert np.allclose(st[13:16], [1e-3, -2e-3, 5e-4], atol=1e-12) and np.abs(st[10:13]).max() < 1e-9
+    assert np.allclose(st[:3], 0) and np.allclose(st[7:10], 0)
+    # no IMU since the last scan -> nullptr (predicted_states_.empty(), LTB:426); an empty scan -> nullptr
+    assert b.add_range_data(1.3, xyzt[0]).has_result == 0
+    assert b.add_range_data(1.4, np.zeros((0, 4), np.float32)).has_result == 0
+    # motion filter: with generous thresholds only the first matched scan is inserted
+    b2 = make_builder(ctx, orc, max_time_seconds=5.0, max_distance_meters=50.0, max_angle_radians=3.0)
+    b2.set_initial_state(imu_synth.state(times[0] - 0.1))
+    flags = []
+    last = None
+    for k, t1 in enumerate(times):
+        dt, acc, gyr = imu_synth.samples(t1 - 0.1, t1)
+        for j in range(0 if k == 0 else 1, len(dt)):
+            b2.add_imu_data(t1 - 0.1 + j / 200.0, acc[j], gyr[j])
+        r = b2.add_range_data(t1, xyzt[k])
+        assert r.has_result == 1
+        flags.append(r.inserted)
+    assert flags == [1, 0, 0, 0]
+    _, _, _, n0, _ = b2.submap(0)
+    assert n0 == 1 and b2.num_submaps() == 1
+    b.close(); b2.close(); ctx.close()
+
+
+def test_rotational_histogram_against_oracle(orc):
+    import dliom
+    ctx = dliom.Context(0)
+    times, scans = drive(2)
+    opts = orc.FrontEndOptions.defaults()
+    for rows, t in zip(scans, times):
+        import synth
+        pts = orc.ingest_scan(opts, rows, np.zeros((1, 3), np.float32), synth.pose7(t - 0.1), synth.pose7(t))["returns_tracking"]
+        want = orc.compute_histogram(pts, 120)
+        got = np.zeros(120, np.float32)
+        ctx.check(ctx.L.dl_rotational_histogram(ctx.h, np.ascontiguousarray(pts), len(pts), 120, got))
+        assert want.sum() > 1.0
+        assert abs(got.sum() - want.sum()) <= 2e-3 * want.sum()
+        assert np.abs(got - want).sum() <= 0.02 * want.sum()
+    # tiny hand-made slice: four corners of a square ring + an interior point (dropped: closer than 0.2 m to the centroid)
+    sq = np.array([[1, 0, 0.0], [0, 1, 0.0], [-1, 0, 0.0], [0, -1, 0.0], [0.05, 0.0, 0.0]], np.float32) * np.float32(0.5)
+    want = orc.compute_histogram(sq, 8)
+    got = np.zeros(8, np.float32)
+    ctx.check(ctx.L.dl_rotational_histogram(ctx.h, sq, len(sq), 8, got))
+    assert np.allclose(got, want, atol=1e-5)
+    empty = np.ones(8, np.float32)
+    ctx.check(ctx.L.dl_rotational_histogram(ctx.h, np.zeros((1, 3), np.float32), 0, 8, empty))   # no points: all zero
+    assert not empty.any()
+    ctx.close()
