@@ -2557,8 +2557,15 @@ int dl_ltb_add_imu_data(dl_local_trajectory_builder* b, double time, const doubl
 
 int dl_ltb_add_range_data(dl_local_trajectory_builder* b, double time, const float* xyzt, int64_t n, const float* origin,
                           dl_matching_result* out) {
-  if (!b || !out || n < 0 || (n > 0 && !xyzt) || !origin) return DL_ERR_ARG;
+  return dl_ltb_add_synchronized_range_data(b, time, xyzt, n, 4, origin, 1, out);
+}
+
+int dl_ltb_add_synchronized_range_data(dl_local_trajectory_builder* b, double time, const void* rows, int64_t n, int32_t row_floats,
+                                       const float* origin, int32_t num_origins, dl_matching_result* out) {
+  if (!b || !out || n < 0 || (n > 0 && !rows) || !origin || num_origins < 1 || (row_floats != 4 && row_floats != 8)) return DL_ERR_ARG;
+  if (row_floats == 4 && num_origins != 1) return b->ctx->fail(DL_ERR_ARG, "x y z t rows carry no origin index: one origin only");
   dl_context* ctx = b->ctx;
+  const void* xyzt = rows;
   std::memset(out, 0, sizeof(*out));
   out->time = time;
   if (n == 0) return DL_OK;  // "Range data collator filling buffer" (LTB:366-369)
@@ -2597,7 +2604,8 @@ int dl_ltb_add_range_data(dl_local_trajectory_builder* b, double time, const flo
     return DL_OK;
   }
   if (b->dt.size() < 2) return DL_OK;  // predicted_states_.empty() (LTB:426): no IMU since the last scan
-  const dl_frontend_options& fo = b->opt.frontend;
+  dl_frontend_options fo = b->opt.frontend;
+  fo.range_row_floats = row_floats;
   dl_frontend_imu_samples imu{};
   imu.noise = b->opt.imu_noise;
   imu.imu_weight = b->opt.imu_weight;
@@ -2616,8 +2624,8 @@ int dl_ltb_add_range_data(dl_local_trajectory_builder* b, double time, const flo
   ImuRun run;
   run.samples = &imu;
   FrontendBuffers f;
-  DL_TRY(frontend_enqueue_host(ctx, &fo, 1, ranges, sizes, origin, 1, nullptr, nullptr, submap_pose, matching.hi, matching.lo, 0,
-                               &d_results, &run, &f));
+  DL_TRY(frontend_enqueue_host(ctx, &fo, 1, ranges, sizes, origin, num_origins, nullptr, nullptr, submap_pose, matching.hi, matching.lo,
+                               0, &d_results, &run, &f));
   dl_scan_result r{};
   dl_nav_state state{};
   float cur7[7];

@@ -33,7 +33,7 @@ EXPORTS = [
     "dl_comm_unique_id", "dl_comm_create", "dl_comm_destroy", "dl_comm_rank", "dl_comm_world_size", "dl_comm_last_error",
     "dl_comm_all_gather_dev", "dl_comm_all_reduce_f64_dev", "dl_comm_broadcast_dev", "dl_constraint_search_exchange",
     "dl_rotational_histogram", "dl_ltb_create", "dl_ltb_destroy", "dl_ltb_set_initial_state", "dl_ltb_add_imu_data",
-    "dl_ltb_add_range_data", "dl_ltb_get_cloud", "dl_ltb_get_histogram", "dl_ltb_num_submaps", "dl_ltb_get_submap", "dl_ltb_get_state",
+    "dl_ltb_add_range_data", "dl_ltb_add_synchronized_range_data", "dl_ltb_get_cloud", "dl_ltb_get_histogram", "dl_ltb_num_submaps", "dl_ltb_get_submap", "dl_ltb_get_state",
 ]
 
 
@@ -366,6 +366,7 @@ def lib():
     L.dl_ltb_set_initial_state.argtypes = [vp, ip(NavState)]
     L.dl_ltb_add_imu_data.argtypes = [vp, C.c_double, f64p, f64p]
     L.dl_ltb_add_range_data.argtypes = [vp, C.c_double, f32p, C.c_int64, f32p, ip(MatchingResult)]
+    L.dl_ltb_add_synchronized_range_data.argtypes = [vp, C.c_double, vp, C.c_int64, C.c_int32, f32p, C.c_int32, ip(MatchingResult)]
     L.dl_ltb_get_cloud.argtypes = [vp, C.c_int32, vp, C.c_int64, ip(C.c_int64)]
     L.dl_ltb_get_histogram.argtypes = [vp, f32p, C.c_int32]
     L.dl_ltb_num_submaps.argtypes = [vp]
@@ -823,6 +824,15 @@ class LocalTrajectoryBuilder:
         out = MatchingResult()
         self.ctx.check(self.ctx.L.dl_ltb_add_range_data(self.h, float(time), rows, len(rows), np.ascontiguousarray(origin, np.float32),
                                                         C.byref(out)))
+        return out
+
+    def add_synchronized_range_data(self, time, rows, origins):
+        """rows: RANGE_DTYPE-like 32-byte RangeMeasurement records (x y z t + u64 origin index), time-sorted; origins: (k, 3)."""
+        rows = np.ascontiguousarray(rows)
+        origins = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        out = MatchingResult()
+        self.ctx.check(self.ctx.L.dl_ltb_add_synchronized_range_data(self.h, float(time), rows.ctypes.data, len(rows), 8, origins,
+                                                                     len(origins), C.byref(out)))
         return out
 
     def cloud(self, which):

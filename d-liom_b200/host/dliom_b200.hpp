@@ -5,12 +5,18 @@
 //   sensor::VoxelFilter, sensor::AdaptiveVoxelFilter        C/sensor/internal/voxel_filter.h:34-79
 //   scan_matching::RealTimeCorrelativeScanMatcher3D          SM/real_time_correlative_scan_matcher_3d.h:33-60
 //   scan_matching::CeresScanMatcher3D                        SM/ceres_scan_matcher_3d.h:34-61
+//   mapping::RangeDataSynchronizer                           C/mapping/internal/3d/range_data_synchronizer.h:30-68
+//   mapping::LocalTrajectoryBuilder3D                        C/mapping/internal/3d/local_trajectory_builder_3d.h:81-113
 // Eigen / protobuf types are replaced by the plain structs below (this image has neither); INTEGRATION.md shows
 // the three-line adapters for Eigen::Vector3f / transform::Rigid3d / proto options in a real Cartographer tree.
 // Errors: the reference CHECK-aborts; this shim throws dliom::Error carrying the C-ABI status and message.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
+#include <cstring>
+#include <deque>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -349,4 +355,211 @@ class ConstraintBuilder3D {
 };
 
 }  // namespace constraints
+
+namespace sensor {
+struct ImuData {  // sensor::ImuData (C/sensor/imu_data.h)
+  double time;
+  std::array<double, 3> linear_acceleration, angular_velocity;
+};
+struct TimedPointCloudData {  // sensor::TimedPointCloudData (C/sensor/timed_point_cloud_data.h:27-31)
+  double time;  // acquisition time of the LAST point; ranges[i][3] <= 0 is relative to it
+  std::array<float, 3> origin;
+  TimedPointCloud ranges;
+};
+struct RangeMeasurement {  // TimedPointCloudOriginData::RangeMeasurement (timed_point_cloud_data.h:33-42), 32 bytes
+  std::array<float, 4> point_time;
+  uint64_t origin_index;
+  uint64_t pad_ = 0;
+};
+static_assert(sizeof(RangeMeasurement) == 32, "RangeMeasurement layout");
+struct TimedPointCloudOriginData {
+  double time = 0;
+  std::vector<std::array<float, 3>> origins;
+  std::vector<RangeMeasurement> ranges;
+};
+struct RangeData {  // sensor::RangeData
+  std::array<float, 3> origin;
+  PointCloud returns, misses;
+};
+}  // namespace sensor
+
+namespace mapping {
+
+// range_data_synchronizer.{h,cc}: the FIRST expected sensor is the prior LiDAR; clouds of the others are queued and the part of
+// the oldest queued cloud that overlaps the prior cloud's sweep [start, end] is merged into it, re-stamped relative to the prior
+// cloud's end and sorted by time. Host bookkeeping before the path, kept on the host here too.
+class RangeDataSynchronizer {
+ public:
+  explicit RangeDataSynchronizer(const std::vector<std::string>& expected_range_sensor_ids)
+      : expected_sensor_ids_(expected_range_sensor_ids.begin(), expected_range_sensor_ids.end()),
+        prior_sensor_id_(expected_range_sensor_ids.empty() ? std::string() : expected_range_sensor_ids.front()) {}
+
+  sensor::TimedPointCloudOriginData AddRangeData(const std::string& sensor_id, const sensor::TimedPointCloudData& data, bool deskew) {
+    if (!expected_sensor_ids_.count(sensor_id)) throw Error(DL_ERR_ARG, "unexpected range sensor id (CHECK_NE)");
+    sensor::TimedPointCloudOriginData result;
+    sensor::TimedPointCloudData cloud = data;
+    if (deskew) StampRangeData(&cloud, 0.1);
+    if (sensor_id != prior_sensor_id_) {
+      secondary_.push_back(cloud);
+      return result;
+    }
+    if (secondary_.empty() || cloud.ranges.empty()) return Single(cloud);
+    const double end = cloud.time, start = end + cloud.ranges.front()[3];
+    while (!secondary_.empty() && secondary_.front().time < start) secondary_.pop_front();  // pop old clouds
+    if (secondary_.empty()) return Single(cloud);
+    const sensor::TimedPointCloudData& sec = secondary_.front();
+    if (sec.ranges.empty() || sec.time + sec.ranges.front()[3] > end) return Single(cloud);  // "secondary lidar may be too fast"
+    int i_start = -1, i_end = -1;
+    for (int i = 0; i < (int)sec.ranges.size(); ++i) {
+      const double t = sec.time + sec.ranges[i][3];
+      if (t >= start && t <= end && i_start == -1) i_start = i;
+      if (i_start != -1 && t > end) {
+        i_end = i - 1;
+        break;
+      }
+    }
+    if (i_start == -1) throw Error(DL_ERR_ARG, "no overlap between the two sweeps (CHECK)");
+    if (i_end == -1) i_end = (int)sec.ranges.size() - 1;
+    result.time = cloud.time;
+    result.origins = {cloud.origin, sec.origin};
+    result.ranges.reserve(cloud.ranges.size() + (size_t)(i_end - i_start + 1));
+    for (size_t i = 0; i < cloud.ranges.size(); ++i) result.ranges.push_back({data.ranges[i], 0});  // the prior cloud keeps its own times
+    for (int i = i_start; i <= i_end; ++i) {
+      sensor::RangeMeasurement m{sec.ranges[i], 1};
+      const double relative_t = sec.ranges[i][3];
+      m.point_time[3] = (float)(relative_t + sec.time - end);
+      result.ranges.push_back(m);
+    }
+    std::stable_sort(result.ranges.begin(), result.ranges.end(),
+                     [](const sensor::RangeMeasurement& a, const sensor::RangeMeasurement& b) { return a.point_time[3] < b.point_time[3]; });
+    return result;
+  }
+
+ private:
+  static sensor::TimedPointCloudOriginData Single(const sensor::TimedPointCloudData& cloud) {  // ToTimedPointCloudOriginData
+    sensor::TimedPointCloudOriginData r;
+    r.time = cloud.time;
+    r.origins = {cloud.origin};
+    r.ranges.reserve(cloud.ranges.size());
+    for (const auto& p : cloud.ranges) r.ranges.push_back({p, 0});
+    return r;
+  }
+  static void StampRangeData(sensor::TimedPointCloudData* cloud, double scan_period) {  // :117-131, the "very naive" stamping
+    const int n = (int)cloud->ranges.size();
+    if (n < 2) return;
+    const double duration = scan_period / (n - 1);
+    for (int i = 0; i < n; ++i) cloud->ranges[i][3] = (float)(-scan_period + i * duration);
+    cloud->ranges.back()[3] = 0.f;
+  }
+  const std::set<std::string> expected_sensor_ids_;
+  const std::string prior_sensor_id_;
+  std::deque<sensor::TimedPointCloudData> secondary_;
+};
+
+struct LocalTrajectoryBuilderOptions3D {  // proto::LocalTrajectoryBuilderOptions3D, the fields the path reads
+  dl_ltb_options c{};
+  bool enable_manual_deskew = false;      // eable_mannually_discrew: re-stamp the points uniformly over the scan period
+  LocalTrajectoryBuilderOptions3D() {     // trajectory_builder_3d.lua defaults
+    dl_frontend_options& f = c.frontend;
+    f.min_range = 1.f; f.max_range = 60.f; f.voxel_filter_size = 0.15f;
+    f.high_resolution_adaptive_voxel_filter = {2.f, 150.f, 15.f};
+    f.low_resolution_adaptive_voxel_filter = {4.f, 200.f, 60.f};
+    f.scan_period = 0.1;
+    f.ceres_scan_matcher.num_occupied_space_weights = 2;
+    f.ceres_scan_matcher.occupied_space_weight[0] = 1.; f.ceres_scan_matcher.occupied_space_weight[1] = 6.;
+    f.ceres_scan_matcher.translation_weight = 5.; f.ceres_scan_matcher.rotation_weight = 4e2;
+    f.ceres_scan_matcher.max_num_iterations = 12; f.ceres_scan_matcher.num_threads = 1;
+    c.imu_noise = {3.99e-2, 1.56e-2, 6.4e-5, 3.6e-5};
+    c.imu_weight = 1.; c.gravity = 9.8;
+    c.high_resolution = 0.1f; c.low_resolution = 0.45f; c.num_range_data = 160; c.high_resolution_max_range = 20;
+    c.range_data_inserter = {0.55, 0.49, 2, 0};
+    c.motion_filter_max_time_seconds = 0.5; c.motion_filter_max_distance_meters = 0.1; c.motion_filter_max_angle_radians = 0.004;
+    c.rotational_histogram_size = 120; c.frames_for_static_initialization = 7;
+  }
+};
+
+struct TrajectoryNodeData {  // mapping::TrajectoryNode::Data (C/mapping/trajectory_node.h)
+  double time;
+  std::array<double, 4> gravity_alignment;  // w x y z
+  PointCloud high_resolution_point_cloud, low_resolution_point_cloud;
+  std::vector<float> rotational_scan_matcher_histogram;
+  Rigid3d local_pose;
+};
+
+class LocalTrajectoryBuilder3D {  // local_trajectory_builder_3d.h:81-113
+ public:
+  struct InsertionResult {
+    std::shared_ptr<const TrajectoryNodeData> constant_data;
+    std::vector<int> insertion_submaps;  // indices; the grids are reachable through submap()
+  };
+  struct MatchingResult {
+    double time;
+    Rigid3d local_pose;
+    sensor::RangeData range_data_in_local;
+    std::unique_ptr<const InsertionResult> insertion_result;  // nullptr if dropped by the motion filter
+  };
+  LocalTrajectoryBuilder3D(Context* ctx, const LocalTrajectoryBuilderOptions3D& options,
+                           const std::vector<std::string>& expected_range_sensor_ids)
+      : ctx_(ctx), options_(options), synchronizer_(expected_range_sensor_ids) {
+    ctx->check(dl_ltb_create(ctx->get(), &options.c, &builder_));
+  }
+  ~LocalTrajectoryBuilder3D() { dl_ltb_destroy(builder_); }
+  LocalTrajectoryBuilder3D(const LocalTrajectoryBuilder3D&) = delete;
+  LocalTrajectoryBuilder3D& operator=(const LocalTrajectoryBuilder3D&) = delete;
+
+  void AddImuData(const sensor::ImuData& imu_data) {
+    ctx_->check(dl_ltb_add_imu_data(builder_, imu_data.time, imu_data.linear_acceleration.data(), imu_data.angular_velocity.data()));
+  }
+  // Returns nullptr while initialising, when no IMU arrived since the last scan, when the secondary LiDAR's cloud was only
+  // queued, or when the scan was dropped (empty filtered clouds), like the reference.
+  std::unique_ptr<MatchingResult> AddRangeData(const std::string& sensor_id, const sensor::TimedPointCloudData& unsynchronized_data) {
+    const sensor::TimedPointCloudOriginData data = synchronizer_.AddRangeData(sensor_id, unsynchronized_data, options_.enable_manual_deskew);
+    if (data.ranges.empty()) return nullptr;
+    dl_matching_result r{};
+    ctx_->check(dl_ltb_add_synchronized_range_data(builder_, data.time, data.ranges.data(), (int64_t)data.ranges.size(), 8,
+                                                   data.origins[0].data(), (int32_t)data.origins.size(), &r));
+    if (!r.has_result) return nullptr;
+    std::unique_ptr<MatchingResult> out(new MatchingResult);
+    out->time = r.time;
+    out->local_pose = Rigid3d::from7(r.local_pose);
+    out->range_data_in_local.origin = {r.origin_in_local[0], r.origin_in_local[1], r.origin_in_local[2]};
+    out->range_data_in_local.returns = Cloud(0);
+    out->range_data_in_local.misses = Cloud(1);
+    if (r.inserted) {
+      auto node = std::make_shared<TrajectoryNodeData>();
+      node->time = r.time;
+      node->gravity_alignment = {r.local_pose[3], r.local_pose[4], r.local_pose[5], r.local_pose[6]};
+      node->high_resolution_point_cloud = Cloud(2);
+      node->low_resolution_point_cloud = Cloud(3);
+      node->rotational_scan_matcher_histogram.resize(options_.c.rotational_histogram_size);
+      ctx_->check(dl_ltb_get_histogram(builder_, node->rotational_scan_matcher_histogram.data(), options_.c.rotational_histogram_size));
+      node->local_pose = out->local_pose;
+      std::unique_ptr<InsertionResult> ins(new InsertionResult);
+      ins->constant_data = node;
+      for (int k = 0; k < r.num_insertion_submaps; ++k) ins->insertion_submaps.push_back(r.insertion_submap_index[k]);
+      out->insertion_result = std::move(ins);
+    }
+    return out;
+  }
+  void AddOdometryData(double /*time*/, const Rigid3d& /*pose*/) {}  // the fork never constructs its extrapolator (LTB:574-582)
+  // Replaces the NDT initialisation when the caller knows the state (tests, re-localisation).
+  void SetInitialState(const dl_nav_state& state) { ctx_->check(dl_ltb_set_initial_state(builder_, &state)); }
+  int num_submaps() const { return dl_ltb_num_submaps(builder_); }
+  dl_local_trajectory_builder* get() const { return builder_; }
+
+ private:
+  PointCloud Cloud(int which) const {
+    int64_t n = 0;
+    ctx_->check(dl_ltb_get_cloud(builder_, which, nullptr, 0, &n));
+    PointCloud c((size_t)n);
+    if (n) ctx_->check(dl_ltb_get_cloud(builder_, which, c[0].data(), n, &n));
+    return c;
+  }
+  Context* ctx_;
+  LocalTrajectoryBuilderOptions3D options_;
+  RangeDataSynchronizer synchronizer_;
+  dl_local_trajectory_builder* builder_ = nullptr;
+};
+
+}  // namespace mapping
 }  // namespace dliom

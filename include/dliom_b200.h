@@ -542,6 +542,11 @@ int dl_ltb_add_imu_data(dl_local_trajectory_builder* builder, double time, const
 /* xyzt: n TimedPointCloud rows (x y z t, t <= 0 relative to `time`, the last point's acquisition); origin: 3 floats (tracking frame). */
 int dl_ltb_add_range_data(dl_local_trajectory_builder* builder, double time, const float* xyzt, int64_t n, const float* origin,
                           dl_matching_result* result);
+/* The same for the output of the range-data synchroniser (C/mapping/internal/3d/range_data_synchronizer.cc:29-117, kaist / viral
+ * run two LiDARs): rows of row_floats floats — 8 = RangeMeasurement {x y z t, u64 origin index}, 4 = x y z t with one origin —
+ * sorted by time, and one origin per sensor. */
+int dl_ltb_add_synchronized_range_data(dl_local_trajectory_builder* builder, double time, const void* rows, int64_t n,
+                                       int32_t row_floats, const float* origins, int32_t num_origins, dl_matching_result* result);
 /* Clouds of the last scan that produced a result. which: 0 returns / 1 misses of range_data_in_local, 2 / 3 the high / low
  * resolution point clouds in the tracking frame (TrajectoryNode::Data). Pass out = NULL to query *num_points. */
 int dl_ltb_get_cloud(const dl_local_trajectory_builder* builder, int32_t which, float* out, int64_t capacity_points, int64_t* num_points);

@@ -193,3 +193,99 @@ def test_rotational_histogram_against_oracle(orc):
     ctx.check(ctx.L.dl_rotational_histogram(ctx.h, np.zeros((1, 3), np.float32), 0, 8, empty))   # no points: all zero
     assert not empty.any()
     ctx.close()
+
+
+def _synchronize(prior, secondary_queue):
+    """Python twin of RangeDataSynchronizer::AddRangeData for the prior sensor (range_data_synchronizer.cc:43-109):
+    prior = (time, xyzt float32 [n,4]); secondary_queue = list of (time, xyzt). Returns RangeMeasurement rows + number merged."""
+    from synth import RANGE_DTYPE
+    t_end, a = prior
+    start = t_end + float(a[0, 3])
+    while secondary_queue and secondary_queue[0][0] < start:
+        secondary_queue.pop(0)
+    rows = np.zeros(len(a), RANGE_DTYPE)
+    rows["x"], rows["y"], rows["z"], rows["t"] = a[:, 0], a[:, 1], a[:, 2], a[:, 3]
+    if not secondary_queue:
+        return rows, 0
+    tb, bpts = secondary_queue[0]
+    if tb + float(bpts[0, 3]) > t_end:
+        return rows, 0
+    tt = tb + bpts[:, 3].astype(np.float64)
+    inside = np.nonzero((tt >= start) & (tt <= t_end))[0]
+    i_start = int(inside[0])
+    after = np.nonzero((np.arange(len(tt)) > i_start) & (tt > t_end))[0]
+    i_end = int(after[0]) - 1 if len(after) else len(tt) - 1
+    sel = bpts[i_start:i_end + 1]
+    extra = np.zeros(len(sel), RANGE_DTYPE)
+    extra["x"], extra["y"], extra["z"] = sel[:, 0], sel[:, 1], sel[:, 2]
+    extra["t"] = (sel[:, 3].astype(np.float64) + tb - t_end).astype(np.float32)
+    extra["origin_index"] = 1
+    merged = np.concatenate([rows, extra])
+    return merged[np.argsort(merged["t"], kind="stable")], len(sel)
+
+
+def test_cpp_shim_replays_a_two_lidar_drive(orc, tmp_path):
+    """host/dliom_b200.hpp: mapping::LocalTrajectoryBuilder3D + RangeDataSynchronizer (two LiDARs, the kaist / viral set-up) driven
+    by a C++ program from a recorded event file; the same events through the Python binding with a Python restatement of the
+    synchroniser must give the same poses to the last bit (same C-ABI object underneath)."""
+    import os
+    import struct
+    import subprocess
+    import dliom
+    import synth
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "d-liom_b200", "host")
+    exe = str(tmp_path / "example_trajectory")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(host, "example_trajectory.cc"), "-o", exe,
+                           "-L" + os.path.join(root, "d-liom_b200"), "-ldliom_b200", "-Wl,-rpath," + os.path.join(root, "d-liom_b200")])
+    scene = synth.Scene(42)
+    n = 8
+    times = [2.0 + 0.1 * k for k in range(n)]
+    init = imu_synth.state(times[0] - 0.1)
+    events = []
+    for k, t1 in enumerate(times):
+        dt, acc, gyr = imu_synth.samples(t1 - 0.1, t1)
+        for j in range(0 if k == 0 else 1, len(dt)):
+            events.append(("imu", t1 - 0.1 + j / 200.0, acc[j], gyr[j]))
+        for kind, t in ((2, t1 - 0.03), (1, t1)):      # the secondary sweep ends 30 ms before the prior one
+            r = synth.make_scan(scene, 16, t)
+            events.append(("range", kind, t, np.stack([r["x"], r["y"], r["z"], r["t"]], 1).astype(np.float32)))
+    path = str(tmp_path / "drive.bin")
+    with open(path, "wb") as f:
+        f.write(dliom.NavState.from16(init))
+        f.write(struct.pack("<i", len(events)))
+        for e in events:
+            if e[0] == "imu":
+                f.write(struct.pack("<id", 0, e[1]) + np.asarray(e[2], np.float64).tobytes() + np.asarray(e[3], np.float64).tobytes())
+            else:
+                f.write(struct.pack("<id", e[1], e[2]) + np.zeros(3, np.float32).tobytes() + struct.pack("<i", len(e[3])) + e[3].tobytes())
+    out = subprocess.run([exe, path], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.strip().splitlines()
+    results = [l.split() for l in lines if l.startswith("result")]
+    assert len([l for l in lines if l.startswith("none")]) == n      # the secondary clouds are only queued
+    assert len(results) == n
+    # the Python twin
+    ctx = dliom.Context(0)
+    fo = dliom.FrontendOptions.from_oracle(orc.FrontEndOptions.defaults())
+    b = dliom.LocalTrajectoryBuilder(ctx, dliom.LtbOptions.defaults(fo, NOISE, imu_weight=0.7, num_range_data=5, max_time_seconds=0.05))
+    b.set_initial_state(init)
+    queue, k = [], 0
+    for e in events:
+        if e[0] == "imu":
+            b.add_imu_data(e[1], e[2], e[3])
+        elif e[1] == 2:
+            queue.append((e[2], e[3]))
+        else:
+            rows, merged = _synchronize((e[2], e[3]), queue)
+            assert merged > 0 and rows["t"].min() >= -0.1 and rows["t"].max() == 0.0
+            r = b.add_synchronized_range_data(e[2], rows, np.zeros((2, 3), np.float32))
+            got = results[k]
+            assert r.has_result == 1 and float(got[1]) == pytest.approx(e[2])
+            assert [float(v) for v in got[2:9]] == list(r.local_pose)          # printed with %.17g: exact round trip
+            assert int(got[9]) == r.inserted == 1 and int(got[10]) == r.num_returns and int(got[11]) == b.num_submaps()
+            assert (int(got[12]), int(got[13]), int(got[14])) == (r.num_high_resolution, r.num_low_resolution, r.num_insertion_submaps)
+            k += 1
+    assert b.num_submaps() == 2
+    b.close()
+    ctx.close()
