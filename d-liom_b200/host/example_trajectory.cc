@@ -21,7 +21,6 @@ int main(int argc, char** argv) {
     options.c.num_range_data = 5;
     options.c.motion_filter_max_time_seconds = 0.05;
     options.c.imu_weight = 0.7;
-    options.c.frontend.min_range = 0.5f; options.c.frontend.max_range = 100.f;  // the oracle's FrontEndOptions.defaults()
     if (argc > 2) options.c.frontend.voxel_filter_size = (float)std::atof(argv[2]);
     mapping::LocalTrajectoryBuilder3D builder(&ctx, options, {"lidar_a", "lidar_b"});
     dl_nav_state init{};
