@@ -32,7 +32,7 @@ EXPORTS = [
     "dl_frontend_collect_imu",
     "dl_comm_unique_id", "dl_comm_create", "dl_comm_destroy", "dl_comm_rank", "dl_comm_world_size", "dl_comm_last_error",
     "dl_comm_all_gather_dev", "dl_comm_all_reduce_f64_dev", "dl_comm_broadcast_dev", "dl_constraint_search_exchange",
-    "dl_rotational_histogram", "dl_ltb_create", "dl_ltb_destroy", "dl_ltb_set_initial_state", "dl_ltb_add_imu_data",
+    "dl_pose_graph_solve", "dl_rotational_histogram", "dl_ltb_create", "dl_ltb_destroy", "dl_ltb_set_initial_state", "dl_ltb_add_imu_data",
     "dl_ltb_add_range_data", "dl_ltb_add_synchronized_range_data", "dl_ltb_get_cloud", "dl_ltb_get_histogram", "dl_ltb_num_submaps", "dl_ltb_get_submap", "dl_ltb_get_state",
 ]
 
@@ -241,6 +241,20 @@ class ImuSamples:
                                         self.acc.ctypes.data, self.gyr.ctypes.data)
 
 
+class SpaConstraint(C.Structure):   # dl_spa_constraint
+    _fields_ = [("submap", C.c_int32), ("node", C.c_int32), ("zbar", C.c_double * 7), ("translation_weight", C.c_double),
+                ("rotation_weight", C.c_double)]
+
+
+class PoseGraphOptions(C.Structure):
+    _fields_ = [("max_num_iterations", C.c_int32), ("fix_z", C.c_int32)]
+
+
+class PoseGraphInfo(C.Structure):
+    _fields_ = [("num_local_parameters", C.c_int32), ("all_reduce_count", C.c_int32), ("all_reduce_bytes", C.c_int64),
+                ("all_reduce_ms", C.c_float), ("reserved", C.c_int32)]
+
+
 class LtbOptions(C.Structure):   # dl_ltb_options
     _fields_ = [("frontend", FrontendOptions), ("imu_noise", ImuNoise), ("imu_weight", C.c_double), ("gravity", C.c_double),
                 ("high_resolution", C.c_float), ("low_resolution", C.c_float), ("num_range_data", C.c_int32),
@@ -359,6 +373,8 @@ def lib():
     L.dl_comm_broadcast_dev.argtypes = [vp, vp, C.c_int64, C.c_int32]
     L.dl_constraint_search_exchange.argtypes = [vp, vp, ip(ConstraintOptions), C.c_int32, C.c_int32, i32p, i32p, f64p, f32p, i64p,
                                                 f32p, i64p, C.c_void_p, C.c_void_p, ip(ConstraintRow), ip(ExchangeInfo)]
+    L.dl_pose_graph_solve.argtypes = [vp, vp, ip(PoseGraphOptions), C.c_int32, C.c_int32, f64p, vp, C.c_int32, ip(SolveSummary),
+                                      ip(PoseGraphInfo)]
     L.dl_rotational_histogram.argtypes = [vp, f32p, C.c_int64, C.c_int32, f32p]
     L.dl_ltb_create.argtypes = [vp, ip(LtbOptions), ip(vp)]
     L.dl_ltb_destroy.argtypes = [vp]
@@ -556,6 +572,21 @@ class Context:
                                                         np.ascontiguousarray(pose_guesses, np.float64).reshape(-1, 7), hi_all,
                                                         hi_off, lo_all, lo_off, hg, lg, table, C.byref(info)))
         return table, info
+
+    def pose_graph_solve(self, submap_poses, node_poses, constraints, fix_z=False, max_iter=50, comm=None):
+        """OptimizationProblem3D::Solve (SPA only) on the device. constraints: this rank's (submap, node, zbar7, translation_weight,
+        rotation_weight) tuples; with `comm` the normal equations are all-reduced over the ranks. -> (submaps, nodes, summary, info)."""
+        S, N = len(submap_poses), len(node_poses)
+        poses = np.ascontiguousarray(np.concatenate([np.asarray(submap_poses, np.float64).reshape(S, 7),
+                                                     np.asarray(node_poses, np.float64).reshape(N, 7)]))
+        cs = (SpaConstraint * max(len(constraints), 1))()
+        for k, (i, j, z, tw, rw) in enumerate(constraints):
+            cs[k] = SpaConstraint(int(i), int(j), (C.c_double * 7)(*[float(v) for v in z]), float(tw), float(rw))
+        opt = PoseGraphOptions(int(max_iter), int(bool(fix_z)))
+        s, info = SolveSummary(), PoseGraphInfo()
+        self.check(self.L.dl_pose_graph_solve(self.h, comm.h if comm else None, C.byref(opt), S, N, poses, C.cast(cs, C.c_void_p),
+                                              len(constraints), C.byref(s), C.byref(info)))
+        return poses[:S].copy(), poses[S:].copy(), s.as_dict(), info
 
     @staticmethod
     def _pairs(clouds, grids):

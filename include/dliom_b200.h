@@ -297,6 +297,33 @@ int dl_constraint_search_exchange(dl_context* ctx, dl_comm* comm, const dl_const
                                   const dl_grid* const* high_resolution_grids, const dl_grid* const* low_resolution_grids,
                                   dl_constraint_row* table, dl_exchange_info* info);
 
+/* ---- optimization::OptimizationProblem3D::Solve as this fork runs it (C/mapping/internal/optimization/optimization_problem_3d.cc:259-589
+ *      with the IMU / consecutive-node terms commented out there): sparse pose adjustment over the SpaCostFunction3D constraints
+ *      (cost_functions/spa_cost_function_3d.h:35-58), first submap's translation constant and yaw fixed, LM as pose_graph.lua sets
+ *      it. poses: num_submaps submap poses then num_nodes node poses, 7 doubles each (t xyz, q wxyz), in-out, identical on every
+ *      rank. constraints: THIS RANK'S share (e.g. the rows it contributed to dl_constraint_search_exchange); with a communicator
+ *      the per-rank normal equations are summed by one ncclAllReduce(fp64) per evaluation and every rank returns the same poses.
+ *      comm may be NULL (single process: all constraints local). Dense normal equations: local size <= 3072. ------------------- */
+typedef struct dl_spa_constraint { /* PoseGraphInterface::Constraint: node j observed from submap i */
+  int32_t submap, node;
+  double zbar[7];
+  double translation_weight, rotation_weight;
+} dl_spa_constraint;
+typedef struct dl_pose_graph_options {
+  int32_t max_num_iterations; /* pose_graph.lua optimization_problem.ceres_solver_options.max_num_iterations (50) */
+  int32_t fix_z;              /* optimization_problem.fix_z_in_3d */
+} dl_pose_graph_options;
+typedef struct dl_pose_graph_info {
+  int32_t num_local_parameters;
+  int32_t all_reduce_count;   /* one per evaluation */
+  int64_t all_reduce_bytes;   /* per all-reduce: (n^2 + n + 1) doubles */
+  float all_reduce_ms;        /* summed device time of the all-reduces (CUDA events) */
+  int32_t reserved;
+} dl_pose_graph_info;
+int dl_pose_graph_solve(dl_context* ctx, dl_comm* comm, const dl_pose_graph_options* options, int32_t num_submaps, int32_t num_nodes,
+                        double* poses, const dl_spa_constraint* constraints, int32_t num_constraints, dl_solve_summary* summary,
+                        dl_pose_graph_info* info);
+
 /* ---- IMU: pre-integration (LocalTrajectoryBuilder3D::AddImuData, LTB:164-201, with the in-repo mid-point integrator
  *      C/mapping/internal/3d/initialization/integration_base.h:109-265 instead of the un-vendored GTSAM one) and the
  *      scan match with the pre-integration residual (integration_base.h:267-301) fused into the same solve.
