@@ -253,23 +253,29 @@ __global__ void __launch_bounds__(1024) spa_step_kernel(StepArgs a) {
   }
   int valid = ok_s;
   if (valid) {
-    if (tid == 0) {  // triangular solves: O(n^2), one thread (n <= 3072)
-      for (int i = 0; i < n; ++i) {
-        double s = a.gs[i];
-        for (int k = 0; k < i; ++k) s -= a.A[(size_t)i * n + k] * a.step[k];
-        a.step[i] = s / a.A[(size_t)i * n + i];
-      }
-      for (int i = n - 1; i >= 0; --i) {
-        double s = a.step[i];
-        for (int k = i + 1; k < n; ++k) s -= a.A[(size_t)k * n + i] * a.step[k];
-        a.step[i] = s / a.A[(size_t)i * n + i];
-      }
-      int fin = 1;
-      for (int i = 0; i < n; ++i) {
-        if (!isfinite(a.step[i])) fin = 0;
-        a.step[i] = -a.step[i];
-      }
-      ok_s = fin;
+    // triangular solves, column-oriented so that every step is one parallel axpy: L z = gs, then L^T y = z
+    for (int j = tid; j < n; j += nt) a.step[j] = a.gs[j];
+    __syncthreads();
+    for (int i = 0; i < n; ++i) {
+      if (tid == 0) a.step[i] /= a.A[(size_t)i * n + i];
+      __syncthreads();
+      const double zi = a.step[i];
+      for (int j = i + 1 + tid; j < n; j += nt) a.step[j] -= a.A[(size_t)j * n + i] * zi;
+      __syncthreads();
+    }
+    for (int i = n - 1; i >= 0; --i) {
+      if (tid == 0) a.step[i] /= a.A[(size_t)i * n + i];
+      __syncthreads();
+      const double yi = a.step[i];
+      const double* row = a.A + (size_t)i * n;
+      for (int j = tid; j < i; j += nt) a.step[j] -= row[j] * yi;
+      __syncthreads();
+    }
+    if (tid == 0) ok_s = 1;
+    __syncthreads();
+    for (int j = tid; j < n; j += nt) {
+      if (!isfinite(a.step[j])) ok_s = 0;
+      a.step[j] = -a.step[j];
     }
     __syncthreads();
     valid = ok_s;
