@@ -223,6 +223,7 @@ def workload_config(args, batch):
                         f"searches per rank, ncclAllGather of the constraint rows)",
             "imu": True, "scans_per_step_per_gpu": batch, "distinct_scans": batch, "beams": args.beams,
             "map_scans": args.map_scans, "row_bytes": 4 * args.row_floats,
+            "row_layout": {3: "x y z (12 B) + per-point times as runs", 4: "x y z t (16 B)", 8: "RangeMeasurement (32 B)"}[args.row_floats],
             "l2_policy": f"inputs ({batch} x {130605 * 4 * args.row_floats / 1e6:.1f} MB) exceed the 126 MB L2; no explicit flush",
             "parallelism": f"scans sharded over {args.gpus} gpu(s); loop-closure pairs sharded by submap owner, one ncclAllGather per step"}
 
@@ -238,8 +239,9 @@ def main():
     ap.add_argument("--map-scans", type=int, default=40)
     ap.add_argument("--pairs", type=int, default=8, help="loop-closure (node, submap) searches per rank and step")
     ap.add_argument("--cpu-sample", type=int, default=0, help="scans in the cpu_baseline sample (0 = 8 x threads)")
-    ap.add_argument("--row-floats", type=int, default=4, choices=[4, 8],
-                    help="4: TimedPointCloud rows x y z t (what AddRangeData receives); 8: RangeMeasurement rows")
+    ap.add_argument("--row-floats", type=int, default=3, choices=[3, 4, 8],
+                    help="3: x y z rows + the per-point times as runs (12 B/point); 4: TimedPointCloud rows x y z t (what AddRangeData "
+                         "receives); 8: RangeMeasurement rows")
     ap.add_argument("--no-extras", action="store_true", help="skip the configs[2] / mode-F / no-IMU extra measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -272,6 +274,9 @@ def main():
     fo = dliom.FrontendOptions.from_oracle(w["opts"])
     fo.range_row_floats = args.row_floats
     row_bytes = 4 * args.row_floats
+    runs_bytes = 0
+    if args.row_floats == 3:   # bare x y z rows; the times travel as ~2 k runs per sweep (bit-identical deskew)
+        runs_bytes = dliom.TimeRuns([s["t"] for s in w["scans"]]).attach(fo)._time_runs.nbytes
 
     sizes = np.array([len(s) for s in w["scans"]], np.int64)
     cap = int(sizes.max())
@@ -413,6 +418,8 @@ def main():
     imu_one = dliom.ImuSamples(IMU_NOISE, w["intervals"][:1], w["states_i"][:1], imu_weight=IMU_WEIGHT)
     fo_one = dliom.FrontendOptions.from_oracle(w["opts"])
     fo_one.range_row_floats = args.row_floats
+    if args.row_floats == 3:
+        dliom.TimeRuns([w["scans"][0]["t"]]).attach(fo_one)
     lat = []
     for _ in range(25):
         t1 = time.perf_counter()
@@ -436,7 +443,7 @@ def main():
         def fetch_lane0():
             ctx.synchronize()
             return ctx.fetch_results(C.c_void_p(dev_lanes[0][1].data_ptr()), B)
-        extras = measure_extras(args, w, dliom, ctx, timed_device_loop, fetch_lane0, B)
+        extras = measure_extras(args, w, dliom, ctx, timed_device_loop, fetch_lane0, B, fo)
 
     t = torch.tensor([ms_total, e2e_s * 1e3, e2e_sync_s * 1e3, collective_ms or 0.0], dtype=torch.float64, device=device)
     if dist is not None:
@@ -455,7 +462,7 @@ def main():
         adaptive_bytes = sum(12.0 * (r.num_cropped_high * r.num_passes_high + r.num_cropped_low * r.num_passes_low) +
                              12.0 * (r.num_high_resolution + r.num_low_resolution) for r in res)
         stage_bytes = {
-            "voxel_filter_first": 16.0 * n_raw + 16.0 * n1,                          # 16 N_in + 16 N_out
+            "voxel_filter_first": 16.0 * n_raw + 16.0 * n1,                          # 16 N_in + 16 N_out (SURVEY 8d's model; 12 B rows read less)
             "ingest_second_filter": 28.0 * n1 + 12.0 * n1 + 12.0 * n2,               # ingest 28 N + second pass 12 N_in + 12 N_out
             "adaptive_voxel_filter": adaptive_bytes,
             "nls_solve": 28.0 * evals,
@@ -519,7 +526,7 @@ def main():
                       "same_iteration_counts": bool(all(r.summary.num_iterations == it for r, it in zip(res, want[4]))),
                       "all_ok": bool(all(r.ok == 1 for r in res) and all(ok_cpu == 1))}
 
-        h2d = int(sizes.sum() * row_bytes) + imu_bytes
+        h2d = int(sizes.sum() * row_bytes) + imu_bytes + runs_bytes
         d2h = int(B * (C.sizeof(dliom.ScanResult) + 128))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -553,7 +560,7 @@ def main():
         dist.destroy_process_group()
 
 
-def measure_extras(args, w, dliom, ctx, timed_device_loop, fetch_lane0, B):
+def measure_extras(args, w, dliom, ctx, timed_device_loop, fetch_lane0, B, fo):
     """Secondary measurements at N = 1: each is its own short device-timed loop over the same resident batch."""
     extras = {}
     steps = max(10, min(args.steps, 30))
@@ -571,8 +578,7 @@ def measure_extras(args, w, dliom, ctx, timed_device_loop, fetch_lane0, B):
         extras["front_end_only"] = {"error": str(e)}
     try:
         # mode F: adaptive filters pass everything through, the matcher sees the whole filtered cloud
-        ff = dliom.FrontendOptions.from_oracle(w["opts"])
-        ff.range_row_floats = args.row_floats
+        ff = dliom.FrontendOptions.from_buffer_copy(fo)     # same rows / time runs as the headline step
         ff.high_resolution_adaptive_voxel_filter.min_num_points = 1e9
         ff.low_resolution_adaptive_voxel_filter.min_num_points = 1e9
         timed_device_loop(2, ff, with_exchange=False)

@@ -1697,7 +1697,11 @@ FrontendArgs make_frontend_args(const dl_frontend_options& o, const FrontendBuff
   return fa;
 }
 
-int row_floats_of(const dl_frontend_options& o) { return o.range_row_floats == 4 ? 4 : 8; }
+size_t time_runs_bytes(const dl_frontend_options& o, int num_scans) {  // device copies of the time_run_* arrays
+  if (o.range_row_floats != 3 || !o.time_run_offsets || num_scans <= 0) return 0;
+  return arena_bytes({(size_t)(num_scans + 1) * 4, (size_t)o.time_run_offsets[num_scans] * 4, (size_t)o.time_run_offsets[num_scans] * 4});
+}
+int row_floats_of(const dl_frontend_options& o) { return o.range_row_floats == 4 ? 4 : (o.range_row_floats == 3 ? 3 : 8); }
 
 ScanConstants make_scan_constants(const double* prev7, const double* cur7) {  // dl_pipeline.cuh has the arithmetic
   return dl::make_scan_constants(pose_from7(prev7), pose_from7(cur7));
@@ -1863,7 +1867,17 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
   const int rf = row_floats_of(o);
   DL_TRY(frontend_upload_small(ctx, o, f, sizes, origins, num_origins, raw ? nullptr : prev_poses, cur_poses, hi, lo,
                                d_imu_ok));
-  const FrontendArgs fa = make_frontend_args(o, f, d_ranges, in_cap, rf);
+  FrontendArgs fa = make_frontend_args(o, f, d_ranges, in_cap, rf);
+  if (rf == 3) {  // per-point times as runs: validated by check_frontend, uploaded next to the scans
+    const size_t runs = (size_t)o.time_run_offsets[num_scans];
+    int32_t* d_ro = a.take<int32_t>((size_t)num_scans + 1);
+    int32_t* d_rf = a.take<int32_t>(runs);
+    float* d_rv = a.take<float>(runs);
+    DL_TRY(h2d(ctx, d_ro, o.time_run_offsets, (size_t)num_scans + 1));
+    DL_TRY(h2d(ctx, d_rf, o.time_run_first_row, runs));
+    DL_TRY(h2d(ctx, d_rv, o.time_run_value, runs));
+    fa.run_offsets = d_ro; fa.run_first_row = d_rf; fa.run_value = d_rv;
+  }
   DL_TRY(launch_fe_prepare(ctx, fa, f.batch));
   const Rigidd submap = pose_from7(submap_local_pose);
   const bool rtcsm = o.use_online_correlative_scan_matching != 0;
@@ -2058,6 +2072,19 @@ int check_frontend(dl_context* ctx, const dl_frontend_options* o, int num_scans,
     m = std::max(m, sizes[b]);
   }
   *max_size = m;
+  if (o->range_row_floats == 3 && num_scans > 0) {
+    if (!o->time_run_offsets || !o->time_run_first_row || !o->time_run_value)
+      return ctx->fail(DL_ERR_ARG, "range_row_floats = 3 needs the time_run_* arrays");
+    if (o->time_run_offsets[0] != 0) return ctx->fail(DL_ERR_ARG, "time_run_offsets[0] must be 0");
+    for (int b = 0; b < num_scans; ++b) {
+      const int32_t r0 = o->time_run_offsets[b], r1 = o->time_run_offsets[b + 1];
+      if (r1 < r0 || (sizes[b] > 0 && r1 == r0)) return ctx->fail(DL_ERR_ARG, "every non-empty scan needs at least one time run");
+      for (int32_t r = r0; r < r1; ++r)
+        if ((r == r0 ? o->time_run_first_row[r] != 0 : o->time_run_first_row[r] <= o->time_run_first_row[r - 1]) ||
+            o->time_run_first_row[r] >= std::max<int64_t>(sizes[b], 1))
+          return ctx->fail(DL_ERR_ARG, "time_run_first_row must start at 0 and ascend inside the scan");
+    }
+  }
   return DL_OK;
 }
 
@@ -2080,7 +2107,7 @@ int dl_frontend_match_batch_dev(dl_context* ctx, const dl_frontend_options* opti
   DL_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t extra = options->use_online_correlative_scan_matching
                            ? (size_t)num_scans * rtcsm_scratch_bound(options->real_time_correlative_scan_matcher, hi->resolution, false) : 0;
-  DL_TRY(ctx->reserve_device(frontend_bytes(num_scans, cap_rows, num_origins, extra)));
+  DL_TRY(ctx->reserve_device(frontend_bytes(num_scans, cap_rows, num_origins, extra) + time_runs_bytes(*options, num_scans)));
   Arena a(ctx->d_scratch);
   return frontend_run(ctx, *options, num_scans, (float*)ranges_dev, cap_rows, nullptr, sizes, origins, num_origins,
                       prev_poses, predicted_poses, submap_local_pose, hi, lo, a, results_dev);
@@ -2119,7 +2146,7 @@ static int frontend_enqueue_host(dl_context* ctx, const dl_frontend_options* opt
                            ? (size_t)num_scans * rtcsm_scratch_bound(options->real_time_correlative_scan_matcher, hi->resolution, false) : 0;
   const size_t device_extra = imu ? imu_run_device_bytes(num_scans, imu->samples) : 0;
   DL_TRY(ctx->reserve_device(frontend_bytes(num_scans, cap, num_origins, extra) + (size_t)num_scans * cap * 32 + 256 +
-                             (size_t)num_scans * sizeof(dl_scan_result) + 256 + device_extra));
+                             (size_t)num_scans * sizeof(dl_scan_result) + 256 + device_extra + time_runs_bytes(*options, num_scans)));
   if (pinned_extra) DL_TRY(ctx->reserve_pinned(frontend_small_bytes(num_scans, num_origins) + pinned_extra + 256));
   Arena a(ctx->d_scratch);
   float* d_ranges = a.take<float>((size_t)num_scans * cap * 8);
@@ -2225,7 +2252,8 @@ int dl_frontend_match_batch_imu_samples_dev(dl_context* ctx, const dl_frontend_o
       cap_rows < 1)
     return DL_ERR_ARG;
   DL_CUDA(ctx, cudaSetDevice(ctx->device));
-  DL_TRY(ctx->reserve_device(frontend_bytes(num_scans, cap_rows, num_origins, 0) + imu_run_device_bytes(num_scans, imu)));
+  DL_TRY(ctx->reserve_device(frontend_bytes(num_scans, cap_rows, num_origins, 0) + imu_run_device_bytes(num_scans, imu) +
+                             time_runs_bytes(*options, num_scans)));
   Arena a(ctx->d_scratch);
   ImuRun run;
   run.samples = imu;

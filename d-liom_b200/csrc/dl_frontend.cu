@@ -46,6 +46,17 @@ __device__ __forceinline__ Vec3f load_xyz(const float* __restrict__ rows, int ro
   return {v.x, v.y, v.z};
 }
 
+// Time of row i of scan b: the row's fourth float, or (12-byte rows) the value of the run that contains the row.
+__device__ __forceinline__ float point_time(const FrontendArgs& a, int b, const float* __restrict__ rows, int rf, int i) {
+  if (rf != 3) return rows[(size_t)i * rf + 3];
+  int lo = a.run_offsets[b], hi = a.run_offsets[b + 1] - 1;  // last run whose first row is <= i
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (a.run_first_row[mid] <= i) lo = mid; else hi = mid - 1;
+  }
+  return a.run_value[lo];
+}
+
 // ---------------------------------------------------------------------------------------------------- A
 __global__ void __launch_bounds__(kBlock) fe_first_filter_insert(FrontendArgs a) {
   const int b = a.first_scan + blockIdx.y;
@@ -106,7 +117,13 @@ __device__ __forceinline__ bool pack_key(const Int3& c, bool miss, unsigned long
 // Heavy per-survivor work of kernel B (double slerp, pose composition, transform, gate, second-filter insert).
 __device__ __forceinline__ int ingest_survivor(const FrontendArgs& a, int b, const float* rows, int rf, const ScanConstants& sc,
                                                bool no_deskew, unsigned long long* keys, uint32_t* mins, uint32_t mask2, int i) {
-  const float4 h = __ldg((const float4*)(rows + (size_t)i * rf));
+  float4 h;
+  if (rf == 3) {
+    const float* p = rows + (size_t)i * 3;
+    h = make_float4(p[0], p[1], p[2], point_time(a, b, rows, rf, i));
+  } else {
+    h = __ldg((const float4*)(rows + (size_t)i * rf));
+  }
   const unsigned long long origin_index = rf >= 8 ? *(const unsigned long long*)(rows + (size_t)i * rf + 4) : 0ull;
   const float* o = a.origins + 3 * origin_index;
   const Rigidf pose = point_pose(sc, no_deskew, a.scan_period, h.w);
@@ -163,7 +180,7 @@ __global__ void __launch_bounds__(kBlock) fe_ingest_second_insert(FrontendArgs a
   uint32_t* mins = a.min2 + (size_t)b * a.tcap2;
   const uint32_t mask2 = (uint32_t)a.tcap2 - 1;
   const ScanConstants& sc = a.scans[b];
-  const bool no_deskew = n > 0 && (double)fabsf(rows[3]) < 1e-3;  // first survivor is row 0 (LTB:430-433)
+  const bool no_deskew = n > 0 && (double)fabsf(point_time(a, b, rows, rf, 0)) < 1e-3;  // first survivor is row 0 (LTB:430-433)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int* q = queue[warp];
   int queued = 0, survivors = 0, returns = 0, last = -1;
@@ -337,8 +354,8 @@ __global__ void fe_current_pose(FrontendArgs a, int batch) {
   const int last = a.last_index[b];
   Rigidf cur = to_float(a.scans[b].cur);
   if (last >= 0) {
-    const bool no_deskew = (double)fabsf(rows[3]) < 1e-3;
-    cur = point_pose(a.scans[b], no_deskew, a.scan_period, rows[(size_t)last * rf + 3]);
+    const bool no_deskew = (double)fabsf(point_time(a, b, rows, rf, 0)) < 1e-3;
+    cur = point_pose(a.scans[b], no_deskew, a.scan_period, point_time(a, b, rows, rf, last));
   }
   const Rigidf back = inverse(cur);
   float* cp = a.current_pose + 7 * b;

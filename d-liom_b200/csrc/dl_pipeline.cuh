@@ -70,7 +70,10 @@ struct IngestArgs {
 
 // Fused front half (dl_frontend.cu).
 struct FrontendArgs {
-  const float* ranges;   // scan b starts at row b * in_cap; rows of row_floats floats (4: x y z t, 8: + u64 origin index)
+  const float* ranges;   // scan b starts at row b * in_cap; rows of row_floats floats (3: x y z, 4: x y z t, 8: + u64 origin index)
+  const int32_t* run_offsets;    // row_floats == 3: per-point times as runs (dl_frontend_options::time_run_*), device copies
+  const int32_t* run_first_row;
+  const float* run_value;
   int64_t in_cap;
   int row_floats;
   int first_scan;        // kernels handle scans [first_scan, first_scan + gridDim.y): lets sub-batches pipeline

@@ -184,7 +184,8 @@ class FrontendOptions(C.Structure):
                 ("use_online_correlative_scan_matching", C.c_int32), ("range_row_floats", C.c_int32),
                 ("scan_period", C.c_double),
                 ("real_time_correlative_scan_matcher", RtcsmOptions), ("ceres_scan_matcher", CeresOptions),
-                ("host_scan_stride_rows", C.c_int64)]
+                ("host_scan_stride_rows", C.c_int64), ("time_run_offsets", C.c_void_p), ("time_run_first_row", C.c_void_p),
+                ("time_run_value", C.c_void_p)]
 
     @staticmethod
     def from_oracle(o):
@@ -399,6 +400,38 @@ def lib():
     L.dl_copy_to_host.argtypes = [vp, vp, vp, C.c_int64]
     _LIB = L
     return L
+
+
+class TimeRuns:
+    """Per-point times of a batch of scans as runs (dl_frontend_options::time_run_*), for 12-byte x y z rows. Built from the per-scan
+    time arrays; attach() points an options block at the arrays (which stay alive with this object)."""
+
+    def __init__(self, times_per_scan):
+        offs, firsts, values = [0], [], []
+        for t in times_per_scan:
+            t = np.ascontiguousarray(t, np.float32)
+            if len(t):
+                start = np.concatenate([[0], np.nonzero(t[1:].view(np.uint32) != t[:-1].view(np.uint32))[0] + 1])
+                firsts.append(start.astype(np.int32))
+                values.append(t[start])
+                offs.append(offs[-1] + len(start))
+            else:
+                offs.append(offs[-1])
+        self.offsets = np.ascontiguousarray(offs, np.int32)
+        self.first_row = np.ascontiguousarray(np.concatenate(firsts) if firsts else np.zeros(0, np.int32), np.int32)
+        self.value = np.ascontiguousarray(np.concatenate(values) if values else np.zeros(0, np.float32), np.float32)
+
+    @property
+    def nbytes(self):
+        return self.offsets.nbytes + self.first_row.nbytes + self.value.nbytes
+
+    def attach(self, options):
+        options.range_row_floats = 3
+        options.time_run_offsets = self.offsets.ctypes.data
+        options.time_run_first_row = self.first_row.ctypes.data
+        options.time_run_value = self.value.ctypes.data
+        options._time_runs = self
+        return options
 
 
 class HostScanBatch:

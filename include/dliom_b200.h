@@ -370,7 +370,8 @@ typedef struct dl_frontend_options { /* C/mapping/proto/3d/local_trajectory_buil
   int32_t use_online_correlative_scan_matching;
   /* layout of the `ranges` rows: 8 (default when 0) = RangeMeasurement {x y z t, u64 origin index} as produced by
    * RangeDataSynchronizer; 4 = sensor::TimedPointCloud rows {x y z t} of a single sensor (origin index 0), the
-   * layout AddRangeData itself receives (timed_point_cloud_data.h:27-31) — half the host-to-device bytes. */
+   * layout AddRangeData itself receives (timed_point_cloud_data.h:27-31) — half the host-to-device bytes; 3 = bare x y z
+   * rows with the times given as runs (time_run_* below) — three eighths. */
   int32_t range_row_floats;
   double scan_period;
   dl_rtcsm_options real_time_correlative_scan_matcher;
@@ -380,6 +381,14 @@ typedef struct dl_frontend_options { /* C/mapping/proto/3d/local_trajectory_buil
    * stride >= every sizes[b]; each sub-batch is then uploaded by a single strided copy (rows between a scan's end and the
    * next scan's start are read but ignored). Checked against the pointers; DL_ERR_ARG if they disagree. */
   int64_t host_scan_stride_rows;
+  /* range_row_floats == 3 only: rows are bare {x y z} (12 bytes) and the per-point times come as RUNS — a spinning LiDAR stamps a
+   * whole firing column with one time, so a 130k-point sweep has ~2k distinct times. Scan k owns runs
+   * [time_run_offsets[k], time_run_offsets[k+1]); run r starts at row time_run_first_row[r] of its scan (ascending, the first is 0)
+   * and all rows up to the next run's first row carry time_run_value[r]. The deskew sees exactly the floats the 16-byte rows
+   * would carry (bit-identical results) while the host-to-device copy shrinks by a quarter. Single sensor (origin index 0). */
+  const int32_t* time_run_offsets;
+  const int32_t* time_run_first_row;
+  const float* time_run_value;
 } dl_frontend_options;
 
 typedef struct dl_scan_result {

@@ -97,3 +97,44 @@ def test_strided_host_layout_single_copy(orc):
     with pytest.raises(dliom.DlError):
         c.frontend_match_batch(fo, views, *args)                      # smaller than a scan
     c.close()
+
+
+def test_twelve_byte_rows_with_time_runs_are_bit_identical(orc):
+    """range_row_floats = 3: bare x y z rows + the per-point times as runs (a spinning LiDAR stamps a firing column with one time).
+    Same floats reach the deskew, so every result equals the 16-byte-row call bit for bit; a quarter fewer bytes cross PCIe."""
+    import dliom
+    from helpers import workload
+    w = workload()
+    ctx = dliom.Context(0)
+    hi, lo = dliom.Grid.from_oracle(ctx, w["hi"]), dliom.Grid.from_oracle(ctx, w["lo"])
+    fo4 = dliom.FrontendOptions.from_oracle(w["opts"])
+    fo4.range_row_floats = 4
+    rows4 = [np.ascontiguousarray(np.stack([s["x"], s["y"], s["z"], s["t"]], 1)) for s in w["scans"]]
+    want = ctx.frontend_match_batch(fo4, rows4, w["origin"], w["prev"], w["cur"], w["submap_pose"], hi, lo)
+    fo3 = dliom.FrontendOptions.from_oracle(w["opts"])
+    runs = dliom.TimeRuns([s["t"] for s in w["scans"]]).attach(fo3)
+    rows3 = [np.ascontiguousarray(r[:, :3]) for r in rows4]
+    got = ctx.frontend_match_batch(fo3, rows3, w["origin"], w["prev"], w["cur"], w["submap_pose"], hi, lo)
+    tr = fo3._time_runs
+    assert tr.offsets[-1] < 0.1 * sum(len(r) for r in rows4)          # ~1 800 columns per 28 800-point sweep
+    for a, b in zip(got, want):
+        assert a.ok == b.ok == 1 and list(a.pose_estimate_local) == list(b.pose_estimate_local)
+        assert (a.num_first_filter, a.num_returns, a.num_misses, a.num_high_resolution) == (b.num_first_filter, b.num_returns, b.num_misses, b.num_high_resolution)
+    # a scan without per-point times (|t_0| < 1e-3 -> no deskew, LTB:430-433) as a single run
+    flat = dliom.FrontendOptions.from_oracle(w["opts"])
+    dliom.TimeRuns([np.zeros(len(r), np.float32) for r in rows3]).attach(flat)
+    z4 = [np.ascontiguousarray(np.concatenate([r, np.zeros((len(r), 1), np.float32)], 1)) for r in rows3]
+    a = ctx.frontend_match_batch(flat, rows3, w["origin"], w["prev"], w["cur"], w["submap_pose"], hi, lo)
+    b = ctx.frontend_match_batch(fo4, z4, w["origin"], w["prev"], w["cur"], w["submap_pose"], hi, lo)
+    assert all(list(x.pose_estimate_local) == list(y.pose_estimate_local) for x, y in zip(a, b))
+    # argument checks: runs missing, not starting at row 0, not ascending
+    bad = dliom.FrontendOptions.from_oracle(w["opts"])
+    bad.range_row_floats = 3
+    with pytest.raises(dliom.DlError):
+        ctx.frontend_match_batch(bad, rows3, w["origin"], w["prev"], w["cur"], w["submap_pose"], hi, lo)
+    broken = dliom.TimeRuns([s["t"] for s in w["scans"]])
+    broken.first_row[0] = 1
+    broken.attach(bad)
+    with pytest.raises(dliom.DlError):
+        ctx.frontend_match_batch(bad, rows3, w["origin"], w["prev"], w["cur"], w["submap_pose"], hi, lo)
+    ctx.close()
