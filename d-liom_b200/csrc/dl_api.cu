@@ -1701,6 +1701,9 @@ size_t time_runs_bytes(const dl_frontend_options& o, int num_scans) {  // device
   if (o.range_row_floats != 3 || !o.time_run_offsets || num_scans <= 0) return 0;
   return arena_bytes({(size_t)(num_scans + 1) * 4, (size_t)o.time_run_offsets[num_scans] * 4, (size_t)o.time_run_offsets[num_scans] * 4});
 }
+size_t time_expand_bytes(const dl_frontend_options& o, int num_scans, int64_t cap) {
+  return o.range_row_floats == 3 ? (size_t)num_scans * (size_t)cap * 4 + 256 : 0;
+}
 int row_floats_of(const dl_frontend_options& o) { return o.range_row_floats == 4 ? 4 : (o.range_row_floats == 3 ? 3 : 8); }
 
 ScanConstants make_scan_constants(const double* prev7, const double* cur7) {  // dl_pipeline.cuh has the arithmetic
@@ -1877,6 +1880,13 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
     DL_TRY(h2d(ctx, d_rf, o.time_run_first_row, runs));
     DL_TRY(h2d(ctx, d_rv, o.time_run_value, runs));
     fa.run_offsets = d_ro; fa.run_first_row = d_rf; fa.run_value = d_rv;
+    if (runs > (size_t)8 * num_scans) {  // many runs per scan: expand once instead of searching per survivor
+      int max_runs = 0;
+      for (int b = 0; b < num_scans; ++b) max_runs = std::max(max_runs, (int)(o.time_run_offsets[b + 1] - o.time_run_offsets[b]));
+      float* d_times = a.take<float>((size_t)num_scans * in_cap);
+      DL_TRY(launch_fe_expand_times(ctx, fa, num_scans, max_runs, d_times));  // needs counts + runs only, both uploaded above
+      fa.times = d_times;
+    }
   }
   DL_TRY(launch_fe_prepare(ctx, fa, f.batch));
   const Rigidd submap = pose_from7(submap_local_pose);
@@ -2107,7 +2117,7 @@ int dl_frontend_match_batch_dev(dl_context* ctx, const dl_frontend_options* opti
   DL_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t extra = options->use_online_correlative_scan_matching
                            ? (size_t)num_scans * rtcsm_scratch_bound(options->real_time_correlative_scan_matcher, hi->resolution, false) : 0;
-  DL_TRY(ctx->reserve_device(frontend_bytes(num_scans, cap_rows, num_origins, extra) + time_runs_bytes(*options, num_scans)));
+  DL_TRY(ctx->reserve_device(frontend_bytes(num_scans, cap_rows, num_origins, extra) + time_runs_bytes(*options, num_scans) + time_expand_bytes(*options, num_scans, cap_rows)));
   Arena a(ctx->d_scratch);
   return frontend_run(ctx, *options, num_scans, (float*)ranges_dev, cap_rows, nullptr, sizes, origins, num_origins,
                       prev_poses, predicted_poses, submap_local_pose, hi, lo, a, results_dev);
@@ -2146,7 +2156,7 @@ static int frontend_enqueue_host(dl_context* ctx, const dl_frontend_options* opt
                            ? (size_t)num_scans * rtcsm_scratch_bound(options->real_time_correlative_scan_matcher, hi->resolution, false) : 0;
   const size_t device_extra = imu ? imu_run_device_bytes(num_scans, imu->samples) : 0;
   DL_TRY(ctx->reserve_device(frontend_bytes(num_scans, cap, num_origins, extra) + (size_t)num_scans * cap * 32 + 256 +
-                             (size_t)num_scans * sizeof(dl_scan_result) + 256 + device_extra + time_runs_bytes(*options, num_scans)));
+                             (size_t)num_scans * sizeof(dl_scan_result) + 256 + device_extra + time_runs_bytes(*options, num_scans) + time_expand_bytes(*options, num_scans, cap)));
   if (pinned_extra) DL_TRY(ctx->reserve_pinned(frontend_small_bytes(num_scans, num_origins) + pinned_extra + 256));
   Arena a(ctx->d_scratch);
   float* d_ranges = a.take<float>((size_t)num_scans * cap * 8);
@@ -2253,7 +2263,7 @@ int dl_frontend_match_batch_imu_samples_dev(dl_context* ctx, const dl_frontend_o
     return DL_ERR_ARG;
   DL_CUDA(ctx, cudaSetDevice(ctx->device));
   DL_TRY(ctx->reserve_device(frontend_bytes(num_scans, cap_rows, num_origins, 0) + imu_run_device_bytes(num_scans, imu) +
-                             time_runs_bytes(*options, num_scans)));
+                             time_runs_bytes(*options, num_scans) + time_expand_bytes(*options, num_scans, cap_rows)));
   Arena a(ctx->d_scratch);
   ImuRun run;
   run.samples = imu;

@@ -49,12 +49,26 @@ __device__ __forceinline__ Vec3f load_xyz(const float* __restrict__ rows, int ro
 // Time of row i of scan b: the row's fourth float, or (12-byte rows) the value of the run that contains the row.
 __device__ __forceinline__ float point_time(const FrontendArgs& a, int b, const float* __restrict__ rows, int rf, int i) {
   if (rf != 3) return rows[(size_t)i * rf + 3];
+  if (a.times) return a.times[(size_t)b * a.in_cap + i];
   int lo = a.run_offsets[b], hi = a.run_offsets[b + 1] - 1;  // last run whose first row is <= i
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
     if (a.run_first_row[mid] <= i) lo = mid; else hi = mid - 1;
   }
   return a.run_value[lo];
+}
+
+// 12-byte rows: one float per row from the runs, written once per batch (one warp per run, contiguous stores), so that the
+// latency-bound ingest kernel pays one 4-byte load per survivor instead of an 11-step search of the run table.
+__global__ void __launch_bounds__(kBlock) fe_expand_times(FrontendArgs a, float* __restrict__ times) {
+  const int b = blockIdx.y;
+  const int r0 = a.run_offsets[b], r1 = a.run_offsets[b + 1];
+  const int r = r0 + blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+  if (r >= r1) return;
+  const int begin = a.run_first_row[r], end = r + 1 < r1 ? a.run_first_row[r + 1] : a.counts[b];
+  const float t = a.run_value[r];
+  float* out = times + (size_t)b * a.in_cap;
+  for (int i = begin + (threadIdx.x & 31); i < end; i += 32) out[i] = t;
 }
 
 // ---------------------------------------------------------------------------------------------------- A
@@ -389,6 +403,13 @@ int launch_fe_prepare(dl_context* ctx, const FrontendArgs& a, int batch) {
   DL_CUDA(ctx, cudaMemsetAsync(a.win, 0, (size_t)batch * a.cap, ctx->stream));
   fe_reset_counters<<<(batch + 127) / 128, 128, 0, ctx->stream>>>(a, batch);
   DL_LAUNCH_CHECK(ctx, "fe_reset_counters");
+  return DL_OK;
+}
+
+int launch_fe_expand_times(dl_context* ctx, const FrontendArgs& a, int batch, int max_runs_per_scan, float* times_out) {
+  if (batch <= 0 || max_runs_per_scan <= 0) return DL_OK;
+  fe_expand_times<<<dim3((max_runs_per_scan + kBlock / 32 - 1) / (kBlock / 32), batch), kBlock, 0, ctx->stream>>>(a, times_out);
+  DL_LAUNCH_CHECK(ctx, "fe_expand_times");
   return DL_OK;
 }
 

@@ -74,6 +74,7 @@ struct FrontendArgs {
   const int32_t* run_offsets;    // row_floats == 3: per-point times as runs (dl_frontend_options::time_run_*), device copies
   const int32_t* run_first_row;
   const float* run_value;
+  const float* times;            // optional: the runs expanded to one float per row (scan b at b * in_cap); null = search the runs
   int64_t in_cap;
   int row_floats;
   int first_scan;        // kernels handle scans [first_scan, first_scan + gridDim.y): lets sub-batches pipeline
@@ -99,6 +100,7 @@ struct FrontendArgs {
   int32_t* error_flag;
 };
 int launch_fe_prepare(dl_context* ctx, const FrontendArgs& a, int batch);
+int launch_fe_expand_times(dl_context* ctx, const FrontendArgs& a, int batch, int max_runs_per_scan, float* times_out);
 int launch_fe_first_filter(dl_context* ctx, FrontendArgs a, int first_scan, int num_scans);
 int launch_fe_rest(dl_context* ctx, FrontendArgs a, int first_scan, int batch);
 

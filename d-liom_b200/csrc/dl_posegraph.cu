@@ -232,43 +232,43 @@ __global__ void __launch_bounds__(1024) spa_step_kernel(StepArgs a) {
   }
   if (tid == 0) ok_s = 1;
   __syncthreads();
-  // left-looking Cholesky, row i owned by thread i (mod nt); L overwrites the lower triangle of A
+  // Cholesky A = U^T U, left-looking by columns of U; U overwrites the UPPER triangle (row-major), so that for a fixed k the
+  // threads (one per column i) read consecutive addresses U[k][i] and U[k][j] is a broadcast: coalesced, unlike rows of L.
   for (int j = 0; j < n; ++j) {
+    for (int i = j + tid; i < n; i += nt) {  // s_i = A[j][i] - sum_k U[k][i] U[k][j], the diagonal (i == j) included
+      double s = a.A[(size_t)j * n + i];
+      for (int k = 0; k < j; ++k) s -= a.A[(size_t)k * n + i] * a.A[(size_t)k * n + j];
+      a.A[(size_t)j * n + i] = s;
+    }
+    __syncthreads();
     if (tid == 0) {
-      double s = a.A[(size_t)j * n + j];
-      for (int k = 0; k < j; ++k) s -= a.A[(size_t)j * n + k] * a.A[(size_t)j * n + k];
+      const double s = a.A[(size_t)j * n + j];
       if (!(s > 0.)) ok_s = 0; else a.A[(size_t)j * n + j] = sqrt(s);
     }
     __syncthreads();
     if (!ok_s) break;
     const double djj = a.A[(size_t)j * n + j];
-    for (int i = j + 1 + tid; i < n; i += nt) {
-      double s = a.A[(size_t)i * n + j];
-      const double* ri = a.A + (size_t)i * n;
-      const double* rj = a.A + (size_t)j * n;
-      for (int k = 0; k < j; ++k) s -= ri[k] * rj[k];
-      a.A[(size_t)i * n + j] = s / djj;
-    }
+    for (int i = j + 1 + tid; i < n; i += nt) a.A[(size_t)j * n + i] /= djj;
     __syncthreads();
   }
   int valid = ok_s;
   if (valid) {
-    // triangular solves, column-oriented so that every step is one parallel axpy: L z = gs, then L^T y = z
+    // triangular solves as parallel axpys: U^T z = gs (row i of U is contiguous), then U y = z
     for (int j = tid; j < n; j += nt) a.step[j] = a.gs[j];
     __syncthreads();
     for (int i = 0; i < n; ++i) {
       if (tid == 0) a.step[i] /= a.A[(size_t)i * n + i];
       __syncthreads();
       const double zi = a.step[i];
-      for (int j = i + 1 + tid; j < n; j += nt) a.step[j] -= a.A[(size_t)j * n + i] * zi;
+      const double* row = a.A + (size_t)i * n;
+      for (int j = i + 1 + tid; j < n; j += nt) a.step[j] -= row[j] * zi;
       __syncthreads();
     }
     for (int i = n - 1; i >= 0; --i) {
       if (tid == 0) a.step[i] /= a.A[(size_t)i * n + i];
       __syncthreads();
       const double yi = a.step[i];
-      const double* row = a.A + (size_t)i * n;
-      for (int j = tid; j < i; j += nt) a.step[j] -= row[j] * yi;
+      for (int j = tid; j < i; j += nt) a.step[j] -= a.A[(size_t)j * n + i] * yi;
       __syncthreads();
     }
     if (tid == 0) ok_s = 1;
