@@ -276,7 +276,7 @@ def main():
     row_bytes = 4 * args.row_floats
     runs_bytes = 0
     if args.row_floats == 3:   # bare x y z rows; the times travel as ~2 k runs per sweep (bit-identical deskew)
-        runs_bytes = dliom.TimeRuns([s["t"] for s in w["scans"]]).attach(fo)._time_runs.nbytes
+        runs_bytes = dliom.TimeRuns([s["t"] for s in w["scans"]], pin=True).attach(fo)._time_runs.nbytes
 
     sizes = np.array([len(s) for s in w["scans"]], np.int64)
     cap = int(sizes.max())

@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(kBlock) fe_expand_times(FrontendArgs a, float*
   const int r0 = a.run_offsets[b], r1 = a.run_offsets[b + 1];
   const int r = r0 + blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
   if (r >= r1) return;
-  const int begin = a.run_first_row[r], end = r + 1 < r1 ? a.run_first_row[r + 1] : a.counts[b];
+  const int n = a.counts[b];
+  const int begin = max(0, a.run_first_row[r]), end = min(n, r + 1 < r1 ? a.run_first_row[r + 1] : n);  // clamped to the scan
   const float t = a.run_value[r];
   float* out = times + (size_t)b * a.in_cap;
   for (int i = begin + (threadIdx.x & 31); i < end; i += 32) out[i] = t;

@@ -406,7 +406,7 @@ class TimeRuns:
     """Per-point times of a batch of scans as runs (dl_frontend_options::time_run_*), for 12-byte x y z rows. Built from the per-scan
     time arrays; attach() points an options block at the arrays (which stay alive with this object)."""
 
-    def __init__(self, times_per_scan):
+    def __init__(self, times_per_scan, pin=False):
         offs, firsts, values = [0], [], []
         for t in times_per_scan:
             t = np.ascontiguousarray(t, np.float32)
@@ -420,6 +420,10 @@ class TimeRuns:
         self.offsets = np.ascontiguousarray(offs, np.int32)
         self.first_row = np.ascontiguousarray(np.concatenate(firsts) if firsts else np.zeros(0, np.int32), np.int32)
         self.value = np.ascontiguousarray(np.concatenate(values) if values else np.zeros(0, np.float32), np.float32)
+        if pin:   # page-locked: the per-batch upload of the table is then asynchronous
+            import torch
+            self._pinned = [torch.from_numpy(a).pin_memory() for a in (self.offsets, self.first_row, self.value)]
+            self.offsets, self.first_row, self.value = [t.numpy() for t in self._pinned]
 
     @property
     def nbytes(self):

@@ -127,13 +127,13 @@ def test_twelve_byte_rows_with_time_runs_are_bit_identical(orc):
     a = ctx.frontend_match_batch(flat, rows3, w["origin"], w["prev"], w["cur"], w["submap_pose"], hi, lo)
     b = ctx.frontend_match_batch(fo4, z4, w["origin"], w["prev"], w["cur"], w["submap_pose"], hi, lo)
     assert all(list(x.pose_estimate_local) == list(y.pose_estimate_local) for x, y in zip(a, b))
-    # argument checks: runs missing, not starting at row 0, not ascending
+    # argument checks: runs missing, not starting at row 0
     bad = dliom.FrontendOptions.from_oracle(w["opts"])
     bad.range_row_floats = 3
     with pytest.raises(dliom.DlError):
         ctx.frontend_match_batch(bad, rows3, w["origin"], w["prev"], w["cur"], w["submap_pose"], hi, lo)
     broken = dliom.TimeRuns([s["t"] for s in w["scans"]])
-    broken.first_row[0] = 1
+    broken.first_row[0] = 1          # a scan's first run must start at its row 0
     broken.attach(bad)
     with pytest.raises(dliom.DlError):
         ctx.frontend_match_batch(bad, rows3, w["origin"], w["prev"], w["cur"], w["submap_pose"], hi, lo)
