@@ -389,7 +389,7 @@ extern "C" int dl_pose_graph_solve(dl_context* ctx, dl_comm* comm, const dl_pose
   cudaEvent_t ev0, ev1;
   cudaEventCreate(&ev0);
   cudaEventCreate(&ev1);
-  float reduce_ms = 0.f;
+  float reduce_ms = 0.f, reduce_min_ms = 1e30f;
   int reductions = 0;
   // evaluation at `at` into system `buf`: local constraints, then the all-reduce over the ranks
   auto evaluate = [&](const double* at, int buf) -> int {
@@ -409,6 +409,7 @@ extern "C" int dl_pose_graph_solve(dl_context* ctx, dl_comm* comm, const dl_pose
       float ms = 0.f;
       cudaEventElapsedTime(&ms, ev0, ev1);
       reduce_ms += ms;
+      reduce_min_ms = std::fmin(reduce_min_ms, ms);
       ++reductions;
     }
     return DL_OK;
@@ -544,6 +545,7 @@ extern "C" int dl_pose_graph_solve(dl_context* ctx, dl_comm* comm, const dl_pose
     info->all_reduce_count = reductions;
     info->all_reduce_bytes = (int64_t)sys * 8;
     info->all_reduce_ms = reduce_ms;
+    info->all_reduce_min_ms = reductions ? reduce_min_ms : 0.f;
   }
 #undef PG_CUDA
   return DL_OK;

@@ -253,7 +253,7 @@ class PoseGraphOptions(C.Structure):
 
 class PoseGraphInfo(C.Structure):
     _fields_ = [("num_local_parameters", C.c_int32), ("all_reduce_count", C.c_int32), ("all_reduce_bytes", C.c_int64),
-                ("all_reduce_ms", C.c_float), ("reserved", C.c_int32)]
+                ("all_reduce_ms", C.c_float), ("all_reduce_min_ms", C.c_float)]
 
 
 class LtbOptions(C.Structure):   # dl_ltb_options

@@ -318,7 +318,7 @@ typedef struct dl_pose_graph_info {
   int32_t all_reduce_count;   /* one per evaluation */
   int64_t all_reduce_bytes;   /* per all-reduce: (n^2 + n + 1) doubles */
   float all_reduce_ms;        /* summed device time of the all-reduces (CUDA events) */
-  int32_t reserved;
+  float all_reduce_min_ms;    /* fastest single all-reduce (the first one carries NCCL's lazy connection set-up) */
 } dl_pose_graph_info;
 int dl_pose_graph_solve(dl_context* ctx, dl_comm* comm, const dl_pose_graph_options* options, int32_t num_submaps, int32_t num_nodes,
                         double* poses, const dl_spa_constraint* constraints, int32_t num_constraints, dl_solve_summary* summary,

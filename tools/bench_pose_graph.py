@@ -74,13 +74,14 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     if rank == 0:
         err = max(np.linalg.norm(compose(inverse(t), compose(inverse(s_out[0]), p))[:3]) for t, p in zip(truth, n_out))
-        ar_ms = info.all_reduce_ms / max(info.all_reduce_count, 1)
+        ar_ms = info.all_reduce_min_ms if info.all_reduce_min_ms > 0 else info.all_reduce_ms / max(info.all_reduce_count, 1)
         print(json.dumps({"what": "dl_pose_graph_solve: SPA with ncclAllReduce(fp64) of the normal equations", "ranks": world,
                           "submaps": S, "nodes": N, "constraints": len(cons), "constraints_this_rank": len(mine),
                           "local_parameters": info.num_local_parameters, "iterations": summary["num_iterations"],
                           "evaluations": summary["num_evaluations"], "initial_cost": summary["initial_cost"],
                           "final_cost": summary["final_cost"], "solve_s": float(tmax[0]),
                           "all_reduce": {"count": info.all_reduce_count, "bytes_each": int(info.all_reduce_bytes), "ms_each": ar_ms,
+                                         "ms_mean": info.all_reduce_ms / max(info.all_reduce_count, 1),
                                          "algbw_gbs": info.all_reduce_bytes / (ar_ms * 1e-3) / 1e9 if ar_ms > 0 else None,
                                          "busbw_gbs": (info.all_reduce_bytes / (ar_ms * 1e-3) / 1e9 * 2 * (world - 1) / world) if ar_ms > 0 and world > 1 else None},
                           "replicas_bit_identical": bool(torch.equal(lo, hi)), "max_node_error_m": float(err)}))

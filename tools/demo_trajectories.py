@@ -10,9 +10,9 @@
     python tools/demo_trajectories.py                                   # 1 GPU, 1 trajectory
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/demo_trajectories.py
 
-Prints one JSON line (rank 0) and exits non-zero if a node's constraint against its OWN trajectory's submap is further than
-0.2 m from the synthetic truth (constraints against other trajectories' submaps are reported, not judged: a node may see
-little of a neighbouring submap, and min_score is far below the stock 0.55 here).
+Prints one JSON line (rank 0) and exits non-zero if, at the reference's min_score (0.55), a node's constraint against its OWN
+trajectory's submap is further than 0.2 m from the synthetic truth or one against ANOTHER trajectory's submap further than 0.3 m.
+The same searches at --min-score (0.3) are reported next to it: that is where round 1's 4.8 m "inter-trajectory error" came from.
 """
 import argparse
 import json
@@ -109,42 +109,68 @@ def main():
             pair_nodes.append((node_id, all_truth[r][k].astype(np.float64)))
             g7.append(gg)
             hs.append(all_hi[r][all_hi[r][:, 0] == k][:, 1:]); ls.append(all_lo[r][all_lo[r][:, 0] == k][:, 1:])
-    opt = dliom.ConstraintOptions.defaults(min_score=args.min_score, min_low_resolution_score=0.3)
-    t0 = time.perf_counter()
-    cons = ctx.constraint_search_batch(opt, g7, hs, ls, [hi] * len(g7), [lo] * len(g7))
-    search_s = time.perf_counter() - t0
-    worst, worst_other = 0.0, 0.0   # own-trajectory nodes are the check; other trajectories' nodes may see little of this submap
-    for c, (node_id, tr) in zip(cons, pair_nodes):
-        if c.found:
-            err = float(np.abs(np.array(c.pose[:3]) - tr[:3]).max())
-            if node_id // 1000 == rank:
-                worst = max(worst, err)
-            else:
-                worst_other = max(worst_other, err)
+    # The asserted table uses the reference's min_score (pose_graph.lua: 0.55); --min-score (default 0.3) is run as well and only
+    # REPORTED: in this corridor-like street (facades parallel to the driving direction) a node that sees only the far end of a
+    # neighbouring submap has a nearly flat score along the street, and below ~0.5 the best leaf can sit metres away along x —
+    # round 1's "4.8 m inter-trajectory error" was exactly that (error along x, score 0.3-0.45), not a frame bug in the exchange.
+    idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        idt.copy_(torch.tensor(list(dliom.comm_unique_id()), dtype=torch.uint8))
+    if world > 1:
+        dist.broadcast(idt, 0)
+    comm = dliom.Comm(ctx, bytes(idt.cpu().numpy().tolist()), rank, world)
+    node_ids = [n for n, _ in pair_nodes]
+    truth_of = {n: tr for n, tr in pair_nodes}
 
-    # ---- exchange 2: the constraint table
-    t0 = time.perf_counter()
-    rows = shard.constraint_rows([rank] * len(cons), [n for n, _ in pair_nodes], cons)
-    table = shard.all_gather_constraints(d, rows, dev, max_rows=len(cons))
-    gather_s = time.perf_counter() - t0
-    stats = torch.tensor([worst, front_err, build_s, match_s, exchange_s, search_s, gather_s, worst_other], dtype=torch.float64, device=dev)
+    def search(min_score):
+        opt = dliom.ConstraintOptions.defaults(min_score=min_score, min_low_resolution_score=min(0.55, max(0.3, min_score)))
+        t0 = time.perf_counter()
+        # searches sharded by submap owner (this rank owns submap `rank`) + ONE ncclAllGather of the rows, issued from the C-ABI
+        table, info = ctx.constraint_search_exchange(comm, opt, len(g7), [rank] * len(g7), node_ids, g7, hs, ls, [hi] * len(g7),
+                                                     [lo] * len(g7))
+        return table, info, time.perf_counter() - t0
+    search(0.55)                          # warm-up: NCCL sets its connections up lazily on the first collective
+    table, info, search_s = search(0.55)
+    loose, _, _ = search(args.min_score)
+
+    def errors(tab):
+        own, other = [], []
+        for r in tab:
+            if r.found != 1:
+                continue
+            tr = truth_of[r.node_id]
+            e = np.array(r.pose[:3]) - tr[:3]
+            (own if r.node_id // 1000 == r.submap_id else other).append((float(np.abs(e).max()), [float(v) for v in e], float(r.score)))
+        return own, other
+    own, other = errors(table)
+    own_l, other_l = errors(loose)
+    worst = max([e[0] for e in own], default=0.0)
+    worst_other = max([e[0] for e in other], default=0.0)
+    worst_loose = max(other_l, default=(0.0, [0, 0, 0], 0.0))
+    stats = torch.tensor([worst, front_err, build_s, match_s, exchange_s, search_s, info.collective_ms, worst_other], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    worst, front_err = float(stats[0]), float(stats[1])
+    worst, front_err, worst_other = float(stats[0]), float(stats[1]), float(stats[7])
     if rank == 0:
-        own = int(np.sum(table[:, 0] == table[:, 1] // 1000))
         print(json.dumps({"demo": "configs[4] shape: %d trajectories x (%d map sweeps + %d nodes), %d-beam" %
                                   (world, args.map_scans, args.nodes, args.beams), "n_gpus": world,
-                          "searches": world * len(cons), "constraints": int(len(table)), "intra_trajectory": own,
-                          "inter_trajectory": int(len(table)) - own,
-                          "max_constraint_error_m": worst, "max_inter_trajectory_constraint_error_m": float(stats[7]),
+                          "searches": world * len(g7), "min_score": 0.55,
+                          "constraints": len(own) + len(other), "intra_trajectory": len(own), "inter_trajectory": len(other),
+                          "max_constraint_error_m": worst, "max_inter_trajectory_constraint_error_m": worst_other,
                           "max_front_end_error_m": front_err,
+                          "loose_threshold": {"min_score": args.min_score, "inter_trajectory": len(other_l),
+                                              "worst_inter_error_m": worst_loose[0], "worst_inter_error_xyz": worst_loose[1],
+                                              "score_of_worst": worst_loose[2],
+                                              "note": "reported only: low-score matches along the street's symmetry axis"},
+                          "collective": {"name": "ncclAllGather (dl_constraint_search_exchange)", "bytes": int(info.bytes_received),
+                                         "ms": float(stats[6])},
                           "seconds_max_over_ranks": {"build_submap": float(stats[2]), "front_end": float(stats[3]),
-                                                     "node_exchange": float(stats[4]), "search": float(stats[5]),
-                                                     "constraint_allgather": float(stats[6])}}))
+                                                     "node_exchange": float(stats[4]), "search_and_exchange": float(stats[5])}}))
+    comm.close()
     if world > 1:
         dist.destroy_process_group()
-    return 0 if worst < 0.2 and front_err < 0.1 else 1   # one hi-res voxel
+    # every constraint that passes the reference's min_score must be right: own submap within 2 voxels, other trajectories' within 0.3 m
+    return 0 if worst < 0.2 and worst_other < 0.3 and front_err < 0.1 else 1
 
 
 if __name__ == "__main__":
