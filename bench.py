@@ -304,11 +304,13 @@ def main():
     if dist is not None:
         dist.broadcast(idt, 0)
     comm = dliom.Comm(ctx3, bytes(idt.cpu().numpy().tolist()), rank, world)
-    lc = loop_closure_pairs(w, args, rank)
+    lc = loop_closure_pairs(w, args, rank) if args.pairs > 0 else None
     copt = dliom.ConstraintOptions.defaults(min_score=0.3, min_low_resolution_score=0.3, xy_window=3.0, z_window=0.5)
     exchange = {"ms": [], "found": 0, "bytes": 0, "rows": 0}
 
     def step_exchange():
+        if args.pairs <= 0:     # --pairs 0: front end only (experiments)
+            return None
         table, info = ctx3.constraint_search_exchange(comm, copt, args.pairs, lc["submaps"], lc["nodes"], lc["guesses"], lc["hi"],
                                                       lc["lo"], [hi] * args.pairs, [lo] * args.pairs)
         exchange["ms"].append(info.collective_ms)
