@@ -2791,3 +2791,49 @@ int dl_ltb_get_state(const dl_local_trajectory_builder* b, dl_nav_state* state, 
 }
 
 }  // extern "C"
+
+
+// ------------------------------------------------------------------------------------------------ two-stage window (dl_window.cu)
+extern "C" int dl_window_optimize_batch(dl_context* ctx, const dl_window_options* options, int32_t count, const dl_nav_state* states_i,
+                                        const double* prior_information, const dl_preintegration* preintegrations,
+                                        const double* matched_poses, const dl_nav_state* initial_states_j, dl_nav_state* states_i_out,
+                                        dl_nav_state* states_j_out, double* information_out, dl_solve_summary* summaries) {
+  if (!ctx || !options || count < 0) return DL_ERR_ARG;
+  if (count == 0) return DL_OK;
+  if (!states_i || !prior_information || !preintegrations || !matched_poses || !states_j_out || !information_out) return DL_ERR_ARG;
+  if (!(options->pose_sigma_translation > 0.) || !(options->pose_sigma_rotation > 0.) || !(options->imu_weight > 0.) ||
+      (options->use_gravity_factor && !(options->gravity_sigma > 0.)))
+    return ctx->fail(DL_ERR_ARG, "dl_window_options: sigmas and the IMU weight must be positive");
+  DL_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t n = (size_t)count;
+  DL_TRY(ctx->reserve_device(arena_bytes({n * sizeof(dl_nav_state), n * 225 * 8, n * sizeof(dl_preintegration), n * 56,
+                                          n * sizeof(dl_nav_state), n * sizeof(dl_nav_state), n * sizeof(dl_nav_state), n * 225 * 8,
+                                          n * sizeof(dl_solve_summary)})));
+  Arena a(ctx->d_scratch);
+  dl_nav_state* d_si = a.take<dl_nav_state>(n);
+  double* d_prior = a.take<double>(n * 225);
+  dl_preintegration* d_pre = a.take<dl_preintegration>(n);
+  double* d_z = a.take<double>(n * 7);
+  dl_nav_state* d_init = a.take<dl_nav_state>(n);
+  dl_nav_state* d_si_out = a.take<dl_nav_state>(n);
+  dl_nav_state* d_sj_out = a.take<dl_nav_state>(n);
+  double* d_info = a.take<double>(n * 225);
+  dl_solve_summary* d_sum = a.take<dl_solve_summary>(n);
+  DL_TRY(h2d(ctx, d_si, states_i, n));
+  DL_TRY(h2d(ctx, d_prior, prior_information, n * 225));
+  DL_TRY(h2d(ctx, d_pre, preintegrations, n));
+  DL_TRY(h2d(ctx, d_z, matched_poses, n * 7));
+  if (initial_states_j) DL_TRY(h2d(ctx, d_init, initial_states_j, n));
+  DL_CUDA(ctx, cudaMemsetAsync(d_sj_out, 0, n * sizeof(dl_nav_state), ctx->stream));
+  DL_CUDA(ctx, cudaMemsetAsync(d_info, 0, n * 225 * 8, ctx->stream));
+  DL_TRY(launch_window_optimize(ctx, count, d_si, d_prior, d_pre, d_z, initial_states_j ? d_init : nullptr, *options, d_si_out, d_sj_out,
+                                d_info, d_sum));
+  DL_TRY(d2h(ctx, states_j_out, d_sj_out, n));
+  if (states_i_out) DL_TRY(d2h(ctx, states_i_out, d_si_out, n));
+  DL_TRY(d2h(ctx, information_out, d_info, n * 225));
+  std::vector<dl_solve_summary> sums(n);
+  DL_TRY(d2h(ctx, sums.data(), d_sum, n));
+  DL_TRY(sync(ctx));
+  if (summaries) std::memcpy(summaries, sums.data(), n * sizeof(dl_solve_summary));
+  return DL_OK;
+}

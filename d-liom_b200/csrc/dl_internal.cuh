@@ -309,6 +309,11 @@ int grid_insert_device(dl_context* ctx, dl_grid* g, const Vec3f& origin, const f
                        const uint16_t* d_hit_table, const uint16_t* d_miss_table, int32_t* d_bbox, uint32_t* d_update_list);
 int launch_transform_filter(dl_context* ctx, const float* in, int n, const Rigidf& to_submap, const Vec3f& origin_submap,
                             float max_range, float* all, float* near, int32_t* near_count, int32_t* tile_counts);
+// dl_window.cu
+int launch_window_optimize(dl_context* ctx, int count, const dl_nav_state* states_i, const double* prior_information,
+                           const dl_preintegration* preint, const double* matched_pose, const dl_nav_state* initial_j,
+                           const dl_window_options& opt, dl_nav_state* states_i_out, dl_nav_state* states_j_out,
+                           double* information_out, dl_solve_summary* summaries);
 // dl_histogram.cu
 size_t rotational_histogram_scratch_bytes(int64_t n);
 int launch_rotational_histogram(dl_context* ctx, Arena& a, const float* d_points, int64_t n, int size, float* d_histogram,

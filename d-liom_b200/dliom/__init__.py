@@ -32,7 +32,7 @@ EXPORTS = [
     "dl_frontend_collect_imu",
     "dl_comm_unique_id", "dl_comm_create", "dl_comm_destroy", "dl_comm_rank", "dl_comm_world_size", "dl_comm_last_error",
     "dl_comm_all_gather_dev", "dl_comm_all_reduce_f64_dev", "dl_comm_broadcast_dev", "dl_constraint_search_exchange",
-    "dl_pose_graph_solve", "dl_rotational_histogram", "dl_ltb_create", "dl_ltb_destroy", "dl_ltb_set_initial_state", "dl_ltb_add_imu_data",
+    "dl_pose_graph_solve", "dl_window_optimize_batch", "dl_rotational_histogram", "dl_ltb_create", "dl_ltb_destroy", "dl_ltb_set_initial_state", "dl_ltb_add_imu_data",
     "dl_ltb_add_range_data", "dl_ltb_add_synchronized_range_data", "dl_ltb_get_cloud", "dl_ltb_get_histogram", "dl_ltb_num_submaps", "dl_ltb_get_submap", "dl_ltb_get_state",
 ]
 
@@ -242,6 +242,12 @@ class ImuSamples:
                                         self.acc.ctypes.data, self.gyr.ctypes.data)
 
 
+class WindowOptions(C.Structure):   # dl_window_options
+    _fields_ = [("pose_sigma_translation", C.c_double), ("pose_sigma_rotation", C.c_double), ("imu_weight", C.c_double),
+                ("gravity", C.c_double * 3), ("max_num_iterations", C.c_int32), ("use_gravity_factor", C.c_int32),
+                ("gravity_sigma", C.c_double), ("gravity_direction", C.c_double * 3), ("body_reference_direction", C.c_double * 3)]
+
+
 class SpaConstraint(C.Structure):   # dl_spa_constraint
     _fields_ = [("submap", C.c_int32), ("node", C.c_int32), ("zbar", C.c_double * 7), ("translation_weight", C.c_double),
                 ("rotation_weight", C.c_double)]
@@ -374,6 +380,7 @@ def lib():
     L.dl_comm_broadcast_dev.argtypes = [vp, vp, C.c_int64, C.c_int32]
     L.dl_constraint_search_exchange.argtypes = [vp, vp, ip(ConstraintOptions), C.c_int32, C.c_int32, i32p, i32p, f64p, f32p, i64p,
                                                 f32p, i64p, C.c_void_p, C.c_void_p, ip(ConstraintRow), ip(ExchangeInfo)]
+    L.dl_window_optimize_batch.argtypes = [vp, ip(WindowOptions), C.c_int32, vp, f64p, vp, f64p, vp, vp, vp, f64p, vp]
     L.dl_pose_graph_solve.argtypes = [vp, vp, ip(PoseGraphOptions), C.c_int32, C.c_int32, f64p, vp, C.c_int32, ip(SolveSummary),
                                       ip(PoseGraphInfo)]
     L.dl_rotational_histogram.argtypes = [vp, f32p, C.c_int64, C.c_int32, f32p]
@@ -609,6 +616,28 @@ class Context:
                                                         np.ascontiguousarray(pose_guesses, np.float64).reshape(-1, 7), hi_all,
                                                         hi_off, lo_all, lo_off, hg, lg, table, C.byref(info)))
         return table, info
+
+    def window_optimize_batch(self, means_i, prior_infos, preints, matched_poses, sigma_t=0.05, sigma_r=0.01, imu_weight=1.0,
+                              gravity=(0.0, 0.0, 9.8), max_iter=10, gravity_factor=None, initial_j=None):
+        """WindowOptimize's stand-in (dl_window_optimize_batch) for len(means_i) trajectories. means_i / initial_j: 16-vectors;
+        prior_infos: (n, 15, 15); preints: ctypes Preintegration objects. -> (states_i smoothed, states_j, informations, summaries)."""
+        n = len(means_i)
+        opt = WindowOptions(sigma_t, sigma_r, imu_weight, (C.c_double * 3)(*gravity), int(max_iter), 1 if gravity_factor else 0,
+                            float(gravity_factor[0]) if gravity_factor else 1.0,
+                            (C.c_double * 3)(*(gravity_factor[1] if gravity_factor else (0, 0, 1))),
+                            (C.c_double * 3)(*(gravity_factor[2] if gravity_factor else (0, 0, 1))))
+        si = (NavState * n)(*[NavState.from16(x) for x in means_i])
+        pm = (Preintegration * n)(*preints)
+        init = (NavState * n)(*[NavState.from16(x) for x in initial_j]) if initial_j is not None else None
+        out_i, out_j = (NavState * n)(), (NavState * n)()
+        info = np.zeros((n, 15, 15))
+        sums = (SolveSummary * n)()
+        self.check(self.L.dl_window_optimize_batch(self.h, C.byref(opt), n, C.cast(si, C.c_void_p),
+                                                   np.ascontiguousarray(prior_infos, np.float64).reshape(-1), C.cast(pm, C.c_void_p),
+                                                   np.ascontiguousarray(matched_poses, np.float64).reshape(-1),
+                                                   C.cast(init, C.c_void_p) if init is not None else None, C.cast(out_i, C.c_void_p),
+                                                   C.cast(out_j, C.c_void_p), info.reshape(-1), C.cast(sums, C.c_void_p)))
+        return (np.array([o.to16() for o in out_i]), np.array([o.to16() for o in out_j]), info, [s.as_dict() for s in sums])
 
     def pose_graph_solve(self, submap_poses, node_poses, constraints, fix_z=False, max_iter=50, comm=None):
         """OptimizationProblem3D::Solve (SPA only) on the device. constraints: this rank's (submap, node, zbar7, translation_weight,

@@ -358,6 +358,35 @@ int dl_fused_match_batch(dl_context* ctx, const dl_ceres_options* options, doubl
                          const dl_preintegration* preintegrations, const float* const* clouds, const int64_t* sizes,
                          const dl_grid* const* grids, dl_nav_state* states_j_out, dl_solve_summary* summaries);
 
+/* ---- the reference's TWO-STAGE mode, second stage: LocalTrajectoryBuilder3D::WindowOptimize (LTB:693-863) as a fixed-lag smoother
+ *      on the device, no GTSAM. Per trajectory: the previous key x_i with its carried marginal (prior), the IMU factor between x_i
+ *      and the new key x_j (the in-repo pre-integration residual with first-order bias correction, integration_base.h:267-301,
+ *      weighted by its propagated covariance; the last six rows are the bias random walk), the scan matcher's pose as a prior on
+ *      x_j with diagonal sigmas (ceres_pose_noise_{t,r}, LTB:94-101, :815-818), optionally the gravity-direction prior
+ *      (gravity_factor.cc:10-31). Gauss-Newton on the 30 local parameters, then the Schur complement on x_i: the information of
+ *      x_j, which is the next call's prior — what iSAM2's marginal of the newest key carries between the reference's re-seeds
+ *      (LTB:750-797). Tangent order everywhere: p, theta, v, b_a, b_g; rotations perturb on the left, q <- exp(theta) q with
+ *      |theta| the HALF angle (the chart of dl_fused_match_batch). GTSAM's own integrator / factor are not restated (neither
+ *      library is in this image): parity of this row is oracle <-> device. ------------------------------------------------ */
+typedef struct dl_window_options {
+  double pose_sigma_translation; /* imu_options.ceres_pose_noise_t */
+  double pose_sigma_rotation;    /* imu_options.ceres_pose_noise_r (on 2 vec(q_m^-1 q_j), i.e. the full angle) */
+  double imu_weight;             /* scales the IMU factor's square-root information (1 = the propagated covariance as is) */
+  double gravity[3];             /* +9.8 z: the convention of integration_base.h:292-297 */
+  int32_t max_num_iterations;    /* Gauss-Newton iterations (10 when 0) */
+  int32_t use_gravity_factor;
+  double gravity_sigma;          /* imu_options.prior_gravity_noise */
+  double gravity_direction[3];   /* estimated up direction in the local frame (g_vec_est_G_ normalised) */
+  double body_reference_direction[3]; /* the reference direction in the body frame that should map to it */
+} dl_window_options;
+/* `count` independent trajectories. prior_information: 225 doubles each (row-major 15 x 15). matched_poses: 7 each.
+ * initial_states_j may be NULL (start from the IMU prediction). states_i_out (optional) receives the smoothed previous keys.
+ * summaries[k].termination: 0 converged, 1 iteration limit, 2 a covariance / system was not positive definite (no output). */
+int dl_window_optimize_batch(dl_context* ctx, const dl_window_options* options, int32_t count, const dl_nav_state* states_i,
+                             const double* prior_information, const dl_preintegration* preintegrations, const double* matched_poses,
+                             const dl_nav_state* initial_states_j, dl_nav_state* states_i_out, dl_nav_state* states_j_out,
+                             double* information_out, dl_solve_summary* summaries);
+
 /* ---- the per-scan front end of LocalTrajectoryBuilder3D::AddRangeData / AddAccumulatedRangeData
  *      (LTB:393-554): voxel filter -> deskew/transform/range gate -> voxel filter -> adaptive filters ->
  *      [RT-CSM] -> Ceres match, for a batch of independent scans against one submap. ---------------------------- */

@@ -459,6 +459,30 @@ def imu_residual(state_i, state_j, m, G=GRAVITY, jacobian=True):
     return r, J
 
 
+def window_optimize(mean_i, prior_info, m, matched_pose, sigma_t=0.05, sigma_r=0.01, imu_weight=1.0, G=GRAVITY, max_iter=10,
+                    gravity_factor=None, initial_j=None):
+    """The fixed-lag smoother standing in for WindowOptimize (orc_window.h). gravity_factor: None or (sigma, direction, body_ref).
+    -> (state_i smoothed, state_j, information 15x15, summary dict)."""
+    opts = np.array([sigma_t, sigma_r, imu_weight, *G, max_iter, 1.0 if gravity_factor else 0.0,
+                     gravity_factor[0] if gravity_factor else 1.0], np.float64)
+    dirs = np.array([*(gravity_factor[1] if gravity_factor else (0, 0, 1)), *(gravity_factor[2] if gravity_factor else (0, 0, 1))], np.float64)
+    xi, xj, info = np.zeros(16), np.zeros(16), np.zeros(225)
+    it, term = C.c_int(0), C.c_int(0)
+    costs = np.zeros(2)
+    init = np.ascontiguousarray(initial_j, np.float64) if initial_j is not None else None
+    f = lib().orc_window_optimize
+    ok = f(opts.ctypes.data_as(C.c_void_p), dirs.ctypes.data_as(C.c_void_p),
+           np.ascontiguousarray(mean_i, np.float64).ctypes.data_as(C.c_void_p),
+           np.ascontiguousarray(prior_info, np.float64).reshape(-1).ctypes.data_as(C.c_void_p), C.byref(m),
+           np.ascontiguousarray(matched_pose, np.float64).ctypes.data_as(C.c_void_p),
+           init.ctypes.data_as(C.c_void_p) if init is not None else None, xi.ctypes.data_as(C.c_void_p), xj.ctypes.data_as(C.c_void_p),
+           info.ctypes.data_as(C.c_void_p), C.byref(it), costs.ctypes.data_as(C.c_void_p), C.byref(term))
+    if not ok:
+        raise RuntimeError("a covariance or the normal equations are not positive definite")
+    return xi, xj, info.reshape(15, 15), {"num_iterations": it.value, "initial_cost": costs[0], "final_cost": costs[1],
+                                          "termination": term.value}
+
+
 def fused_match(clouds, grids, occ_weights, trans_w, rot_w, target_translation, state_i, initial_j, m, G=GRAVITY,
                 imu_weight=1.0, nonmono=False, max_iter=12):
     clouds, cp, gp, sizes = _pairs(clouds, grids)

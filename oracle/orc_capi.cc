@@ -18,6 +18,7 @@
 #include "orc_nls.h"
 #include "orc_posegraph.h"
 #include "orc_rtcsm.h"
+#include "orc_window.h"
 
 using namespace orc;
 
@@ -426,6 +427,21 @@ int orc_fused_match(int n_pairs, const float* const* clouds, const int64_t* size
     *summary = {s.initial_cost, s.final_cost, (int)s.iterations.size(), s.num_successful_steps,
                 s.num_unsuccessful_steps, s.termination, s.num_residual_evaluations, s.num_jacobian_evaluations};
   return 1;
+}
+
+// ---- two-stage window (orc_window.h). options10: sigma_t, sigma_r, imu_weight, gravity xyz, max_iter, use_gravity, gravity_sigma;
+//      directions6: gravity direction xyz, body reference direction xyz. States as 16 doubles. Returns 1 on success.
+int orc_window_optimize(const double* options9, const double* directions6, const double* mean_i, const double* prior_info225,
+                        const OrcPreintegration* m, const double* matched7, const double* initial_j_or_null, double* xi_out,
+                        double* xj_out, double* info_out225, int* iterations, double* costs2, int* termination) {
+  WindowOptions o;
+  o.pose_sigma_t = options9[0]; o.pose_sigma_r = options9[1]; o.imu_weight = options9[2];
+  o.gravity = {options9[3], options9[4], options9[5]};
+  o.max_num_iterations = (int)options9[6]; o.use_gravity_factor = options9[7] != 0.; o.gravity_sigma = options9[8];
+  o.gravity_direction = {directions6[0], directions6[1], directions6[2]};
+  o.body_reference_direction = {directions6[3], directions6[4], directions6[5]};
+  return window_optimize(o, mean_i, prior_info225, preint_in(*m), pose_in(matched7), initial_j_or_null, xi_out, xj_out, info_out225,
+                         iterations, costs2, costs2 + 1, termination) ? 1 : 0;
 }
 
 // ---- per-scan front end
