@@ -2512,6 +2512,16 @@ struct dl_local_trajectory_builder {
   Rigidd motion_last_pose{{0, 0, 0}, {1, 0, 0, 0}};
   std::vector<float> clouds[4];            // returns / misses in the local frame, high / low resolution cloud in the tracking frame
   std::vector<float> histogram;
+  double window_information[225];          // two-stage mode: the marginal of the previous key (prior of the next window update)
+  void reset_window_information() {        // prior_pose_noise_, prior_vel_noise_, prior_bias_noise_ (LTB:84-90)
+    for (double& v : window_information) v = 0.;
+    const double sp = opt.prior_pose_noise > 0 ? opt.prior_pose_noise : 1e-2, sv = opt.prior_velocity_noise > 0 ? opt.prior_velocity_noise : 1e4,
+                 sb = opt.prior_bias_noise > 0 ? opt.prior_bias_noise : 1e-2;
+    for (int k = 0; k < 15; ++k) {
+      const double s = k < 6 ? sp : (k < 9 ? sv : sb);
+      window_information[k * 15 + k] = 1.0 / (s * s);
+    }
+  }
 };
 
 namespace {
@@ -2576,6 +2586,7 @@ int dl_ltb_set_initial_state(dl_local_trajectory_builder* b, const dl_nav_state*
   b->prev_state = *state;
   b->initialized = true;
   b->dt.clear(); b->acc.clear(); b->gyr.clear();
+  b->reset_window_information();
   return DL_OK;
 }
 
@@ -2638,6 +2649,7 @@ int dl_ltb_add_synchronized_range_data(dl_local_trajectory_builder* b, double ti
       for (int c = 0; c < 3; ++c) st.bg[c] = gm[c];
       b->prev_state = st;
       b->initialized = true;
+      b->reset_window_information();
       b->init_acc.clear(); b->init_gyr.clear();
     }
     return DL_OK;
@@ -2660,20 +2672,40 @@ int dl_ltb_add_synchronized_range_data(dl_local_trajectory_builder* b, double ti
   const int64_t sizes[1] = {n};
   DL_TRY(check_imu_samples(ctx, &fo, &imu, 1));
   dl_scan_result* d_results = nullptr;
-  ImuRun run;
-  run.samples = &imu;
   FrontendBuffers f;
-  DL_TRY(frontend_enqueue_host(ctx, &fo, 1, ranges, sizes, origin, num_origins, nullptr, nullptr, submap_pose, matching.hi, matching.lo,
-                               0, &d_results, &run, &f));
   dl_scan_result r{};
   dl_nav_state state{};
   float cur7[7];
-  DL_TRY(d2h(ctx, &r, d_results, 1));
-  DL_TRY(d2h(ctx, &state, run.d_states, 1));
-  DL_TRY(d2h(ctx, cur7, f.current_pose, 7));
-  DL_TRY(sync(ctx));
-  out->scan = r;
-  if (r.ok != 1) return DL_OK;  // dropped like the reference's nullptr (LTB:497-534); the interval keeps integrating
+  dl_preintegration m{};   // two-stage mode: the interval's pre-integration and the predicted state
+  dl_nav_state pred{};
+  if (!b->opt.two_stage) {
+    ImuRun run;
+    run.samples = &imu;
+    DL_TRY(frontend_enqueue_host(ctx, &fo, 1, ranges, sizes, origin, num_origins, nullptr, nullptr, submap_pose, matching.hi, matching.lo,
+                                 0, &d_results, &run, &f));
+    DL_TRY(d2h(ctx, &r, d_results, 1));
+    DL_TRY(d2h(ctx, &state, run.d_states, 1));
+    DL_TRY(d2h(ctx, cur7, f.current_pose, 7));
+    DL_TRY(sync(ctx));
+    out->scan = r;
+    if (r.ok != 1) return DL_OK;  // dropped like the reference's nullptr (LTB:497-534); the interval keeps integrating
+  } else {
+    // the reference's chain: predict (AddImuData, LTB:188-199) -> plain match from the prediction (LTB:535-542) -> window (LTB:555)
+    std::vector<double> bias(b->prev_state.ba, b->prev_state.ba + 3);
+    bias.insert(bias.end(), b->prev_state.bg, b->prev_state.bg + 3);
+    DL_TRY(dl_imu_preintegrate(ctx, &b->opt.imu_noise, 1, offsets, b->dt.data(), b->acc.data(), b->gyr.data(), bias.data(), &m));
+    DL_TRY(dl_imu_predict(&b->prev_state, &m, imu.gravity, &pred));
+    double prev7[7], pred7[7];
+    for (int k = 0; k < 3; ++k) { prev7[k] = b->prev_state.p[k]; pred7[k] = pred.p[k]; }
+    for (int k = 0; k < 4; ++k) { prev7[3 + k] = b->prev_state.q[k]; pred7[3 + k] = pred.q[k]; }
+    DL_TRY(frontend_enqueue_host(ctx, &fo, 1, ranges, sizes, origin, num_origins, prev7, pred7, submap_pose, matching.hi, matching.lo, 0,
+                                 &d_results, nullptr, &f));
+    DL_TRY(d2h(ctx, &r, d_results, 1));
+    DL_TRY(d2h(ctx, cur7, f.current_pose, 7));
+    DL_TRY(sync(ctx));
+    out->scan = r;
+    if (r.ok != 1) return DL_OK;
+  }
   std::vector<float> returns_tracking((size_t)r.num_returns * 3), misses_tracking((size_t)r.num_misses * 3);
   b->clouds[2].resize((size_t)r.num_high_resolution * 3);
   b->clouds[3].resize((size_t)r.num_low_resolution * 3);
@@ -2682,6 +2714,28 @@ int dl_ltb_add_synchronized_range_data(dl_local_trajectory_builder* b, double ti
   DL_TRY(d2h(ctx, b->clouds[2].data(), f.clouds, b->clouds[2].size()));
   DL_TRY(d2h(ctx, b->clouds[3].data(), f.clouds + (size_t)f.cap * 3, b->clouds[3].size()));
   DL_TRY(sync(ctx));
+  if (b->opt.two_stage) {
+    // WindowOptimize(pose_estimate) (LTB:555): the matched pose is a prior on the new key next to the IMU factor and the carried
+    // marginal of the previous key. (Runs after the clouds have left the scratch arena, which this call reuses.)
+    dl_window_options wo{};
+    wo.pose_sigma_translation = b->opt.ceres_pose_noise_t > 0 ? b->opt.ceres_pose_noise_t : 1e-2;
+    wo.pose_sigma_rotation = b->opt.ceres_pose_noise_r > 0 ? b->opt.ceres_pose_noise_r : 1e-2;
+    wo.imu_weight = b->opt.imu_weight > 0 ? b->opt.imu_weight : 1.0;
+    wo.gravity[2] = b->opt.gravity;
+    wo.max_num_iterations = 10;
+    dl_solve_summary ws{};
+    double info_out[225];
+    DL_TRY(dl_window_optimize_batch(ctx, &wo, 1, &b->prev_state, b->window_information, &m, r.pose_estimate_local, &pred, nullptr, &state,
+                                    info_out, &ws));
+    if (ws.termination == 2) {  // the reference's FailureDetection path (LTB:856-859): fall back to matched pose + predicted rest, re-seed
+      state = pred;
+      for (int k = 0; k < 3; ++k) state.p[k] = r.pose_estimate_local[k];
+      for (int k = 0; k < 4; ++k) state.q[k] = r.pose_estimate_local[3 + k];
+      b->reset_window_information();
+    } else {
+      std::memcpy(b->window_information, info_out, sizeof(info_out));
+    }
+  }
   // the estimate becomes the previous state; the last sample of the interval latches the next one
   b->prev_state = state;
   {

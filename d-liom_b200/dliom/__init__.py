@@ -268,7 +268,9 @@ class LtbOptions(C.Structure):   # dl_ltb_options
                 ("high_resolution_max_range", C.c_int32), ("range_data_inserter", RangeDataInserterOptions),
                 ("motion_filter_max_time_seconds", C.c_double), ("motion_filter_max_distance_meters", C.c_double),
                 ("motion_filter_max_angle_radians", C.c_double), ("rotational_histogram_size", C.c_int32),
-                ("frames_for_static_initialization", C.c_int32)]
+                ("frames_for_static_initialization", C.c_int32), ("two_stage", C.c_int32), ("reserved", C.c_int32),
+                ("ceres_pose_noise_t", C.c_double), ("ceres_pose_noise_r", C.c_double), ("prior_pose_noise", C.c_double),
+                ("prior_velocity_noise", C.c_double), ("prior_bias_noise", C.c_double)]
 
     @staticmethod
     def defaults(frontend, noise4, **kw):
@@ -285,6 +287,10 @@ class LtbOptions(C.Structure):   # dl_ltb_options
         o.motion_filter_max_angle_radians = kw.pop("max_angle_radians", 0.004)
         o.rotational_histogram_size = kw.pop("rotational_histogram_size", 120)
         o.frames_for_static_initialization = kw.pop("frames_for_static_initialization", 7)
+        o.two_stage = int(kw.pop("two_stage", 0))
+        o.ceres_pose_noise_t, o.ceres_pose_noise_r = kw.pop("ceres_pose_noise_t", 1e-2), kw.pop("ceres_pose_noise_r", 1e-2)
+        o.prior_pose_noise = kw.pop("prior_pose_noise", 1e-2)
+        o.prior_velocity_noise, o.prior_bias_noise = kw.pop("prior_velocity_noise", 1e4), kw.pop("prior_bias_noise", 1e-2)
         assert not kw, kw
         return o
 

@@ -475,6 +475,8 @@ struct LocalTrajectoryBuilderOptions3D {  // proto::LocalTrajectoryBuilderOption
     c.range_data_inserter = {0.55, 0.49, 2, 0};
     c.motion_filter_max_time_seconds = 0.5; c.motion_filter_max_distance_meters = 0.1; c.motion_filter_max_angle_radians = 0.004;
     c.rotational_histogram_size = 120; c.frames_for_static_initialization = 7;
+    c.two_stage = 0;  // 1 = the reference's chain: plain match, then the window update (dl_window_optimize_batch)
+    c.ceres_pose_noise_t = 1e-2; c.ceres_pose_noise_r = 1e-2; c.prior_pose_noise = 1e-2; c.prior_velocity_noise = 1e4; c.prior_bias_noise = 1e-2;
   }
 };
 

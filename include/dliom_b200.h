@@ -585,6 +585,13 @@ typedef struct dl_ltb_options { /* proto::LocalTrajectoryBuilderOptions3D, the f
   double motion_filter_max_time_seconds, motion_filter_max_distance_meters, motion_filter_max_angle_radians;
   int32_t rotational_histogram_size;
   int32_t frames_for_static_initialization;        /* 7 in the reference (LTB:376) */
+  /* 0: the fused solve (scan match + IMU residual in one problem) gives the node's state. 1: the reference's TWO-STAGE chain —
+   * plain CeresScanMatcher3D::Match from the IMU-predicted pose (LTB:535-542), then the window update with that pose as a prior
+   * (dl_window_optimize_batch; LTB:555, :693-863); the carried information starts from the reference's priors (LTB:84-90). */
+  int32_t two_stage;
+  int32_t reserved;
+  double ceres_pose_noise_t, ceres_pose_noise_r;   /* imu_options: sigmas of the matched pose in the window */
+  double prior_pose_noise, prior_velocity_noise, prior_bias_noise; /* LTB:84-90: prior_pose_n, 1e4, 1e-2 */
 } dl_ltb_options;
 typedef struct dl_matching_result {
   int32_t has_result;                              /* 0 <=> the reference returns nullptr (initialising, no IMU yet, scan dropped) */

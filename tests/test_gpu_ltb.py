@@ -289,3 +289,51 @@ def test_cpp_shim_replays_a_two_lidar_drive(orc, tmp_path):
     assert b.num_submaps() == 2
     b.close()
     ctx.close()
+
+
+def test_two_stage_mode_follows_the_reference_chain(orc):
+    """dl_ltb_options.two_stage = 1: predict -> plain CeresScanMatcher3D::Match from the prediction (LTB:535-542) -> window update
+    with the matched pose as a prior (LTB:555, :693-863, here dl_window_optimize_batch). The oracle runs the same chain with its
+    own smoother state (estimate + carried information); the maps it matches against are the builder's own, exported per scan."""
+    import dliom
+    ctx = dliom.Context(0)
+    opts = orc.FrontEndOptions.defaults()
+    times, scans = drive(7)
+    b = make_builder(ctx, orc, num_range_data=50, max_time_seconds=0.05, two_stage=1, ceres_pose_noise_t=0.02, ceres_pose_noise_r=0.01,
+                     prior_pose_noise=0.01, prior_velocity_noise=0.2, prior_bias_noise=0.01)
+    state = imu_synth.state(times[0] - 0.1)
+    b.set_initial_state(state)
+    info = np.diag([1 / 0.01 ** 2] * 6 + [1 / 0.2 ** 2] * 3 + [1 / 0.01 ** 2] * 6)
+    origin = np.zeros((1, 3), np.float32)
+    last_t, latch = None, None
+    for k, (t1, rows) in enumerate(zip(times, scans)):
+        dt, acc, gyr = imu_synth.samples(t1 - 0.1, t1)
+        ts = t1 - 0.1 + np.arange(len(dt)) / 200.0
+        iv_dt, iv_acc, iv_gyr = ([latch[0]] if latch else []), ([latch[1]] if latch else []), ([latch[2]] if latch else [])
+        for j in range(0 if k == 0 else 1, len(dt)):
+            b.add_imu_data(ts[j], acc[j], gyr[j])
+            d = 1.0 / 500.0 if last_t is None else ts[j] - last_t
+            last_t = ts[j]
+            iv_dt.append(d); iv_acc.append(acc[j]); iv_gyr.append(gyr[j])
+        latch = (iv_dt[-1], iv_acc[-1], iv_gyr[-1])
+        hi, lo, sp, _, _ = b.submap(0)
+        ohi, olo = oracle_grids(orc, hi, lo)
+        xyzt = np.stack([rows["x"], rows["y"], rows["z"], rows["t"]], 1)
+        r = b.add_range_data(t1, xyzt)
+        assert r.has_result == 1 and r.scan.ok == 1
+        # the oracle's chain from ITS state
+        m = orc.imu_preintegrate(NOISE, state[10:13], state[13:16], np.array(iv_dt), np.array(iv_acc), np.array(iv_gyr))
+        pred = orc.imu_predict(state, m)
+        _, poses, ok = orc.frontend_batch(opts, [rows], origin, [state[:7]], [pred[:7]], sp, ohi, olo, 1)
+        assert ok[0] == 1
+        dtm, drm = pose_error(np.array(r.scan.pose_estimate_local[:]), poses[0])
+        assert dtm < 1e-6 and drm < 1e-7                                   # stage one: the plain match
+        _, state, info, ws = orc.window_optimize(state, info, m, poses[0], sigma_t=0.02, sigma_r=0.01, imu_weight=0.7, initial_j=pred)
+        got = NavStateVec(r.state)
+        dtn, drn = pose_error(got[:7], state[:7])
+        assert dtn < 2e-6 and drn < 1e-6, (k, dtn, drn)                      # stage two: the window
+        assert np.abs(got[7:] - state[7:]).max() < 1e-5
+        # the window moves the pose only a little away from the matcher (sigma 2 cm / 0.01 rad against a good prediction)
+        assert pose_error(got[:7], poses[0])[0] < 0.05
+    b.close()
+    ctx.close()
