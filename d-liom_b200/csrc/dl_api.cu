@@ -1638,7 +1638,7 @@ size_t frontend_bytes(int batch, int64_t cap, int num_origins, size_t extra, boo
                               B * C * 12, B * C * 12, B * 2 * C * 12, B * 28, (size_t)num_origins * 12,
                               B * 2 * 32 * 4, B * 4, B * sizeof(ScanConstants), 2 * sizeof(AdaptiveParams), B * 56, B * 24,
                               B * sizeof(NlsProblem), B * sizeof(NlsOutput),
-                              B * (size_t)next_pow2(cap) * 8, B * (size_t)next_pow2(cap) * 4, B * 4, 64, B * 28, B * C, B * C * 16,
+                              B * (size_t)next_pow2(cap) * 8, B * (size_t)next_pow2(cap) * 4, B * 4, B * 4 + 64, B * 28, B * C, B * C * 16,
                               adaptive_first_pass_bytes(2 * batch, cap) + 16 * 1024});
   if (stagewise) bytes += arena_bytes({B * tiles * 4, B * C * 4, B * C * 4, B * C * 4, B * C * 4, B * C * 12, B * C * 12, B * C * 12, B * C});
   return bytes + extra + 8192;
@@ -1665,7 +1665,7 @@ void carve(Arena& a, int batch, int64_t cap, int num_origins, FrontendBuffers* f
   f->problems = a.take<NlsProblem>(B); f->nls_out = a.take<NlsOutput>(B);
   f->tcap2 = next_pow2(cap);
   f->keys2 = a.take<unsigned long long>(B * f->tcap2); f->min2 = a.take<uint32_t>(B * f->tcap2);
-  f->last_index = a.take<int32_t>(B); f->error_flag = a.take<int32_t>(1);
+  f->last_index = a.take<int32_t>(B); f->error_flag = a.take<int32_t>(B);
   f->back_pose = a.take<float>(B * 7);
   f->win = a.take<uint8_t>(B * C);
   f->local4 = a.take<float>(B * C * 4);
@@ -2053,7 +2053,7 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
       ra.batch = nb; ra.first_counts = f.n1 + b0; ra.return_counts = f.n2 + b0; ra.miss_counts = f.n3 + b0;
       ra.adaptive_counts = f.countsA + 2 * b0; ra.adaptive_cropped = f.croppedA + 2 * b0; ra.adaptive_passes = f.npassesA + 2 * b0;
       ra.rtcsm_scores = have_scores ? f.rtcsm_scores + b0 : nullptr; ra.nls = f.nls_out + b0; ra.fused = (imu || raw) ? d_fused + b0 : nullptr; ra.submap = submap;
-      ra.results = d_results + b0; ra.error_flag = f.error_flag;
+      ra.results = d_results + b0; ra.error_flag = f.error_flag + b0;
       ra.imu_ok = d_imu_ok ? d_imu_ok + b0 : nullptr; ra.states_out = d_states_out ? d_states_out + b0 : nullptr;
       DL_TRY(launch_finalize_results(ctx, ra));
       return DL_OK;

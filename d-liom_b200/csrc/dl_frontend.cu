@@ -162,7 +162,7 @@ __device__ __forceinline__ int ingest_survivor(const FrontendArgs& a, int b, con
     const Int3 c = cell_index(outp, make_divider(a.second_resolution));
     unsigned long long key;
     if (!pack_key(c, cls == 2, &key)) {
-      *a.error_flag = 1;
+      a.error_flag[b] = 1;  // per scan: only this scan's result is invalidated
       cls = 0;
     } else {
       uint32_t hh = (hash_cell(c) ^ (cls == 2 ? 0x9e3779b9u : 0u)) & mask2;
@@ -392,7 +392,7 @@ __global__ void fe_reset_counters(FrontendArgs a, int batch) {
     float* cp = a.current_pose + 7 * b;
     cp[0] = cur.t.x; cp[1] = cur.t.y; cp[2] = cur.t.z; cp[3] = cur.q.w; cp[4] = cur.q.x; cp[5] = cur.q.y; cp[6] = cur.q.z;
   }
-  if (b == 0) *a.error_flag = 0;
+  a.error_flag[b] = 0;
 }
 
 }  // namespace

@@ -211,7 +211,7 @@ __global__ void finalize_results_kernel(ResultArgs a) {
   r.reserved = 0;
   // the reference drops the scan when any of the three clouds is empty (LTB:497-500, :510-513, :531-534)
   r.ok = (a.return_counts[b] > 0 && n_hi > 0 && n_lo > 0) ? 1 : 0;
-  if (a.error_flag && *a.error_flag) r.ok = -1;  // a point fell outside +-2^20 voxels: results are not valid
+  if (a.error_flag && a.error_flag[b]) r.ok = -1;  // a point fell outside +-2^20 voxels: results are not valid
   if (a.imu_ok && a.imu_ok[b] == 0) r.ok = -2;   // no IMU factor (no samples / covariance not positive definite): no solve ran
   const double* pose = a.fused ? a.fused[b].state : a.nls[b].pose;
   r.summary = a.fused ? a.fused[b].summary : a.nls[b].summary;

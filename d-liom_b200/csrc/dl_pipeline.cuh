@@ -97,7 +97,7 @@ struct FrontendArgs {
   int32_t *n_first, *n_returns_local, *n_returns, *n_misses, *last_index;
   float* current_pose;
   float* back_pose;              // inverse of current_pose, 7 floats per scan
-  int32_t* error_flag;
+  int32_t* error_flag;            // one per scan
 };
 int launch_fe_prepare(dl_context* ctx, const FrontendArgs& a, int batch);
 int launch_fe_expand_times(dl_context* ctx, const FrontendArgs& a, int batch, int max_runs_per_scan, float* times_out);
@@ -116,7 +116,7 @@ struct ResultArgs {
   const NlsOutput* nls;
   const FusedOutput* fused;        // optional: the fused (IMU) solve's output replaces `nls`
   Rigidd submap;
-  const int32_t* error_flag;       // set by the fused front half when a voxel key could not be packed
+  const int32_t* error_flag;       // per scan: set by the fused front half when a voxel key could not be packed
   const int32_t* imu_ok;           // optional: 0 = the scan's IMU factor could not be formed (result ok = -2)
   dl_nav_state* states_out;        // optional (fused solve): the estimated state in the LOCAL frame
   dl_scan_result* results;
