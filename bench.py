@@ -31,6 +31,9 @@ import sys
 import threading
 import time
 
+# NCCL prints its version banner (NCCL_DEBUG=VERSION/WARN) to stdout by default; stdout carries the ONE JSON line only.
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

@@ -1611,12 +1611,10 @@ struct FrontendBuffers {
       *passesA, *rtcsm_scores;
   uint8_t* cls;
   // fused front half
-  int64_t tcap2 = 0;
-  unsigned long long* keys2;
-  uint32_t* min2;
+  int64_t tcap2 = 0, bit_words = 0;
+  unsigned long long* slots2;  // second filter: one 64-bit word per slot (dl_frontend.cu)
+  uint32_t* bits;              // two survivor bitmaps per scan
   int32_t *last_index, *error_flag;
-  float* back_pose;
-  uint8_t* win;
   float* local4;
   uint8_t* adaptive_first;  // scratch of the adaptive filters' grid-wide first pass (dl_voxel.cu)
   ScanConstants* scans;
@@ -1638,7 +1636,7 @@ size_t frontend_bytes(int batch, int64_t cap, int num_origins, size_t extra, boo
                               B * C * 12, B * C * 12, B * 2 * C * 12, B * 28, (size_t)num_origins * 12,
                               B * 2 * 32 * 4, B * 4, B * sizeof(ScanConstants), 2 * sizeof(AdaptiveParams), B * 56, B * 24,
                               B * sizeof(NlsProblem), B * sizeof(NlsOutput),
-                              B * (size_t)next_pow2(cap) * 8, B * (size_t)next_pow2(cap) * 4, B * 4, B * 4 + 64, B * 28, B * C, B * C * 16,
+                              B * (size_t)next_pow2(cap) * 8, B * 2 * ((C + 31) / 32) * 4, B * 4, B * 4 + 64, B * C * 16,
                               adaptive_first_pass_bytes(2 * batch, cap) + 16 * 1024});
   if (stagewise) bytes += arena_bytes({B * tiles * 4, B * C * 4, B * C * 4, B * C * 4, B * C * 4, B * C * 12, B * C * 12, B * C * 12, B * C});
   return bytes + extra + 8192;
@@ -1664,10 +1662,9 @@ void carve(Arena& a, int batch, int64_t cap, int num_origins, FrontendBuffers* f
   f->initial_pose = a.take<double>(B * 7); f->target = a.take<double>(B * 3);
   f->problems = a.take<NlsProblem>(B); f->nls_out = a.take<NlsOutput>(B);
   f->tcap2 = next_pow2(cap);
-  f->keys2 = a.take<unsigned long long>(B * f->tcap2); f->min2 = a.take<uint32_t>(B * f->tcap2);
+  f->bit_words = (int64_t)((C + 31) / 32);
+  f->slots2 = a.take<unsigned long long>(B * f->tcap2); f->bits = a.take<uint32_t>(B * 2 * f->bit_words);
   f->last_index = a.take<int32_t>(B); f->error_flag = a.take<int32_t>(B);
-  f->back_pose = a.take<float>(B * 7);
-  f->win = a.take<uint8_t>(B * C);
   f->local4 = a.take<float>(B * C * 4);
   f->adaptive_first = a.take<uint8_t>(adaptive_first_pass_bytes(2 * batch, cap) + 16 * 1024);
   f->block_counts = nullptr; f->slot = nullptr; f->keep1 = f->keep2 = f->keep3 = nullptr;
@@ -1689,11 +1686,14 @@ FrontendArgs make_frontend_args(const dl_frontend_options& o, const FrontendBuff
   fa.first_resolution = 0.5f * o.voxel_filter_size;  // LTB:394
   fa.second_resolution = o.voxel_filter_size;        // LTB:479-484
   fa.min_range = o.min_range; fa.max_range = o.max_range; fa.scan_period = o.scan_period;
-  fa.table1 = f.table; fa.keys2 = f.keys2; fa.min2 = f.min2;
-  fa.local = f.local4; fa.win = f.win; fa.tile_counts = f.tile_counts;
+  fa.table1 = f.table; fa.slots2 = f.slots2; fa.bits = f.bits; fa.bit_words = f.bit_words;
+  fa.idx_bits = 1;
+  while (((int64_t)1 << fa.idx_bits) < f.cap) ++fa.idx_bits;      // point indices are < cap
+  fa.axis_bits = std::min(21, (63 - fa.idx_bits) / 3);             // 15 bits per axis up to 256 k points per scan
+  fa.local = f.local4;
   fa.returns_tracking = f.returns_tracking; fa.misses_tracking = f.misses_tracking;
   fa.n_first = f.n1; fa.n_returns_local = f.n_ret; fa.n_returns = f.n2; fa.n_misses = f.n3; fa.last_index = f.last_index;
-  fa.current_pose = f.current_pose; fa.back_pose = f.back_pose; fa.error_flag = f.error_flag;
+  fa.current_pose = f.current_pose; fa.error_flag = f.error_flag;
   return fa;
 }
 
@@ -1702,7 +1702,8 @@ size_t time_runs_bytes(const dl_frontend_options& o, int num_scans) {  // device
   return arena_bytes({(size_t)(num_scans + 1) * 4, (size_t)o.time_run_offsets[num_scans] * 4, (size_t)o.time_run_offsets[num_scans] * 4});
 }
 size_t time_expand_bytes(const dl_frontend_options& o, int num_scans, int64_t cap) {
-  return o.range_row_floats == 3 ? (size_t)num_scans * (size_t)cap * 4 + 256 : 0;
+  if (o.range_row_floats != 3 || !o.time_run_offsets || num_scans <= 0) return 0;
+  return (size_t)num_scans * (size_t)cap * 4 + (size_t)o.time_run_offsets[num_scans] * 32 + 768;  // run ids per row + run poses
 }
 int row_floats_of(const dl_frontend_options& o) { return o.range_row_floats == 4 ? 4 : (o.range_row_floats == 3 ? 3 : 8); }
 
@@ -1883,9 +1884,11 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
     if (runs > (size_t)8 * num_scans) {  // many runs per scan: expand once instead of searching per survivor
       int max_runs = 0;
       for (int b = 0; b < num_scans; ++b) max_runs = std::max(max_runs, (int)(o.time_run_offsets[b + 1] - o.time_run_offsets[b]));
-      float* d_times = a.take<float>((size_t)num_scans * in_cap);
-      DL_TRY(launch_fe_expand_times(ctx, fa, num_scans, max_runs, d_times));  // needs counts + runs only, both uploaded above
-      fa.times = d_times;
+      int32_t* d_run_of_row = a.take<int32_t>((size_t)num_scans * in_cap);
+      DL_TRY(launch_fe_expand_runs(ctx, fa, num_scans, max_runs, d_run_of_row));  // needs counts + runs only, both uploaded above
+      fa.run_of_row = d_run_of_row;
+      fa.run_pose = a.take<float>(runs * 8);  // filled per sub-batch by fe_run_poses once the scans' deskew constants exist
+      fa.max_runs = max_runs;
     }
   }
   DL_TRY(launch_fe_prepare(ctx, fa, f.batch));

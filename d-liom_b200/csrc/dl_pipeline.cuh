@@ -74,7 +74,9 @@ struct FrontendArgs {
   const int32_t* run_offsets;    // row_floats == 3: per-point times as runs (dl_frontend_options::time_run_*), device copies
   const int32_t* run_first_row;
   const float* run_value;
-  const float* times;            // optional: the runs expanded to one float per row (scan b at b * in_cap); null = search the runs
+  const int32_t* run_of_row;     // optional: the run index of every row (scan b at b * in_cap); null = search the runs
+  float* run_pose;               // optional (with run_of_row): deskew pose of every run, 8 floats (t xyz, q wxyz, pad), fe_run_poses
+  int max_runs;                  // most runs any scan of the batch has
   int64_t in_cap;
   int row_floats;
   int first_scan;        // kernels handle scans [first_scan, first_scan + gridDim.y): lets sub-batches pipeline
@@ -87,20 +89,19 @@ struct FrontendArgs {
   float first_resolution, second_resolution, min_range, max_range;
   double scan_period;
   uint32_t* table1;              // first filter: slot -> min point index
-  unsigned long long* keys2;     // second filter: slot -> packed voxel key (bit 63 = miss)
-  uint32_t* min2;
+  unsigned long long* slots2;    // second filter: slot -> [miss | relative voxel key | point index] (dl_frontend.cu)
+  int idx_bits, axis_bits;       // widths of the index field and of one axis of the key
+  uint32_t* bits;                // per scan two bitmaps (returns, misses) of bit_words words: bit i = point i survives
+  int64_t bit_words;             // ceil(cap / 32)
   float* local;                  // float4 per input row: local-frame point of a first-filter survivor + class in .w
-  uint8_t* win;                  // 1 = owns its second-filter voxel
-  int32_t* tile_counts;
   float* returns_tracking;
   float* misses_tracking;
   int32_t *n_first, *n_returns_local, *n_returns, *n_misses, *last_index;
   float* current_pose;
-  float* back_pose;              // inverse of current_pose, 7 floats per scan
   int32_t* error_flag;            // one per scan
 };
 int launch_fe_prepare(dl_context* ctx, const FrontendArgs& a, int batch);
-int launch_fe_expand_times(dl_context* ctx, const FrontendArgs& a, int batch, int max_runs_per_scan, float* times_out);
+int launch_fe_expand_runs(dl_context* ctx, const FrontendArgs& a, int batch, int max_runs_per_scan, int32_t* run_of_row_out);
 int launch_fe_first_filter(dl_context* ctx, FrontendArgs a, int first_scan, int num_scans);
 int launch_fe_rest(dl_context* ctx, FrontendArgs a, int first_scan, int batch);
 
