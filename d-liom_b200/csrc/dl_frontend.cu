@@ -91,6 +91,8 @@ __global__ void __launch_bounds__(kBlock) fe_first_filter_insert(FrontendArgs a)
     const Int3 c = cell_index(load_xyz(rows, a.row_floats, i), res);
     uint32_t h = hash_cell(c) & mask;
     for (;;) {
+      // (a plain load before the CAS — two thirds of the points meet an owner with a lower index — was measured and is slower:
+      //  113.2 k vs 115.3 k scans/s, profiles/r2y_sweep.log: the kernel is bound by dependent round trips, not by atomic throughput)
       const uint32_t prev = atomicCAS(tab + h, kEmpty32, (uint32_t)i);
       if (prev == kEmpty32) break;
       const Int3 o = cell_index(load_xyz(rows, a.row_floats, prev), res);
@@ -470,6 +472,7 @@ int launch_fe_first_filter(dl_context* ctx, FrontendArgs a, int first_scan, int 
   if (num_scans <= 0) return DL_OK;
   a.first_scan = first_scan;
   const int tiles = (int)std::min<int64_t>((a.cap + kBlock - 1) / kBlock, 128);
+  if (const char* env = std::getenv("DLIOM_FE_FLAGS")) a.flags = std::atoi(env);  // experiments: 1 = always CAS in the first filter
   fe_first_filter_insert<<<dim3(tiles, num_scans), kBlock, 0, ctx->stream>>>(a);
   DL_LAUNCH_CHECK(ctx, "fe_first_filter_insert");
   return DL_OK;

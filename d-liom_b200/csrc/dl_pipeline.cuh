@@ -79,6 +79,7 @@ struct FrontendArgs {
   int max_runs;                  // most runs any scan of the batch has
   int64_t in_cap;
   int row_floats;
+  int flags;             // experiment switches (DLIOM_FE_FLAGS), 0 = defaults
   int first_scan;        // kernels handle scans [first_scan, first_scan + gridDim.y): lets sub-batches pipeline
   const int32_t* counts;
   const ScanConstants* scans;
