@@ -80,27 +80,43 @@ __global__ void __launch_bounds__(kBlock) fe_expand_runs(FrontendArgs a, int32_t
 }
 
 // ---------------------------------------------------------------------------------------------------- A
-__global__ void __launch_bounds__(kBlock) fe_first_filter_insert(FrontendArgs a) {
+// kFirstBatch points in flight per thread (all row loads, then all claims, then the collisions): an experiment knob, see the launcher.
+template <int kFirstBatch>
+__global__ void __launch_bounds__(kBlock, kFirstBatch == 1 ? 8 : (kFirstBatch == 2 ? 6 : 5)) fe_first_filter_insert(FrontendArgs a) {
   const int b = a.first_scan + blockIdx.y;
   const int n = a.counts[b];
   const float* rows = a.ranges + (size_t)b * a.in_cap * a.row_floats;
   uint32_t* tab = a.table1 + (size_t)b * a.tcap1;
   const uint32_t mask = (uint32_t)a.tcap1 - 1;
   const CellDivider res = make_divider(a.first_resolution);
-  for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
-    const Int3 c = cell_index(load_xyz(rows, a.row_floats, i), res);
-    uint32_t h = hash_cell(c) & mask;
-    for (;;) {
-      // (a plain load before the CAS — two thirds of the points meet an owner with a lower index — was measured and is slower:
-      //  113.2 k vs 115.3 k scans/s, profiles/r2y_sweep.log: the kernel is bound by dependent round trips, not by atomic throughput)
-      const uint32_t prev = atomicCAS(tab + h, kEmpty32, (uint32_t)i);
-      if (prev == kEmpty32) break;
-      const Int3 o = cell_index(load_xyz(rows, a.row_floats, prev), res);
-      if (o.x == c.x && o.y == c.y && o.z == c.z) {
-        if ((uint32_t)i < prev) atomicMin(tab + h, (uint32_t)i);  // the owner only ever decreases
-        break;
+  const int stride = gridDim.x * kBlock;
+  for (int i0 = blockIdx.x * kBlock + threadIdx.x; i0 < n; i0 += kFirstBatch * stride) {
+    Int3 c[kFirstBatch];
+    uint32_t h[kFirstBatch], prev[kFirstBatch];
+#pragma unroll
+    for (int u = 0; u < kFirstBatch; ++u) {
+      const int i = i0 + u * stride;
+      c[u] = cell_index(i < n ? load_xyz(rows, a.row_floats, i) : Vec3f{0.f, 0.f, 0.f}, res);
+      h[u] = hash_cell(c[u]) & mask;
+    }
+#pragma unroll
+    for (int u = 0; u < kFirstBatch; ++u) {
+      const int i = i0 + u * stride;
+      prev[u] = i < n ? atomicCAS(tab + h[u], kEmpty32, (uint32_t)i) : kEmpty32;
+    }
+#pragma unroll
+    for (int u = 0; u < kFirstBatch; ++u) {
+      const int i = i0 + u * stride;
+      uint32_t p = prev[u], hh = h[u];
+      while (p != kEmpty32) {  // the slot has an owner: same voxel -> the lower index stays; else probe on
+        const Int3 o = cell_index(load_xyz(rows, a.row_floats, p), res);
+        if (o.x == c[u].x && o.y == c[u].y && o.z == c[u].z) {
+          if ((uint32_t)i < p) atomicMin(tab + hh, (uint32_t)i);  // the owner only ever decreases
+          break;
+        }
+        hh = (hh + 1) & mask;
+        p = atomicCAS(tab + hh, kEmpty32, (uint32_t)i);
       }
-      h = (h + 1) & mask;
     }
   }
 }
@@ -247,14 +263,15 @@ __global__ void __launch_bounds__(kBlock, kRunPose ? 6 : 4) fe_ingest_second_ins
   // The first filter's survivors are exactly the non-empty table slots: stream the table (coalesced) instead of
   // probing it once per raw point. Order does not matter here: the second filter keys on the original index.
   if (n == 0) return;
+  // (four slots per thread and step through one 16-byte load: same kernel time in the serial launch list, slightly slower in the
+  //  overlapped step — profiles/r3b_ab.log — so the stream stays one slot per thread)
   for (int h = blockIdx.x * kBlock + threadIdx.x; h < (int)a.tcap1; h += gridDim.x * kBlock) {
     const uint32_t owner = __ldcg(tab + h);
     const bool surv = owner != kEmpty32;
-    const int i = (int)owner;
     const unsigned ballot = __ballot_sync(0xffffffffu, surv);
     if (surv) {
-      q[queued + __popc(ballot & ((1u << lane) - 1))] = i;
-      last = max(last, i);
+      q[queued + __popc(ballot & ((1u << lane) - 1))] = (int)owner;
+      last = max(last, (int)owner);
     }
     queued += __popc(ballot);
     survivors += surv;
@@ -473,7 +490,12 @@ int launch_fe_first_filter(dl_context* ctx, FrontendArgs a, int first_scan, int 
   a.first_scan = first_scan;
   const int tiles = (int)std::min<int64_t>((a.cap + kBlock - 1) / kBlock, 128);
   if (const char* env = std::getenv("DLIOM_FE_FLAGS")) a.flags = std::atoi(env);  // experiments: 1 = always CAS in the first filter
-  fe_first_filter_insert<<<dim3(tiles, num_scans), kBlock, 0, ctx->stream>>>(a);
+  // points in flight per thread: 1 is the measured optimum (profiles/r3a_sweep.log: 113.4 k scans/s; 2 -> 108.8 k; 4 -> 94.2 k) —
+  // the kernel runs at the L2's atomic throughput (~130 G CAS/s), more outstanding atomics only lengthen its queues
+  const int batch_points = (a.flags & 3) == 2 ? 2 : ((a.flags & 3) == 3 ? 4 : 1);
+  if (batch_points == 1) fe_first_filter_insert<1><<<dim3(tiles, num_scans), kBlock, 0, ctx->stream>>>(a);
+  else if (batch_points == 2) fe_first_filter_insert<2><<<dim3(tiles, num_scans), kBlock, 0, ctx->stream>>>(a);
+  else fe_first_filter_insert<4><<<dim3(tiles, num_scans), kBlock, 0, ctx->stream>>>(a);
   DL_LAUNCH_CHECK(ctx, "fe_first_filter_insert");
   return DL_OK;
 }

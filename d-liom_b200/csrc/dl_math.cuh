@@ -8,6 +8,7 @@
 // Reference interfaces: C/transform/rigid_transform.h:124-219, C/transform/transform.h:33-37,85-99,
 // C/common/port.h:41-43 (RoundToInt = lround, ties away from zero).
 #pragma once
+#include <cstring>
 #include <cmath>
 #include <cstdint>
 
@@ -118,13 +119,25 @@ struct CellDivider {
   float resolution, inverse;
 };
 DL_HD CellDivider make_divider(float resolution) { return {resolution, 1.0f / resolution}; }
+// The rounding itself stays on the FMA pipe (no FRND / F2I, which issue at a quarter of the rate and were the hottest lines of
+// every voxel kernel in ncu): adding 1.5 * 2^23 to 0 <= aq < 2^22 rounds aq to the nearest integer and leaves that integer in the
+// low mantissa bits of the sum; away from a k + 0.5 boundary nearest-even IS lround.
 DL_HD int round_div(float x, const CellDivider& d) {
   const float q = x * d.inverse;
   const float aq = fabsf(q);
-  const float fr = aq - floorf(aq);                       // exact
-  if (fabsf(fr - 0.5f) > aq * 4.8e-7f + 1e-30f && aq < 4194304.f) {
-    const int k = (int)floorf(aq + 0.5f);                   // aq + 0.5 is exact below 2^22
-    return q < 0.f ? -k : k;
+  if (aq < 4194304.f) {
+    const float t = aq + 12582912.f;          // bits: 0x4B400000 + nearest integer
+    const float dist = fabsf(aq - (t - 12582912.f));  // exact distance to that integer, <= 0.5
+    if (0.5f - dist > aq * 4.8e-7f + 1e-30f) {        // exact; == |frac(aq) - 0.5| of the boundary test
+#ifdef __CUDA_ARCH__
+      const int k = __float_as_int(t) - 0x4B400000;
+#else
+      int bits;
+      memcpy(&bits, &t, sizeof(bits));
+      const int k = bits - 0x4B400000;
+#endif
+      return q < 0.f ? -k : k;
+    }
   }
   return round_to_int(x / d.resolution);
 }

@@ -166,35 +166,54 @@ __device__ __forceinline__ int block_sum_1024(int v) {
   return result;
 }
 
-// Order-preserving compaction of ids [0, n) with predicate flags computed by `pred`; returns the count.
+// Exclusive prefix of one value per warp over the 32 warps of the CTA (value must be warp-uniform); *total = the sum.
+__device__ __forceinline__ int warp_bases_1024(int warp_value, int* total) {
+  __shared__ int ws[kAdaptiveWarps], wb[kAdaptiveWarps + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();  // protects ws / wb across successive calls
+  if (lane == 0) ws[warp] = warp_value;
+  __syncthreads();
+  if (warp == 0) {
+    const int v = ws[lane];
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    wb[lane] = inc - v;
+    if (lane == 31) wb[kAdaptiveWarps] = inc;
+  }
+  __syncthreads();
+  *total = wb[kAdaptiveWarps];
+  return wb[warp];
+}
+
+// Order-preserving compaction of ids [0, n) with predicate flags computed by `pred` (pure: it is evaluated twice); returns the
+// count. Every warp owns a contiguous chunk of ids: it counts its flags (no barrier between its rounds, so the loads behind
+// `pred` pipeline), ONE block scan turns the 32 counts into bases, and a second sweep writes. (Round 1 walked the ids 1024 at a
+// time with three barriers and a 32-step shared-memory sum per round: 19 % of the kernel's stall samples.)
 template <typename Pred, typename Emit>
 __device__ __forceinline__ int block_compact_1024(int n, Pred pred, Emit emit) {
-  __shared__ int ws[32];
-  __shared__ int running;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) running = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += kAdaptiveBlock) {
-    const int i = base + threadIdx.x;
-    const int flag = (i < n) ? (pred(i) ? 1 : 0) : 0;
-    const unsigned ballot = __ballot_sync(0xffffffffu, flag);
-    const int in_warp = __popc(ballot & ((1u << lane) - 1));
-    if (lane == 0) ws[warp] = __popc(ballot);
-    __syncthreads();
-    int warp_base = 0, tile_total = 0;
-#pragma unroll
-    for (int w = 0; w < kAdaptiveWarps; ++w) {
-      const int s = ws[w];
-      if (w < warp) warp_base += s;
-      tile_total += s;
-    }
-    const int start = running;
-    if (flag) emit(start + warp_base + in_warp, i);
-    __syncthreads();
-    if (threadIdx.x == 0) running = start + tile_total;
-    __syncthreads();
+  const int chunk = ((n + kAdaptiveBlock - 1) / kAdaptiveBlock) * 32;  // ids per warp, a multiple of 32
+  const int begin = warp * chunk, end = min(n, begin + chunk);
+  int count = 0;
+  for (int base = begin; base < end; base += 32) {
+    const int i = base + lane;
+    count += __popc(__ballot_sync(0xffffffffu, i < end && pred(i)));
   }
-  return running;
+  int total;
+  int pos = warp_bases_1024(count, &total);
+  for (int base = begin; base < end; base += 32) {
+    const int i = base + lane;
+    const bool flag = i < end && pred(i);
+    const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+    if (flag) emit(pos + __popc(ballot & ((1u << lane) - 1)), i);
+    pos += __popc(ballot);
+  }
+  __syncthreads();  // the emitted list is complete for every reader
+  return total;
 }
 
 // The reference's search over voxel edge lengths (AdaptivelyVoxelFiltered, voxel_filter.cc:40-77), statement for
@@ -236,6 +255,7 @@ constexpr int kFastPoints = 8;                        // points per thread held 
 constexpr int kFastSlots = 4096;                      // shared-memory table slots (12 B each = 48 KiB)
 constexpr int kFastExtra = 14336;                     // further points cached in shared memory (12 B each = 168 KiB)
 constexpr int kFastCapacity = kFastPoints * 1024 + kFastExtra;  // 22 528 points
+static_assert(kFastCapacity / 1024 <= 32, "the compaction keeps one round count per lane");
 constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
 
 struct FastTable {
@@ -488,42 +508,52 @@ __global__ void __launch_bounds__(kAdaptiveBlock) adaptive_voxel_kernel(
     bool done = ok;
     if (ok && last_edge != result_edge) done = fast_pass(fast, px, py, pz, m, result_edge, &fail_flag) >= 0;
     if (done) {
-      // ordered compaction of the survivors, 1024 ids per round
-      __shared__ int ws2[32];
-      __shared__ int running2;
+      // Ordered compaction of the survivors. Id j = k * 1024 + t belongs to round k, warp t / 32: the output order is (round, warp,
+      // lane). Every warp counts its survivors per round (lane k keeps round k's count: at most kFastCapacity / 1024 = 22 rounds), ONE block
+      // scan over the (round, warp) sequence gives every warp its base per round, then the warps write.
+      __shared__ int seq[32 * kAdaptiveWarps];
       const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-      if (threadIdx.x == 0) running2 = 0;
-      __syncthreads();
-      auto emit_round = [&](int j, float x, float y, float z) {
-        const int flag = (j < m && fast_survives(fast, x, y, z, result_edge, j)) ? 1 : 0;
-        const unsigned ballot = __ballot_sync(0xffffffffu, flag);
-        if (lane == 0) ws2[warp] = __popc(ballot);
-        __syncthreads();
-        int warp_base = 0, tile_total = 0;
-#pragma unroll
-        for (int w = 0; w < kAdaptiveWarps; ++w) {
-          const int s = ws2[w];
-          if (w < warp) warp_base += s;
-          tile_total += s;
-        }
-        const int start = running2;
-        if (flag) out[start + warp_base + __popc(ballot & ((1u << lane) - 1))] = (int32_t)rows[j];
-        __syncthreads();
-        if (threadIdx.x == 0) running2 = start + tile_total;
-        __syncthreads();
+      const int rounds = (m + kAdaptiveBlock - 1) / kAdaptiveBlock;
+      uint32_t flags = 0;
+      int my_round_count = 0;
+      auto test_round = [&](int k, float x, float y, float z) {
+        const int j = k * kAdaptiveBlock + threadIdx.x;
+        const bool f = j < m && fast_survives(fast, x, y, z, result_edge, j);
+        const unsigned ballot = __ballot_sync(0xffffffffu, f);
+        if (f) flags |= 1u << k;
+        if (lane == k) my_round_count = __popc(ballot);
       };
 #pragma unroll
       for (int k = 0; k < kFastPoints; ++k) {
-        if (k * kAdaptiveBlock >= m) break;
-        emit_round(k * kAdaptiveBlock + threadIdx.x, px[k], py[k], pz[k]);
+        if (k >= rounds) break;
+        test_round(k, px[k], py[k], pz[k]);
       }
-      for (int base = kFastPoints * kAdaptiveBlock; base < m; base += kAdaptiveBlock) {
-        const int j = base + threadIdx.x;
-        const float* e = fast.extra + (size_t)(min(j, m - 1) - kFastPoints * kAdaptiveBlock) * 3;
-        emit_round(j, e[0], e[1], e[2]);
+      for (int k = kFastPoints; k < rounds; ++k) {
+        const float* e = fast.extra + (size_t)(min(k * kAdaptiveBlock + (int)threadIdx.x, m - 1) - kFastPoints * kAdaptiveBlock) * 3;
+        test_round(k, e[0], e[1], e[2]);
+      }
+      if (lane < rounds) seq[lane * kAdaptiveWarps + warp] = my_round_count;
+      __syncthreads();
+      // exclusive scan of seq[0 .. rounds * 32): one entry per thread
+      const int entries = rounds * kAdaptiveWarps;
+      const int v = (int)threadIdx.x < entries ? seq[threadIdx.x] : 0;
+      int inc = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+      }
+      int kept;
+      const int wbase = warp_bases_1024(__shfl_sync(0xffffffffu, inc, 31), &kept);
+      if ((int)threadIdx.x < entries) seq[threadIdx.x] = wbase + inc - v;
+      __syncthreads();
+      for (int k = 0; k < rounds; ++k) {
+        const bool f = (flags >> k) & 1u;
+        const unsigned ballot = __ballot_sync(0xffffffffu, f);
+        if (f) out[seq[k * kAdaptiveWarps + warp] + __popc(ballot & ((1u << lane) - 1))] = (int32_t)rows[k * kAdaptiveBlock + threadIdx.x];
       }
       if (threadIdx.x == 0) {
-        keep_counts[pair] = running2;
+        keep_counts[pair] = kept;
         num_passes[pair] = npass;
       }
       return;
