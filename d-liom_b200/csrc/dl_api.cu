@@ -1905,6 +1905,9 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
   // halves on one stream costs more than the priority gains; 1 is kept for experiments.)
   int split = 0;
   if (const char* env = std::getenv("DLIOM_PIPELINE")) split = rtcsm ? 0 : std::atoi(env);
+  // DLIOM_SERIAL=1: every sub-batch on the main stream, nothing overlaps (bench.py's per-stage roofline pass: the stage events then
+  // bracket the kernels' own durations at the sub-batch size the step really uses)
+  const bool serial = std::getenv("DLIOM_SERIAL") != nullptr && !split;
   cudaStream_t main_stream = ctx->stream;
   cudaEvent_t prepared = ctx->take_event();
   DL_CUDA(ctx, cudaEventRecord(prepared, main_stream));
@@ -1962,7 +1965,7 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
   for (int k = 0; k < chunks && status == DL_OK; ++k) {
     const int b0 = bounds[k], b1 = bounds[k + 1], nb = b1 - b0;
     if (nb <= 0) continue;
-    ctx->stream = split ? main_stream : ((k & 1) ? ctx->aux_stream : main_stream);
+    ctx->stream = (split || serial) ? main_stream : ((k & 1) ? ctx->aux_stream : main_stream);
     auto run = [&]() -> int {
       {
         StageScope st(ctx, "voxel_filter_first");

@@ -605,6 +605,13 @@ class Context:
                                    hi_grids, lo_grids):
         """This rank's (node, submap) searches + the ncclAllGather of the constraint rows -> (table of world * capacity
         ConstraintRow, ExchangeInfo). Pruned pairs have found == 0, unused slots found == -1."""
+        return self.constraint_exchange_plan(comm, options, capacity, submap_ids, node_ids, pose_guesses, hi_clouds, lo_clouds,
+                                             hi_grids, lo_grids)()
+
+    def constraint_exchange_plan(self, comm, options, capacity, submap_ids, node_ids, pose_guesses, hi_clouds, lo_clouds,
+                                 hi_grids, lo_grids):
+        """The marshalled arguments of constraint_search_exchange as a callable: a caller that repeats the same exchange (or
+        runs it from a worker thread, like the reference's constraint-builder pool) pays the numpy packing once."""
         count = len(pose_guesses)
         his = [np.ascontiguousarray(c, np.float32).reshape(-1, 3) for c in hi_clouds]
         los = [np.ascontiguousarray(c, np.float32).reshape(-1, 3) for c in lo_clouds]
@@ -614,14 +621,19 @@ class Context:
         lo_all = np.ascontiguousarray(np.concatenate(los) if count else np.zeros((1, 3), np.float32))
         hg = (C.c_void_p * max(count, 1))(*[g.h for g in hi_grids])
         lg = (C.c_void_p * max(count, 1))(*[g.h for g in lo_grids])
-        table = (ConstraintRow * (comm.world * capacity))()
-        info = ExchangeInfo()
-        self.check(self.L.dl_constraint_search_exchange(self.h, comm.h, C.byref(options), count, capacity,
-                                                        np.ascontiguousarray(submap_ids, np.int32),
-                                                        np.ascontiguousarray(node_ids, np.int32),
-                                                        np.ascontiguousarray(pose_guesses, np.float64).reshape(-1, 7), hi_all,
-                                                        hi_off, lo_all, lo_off, hg, lg, table, C.byref(info)))
-        return table, info
+        sub = np.ascontiguousarray(submap_ids, np.int32)
+        nod = np.ascontiguousarray(node_ids, np.int32)
+        guesses = np.ascontiguousarray(pose_guesses, np.float64).reshape(-1, 7)
+        keep = (hi_grids, lo_grids)   # the grids must outlive the plan
+
+        def run():
+            table = (ConstraintRow * (comm.world * capacity))()
+            info = ExchangeInfo()
+            self.check(self.L.dl_constraint_search_exchange(self.h, comm.h, C.byref(options), count, capacity, sub, nod, guesses,
+                                                            hi_all, hi_off, lo_all, lo_off, hg, lg, table, C.byref(info)))
+            return table, info
+        run.keep = keep
+        return run
 
     def window_optimize_batch(self, means_i, prior_infos, preints, matched_poses, sigma_t=0.05, sigma_r=0.01, imu_weight=1.0,
                               gravity=(0.0, 0.0, 9.8), max_iter=10, gravity_factor=None, initial_j=None):

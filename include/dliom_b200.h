@@ -426,7 +426,10 @@ typedef struct dl_scan_result {
   dl_solve_summary summary;
   float rtcsm_score;
   int32_t ok;                             /* 0 = dropped (empty cloud), like the reference's nullptr; -1 = a point lay
-                                             outside +-2^20 voxels of the fused front half (results invalid); -2 = no IMU
+                                             outside the voxel-key span of the fused front half: +-2^(b-1) voxels of
+                                             voxel_filter_size around the scan's pose, b = min(21, (63 - ceil(log2(capacity)))
+                                             / 3), i.e. +-2.4 km at 0.15 m for scans up to 256 k points (results invalid;
+                                             dl_voxel_filter itself has no limit); -2 = no IMU
                                              factor could be formed for this scan (dl_frontend_*_imu_samples) */
   int32_t num_first_filter, num_returns, num_misses, num_high_resolution, num_low_resolution;
   /* adaptive filter bookkeeping: points inside max_range and voxel passes run, per filter (high, low) */

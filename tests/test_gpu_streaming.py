@@ -138,3 +138,28 @@ def test_twelve_byte_rows_with_time_runs_are_bit_identical(orc):
     with pytest.raises(dliom.DlError):
         ctx.frontend_match_batch(bad, rows3, w["origin"], w["prev"], w["cur"], w["submap_pose"], hi, lo)
     ctx.close()
+
+
+def test_key_range_flag_is_per_scan(orc):
+    """The fused front half keys its second voxel filter on voxel indices RELATIVE to the scan's pose (dl_frontend.cu): with a
+    0.4 mm voxel the 16-bit axis span of a ~29 k-point scan is +-13 m, so a scan with farther points is flagged (ok = -1) while a
+    scan of the same batch whose points all lie within 5 m is registered normally."""
+    import dliom
+    from helpers import workload
+    w = workload()
+    ctx = dliom.Context(0)
+    hi, lo = dliom.Grid.from_oracle(ctx, w["hi"]), dliom.Grid.from_oracle(ctx, w["lo"])
+    fo = dliom.FrontendOptions.from_oracle(w["opts"])
+    fo.range_row_floats = 4
+    fo.voxel_filter_size = 4e-4
+    full = np.ascontiguousarray(np.stack([w["scans"][0][k] for k in "xyzt"], 1))
+    near = np.ascontiguousarray(full[np.linalg.norm(full[:, :3], axis=1) < 5.0])
+    near[-1, 3] = 0.0
+    assert len(near) > 500 and np.linalg.norm(full[:, :3], axis=1).max() > 20.0
+    res = ctx.frontend_match_batch(fo, [near, full], w["origin"], w["prev"][[0, 0]], w["cur"][[0, 0]], w["submap_pose"], hi, lo)
+    assert res[0].ok == 1 and res[1].ok == -1
+    # the stock voxel size is nowhere near the limit
+    fo.voxel_filter_size = w["opts"].voxel_filter_size
+    res = ctx.frontend_match_batch(fo, [near, full], w["origin"], w["prev"][[0, 0]], w["cur"][[0, 0]], w["submap_pose"], hi, lo)
+    assert res[0].ok == 1 and res[1].ok == 1
+    ctx.close()
