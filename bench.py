@@ -81,6 +81,37 @@ def physical_cores():
         return None
 
 
+def usable_cpus():
+    """(threads to use, description): os.cpu_count() capped by the affinity mask and by the container's CFS quota. The pool's GPU
+    boxes show 128 logical CPUs but run under `cpu.max = 1600000 100000` (16 CPUs' worth of time): 128 busy threads are then
+    throttled to ~700 scans/s, 16 threads run at their full 1 100 scans/s (tools/cpu_scaling.py, profiles/r3_cpu_scaling.json) —
+    the reference arm must use what the box really grants to be the best the host can do."""
+    n = os.cpu_count() or 1
+    note = f"os.cpu_count() = {n}"
+    try:
+        aff = len(os.sched_getaffinity(0))
+        if aff < n:
+            n, note = aff, note + f", affinity {aff}"
+    except (AttributeError, OSError):
+        pass
+    quota = period = None
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]       # cgroup v2
+        if q != "max":
+            quota, period = float(q), float(p)
+    except (OSError, ValueError):
+        try:                                                              # cgroup v1
+            quota = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        except (OSError, ValueError):
+            pass
+    if quota and period and quota > 0:
+        cap = max(1, int(-(-quota // period)))
+        note += f", cgroup quota {quota / period:g} CPUs"
+        n = min(n, cap)
+    return n, note
+
+
 def build_workload(args, rank):
     """Submap cells (built with the oracle's range-data inserter, like the reference builds a submap: hit 0.55 /
     miss 0.49 / 2 free voxels, high-res max range 20 m) + the batch of DISTINCT scans to register, each with the IMU
@@ -196,7 +227,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     w = build_workload(args, 0)
-    threads = os.cpu_count() or 1
+    threads, cpu_note = usable_cpus()
     sample = max(args.batch, 8 * threads)   # >= 8 scans per pooled thread, handed out from a work queue
     sel = [i % args.batch for i in range(sample)]
     cpu_chain(w, sel[:threads], threads)    # spawn the pool
@@ -212,6 +243,7 @@ def run_reference(args, rank, world):
             "dtype": "f64", "data": "synthetic", "impl": "reference",
             "config": workload_config(args, args.batch),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "physical_cores": physical_cores(), "kind": "port",
+                             "cpus": cpu_note,
                              "sample": f"{sample} scans per step ({args.batch} distinct, cycled), median of {args.steps} steps, "
                                        f"persistent pool of {threads} threads fed from a work queue"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -608,8 +640,8 @@ def main():
         cpu = None
         parity = None
         if world == 1:
-            threads = os.cpu_count() or 1
-            sample = args.cpu_sample or 8 * threads
+            threads, cpu_note = usable_cpus()
+            sample = args.cpu_sample or max(B, 8 * threads)
             sel = [i % B for i in range(sample)]
             cpu_chain(w, sel[:threads], threads)   # spawn the pool
             runs = [cpu_chain(w, sel, threads) for _ in range(3)]
@@ -617,6 +649,7 @@ def main():
             one_n = 16
             secs1 = cpu_chain(w, list(range(one_n)), 1)[0]
             cpu = {"value": sample / secs, "unit": UNIT, "cores": threads, "physical_cores": physical_cores(), "kind": "port",
+                   "cpus": cpu_note,
                    "sample": f"{sample} scans ({B} distinct, cycled; {secs:.2f} s, median of 3), persistent pool of {threads} threads "
                              f"fed from a work queue",
                    "all_cores": sample / secs, "single_thread": one_n / secs1,
