@@ -261,9 +261,10 @@ def workload_config(args, batch):
             "row_layout": {3: "x y z (12 B) + per-point times as runs", 4: "x y z t (16 B)", 8: "RangeMeasurement (32 B)"}[args.row_floats],
             "l2_policy": f"inputs ({batch} x {130605 * 4 * args.row_floats / 1e6:.1f} MB) exceed the 126 MB L2; no explicit flush",
             "parallelism": f"scans sharded over {args.gpus} gpu(s); loop-closure pairs sharded by submap owner, one ncclAllGather per step",
-            "exchange_thread": "each step's exchange (searches + all-gather + table on the host) is issued from a second host thread "
-                               "with its own context, like the reference's constraint-builder pool; every one of the K exchanges "
-                               "completes inside the timed region"}
+            "exchange_thread": f"each step's exchange (searches + all-gather + table on the host) is issued from one of "
+                               f"{args.exchange_threads} background host threads (own context + NCCL communicator each, step k -> "
+                               "thread k mod T), like the reference's constraint-builder pool; every one of the K exchanges completes "
+                               "inside the timed region"}
 
 
 _T0 = time.perf_counter()
@@ -284,6 +285,9 @@ def main():
     ap.add_argument("--beams", type=int, default=64)
     ap.add_argument("--map-scans", type=int, default=40)
     ap.add_argument("--pairs", type=int, default=8, help="loop-closure (node, submap) searches per rank and step")
+    ap.add_argument("--exchange-threads", type=int, default=2,
+                    help="host threads (each with its own context and NCCL communicator) that run the exchange steps; step k "
+                         "goes to thread k mod T on every rank, so the collectives pair up")
     ap.add_argument("--cpu-sample", type=int, default=0, help="scans in the cpu_baseline sample (0 = 8 x threads)")
     ap.add_argument("--row-floats", type=int, default=3, choices=[3, 4, 8],
                     help="3: x y z rows + the per-point times as runs (12 B/point); 4: TimedPointCloud rows x y z t (what AddRangeData "
@@ -313,7 +317,9 @@ def main():
 
     w = build_workload(args, rank)
     B = args.batch
-    ctx, ctx2, ctx3 = dliom.Context(local_rank), dliom.Context(local_rank), dliom.Context(local_rank)
+    ctx, ctx2 = dliom.Context(local_rank), dliom.Context(local_rank)
+    xctxs = [dliom.Context(local_rank) for _ in range(max(1, args.exchange_threads))]   # one context per exchange thread
+    ctx3 = xctxs[0]
     hi, lo = ctx.grid(0.1), ctx.grid(0.45)
     hi.set_cells(*w["hi"].export())
     lo.set_cells(*w["lo"].export())
@@ -343,21 +349,26 @@ def main():
     dev_lanes = [(c, torch.zeros(res_bytes, dtype=torch.uint8, device=device), torch.zeros((B, 16), dtype=torch.float64, device=device), im)
                  for c, im in zip((ctx, ctx2), imus)]
 
-    # ---- the exchange step: NCCL communicator owned by the C-ABI library, created from an id that torch.distributed carries
-    idt = torch.zeros(128, dtype=torch.uint8, device=device)
-    if rank == 0:
-        idt.copy_(torch.tensor(list(dliom.comm_unique_id()), dtype=torch.uint8))
-    if dist is not None:
-        dist.broadcast(idt, 0)
-    comm = dliom.Comm(ctx3, bytes(idt.cpu().numpy().tolist()), rank, world)
+    # ---- the exchange step: NCCL communicators owned by the C-ABI library, created from ids that torch.distributed carries
+    comms = []
+    for xc in xctxs:
+        idt = torch.zeros(128, dtype=torch.uint8, device=device)
+        if rank == 0:
+            idt.copy_(torch.tensor(list(dliom.comm_unique_id()), dtype=torch.uint8))
+        if dist is not None:
+            dist.broadcast(idt, 0)
+        comms.append(dliom.Comm(xc, bytes(idt.cpu().numpy().tolist()), rank, world))
+        xc.set_blocking_sync(True)   # exchange threads sleep in their waits: the box grants 16 CPUs for up to 8 ranks x 4 threads
+    comm = comms[0]
     lc = loop_closure_pairs(w, args, rank) if args.pairs > 0 else None
     copt = dliom.ConstraintOptions.defaults(min_score=0.3, min_low_resolution_score=0.3, xy_window=3.0, z_window=0.5)
     exchange = {"ms": [], "found": 0, "bytes": 0, "rows": 0}
 
-    plan = None
+    plans = []
     if args.pairs > 0:
-        plan = ctx3.constraint_exchange_plan(comm, copt, args.pairs, lc["submaps"], lc["nodes"], lc["guesses"], lc["hi"], lc["lo"],
-                                             [hi] * args.pairs, [lo] * args.pairs)
+        plans = [xc.constraint_exchange_plan(cm, copt, args.pairs, lc["submaps"], lc["nodes"], lc["guesses"], lc["hi"], lc["lo"],
+                                             [hi] * args.pairs, [lo] * args.pairs) for xc, cm in zip(xctxs, comms)]
+    exchange_lock = threading.Lock()
 
     class ExchangeWorker(threading.Thread):
         """The exchange steps run on their own host thread and context, like the reference's constraint builder, whose searches
@@ -365,8 +376,9 @@ def main():
         overlaps the front end of step k+1 instead of blocking the thread that launches it. submit() queues one exchange,
         drain() returns when every queued exchange has completed (each one ends with a device sync and the table on the host)."""
 
-        def __init__(self):
+        def __init__(self, plan):
             super().__init__(daemon=True)
+            self.plan = plan
             self.cv = threading.Condition()
             self.pending = 0
             self.error = None
@@ -381,11 +393,12 @@ def main():
                     if self.stop:
                         return
                 try:
-                    table, info = plan()
-                    exchange["ms"].append(info.collective_ms)
-                    exchange["found"] = info.found_total
-                    exchange["bytes"] = int(info.bytes_received)
-                    exchange["rows"] = len(table)
+                    table, info = self.plan()
+                    with exchange_lock:
+                        exchange["ms"].append(info.collective_ms)
+                        exchange["found"] = info.found_total
+                        exchange["bytes"] = int(info.bytes_received)
+                        exchange["rows"] = len(table)
                 except Exception as e:   # surfaced by drain()
                     self.error = e
                 with self.cv:
@@ -409,15 +422,17 @@ def main():
                 self.stop = True
                 self.cv.notify_all()
 
-    worker = ExchangeWorker() if plan is not None else None
+    workers = [ExchangeWorker(p) for p in plans]
+    submitted = [0]
 
     def step_exchange():
-        if worker is not None:     # --pairs 0: front end only (experiments)
-            worker.submit()
+        if workers:                # --pairs 0: front end only (experiments)
+            workers[submitted[0] % len(workers)].submit()   # same assignment on every rank: the all-gathers pair up
+            submitted[0] += 1
 
     def drain_exchange():
-        if worker is not None:
-            worker.drain()
+        for wk in workers:
+            wk.drain()
 
     def step_dev(i, options=None, lanes=None):
         """One pass of the hot path over the HBM-resident batch. Successive steps alternate between two contexts (own
@@ -447,7 +462,7 @@ def main():
 
     def barrier():
         torch.cuda.synchronize()
-        for c in (ctx, ctx2, ctx3):
+        for c in [ctx, ctx2] + xctxs:
             c.synchronize()
         if dist is not None:
             dist.barrier()
@@ -457,7 +472,7 @@ def main():
         """CUDA events on the launching streams: the first context's stream opens the region; the closing event is recorded on
         the same stream after it has been made to wait for the other contexts' streams (event waits, no host sync)."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        others = [torch.cuda.ExternalStream(c.stream, device=device) for c in (ctx2, ctx3)]
+        others = [torch.cuda.ExternalStream(c.stream, device=device) for c in [ctx2] + xctxs]
         barrier()
         gate = torch.cuda.Event()
         gate.record(stream)
@@ -498,9 +513,9 @@ def main():
     ctx.set_profiling(True)
     ctx.read_profile()
     exchange["ms"].clear()
-    launches0 = sum(c.launches for c in (ctx, ctx2, ctx3))
+    launches0 = sum(c.launches for c in [ctx, ctx2] + xctxs)
     ms_total = timed_device_loop(args.steps)
-    launches = sum(c.launches for c in (ctx, ctx2, ctx3)) - launches0
+    launches = sum(c.launches for c in [ctx, ctx2] + xctxs) - launches0
     profile = ctx.read_profile()
     ctx.set_profiling(False)
     collective_ms = float(np.median(exchange["ms"])) if exchange["ms"] else None
@@ -694,10 +709,11 @@ def main():
         print(json.dumps(line))
     note("line printed")
     sampler.stop_flag = True
-    if worker is not None:
-        worker.close()
-        worker.join(timeout=5)
-    comm.close()
+    for wk in workers:
+        wk.close()
+        wk.join(timeout=5)
+    for cm in comms:
+        cm.close()
     if dist is not None:
         dist.destroy_process_group()
     note("done")

@@ -118,7 +118,7 @@ int d2h(dl_context* ctx, T* dst, const T* src, size_t count) {
   return DL_OK;
 }
 int sync(dl_context* ctx) {
-  DL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  DL_CUDA(ctx, ctx->wait_stream());
   return DL_OK;
 }
 }  // namespace
@@ -172,6 +172,7 @@ void dl_context_destroy(dl_context* ctx) {
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->tail_stream) cudaStreamDestroy(ctx->tail_stream);
   if (ctx->batch_done) cudaEventDestroy(ctx->batch_done);
+  if (ctx->sync_event) cudaEventDestroy(ctx->sync_event);
   if (ctx->d_fcsm_lut) cudaFree(ctx->d_fcsm_lut);
   if (ctx->h_adaptive_stats) cudaFreeHost(ctx->h_adaptive_stats);
   if (ctx->d_adaptive_stats) cudaFree(ctx->d_adaptive_stats);
@@ -197,6 +198,11 @@ uint64_t dl_context_stream(const dl_context* ctx) { return ctx ? (uint64_t)(uint
 int dl_context_synchronize(dl_context* ctx) {
   if (!ctx) return DL_ERR_ARG;
   return sync(ctx);
+}
+int dl_context_set_blocking_sync(dl_context* ctx, int enabled) {
+  if (!ctx) return DL_ERR_ARG;
+  ctx->blocking_sync = enabled != 0;
+  return DL_OK;
 }
 int dl_context_set_profiling(dl_context* ctx, int enabled) {
   if (!ctx) return DL_ERR_ARG;

@@ -111,7 +111,7 @@ int comm_all_gather(dl_comm* c, const void* send_dev, void* recv_dev, size_t byt
   DL_NCCL(ctx, a->AllGather(send_dev, recv_dev, bytes, ncclChar, c->comm, ctx->stream));
   if (ms) {
     DL_CUDA(ctx, cudaEventRecord(c->e1, ctx->stream));
-    DL_CUDA(ctx, cudaEventSynchronize(c->e1));
+    DL_CUDA(ctx, ctx->blocking_sync ? ctx->wait_stream() : cudaEventSynchronize(c->e1));
     DL_CUDA(ctx, cudaEventElapsedTime(ms, c->e0, c->e1));
   }
   return DL_OK;

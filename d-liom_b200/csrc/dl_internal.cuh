@@ -92,6 +92,19 @@ struct dl_context {
   }
   int reserve_device(size_t bytes);
   int reserve_pinned(size_t bytes);
+  // Host wait for everything on `stream`. blocking_sync: the thread sleeps on a cudaEventBlockingSync event instead of
+  // spinning in cudaStreamSynchronize — for background threads (loop closure, pose graph) on hosts with fewer CPUs than threads.
+  bool blocking_sync = false;
+  cudaEvent_t sync_event = nullptr;
+  cudaError_t wait_stream() {
+    if (!blocking_sync) return cudaStreamSynchronize(stream);
+    if (!sync_event) {
+      const cudaError_t e = cudaEventCreateWithFlags(&sync_event, cudaEventBlockingSync | cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+    }
+    const cudaError_t e = cudaEventRecord(sync_event, stream);
+    return e != cudaSuccess ? e : cudaEventSynchronize(sync_event);
+  }
 };
 
 struct dl_grid {

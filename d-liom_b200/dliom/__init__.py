@@ -21,7 +21,7 @@ u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
 DL_MAX_PAIRS = 4
 EXPORTS = [
     "dl_context_create", "dl_context_destroy", "dl_last_error", "dl_status_string", "dl_context_kernel_launches",
-    "dl_context_stream", "dl_context_synchronize", "dl_context_set_profiling", "dl_context_read_profile", "dl_grid_create", "dl_grid_destroy", "dl_grid_set_cells",
+    "dl_context_stream", "dl_context_synchronize", "dl_context_set_profiling", "dl_context_set_blocking_sync", "dl_context_read_profile", "dl_grid_create", "dl_grid_destroy", "dl_grid_set_cells",
     "dl_grid_sync", "dl_grid_resolution", "dl_grid_num_bricks", "dl_grid_lookup", "dl_grid_interpolate",
     "dl_grid_insert_range_data", "dl_submap_insert_range_data", "dl_grid_export_cells",
     "dl_voxel_filter", "dl_voxel_indices", "dl_adaptive_voxel_filter", "dl_rtcsm_match", "dl_fcsm_match_3dof", "dl_fcsm_match", "dl_constraint_search_batch", "dl_ceres_match",
@@ -323,6 +323,7 @@ def lib():
     L.dl_context_stream.restype = C.c_uint64
     L.dl_context_synchronize.argtypes = [vp]
     L.dl_context_set_profiling.argtypes = [vp, C.c_int]
+    L.dl_context_set_blocking_sync.argtypes = [vp, C.c_int]
     L.dl_context_read_profile.argtypes = [vp, ip(StageTime), C.c_int32, ip(C.c_int32)]
     L.dl_grid_create.argtypes = [vp, C.c_float, ip(vp)]
     L.dl_grid_destroy.argtypes = [vp]
@@ -495,6 +496,10 @@ class Context:
 
     def set_profiling(self, on):
         self.check(self.L.dl_context_set_profiling(self.h, int(on)))
+
+    def set_blocking_sync(self, on=True):
+        """Host waits of this context sleep instead of spinning (background threads on hosts with few CPUs)."""
+        self.check(self.L.dl_context_set_blocking_sync(self.h, int(on)))
 
     def read_profile(self):
         """{stage: (total ms, calls)} since the last read (device time between CUDA events on the context stream)."""

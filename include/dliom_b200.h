@@ -53,6 +53,9 @@ typedef struct dl_stage_time {
   int64_t calls;
 } dl_stage_time;
 int dl_context_set_profiling(dl_context* ctx, int enabled);
+/* Host waits of this context sleep (cudaEventBlockingSync) instead of spinning: for the background threads that run loop
+ * closure / the pose graph (the reference's thread pool at nice(10), C/common/thread_pool.cc) on hosts with few CPUs. */
+int dl_context_set_blocking_sync(dl_context* ctx, int enabled);
 int dl_context_read_profile(dl_context* ctx, dl_stage_time* out, int32_t capacity, int32_t* num_stages);
 /* The context's cudaStream_t as an integer, and a blocking wait on it. */
 uint64_t dl_context_stream(const dl_context* ctx);
