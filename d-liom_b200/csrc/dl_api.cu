@@ -1688,7 +1688,12 @@ FrontendArgs make_frontend_args(const dl_frontend_options& o, const FrontendBuff
                                 int64_t in_cap, int row_floats) {
   FrontendArgs fa{};
   fa.ranges = d_ranges; fa.in_cap = in_cap; fa.row_floats = row_floats; fa.counts = f.counts0; fa.scans = f.scans;
-  fa.origins = f.origins; fa.cap = f.cap; fa.tiles = f.tiles; fa.tcap1 = f.tcap; fa.tcap2 = f.tcap2;
+  fa.origins = f.origins; fa.cap = f.cap; fa.tiles = f.tiles; fa.tcap2 = f.tcap2;
+  // First-filter table of the fused path: 1.25 slots per point (load <= 0.8 even if every point had its own voxel; ~0.3 on real
+  // sweeps) instead of the next power of two above 2 * cap — the table is memset, hammered with atomics and streamed once per
+  // scan, so its size is DRAM and L2 traffic. (The allocation keeps the power-of-two size the stage-wise kernels index with.)
+  fa.tcap1 = std::min<int64_t>(f.tcap, ((f.cap + f.cap / 4 + 63) / 64) * 64);
+  if (const char* env = std::getenv("DLIOM_TABLE1_POW2")) fa.tcap1 = std::atoi(env) ? f.tcap : fa.tcap1;
   fa.first_resolution = 0.5f * o.voxel_filter_size;  // LTB:394
   fa.second_resolution = o.voxel_filter_size;        // LTB:479-484
   fa.min_range = o.min_range; fa.max_range = o.max_range; fa.scan_period = o.scan_period;

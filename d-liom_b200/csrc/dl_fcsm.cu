@@ -311,9 +311,13 @@ __device__ bool low_resolution_gate(const FcsmPair& pr, const Vec3f& t, float* p
   return pass_s != 0;
 }
 
-// One CTA (64 threads) per (block, pair): thread = one (y, z) offset of the block with its 8 x offsets. round 0 opens the
-// blocks within 1/8 of the pair's largest bound; round 1 every other block whose bound still reaches the best leaf so far.
-__global__ void __launch_bounds__(64) fcsm_block_kernel(const FcsmPair* __restrict__ pairs, const int* __restrict__ bounds, int stride,
+// One CTA per (block, pair): 64 leaf threads (one (y, z) offset of the block with its 8 x offsets each) x kPointGroups groups that
+// share the node's points (group g takes points g, g + kPointGroups, ...; the leaf sums are integers, so adding the groups' partial
+// sums is exact and order-free). A search is a handful of open blocks, i.e. its time is ONE CTA's walk over the cloud — the
+// groups cut that walk's length, which is what the exchange step waits for. round 0 opens the blocks within 1/8 of the pair's
+// largest bound; round 1 every other block whose bound still reaches the best leaf so far.
+constexpr int kPointGroups = 4;
+__global__ void __launch_bounds__(64 * kPointGroups) fcsm_block_kernel(const FcsmPair* __restrict__ pairs, const int* __restrict__ bounds, int stride,
                                                         const int* __restrict__ max_bound, unsigned long long* __restrict__ best,
                                                         const uint8_t* __restrict__ lut, int round) {
   __shared__ int tile[kTile * 3];
@@ -341,19 +345,20 @@ __global__ void __launch_bounds__(64) fcsm_block_kernel(const FcsmPair* __restri
   __syncthreads();
   if (skip) return;
   const int side = 2 * pr.wxy + 1;
+  const int leaf = threadIdx.x & 63, group = threadIdx.x >> 6;
   const int ox0 = -pr.wxy + kSub * (b % bx);
-  const int oy = -pr.wxy + kSub * ((b / bx) % by) + (threadIdx.x & 7);
-  const int oz = -pr.wz + kSub * (b / (bx * by)) + (threadIdx.x >> 3);
+  const int oy = -pr.wxy + kSub * ((b / bx) % by) + (leaf & 7);
+  const int oz = -pr.wz + kSub * (b / (bx * by)) + (leaf >> 3);
   const bool active = oy <= pr.wxy && oz <= pr.wz;
   const int half = (64 << pr.hi.bits) >> 1;
   int sum[kRun] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int base = 0; base < pr.n_hi; base += kTile) {
     const int count = min(kTile, pr.n_hi - base);
     __syncthreads();
-    for (int j = threadIdx.x; j < count * 3; j += 64) tile[j] = pr.cells[base * 3 + j];
+    for (int j = threadIdx.x; j < count * 3; j += 64 * kPointGroups) tile[j] = pr.cells[base * 3 + j];
     __syncthreads();
     if (active)
-      for (int j = 0; j < count; ++j) {
+      for (int j = group; j < count; j += kPointGroups) {
         const int sx = tile[3 * j] + ox0 + half, sy = tile[3 * j + 1] + oy + half, sz = tile[3 * j + 2] + oz + half;
         const int phase = sx & 7;  // block-uniform
         const uint4* p0 = brick_row(pr.hi, sx - phase, sy, sz);
@@ -373,6 +378,18 @@ __global__ void __launch_bounds__(64) fcsm_block_kernel(const FcsmPair* __restri
         }
       }
   }
+  // fold the groups' partial sums into group 0 (integers: exact), then only the 64 leaf threads go on
+  __shared__ int partial[kPointGroups - 1][64][kRun];
+  if (group > 0) {
+#pragma unroll
+    for (int k = 0; k < kRun; ++k) partial[group - 1][leaf][k] = sum[k];
+  }
+  __syncthreads();  // also: everyone is done with `tile`
+  if (group > 0) return;  // whole warps leave; the barriers below count the remaining threads only
+#pragma unroll
+  for (int g = 0; g < kPointGroups - 1; ++g)
+#pragma unroll
+    for (int k = 0; k < kRun; ++k) sum[k] += partial[g][leaf][k];
   // Candidate leaves of this block, best first: (score bits << 32 | ~index), the same key `best` is maximised with. Only the
   // best candidate that PASSES the low-resolution gate can win, so the CTA walks its candidates in descending key order,
   // evaluates the gate cooperatively (low_resolution_gate) and stops at the first pass — or as soon as the remaining keys
@@ -380,7 +397,6 @@ __global__ void __launch_bounds__(64) fcsm_block_kernel(const FcsmPair* __restri
   // (~150 us per leaf of three-level walks): the dominant cost of the whole search.
   __shared__ unsigned long long cand[64 * kRun];
   __shared__ unsigned long long pick_s;
-  __syncthreads();  // everyone is done with `tile`
 #pragma unroll
   for (int k = 0; k < kRun; ++k) {
     const float sc = sum_to_score(sum[k], pr.n_hi);
@@ -492,7 +508,7 @@ int launch_fcsm_pruned(dl_context* ctx, const FcsmPair* pairs_dev, int count, in
   fcsm_bounds_kernel<<<dim3((max_blocks + 3) / 4, count), 128, 0, ctx->stream>>>(pairs_dev, bounds_dev, max_blocks, max_bound_dev);
   DL_LAUNCH_CHECK(ctx, "fcsm_bounds_kernel");
   for (int round = 0; round < 2; ++round) {
-    fcsm_block_kernel<<<dim3(max_blocks, count), 64, 0, ctx->stream>>>(pairs_dev, bounds_dev, max_blocks, max_bound_dev, best_dev,
+    fcsm_block_kernel<<<dim3(max_blocks, count), 64 * kPointGroups, 0, ctx->stream>>>(pairs_dev, bounds_dev, max_blocks, max_bound_dev, best_dev,
                                                                        ctx->d_fcsm_lut, round);
     DL_LAUNCH_CHECK(ctx, "fcsm_block_kernel");
   }

@@ -45,6 +45,9 @@ __device__ __forceinline__ uint32_t hash_cell(const Int3& c) {
   return h;
 }
 
+// Slot of a 32-bit hash in a table of `tcap` slots, tcap arbitrary (multiply-shift range reduction: no power-of-two padding).
+__device__ __forceinline__ uint32_t table_slot(uint32_t hash, uint32_t tcap) { return __umulhi(hash, tcap); }
+
 __device__ __forceinline__ Vec3f load_xyz(const float* __restrict__ rows, int row_floats, uint32_t i) {
   if (row_floats == 3) {
     const float* p = rows + (size_t)i * 3;
@@ -87,7 +90,7 @@ __global__ void __launch_bounds__(kBlock, kFirstBatch == 1 ? 8 : (kFirstBatch ==
   const int n = a.counts[b];
   const float* rows = a.ranges + (size_t)b * a.in_cap * a.row_floats;
   uint32_t* tab = a.table1 + (size_t)b * a.tcap1;
-  const uint32_t mask = (uint32_t)a.tcap1 - 1;
+  const uint32_t tcap = (uint32_t)a.tcap1;  // any size (not a power of two): slot = hash * tcap >> 32
   const CellDivider res = make_divider(a.first_resolution);
   const int stride = gridDim.x * kBlock;
   for (int i0 = blockIdx.x * kBlock + threadIdx.x; i0 < n; i0 += kFirstBatch * stride) {
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(kBlock, kFirstBatch == 1 ? 8 : (kFirstBatch ==
     for (int u = 0; u < kFirstBatch; ++u) {
       const int i = i0 + u * stride;
       c[u] = cell_index(i < n ? load_xyz(rows, a.row_floats, i) : Vec3f{0.f, 0.f, 0.f}, res);
-      h[u] = hash_cell(c[u]) & mask;
+      h[u] = table_slot(hash_cell(c[u]), tcap);
     }
 #pragma unroll
     for (int u = 0; u < kFirstBatch; ++u) {
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(kBlock, kFirstBatch == 1 ? 8 : (kFirstBatch ==
           if ((uint32_t)i < p) atomicMin(tab + hh, (uint32_t)i);  // the owner only ever decreases
           break;
         }
-        hh = (hh + 1) & mask;
+        hh = hh + 1 == tcap ? 0u : hh + 1;
         p = atomicCAS(tab + hh, kEmpty32, (uint32_t)i);
       }
     }

@@ -64,7 +64,11 @@ int dl_context_synchronize(dl_context* ctx);
 /* ---- probability grid: device mirror of mapping::HybridGrid (C/mapping/3d/hybrid_grid.h:411-547) ---------
  * Cells are given as the HybridGrid proto layout (parallel x/y/z/value arrays, hybrid_grid.h:530-542) and must
  * hold post-FinishUpdate values (< 32768). dl_grid_set_cells may be called again after every host
- * InsertRangeData with just the touched cells; only dirty 8^3 bricks are re-uploaded by dl_grid_sync. */
+ * InsertRangeData with just the touched cells; only dirty 8^3 bricks are re-uploaded by dl_grid_sync.
+ * Sharing: any number of contexts (host threads) may READ a grid concurrently (matchers, loop-closure searches; the search index
+ * of a grid is built once under a lock) — as the reference shares a finished Submap3D's HybridGrid between its thread-pool
+ * workers. A grid that is being modified (dl_grid_set_cells / dl_grid_sync / dl_*_insert_range_data) must not be in use by
+ * another context at the same time: the active submaps belong to the one front-end thread (Node::mutex_ in the reference). */
 int dl_grid_create(dl_context* ctx, float resolution, dl_grid** out);
 void dl_grid_destroy(dl_grid* grid);
 int dl_grid_set_cells(dl_grid* grid, int64_t n, const int32_t* x, const int32_t* y, const int32_t* z,
