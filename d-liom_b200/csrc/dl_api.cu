@@ -1689,11 +1689,13 @@ FrontendArgs make_frontend_args(const dl_frontend_options& o, const FrontendBuff
   FrontendArgs fa{};
   fa.ranges = d_ranges; fa.in_cap = in_cap; fa.row_floats = row_floats; fa.counts = f.counts0; fa.scans = f.scans;
   fa.origins = f.origins; fa.cap = f.cap; fa.tiles = f.tiles; fa.tcap2 = f.tcap2;
-  // First-filter table of the fused path: 1.25 slots per point (load <= 0.8 even if every point had its own voxel; ~0.3 on real
-  // sweeps) instead of the next power of two above 2 * cap — the table is memset, hammered with atomics and streamed once per
-  // scan, so its size is DRAM and L2 traffic. (The allocation keeps the power-of-two size the stage-wise kernels index with.)
-  fa.tcap1 = std::min<int64_t>(f.tcap, ((f.cap + f.cap / 4 + 63) / 64) * 64);
-  if (const char* env = std::getenv("DLIOM_TABLE1_POW2")) fa.tcap1 = std::atoi(env) ? f.tcap : fa.tcap1;
+  // First-filter table of the fused path: the next power of two above 2 * cap (load ~0.18 on real sweeps). A compact table of
+  // 1.25 slots per point (the kernels take any size: slot = hash * tcap >> 32) saves a third of the memset and of the ingest
+  // kernel's table stream but costs the first filter more in collisions than it saves: 117.5 k vs 119.8 k scans/s
+  // (profiles/r3j_ab.log) — kept as DLIOM_TABLE1_COMPACT=1 for experiments.
+  fa.tcap1 = f.tcap;
+  if (const char* env = std::getenv("DLIOM_TABLE1_COMPACT"))
+    if (std::atoi(env)) fa.tcap1 = std::min<int64_t>(f.tcap, ((f.cap + f.cap / 4 + 63) / 64) * 64);
   fa.first_resolution = 0.5f * o.voxel_filter_size;  // LTB:394
   fa.second_resolution = o.voxel_filter_size;        // LTB:479-484
   fa.min_range = o.min_range; fa.max_range = o.max_range; fa.scan_period = o.scan_period;
@@ -1892,12 +1894,18 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
     DL_TRY(h2d(ctx, d_rf, o.time_run_first_row, runs));
     DL_TRY(h2d(ctx, d_rv, o.time_run_value, runs));
     fa.run_offsets = d_ro; fa.run_first_row = d_rf; fa.run_value = d_rv;
-    if (runs > (size_t)8 * num_scans) {  // many runs per scan: expand once instead of searching per survivor
+    if (runs > (size_t)8 * num_scans) {  // many runs per scan: one deskew pose per run (fe_run_poses) instead of one per survivor
       int max_runs = 0;
       for (int b = 0; b < num_scans; ++b) max_runs = std::max(max_runs, (int)(o.time_run_offsets[b + 1] - o.time_run_offsets[b]));
-      int32_t* d_run_of_row = a.take<int32_t>((size_t)num_scans * in_cap);
-      DL_TRY(launch_fe_expand_runs(ctx, fa, num_scans, max_runs, d_run_of_row));  // needs counts + runs only, both uploaded above
-      fa.run_of_row = d_run_of_row;
+      // The run of a row is found by a binary search of the scan's ~2 k run starts (L1-resident) per survivor. Expanding the run
+      // index of EVERY row once per batch (4 B per row, one more kernel and 17 MB of writes per step, then one random sector per
+      // survivor) makes the ingest kernel itself 5 % faster but the step 1.6 % slower (profiles/r3k_sweep.log): DLIOM_EXPAND_RUNS=1.
+      const char* expand = std::getenv("DLIOM_EXPAND_RUNS");
+      if (expand && std::atoi(expand) != 0) {
+        int32_t* d_run_of_row = a.take<int32_t>((size_t)num_scans * in_cap);
+        DL_TRY(launch_fe_expand_runs(ctx, fa, num_scans, max_runs, d_run_of_row));  // needs counts + runs only, both uploaded above
+        fa.run_of_row = d_run_of_row;
+      }
       fa.run_pose = a.take<float>(runs * 8);  // filled per sub-batch by fe_run_poses once the scans' deskew constants exist
       fa.max_runs = max_runs;
     }

@@ -57,16 +57,21 @@ __device__ __forceinline__ Vec3f load_xyz(const float* __restrict__ rows, int ro
   return {v.x, v.y, v.z};
 }
 
-// Time of row i of scan b: the row's fourth float, or (12-byte rows) the value of the run that contains the row.
-__device__ __forceinline__ float point_time(const FrontendArgs& a, int b, const float* __restrict__ rows, int rf, int i) {
-  if (rf != 3) return rows[(size_t)i * rf + 3];
-  if (a.run_of_row) return a.run_value[a.run_of_row[(size_t)b * a.in_cap + i]];
+// 12-byte rows: index (into the batch's run arrays) of the time run that contains row i of scan b.
+__device__ __forceinline__ int run_index(const FrontendArgs& a, int b, int i) {
+  if (a.run_of_row) return a.run_of_row[(size_t)b * a.in_cap + i];
   int lo = a.run_offsets[b], hi = a.run_offsets[b + 1] - 1;  // last run whose first row is <= i
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
-    if (a.run_first_row[mid] <= i) lo = mid; else hi = mid - 1;
+    if (__ldg(a.run_first_row + mid) <= i) lo = mid; else hi = mid - 1;
   }
-  return a.run_value[lo];
+  return lo;
+}
+
+// Time of row i of scan b: the row's fourth float, or (12-byte rows) the value of the run that contains the row.
+__device__ __forceinline__ float point_time(const FrontendArgs& a, int b, const float* __restrict__ rows, int rf, int i) {
+  if (rf != 3) return rows[(size_t)i * rf + 3];
+  return a.run_value[run_index(a, b, i)];
 }
 
 // 12-byte rows: the run index of every row, written once per batch (one warp per run, contiguous stores), so that the
@@ -194,7 +199,7 @@ __device__ __forceinline__ int ingest_survivor(const FrontendArgs& a, int b, con
   if (kRunPose) {  // 12-byte rows, per-run pose table
     const float* p = rows + (size_t)i * 3;
     h = make_float4(p[0], p[1], p[2], 0.f);
-    const float4* rp = (const float4*)(a.run_pose + (size_t)8 * a.run_of_row[(size_t)b * a.in_cap + i]);
+    const float4* rp = (const float4*)(a.run_pose + (size_t)8 * run_index(a, b, i));
     const float4 p0 = __ldg(rp), p1 = __ldg(rp + 1);
     pose = Rigidf{{p0.x, p0.y, p0.z}, {p0.w, p1.x, p1.y, p1.z}};
   } else if (rf == 3) {
@@ -509,7 +514,7 @@ int launch_fe_rest(dl_context* ctx, FrontendArgs a, int first_scan, int batch) {
   const int tiles = (int)std::min<int64_t>((a.cap + kBlock - 1) / kBlock, 128);
   int per_scan = 48;  // measured best of {8, 20, 32, 48, 64}: enough CTAs in flight to hide the random-access latency
   if (const char* env = std::getenv("DLIOM_INGEST_GRID")) per_scan = std::max(1, std::atoi(env));
-  if (a.run_pose && a.run_of_row && a.max_runs > 0) {
+  if (a.run_pose && a.max_runs > 0) {
     fe_run_poses<<<dim3((a.max_runs + 127) / 128, batch), 128, 0, ctx->stream>>>(a);
     DL_LAUNCH_CHECK(ctx, "fe_run_poses");
     fe_ingest_second_insert<true><<<dim3(per_scan, batch), kBlock, 0, ctx->stream>>>(a);
