@@ -198,19 +198,33 @@ __device__ __forceinline__ int block_compact_1024(int n, Pred pred, Emit emit) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int chunk = ((n + kAdaptiveBlock - 1) / kAdaptiveBlock) * 32;  // ids per warp, a multiple of 32
   const int begin = warp * chunk, end = min(n, begin + chunk);
+  // four 32-id rounds per iteration: the four loads behind `pred` are in flight together (a ballot per round would serialise them)
   int count = 0;
-  for (int base = begin; base < end; base += 32) {
-    const int i = base + lane;
-    count += __popc(__ballot_sync(0xffffffffu, i < end && pred(i)));
+  for (int base = begin; base < end; base += 128) {
+    bool f[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + 32 * u + lane;
+      f[u] = i < end && pred(i);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) count += __popc(__ballot_sync(0xffffffffu, f[u]));
   }
   int total;
   int pos = warp_bases_1024(count, &total);
-  for (int base = begin; base < end; base += 32) {
-    const int i = base + lane;
-    const bool flag = i < end && pred(i);
-    const unsigned ballot = __ballot_sync(0xffffffffu, flag);
-    if (flag) emit(pos + __popc(ballot & ((1u << lane) - 1)), i);
-    pos += __popc(ballot);
+  for (int base = begin; base < end; base += 128) {
+    bool f[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + 32 * u + lane;
+      f[u] = i < end && pred(i);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned ballot = __ballot_sync(0xffffffffu, f[u]);
+      if (f[u]) emit(pos + __popc(ballot & ((1u << lane) - 1)), base + 32 * u + lane);
+      pos += __popc(ballot);
+    }
   }
   __syncthreads();  // the emitted list is complete for every reader
   return total;
