@@ -124,6 +124,18 @@ def test_adaptive_voxel_filter_same_passes_and_survivors(ctx, orc, opts):
     assert np.array_equal(keep, want_keep)
 
 
+@pytest.mark.parametrize("opts", [(4.0, 200, 60.0), (0.5, 3000, 40.0), (2.0, 150, 15.0)])
+def test_adaptive_voxel_filter_large_cloud(ctx, orc, opts):
+    """40 000 points: more than the 22 528 the shared-memory fast mode holds when the range crop keeps most of them (generic
+    global-memory search, two-sweep crop and compaction), and the fast mode again when max_range = 15 m crops the cloud down."""
+    rng = np.random.RandomState(6)
+    pts = (rng.normal(0, 1, (40000, 3)) * np.array([15, 15, 2])).astype(np.float32)
+    want_keep, want_passes = orc.adaptive_voxel_filter(pts, *opts)
+    keep, passes = ctx.adaptive_voxel_filter(pts, *opts)
+    assert np.array_equal(passes, want_passes)
+    assert np.array_equal(keep, want_keep)
+
+
 def test_adaptive_voxel_filter_small_inputs(ctx, orc):
     for n in (0, 1, 100, 150, 151):
         pts = np.random.RandomState(n).normal(0, 5, (n, 3)).astype(np.float32)
