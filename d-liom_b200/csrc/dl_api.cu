@@ -1822,6 +1822,22 @@ size_t imu_run_device_bytes(int num_scans, const dl_frontend_imu_samples* raw) {
   return bytes + 1024;
 }
 
+// CTAs per least-squares problem. The pipeline's adaptive filters hand the matcher a few hundred points: one CTA. With the filters
+// opened up (min_num_points in the thousands: SURVEY 8d's full-cloud mode F, tens of thousands of points per solve) one 256-thread
+// CTA per problem is latency-bound and leaves half the SMs idle, so the problem is spread over a thread-block cluster — as many
+// CTAs as keep the launch within one wave of the SMs (2 for the bench's 74-problem sub-batches), at most the portable 8.
+// DLIOM_NLS_CLUSTER=n forces n (1 = never).
+int solve_cluster_size(dl_context* ctx, const dl_frontend_options& o, int problems) {
+  if (const char* env = std::getenv("DLIOM_NLS_CLUSTER")) return std::max(1, std::min(8, std::atoi(env)));
+  const float few = 4096.f;
+  if (o.high_resolution_adaptive_voxel_filter.min_num_points < few && o.low_resolution_adaptive_voxel_filter.min_num_points < few) return 1;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  int cs = 1;
+  while (cs < 8 && problems * cs * 2 <= sms) cs *= 2;
+  return cs;
+}
+
 // The batch is processed as `chunks` sub-batches that alternate between two streams, so that
 //   - with host scans (host_ranges != nullptr) the upload of sub-batch k+1 (copy stream) overlaps the kernels of k;
 //   - the latency-bound tail of sub-batch k (adaptive filter: 2 CTAs per scan, LM solve: 1 CTA per scan) overlaps the
@@ -2068,11 +2084,12 @@ int frontend_run(dl_context* ctx, const dl_frontend_options& o, int num_scans, f
       }
       {
         StageScope st(ctx, "nls_solve");
+        NlsOptions no = to_nls_options(o.ceres_scan_matcher, 2);
+        no.cluster = solve_cluster_size(ctx, o, nb);
         if (imu || raw)  // pose part of the initial state comes from problems[].initial_dev like the plain solve's
-          DL_TRY(launch_nls_fused(ctx, to_nls_options(o.ceres_scan_matcher, 2), f.problems + b0, d_terms + b0, d_init16 + 16 * b0, nb,
-                                  d_fused + b0));
+          DL_TRY(launch_nls_fused(ctx, no, f.problems + b0, d_terms + b0, d_init16 + 16 * b0, nb, d_fused + b0));
         else
-          DL_TRY(launch_nls(ctx, to_nls_options(o.ceres_scan_matcher, 2), f.problems + b0, nb, f.nls_out + b0));
+          DL_TRY(launch_nls(ctx, no, f.problems + b0, nb, f.nls_out + b0));
       }
       ResultArgs ra{};
       ra.batch = nb; ra.first_counts = f.n1 + b0; ra.return_counts = f.n2 + b0; ra.miss_counts = f.n3 + b0;

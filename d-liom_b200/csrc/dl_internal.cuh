@@ -249,6 +249,7 @@ struct NlsOptions {
   double occ_weight[DL_MAX_PAIRS];
   double trans_weight, rot_weight;
   int only_yaw, nonmono, max_iter;
+  int cluster;  // CTAs per problem (thread-block cluster; 0 / 1 = one CTA): > 1 for clouds of tens of thousands of points, see dl_nls.cu
 };
 struct NlsOutput {
   double pose[7];

@@ -24,6 +24,8 @@
 #include <cstdlib>
 #include <type_traits>
 
+#include <cooperative_groups.h>
+
 #include "dl_internal.cuh"
 
 namespace dl {
@@ -173,7 +175,10 @@ __device__ __forceinline__ double warp_reduce_scatter32(double (&v)[32], int lan
 // Point pass of one evaluation at sh.x: every participating thread accumulates cost*2, J^T r and J^T J (local
 // parameterisation) over its points; each warp leaves its partial sums in sh.red[warp][0..27].
 // Threads [0, point_threads) take part (whole warps); the caller synchronises the block afterwards.
-__device__ __forceinline__ void evaluate_points(const NlsOptions& opt, const NlsProblem& prob, Shared& sh, int point_threads) {
+// A problem may be spread over the CTAs of a thread-block cluster (full-cloud solves): CTA `rank` of `ranks` takes points
+// rank * point_threads + threadIdx.x, + ranks * point_threads, ... and leaves its partial sums in ITS sh.red.
+__device__ __forceinline__ void evaluate_points(const NlsOptions& opt, const NlsProblem& prob, Shared& sh, int point_threads,
+                                                int rank = 0, int ranks = 1) {
   if ((int)threadIdx.x >= point_threads) return;
   double x[7];
 #pragma unroll
@@ -191,7 +196,7 @@ __device__ __forceinline__ void evaluate_points(const NlsOptions& opt, const Nls
     const double s = sh.scaling[k];
     const float* __restrict__ cloud = prob.cloud[k];
     const GridView g = prob.grid[k];
-    for (int i = threadIdx.x; i < n; i += point_threads) {
+    for (int i = rank * point_threads + threadIdx.x; i < n; i += ranks * point_threads) {
       const Vec3d v{(double)cloud[3 * i], (double)cloud[3 * i + 1], (double)cloud[3 * i + 2]};
       const Vec3d w = add(rotate(q, v), Vec3d{x[0], x[1], x[2]});
       double m, gx, gy, gz;
@@ -233,10 +238,18 @@ __device__ __forceinline__ void evaluate_points(const NlsOptions& opt, const Nls
 // Warp 0, after the block barrier that follows evaluate_points: warps are summed in index order, then the two
 // 3-residual blocks (translation_delta_cost_functor_3d.h:38-44, rotation_delta_cost_functor_3d.h:42-53) are added.
 // Leaves the totals in sh.acc (visible to warp 0 after the trailing __syncwarp).
+// With a cluster, CTA 0 reads the other CTAs' partial sums through distributed shared memory, CTAs in rank order.
 __device__ __forceinline__ void finish_points(const NlsOptions& opt, Shared& sh, int point_warps, const double* target_q_inv,
-                                              const double* target_t, int lane) {
+                                              const double* target_t, int lane, int ranks = 1) {
   double v = 0.0;
   for (int w = 0; w < point_warps; ++w) v += sh.red[w][lane];
+  if (ranks > 1) {
+    cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+    for (int r = 1; r < ranks; ++r) {
+      const double* remote = cluster.map_shared_rank(&sh.red[0][0], r);
+      for (int w = 0; w < point_warps; ++w) v += remote[w * 32 + lane];
+    }
+  }
   const double* x = sh.x;
   if (opt.trans_weight > 0.) {
     const double s = opt.trans_weight;
@@ -732,7 +745,17 @@ __device__ __forceinline__ void solve_body(const NlsOptions& opt, const NlsProbl
   __shared__ double xfull[16];
   ImuShared* is = FUSED ? reinterpret_cast<ImuShared*>(&is_storage) : nullptr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-  // with the IMU term and more than one warp, the last warp is the IMU warp and the others take the points
+  // Thread-block cluster (opt.cluster CTAs per problem, launched with cudaLaunchAttributeClusterDimension): every CTA evaluates
+  // its share of the points, CTA 0 gathers the partial normal equations through distributed shared memory, runs the trust-region
+  // step and pushes the next evaluation point (or the stop flag) into every CTA's shared memory. cluster.sync() replaces the
+  // block barriers. One CTA per problem (ranks == 1) is the path of the ~400-point pipeline solves: unchanged arithmetic.
+  cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+  const int ranks = opt.cluster > 1 ? (int)cluster.num_blocks() : 1;
+  const int rank = ranks > 1 ? (int)cluster.block_rank() : 0;
+  auto barrier = [&]() {
+    if (ranks > 1) cluster.sync(); else __syncthreads();
+  };
+  // with the IMU term and more than one warp, the last warp is the IMU warp (in CTA 0) and the others take the points
   const int imu_warp = FUSED ? warps - 1 : -1;
   const int point_warps = (FUSED && warps > 1) ? warps - 1 : warps;
   {
@@ -749,34 +772,39 @@ __device__ __forceinline__ void solve_body(const NlsOptions& opt, const NlsProbl
       st.nl = FUSED ? 15 : (st.only_yaw ? 4 : 6);
       st.max_iter = opt.max_iter;
       st.max_nonmono = opt.nonmono ? Lm::max_consecutive_nonmonotonic : 0;
+      sh.stop = 0;
     }
     if (FUSED)
       for (int e = threadIdx.x; e < 225; e += blockDim.x) is->W[e] = imu->W[e];
   }
-  __syncthreads();
+  barrier();
   bool first = true;
   for (;;) {
-    evaluate_points(opt, prob, sh, point_warps * 32);
-    if (FUSED && warp == imu_warp) imu_normal_equations(*imu, xfull, *is, lane);
-    __syncthreads();  // partial sums (and the IMU term) are in shared memory
-    if (warp == 0) {
-      finish_points(opt, sh, point_warps, st.target_q_inv, st.target_t, lane);
+    evaluate_points(opt, prob, sh, point_warps * 32, rank, ranks);
+    if (FUSED && rank == 0 && warp == imu_warp) imu_normal_equations(*imu, xfull, *is, lane);
+    barrier();  // partial sums (and the IMU term) are in (distributed) shared memory
+    if (rank == 0 && warp == 0) {
+      finish_points(opt, sh, point_warps, st.target_q_inv, st.target_t, lane, ranks);
       int stop = 0;
       if (first) lm_iteration_zero<N>(st, sh, is, lane);
       else stop = lm_process_candidate<N>(st, sh, is, lane);
       if (!stop) stop = lm_prepare_step<N>(st, lane);
       if (lane == 0) {
-        sh.stop = stop;
-        if (!stop) {
-          for (int i = 0; i < 7; ++i) sh.x[i] = st.cand[i];
-          for (int i = 0; i < NA; ++i) xfull[i] = st.cand[i];
+        for (int r = 0; r < ranks; ++r) {  // r = 0 is this CTA itself
+          Shared* dst = ranks > 1 ? cluster.map_shared_rank(&sh, r) : &sh;
+          dst->stop = stop;
+          if (!stop)
+            for (int i = 0; i < 7; ++i) dst->x[i] = st.cand[i];
         }
+        if (!stop)
+          for (int i = 0; i < NA; ++i) xfull[i] = st.cand[i];
       }
     }
     first = false;
-    __syncthreads();  // the next evaluation point (or the stop flag) is visible to everyone
+    barrier();  // the next evaluation point (or the stop flag) is visible to every CTA of the problem
     if (sh.stop) break;
   }
+  if (rank != 0) return;
   if (threadIdx.x == 0) {
     for (int i = 0; i < NA; ++i) pose_out[i] = st.best_x[i];
     summary->initial_cost = st.initial_cost;
@@ -790,20 +818,22 @@ __device__ __forceinline__ void solve_body(const NlsOptions& opt, const NlsProbl
   }
 }
 
-__global__ void __launch_bounds__(kBlock) nls_solve_kernel(NlsOptions opt, const NlsProblem* __restrict__ problems,
+__global__ void __launch_bounds__(kBlock, 2) nls_solve_kernel(NlsOptions opt, const NlsProblem* __restrict__ problems,
                                                            NlsOutput* __restrict__ outputs) {
-  NlsOutput& o = outputs[blockIdx.x];
-  if (problems[blockIdx.x].enabled_dev && *problems[blockIdx.x].enabled_dev == 0) return;  // block-uniform
-  solve_body<false>(opt, problems[blockIdx.x], nullptr, nullptr, o.pose, &o.summary);
+  const int p = blockIdx.x / (opt.cluster > 1 ? opt.cluster : 1);
+  NlsOutput& o = outputs[p];
+  if (problems[p].enabled_dev && *problems[p].enabled_dev == 0) return;  // uniform over the problem's CTA(s)
+  solve_body<false>(opt, problems[p], nullptr, nullptr, o.pose, &o.summary);
 }
 
-__global__ void __launch_bounds__(kBlock) nls_fused_kernel(NlsOptions opt, const NlsProblem* __restrict__ problems,
+__global__ void __launch_bounds__(kBlock, 2) nls_fused_kernel(NlsOptions opt, const NlsProblem* __restrict__ problems,
                                                            const ImuTerm* __restrict__ imu,
                                                            const double* __restrict__ initial16,
                                                            FusedOutput* __restrict__ outputs) {
-  FusedOutput& o = outputs[blockIdx.x];
-  if (problems[blockIdx.x].enabled_dev && *problems[blockIdx.x].enabled_dev == 0) return;  // block-uniform
-  solve_body<true>(opt, problems[blockIdx.x], imu + blockIdx.x, initial16 + 16 * blockIdx.x, o.state, &o.summary);
+  const int p = blockIdx.x / (opt.cluster > 1 ? opt.cluster : 1);
+  FusedOutput& o = outputs[p];
+  if (problems[p].enabled_dev && *problems[p].enabled_dev == 0) return;  // uniform over the problem's CTA(s)
+  solve_body<true>(opt, problems[p], imu + p, initial16 + 16 * p, o.state, &o.summary);
 }
 
 // One evaluation pass at a given pose; writes the 28 reduced doubles (cost, g, H upper triangle).
@@ -859,9 +889,28 @@ static int nls_block_threads() {
   return threads;
 }
 
+// One CTA per problem, or opt.cluster CTAs (a thread-block cluster) per problem. The kernels find their problem as
+// blockIdx.x / cluster size.
+template <typename Kernel, typename... Args>
+static cudaError_t launch_solve(Kernel kernel, const NlsOptions& opt, int count, cudaStream_t stream, Args... args) {
+  const int cs = opt.cluster > 1 ? opt.cluster : 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(count * cs));
+  cfg.blockDim = dim3((unsigned)(cs > 1 ? kBlock : nls_block_threads()));
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cs > 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 int launch_nls(dl_context* ctx, const NlsOptions& opt, const NlsProblem* problems_dev, int count, NlsOutput* out_dev) {
   if (count <= 0) return DL_OK;
-  nls_solve_kernel<<<count, nls_block_threads(), 0, ctx->stream>>>(opt, problems_dev, out_dev);
+  DL_CUDA(ctx, launch_solve(nls_solve_kernel, opt, count, ctx->stream, opt, problems_dev, out_dev));
   DL_LAUNCH_CHECK(ctx, "nls_solve_kernel");
   return DL_OK;
 }
@@ -869,7 +918,7 @@ int launch_nls(dl_context* ctx, const NlsOptions& opt, const NlsProblem* problem
 int launch_nls_fused(dl_context* ctx, const NlsOptions& opt, const NlsProblem* problems_dev, const ImuTerm* imu_terms_dev,
                      const double* initial16_dev, int count, FusedOutput* out_dev) {
   if (count <= 0) return DL_OK;
-  nls_fused_kernel<<<count, nls_block_threads(), 0, ctx->stream>>>(opt, problems_dev, imu_terms_dev, initial16_dev, out_dev);
+  DL_CUDA(ctx, launch_solve(nls_fused_kernel, opt, count, ctx->stream, opt, problems_dev, imu_terms_dev, initial16_dev, out_dev));
   DL_LAUNCH_CHECK(ctx, "nls_fused_kernel");
   return DL_OK;
 }

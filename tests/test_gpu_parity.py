@@ -411,6 +411,40 @@ def test_frontend_batch_matches_oracle(ctx, orc, use_rtcsm):
         assert dt < 0.2 and dr < 0.02, (s, dt, dr)
 
 
+def test_full_cloud_solve_on_a_cluster(ctx, orc, monkeypatch):
+    """SURVEY 8d's mode F: adaptive filters opened up, the matcher sees every point of the second voxel filter (thousands per
+    solve). The batched front end then spreads each problem over a thread-block cluster (partial normal equations through
+    distributed shared memory): same result as one CTA per problem and as the oracle, same iteration counts."""
+    import dliom
+    w = workload()
+    opts = orc.FrontEndOptions.defaults()
+    opts.hi_min_num_points = 1e9
+    opts.lo_min_num_points = 1e9
+    fo = dliom.FrontendOptions.from_oracle(opts)
+    hi, lo = dev_grid(ctx, w["hi"]), dev_grid(ctx, w["lo"])
+    args = (fo, w["scans"], w["origin"], w["prev"], w["cur"], w["submap_pose"], hi, lo)
+    runs = {}
+    for cs in ("1", "2", "8", None):        # None: the library picks (4 problems -> 8 CTAs each)
+        if cs is None:
+            monkeypatch.delenv("DLIOM_NLS_CLUSTER", raising=False)
+        else:
+            monkeypatch.setenv("DLIOM_NLS_CLUSTER", cs)
+        runs[cs] = ctx.frontend_match_batch(*args)
+    for s, one in enumerate(runs["1"]):
+        assert one.ok == 1 and one.num_high_resolution + one.num_low_resolution > 3000
+        for cs in ("2", "8", None):
+            r = runs[cs][s]
+            dt, dr = pose_error(np.array(r.pose_estimate_local), np.array(one.pose_estimate_local))
+            assert r.ok == 1 and dt < 1e-9 and dr < 1e-10, (cs, s, dt, dr)
+            assert r.summary.num_iterations == one.summary.num_iterations
+            assert abs(r.summary.final_cost - one.summary.final_cost) <= 1e-9 * abs(one.summary.final_cost)
+        ing = orc.ingest_scan(opts, w["scans"][s], w["origin"], w["prev"][s], w["cur"][s])
+        want = orc.match_scan(opts, ing["returns_tracking"], ing["current_pose"].astype(np.float64), w["submap_pose"], w["hi"], w["lo"])
+        assert (one.num_high_resolution, one.num_low_resolution) == (len(want["hi_keep"]), len(want["lo_keep"]))
+        dt, dr = pose_error(np.array(runs[None][s].pose_estimate_local), want["pose_estimate_local"])
+        assert dt < 1e-7 and dr < 1e-8, (s, dt, dr)
+
+
 # ---------------------------------------------------------------- BASELINE.json configs[2] and configs[3] as parity cases
 def test_config2_128_beam_fine_grid_correlative_then_ceres(ctx, orc):
     """configs[2]: 128-beam (~260k points) scan, 0.05 m HybridGrid, correlative + Ceres refine — the whole front end
