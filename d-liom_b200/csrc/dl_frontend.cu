@@ -1,8 +1,10 @@
-// Fused scan front half for the batched front end: 4 launches per sub-batch instead of the 11 of the stage-wise path
+// Fused scan front half for the batched front end: 4 launches per sub-batch (5 with per-run deskew poses) instead of the 11 of the stage-wise path
 // (dl_voxel.cu + dl_ingest.cu, which stay as the standalone filter API and as a cross-check in the tests).
 //
 //   A  fe_first_filter_insert   first voxel filter (LTB:393-395): every point proposes its index for its voxel
 //                               (atomicCAS claim + atomicMin), one 128-bit load per point.
+//   B0 fe_run_poses             12-byte rows with the point times as runs: the deskew pose (fp64 slerp + composition, LTB:430-445) once
+//                               per RUN instead of once per survivor; kernel B then loads the finished Rigid3f.
 //   B  fe_ingest_second_insert  for each first-filter survivor: deskew + transform + range gate (LTB:426-472) and
 //                               immediately the SECOND voxel filter's insert (LTB:479-484) keyed on the local-frame
 //                               voxel — no compaction in between: ids stay the original input indices, which
@@ -74,8 +76,8 @@ __device__ __forceinline__ float point_time(const FrontendArgs& a, int b, const 
   return a.run_value[run_index(a, b, i)];
 }
 
-// 12-byte rows: the run index of every row, written once per batch (one warp per run, contiguous stores), so that the
-// latency-bound ingest kernel pays one 4-byte load per survivor instead of an 11-step search of the run table.
+// 12-byte rows, optional (DLIOM_EXPAND_RUNS=1; the default is the binary search in run_index): the run index of every row, written
+// once per batch (one warp per run, contiguous stores), one 4-byte load per survivor instead of an 11-step search of the run table.
 __global__ void __launch_bounds__(kBlock) fe_expand_runs(FrontendArgs a, int32_t* __restrict__ run_of_row) {
   const int b = blockIdx.y;
   const int r0 = a.run_offsets[b], r1 = a.run_offsets[b + 1];
