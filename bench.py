@@ -31,7 +31,11 @@ import sys
 import threading
 import time
 
-# NCCL prints its version banner (NCCL_DEBUG=VERSION/WARN) to stdout by default; stdout carries the ONE JSON line only.
+# stdout carries the ONE JSON line only. NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION (the pool's boxes set
+# it) and honours NCCL_DEBUG_FILE only above that level: raise VERSION to WARN (same banner, nothing else unless something is
+# wrong) and point the log at stderr. Any other level the caller chose (INFO to see the transports, ...) is left alone.
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np
